@@ -1,0 +1,137 @@
+/* nsb200.h -- C ABI of the B200-native streaming ASR engine (libnsb200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of m1el/nemotron-speech.cpp:
+ *   16 kHz s16le PCM -> log-mel -> dw-striding subsampling -> N cache-aware FastConformer
+ *   layers -> RNN-T (LSTM prediction net + joint) greedy decode, for many independent streams.
+ *
+ * Plain C, opaque handles, int status (0 = ok, <0 = error; text via nsb_last_error()).
+ * No torch / ggml / C++ types cross this boundary. Every entry point cites the reference
+ * interface it replaces (paths relative to the reference repo).
+ *
+ * There is NO CPU fallback: every call that computes runs hand-written sm_100a kernels and
+ * fails with NSB_ERR_CUDA when no CUDA device is usable.
+ */
+#ifndef NSB200_H
+#define NSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSB_OK 0
+#define NSB_ERR_ARG (-1)
+#define NSB_ERR_IO (-2)
+#define NSB_ERR_FORMAT (-3)
+#define NSB_ERR_CUDA (-4)
+#define NSB_ERR_STATE (-5)
+#define NSB_ERR_NOMEM (-6)
+
+/* arithmetic the per-layer weight GEMMs run in (what ggml picks from the tensor type,
+ * src/nemo-ggml.cpp:187-191 "quantized tensors stay quantized, ggml_mul_mat handles dequant") */
+enum nsb_compute {
+    NSB_COMPUTE_AUTO = 0, /* from the GGUF tensor type: F32 -> F32, F16 -> F16, Q8_0 -> Q8_0 fused dequant */
+    NSB_COMPUTE_F32 = 1,  /* SIMT fp32 GEMM (strict parity with the f32 reference path)                   */
+    NSB_COMPUTE_F16 = 2,  /* tcgen05 kind::f16, fp16 operands, fp32 TMEM accumulate                       */
+    NSB_COMPUTE_BF16 = 3, /* tcgen05 kind::f16, bf16 operands, fp32 TMEM accumulate                       */
+    NSB_COMPUTE_Q8_0 = 4  /* Q8_0 weights resident in HBM, dequantised to fp16 in the operand producer    */
+};
+enum nsb_kv_dtype { NSB_KV_F32 = 0, NSB_KV_F16 = 1, NSB_KV_BF16 = 2 };
+
+typedef struct nsb_engine nsb_engine;
+
+typedef struct nsb_engine_config {
+    int32_t device;            /* CUDA ordinal                                                         */
+    int32_t compute;           /* enum nsb_compute                                                     */
+    int32_t kv_dtype;          /* enum nsb_kv_dtype: storage of the per-stream K/V ring                */
+    int32_t att_right_context; /* R in {0,1,6,13}: nemo_cache_config::att_right_context (nemo-stream.h:26) */
+    int32_t max_streams;       /* stream slots resident on this GPU                                    */
+    int32_t use_cuda_graph;    /* capture the per-step launch sequence per batch size                  */
+    int32_t reserved[6];
+} nsb_engine_config;
+
+typedef struct nsb_stats {
+    int64_t steps;             /* engine steps run                                                     */
+    int64_t chunks;            /* stream-chunks processed (sum over streams)                           */
+    int64_t kernel_launches;   /* kernels of this library launched                                     */
+    double device_ms;          /* CUDA-event time of all steps                                         */
+    double last_step_ms;
+} nsb_stats;
+
+/* ---- GGUF metadata without touching the GPU: what nemo_model_load reads before the tensor data
+ *      (src/nemo-ggml.cpp:99-146: nemo.* hparams and tokenizer.vocab) ------------------------ */
+typedef struct nsb_model_info {
+    int32_t n_mels, d_model, n_heads, d_head, d_ff, n_layers, kernel_size, vocab_size, decoder_dim, joint_dim;
+    int32_t n_tensors;
+    int32_t weight_type;      /* ggml type of the per-layer matrices: 0 F32, 1 F16, 8 Q8_0 */
+    char vocab[1025 * 8];     /* char8 pieces, NUL padded (bounded copy + zero fill)        */
+} nsb_model_info;
+int nsb_gguf_probe(const char* gguf_path, nsb_model_info* info);
+
+/* ---- engine lifetime: replaces nemo_init_with_backend / nemo_model_load / nemo_free
+ *      (src/nemo-ggml.h:231-242, src/nemo-ggml.cpp:83-463) --------------------------------- */
+void nsb_default_config(nsb_engine_config* cfg);
+int nsb_engine_create(const char* gguf_path, const nsb_engine_config* cfg, nsb_engine** out);
+void nsb_engine_destroy(nsb_engine* e);
+const char* nsb_last_error(void);
+
+/* model facts (src/nemo-ggml.h:37-49 nemo_hparams; :157-160 char8 vocab) */
+int nsb_engine_n_layers(const nsb_engine* e);
+int nsb_engine_vocab_size(const nsb_engine* e);
+const char* nsb_engine_vocab(const nsb_engine* e); /* vocab_size * 8 bytes, NUL padded */
+int nsb_engine_chunk_samples(const nsb_engine* e); /* nemo_cache_config::get_chunk_samples (nemo-stream.h:85-87) */
+int nsb_engine_shift_samples(const nsb_engine* e); /* 160 * get_shift_mel_frames (nemo-stream.h:76-81)          */
+int nsb_engine_compute(const nsb_engine* e);       /* resolved enum nsb_compute                                  */
+
+/* ---- streams: replaces nemo_stream_init / reset / free (src/nemo-stream.h:262-312) ------- */
+int nsb_stream_open(nsb_engine* e);                /* returns stream id >= 0, or <0 */
+int nsb_stream_close(nsb_engine* e, int stream);
+int nsb_stream_reset(nsb_engine* e, int stream);   /* re-zeroes caches too (the reference's reset does not) */
+
+/* ---- the hot call: replaces nemo_stream_process_incremental (src/nemo-stream.cpp:1074-1134)
+ *      split into push (buffer PCM, any length) / step (one batched chunk for every stream that
+ *      has a full chunk buffered) / pop (token ids decoded so far). ------------------------- */
+int nsb_stream_push_pcm(nsb_engine* e, int stream, const int16_t* pcm, int n_samples);
+int nsb_stream_ready(const nsb_engine* e, int stream); /* 1 if a full chunk is buffered */
+int nsb_engine_step(nsb_engine* e);                    /* returns #streams advanced (0 = nothing ready), <0 error */
+int nsb_engine_drain(nsb_engine* e);                   /* step until nothing is ready; returns total stream-chunks */
+int nsb_stream_pop_tokens(nsb_engine* e, int stream, int32_t* out, int cap); /* returns n copied (FIFO) */
+int nsb_stream_chunks(const nsb_engine* e, int stream);                      /* nemo_stream_context::total_chunks_processed */
+
+/* tokens_to_text (src/nemo-ggml.cpp:1432-1458, no timestamps). Returns bytes written (excl. NUL) or -needed */
+int nsb_detokenize(const nsb_engine* e, const int32_t* tokens, int n, char* out, int cap);
+
+void nsb_engine_get_stats(const nsb_engine* e, nsb_stats* out);
+
+/* ---- benchmarking hooks (device-resident inputs; no PCIe inside the timed region) --------
+ * nsb_bench_prepare: open `n_streams` streams, warm their caches by running `warm_chunks` chunks
+ * of synthetic audio, and stage one more chunk of PCM per stream in HBM.
+ * nsb_bench_step: run ONE batched step over all those streams from the staged PCM (state
+ * advances; tokens are produced and discarded). Returns device ms of the step via *ms. */
+int nsb_bench_prepare(nsb_engine* e, int n_streams, const int16_t* pcm, int samples_per_stream, int warm_chunks);
+int nsb_bench_step(nsb_engine* e, float* ms);
+
+/* ---- parity / debug taps (host buffers) --------------------------------------------------
+ * When enabled, the engine keeps the tensors of the LAST step: names
+ *   "mel" [B, M, 128]  "sub" [B*T, 1024]  "layer.<l>" [B*T, 1024]  "enc" [B*T, 1024]
+ * and, for decode, every joint evaluation's logits of batch row 0 ("logits", up to cap evals).
+ * Rows are ordered by the step's batch order = ascending stream id. */
+int nsb_debug_enable(nsb_engine* e, int on);
+int nsb_debug_get(nsb_engine* e, const char* name, float* out, size_t cap_floats); /* returns #floats or <0 */
+int nsb_debug_get_cache(nsb_engine* e, int stream, int which /*0=k,1=v,2=conv*/, int layer, float* out, size_t cap);
+
+/* ---- stand-alone operators (unit parity against the oracle; host in / host out) ----------
+ * nsb_op_logmel: nemo_preprocessor_process (src/preprocessor.cpp:330-395) for a batch of
+ *   independent streams starting at stream start: pcm [n_streams, n_samples] -> mel
+ *   [n_streams, n_frames, 128]; returns n_frames = (256 + n_samples - 512)/160 + 1.
+ * nsb_op_gemm: y[rows, n_out] = x[rows, n_in] * W^T for a named per-layer weight, in the
+ *   engine's compute arithmetic (ggml_mul_mat, e.g. src/nemo-stream.cpp:571-573). */
+int nsb_op_logmel(nsb_engine* e, const int16_t* pcm, int n_streams, int n_samples, float* mel_out, size_t cap_floats);
+int nsb_op_gemm(nsb_engine* e, const char* weight_name, const float* x, int rows, float* y, size_t cap_floats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSB200_H */

@@ -1,0 +1,232 @@
+"""Python face of libnsb200.so -- the B200-native streaming ASR engine (C ABI: include/nsb200.h).
+
+ctypes only: the library is plain C ABI + CUDA runtime; torch is not involved in the data path.
+Importing this module never falls back to anything: if the shared library is missing it raises,
+and every compute call raises NsbError when no sm_100 GPU is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_DIR, "libnsb200.so")
+
+COMPUTE_AUTO, COMPUTE_F32, COMPUTE_F16, COMPUTE_BF16, COMPUTE_Q8_0 = 0, 1, 2, 3, 4
+KV_F32, KV_F16, KV_BF16 = 0, 1, 2
+
+
+class NsbError(RuntimeError):
+    pass
+
+
+class EngineConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("compute", C.c_int32), ("kv_dtype", C.c_int32), ("att_right_context", C.c_int32),
+                ("max_streams", C.c_int32), ("use_cuda_graph", C.c_int32), ("reserved", C.c_int32 * 6)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("steps", C.c_int64), ("chunks", C.c_int64), ("kernel_launches", C.c_int64), ("device_ms", C.c_double),
+                ("last_step_ms", C.c_double)]
+
+
+class ModelInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_mels", "d_model", "n_heads", "d_head", "d_ff", "n_layers", "kernel_size", "vocab_size",
+                                         "decoder_dim", "joint_dim", "n_tensors", "weight_type")] + [("vocab", C.c_char * (1025 * 8))]
+
+
+EXPORTS = ["nsb_gguf_probe", "nsb_default_config", "nsb_engine_create", "nsb_engine_destroy", "nsb_last_error", "nsb_engine_n_layers",
+           "nsb_engine_vocab_size", "nsb_engine_vocab", "nsb_engine_chunk_samples", "nsb_engine_shift_samples", "nsb_engine_compute",
+           "nsb_stream_open", "nsb_stream_close", "nsb_stream_reset", "nsb_stream_push_pcm", "nsb_stream_ready", "nsb_engine_step",
+           "nsb_engine_drain", "nsb_stream_pop_tokens", "nsb_stream_chunks", "nsb_detokenize", "nsb_engine_get_stats",
+           "nsb_bench_prepare", "nsb_bench_step", "nsb_debug_enable", "nsb_debug_get", "nsb_debug_get_cache", "nsb_op_logmel",
+           "nsb_op_gemm"]
+
+
+def build(force: bool = False) -> str:
+    """Compile libnsb200.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.check_call(["make", "-C", _DIR, "-j8", "all"], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_i16p = np.ctypeslib.ndpointer(dtype=np.int16, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NsbError(f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no fallback path)")
+        L = C.CDLL(LIB_PATH)
+        vp, ci = C.c_void_p, C.c_int
+        L.nsb_last_error.restype = C.c_char_p
+        L.nsb_gguf_probe.argtypes = [C.c_char_p, C.POINTER(ModelInfo)]
+        L.nsb_default_config.argtypes = [C.POINTER(EngineConfig)]
+        L.nsb_engine_create.argtypes = [C.c_char_p, C.POINTER(EngineConfig), C.POINTER(vp)]
+        L.nsb_engine_destroy.argtypes = [vp]
+        for n in ("nsb_engine_n_layers", "nsb_engine_vocab_size", "nsb_engine_chunk_samples", "nsb_engine_shift_samples",
+                  "nsb_engine_compute", "nsb_stream_open", "nsb_engine_step", "nsb_engine_drain"):
+            getattr(L, n).argtypes = [vp]
+        L.nsb_engine_vocab.argtypes = [vp]
+        L.nsb_engine_vocab.restype = vp
+        for n in ("nsb_stream_close", "nsb_stream_reset", "nsb_stream_ready", "nsb_stream_chunks"):
+            getattr(L, n).argtypes = [vp, ci]
+        L.nsb_stream_push_pcm.argtypes = [vp, ci, _i16p, ci]
+        L.nsb_stream_pop_tokens.argtypes = [vp, ci, _i32p, ci]
+        L.nsb_detokenize.argtypes = [vp, _i32p, ci, C.c_char_p, ci]
+        L.nsb_engine_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.nsb_bench_prepare.argtypes = [vp, ci, _i16p, ci, ci]
+        L.nsb_bench_step.argtypes = [vp, C.POINTER(C.c_float)]
+        L.nsb_debug_enable.argtypes = [vp, ci]
+        L.nsb_debug_get.argtypes = [vp, C.c_char_p, _f32p, C.c_size_t]
+        L.nsb_debug_get_cache.argtypes = [vp, ci, ci, ci, _f32p, C.c_size_t]
+        L.nsb_op_logmel.argtypes = [vp, _i16p, ci, ci, _f32p, C.c_size_t]
+        L.nsb_op_gemm.argtypes = [vp, C.c_char_p, _f32p, ci, _f32p, C.c_size_t]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int) -> int:
+    if rc < 0:
+        raise NsbError(f"nsb error {rc}: {lib().nsb_last_error().decode(errors='replace')}")
+    return rc
+
+
+def probe(path: str) -> ModelInfo:
+    info = ModelInfo()
+    _check(lib().nsb_gguf_probe(path.encode(), C.byref(info)))
+    return info
+
+
+class Engine:
+    """One engine per GPU: weights + per-stream caches resident in HBM; streams are slots."""
+
+    def __init__(self, gguf_path: str, right_context: int = 0, max_streams: int = 1, compute: int = COMPUTE_AUTO,
+                 kv_dtype: int = KV_F32, device: int = 0):
+        cfg = EngineConfig()
+        lib().nsb_default_config(C.byref(cfg))
+        cfg.device, cfg.compute, cfg.kv_dtype = device, compute, kv_dtype
+        cfg.att_right_context, cfg.max_streams = right_context, max_streams
+        h = C.c_void_p()
+        _check(lib().nsb_engine_create(gguf_path.encode(), C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.T = 1 + right_context
+        self.max_streams = max_streams
+        self.n_layers = lib().nsb_engine_n_layers(h)
+        self.chunk_samples = lib().nsb_engine_chunk_samples(h)
+        self.shift_samples = lib().nsb_engine_shift_samples(h)
+        self.compute = lib().nsb_engine_compute(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().nsb_engine_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    # ---- streams ----
+    def open_stream(self) -> int:
+        return _check(lib().nsb_stream_open(self.h))
+
+    def close_stream(self, s: int):
+        _check(lib().nsb_stream_close(self.h, s))
+
+    def reset_stream(self, s: int):
+        _check(lib().nsb_stream_reset(self.h, s))
+
+    def push(self, s: int, pcm: np.ndarray):
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        if len(pcm):
+            _check(lib().nsb_stream_push_pcm(self.h, s, pcm, len(pcm)))
+
+    def ready(self, s: int) -> bool:
+        return _check(lib().nsb_stream_ready(self.h, s)) == 1
+
+    def step(self) -> int:
+        return _check(lib().nsb_engine_step(self.h))
+
+    def drain(self) -> int:
+        return _check(lib().nsb_engine_drain(self.h))
+
+    def pop_tokens(self, s: int) -> np.ndarray:
+        out, buf = [], np.empty(1024, dtype=np.int32)
+        while True:
+            n = _check(lib().nsb_stream_pop_tokens(self.h, s, buf, len(buf)))
+            if n == 0:
+                break
+            out.append(buf[:n].copy())
+        return np.concatenate(out) if out else np.empty(0, dtype=np.int32)
+
+    def chunks(self, s: int) -> int:
+        return _check(lib().nsb_stream_chunks(self.h, s))
+
+    def detok(self, toks) -> str:
+        t = np.ascontiguousarray(toks, dtype=np.int32)
+        buf = C.create_string_buffer(16 * max(1, len(t)) + 16)
+        n = _check(lib().nsb_detokenize(self.h, t, len(t), buf, len(buf)))
+        return buf.raw[:n].decode("utf-8")
+
+    def stats(self) -> Stats:
+        s = Stats()
+        lib().nsb_engine_get_stats(self.h, C.byref(s))
+        return s
+
+    # ---- bench ----
+    def bench_prepare(self, pcm: np.ndarray, warm_chunks: int):
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        assert pcm.ndim == 2
+        _check(lib().nsb_bench_prepare(self.h, pcm.shape[0], pcm.reshape(-1), pcm.shape[1], warm_chunks))
+
+    def bench_step(self) -> float:
+        ms = C.c_float()
+        _check(lib().nsb_bench_step(self.h, C.byref(ms)))
+        return ms.value
+
+    # ---- debug / operators ----
+    def debug_enable(self, on: bool = True):
+        _check(lib().nsb_debug_enable(self.h, 1 if on else 0))
+
+    def debug_get(self, name: str, B: int) -> np.ndarray:
+        rows = self.max_streams * self.T
+        if name == "mel":
+            M = 9 + 8 * self.T
+            buf = np.empty(self.max_streams * M * 128, dtype=np.float32)
+            _check(lib().nsb_debug_get(self.h, name.encode(), buf, buf.size))
+            return buf.reshape(self.max_streams, M, 128)[:B].copy()
+        if name == "logits":
+            buf = np.empty((11 * self.T) * 1025, dtype=np.float32)
+            n = _check(lib().nsb_debug_get(self.h, name.encode(), buf, buf.size))
+            return buf[:n].reshape(-1, 1025).copy()
+        buf = np.empty(rows * 1024, dtype=np.float32)
+        _check(lib().nsb_debug_get(self.h, name.encode(), buf, buf.size))
+        return buf.reshape(rows, 1024)[: B * self.T].copy()
+
+    def debug_cache(self, stream: int, which: int, layer: int) -> np.ndarray:
+        rows = 70 if which < 2 else 8
+        buf = np.empty(rows * 1024, dtype=np.float32)
+        _check(lib().nsb_debug_get_cache(self.h, stream, which, layer, buf, buf.size))
+        return buf.reshape(rows, 1024)
+
+    def op_logmel(self, pcm: np.ndarray) -> np.ndarray:
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        if pcm.ndim == 1:
+            pcm = pcm[None]
+        ns, n = pcm.shape
+        nf = (256 + n - 512 + 160) // 160 if 256 + n >= 512 else 0
+        out = np.empty((ns, max(nf, 1), 128), dtype=np.float32)
+        got = _check(lib().nsb_op_logmel(self.h, pcm.reshape(-1), ns, n, out.reshape(-1), out.size))
+        assert got == nf, (got, nf)
+        return out[:, :nf]
+
+    def op_gemm(self, weight_name: str, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        y = np.empty((x.shape[0], 4096), dtype=np.float32)
+        n_out = _check(lib().nsb_op_gemm(self.h, weight_name.encode(), x, x.shape[0], y.reshape(-1), y.size))
+        return y.reshape(-1)[: x.shape[0] * n_out].reshape(x.shape[0], n_out).copy()

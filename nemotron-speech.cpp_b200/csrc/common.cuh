@@ -1,0 +1,96 @@
+// common.cuh -- shared declarations for the sm_100a engine (internal; the public face is include/nsb200.h)
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+namespace nsb {
+
+// ------------------------------------------------------------------------------------------
+// model constants (nemotron-speech-streaming-en-0.6b; reference src/nemo-ggml.h:37-49, :129-133)
+// ------------------------------------------------------------------------------------------
+constexpr int D_MODEL = 1024, D_FF = 4096, N_HEADS = 8, D_HEAD = 128;
+constexpr int N_MELS = 128, N_FFT = 512, N_BINS = 257, HOP = 160, WIN = 400;
+constexpr int ATT_L = 70;            // att_left_context  (nemo-stream.h:25)
+constexpr int CONV_K = 9;            // conv_kernel_size  (nemo-stream.h:30)
+constexpr int PRE_CACHE = 9;         // pre_encode_cache_size (nemo-stream.h:57)
+constexpr int DROP_PRE = 2;          // drop_extra_pre_encoded (nemo-stream.h:55)
+constexpr int SUB_CH = 256, SUB_W = 17;
+constexpr int HID = 640, JOINT = 640, VOCAB = 1025, BLANK = 1024;
+constexpr int MAX_SYMBOLS = 10;      // nemo-stream.cpp:797
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define NSB_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            throw ::nsb::CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                                   std::to_string(__LINE__) + ")");                                 \
+    } while (0)
+
+// Epilogues shared by the SIMT and the tcgen05 GEMM
+enum Epi : int {
+    EPI_NONE = 0,      // C = acc (+bias)
+    EPI_RELU = 1,      // C = relu(acc + bias)
+    EPI_SILU = 2,      // C = silu(acc)
+    EPI_RESID = 3      // C (f32, in place) += alpha * acc
+};
+enum OutType : int { OUT_F32 = 0, OUT_F16 = 1, OUT_BF16 = 2 };
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_exact(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float sigmoid_exact(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// store one value as OutType ot at element index i of a raw pointer
+__device__ __forceinline__ void store_out(void* p, size_t i, float v, int ot) {
+    if (ot == OUT_F32) ((float*)p)[i] = v;
+    else if (ot == OUT_F16) ((__half*)p)[i] = __float2half_rn(v);
+    else ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(v);
+}
+__device__ __forceinline__ float load_kv(const void* p, size_t i, int kv) {
+    if (kv == 0) return ((const float*)p)[i];
+    if (kv == 1) return __half2float(((const __half*)p)[i]);
+    return __bfloat162float(((const __nv_bfloat16*)p)[i]);
+}
+__device__ __forceinline__ float round_kv(float v, int kv) {
+    if (kv == 0) return v;
+    if (kv == 1) return __half2float(__float2half_rn(v));
+    return __bfloat162float(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ void store_kv(void* p, size_t i, float v, int kv) {
+    if (kv == 0) ((float*)p)[i] = v;
+    else if (kv == 1) ((__half*)p)[i] = __float2half_rn(v);
+    else ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(v);
+}
+inline size_t kv_elem_size(int kv) { return kv == 0 ? 4 : 2; }
+inline size_t out_elem_size(int ot) { return ot == OUT_F32 ? 4 : 2; }
+
+}  // namespace nsb

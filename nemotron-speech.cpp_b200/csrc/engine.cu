@@ -1,0 +1,623 @@
+// engine.cu -- host orchestration of the B200 streaming engine: weight residency, per-stream state in HBM,
+// PCM staging, the batched per-chunk launch sequence, token hand-back.
+//
+// Replaces (reference, relative to its repo root):
+//   nemo_model_load / nemo_init_with_backend             src/nemo-ggml.cpp:83-433
+//   nemo_stream_context::init / nemo_encoder_graph::init src/nemo-stream.cpp:36-79, :257-302
+//   nemo_stream_process_incremental + process_mel_chunk_streaming   src/nemo-stream.cpp:961-1134
+// with one difference in shape: the reference handles ONE stream per context; this engine advances every
+// stream that has a full chunk buffered in ONE batched step (B streams x T frames = B*T token rows per GEMM).
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace nsb {
+
+// implemented in gemm_tc.cu (tcgen05 / TMEM / TMA)
+void launch_gemm_tc(const GemmArgs& a, int in_type /*OUT_F16 | OUT_BF16*/, cudaStream_t st);
+
+namespace {
+
+__global__ void convert_kernel(const float* __restrict__ in, void* __restrict__ out, size_t n, int out_type) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        store_out(out, i, in[i], out_type);
+}
+void convert_to(const float* d_in, void* d_out, size_t n, int out_type, cudaStream_t st) {
+    if (!n) return;
+    int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+    convert_kernel<<<blocks, 256, 0, st>>>(d_in, d_out, n, out_type);
+}
+
+std::vector<float> read_matrix_f32(const GgufFile& g, const std::string& name) {
+    const GgufTensor& t = g.require(name);
+    std::vector<uint8_t> raw = g.read(t);
+    std::vector<float> out((size_t)t.n_elements());
+    if (t.type == GGML_F32) memcpy(out.data(), raw.data(), raw.size());
+    else if (t.type == GGML_F16) { for (size_t i = 0; i < out.size(); ++i) { uint16_t h; memcpy(&h, &raw[2 * i], 2); out[i] = half_bits_to_float(h); } }
+    else if (t.type == GGML_Q8_0) {                       // block = fp16 d + 32 x int8 along ne0 (convert_to_gguf.py:93-129)
+        const size_t nb = out.size() / 32;
+        for (size_t b = 0; b < nb; ++b) {
+            uint16_t h; memcpy(&h, &raw[b * 34], 2); const float d = half_bits_to_float(h);
+            const int8_t* q = (const int8_t*)&raw[b * 34 + 2];
+            for (int i = 0; i < 32; ++i) out[b * 32 + i] = d * (float)q[i];
+        }
+    } else throw std::runtime_error("unsupported tensor type for " + name);
+    return out;
+}
+
+void upload(DevBuf& d, const std::vector<float>& h) {
+    d.alloc(h.size() * sizeof(float), false);
+    NSB_CUDA(cudaMemcpy(d.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+}
+
+// positional table row for relative position p (src/nemo-ggml.cpp:17-32)
+void pos_emb_row(int p_int, float* row) {
+    const float p = (float)p_int;
+    for (int i = 0; i < D_MODEL; i += 2) {
+        const float div_term = std::exp(-(float)i * std::log(10000.0f) / (float)D_MODEL);
+        row[i] = std::sin(p * div_term);
+        row[i + 1] = std::cos(p * div_term);
+    }
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+Engine::Engine(const std::string& path, const nsb_engine_config& cfg) : cfg_(cfg) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        throw CudaError("no CUDA device available (this engine has no CPU fallback)");
+    device_ = cfg.device;
+    NSB_CUDA(cudaSetDevice(device_));
+    cudaDeviceProp prop{};
+    NSB_CUDA(cudaGetDeviceProperties(&prop, device_));
+    if (prop.major != 10) throw CudaError(std::string("device '") + prop.name + "' is not sm_100 (kernels are built for sm_100a only)");
+    NSB_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+    NSB_CUDA(cudaEventCreate(&ev0_));
+    NSB_CUDA(cudaEventCreate(&ev1_));
+
+    R = cfg.att_right_context;
+    if (R < 0 || R > 64) throw std::invalid_argument("att_right_context out of range");
+    T = 1 + R;
+    max_streams = std::max(1, cfg.max_streams);
+    kv_dtype = cfg.kv_dtype;
+    if (kv_dtype < 0 || kv_dtype > 2) throw std::invalid_argument("kv_dtype");
+
+    GgufFile g;
+    g.open(path);
+    n_layers = g.u32.count("nemo.n_layers") ? (int)g.u32["nemo.n_layers"] : 24;
+    const int vs = g.u32.count("nemo.vocab_size") ? (int)g.u32["nemo.vocab_size"] : VOCAB;
+    if (vs != VOCAB) throw std::runtime_error("unsupported vocab_size (expected 1025)");
+    // vocab: bounded copy + zero fill (the reference memcpy's vocab_size*8 bytes unconditionally, nemo-ggml.cpp:137-146)
+    vocab.assign((size_t)VOCAB * 8, 0);
+    memcpy(vocab.data(), g.vocab_raw.data(), std::min(g.vocab_raw.size(), vocab.size()));
+
+    compute = cfg.compute;
+    if (compute == NSB_COMPUTE_AUTO) {
+        const int t = g.require("encoder.layers.0.feed_forward1.linear1.weight").type;
+        compute = t == GGML_F32 ? NSB_COMPUTE_F32 : t == GGML_F16 ? NSB_COMPUTE_F16 : NSB_COMPUTE_Q8_0;
+    }
+    load_weights(g);
+    alloc_state();
+    build_pos_tables(g);
+    NSB_CUDA(cudaStreamSynchronize(st_));
+}
+
+Engine::~Engine() {
+    cudaSetDevice(device_);
+    cudaDeviceSynchronize();
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+    if (st_) cudaStreamDestroy(st_);
+}
+
+void Engine::upload_weight(Weight& w, const std::string& name, const std::vector<float>& host, int n_out, int n_in) {
+    w.name = name; w.n_out = n_out; w.n_in = n_in;
+    if ((size_t)n_out * n_in != host.size()) throw std::runtime_error("shape mismatch for " + name);
+    const int at = act_type();
+    if (at == OUT_F32) { upload(w.data, host); return; }
+    DevBuf tmp; upload(tmp, host);
+    w.data.alloc(host.size() * 2, false);
+    convert_to(tmp.as<float>(), w.data.p, host.size(), at, st_);
+    NSB_CUDA(cudaStreamSynchronize(st_));
+}
+
+void Engine::load_weights(const GgufFile& g) {
+    auto vec = [&](DevBuf& d, const std::string& n, size_t expect) {
+        std::vector<float> h = g.read_f32(n);
+        if (h.size() != expect) throw std::runtime_error("unexpected size for " + n);
+        upload(d, h);
+    };
+    auto f32_weight = [&](Weight& w, const std::string& n, int n_out, int n_in, std::vector<float> h) {
+        w.name = n; w.n_out = n_out; w.n_in = n_in; upload(w.data, h);
+    };
+    // ---- front-end tables (src/preprocessor.cpp:80-110, :296-299) ----
+    {
+        std::vector<float> win = g.read_f32("preprocessor.featurizer.window"), fb = g.read_f32("preprocessor.featurizer.fb");
+        if (win.size() != WIN || fb.size() != (size_t)N_MELS * N_BINS) throw std::runtime_error("preprocessor tensor sizes");
+        std::vector<float> w512(N_FFT, 0.f), c(N_FFT), s(N_FFT), fbt((size_t)N_BINS * N_MELS);
+        memcpy(w512.data() + (N_FFT - WIN) / 2, win.data(), WIN * sizeof(float));
+        for (int i = 0; i < N_FFT; ++i) { const float th = (2.0f * (float)M_PI * i) / N_FFT; s[i] = sinf(th); c[i] = cosf(th); }
+        for (int m = 0; m < N_MELS; ++m) for (int k = 0; k < N_BINS; ++k) fbt[(size_t)k * N_MELS + m] = fb[(size_t)m * N_BINS + k];
+        upload(window_, w512); upload(cos_t_, c); upload(sin_t_, s); upload(fb_t_, fbt);
+    }
+    // ---- subsampling stem: always f32 (never quantised by the converter, convert_to_gguf.py:226) ----
+    {
+        auto conv_t = [&](DevBuf& d, const std::string& n) {           // [256][1][3][3] -> tap-major [9][256]
+            std::vector<float> w = g.read_f32(n), t((size_t)9 * SUB_CH);
+            if (w.size() != (size_t)SUB_CH * 9) throw std::runtime_error("unexpected size for " + n);
+            for (int oc = 0; oc < SUB_CH; ++oc) for (int k = 0; k < 9; ++k) t[(size_t)k * SUB_CH + oc] = w[(size_t)oc * 9 + k];
+            upload(d, t);
+        };
+        const std::string p = "encoder.pre_encode.";
+        conv_t(c0_w_, p + "conv.0.weight"); vec(c0_b_, p + "conv.0.bias", SUB_CH);
+        conv_t(c2_w_, p + "conv.2.weight"); vec(c2_b_, p + "conv.2.bias", SUB_CH);
+        conv_t(c5_w_, p + "conv.5.weight"); vec(c5_b_, p + "conv.5.bias", SUB_CH);
+        f32_weight(c3_w_, p + "conv.3.weight", SUB_CH, SUB_CH, g.read_f32(p + "conv.3.weight")); vec(c3_b_, p + "conv.3.bias", SUB_CH);
+        f32_weight(c6_w_, p + "conv.6.weight", SUB_CH, SUB_CH, g.read_f32(p + "conv.6.weight")); vec(c6_b_, p + "conv.6.bias", SUB_CH);
+        // out linear: reference flattens (c*17 + w) (nemo-ggml.cpp:937-940); our activations are NHWC so permute columns to (w*256 + c)
+        std::vector<float> w = g.read_f32(p + "out.weight"), wp(w.size());
+        if (w.size() != (size_t)D_MODEL * SUB_CH * SUB_W) throw std::runtime_error("pre_encode.out.weight size");
+        for (int n = 0; n < D_MODEL; ++n) for (int c = 0; c < SUB_CH; ++c) for (int x = 0; x < SUB_W; ++x)
+            wp[(size_t)n * SUB_CH * SUB_W + x * SUB_CH + c] = w[(size_t)n * SUB_CH * SUB_W + c * SUB_W + x];
+        f32_weight(sub_out_w_, p + "out.weight", D_MODEL, SUB_CH * SUB_W, std::move(wp));
+        vec(out_b_, p + "out.bias", D_MODEL);
+    }
+    // ---- conformer layers ----
+    layers_.resize(n_layers);
+    for (int l = 0; l < n_layers; ++l) {
+        LayerW& L = layers_[l];
+        const std::string p = "encoder.layers." + std::to_string(l) + ".";
+        const char* norms[5] = {"norm_feed_forward1", "norm_self_att", "norm_conv", "norm_feed_forward2", "norm_out"};
+        for (int i = 0; i < 5; ++i) { vec(L.ln[2 * i], p + norms[i] + ".weight", D_MODEL); vec(L.ln[2 * i + 1], p + norms[i] + ".bias", D_MODEL); }
+        upload_weight(L.ff1a, p + "feed_forward1.linear1.weight", read_matrix_f32(g, p + "feed_forward1.linear1.weight"), D_FF, D_MODEL);
+        upload_weight(L.ff1b, p + "feed_forward1.linear2.weight", read_matrix_f32(g, p + "feed_forward1.linear2.weight"), D_MODEL, D_FF);
+        upload_weight(L.ff2a, p + "feed_forward2.linear1.weight", read_matrix_f32(g, p + "feed_forward2.linear1.weight"), D_FF, D_MODEL);
+        upload_weight(L.ff2b, p + "feed_forward2.linear2.weight", read_matrix_f32(g, p + "feed_forward2.linear2.weight"), D_MODEL, D_FF);
+        {   // q | k | v stacked along the output dim -> one GEMM with N = 3072
+            std::vector<float> q = read_matrix_f32(g, p + "self_attn.linear_q.weight"), k = read_matrix_f32(g, p + "self_attn.linear_k.weight"),
+                               v = read_matrix_f32(g, p + "self_attn.linear_v.weight");
+            q.insert(q.end(), k.begin(), k.end()); q.insert(q.end(), v.begin(), v.end());
+            upload_weight(L.qkv, p + "self_attn.linear_qkv.weight", q, 3 * D_MODEL, D_MODEL);
+        }
+        upload_weight(L.out, p + "self_attn.linear_out.weight", read_matrix_f32(g, p + "self_attn.linear_out.weight"), D_MODEL, D_MODEL);
+        upload_weight(L.pw1, p + "conv.pointwise_conv1.weight", read_matrix_f32(g, p + "conv.pointwise_conv1.weight"), 2 * D_MODEL, D_MODEL);
+        upload_weight(L.pw2, p + "conv.pointwise_conv2.weight", read_matrix_f32(g, p + "conv.pointwise_conv2.weight"), D_MODEL, D_MODEL);
+        vec(L.bias_u, p + "self_attn.pos_bias_u", D_MODEL); vec(L.bias_v, p + "self_attn.pos_bias_v", D_MODEL);
+        {
+            const GgufTensor& dw = g.require(p + "conv.depthwise_conv.weight");       // ggml [1024, k]: tap-major
+            if (dw.ne.size() != 2 || dw.ne[0] != D_MODEL || dw.ne[1] != CONV_K)
+                throw std::runtime_error("depthwise conv weight must be [1024, 9] (2-D, tap-major; reconvert old 3-D files)");
+            vec(L.dw_w, p + "conv.depthwise_conv.weight", (size_t)CONV_K * D_MODEL);
+        }
+        vec(L.cln_g, p + "conv.batch_norm.weight", D_MODEL); vec(L.cln_b, p + "conv.batch_norm.bias", D_MODEL);
+        for (Weight* w : {&L.ff1a, &L.ff1b, &L.ff2a, &L.ff2b, &L.qkv, &L.out, &L.pw1, &L.pw2}) named_[w->name] = w;
+    }
+    // ---- decoder + joint: always f32 ----
+    {
+        const std::string d = "decoder.prediction.";
+        vec(embed_, d + "embed.weight", (size_t)VOCAB * HID);
+        for (int l = 0; l < 2; ++l) {
+            vec(lstm_w_[2 * l], d + "dec_rnn.lstm.weight_ih_l" + std::to_string(l), (size_t)4 * HID * HID);
+            vec(lstm_w_[2 * l + 1], d + "dec_rnn.lstm.weight_hh_l" + std::to_string(l), (size_t)4 * HID * HID);
+            vec(lstm_b_[2 * l], d + "dec_rnn.lstm.bias_ih_l" + std::to_string(l), (size_t)4 * HID);
+            vec(lstm_b_[2 * l + 1], d + "dec_rnn.lstm.bias_hh_l" + std::to_string(l), (size_t)4 * HID);
+        }
+        f32_weight(joint_enc_w_, "joint.enc.weight", JOINT, D_MODEL, g.read_f32("joint.enc.weight"));
+        vec(joint_enc_b_, "joint.enc.bias", JOINT);
+        vec(pred_w_, "joint.pred.weight", (size_t)JOINT * HID); vec(pred_b_, "joint.pred.bias", JOINT);
+        vec(jout_w_, "joint.joint_net.2.weight", (size_t)VOCAB * JOINT); vec(jout_b_, "joint.joint_net.2.bias", VOCAB);
+    }
+}
+
+void Engine::alloc_state() {
+    const int S = max_streams, Cap = ATT_L + T, M = PRE_CACHE + 8 * T;
+    const int t1 = M / 2 + 1, t2 = t1 / 2 + 1, t3 = t2 / 2 + 1;
+    if (t3 != T + DROP_PRE) throw std::runtime_error("unexpected subsampling length");
+    kv_.alloc((size_t)S * n_layers * 2 * Cap * D_MODEL * kv_elem_size(kv_dtype));       // zero-initialised (nemo-stream.cpp:292-297)
+    conv_cache_.alloc((size_t)S * n_layers * (CONV_K - 1) * D_MODEL * 4);
+    mel_hist_.alloc((size_t)S * PRE_CACHE * N_MELS * 4);                                 // 9 zero frames (:59-60)
+    ring_pos_.alloc((size_t)S * 4); valid_len_.alloc((size_t)S * 4);
+    dec_h_.alloc((size_t)S * 2 * HID * 4); dec_c_.alloc((size_t)S * 2 * HID * 4);
+    cand_h_.alloc((size_t)S * 2 * HID * 4); cand_c_.alloc((size_t)S * 2 * HID * 4);
+    dec_proj_.alloc((size_t)S * JOINT * 4);
+    prev_token_.alloc((size_t)S * 4); cand_valid_.alloc((size_t)S * 4);
+    hs_.assign(S, HostStream());
+    for (int s = 0; s < S; ++s) zero_slot(s);
+
+    rl_ = 8 * T * HOP + (N_FFT - HOP) + 1;                                                // 1280 T + 353 samples per stream-step
+    const size_t Mrows = (size_t)S * T;
+    d_pcm_.alloc((size_t)S * rl_ * 2); d_slot_.alloc((size_t)S * 4);
+    mel_new_.alloc((size_t)S * 8 * T * N_MELS * 4);
+    c0_.alloc((size_t)S * t1 * 65 * SUB_CH * 4);
+    dw_.alloc((size_t)S * t2 * 33 * SUB_CH * 4);
+    pw_.alloc((size_t)S * t2 * 33 * SUB_CH * 4);
+    x_.alloc(Mrows * D_MODEL * 4);
+    a_.alloc(Mrows * D_MODEL * act_size());
+    big_.alloc(Mrows * D_FF * act_size());
+    qkv_.alloc(Mrows * 3 * D_MODEL * 4);
+    pw1_.alloc(Mrows * 2 * D_MODEL * 4);
+    encp_.alloc(Mrows * JOINT * 4);
+    out_tok_.alloc((size_t)S * MAX_SYMBOLS * T * 4); out_cnt_.alloc((size_t)S * 4);
+    frame_idx_.alloc((size_t)S * 4); sym_cnt_.alloc((size_t)S * 4); need_lstm_.alloc((size_t)S * 4);
+    const size_t parts = decode_scratch_parts(S);
+    part_val_.alloc(parts * 4); part_idx_.alloc(parts * 4); counters_.alloc(64);
+    h_pcm_.alloc((size_t)S * rl_ * 2); h_slot_.alloc((size_t)S * 4);
+    h_tok_.alloc((size_t)S * MAX_SYMBOLS * T * 4); h_cnt_.alloc((size_t)S * 4);
+}
+
+void Engine::zero_slot(int s) {
+    const int Cap = ATT_L + T;
+    const size_t kvb = (size_t)n_layers * 2 * Cap * D_MODEL * kv_elem_size(kv_dtype);
+    NSB_CUDA(cudaMemsetAsync((char*)kv_.p + (size_t)s * kvb, 0, kvb, st_));
+    const size_t cb = (size_t)n_layers * (CONV_K - 1) * D_MODEL * 4;
+    NSB_CUDA(cudaMemsetAsync((char*)conv_cache_.p + (size_t)s * cb, 0, cb, st_));
+    NSB_CUDA(cudaMemsetAsync((char*)mel_hist_.p + (size_t)s * PRE_CACHE * N_MELS * 4, 0, (size_t)PRE_CACHE * N_MELS * 4, st_));
+    NSB_CUDA(cudaMemsetAsync((char*)dec_h_.p + (size_t)s * 2 * HID * 4, 0, (size_t)2 * HID * 4, st_));
+    NSB_CUDA(cudaMemsetAsync((char*)dec_c_.p + (size_t)s * 2 * HID * 4, 0, (size_t)2 * HID * 4, st_));
+    const int zero = 0, blank = BLANK;
+    NSB_CUDA(cudaMemcpyAsync((char*)ring_pos_.p + (size_t)s * 4, &zero, 4, cudaMemcpyHostToDevice, st_));
+    NSB_CUDA(cudaMemcpyAsync((char*)valid_len_.p + (size_t)s * 4, &zero, 4, cudaMemcpyHostToDevice, st_));
+    NSB_CUDA(cudaMemcpyAsync((char*)cand_valid_.p + (size_t)s * 4, &zero, 4, cudaMemcpyHostToDevice, st_));
+    NSB_CUDA(cudaMemcpyAsync((char*)prev_token_.p + (size_t)s * 4, &blank, 4, cudaMemcpyHostToDevice, st_));   // prev_token = blank (:41-42)
+    NSB_CUDA(cudaStreamSynchronize(st_));
+    hs_[s].buf.clear(); hs_[s].base = 0; hs_[s].n_pushed = 0; hs_[s].chunk_idx = 0; hs_[s].tokens.clear();
+}
+
+// P_l = linear_pos(pos_emb rows) for the L+2T-1 relative positions a chunk can touch, once, at load.
+// (The reference recomputes mul_mat(attn_pos_w, pos_emb) over 2K-1 rows per layer per chunk, nemo-stream.cpp:488.)
+void Engine::build_pos_tables(const GgufFile& g) {
+    const int n_rel = ATT_L + 2 * T - 1;
+    std::vector<float> tab((size_t)n_rel * D_MODEL);
+    for (int r = 0; r < n_rel; ++r) pos_emb_row(r - (T - 1), &tab[(size_t)r * D_MODEL]);
+    DevBuf d_tab; upload(d_tab, tab);
+    DevBuf d_a; const void* A = d_tab.p;
+    if (act_type() != OUT_F32) { d_a.alloc(tab.size() * 2, false); convert_to(d_tab.as<float>(), d_a.p, tab.size(), act_type(), st_); A = d_a.p; }
+    for (int l = 0; l < n_layers; ++l) {
+        const std::string n = "encoder.layers." + std::to_string(l) + ".self_attn.linear_pos.weight";
+        Weight wpos; upload_weight(wpos, n, read_matrix_f32(g, n), D_MODEL, D_MODEL);
+        layers_[l].pos_proj.alloc((size_t)n_rel * D_MODEL * 4, false);
+        gemm(A, D_MODEL, wpos, n_rel, nullptr, layers_[l].pos_proj.p, D_MODEL, EPI_NONE, 1.f, OUT_F32);
+        NSB_CUDA(cudaStreamSynchronize(st_));
+    }
+}
+
+void Engine::gemm(const void* A, long long lda, const Weight& W, int M, const float* bias, void* C, long long ldc, int epi, float alpha,
+                  int out_type) {
+    GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.M = M; a.N = W.n_out; a.K = W.n_in; a.bias = bias; a.C = C; a.ldc = ldc;
+    a.epi = epi; a.alpha = alpha; a.out_type = out_type;
+    if (compute == NSB_COMPUTE_F32) launch_gemm_simt(a, st_);
+    else launch_gemm_tc(a, act_type(), st_);
+    count_launch();
+}
+
+// ------------------------------------------------------------------------------------------
+// streams (host bookkeeping only; all arithmetic is on the device)
+// ------------------------------------------------------------------------------------------
+int Engine::open_stream() {
+    for (int s = 0; s < max_streams; ++s)
+        if (!hs_[s].open) { zero_slot(s); hs_[s].open = true; return s; }
+    throw std::runtime_error("no free stream slot (max_streams = " + std::to_string(max_streams) + ")");
+}
+void Engine::close_stream(int s) { if (s < 0 || s >= max_streams || !hs_[s].open) throw std::invalid_argument("bad stream id"); hs_[s].open = false; }
+void Engine::reset_stream(int s) { if (s < 0 || s >= max_streams || !hs_[s].open) throw std::invalid_argument("bad stream id"); zero_slot(s); }
+
+void Engine::push_pcm(int s, const int16_t* pcm, int n) {
+    if (s < 0 || s >= max_streams || !hs_[s].open) throw std::invalid_argument("bad stream id");
+    if (!pcm || n <= 0) return;                                        // reference returns "" on null/<=0 (nemo-stream.cpp:1079)
+    HostStream& h = hs_[s];
+    h.buf.insert(h.buf.end(), pcm, pcm + n);
+    h.n_pushed += n;
+}
+
+// Chunk c needs mel frames up to 8T(c+1)-1, i.e. padded samples up to 160*(8T(c+1)-1)+512, i.e. raw samples
+// n >= 160*(8T(c+1)-1) + 256  (preprocessor.cpp:320-328 frame count + nemo-stream.cpp:1094-1102 chunk gate)
+bool Engine::ready(int s) const {
+    const HostStream& h = hs_[s];
+    return h.open && h.n_pushed >= (long long)HOP * (8LL * T * (h.chunk_idx + 1) - 1) + N_FFT / 2;
+}
+
+static void stage_row(const HostStream& h, int T, int rl, int16_t* dst) {
+    // row = raw[start-1 .. start + 1280T + 352), start = 1280 T c - 256; negative indices are the 256-zero left pad / x[-1] = 0
+    const long long start = 8LL * T * HOP * h.chunk_idx - N_FFT / 2 - 1;
+    for (int i = 0; i < rl; ++i) {
+        const long long idx = start + i;
+        dst[i] = idx < 0 ? (int16_t)0 : h.buf[(size_t)(idx - h.base)];
+    }
+}
+
+int Engine::step() {
+    NSB_CUDA(cudaSetDevice(device_));
+    std::vector<int> batch;
+    for (int s = 0; s < max_streams; ++s) if (ready(s)) batch.push_back(s);
+    const int B = (int)batch.size();
+    if (!B) return 0;
+    int16_t* hp = h_pcm_.as<int16_t>(); int* hsl = h_slot_.as<int>();
+    for (int b = 0; b < B; ++b) { stage_row(hs_[batch[b]], T, rl_, hp + (size_t)b * rl_); hsl[b] = batch[b]; }
+    NSB_CUDA(cudaMemcpyAsync(d_pcm_.p, hp, (size_t)B * rl_ * 2, cudaMemcpyHostToDevice, st_));
+    NSB_CUDA(cudaMemcpyAsync(d_slot_.p, hsl, (size_t)B * 4, cudaMemcpyHostToDevice, st_));
+    NSB_CUDA(cudaEventRecord(ev0_, st_));
+    run_step_kernels(B, d_pcm_.as<int16_t>());
+    NSB_CUDA(cudaEventRecord(ev1_, st_));
+    NSB_CUDA(cudaMemcpyAsync(h_cnt_.p, out_cnt_.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st_));
+    NSB_CUDA(cudaMemcpyAsync(h_tok_.p, out_tok_.p, (size_t)B * MAX_SYMBOLS * T * 4, cudaMemcpyDeviceToHost, st_));
+    NSB_CUDA(cudaStreamSynchronize(st_));
+    float ms = 0.f; NSB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    stats.steps += 1; stats.chunks += B; stats.device_ms += ms; stats.last_step_ms = ms;
+    collect_tokens(B, batch);
+    return B;
+}
+
+void Engine::collect_tokens(int B, const std::vector<int>& batch) {
+    const int* cnt = h_cnt_.as<int>(); const int* tok = h_tok_.as<int>();
+    for (int b = 0; b < B; ++b) {
+        HostStream& h = hs_[batch[b]];
+        for (int i = 0; i < cnt[b] && i < MAX_SYMBOLS * T; ++i) h.tokens.push_back(tok[(size_t)b * MAX_SYMBOLS * T + i]);
+        h.chunk_idx += 1;
+        // drop samples no later chunk needs: next row starts at 1280 T c' - 257
+        const long long keep_from = std::max(0LL, 8LL * T * HOP * h.chunk_idx - N_FFT / 2 - 1);
+        if (keep_from > h.base) { h.buf.erase(h.buf.begin(), h.buf.begin() + (size_t)(keep_from - h.base)); h.base = keep_from; }
+    }
+}
+
+int Engine::pop_tokens(int s, int32_t* out, int cap) {
+    if (s < 0 || s >= max_streams) throw std::invalid_argument("bad stream id");
+    HostStream& h = hs_[s]; int n = 0;
+    while (n < cap && !h.tokens.empty()) { out[n++] = h.tokens.front(); h.tokens.pop_front(); }
+    return n;
+}
+int Engine::chunks(int s) const { if (s < 0 || s >= max_streams) throw std::invalid_argument("bad stream id"); return (int)hs_[s].chunk_idx; }
+
+// tokens_to_text (src/nemo-ggml.cpp:1432-1458, timestamps off): piece starting with U+2581 -> ' ' + rest
+std::string Engine::detok(const int32_t* t, int n) const {
+    std::string r;
+    for (int i = 0; i < n; ++i) {
+        const int id = t[i];
+        if (id < 0 || id >= VOCAB) continue;
+        char piece[9]; memcpy(piece, &vocab[(size_t)id * 8], 8); piece[8] = 0;
+        const std::string pc(piece);
+        if (pc.size() >= 3 && strncmp(pc.c_str(), "\xe2\x96\x81", 3) == 0) { r += ' '; r += pc.substr(3); } else r += pc;
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// THE HOT PATH: one batched chunk for B streams, PCM already in HBM, tokens left in HBM.
+// ------------------------------------------------------------------------------------------
+void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
+    const int M = PRE_CACHE + 8 * T, t1 = M / 2 + 1, t2 = t1 / 2 + 1, t3 = t2 / 2 + 1;
+    const int rows = B * T, at = act_type();
+    const int* slot = d_slot_.as<int>();
+    float* x = x_.as<float>();
+
+    // P: log-mel of the 8T new frames per stream
+    launch_logmel(d_pcm, rl_, B, 8 * T, window_.as<float>(), cos_t_.as<float>(), sin_t_.as<float>(), fb_t_.as<float>(),
+                  mel_new_.as<float>(), (size_t)8 * T * N_MELS, st_);
+    count_launch();
+    if (debug_) { launch_mel_gather(mel_hist_.as<float>(), mel_new_.as<float>(), slot, B, T, dbg_mel_.as<float>(), st_); count_launch(); }
+    // S: subsampling stem (NHWC)
+    launch_conv0(mel_hist_.as<float>(), mel_new_.as<float>(), slot, B, T, c0_w_.as<float>(), c0_b_.as<float>(), c0_.as<float>(), st_);
+    launch_mel_hist_update(mel_hist_.as<float>(), mel_new_.as<float>(), slot, B, T, st_);
+    launch_dwconv_s2(c0_.as<float>(), B, t1, 65, c2_w_.as<float>(), c2_b_.as<float>(), dw_.as<float>(), st_);
+    count_launch(3);
+    {
+        GemmArgs g; g.A = dw_.p; g.lda = SUB_CH; g.W = c3_w_.data.p; g.M = B * t2 * 33; g.N = SUB_CH; g.K = SUB_CH; g.bias = c3_b_.as<float>();
+        g.C = pw_.p; g.ldc = SUB_CH; g.epi = EPI_RELU; launch_gemm_simt(g, st_); count_launch();
+    }
+    launch_dwconv_s2(pw_.as<float>(), B, t2, 33, c5_w_.as<float>(), c5_b_.as<float>(), dw_.as<float>(), st_); count_launch();
+    {
+        GemmArgs g; g.A = dw_.p; g.lda = SUB_CH; g.W = c6_w_.data.p; g.M = B * t3 * SUB_W; g.N = SUB_CH; g.K = SUB_CH; g.bias = c6_b_.as<float>();
+        g.C = pw_.p; g.ldc = SUB_CH; g.epi = EPI_RELU; launch_gemm_simt(g, st_); count_launch();
+    }
+    {   // flatten + out linear on the T kept frames (frames 0,1 of every stream are dropped: nemo-stream.cpp:136-144)
+        GemmArgs g; g.A = pw_.p; g.lda = SUB_W * SUB_CH; g.group = T; g.group_stride = (long long)t3 * SUB_W * SUB_CH; g.row_off = DROP_PRE;
+        g.W = sub_out_w_.data.p; g.M = rows; g.N = D_MODEL; g.K = SUB_W * SUB_CH; g.bias = out_b_.as<float>();
+        g.C = x; g.ldc = D_MODEL; g.epi = EPI_NONE; launch_gemm_simt(g, st_); count_launch();
+    }
+    if (debug_) NSB_CUDA(cudaMemcpyAsync(dbg_sub_.p, x, (size_t)rows * D_MODEL * 4, cudaMemcpyDeviceToDevice, st_));
+
+    // L: cache-aware conformer layers
+    const long long kv_slot_stride = (long long)n_layers * 2 * (ATT_L + T) * D_MODEL;
+    const long long cc_slot_stride = (long long)n_layers * (CONV_K - 1) * D_MODEL;
+    launch_layernorm(x, rows, layers_[0].ln[0].as<float>(), layers_[0].ln[1].as<float>(), a_.p, at, st_); count_launch();
+    for (int l = 0; l < n_layers; ++l) {
+        LayerW& L = layers_[l];
+        // FFN1: x += 0.5 * W2 silu(W1 LN(x))                                        (nemo-stream.cpp:603-606)
+        gemm(a_.p, D_MODEL, L.ff1a, rows, nullptr, big_.p, D_FF, EPI_SILU, 1.f, at);
+        gemm(big_.p, D_FF, L.ff1b, rows, nullptr, x, D_MODEL, EPI_RESID, 0.5f, OUT_F32);
+        // MHSA over the ring cache                                                  (:609-615)
+        launch_layernorm(x, rows, L.ln[2].as<float>(), L.ln[3].as<float>(), a_.p, at, st_); count_launch();
+        gemm(a_.p, D_MODEL, L.qkv, rows, nullptr, qkv_.p, 3 * D_MODEL, EPI_NONE, 1.f, OUT_F32);
+        {
+            AttnArgs aa; aa.qkv = qkv_.as<float>();
+            const size_t es = kv_elem_size(kv_dtype);
+            aa.k_ring = (char*)kv_.p + (size_t)l * 2 * (ATT_L + T) * D_MODEL * es;
+            aa.v_ring = (char*)aa.k_ring + (size_t)(ATT_L + T) * D_MODEL * es;
+            aa.slot_stride = kv_slot_stride; aa.kv_dtype = kv_dtype; aa.pos_proj = L.pos_proj.as<float>();
+            aa.bias_u = L.bias_u.as<float>(); aa.bias_v = L.bias_v.as<float>(); aa.ctx = a_.p; aa.out_type = at;
+            aa.slot_of_b = slot; aa.ring_pos = ring_pos_.as<int>(); aa.valid_len = valid_len_.as<int>(); aa.B = B; aa.T = T;
+            launch_attention(aa, st_); count_launch();
+        }
+        gemm(a_.p, D_MODEL, L.out, rows, nullptr, x, D_MODEL, EPI_RESID, 1.f, OUT_F32);
+        // conv module                                                               (:618-651)
+        launch_layernorm(x, rows, L.ln[4].as<float>(), L.ln[5].as<float>(), a_.p, at, st_); count_launch();
+        gemm(a_.p, D_MODEL, L.pw1, rows, nullptr, pw1_.p, 2 * D_MODEL, EPI_NONE, 1.f, OUT_F32);
+        {
+            ConvModArgs ca; ca.pw1 = pw1_.as<float>(); ca.conv_cache = conv_cache_.as<float>() + (size_t)l * (CONV_K - 1) * D_MODEL;
+            ca.slot_stride = cc_slot_stride; ca.dw_w = L.dw_w.as<float>(); ca.ln_g = L.cln_g.as<float>(); ca.ln_b = L.cln_b.as<float>();
+            ca.out = a_.p; ca.out_type = at; ca.slot_of_b = slot; ca.B = B; ca.T = T;
+            launch_conv_module(ca, st_); count_launch();
+        }
+        gemm(a_.p, D_MODEL, L.pw2, rows, nullptr, x, D_MODEL, EPI_RESID, 1.f, OUT_F32);
+        // FFN2                                                                      (:654-657)
+        launch_layernorm(x, rows, L.ln[6].as<float>(), L.ln[7].as<float>(), a_.p, at, st_); count_launch();
+        gemm(a_.p, D_MODEL, L.ff2a, rows, nullptr, big_.p, D_FF, EPI_SILU, 1.f, at);
+        gemm(big_.p, D_FF, L.ff2b, rows, nullptr, x, D_MODEL, EPI_RESID, 0.5f, OUT_F32);
+        // norm_out (:659) fused with the next layer's norm_feed_forward1
+        const bool last = l + 1 == n_layers;
+        launch_layernorm2(x, rows, L.ln[8].as<float>(), L.ln[9].as<float>(), last ? nullptr : layers_[l + 1].ln[0].as<float>(),
+                          last ? nullptr : layers_[l + 1].ln[1].as<float>(), last ? nullptr : a_.p, at, st_);
+        count_launch();
+        if (debug_) NSB_CUDA(cudaMemcpyAsync(dbg_layers_.as<float>() + (size_t)l * dbg_B_ * T * D_MODEL, x, (size_t)rows * D_MODEL * 4,
+                                             cudaMemcpyDeviceToDevice, st_));
+    }
+    launch_advance_streams(slot, B, T, ring_pos_.as<int>(), valid_len_.as<int>(), st_); count_launch();
+
+    // G/Y: joint.enc for all frames, then the persistent greedy-decode kernel
+    {
+        GemmArgs g; g.A = x; g.lda = D_MODEL; g.W = joint_enc_w_.data.p; g.M = rows; g.N = JOINT; g.K = D_MODEL; g.bias = joint_enc_b_.as<float>();
+        g.C = encp_.p; g.ldc = JOINT; g.epi = EPI_NONE; launch_gemm_simt(g, st_); count_launch();
+    }
+    DecodeArgs d{};
+    d.w.embed = embed_.as<float>();
+    for (int l = 0; l < 2; ++l) { d.w.w_ih[l] = lstm_w_[2 * l].as<float>(); d.w.w_hh[l] = lstm_w_[2 * l + 1].as<float>();
+                                  d.w.b_ih[l] = lstm_b_[2 * l].as<float>(); d.w.b_hh[l] = lstm_b_[2 * l + 1].as<float>(); }
+    d.w.pred_w = pred_w_.as<float>(); d.w.pred_b = pred_b_.as<float>(); d.w.out_w = jout_w_.as<float>(); d.w.out_b = jout_b_.as<float>();
+    d.s.h = dec_h_.as<float>(); d.s.c = dec_c_.as<float>(); d.s.cand_h = cand_h_.as<float>(); d.s.cand_c = cand_c_.as<float>();
+    d.s.dec_proj = dec_proj_.as<float>(); d.s.prev_token = prev_token_.as<int>(); d.s.cand_valid = cand_valid_.as<int>();
+    d.enc_proj = encp_.as<float>(); d.slot_of_b = slot; d.B = B; d.T = T;
+    d.out_tokens = out_tok_.as<int>(); d.out_count = out_cnt_.as<int>();
+    d.frame_idx = frame_idx_.as<int>(); d.sym_cnt = sym_cnt_.as<int>(); d.need_lstm = need_lstm_.as<int>();
+    d.part_val = part_val_.as<float>(); d.part_idx = part_idx_.as<int>(); d.counters = counters_.as<int>();
+    d.logits_tap = debug_ ? dbg_logits_.as<float>() : nullptr; d.logits_tap_cap = debug_ ? MAX_SYMBOLS * T + T : 0;
+    d.logits_tap_n = debug_ ? dbg_logits_n_.as<int>() : nullptr;
+    launch_decode(d, st_); count_launch();
+}
+
+// ------------------------------------------------------------------------------------------
+// bench hooks
+// ------------------------------------------------------------------------------------------
+void Engine::bench_prepare(int n_streams, const int16_t* pcm, int samples_per_stream, int warm_chunks) {
+    if (n_streams < 1 || n_streams > max_streams) throw std::invalid_argument("bench: n_streams out of range");
+    const long long need_warm = warm_chunks > 0 ? (long long)HOP * (8LL * T * warm_chunks - 1) + N_FFT / 2 : 0;
+    const long long need_all = (long long)HOP * (8LL * T * (warm_chunks + 1) - 1) + N_FFT / 2;
+    if (samples_per_stream < need_all) throw std::invalid_argument("bench: need at least " + std::to_string(need_all) + " samples per stream");
+    for (int s = 0; s < max_streams; ++s) if (hs_[s].open) hs_[s].open = false;
+    std::vector<int> ids;
+    for (int i = 0; i < n_streams; ++i) ids.push_back(open_stream());
+    for (int i = 0; i < n_streams; ++i) if (need_warm) push_pcm(ids[i], pcm + (size_t)i * samples_per_stream, (int)need_warm);
+    while (step() > 0) {}
+    for (int i = 0; i < n_streams; ++i) push_pcm(ids[i], pcm + (size_t)i * samples_per_stream + need_warm, (int)(need_all - need_warm));
+    bench_pcm_.alloc((size_t)n_streams * rl_ * 2, false);
+    int16_t* hp = h_pcm_.as<int16_t>(); int* hsl = h_slot_.as<int>();
+    for (int b = 0; b < n_streams; ++b) {
+        if (!ready(ids[b])) throw std::runtime_error("bench: stream not ready after staging");
+        stage_row(hs_[ids[b]], T, rl_, hp + (size_t)b * rl_); hsl[b] = ids[b];
+    }
+    NSB_CUDA(cudaMemcpy(bench_pcm_.p, hp, (size_t)n_streams * rl_ * 2, cudaMemcpyHostToDevice));
+    NSB_CUDA(cudaMemcpy(d_slot_.p, hsl, (size_t)n_streams * 4, cudaMemcpyHostToDevice));
+    bench_B_ = n_streams;
+}
+
+float Engine::bench_step() {
+    if (!bench_B_) throw std::runtime_error("bench_step before bench_prepare");
+    NSB_CUDA(cudaSetDevice(device_));
+    NSB_CUDA(cudaEventRecord(ev0_, st_));
+    run_step_kernels(bench_B_, bench_pcm_.as<int16_t>());
+    NSB_CUDA(cudaEventRecord(ev1_, st_));
+    NSB_CUDA(cudaEventSynchronize(ev1_));
+    float ms = 0.f; NSB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    stats.steps += 1; stats.chunks += bench_B_; stats.device_ms += ms; stats.last_step_ms = ms;
+    return ms;
+}
+
+// ------------------------------------------------------------------------------------------
+// debug taps + stand-alone operators
+// ------------------------------------------------------------------------------------------
+void Engine::debug_enable(bool on) {
+    debug_ = on;
+    if (!on) return;
+    dbg_B_ = max_streams;
+    const size_t rows = (size_t)dbg_B_ * T;
+    dbg_mel_.alloc((size_t)dbg_B_ * (PRE_CACHE + 8 * T) * N_MELS * 4);
+    dbg_sub_.alloc(rows * D_MODEL * 4);
+    dbg_layers_.alloc((size_t)n_layers * rows * D_MODEL * 4);
+    dbg_logits_.alloc((size_t)(MAX_SYMBOLS * T + T) * VOCAB * 4);
+    dbg_logits_n_.alloc(4);
+}
+
+long long Engine::debug_get(const std::string& name, float* out, size_t cap) {
+    if (!debug_) throw std::runtime_error("debug taps are not enabled");
+    const void* src = nullptr; size_t n = 0;
+    const size_t rows_all = (size_t)dbg_B_ * T;
+    if (name == "mel") { src = dbg_mel_.p; n = (size_t)dbg_B_ * (PRE_CACHE + 8 * T) * N_MELS; }
+    else if (name == "sub") { src = dbg_sub_.p; n = rows_all * D_MODEL; }
+    else if (name == "enc") { src = dbg_layers_.as<float>() + (size_t)(n_layers - 1) * rows_all * D_MODEL; n = rows_all * D_MODEL; }
+    else if (name.rfind("layer.", 0) == 0) {
+        const int l = atoi(name.c_str() + 6);
+        if (l < 0 || l >= n_layers) throw std::invalid_argument("layer index");
+        src = dbg_layers_.as<float>() + (size_t)l * rows_all * D_MODEL; n = rows_all * D_MODEL;
+    } else if (name == "logits") {
+        int ne = 0; NSB_CUDA(cudaMemcpy(&ne, dbg_logits_n_.p, 4, cudaMemcpyDeviceToHost));
+        ne = std::min(ne, MAX_SYMBOLS * T + T);
+        src = dbg_logits_.p; n = (size_t)ne * VOCAB;
+    } else throw std::invalid_argument("unknown tap '" + name + "'");
+    n = std::min(n, cap);
+    NSB_CUDA(cudaMemcpy(out, src, n * 4, cudaMemcpyDeviceToHost));
+    return (long long)n;
+}
+
+long long Engine::debug_get_cache(int stream, int which, int layer, float* out, size_t cap) {
+    if (stream < 0 || stream >= max_streams || layer < 0 || layer >= n_layers) throw std::invalid_argument("bad stream/layer");
+    NSB_CUDA(cudaStreamSynchronize(st_));
+    if (which == 2) {
+        const size_t n = (size_t)(CONV_K - 1) * D_MODEL; if (cap < n) return -(long long)n;
+        NSB_CUDA(cudaMemcpy(out, conv_cache_.as<float>() + ((size_t)stream * n_layers + layer) * n, n * 4, cudaMemcpyDeviceToHost));
+        return (long long)n;
+    }
+    // K / V: return the 70 cache rows in logical order (oldest first), as the reference's rolled cache holds them
+    const int Cap = ATT_L + T; const size_t es = kv_elem_size(kv_dtype);
+    const size_t n = (size_t)ATT_L * D_MODEL; if (cap < n) return -(long long)n;
+    std::vector<uint8_t> raw((size_t)Cap * D_MODEL * es);
+    const size_t off = (((size_t)stream * n_layers + layer) * 2 + (which ? 1 : 0)) * Cap * D_MODEL * es;
+    NSB_CUDA(cudaMemcpy(raw.data(), (char*)kv_.p + off, raw.size(), cudaMemcpyDeviceToHost));
+    int w = 0; NSB_CUDA(cudaMemcpy(&w, ring_pos_.as<int>() + stream, 4, cudaMemcpyDeviceToHost));
+    for (int j = 0; j < ATT_L; ++j) {
+        const int r = (w + Cap - ATT_L + j) % Cap;           // after advance: the 70 rows before the write position
+        for (int c = 0; c < D_MODEL; ++c) {
+            const size_t i = (size_t)r * D_MODEL + c; float v;
+            if (kv_dtype == 0) v = ((const float*)raw.data())[i];
+            else if (kv_dtype == 1) v = half_bits_to_float(((const uint16_t*)raw.data())[i]);
+            else { uint32_t u = (uint32_t)((const uint16_t*)raw.data())[i] << 16; memcpy(&v, &u, 4); }
+            out[(size_t)j * D_MODEL + c] = v;
+        }
+    }
+    return (long long)n;
+}
+
+long long Engine::op_logmel(const int16_t* pcm, int n_streams, int n_samples, float* out, size_t cap) {
+    if (n_streams < 1 || n_samples < 1) throw std::invalid_argument("op_logmel: empty input");
+    const long long avail = N_FFT / 2 + (long long)n_samples;
+    const int n_frames = avail < N_FFT ? 0 : (int)((avail - N_FFT + HOP) / HOP);     // preprocessor.cpp:320-328
+    if (n_frames == 0) return 0;
+    if (cap < (size_t)n_streams * n_frames * N_MELS) return -(long long)((size_t)n_streams * n_frames * N_MELS);
+    const int row = 1 + N_FFT / 2 + n_samples;
+    std::vector<int16_t> h((size_t)n_streams * row, 0);
+    for (int s = 0; s < n_streams; ++s) memcpy(&h[(size_t)s * row + 1 + N_FFT / 2], pcm + (size_t)s * n_samples, (size_t)n_samples * 2);
+    DevBuf d_in, d_out; d_in.alloc(h.size() * 2, false); d_out.alloc((size_t)n_streams * n_frames * N_MELS * 4, false);
+    NSB_CUDA(cudaMemcpy(d_in.p, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+    launch_logmel(d_in.as<int16_t>(), row, n_streams, n_frames, window_.as<float>(), cos_t_.as<float>(), sin_t_.as<float>(), fb_t_.as<float>(),
+                  d_out.as<float>(), (size_t)n_frames * N_MELS, st_);
+    count_launch();
+    NSB_CUDA(cudaStreamSynchronize(st_));
+    NSB_CUDA(cudaMemcpy(out, d_out.p, d_out.bytes, cudaMemcpyDeviceToHost));
+    return n_frames;
+}
+
+long long Engine::op_gemm(const std::string& name, const float* xh, int rows, float* y, size_t cap) {
+    auto it = named_.find(name);
+    if (it == named_.end()) throw std::invalid_argument("op_gemm: unknown weight '" + name + "'");
+    const Weight& W = *it->second;
+    if (cap < (size_t)rows * W.n_out) return -(long long)((size_t)rows * W.n_out);
+    DevBuf dx, da, dy; dx.alloc((size_t)rows * W.n_in * 4, false); dy.alloc((size_t)rows * W.n_out * 4, false);
+    NSB_CUDA(cudaMemcpy(dx.p, xh, dx.bytes, cudaMemcpyHostToDevice));
+    const void* A = dx.p;
+    if (act_type() != OUT_F32) { da.alloc((size_t)rows * W.n_in * 2, false); convert_to(dx.as<float>(), da.p, (size_t)rows * W.n_in, act_type(), st_); A = da.p; }
+    gemm(A, W.n_in, W, rows, nullptr, dy.p, W.n_out, EPI_NONE, 1.f, OUT_F32);
+    NSB_CUDA(cudaStreamSynchronize(st_));
+    NSB_CUDA(cudaMemcpy(y, dy.p, dy.bytes, cudaMemcpyDeviceToHost));
+    return W.n_out;
+}
+
+}  // namespace nsb

@@ -1,0 +1,137 @@
+// engine.h -- per-GPU streaming engine (internal). Public face: include/nsb200.h
+#pragma once
+#include <deque>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/nsb200.h"
+#include "gguf_loader.h"
+#include "kernels.cuh"
+
+namespace nsb {
+
+struct DevBuf {
+    void* p = nullptr; size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { if (p) cudaFree(p); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; } return *this; }
+    ~DevBuf() { if (p) cudaFree(p); }
+    void alloc(size_t n, bool zero = true) {
+        if (p) { cudaFree(p); p = nullptr; }
+        bytes = n; if (!n) return;
+        NSB_CUDA(cudaMalloc(&p, n));
+        if (zero) NSB_CUDA(cudaMemset(p, 0, n));
+    }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct HostPinned {
+    void* p = nullptr; size_t bytes = 0;
+    ~HostPinned() { if (p) cudaFreeHost(p); }
+    void alloc(size_t n) { if (p) { cudaFreeHost(p); p = nullptr; } bytes = n; if (n) NSB_CUDA(cudaMallocHost(&p, n)); }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+// one GEMM weight in the engine's compute arithmetic
+struct Weight {
+    std::string name; int n_out = 0, n_in = 0;
+    DevBuf data;            // f32 / f16 / bf16 [n_out][n_in]
+};
+
+struct LayerW {
+    DevBuf ln[10];          // ff1 g,b | attn g,b | conv g,b | ff2 g,b | out g,b
+    Weight ff1a, ff1b, qkv, out, pw1, pw2, ff2a, ff2b;
+    DevBuf bias_u, bias_v, dw_w, cln_g, cln_b;
+    DevBuf pos_proj;        // [L+2T-1][1024] f32
+};
+
+struct HostStream {
+    bool open = false;
+    std::vector<int16_t> buf;      // raw samples from absolute index `base`
+    long long base = 0, n_pushed = 0, chunk_idx = 0;
+    std::deque<int32_t> tokens;
+};
+
+class Engine {
+public:
+    Engine(const std::string& gguf_path, const nsb_engine_config& cfg);
+    ~Engine();
+
+    int open_stream(); void close_stream(int s); void reset_stream(int s);
+    void push_pcm(int s, const int16_t* pcm, int n);
+    bool ready(int s) const;
+    int step();                       // returns #streams advanced
+    int pop_tokens(int s, int32_t* out, int cap);
+    int chunks(int s) const;
+    std::string detok(const int32_t* t, int n) const;
+
+    void bench_prepare(int n_streams, const int16_t* pcm, int samples_per_stream, int warm_chunks);
+    float bench_step();
+
+    void debug_enable(bool on);
+    long long debug_get(const std::string& name, float* out, size_t cap);
+    long long debug_get_cache(int stream, int which, int layer, float* out, size_t cap);
+    long long op_logmel(const int16_t* pcm, int n_streams, int n_samples, float* out, size_t cap);
+    long long op_gemm(const std::string& name, const float* x, int rows, float* y, size_t cap);
+
+    // facts
+    int n_layers = 0, T = 1, R = 0, compute = NSB_COMPUTE_F32, kv_dtype = NSB_KV_F32, max_streams = 0;
+    std::vector<char> vocab;
+    nsb_stats stats{};
+    int chunk_samples() const { return (PRE_CACHE + 8 * T) * HOP; }
+    int shift_samples() const { return 8 * T * HOP; }
+
+private:
+    void load_weights(const GgufFile& g);
+    void upload_weight(Weight& w, const std::string& name, const std::vector<float>& host, int n_out, int n_in);
+    void alloc_state();
+    void zero_slot(int slot);
+    void build_pos_tables(const GgufFile& g);
+    void gemm(const void* A, long long lda, const Weight& W, int M, const float* bias, void* C, long long ldc, int epi, float alpha,
+              int out_type);
+    void run_step_kernels(int B, const int16_t* d_pcm);      // everything between PCM-in-HBM and tokens-in-HBM
+    void collect_tokens(int B, const std::vector<int>& batch);
+    int act_type() const { return compute == NSB_COMPUTE_F32 ? OUT_F32 : (compute == NSB_COMPUTE_BF16 ? OUT_BF16 : OUT_F16); }
+    size_t act_size() const { return compute == NSB_COMPUTE_F32 ? 4 : 2; }
+    void count_launch(int n = 1) { stats.kernel_launches += n; }
+
+    nsb_engine_config cfg_{};
+    int device_ = 0;
+    cudaStream_t st_ = nullptr;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+
+    // ---- weights ----
+    std::vector<LayerW> layers_;
+    std::map<std::string, Weight*> named_;   // for op_gemm
+    DevBuf window_, cos_t_, sin_t_, fb_t_;
+    DevBuf c0_w_, c0_b_, c2_w_, c2_b_, c3_b_, c5_w_, c5_b_, c6_b_, out_b_;
+    Weight c3_w_, c6_w_, sub_out_w_;         // always f32 (SIMT)
+    Weight joint_enc_w_; DevBuf joint_enc_b_;
+    DevBuf embed_, lstm_w_[4], lstm_b_[4], pred_w_, pred_b_, jout_w_, jout_b_;
+
+    // ---- per-slot state ----
+    DevBuf kv_;                    // [S][layers][2][L+T][1024] kv dtype
+    DevBuf conv_cache_;            // [S][layers][8][1024] f32
+    DevBuf mel_hist_;              // [S][9][128]
+    DevBuf ring_pos_, valid_len_;  // [S] int
+    DevBuf dec_h_, dec_c_, cand_h_, cand_c_, dec_proj_, prev_token_, cand_valid_;
+    std::vector<HostStream> hs_;
+
+    // ---- step workspace (batch-compact) ----
+    int rl_ = 0;                   // PCM row length per stream-step
+    DevBuf d_pcm_, d_slot_, mel_new_, c0_, dw_, pw_, x_, a_, big_, qkv_, pw1_, encp_;
+    DevBuf out_tok_, out_cnt_, frame_idx_, sym_cnt_, need_lstm_, part_val_, part_idx_, counters_;
+    HostPinned h_pcm_, h_slot_, h_tok_, h_cnt_;
+
+    // ---- bench ----
+    DevBuf bench_pcm_; int bench_B_ = 0;
+
+    // ---- debug taps ----
+    bool debug_ = false; int dbg_B_ = 0;
+    DevBuf dbg_mel_, dbg_sub_, dbg_layers_, dbg_logits_, dbg_logits_n_;
+};
+
+}  // namespace nsb

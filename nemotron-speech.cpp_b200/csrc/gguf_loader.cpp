@@ -1,0 +1,133 @@
+#include "gguf_loader.h"
+
+#include <cstdio>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+
+namespace nsb {
+
+namespace {
+struct File {
+    FILE* f = nullptr;
+    explicit File(const std::string& p) : f(fopen(p.c_str(), "rb")) {}
+    ~File() { if (f) fclose(f); }
+};
+template <class T> T rd(FILE* f) {
+    T v{};
+    if (fread(&v, sizeof(T), 1, f) != 1) throw std::runtime_error("gguf: unexpected end of file");
+    return v;
+}
+std::string rd_str(FILE* f) {
+    uint64_t n = rd<uint64_t>(f);
+    if (n > (1ull << 28)) throw std::runtime_error("gguf: string too long");
+    std::string s(n, '\0');
+    if (n && fread(&s[0], 1, n, f) != n) throw std::runtime_error("gguf: unexpected end of file");
+    return s;
+}
+size_t scalar_size(int t) {
+    switch (t) {
+        case 0: case 1: case 7: return 1;       // u8 i8 bool
+        case 2: case 3: return 2;               // u16 i16
+        case 4: case 5: case 6: return 4;       // u32 i32 f32
+        case 10: case 11: case 12: return 8;    // u64 i64 f64
+        default: return 0;
+    }
+}
+}  // namespace
+
+float half_bits_to_float(uint16_t h) {
+    uint32_t sign = (h >> 15) & 1u, exp = (h >> 10) & 0x1fu, man = h & 0x3ffu, f;
+    if (exp == 0) {
+        float v = ldexpf((float)man, -24);   // zero / subnormal: man * 2^-24, exact
+        return sign ? -v : v;
+    } else if (exp == 31) f = (sign << 31) | 0x7f800000u | (man << 13);
+    else f = (sign << 31) | ((exp + 127 - 15) << 23) | (man << 13);
+    float out; memcpy(&out, &f, 4); return out;
+}
+
+void GgufFile::open(const std::string& p) {
+    path = p;
+    File fh(p);
+    if (!fh.f) throw std::runtime_error("gguf: cannot open '" + p + "'");
+    FILE* f = fh.f;
+    char magic[4];
+    if (fread(magic, 1, 4, f) != 4 || memcmp(magic, "GGUF", 4) != 0) throw std::runtime_error("gguf: bad magic in '" + p + "'");
+    uint32_t version = rd<uint32_t>(f);
+    if (version < 2 || version > 3) throw std::runtime_error("gguf: unsupported version " + std::to_string(version));
+    int64_t n_tensors = rd<int64_t>(f), n_kv = rd<int64_t>(f);
+    if (n_tensors < 0 || n_tensors > (1 << 20) || n_kv < 0 || n_kv > (1 << 20)) throw std::runtime_error("gguf: implausible counts");
+    uint64_t alignment = 32;
+    for (int64_t i = 0; i < n_kv; ++i) {
+        std::string key = rd_str(f);
+        int32_t t = rd<int32_t>(f);
+        if (t == 8) {
+            std::string v = rd_str(f);
+            if (key == "tokenizer.vocab") vocab_raw = v;
+        } else if (t == 9) {
+            int32_t et = rd<int32_t>(f);
+            uint64_t n = rd<uint64_t>(f);
+            for (uint64_t k = 0; k < n; ++k) {
+                if (et == 8) rd_str(f);
+                else { size_t sz = scalar_size(et); if (!sz) throw std::runtime_error("gguf: bad array type"); fseek(f, (long)sz, SEEK_CUR); }
+            }
+        } else {
+            size_t sz = scalar_size(t);
+            if (!sz) throw std::runtime_error("gguf: unknown kv type " + std::to_string(t));
+            uint64_t raw = 0;
+            if (fread(&raw, 1, sz, f) != sz) throw std::runtime_error("gguf: unexpected end of file");
+            if (t == 4 || t == 5) u32[key] = (uint32_t)raw;
+            if (key == "general.alignment") alignment = (uint32_t)raw;
+        }
+    }
+    for (int64_t i = 0; i < n_tensors; ++i) {
+        GgufTensor t;
+        t.name = rd_str(f);
+        uint32_t nd = rd<uint32_t>(f);
+        if (nd > 4) throw std::runtime_error("gguf: tensor '" + t.name + "' has >4 dims");
+        t.ne.resize(nd);
+        for (auto& d : t.ne) d = rd<int64_t>(f);
+        t.type = rd<int32_t>(f);
+        t.offset = rd<uint64_t>(f);
+        int64_t n = t.n_elements();
+        switch (t.type) {
+            case GGML_F32: t.nbytes = (size_t)n * 4; break;
+            case GGML_F16: t.nbytes = (size_t)n * 2; break;
+            case GGML_Q8_0:
+                if (t.ne.empty() || t.ne[0] % 32) throw std::runtime_error("gguf: Q8_0 tensor '" + t.name + "' ne0 % 32 != 0");
+                t.nbytes = (size_t)n / 32 * 34; break;
+            default: throw std::runtime_error("gguf: tensor '" + t.name + "' has unsupported type " + std::to_string(t.type) +
+                                              " (supported: F32, F16, Q8_0)");
+        }
+        tensors[t.name] = t;
+    }
+    uint64_t pos = (uint64_t)ftell(f);
+    data_start = (pos + alignment - 1) / alignment * alignment;
+}
+
+const GgufTensor& GgufFile::require(const std::string& name) const {
+    auto it = tensors.find(name);
+    if (it == tensors.end()) throw std::runtime_error("gguf: missing tensor: " + name);
+    return it->second;
+}
+
+std::vector<uint8_t> GgufFile::read(const GgufTensor& t) const {
+    File fh(path);
+    if (!fh.f) throw std::runtime_error("gguf: cannot reopen '" + path + "'");
+    std::vector<uint8_t> buf(t.nbytes);
+    if (fseek(fh.f, (long)(data_start + t.offset), SEEK_SET) != 0 || fread(buf.data(), 1, t.nbytes, fh.f) != t.nbytes)
+        throw std::runtime_error("gguf: failed to read tensor '" + t.name + "'");
+    return buf;
+}
+
+std::vector<float> GgufFile::read_f32(const std::string& name) const {
+    const GgufTensor& t = require(name);
+    std::vector<uint8_t> raw = read(t);
+    std::vector<float> out((size_t)t.n_elements());
+    if (t.type == GGML_F32) memcpy(out.data(), raw.data(), raw.size());
+    else if (t.type == GGML_F16) for (size_t i = 0; i < out.size(); ++i) { uint16_t h; memcpy(&h, &raw[2 * i], 2); out[i] = half_bits_to_float(h); }
+    else throw std::runtime_error("gguf: tensor '" + name + "' expected F32/F16");
+    return out;
+}
+
+}  // namespace nsb

@@ -1,0 +1,100 @@
+// kernels.cuh -- launchers of the hand-written sm_100a kernels (internal)
+#pragma once
+#include "common.cuh"
+
+namespace nsb {
+
+// ---------------------------------------------------------------- front-end (kernels_frontend.cu)
+// log-mel of n_frames frames per row. Row b of `pcm` holds [prev_sample, s_0, s_1, ...] of the
+// 256-zero-left-padded stream; frame j covers s[160 j .. 160 j + 512). Output row stride given.
+void launch_logmel(const int16_t* pcm, int pcm_row_stride, int B, int n_frames, const float* window512,
+                   const float* cos_t, const float* sin_t, const float* fb_t /*[257][128]*/, float* mel_out,
+                   size_t out_batch_stride, cudaStream_t st);
+
+// conv0 (1->256, 3x3 s2, pad 2/1) + ReLU on the chunk image [M = 9 + 8T frames, 128 mels]; frames 0..8 come
+// from the per-slot history, the rest from mel_new. Output NHWC [B][t1][65][256].
+void launch_conv0(const float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, const float* w_t /*[9][256]*/,
+                  const float* bias, float* out, cudaStream_t st);
+// history = last 9 frames of [hist || new]
+void launch_mel_hist_update(float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, cudaStream_t st);
+// optional tap: full chunk image [B][M][128]
+void launch_mel_gather(const float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, float* out, cudaStream_t st);
+// depthwise 3x3 s2 (+bias), NHWC, C = 256
+void launch_dwconv_s2(const float* in, int B, int H, int W, const float* w_t /*[9][256]*/, const float* bias, float* out,
+                      cudaStream_t st);
+
+// ---------------------------------------------------------------- SIMT fp32 GEMM (gemm_simt.cu)
+struct GemmArgs {
+    const void* A = nullptr;      // [M, K] row-major (K contiguous); f32 for SIMT, f16/bf16 for tensor-core
+    long long lda = 0;            // elements
+    // optional row map: A row(m) = (m / group) * group_stride + (m % group + row_off) * lda   (group == 0 -> m * lda)
+    int group = 0; long long group_stride = 0; int row_off = 0;
+    const void* W = nullptr;      // [N, K] row-major
+    int M = 0, N = 0, K = 0;
+    const float* bias = nullptr;  // [N] or null
+    void* C = nullptr; long long ldc = 0;
+    int epi = EPI_NONE; float alpha = 1.0f; int out_type = OUT_F32;
+};
+void launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
+
+// ---------------------------------------------------------------- layer kernels (kernels_layer.cu)
+void launch_layernorm(const float* x, int rows, const float* g, const float* b, void* y, int out_type, cudaStream_t st);
+// y1 = LN(x; g1,b1) written back to x (f32) AND y2 = LN(y1; g2,b2) written as out_type  (norm_out fused with next norm_ff1)
+void launch_layernorm2(float* x, int rows, const float* g1, const float* b1, const float* g2, const float* b2, void* y2,
+                       int out_type, cudaStream_t st);
+
+struct AttnArgs {
+    const float* qkv;             // [M][3072] f32 (q | k | v)
+    void* k_ring; void* v_ring;   // layer base; element (slot, r, c) at slot*slot_stride + r*1024 + c
+    long long slot_stride;        // elements
+    int kv_dtype;                 // 0 f32, 1 f16, 2 bf16
+    const float* pos_proj;        // [L + 2T - 1][1024], row = rel + (T-1)
+    const float* bias_u; const float* bias_v;   // [1024]
+    void* ctx; int out_type;      // [M][1024]
+    const int* slot_of_b; const int* ring_pos; const int* valid_len;
+    int B, T;
+};
+void launch_attention(const AttnArgs& a, cudaStream_t st);
+
+struct ConvModArgs {
+    const float* pw1;             // [M][2048] f32  (a | gate)
+    float* conv_cache;            // layer base; (slot, r, c) at slot*slot_stride + r*1024 + c, r in 0..7
+    long long slot_stride;
+    const float* dw_w;            // [9][1024] tap-major (GGUF layout)
+    const float* ln_g; const float* ln_b;
+    void* out; int out_type;      // [M][1024]
+    const int* slot_of_b; int B, T;
+};
+void launch_conv_module(const ConvModArgs& a, cudaStream_t st);
+
+void launch_advance_streams(const int* slot_of_b, int B, int T, int* ring_pos, int* valid_len, cudaStream_t st);
+
+// ---------------------------------------------------------------- RNN-T decode (kernels_decode.cu)
+struct DecodeWeights {
+    const float* embed;                       // [1025][640]
+    const float* w_ih[2]; const float* w_hh[2]; const float* b_ih[2]; const float* b_hh[2];   // [2560][640], [2560]
+    const float* pred_w; const float* pred_b; // [640][640], [640]
+    const float* out_w; const float* out_b;   // [1025][640], [1025]
+};
+struct DecodeState {                          // slot-indexed, device
+    float* h; float* c;                       // [S][1280]
+    float* cand_h; float* cand_c;             // [S][1280]
+    float* dec_proj;                          // [S][640]
+    int* prev_token; int* cand_valid;         // [S]
+};
+struct DecodeArgs {
+    DecodeWeights w; DecodeState s;
+    const float* enc_proj;                    // [B*T][640] (joint.enc applied, bias included)
+    const int* slot_of_b; int B, T;
+    int* out_tokens; int* out_count;          // [B][MAX_SYMBOLS*T], [B]
+    // scratch
+    int* frame_idx; int* sym_cnt; int* need_lstm;     // [B]
+    float* part_val; int* part_idx;           // [B][gridDim]
+    int* counters;                            // [4] : n_active, n_need_lstm (double-buffered)
+    float* logits_tap; int logits_tap_cap; int* logits_tap_n;   // optional: logits of batch row 0 per evaluation
+};
+// cooperative persistent kernel; returns the grid size used
+int launch_decode(const DecodeArgs& a, cudaStream_t st);
+size_t decode_scratch_parts(int B);           // number of (val, idx) partial slots needed = B * grid
+
+}  // namespace nsb

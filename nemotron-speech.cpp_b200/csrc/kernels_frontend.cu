@@ -1,0 +1,153 @@
+// kernels_frontend.cu -- log-mel front-end and dw-striding subsampling stem (sm_100a).
+//
+// Reference behaviour being replaced:
+//   * nemo_preprocessor_process / stft_magnitude / fft_frame  (src/preprocessor.cpp:330-395,167-205,113-161)
+//   * build_causal_conv2d / build_causal_dw_conv2d / build_conv_subsampling stem (src/nemo-ggml.cpp:820-930)
+// The reference runs the mel on one CPU thread per context; here one CTA computes one frame of one
+// stream, so a step launches (8T x B) CTAs.
+#include "kernels.cuh"
+
+namespace nsb {
+
+// ------------------------------------------------------------------------------------------
+// log-mel: one CTA = one 512-sample frame. Shared-memory radix-2 DIT FFT (9 stages x 256
+// butterflies), power spectrum, 128x257 filterbank, log.
+// Arithmetic is written with explicit _rn intrinsics (no FMA contraction) in the same operation
+// order as the reference so that every step up to the final log is bit-identical to its x86 build;
+// the log is taken in fp64 and rounded once (glibc logf is correctly rounded in nearly all cases).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__ pcm, int pcm_row_stride, int n_frames,
+                                                     const float* __restrict__ window, const float* __restrict__ cos_t,
+                                                     const float* __restrict__ sin_t, const float* __restrict__ fb_t,
+                                                     float* __restrict__ mel_out, size_t out_batch_stride) {
+    __shared__ float re[N_FFT], im[N_FFT], pw[N_BINS + 3];
+    const int j = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+    const int16_t* row = pcm + (size_t)b * pcm_row_stride + (size_t)j * HOP;   // row[0] = sample before the frame
+    const float scale = 1.0f / 32768.0f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int i = t + h * 256;
+        const float cur = (float)row[1 + i] * scale, prev = (float)row[i] * scale;     // exact
+        const float y = __fsub_rn(cur, __fmul_rn(0.97f, prev));                          // pre-emphasis :349-356
+        const int r = __brev((unsigned)i) >> 23;                                         // 9-bit reversal :124-127
+        re[r] = __fmul_rn(y, window[i]);                                                 // :184-194
+        im[r] = 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m2 = 1; m2 < N_FFT; m2 <<= 1) {                                             // :131-154
+        const int jj = t & (m2 - 1), i1 = ((t - jj) << 1) + jj, i2 = i1 + m2;
+        const int idx = jj * (N_FFT / (2 * m2));
+        const float wr = cos_t[idx], wi = -sin_t[idx];
+        const float r2 = re[i2], q2 = im[i2], r1 = re[i1], q1 = im[i1];
+        const float tr = __fsub_rn(__fmul_rn(wr, r2), __fmul_rn(wi, q2));
+        const float ti = __fadd_rn(__fmul_rn(wr, q2), __fmul_rn(wi, r2));
+        re[i2] = __fsub_rn(r1, tr); im[i2] = __fsub_rn(q1, ti);
+        re[i1] = __fadd_rn(r1, tr); im[i1] = __fadd_rn(q1, ti);
+        __syncthreads();
+    }
+    for (int k = t; k < N_BINS; k += 256) {                                              // :201, :363-368
+        const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(re[k], re[k]), __fmul_rn(im[k], im[k])));
+        pw[k] = __fmul_rn(mag, mag);
+    }
+    __syncthreads();
+    if (t < N_MELS) {                                                                    // :374-383
+        float sum = 0.0f;
+#pragma unroll 4
+        for (int k = 0; k < N_BINS; ++k) sum = __fadd_rn(sum, __fmul_rn(fb_t[k * N_MELS + t], pw[k]));
+        const float v = __fadd_rn(sum, 5.960464477539063e-8f);
+        mel_out[(size_t)b * out_batch_stride + (size_t)j * N_MELS + t] = (float)log((double)v);
+    }
+}
+
+void launch_logmel(const int16_t* pcm, int pcm_row_stride, int B, int n_frames, const float* window512, const float* cos_t,
+                   const float* sin_t, const float* fb_t, float* mel_out, size_t out_batch_stride, cudaStream_t st) {
+    if (B <= 0 || n_frames <= 0) return;
+    logmel_kernel<<<dim3(n_frames, B), 256, 0, st>>>(pcm, pcm_row_stride, n_frames, window512, cos_t, sin_t, fb_t, mel_out,
+                                                     out_batch_stride);
+}
+
+// ------------------------------------------------------------------------------------------
+// chunk image access: frame f of batch row b  (f < 9 -> history of the slot, else new frames)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float chunk_mel(const float* __restrict__ hist, const float* __restrict__ mel_new, int slot, int b,
+                                           int T, int f, int m) {
+    return f < PRE_CACHE ? hist[((size_t)slot * PRE_CACHE + f) * N_MELS + m]
+                         : mel_new[((size_t)b * 8 * T + (f - PRE_CACHE)) * N_MELS + m];
+}
+
+// conv0: Cin = 1 -> 256, 3x3 stride 2, pad (2,1) on time and freq, + bias, ReLU. One CTA = one output pixel,
+// thread = output channel (NHWC store is fully coalesced; the 9 taps are warp-broadcast loads).
+__global__ void __launch_bounds__(SUB_CH) conv0_kernel(const float* __restrict__ hist, const float* __restrict__ mel_new,
+                                                       const int* __restrict__ slot_of_b, int T, const float* __restrict__ w_t,
+                                                       const float* __restrict__ bias, float* __restrict__ out) {
+    const int ow = blockIdx.x, oh = blockIdx.y, b = blockIdx.z, oc = threadIdx.x;
+    const int M = PRE_CACHE + 8 * T, t1 = gridDim.y, W1 = gridDim.x;
+    const int slot = slot_of_b[b];
+    float acc = 0.0f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+        const int ih = 2 * oh + kh - 2;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const int iw = 2 * ow + kw - 2;
+            const float x = (ih >= 0 && ih < M && iw >= 0 && iw < N_MELS) ? chunk_mel(hist, mel_new, slot, b, T, ih, iw) : 0.0f;
+            acc = fmaf(x, w_t[(kh * 3 + kw) * SUB_CH + oc], acc);
+        }
+    }
+    acc += bias[oc];
+    out[(((size_t)b * t1 + oh) * W1 + ow) * SUB_CH + oc] = fmaxf(acc, 0.0f);
+}
+
+void launch_conv0(const float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, const float* w_t,
+                  const float* bias, float* out, cudaStream_t st) {
+    const int M = PRE_CACHE + 8 * T, t1 = M / 2 + 1, W1 = N_MELS / 2 + 1;
+    conv0_kernel<<<dim3(W1, t1, B), SUB_CH, 0, st>>>(mel_hist, mel_new, slot_of_b, T, w_t, bias, out);
+}
+
+__global__ void __launch_bounds__(N_MELS) mel_hist_update_kernel(float* __restrict__ hist, const float* __restrict__ mel_new,
+                                                                 const int* __restrict__ slot_of_b, int T) {
+    const int b = blockIdx.x, m = threadIdx.x, slot = slot_of_b[b];
+    float v[PRE_CACHE];
+#pragma unroll
+    for (int f = 0; f < PRE_CACHE; ++f) v[f] = chunk_mel(hist, mel_new, slot, b, T, 8 * T + f, m);   // last 9 of [hist || new]
+#pragma unroll
+    for (int f = 0; f < PRE_CACHE; ++f) hist[((size_t)slot * PRE_CACHE + f) * N_MELS + m] = v[f];
+}
+void launch_mel_hist_update(float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, cudaStream_t st) {
+    mel_hist_update_kernel<<<B, N_MELS, 0, st>>>(mel_hist, mel_new, slot_of_b, T);
+}
+
+__global__ void __launch_bounds__(N_MELS) mel_gather_kernel(const float* __restrict__ hist, const float* __restrict__ mel_new,
+                                                            const int* __restrict__ slot_of_b, int T, float* __restrict__ out) {
+    const int f = blockIdx.x, b = blockIdx.y, m = threadIdx.x, M = PRE_CACHE + 8 * T;
+    out[((size_t)b * M + f) * N_MELS + m] = chunk_mel(hist, mel_new, slot_of_b[b], b, T, f, m);
+}
+void launch_mel_gather(const float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, float* out, cudaStream_t st) {
+    mel_gather_kernel<<<dim3(PRE_CACHE + 8 * T, B), N_MELS, 0, st>>>(mel_hist, mel_new, slot_of_b, T, out);
+}
+
+// depthwise 3x3 stride 2 (+bias, no activation), NHWC with C = 256: thread = channel.
+__global__ void __launch_bounds__(SUB_CH) dwconv_s2_kernel(const float* __restrict__ in, int H, int W, const float* __restrict__ w_t,
+                                                           const float* __restrict__ bias, float* __restrict__ out) {
+    const int ow = blockIdx.x, oh = blockIdx.y, b = blockIdx.z, c = threadIdx.x;
+    const int Ho = gridDim.y, Wo = gridDim.x;
+    float acc = 0.0f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+        const int ih = 2 * oh + kh - 2;
+        if (ih < 0 || ih >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const int iw = 2 * ow + kw - 2;
+            if (iw < 0 || iw >= W) continue;
+            acc = fmaf(in[(((size_t)b * H + ih) * W + iw) * SUB_CH + c], w_t[(kh * 3 + kw) * SUB_CH + c], acc);
+        }
+    }
+    out[(((size_t)b * Ho + oh) * Wo + ow) * SUB_CH + c] = acc + bias[c];
+}
+void launch_dwconv_s2(const float* in, int B, int H, int W, const float* w_t, const float* bias, float* out, cudaStream_t st) {
+    dwconv_s2_kernel<<<dim3(W / 2 + 1, H / 2 + 1, B), SUB_CH, 0, st>>>(in, H, W, w_t, bias, out);
+}
+
+}  // namespace nsb
