@@ -1,5 +1,291 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// gemm_tc.cu -- tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T  (fp16 or bf16 operands, fp32 accumulate)
+//
+// This is the kernel behind every per-layer weight matrix of the FastConformer block (FFN linear1/2, fused QKV,
+// attention out, conv pointwise 1/2) when the engine computes in F16 / BF16 / Q8_0 mode, i.e. what the reference
+// delegates to ggml_mul_mat (src/nemo-stream.cpp:457-459, :542, :571-573, :626, :649).
+//
+// Structure (one CTA = one 128 x BN output tile, 192 threads, warp-specialised):
+//   warp 0   : TMA producer   -- cp.async.bulk.tensor.2d of the A tile [128 x 64] and the W tile [BN x 64] per k-block
+//                                into a STAGES-deep shared-memory ring (128-byte swizzle), completion on mbarriers
+//   warp 1   : MMA issuer     -- one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per
+//                                k-block, accumulating in TMEM; tcgen05.commit releases the smem stage / signals the epilogue
+//   warps 2-5: epilogue       -- tcgen05.ld the fp32 accumulator (each warp owns the TMEM lane quarter warp_id % 4),
+//                                apply bias / SiLU / residual and store (f32 or 16-bit)
+// Both operands are K-major, so the same shared-memory descriptor recipe serves A and W.
+// Rows of A beyond M are zero-filled by TMA (tensor map extent = M), so small batches need no padding.
+#include <cuda.h>
+
+#include <mutex>
+
 #include "kernels.cuh"
+
 namespace nsb {
-void launch_gemm_tc(const GemmArgs&, int, cudaStream_t) { throw CudaError("tcgen05 GEMM not built yet: use NSB_COMPUTE_F32"); }
+
+namespace {
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int TC_THREADS = 192;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t it = 0; it < (1u << 26); ++it) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row atoms of 1024 B,
+// SBO = 1024 B between atoms, LBO unused for swizzled K-major (encoded 1), version = 1, layout_type = 2.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// cute::UMMA::InstrDescriptor for kind::f16: c=F32, a/b = F16 (0) or BF16 (1), K-major both, N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t make_idesc(int fmt /*0 f16, 1 bf16*/, int n) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct TcParams {
+    int M, N, K;
+    const float* bias; void* C; long long ldc; int epi; float alpha; int out_type; int fmt;
+};
+
+template <int BN, int STAGES>
+struct Smem {
+    alignas(1024) uint8_t a[STAGES][BM * BK * 2];
+    alignas(1024) uint8_t b[STAGES][BN * BK * 2];
+    alignas(8) uint64_t full[STAGES];
+    uint64_t empty[STAGES];
+    uint64_t tmem_full;
+    uint32_t tmem_slot;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    using S = Smem<BN, STAGES>;
+    S& s = *reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+    const int nk = p.K / BK;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr uint32_t STAGE_BYTES = (BM + BN) * BK * 2;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+        mbar_init(&s.tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 2) tmem_alloc(&s.tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s.tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            for (int kb = 0; kb < nk; ++kb) {
+                const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&s.empty[st], ph ^ 1);
+                mbar_expect_tx(&s.full[st], STAGE_BYTES);
+                tma_load_2d(s.a[st], &tmA, &s.full[st], kb * BK, m0);
+                tma_load_2d(s.b[st], &tmB, &s.full[st], kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc(p.fmt, BN);
+            for (int kb = 0; kb < nk; ++kb) {
+                const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&s.full[st], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(s.a[st]), b_addr = smem_u32(s.b[st]);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                    umma_f16(tmem_base, make_desc(a_addr + k * UMMA_K * 2), make_desc(b_addr + k * UMMA_K * 2), idesc, (kb | k) ? 1u : 0u);
+                umma_commit(&s.empty[st]);                      // smem stage reusable once these MMAs retire
+            }
+            umma_commit(&s.tmem_full);                          // accumulator complete
+        }
+    } else {
+        // ===================== epilogue (4 warps; TMEM lane quarter = warp % 4) =====================
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        mbar_wait(&s.tmem_full, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+            if (row < p.M) {
+                const int n = n0 + c;
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+                if (p.bias) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += p.bias[n + i];
+                }
+                const size_t o = (size_t)row * p.ldc + n;
+                if (p.epi == EPI_RESID) {
+                    float4* dst = reinterpret_cast<float4*>((float*)p.C + o);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float4 x = dst[i];
+                        x.x += p.alpha * v[4 * i]; x.y += p.alpha * v[4 * i + 1]; x.z += p.alpha * v[4 * i + 2]; x.w += p.alpha * v[4 * i + 3];
+                        dst[i] = x;
+                    }
+                } else {
+                    if (p.epi == EPI_SILU) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = silu_exact(v[i]);
+                    } else if (p.epi == EPI_RELU) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                    }
+                    if (p.out_type == OUT_F32) {
+                        float4* dst = reinterpret_cast<float4*>((float*)p.C + o);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    } else if (p.out_type == OUT_F16) {
+                        __half2 h[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                        uint4* dst = reinterpret_cast<uint4*>((__half*)p.C + o);
+                        dst[0] = *reinterpret_cast<uint4*>(&h[0]); dst[1] = *reinterpret_cast<uint4*>(&h[4]);
+                    } else {
+                        __nv_bfloat162 h[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                        uint4* dst = reinterpret_cast<uint4*>((__nv_bfloat16*)p.C + o);
+                        dst[0] = *reinterpret_cast<uint4*>(&h[0]); dst[1] = *reinterpret_cast<uint4*>(&h[4]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+            throw CudaError("cuTensorMapEncodeTiled entry point not available");
+        fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+// 2-D K-major tensor map: dims {K, rows}, row stride ld elements, box {64, box_rows}, 128-byte swizzle
+CUtensorMap make_map(const void* ptr, int rows, int K, long long ld, int box_rows, int fmt) {
+    CUtensorMap m;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = get_encode_fn()(&m, fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr),
+                                       dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return m;
+}
+
+template <int BN, int STAGES>
+void launch_cfg(const GemmArgs& a, int fmt, cudaStream_t st) {
+    static bool attr_set = false;
+    const size_t smem = sizeof(Smem<BN, STAGES>) + 1024;
+    if (!attr_set) {
+        NSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const CUtensorMap tmA = make_map(a.A, a.M, a.K, a.lda, BM, fmt);
+    const CUtensorMap tmB = make_map(a.W, a.N, a.K, a.K, BN, fmt);
+    TcParams p{a.M, a.N, a.K, a.bias, a.C, a.ldc, a.epi, a.alpha, a.out_type, fmt};
+    dim3 grid(a.N / BN, (a.M + BM - 1) / BM);
+    gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
+    NSB_CUDA(cudaGetLastError());
+}
+}  // namespace
+
+// in_type: OUT_F16 or OUT_BF16 (type of A and W). Requires K % 64 == 0, N % 32 == 0, 16-byte aligned rows.
+void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
+    if (a.M <= 0) return;
+    if (a.group != 0) throw CudaError("gemm_tc: row maps are not supported");
+    if (a.K % BK != 0 || a.N % 32 != 0 || (a.lda % 8) != 0 || (a.ldc % 4) != 0)
+        throw CudaError("gemm_tc: unsupported shape (need K % 64 == 0, N % 32 == 0, aligned rows)");
+    const int fmt = in_type == OUT_BF16 ? 1 : 0;
+    const int tiles_m = (a.M + BM - 1) / BM;
+    // pick the widest N tile that still yields >= ~1 wave of CTAs (weight streaming needs many SMs pulling)
+    if (a.N % 128 == 0 && (long long)tiles_m * (a.N / 128) >= 120) launch_cfg<128, 4>(a, fmt, st);
+    else if (a.N % 64 == 0 && (long long)tiles_m * (a.N / 64) >= 120) launch_cfg<64, 6>(a, fmt, st);
+    else launch_cfg<32, 8>(a, fmt, st);
+}
+
+}  // namespace nsb
