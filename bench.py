@@ -1,0 +1,268 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the streaming hot path (BASELINE.json metric: RTFx = audio seconds
+processed per wall second, summed over streams; per-chunk latency alongside).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N = 1 workload = BASELINE.json configs[1]: nemotron-speech-streaming-en-0.6b (24 layers, random-init synthetic
+weights of that architecture), bf16 compute, 64 concurrent streams, 160 ms chunks (att_right_context = 1).
+A "step" = one batched engine step = one 160 ms chunk for every stream (64 x 2 encoder frames).
+N > 1 (torchrun, one rank per GPU): streams are independent, so every rank runs its own 64 streams on its own
+engine with no data-path collective ("weak" scaling); torch.distributed is used only for the barrier and the
+max-over-ranks of the timed region.
+
+  value : device-resident throughput -- PCM of the step already in HBM, CUDA events around the K steps
+  e2e   : the same K steps through the public C ABI with HOST buffers: nsb_stream_push_pcm (pinned staging +
+          H2D inside), nsb_engine_step, nsb_stream_pop_tokens (D2H of the token ids), wall clock
+
+--impl reference times the CPU oracle port of the reference path (oracle/liboracle.so, all host threads) on a
+bounded sample of the same workload; the reference's own ggml build cannot be produced offline.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+N_LAYERS = int(os.environ.get("NSB_BENCH_LAYERS", 24))
+STREAMS = int(os.environ.get("NSB_BENCH_STREAMS", 64))
+RIGHT_CONTEXT = int(os.environ.get("NSB_BENCH_R", 1))
+WARM_CHUNKS = 40            # > 70/T: the 70-frame attention cache is full (steady state) before timing
+T = 1 + RIGHT_CONTEXT
+CHUNK_S = 0.08 * T
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, device: int):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def gemm_algorithmic_bytes(rows: int, elem: int = 2):
+    """Per engine step: bytes every layer GEMM must move once (weights + A operand + C result), and launch count."""
+    shapes = [(4096, 1024, elem), (1024, 4096, 4), (3072, 1024, 4), (1024, 1024, 4), (2048, 1024, 4), (1024, 1024, 4),
+              (4096, 1024, elem), (1024, 4096, 4)]                    # (N, K, bytes per C element); RESID epilogues read+write f32
+    total = 0
+    for n, k, cb in shapes:
+        c_bytes = rows * n * cb * (2 if (n == 1024) else 1)
+        total += n * k * elem + rows * k * elem + c_bytes
+    return total * N_LAYERS, len(shapes) * N_LAYERS
+
+
+def cpu_baseline(threads: int | None, seconds: float = 1.6, streams: int = 2):
+    """Oracle port (reference arithmetic restated, OpenMP over output rows) on a bounded sample of the workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    import synth
+    if threads:
+        O.lib().orc_set_threads(threads)
+    cores = threads or O.lib().orc_get_max_threads()
+    path = synth.cached_model("f32", N_LAYERS, R=RIGHT_CONTEXT)
+    m = O.Model(path, O.MM_REF)
+    pcm = [synth.synth_pcm(s, seconds) for s in range(streams)]
+    t0 = time.perf_counter()
+    chunks = 0
+    for s in range(streams):
+        st = O.Stream(m, RIGHT_CONTEXT)
+        st.push(pcm[s])
+        chunks += st.chunks
+    dt = time.perf_counter() - t0
+    audio = chunks * CHUNK_S
+    return {"value": audio / dt, "unit": "audio_s/s", "cores": cores, "kind": "port",
+            "sample": f"{streams} streams x {seconds:.1f} s synthetic PCM, f32 weights, {N_LAYERS} layers, R={RIGHT_CONTEXT} "
+                      f"({chunks} chunks, {dt:.1f} s wall); oracle/liboracle.so = CPU restatement of the reference streaming path "
+                      f"(ggml build not reproducible offline)"}, dt
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    base, dt = cpu_baseline(None, seconds=2.4, streams=2)
+    line = {"impl": "reference", "metric": "rtfx", "value": base["value"], "unit": "audio_s/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": f"0.6B streaming FastConformer RNN-T, {N_LAYERS} layers, 160 ms chunks (R={RIGHT_CONTEXT}), "
+                                                        f"bounded CPU sample of the {STREAMS}-stream workload"},
+            "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "audio_s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    import nsb200
+    import synth
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    hbm_peak, tf_peak, peak_kind = peaks()
+
+    # synthetic model (f16 GGUF of the 24-layer architecture, cast to bf16 at load) + per-stream synthetic PCM
+    if rank == 0 or world == 1:
+        path = synth.cached_model("f16", N_LAYERS, R=RIGHT_CONTEXT)
+    if world > 1:
+        dist.barrier()
+        path = synth.cached_model("f16", N_LAYERS, R=RIGHT_CONTEXT)
+    eng = nsb200.Engine(path, right_context=RIGHT_CONTEXT, max_streams=STREAMS, compute=nsb200.COMPUTE_BF16, kv_dtype=nsb200.KV_BF16, device=local)
+    shift = eng.shift_samples
+    need = 160 * (8 * T * (WARM_CHUNKS + 1) - 1) + 256
+    base = [synth.synth_pcm(1000 * rank + s, need / 16000.0 + 0.01)[:need] for s in range(8)]
+    pcm = np.stack([np.roll(base[s % 8], 977 * (s // 8)) for s in range(STREAMS)])      # 64 distinct streams from 8 seeds
+    eng.bench_prepare(pcm, WARM_CHUNKS)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident timing: K steps, CUDA events inside the engine per step (engine stream) ----
+    for _ in range(args.warmup):
+        eng.bench_step()
+    st0 = eng.stats()
+    sampler = ClockSampler(local); sampler.start()
+    sync_all()
+    t0 = time.perf_counter()
+    dev_ms = 0.0; lat = []
+    for _ in range(args.steps):
+        ms = eng.bench_step(); dev_ms += ms; lat.append(ms)
+    sync_all()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    st1 = eng.stats()
+    launches = int(st1.kernel_launches - st0.kernel_launches)
+    # device time of the K steps = sum of per-step event times on the engine stream; max over ranks
+    t_dev = torch.tensor([dev_ms / 1e3, wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    t_dev_s, wall_s = float(t_dev[0]), float(t_dev[1])
+    audio_s = world * STREAMS * CHUNK_S * args.steps
+    value = audio_s / t_dev_s
+
+    # ---- per-kernel-class breakdown + roofline of the dominant kernel (layer GEMMs) ----
+    prof, prof_total = eng.bench_profile()
+    g_ms, g_n = prof["layer_gemm"]
+    g_bytes, g_launches = gemm_algorithmic_bytes(STREAMS * T)
+    achieved = (g_bytes / g_n) / ((g_ms / g_n) * 1e-3) / 1e9 if g_n else 0.0
+    roofline = {"bound": "hbm", "kernel": "gemm_tc_kernel (tcgen05 layer GEMMs, all 8 x 24 launches of a step)",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                "peak_kind": peak_kind, "share_of_step": g_ms / prof_total if prof_total else None,
+                "algorithmic_bytes_per_launch": g_bytes / g_n if g_n else None, "avg_launch_us": 1e3 * g_ms / g_n if g_n else None}
+    breakdown = {k: {"ms": round(v[0], 4), "launches": v[1]} for k, v in prof.items()}
+
+    # ---- end to end through the public C ABI with host buffers ----
+    eng2_streams = list(range(STREAMS))
+    for s in eng2_streams:
+        eng.reset_stream(s)
+    e2e_chunks = args.steps + args.warmup
+    need2 = 160 * (8 * T * e2e_chunks - 1) + 256
+    pcm2 = np.stack([np.resize(pcm[s], need2) for s in range(STREAMS)])
+    first = 160 * (8 * T - 1) + 256
+    pos = [0] * STREAMS
+    def feed(n):
+        for s in range(STREAMS):
+            eng.push(s, pcm2[s, pos[s]:pos[s] + n]); pos[s] += n
+    feed(first)
+    for _ in range(args.warmup):
+        assert eng.step() == STREAMS
+        feed(shift)
+    sync_all()
+    t0 = time.perf_counter()
+    ntok = 0
+    for i in range(args.steps):
+        assert eng.step() == STREAMS
+        for s in range(STREAMS):
+            ntok += len(eng.pop_tokens(s))
+        if i + 1 < args.steps:
+            feed(shift)
+    sync_all()
+    e2e_wall = time.perf_counter() - t0
+    t_e2e = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = audio_s / float(t_e2e[0])
+    rl = 1280 * T + 353
+    e2e = {"value": e2e_value, "unit": "audio_s/s", "h2d_bytes_per_step": STREAMS * rl * 2 + STREAMS * 4,
+           "d2h_bytes_per_step": STREAMS * (10 * T + 1) * 4, "ms_per_step": 1e3 * float(t_e2e[0]) / args.steps, "tokens": ntok}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu, _ = cpu_baseline(None)
+        lat_sorted = sorted(lat)
+        line = {"metric": "rtfx", "value": value, "unit": "audio_s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * t_dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"nemotron-speech-streaming-en-0.6b architecture ({N_LAYERS} conformer layers, random-init synthetic weights), "
+                                       f"bf16 tcgen05 GEMMs, bf16 K/V ring, {STREAMS} concurrent streams per GPU, 160 ms chunks (att_right_context={RIGHT_CONTEXT}), "
+                                       f"steady state after {WARM_CHUNKS} warm chunks",
+                           "streams_per_gpu": STREAMS, "chunk_ms": int(CHUNK_S * 1000), "l2_policy": "per-step working set (weights 1.16 GB + K/V ring 0.45 GB) > 126 MB L2"},
+                "p50_chunk_latency_ms": lat_sorted[len(lat) // 2], "p99_chunk_latency_ms": lat_sorted[min(len(lat) - 1, int(0.99 * len(lat)))],
+                "wall_ms_per_step": 1e3 * wall_s / args.steps,
+                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "breakdown": breakdown}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

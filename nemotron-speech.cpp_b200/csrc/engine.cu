@@ -107,6 +107,7 @@ Engine::Engine(const std::string& path, const nsb_engine_config& cfg) : cfg_(cfg
 Engine::~Engine() {
     cudaSetDevice(device_);
     cudaDeviceSynchronize();
+    for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
     if (st_) cudaStreamDestroy(st_);
@@ -287,6 +288,7 @@ void Engine::gemm(const void* A, long long lda, const Weight& W, int M, const fl
                   int out_type) {
     GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.M = M; a.N = W.n_out; a.K = W.n_in; a.bias = bias; a.C = C; a.ldc = ldc;
     a.epi = epi; a.alpha = alpha; a.out_type = out_type;
+    ProfScope ps(this, PC_GEMM);
     if (compute == NSB_COMPUTE_F32) launch_gemm_simt(a, st_);
     else launch_gemm_tc(a, act_type(), st_);
     count_launch();
@@ -392,11 +394,13 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
     float* x = x_.as<float>();
 
     // P: log-mel of the 8T new frames per stream
+    { ProfScope ps(this, PC_MEL);
     launch_logmel(d_pcm, rl_, B, 8 * T, window_.as<float>(), cos_t_.as<float>(), sin_t_.as<float>(), fb_t_.as<float>(),
-                  mel_new_.as<float>(), (size_t)8 * T * N_MELS, st_);
+                  mel_new_.as<float>(), (size_t)8 * T * N_MELS, st_); }
     count_launch();
     if (debug_) { launch_mel_gather(mel_hist_.as<float>(), mel_new_.as<float>(), slot, B, T, dbg_mel_.as<float>(), st_); count_launch(); }
     // S: subsampling stem (NHWC)
+    { ProfScope ps(this, PC_SUBSAMPLE);
     launch_conv0(mel_hist_.as<float>(), mel_new_.as<float>(), slot, B, T, c0_w_.as<float>(), c0_b_.as<float>(), c0_.as<float>(), st_);
     launch_mel_hist_update(mel_hist_.as<float>(), mel_new_.as<float>(), slot, B, T, st_);
     launch_dwconv_s2(c0_.as<float>(), B, t1, 65, c2_w_.as<float>(), c2_b_.as<float>(), dw_.as<float>(), st_);
@@ -415,19 +419,22 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
         g.W = sub_out_w_.data.p; g.M = rows; g.N = D_MODEL; g.K = SUB_W * SUB_CH; g.bias = out_b_.as<float>();
         g.C = x; g.ldc = D_MODEL; g.epi = EPI_NONE; launch_gemm_simt(g, st_); count_launch();
     }
+    }   // PC_SUBSAMPLE
     if (debug_) NSB_CUDA(cudaMemcpyAsync(dbg_sub_.p, x, (size_t)rows * D_MODEL * 4, cudaMemcpyDeviceToDevice, st_));
 
     // L: cache-aware conformer layers
     const long long kv_slot_stride = (long long)n_layers * 2 * (ATT_L + T) * D_MODEL;
     const long long cc_slot_stride = (long long)n_layers * (CONV_K - 1) * D_MODEL;
-    launch_layernorm(x, rows, layers_[0].ln[0].as<float>(), layers_[0].ln[1].as<float>(), a_.p, at, st_); count_launch();
+    { ProfScope ps(this, PC_LAYERNORM);
+      launch_layernorm(x, rows, layers_[0].ln[0].as<float>(), layers_[0].ln[1].as<float>(), a_.p, at, st_); count_launch(); }
+    auto ln = [&](const float* g_, const float* b_) { ProfScope ps(this, PC_LAYERNORM); launch_layernorm(x, rows, g_, b_, a_.p, at, st_); count_launch(); };
     for (int l = 0; l < n_layers; ++l) {
         LayerW& L = layers_[l];
         // FFN1: x += 0.5 * W2 silu(W1 LN(x))                                        (nemo-stream.cpp:603-606)
         gemm(a_.p, D_MODEL, L.ff1a, rows, nullptr, big_.p, D_FF, EPI_SILU, 1.f, at);
         gemm(big_.p, D_FF, L.ff1b, rows, nullptr, x, D_MODEL, EPI_RESID, 0.5f, OUT_F32);
         // MHSA over the ring cache                                                  (:609-615)
-        launch_layernorm(x, rows, L.ln[2].as<float>(), L.ln[3].as<float>(), a_.p, at, st_); count_launch();
+        ln(L.ln[2].as<float>(), L.ln[3].as<float>());
         gemm(a_.p, D_MODEL, L.qkv, rows, nullptr, qkv_.p, 3 * D_MODEL, EPI_NONE, 1.f, OUT_F32);
         {
             AttnArgs aa; aa.qkv = qkv_.as<float>();
@@ -437,34 +444,36 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
             aa.slot_stride = kv_slot_stride; aa.kv_dtype = kv_dtype; aa.pos_proj = L.pos_proj.as<float>();
             aa.bias_u = L.bias_u.as<float>(); aa.bias_v = L.bias_v.as<float>(); aa.ctx = a_.p; aa.out_type = at;
             aa.slot_of_b = slot; aa.ring_pos = ring_pos_.as<int>(); aa.valid_len = valid_len_.as<int>(); aa.B = B; aa.T = T;
-            launch_attention(aa, st_); count_launch();
+            ProfScope ps(this, PC_ATTENTION); launch_attention(aa, st_); count_launch();
         }
         gemm(a_.p, D_MODEL, L.out, rows, nullptr, x, D_MODEL, EPI_RESID, 1.f, OUT_F32);
         // conv module                                                               (:618-651)
-        launch_layernorm(x, rows, L.ln[4].as<float>(), L.ln[5].as<float>(), a_.p, at, st_); count_launch();
+        ln(L.ln[4].as<float>(), L.ln[5].as<float>());
         gemm(a_.p, D_MODEL, L.pw1, rows, nullptr, pw1_.p, 2 * D_MODEL, EPI_NONE, 1.f, OUT_F32);
         {
             ConvModArgs ca; ca.pw1 = pw1_.as<float>(); ca.conv_cache = conv_cache_.as<float>() + (size_t)l * (CONV_K - 1) * D_MODEL;
             ca.slot_stride = cc_slot_stride; ca.dw_w = L.dw_w.as<float>(); ca.ln_g = L.cln_g.as<float>(); ca.ln_b = L.cln_b.as<float>();
             ca.out = a_.p; ca.out_type = at; ca.slot_of_b = slot; ca.B = B; ca.T = T;
-            launch_conv_module(ca, st_); count_launch();
+            ProfScope ps(this, PC_CONVMOD); launch_conv_module(ca, st_); count_launch();
         }
         gemm(a_.p, D_MODEL, L.pw2, rows, nullptr, x, D_MODEL, EPI_RESID, 1.f, OUT_F32);
         // FFN2                                                                      (:654-657)
-        launch_layernorm(x, rows, L.ln[6].as<float>(), L.ln[7].as<float>(), a_.p, at, st_); count_launch();
+        ln(L.ln[6].as<float>(), L.ln[7].as<float>());
         gemm(a_.p, D_MODEL, L.ff2a, rows, nullptr, big_.p, D_FF, EPI_SILU, 1.f, at);
         gemm(big_.p, D_FF, L.ff2b, rows, nullptr, x, D_MODEL, EPI_RESID, 0.5f, OUT_F32);
         // norm_out (:659) fused with the next layer's norm_feed_forward1
         const bool last = l + 1 == n_layers;
-        launch_layernorm2(x, rows, L.ln[8].as<float>(), L.ln[9].as<float>(), last ? nullptr : layers_[l + 1].ln[0].as<float>(),
-                          last ? nullptr : layers_[l + 1].ln[1].as<float>(), last ? nullptr : a_.p, at, st_);
-        count_launch();
+        { ProfScope ps(this, PC_LAYERNORM);
+          launch_layernorm2(x, rows, L.ln[8].as<float>(), L.ln[9].as<float>(), last ? nullptr : layers_[l + 1].ln[0].as<float>(),
+                            last ? nullptr : layers_[l + 1].ln[1].as<float>(), last ? nullptr : a_.p, at, st_);
+          count_launch(); }
         if (debug_) NSB_CUDA(cudaMemcpyAsync(dbg_layers_.as<float>() + (size_t)l * dbg_B_ * T * D_MODEL, x, (size_t)rows * D_MODEL * 4,
                                              cudaMemcpyDeviceToDevice, st_));
     }
-    launch_advance_streams(slot, B, T, ring_pos_.as<int>(), valid_len_.as<int>(), st_); count_launch();
+    { ProfScope ps(this, PC_MISC); launch_advance_streams(slot, B, T, ring_pos_.as<int>(), valid_len_.as<int>(), st_); count_launch(); }
 
     // G/Y: joint.enc for all frames, then the persistent greedy-decode kernel
+    ProfScope ps_dec(this, PC_DECODE);
     {
         GemmArgs g; g.A = x; g.lda = D_MODEL; g.W = joint_enc_w_.data.p; g.M = rows; g.N = JOINT; g.K = D_MODEL; g.bias = joint_enc_b_.as<float>();
         g.C = encp_.p; g.ldc = JOINT; g.epi = EPI_NONE; launch_gemm_simt(g, st_); count_launch();
@@ -520,6 +529,26 @@ float Engine::bench_step() {
     float ms = 0.f; NSB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
     stats.steps += 1; stats.chunks += bench_B_; stats.device_ms += ms; stats.last_step_ms = ms;
     return ms;
+}
+
+cudaEvent_t Engine::prof_event() {
+    if (ev_used_ == ev_pool_.size()) { cudaEvent_t e; NSB_CUDA(cudaEventCreate(&e)); ev_pool_.push_back(e); }
+    return ev_pool_[ev_used_++];
+}
+
+float Engine::bench_profile(float* ms_per_class, int* launches_per_class) {
+    if (!bench_B_) throw std::runtime_error("bench_profile before bench_prepare");
+    NSB_CUDA(cudaSetDevice(device_));
+    prof_.clear(); ev_used_ = 0; profiling_ = true;
+    NSB_CUDA(cudaEventRecord(ev0_, st_));
+    run_step_kernels(bench_B_, bench_pcm_.as<int16_t>());
+    NSB_CUDA(cudaEventRecord(ev1_, st_));
+    profiling_ = false;
+    NSB_CUDA(cudaEventSynchronize(ev1_));
+    for (int c = 0; c < PC_COUNT; ++c) { ms_per_class[c] = 0.f; launches_per_class[c] = 0; }
+    for (const ProfRec& r : prof_) { float ms = 0.f; NSB_CUDA(cudaEventElapsedTime(&ms, r.a, r.b)); ms_per_class[r.cls] += ms; launches_per_class[r.cls] += 1; }
+    float total = 0.f; NSB_CUDA(cudaEventElapsedTime(&total, ev0_, ev1_));
+    return total;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -70,6 +70,9 @@ public:
 
     void bench_prepare(int n_streams, const int16_t* pcm, int samples_per_stream, int warm_chunks);
     float bench_step();
+    // one bench step with every launch bracketed by CUDA events; per-class device ms and launch counts
+    enum { PC_MEL = 0, PC_SUBSAMPLE, PC_LAYERNORM, PC_GEMM, PC_ATTENTION, PC_CONVMOD, PC_DECODE, PC_MISC, PC_COUNT };
+    float bench_profile(float* ms_per_class, int* launches_per_class);
 
     void debug_enable(bool on);
     long long debug_get(const std::string& name, float* out, size_t cap);
@@ -128,6 +131,19 @@ private:
 
     // ---- bench ----
     DevBuf bench_pcm_; int bench_B_ = 0;
+    // ---- per-launch profiling (bench_profile only) ----
+    struct ProfRec { int cls; cudaEvent_t a, b; };
+    bool profiling_ = false; std::vector<ProfRec> prof_; std::vector<cudaEvent_t> ev_pool_; size_t ev_used_ = 0;
+    cudaEvent_t prof_event();
+    struct ProfScope {
+        Engine* e; cudaEvent_t b = nullptr;
+        ProfScope(Engine* e_, int cls) : e(e_) {
+            if (!e->profiling_) return;
+            cudaEvent_t a = e->prof_event(); b = e->prof_event();
+            cudaEventRecord(a, e->st_); e->prof_.push_back({cls, a, b});
+        }
+        ~ProfScope() { if (b) cudaEventRecord(b, e->st_); }
+    };
 
     // ---- debug taps ----
     bool debug_ = false; int dbg_B_ = 0;

@@ -1,7 +1,9 @@
 #!/usr/bin/env python3
-"""Compute the mean encoder output mu of a synthetic model (seed, n_layers) with the CPU oracle
-and store it under tools/calib/ so that tools/synth.py can fold -W_enc@mu into joint.enc.bias.
-Run once per (seed, n_layers); the result is committed (4 KB). Test tooling only."""
+"""Calibrate a synthetic model (seed, n_layers) for one latency mode R with the CPU oracle:
+  mu          mean encoder output (random-weight conformers map every frame to nearly the same direction;
+              tools/synth.py folds -W_enc@mu into joint.enc.bias so the joint sees the per-frame variation)
+  blank_bias  chosen so that ~25 % of encoder frames start an emission (healthy blank / non-blank mix)
+Result: tools/calib/cal_s<seed>_L<layers>_R<R>.npz (committed, 4 KB). Test tooling only."""
 import os
 import sys
 
@@ -14,23 +16,54 @@ import oracle as O  # noqa: E402
 import synth  # noqa: E402
 
 
+def first_eval_margins(s):
+    out, cnt, first = [], 0, True
+    for e in range(s.n_evals()):
+        if first:
+            lg = s.trace_logits(e)
+            out.append(float(lg[:1024].max() - lg[1024]))
+        tok = s.eval_token(e)
+        if tok == 1024:
+            first, cnt = True, 0
+        else:
+            cnt += 1
+            first = cnt == 10
+            if first:
+                cnt = 0
+    return np.array(out)
+
+
 def main():
-    n_layers = int(sys.argv[1]); seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1234
-    out = os.path.join(HERE, "calib", f"mu_s{seed}_L{n_layers}.npy")
-    if os.path.exists(out):
-        os.remove(out)
-    path = f"/tmp/calib_s{seed}_L{n_layers}.gguf"
-    synth.write_gguf(path, n_layers, "f32", seed)
+    n_layers, R = int(sys.argv[1]), int(sys.argv[2])
+    seed = int(sys.argv[3]) if len(sys.argv) > 3 else 1234
+    out = os.path.join(HERE, "calib", f"cal_s{seed}_L{n_layers}_R{R}.npz")
+    path = f"/tmp/calib_s{seed}_L{n_layers}_R{R}.gguf"
+    secs = 7.0
+    synth.write_gguf(path, n_layers, "f32", seed, blank_bias=2.8, R=None)
     m = O.Model(path)
     rows = []
-    for stream in (100, 101, 102):
-        s = O.Stream(m, 13, trace=True)
-        s.push(synth.synth_pcm(stream, 3.5))
+    for stream in (100, 101):
+        s = O.Stream(m, R, trace=True)
+        s.push(synth.synth_pcm(stream, secs))
         rows += [s.trace_enc(c) for c in range(s.chunks)]
-    E = np.concatenate(rows)
-    np.save(out, E.mean(axis=0).astype(np.float32))
+    mu = np.concatenate(rows).mean(axis=0).astype(np.float32)
+    m.close()
+    bb = 2.8
+    for it in range(2):                                   # margins move a little once the bias moves: two passes
+        synth.write_gguf(path, n_layers, "f32", seed, blank_bias=bb, R=None, mu=mu)
+        m = O.Model(path)
+        marg = []
+        for stream in (100, 101):
+            s = O.Stream(m, R, trace=True)
+            s.push(synth.synth_pcm(stream, secs))
+            marg.append(first_eval_margins(s))
+        m.close()
+        marg = np.concatenate(marg)
+        print(f"  pass {it}: blank_bias {bb:.3f} emit frac {np.mean(marg > 0):.2f} q10/50/90 {np.round(np.quantile(marg, [.1, .5, .9]), 2)}")
+        bb = float(bb + np.quantile(marg, 0.75))
+    np.savez(out, mu=mu, blank_bias=np.float32(bb))
     os.remove(path)
-    print(out, E.shape, "mean |mu|", float(np.abs(E.mean(axis=0)).mean()))
+    print(out, "blank_bias", bb)
 
 
 if __name__ == "__main__":

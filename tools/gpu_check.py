@@ -23,8 +23,8 @@ def main():
     L = int(os.environ.get("L", 2)); R = int(os.environ.get("R", 1)); compute = int(os.environ.get("COMPUTE", 1))
     kv = int(os.environ.get("KV", 0)); nstream = int(os.environ.get("NS", 3)); secs = float(os.environ.get("SECS", 3.0))
     wtype = os.environ.get("WTYPE", "f32")
-    mm = {1: O.MM_REF, 2: O.MM_F16, 3: O.MM_BF16, 4: O.MM_Q8FAST}[compute]
-    path = synth.cached_model(wtype, L)
+    mm = {0: (O.MM_Q8FAST if wtype == "q8_0" else O.MM_REF), 1: O.MM_REF, 2: O.MM_F16, 3: O.MM_BF16, 4: O.MM_Q8FAST}[compute]
+    path = synth.cached_model(wtype, L, R=R)
     t0 = time.time()
     eng = nsb200.Engine(path, right_context=R, max_streams=nstream, compute=compute, kv_dtype=kv)
     print(f"engine up in {time.time()-t0:.1f}s  layers={eng.n_layers} T={eng.T} compute={eng.compute}", flush=True)

@@ -11,7 +11,7 @@ def main():
     L = 2
     ok = True
     for wtype, compute, mm in (("f32", 2, O.MM_F16), ("f32", 3, O.MM_BF16), ("f16", 0, O.MM_REF), ("q8_0", 0, O.MM_Q8FAST)):
-        path = synth.cached_model(wtype, L)
+        path = synth.cached_model(wtype, L, R=0)
         eng = nsb200.Engine(path, right_context=0, max_streams=1, compute=compute)
         om = O.Model(path, mm)
         rng = np.random.default_rng(0)

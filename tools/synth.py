@@ -36,6 +36,7 @@ D_MODEL, D_FF, N_HEADS, D_HEAD = 1024, 4096, 8, 128
 N_MELS, N_BINS, WIN = 128, 257, 400
 VOCAB, HID, JOINT = 1025, 640, 640
 KSIZE = 9
+BRANCH_GAIN = float(os.environ.get("NSB_BRANCH_GAIN", 0.15))
 ENC_GAIN = float(os.environ.get("NSB_ENC_GAIN", 4.0))
 PRED_GAIN = float(os.environ.get("NSB_PRED_GAIN", 1.0))
 SUB_CH, SUB_W = 256, 17
@@ -68,14 +69,14 @@ def tensor_specs(n_layers: int):
         yield p + "norm_feed_forward1.weight", (D_MODEL,), ("g", 0)
         yield p + "norm_feed_forward1.bias", (D_MODEL,), ("b", 0)
         yield p + "feed_forward1.linear1.weight", (D_FF, D_MODEL), ("w", D_MODEL)
-        yield p + "feed_forward1.linear2.weight", (D_MODEL, D_FF), ("w", D_FF)
+        yield p + "feed_forward1.linear2.weight", (D_MODEL, D_FF), ("wbr", D_FF)
         yield p + "norm_self_att.weight", (D_MODEL,), ("g", 0)
         yield p + "norm_self_att.bias", (D_MODEL,), ("b", 0)
         yield p + "self_attn.linear_q.weight", (D_MODEL, D_MODEL), ("w", D_MODEL)
         yield p + "self_attn.linear_k.weight", (D_MODEL, D_MODEL), ("w", D_MODEL)
         yield p + "self_attn.linear_v.weight", (D_MODEL, D_MODEL), ("w", D_MODEL)
         yield p + "self_attn.linear_pos.weight", (D_MODEL, D_MODEL), ("w", D_MODEL)
-        yield p + "self_attn.linear_out.weight", (D_MODEL, D_MODEL), ("w", D_MODEL)
+        yield p + "self_attn.linear_out.weight", (D_MODEL, D_MODEL), ("wbr", D_MODEL)
         yield p + "self_attn.pos_bias_u", (N_HEADS, D_HEAD), ("b", 0)
         yield p + "self_attn.pos_bias_v", (N_HEADS, D_HEAD), ("b", 0)
         yield p + "norm_conv.weight", (D_MODEL,), ("g", 0)
@@ -84,11 +85,11 @@ def tensor_specs(n_layers: int):
         yield p + "conv.depthwise_conv.weight", (D_MODEL, 1, KSIZE), ("w", KSIZE)
         yield p + "conv.batch_norm.weight", (D_MODEL,), ("g", 0)
         yield p + "conv.batch_norm.bias", (D_MODEL,), ("b", 0)
-        yield p + "conv.pointwise_conv2.weight", (D_MODEL, D_MODEL, 1), ("w", D_MODEL)
+        yield p + "conv.pointwise_conv2.weight", (D_MODEL, D_MODEL, 1), ("wbr", D_MODEL)
         yield p + "norm_feed_forward2.weight", (D_MODEL,), ("g", 0)
         yield p + "norm_feed_forward2.bias", (D_MODEL,), ("b", 0)
         yield p + "feed_forward2.linear1.weight", (D_FF, D_MODEL), ("w", D_MODEL)
-        yield p + "feed_forward2.linear2.weight", (D_MODEL, D_FF), ("w", D_FF)
+        yield p + "feed_forward2.linear2.weight", (D_MODEL, D_FF), ("wbr", D_FF)
         yield p + "norm_out.weight", (D_MODEL,), ("g", 0)
         yield p + "norm_out.bias", (D_MODEL,), ("b", 0)
     d = "decoder.prediction."
@@ -127,11 +128,27 @@ def mel_filterbank() -> np.ndarray:
     return fb.astype(np.float32)
 
 
+def load_calibration(seed: int, n_layers: int, R):
+    """(mu [1024] or None, blank_bias) for a (seed, n_layers, right_context) model; see tools/calibrate.py."""
+    if R is not None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "calib", f"cal_s{seed}_L{n_layers}_R{R}.npz")
+        if os.path.exists(path):
+            z = np.load(path)
+            return z["mu"].astype(np.float32), float(z["blank_bias"])
+    return None, 2.8
+
+
+_CAL_MU = None   # set by write_gguf / write_nemo_bin while generating
+
+
 def gen_tensor(name: str, shape, kind, seed: int, blank_bias: float, logit_gain: float) -> np.ndarray:
     k, fan_in = kind
     rng = np.random.default_rng([seed, zlib.crc32(name.encode())])
     if k == "w":
         return (rng.standard_normal(shape, dtype=np.float32) * np.float32(1.0 / np.sqrt(fan_in)))
+    if k == "wbr":       # last matrix of every residual branch: small gain keeps the random net close to identity,
+        # otherwise 24 random layers collapse all frames onto one direction and the output ignores the audio
+        return (rng.standard_normal(shape, dtype=np.float32) * np.float32(BRANCH_GAIN / np.sqrt(fan_in)))
     if k == "w0":        # zero-mean 3x3 filters: reject the large DC level of log-mel so frames differ
         w = rng.standard_normal(shape, dtype=np.float32)
         w -= w.mean(axis=(2, 3), keepdims=True)
@@ -141,14 +158,12 @@ def gen_tensor(name: str, shape, kind, seed: int, blank_bias: float, logit_gain:
     if k == "benc":
         # Random-weight conformers map every frame to almost the same direction (frame-to-frame
         # correlation ~0.95), which would make the RNN-T decisions ignore the audio. Cancel the
-        # common component mu (tools/calibrate.py, committed under tools/calib/) through the bias so
+        # common component mu (per latency mode; tools/calibrate.py, committed under tools/calib/) through the bias so
         # that the joint sees the per-frame variation: b = 0.1*N - W_enc @ mu.
         b = (0.1 * rng.standard_normal(shape, dtype=np.float32)).astype(np.float32)
-        mu_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "calib", f"mu_s{seed}_L{fan_in}.npy")
-        if os.path.exists(mu_path):
-            mu = np.load(mu_path).astype(np.float32)
+        if _CAL_MU is not None:
             w = gen_tensor("joint.enc.weight", (JOINT, D_MODEL), ("wenc", D_MODEL), seed, blank_bias, logit_gain)
-            b = (b - w @ mu).astype(np.float32)
+            b = (b - w @ _CAL_MU).astype(np.float32)
         return b
     if k == "wpred":
         return (rng.standard_normal(shape, dtype=np.float32) * np.float32(PRED_GAIN / np.sqrt(fan_in)))
@@ -230,7 +245,12 @@ def _wstr(f, s):
 
 
 def write_gguf(path: str, n_layers: int = 24, wtype: str = "f32", seed: int = 1234,
-               blank_bias: float = 2.8, logit_gain: float = 1.0) -> None:
+               blank_bias: float | None = None, logit_gain: float = 1.0, R=None, mu=None) -> None:
+    """R selects the committed calibration (mean encoder output + blank bias) of that latency mode."""
+    global _CAL_MU
+    cal_mu, cal_bb = load_calibration(seed, n_layers, R)
+    _CAL_MU = mu if mu is not None else cal_mu
+    blank_bias = cal_bb if blank_bias is None else blank_bias
     specs = list(tensor_specs(n_layers))
     hparams = [("nemo.n_mels", N_MELS), ("nemo.d_model", D_MODEL), ("nemo.n_heads", N_HEADS),
                ("nemo.d_head", D_HEAD), ("nemo.d_ff", D_FF), ("nemo.n_layers", n_layers),
@@ -295,7 +315,10 @@ def _prepared_size(name, shape, wtype):
 
 
 def write_nemo_bin(path: str, n_layers: int = 24, seed: int = 1234,
-                   blank_bias: float = 2.8, logit_gain: float = 1.0) -> None:
+                   blank_bias: float | None = None, logit_gain: float = 1.0, R=None) -> None:
+    global _CAL_MU
+    _CAL_MU, cal_bb = load_calibration(seed, n_layers, R)
+    blank_bias = cal_bb if blank_bias is None else blank_bias
     specs = list(tensor_specs(n_layers))
     tmp = path + ".tmp"
     with open(tmp, "wb") as f:
@@ -350,17 +373,18 @@ def sine_pcm(seconds: float, freq: float = 440.0, sr: int = 16000) -> np.ndarray
     return (np.float32(0.5) * np.sin(np.float32(2.0 * np.pi * freq) * t) * np.float32(32767.0)).astype(np.int16)
 
 
-def cached_model(kind: str, n_layers: int, seed: int = 1234, cache_dir: str | None = None) -> str:
-    """Materialise (once) and return the path of a synthetic model file. kind: f32|f16|q8_0|nemo."""
+def cached_model(kind: str, n_layers: int, seed: int = 1234, cache_dir: str | None = None, R: int | None = 1) -> str:
+    """Materialise (once) and return the path of a synthetic model file. kind: f32|f16|q8_0|nemo.
+    R = latency mode whose calibration (tools/calib/) shapes joint.enc.bias and the blank bias."""
     cache_dir = cache_dir or os.environ.get("NSB_SYNTH_DIR", "/tmp/nsb200_synth")
     os.makedirs(cache_dir, exist_ok=True)
     ext = "bin" if kind == "nemo" else "gguf"
-    path = os.path.join(cache_dir, f"synth_s{seed}_L{n_layers}_{kind}.{ext}")
+    path = os.path.join(cache_dir, f"synth_s{seed}_L{n_layers}_R{R}_{kind}.{ext}")
     if not os.path.exists(path):
         if kind == "nemo":
-            write_nemo_bin(path, n_layers, seed)
+            write_nemo_bin(path, n_layers, seed, R=R)
         else:
-            write_gguf(path, n_layers, kind, seed)
+            write_gguf(path, n_layers, kind, seed, R=R)
     return path
 
 
@@ -370,11 +394,12 @@ def main():
     ap.add_argument("--type", default="f32", choices=["f32", "f16", "q8_0", "nemo"])
     ap.add_argument("--layers", type=int, default=24)
     ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--right-context", type=int, default=1)
     a = ap.parse_args()
     if a.type == "nemo":
-        write_nemo_bin(a.out, a.layers, a.seed)
+        write_nemo_bin(a.out, a.layers, a.seed, R=a.right_context)
     else:
-        write_gguf(a.out, a.layers, a.type, a.seed)
+        write_gguf(a.out, a.layers, a.type, a.seed, R=a.right_context)
     print(a.out, os.path.getsize(a.out))
 
 
