@@ -47,9 +47,16 @@ std::vector<float> read_matrix_f32(const GgufFile& g, const std::string& name) {
     return out;
 }
 
+// Host -> device copy that is COMPLETE on return. cudaMemcpy from pageable memory may return while the DMA from the
+// staging buffer is still in flight, and the engine's kernels run on a non-blocking stream that is not ordered after
+// the legacy stream -- so every load-time / operator upload goes through here.
+void h2d_sync(void* dst, const void* src, size_t bytes) {
+    NSB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    NSB_CUDA(cudaDeviceSynchronize());
+}
 void upload(DevBuf& d, const std::vector<float>& h) {
     d.alloc(h.size() * sizeof(float), false);
-    NSB_CUDA(cudaMemcpy(d.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    h2d_sync(d.p, h.data(), h.size() * sizeof(float));
 }
 
 // positional table row for relative position p (src/nemo-ggml.cpp:17-32)
@@ -514,8 +521,8 @@ void Engine::bench_prepare(int n_streams, const int16_t* pcm, int samples_per_st
         if (!ready(ids[b])) throw std::runtime_error("bench: stream not ready after staging");
         stage_row(hs_[ids[b]], T, rl_, hp + (size_t)b * rl_); hsl[b] = ids[b];
     }
-    NSB_CUDA(cudaMemcpy(bench_pcm_.p, hp, (size_t)n_streams * rl_ * 2, cudaMemcpyHostToDevice));
-    NSB_CUDA(cudaMemcpy(d_slot_.p, hsl, (size_t)n_streams * 4, cudaMemcpyHostToDevice));
+    h2d_sync(bench_pcm_.p, hp, (size_t)n_streams * rl_ * 2);
+    h2d_sync(d_slot_.p, hsl, (size_t)n_streams * 4);
     bench_B_ = n_streams;
 }
 
@@ -625,7 +632,7 @@ long long Engine::op_logmel(const int16_t* pcm, int n_streams, int n_samples, fl
     std::vector<int16_t> h((size_t)n_streams * row, 0);
     for (int s = 0; s < n_streams; ++s) memcpy(&h[(size_t)s * row + 1 + N_FFT / 2], pcm + (size_t)s * n_samples, (size_t)n_samples * 2);
     DevBuf d_in, d_out; d_in.alloc(h.size() * 2, false); d_out.alloc((size_t)n_streams * n_frames * N_MELS * 4, false);
-    NSB_CUDA(cudaMemcpy(d_in.p, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+    h2d_sync(d_in.p, h.data(), h.size() * 2);
     launch_logmel(d_in.as<int16_t>(), row, n_streams, n_frames, window_.as<float>(), cos_t_.as<float>(), sin_t_.as<float>(), fb_t_.as<float>(),
                   d_out.as<float>(), (size_t)n_frames * N_MELS, st_);
     count_launch();
@@ -640,7 +647,7 @@ long long Engine::op_gemm(const std::string& name, const float* xh, int rows, fl
     const Weight& W = *it->second;
     if (cap < (size_t)rows * W.n_out) return -(long long)((size_t)rows * W.n_out);
     DevBuf dx, da, dy; dx.alloc((size_t)rows * W.n_in * 4, false); dy.alloc((size_t)rows * W.n_out * 4, false);
-    NSB_CUDA(cudaMemcpy(dx.p, xh, dx.bytes, cudaMemcpyHostToDevice));
+    h2d_sync(dx.p, xh, dx.bytes);
     const void* A = dx.p;
     if (act_type() != OUT_F32) { da.alloc((size_t)rows * W.n_in * 2, false); convert_to(dx.as<float>(), da.p, (size_t)rows * W.n_in, act_type(), st_); A = da.p; }
     gemm(A, W.n_in, W, rows, nullptr, dy.p, W.n_out, EPI_NONE, 1.f, OUT_F32);

@@ -23,7 +23,7 @@ struct DevBuf {
         if (p) { cudaFree(p); p = nullptr; }
         bytes = n; if (!n) return;
         NSB_CUDA(cudaMalloc(&p, n));
-        if (zero) NSB_CUDA(cudaMemset(p, 0, n));
+        if (zero) { NSB_CUDA(cudaMemset(p, 0, n)); NSB_CUDA(cudaDeviceSynchronize()); }   // legacy-stream memset must not race the engine stream
     }
     template <class T> T* as() const { return (T*)p; }
 };
