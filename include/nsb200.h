@@ -118,6 +118,9 @@ int nsb_bench_step(nsb_engine* e, float* ms);
 #define NSB_PROFILE_CLASSES 8
 int nsb_bench_profile(nsb_engine* e, float* ms_per_class, int* launches_per_class, float* total_ms);
 
+/* cudaProfilerStart / cudaProfilerStop, so that `ncu --profile-from-start off` captures only the steady-state steps */
+int nsb_profiler_range(int on);
+
 /* ---- parity / debug taps (host buffers) --------------------------------------------------
  * When enabled, the engine keeps the tensors of the LAST step: names
  *   "mel" [B, M, 128]  "sub" [B*T, 1024]  "layer.<l>" [B*T, 1024]  "enc" [B*T, 1024]

@@ -42,7 +42,7 @@ EXPORTS = ["nsb_gguf_probe", "nsb_default_config", "nsb_engine_create", "nsb_eng
            "nsb_engine_vocab_size", "nsb_engine_vocab", "nsb_engine_chunk_samples", "nsb_engine_shift_samples", "nsb_engine_compute",
            "nsb_stream_open", "nsb_stream_close", "nsb_stream_reset", "nsb_stream_push_pcm", "nsb_stream_ready", "nsb_engine_step",
            "nsb_engine_drain", "nsb_stream_pop_tokens", "nsb_stream_chunks", "nsb_detokenize", "nsb_engine_get_stats",
-           "nsb_bench_prepare", "nsb_bench_step", "nsb_bench_profile", "nsb_debug_enable", "nsb_debug_get", "nsb_debug_get_cache", "nsb_op_logmel",
+           "nsb_bench_prepare", "nsb_bench_step", "nsb_bench_profile", "nsb_profiler_range", "nsb_debug_enable", "nsb_debug_get", "nsb_debug_get_cache", "nsb_op_logmel",
            "nsb_op_gemm"]
 
 
@@ -85,6 +85,7 @@ def lib():
         L.nsb_bench_prepare.argtypes = [vp, ci, _i16p, ci, ci]
         L.nsb_bench_step.argtypes = [vp, C.POINTER(C.c_float)]
         L.nsb_bench_profile.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_float)]
+        L.nsb_profiler_range.argtypes = [ci]
         L.nsb_debug_enable.argtypes = [vp, ci]
         L.nsb_debug_get.argtypes = [vp, C.c_char_p, _f32p, C.c_size_t]
         L.nsb_debug_get_cache.argtypes = [vp, ci, ci, ci, _f32p, C.c_size_t]
@@ -110,11 +111,12 @@ class Engine:
     """One engine per GPU: weights + per-stream caches resident in HBM; streams are slots."""
 
     def __init__(self, gguf_path: str, right_context: int = 0, max_streams: int = 1, compute: int = COMPUTE_AUTO,
-                 kv_dtype: int = KV_F32, device: int = 0):
+                 kv_dtype: int = KV_F32, device: int = 0, cuda_graph: bool = True):
         cfg = EngineConfig()
         lib().nsb_default_config(C.byref(cfg))
         cfg.device, cfg.compute, cfg.kv_dtype = device, compute, kv_dtype
         cfg.att_right_context, cfg.max_streams = right_context, max_streams
+        cfg.use_cuda_graph = 1 if cuda_graph else 0
         h = C.c_void_p()
         _check(lib().nsb_engine_create(gguf_path.encode(), C.byref(cfg), C.byref(h)))
         self.h = h

@@ -3,6 +3,8 @@
 #include <cstring>
 #include <string>
 
+#include <cuda_profiler_api.h>
+
 #include "engine.h"
 
 using nsb::Engine;
@@ -51,7 +53,7 @@ void nsb_default_config(nsb_engine_config* c) {
     if (!c) return;
     memset(c, 0, sizeof(*c));
     c->device = 0; c->compute = NSB_COMPUTE_AUTO; c->kv_dtype = NSB_KV_F32; c->att_right_context = 0;   // default_config(): pure causal (nemo-stream.h:103-105)
-    c->max_streams = 1; c->use_cuda_graph = 0;
+    c->max_streams = 1; c->use_cuda_graph = 1;
 }
 
 int nsb_engine_create(const char* path, const nsb_engine_config* cfg, nsb_engine** out) {
@@ -108,6 +110,8 @@ int nsb_bench_step(nsb_engine* e, float* ms) {
 int nsb_bench_profile(nsb_engine* e, float* ms_per_class, int* launches_per_class, float* total_ms) {
     if (!e || !ms_per_class || !launches_per_class) return fail(NSB_ERR_ARG, "bad argument");
     NSB_TRY const float t = e->impl->bench_profile(ms_per_class, launches_per_class); if (total_ms) *total_ms = t; return NSB_OK; NSB_CATCH }
+
+int nsb_profiler_range(int on) { return (on ? cudaProfilerStart() : cudaProfilerStop()) == cudaSuccess ? NSB_OK : NSB_ERR_CUDA; }
 
 int nsb_debug_enable(nsb_engine* e, int on) { if (!e) return fail(NSB_ERR_ARG, "null engine"); NSB_TRY e->impl->debug_enable(on != 0); return NSB_OK; NSB_CATCH }
 int nsb_debug_get(nsb_engine* e, const char* name, float* out, size_t cap) {

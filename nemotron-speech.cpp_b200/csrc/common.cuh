@@ -39,7 +39,8 @@ enum Epi : int {
     EPI_NONE = 0,      // C = acc (+bias)
     EPI_RELU = 1,      // C = relu(acc + bias)
     EPI_SILU = 2,      // C = silu(acc)
-    EPI_RESID = 3      // C (f32, in place) += alpha * acc
+    EPI_RESID = 3,     // C (f32, in place) += alpha * acc
+    EPI_PARTIAL = 4    // split-K: C[z][M][N] (f32 workspace) = partial acc of k-slice z; reduced by the following LayerNorm kernel
 };
 enum OutType : int { OUT_F32 = 0, OUT_F16 = 1, OUT_BF16 = 2 };
 

@@ -18,6 +18,8 @@ namespace nsb {
 // implemented in gemm_tc.cu (tcgen05 / TMEM / TMA)
 void launch_gemm_tc(const GemmArgs& a, int in_type /*OUT_F16 | OUT_BF16*/, cudaStream_t st);
 
+constexpr int MAX_SPLITS = 8;
+
 namespace {
 
 __global__ void convert_kernel(const float* __restrict__ in, void* __restrict__ out, size_t n, int out_type) {
@@ -114,6 +116,7 @@ Engine::Engine(const std::string& path, const nsb_engine_config& cfg) : cfg_(cfg
 Engine::~Engine() {
     cudaSetDevice(device_);
     cudaDeviceSynchronize();
+    for (auto& g : graphs_) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
@@ -247,6 +250,7 @@ void Engine::alloc_state() {
     qkv_.alloc(Mrows * 3 * D_MODEL * 4);
     pw1_.alloc(Mrows * 2 * D_MODEL * 4);
     encp_.alloc(Mrows * JOINT * 4);
+    part_.alloc((size_t)MAX_SPLITS * std::min<size_t>(Mrows, 1024) * D_MODEL * 4);       // split-K workspace (only used when rows <= 1024)
     out_tok_.alloc((size_t)S * MAX_SYMBOLS * T * 4); out_cnt_.alloc((size_t)S * 4);
     frame_idx_.alloc((size_t)S * 4); sym_cnt_.alloc((size_t)S * 4); need_lstm_.alloc((size_t)S * 4);
     const size_t parts = decode_scratch_parts(S);
@@ -301,6 +305,23 @@ void Engine::gemm(const void* A, long long lda, const Weight& W, int M, const fl
     count_launch();
 }
 
+void Engine::gemm_residual(const void* A, long long lda, const Weight& W, int M, float* x, float alpha) {
+    // The N = 1024 GEMMs have few output tiles: with <= 1024 token rows the K dimension is split across CTAs so that
+    // >= ~1 wave of SMs pulls weights; the fp32 partials land in part_ and the NEXT LayerNorm kernel adds them to x.
+    int splits = 1;
+    if (compute != NSB_COMPUTE_F32 && M <= 1024) {
+        const int tiles = ((M + 127) / 128) * (W.n_out / (W.n_in >= 4096 ? 64 : 32));
+        const int nk = W.n_in / 64;
+        while (splits < MAX_SPLITS && tiles * splits < 120 && nk % (splits * 2) == 0 && nk / (splits * 2) >= 2) splits *= 2;
+    }
+    if (splits == 1) { gemm(A, lda, W, M, nullptr, x, D_MODEL, EPI_RESID, alpha, OUT_F32); return; }
+    GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.M = M; a.N = W.n_out; a.K = W.n_in; a.C = part_.p; a.ldc = D_MODEL;
+    a.epi = EPI_PARTIAL; a.out_type = OUT_F32; a.splits = splits;
+    { ProfScope ps(this, PC_GEMM); launch_gemm_tc(a, act_type(), st_); }
+    count_launch();
+    pending_.part = part_.as<float>(); pending_.n = splits; pending_.alpha = alpha;
+}
+
 // ------------------------------------------------------------------------------------------
 // streams (host bookkeeping only; all arithmetic is on the device)
 // ------------------------------------------------------------------------------------------
@@ -347,7 +368,7 @@ int Engine::step() {
     NSB_CUDA(cudaMemcpyAsync(d_pcm_.p, hp, (size_t)B * rl_ * 2, cudaMemcpyHostToDevice, st_));
     NSB_CUDA(cudaMemcpyAsync(d_slot_.p, hsl, (size_t)B * 4, cudaMemcpyHostToDevice, st_));
     NSB_CUDA(cudaEventRecord(ev0_, st_));
-    run_step_kernels(B, d_pcm_.as<int16_t>());
+    run_step(B, d_pcm_.as<int16_t>());
     NSB_CUDA(cudaEventRecord(ev1_, st_));
     NSB_CUDA(cudaMemcpyAsync(h_cnt_.p, out_cnt_.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st_));
     NSB_CUDA(cudaMemcpyAsync(h_tok_.p, out_tok_.p, (size_t)B * MAX_SYMBOLS * T * 4, cudaMemcpyDeviceToHost, st_));
@@ -391,6 +412,26 @@ std::string Engine::detok(const int32_t* t, int n) const {
     return r;
 }
 
+void Engine::run_step(int B, const int16_t* d_pcm) {
+    if (!cfg_.use_cuda_graph || debug_ || profiling_) { run_step_kernels(B, d_pcm); return; }
+    StepGraph& g = graphs_[{B, (const void*)d_pcm}];
+    if (!g.exec) {
+        const long long before = stats.kernel_launches;
+        cudaGraph_t graph = nullptr;
+        NSB_CUDA(cudaStreamBeginCapture(st_, cudaStreamCaptureModeRelaxed));
+        try { run_step_kernels(B, d_pcm); }
+        catch (...) { cudaStreamEndCapture(st_, &graph); if (graph) cudaGraphDestroy(graph); graphs_.erase({B, (const void*)d_pcm}); throw; }
+        NSB_CUDA(cudaStreamEndCapture(st_, &graph));
+        const cudaError_t err = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (err != cudaSuccess) { graphs_.erase({B, (const void*)d_pcm}); throw CudaError(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(err)); }
+        g.launches = stats.kernel_launches - before;
+        stats.kernel_launches = before;                                         // capture launched nothing yet
+    }
+    NSB_CUDA(cudaGraphLaunch(g.exec, st_));
+    stats.kernel_launches += g.launches;
+}
+
 // ------------------------------------------------------------------------------------------
 // THE HOT PATH: one batched chunk for B streams, PCM already in HBM, tokens left in HBM.
 // ------------------------------------------------------------------------------------------
@@ -432,14 +473,16 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
     // L: cache-aware conformer layers
     const long long kv_slot_stride = (long long)n_layers * 2 * (ATT_L + T) * D_MODEL;
     const long long cc_slot_stride = (long long)n_layers * (CONV_K - 1) * D_MODEL;
-    { ProfScope ps(this, PC_LAYERNORM);
-      launch_layernorm(x, rows, layers_[0].ln[0].as<float>(), layers_[0].ln[1].as<float>(), a_.p, at, st_); count_launch(); }
-    auto ln = [&](const float* g_, const float* b_) { ProfScope ps(this, PC_LAYERNORM); launch_layernorm(x, rows, g_, b_, a_.p, at, st_); count_launch(); };
+    pending_ = PartialSum{};
+    auto ln = [&](const float* g_, const float* b_) {
+        ProfScope ps(this, PC_LAYERNORM); launch_layernorm(x, rows, g_, b_, a_.p, at, pending_, st_); count_launch(); pending_ = PartialSum{};
+    };
+    ln(layers_[0].ln[0].as<float>(), layers_[0].ln[1].as<float>());
     for (int l = 0; l < n_layers; ++l) {
         LayerW& L = layers_[l];
         // FFN1: x += 0.5 * W2 silu(W1 LN(x))                                        (nemo-stream.cpp:603-606)
         gemm(a_.p, D_MODEL, L.ff1a, rows, nullptr, big_.p, D_FF, EPI_SILU, 1.f, at);
-        gemm(big_.p, D_FF, L.ff1b, rows, nullptr, x, D_MODEL, EPI_RESID, 0.5f, OUT_F32);
+        gemm_residual(big_.p, D_FF, L.ff1b, rows, x, 0.5f);
         // MHSA over the ring cache                                                  (:609-615)
         ln(L.ln[2].as<float>(), L.ln[3].as<float>());
         gemm(a_.p, D_MODEL, L.qkv, rows, nullptr, qkv_.p, 3 * D_MODEL, EPI_NONE, 1.f, OUT_F32);
@@ -453,7 +496,7 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
             aa.slot_of_b = slot; aa.ring_pos = ring_pos_.as<int>(); aa.valid_len = valid_len_.as<int>(); aa.B = B; aa.T = T;
             ProfScope ps(this, PC_ATTENTION); launch_attention(aa, st_); count_launch();
         }
-        gemm(a_.p, D_MODEL, L.out, rows, nullptr, x, D_MODEL, EPI_RESID, 1.f, OUT_F32);
+        gemm_residual(a_.p, D_MODEL, L.out, rows, x, 1.f);
         // conv module                                                               (:618-651)
         ln(L.ln[4].as<float>(), L.ln[5].as<float>());
         gemm(a_.p, D_MODEL, L.pw1, rows, nullptr, pw1_.p, 2 * D_MODEL, EPI_NONE, 1.f, OUT_F32);
@@ -463,17 +506,17 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
             ca.out = a_.p; ca.out_type = at; ca.slot_of_b = slot; ca.B = B; ca.T = T;
             ProfScope ps(this, PC_CONVMOD); launch_conv_module(ca, st_); count_launch();
         }
-        gemm(a_.p, D_MODEL, L.pw2, rows, nullptr, x, D_MODEL, EPI_RESID, 1.f, OUT_F32);
+        gemm_residual(a_.p, D_MODEL, L.pw2, rows, x, 1.f);
         // FFN2                                                                      (:654-657)
         ln(L.ln[6].as<float>(), L.ln[7].as<float>());
         gemm(a_.p, D_MODEL, L.ff2a, rows, nullptr, big_.p, D_FF, EPI_SILU, 1.f, at);
-        gemm(big_.p, D_FF, L.ff2b, rows, nullptr, x, D_MODEL, EPI_RESID, 0.5f, OUT_F32);
+        gemm_residual(big_.p, D_FF, L.ff2b, rows, x, 0.5f);
         // norm_out (:659) fused with the next layer's norm_feed_forward1
         const bool last = l + 1 == n_layers;
         { ProfScope ps(this, PC_LAYERNORM);
           launch_layernorm2(x, rows, L.ln[8].as<float>(), L.ln[9].as<float>(), last ? nullptr : layers_[l + 1].ln[0].as<float>(),
-                            last ? nullptr : layers_[l + 1].ln[1].as<float>(), last ? nullptr : a_.p, at, st_);
-          count_launch(); }
+                            last ? nullptr : layers_[l + 1].ln[1].as<float>(), last ? nullptr : a_.p, at, pending_, st_);
+          count_launch(); pending_ = PartialSum{}; }
         if (debug_) NSB_CUDA(cudaMemcpyAsync(dbg_layers_.as<float>() + (size_t)l * dbg_B_ * T * D_MODEL, x, (size_t)rows * D_MODEL * 4,
                                              cudaMemcpyDeviceToDevice, st_));
     }
@@ -530,7 +573,7 @@ float Engine::bench_step() {
     if (!bench_B_) throw std::runtime_error("bench_step before bench_prepare");
     NSB_CUDA(cudaSetDevice(device_));
     NSB_CUDA(cudaEventRecord(ev0_, st_));
-    run_step_kernels(bench_B_, bench_pcm_.as<int16_t>());
+    run_step(bench_B_, bench_pcm_.as<int16_t>());
     NSB_CUDA(cudaEventRecord(ev1_, st_));
     NSB_CUDA(cudaEventSynchronize(ev1_));
     float ms = 0.f; NSB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));

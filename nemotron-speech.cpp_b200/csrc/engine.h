@@ -95,7 +95,15 @@ private:
     void build_pos_tables(const GgufFile& g);
     void gemm(const void* A, long long lda, const Weight& W, int M, const float* bias, void* C, long long ldc, int epi, float alpha,
               int out_type);
+    // x += alpha * A W^T. Small batches: split-K into the workspace, reduction folded into the next LayerNorm (pending_).
+    void gemm_residual(const void* A, long long lda, const Weight& W, int M, float* x, float alpha);
+    PartialSum pending_{};
     void run_step_kernels(int B, const int16_t* d_pcm);      // everything between PCM-in-HBM and tokens-in-HBM
+    // run_step_kernels through a CUDA graph captured once per (batch size, PCM buffer): the ~350 launches of a step become
+    // one cudaGraphLaunch (cfg.use_cuda_graph; bypassed while debug taps or per-launch profiling are on)
+    void run_step(int B, const int16_t* d_pcm);
+    struct StepGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; };
+    std::map<std::pair<int, const void*>, StepGraph> graphs_;
     void collect_tokens(int B, const std::vector<int>& batch);
     int act_type() const { return compute == NSB_COMPUTE_F32 ? OUT_F32 : (compute == NSB_COMPUTE_BF16 ? OUT_BF16 : OUT_F16); }
     size_t act_size() const { return compute == NSB_COMPUTE_F32 ? 4 : 2; }
@@ -125,7 +133,7 @@ private:
 
     // ---- step workspace (batch-compact) ----
     int rl_ = 0;                   // PCM row length per stream-step
-    DevBuf d_pcm_, d_slot_, mel_new_, c0_, dw_, pw_, x_, a_, big_, qkv_, pw1_, encp_;
+    DevBuf d_pcm_, d_slot_, mel_new_, c0_, dw_, pw_, x_, a_, big_, qkv_, pw1_, encp_, part_;
     DevBuf out_tok_, out_cnt_, frame_idx_, sym_cnt_, need_lstm_, part_val_, part_idx_, counters_;
     HostPinned h_pcm_, h_slot_, h_tok_, h_cnt_;
 

@@ -120,7 +120,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     S& s = *reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
-    const int nk = p.K / BK;
+    const int nk = p.K / BK / (int)gridDim.z;                                   // k-blocks of this split
+    const int kb0 = (int)blockIdx.z * nk;
     constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
     constexpr uint32_t STAGE_BYTES = (BM + BN) * BK * 2;
 
@@ -146,8 +147,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&s.empty[st], ph ^ 1);
                 mbar_expect_tx(&s.full[st], STAGE_BYTES);
-                tma_load_2d(s.a[st], &tmA, &s.full[st], kb * BK, m0);
-                tma_load_2d(s.b[st], &tmB, &s.full[st], kb * BK, n0);
+                tma_load_2d(s.a[st], &tmA, &s.full[st], (kb0 + kb) * BK, m0);
+                tma_load_2d(s.b[st], &tmB, &s.full[st], (kb0 + kb) * BK, n0);
             }
         }
     } else if (warp == 1) {
@@ -186,7 +187,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int i = 0; i < 16; ++i) v[i] += p.bias[n + i];
                 }
                 const size_t o = (size_t)row * p.ldc + n;
-                if (p.epi == EPI_RESID) {
+                if (p.epi == EPI_PARTIAL) {
+                    float4* dst = reinterpret_cast<float4*>((float*)p.C + (size_t)blockIdx.z * p.M * p.ldc + o);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                } else if (p.epi == EPI_RESID) {
                     float4* dst = reinterpret_cast<float4*>((float*)p.C + o);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -268,7 +273,7 @@ void launch_cfg(const GemmArgs& a, int fmt, cudaStream_t st) {
     const CUtensorMap tmA = make_map(a.A, a.M, a.K, a.lda, BM, fmt);
     const CUtensorMap tmB = make_map(a.W, a.N, a.K, a.K, BN, fmt);
     TcParams p{a.M, a.N, a.K, a.bias, a.C, a.ldc, a.epi, a.alpha, a.out_type, fmt};
-    dim3 grid(a.N / BN, (a.M + BM - 1) / BM);
+    dim3 grid(a.N / BN, (a.M + BM - 1) / BM, a.splits);
     gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
     NSB_CUDA(cudaGetLastError());
 }
@@ -282,6 +287,11 @@ void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
         throw CudaError("gemm_tc: unsupported shape (need K % 64 == 0, N % 32 == 0, aligned rows)");
     const int fmt = in_type == OUT_BF16 ? 1 : 0;
     const int tiles_m = (a.M + BM - 1) / BM;
+    if (a.splits > 1) {
+        if (a.epi != EPI_PARTIAL || (a.K / BK) % a.splits != 0) throw CudaError("gemm_tc: bad split-K request");
+        if (a.N % 64 == 0 && a.K >= 4096) launch_cfg<64, 6>(a, fmt, st); else launch_cfg<32, 8>(a, fmt, st);
+        return;
+    }
     // pick the widest N tile that still yields >= ~1 wave of CTAs (weight streaming needs many SMs pulling)
     if (a.N % 128 == 0 && (long long)tiles_m * (a.N / 128) >= 120) launch_cfg<128, 4>(a, fmt, st);
     else if (a.N % 64 == 0 && (long long)tiles_m * (a.N / 64) >= 120) launch_cfg<64, 6>(a, fmt, st);

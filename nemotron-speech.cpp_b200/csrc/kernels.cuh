@@ -34,14 +34,17 @@ struct GemmArgs {
     const float* bias = nullptr;  // [N] or null
     void* C = nullptr; long long ldc = 0;
     int epi = EPI_NONE; float alpha = 1.0f; int out_type = OUT_F32;
+    int splits = 1;               // split-K factor (EPI_PARTIAL only): C is a [splits][M][N] f32 workspace
 };
 void launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
 
 // ---------------------------------------------------------------- layer kernels (kernels_layer.cu)
-void launch_layernorm(const float* x, int rows, const float* g, const float* b, void* y, int out_type, cudaStream_t st);
+// Pending split-K reduction folded into a LayerNorm kernel: x += alpha * sum_s part[s] (fixed order => deterministic)
+struct PartialSum { const float* part = nullptr; int n = 0; float alpha = 0.f; };
+void launch_layernorm(float* x, int rows, const float* g, const float* b, void* y, int out_type, const PartialSum& ps, cudaStream_t st);
 // y1 = LN(x; g1,b1) written back to x (f32) AND y2 = LN(y1; g2,b2) written as out_type  (norm_out fused with next norm_ff1)
 void launch_layernorm2(float* x, int rows, const float* g1, const float* b1, const float* g2, const float* b2, void* y2,
-                       int out_type, cudaStream_t st);
+                       int out_type, const PartialSum& ps, cudaStream_t st);
 
 struct AttnArgs {
     const float* qkv;             // [M][3072] f32 (q | k | v)

@@ -40,6 +40,7 @@ struct DecSmem {
     float w_val[NW][GS]; int w_idx[NW][GS];
     int list[MAXB];                  // compacted stream list of the current phase
     int warp_cnt[NW];
+    int g_slot[GS], g_aux[GS];       // per-group metadata hoisted out of the staging loops (slot; prev_token or frame row)
     int n_list;
 };
 
@@ -105,11 +106,14 @@ __device__ void lstm_phase(const DecodeArgs& a, DecSmem& sm, int layer, int n, i
     const int g0 = p.group * GS, gn = min(GS, n - g0);
     const int upb = (HID + p.n_rs - 1) / p.n_rs, u0 = min(HID, p.rs * upb), u1 = min(HID, u0 + upb);
     if (u0 >= u1) return;
-    for (int e = tid; e < gn * HID; e += NT) {                                    // stage x and h
-        const int g = e / HID, k = e % HID, slot = a.slot_of_b[sm.list[g0 + g]];
-        sm.xs[g][k] = layer == 0 ? __ldg(a.w.embed + (size_t)a.s.prev_token[slot] * HID + k)     // nemo-stream.cpp:825-828
-                                 : a.s.cand_h[(size_t)slot * 2 * HID + k];                       // layer-1 input = layer-0 h'
-        sm.hs[g][k] = a.s.h[(size_t)slot * 2 * HID + layer * HID + k];
+    if (tid < gn) { const int slot = a.slot_of_b[sm.list[g0 + tid]]; sm.g_slot[tid] = slot; sm.g_aux[tid] = a.s.prev_token[slot]; }
+    __syncthreads();
+    for (int g = 0; g < gn; ++g) {                                                // stage x and h (independent coalesced loads)
+        const int slot = sm.g_slot[g];
+        const float* xsrc = layer == 0 ? a.w.embed + (size_t)sm.g_aux[g] * HID                   // nemo-stream.cpp:825-828
+                                       : a.s.cand_h + (size_t)slot * 2 * HID;                    // layer-1 input = layer-0 h'
+        const float* hsrc = a.s.h + (size_t)slot * 2 * HID + layer * HID;
+        for (int k = tid; k < HID; k += NT) { sm.xs[g][k] = xsrc[k]; sm.hs[g][k] = hsrc[k]; }
     }
     __syncthreads();
     for (int ub = u0; ub < u1; ub += UB) {
@@ -129,7 +133,7 @@ __device__ void lstm_phase(const DecodeArgs& a, DecSmem& sm, int layer, int n, i
         }
         __syncthreads();
         for (int e = tid; e < gn * nu; e += NT) {
-            const int g = e / nu, uu = e % nu, slot = a.slot_of_b[sm.list[g0 + g]];
+            const int g = e / nu, uu = e % nu, slot = sm.g_slot[g];
             const float ig = sigmoid_exact(sm.gates[g][0 * UB + uu]), fg = sigmoid_exact(sm.gates[g][1 * UB + uu]);
             const float gg = tanhf(sm.gates[g][2 * UB + uu]), og = sigmoid_exact(sm.gates[g][3 * UB + uu]);
             const size_t o = (size_t)slot * 2 * HID + layer * HID + ub + uu;
@@ -148,9 +152,11 @@ __device__ void pred_phase(const DecodeArgs& a, DecSmem& sm, int n, int nblk, in
     const int g0 = p.group * GS, gn = min(GS, n - g0);
     const int rpb = (JOINT + p.n_rs - 1) / p.n_rs, j0 = min(JOINT, p.rs * rpb), j1 = min(JOINT, j0 + rpb);
     if (j0 >= j1) return;
-    for (int e = tid; e < gn * HID; e += NT) {
-        const int g = e / HID, k = e % HID, slot = a.slot_of_b[sm.list[g0 + g]];
-        sm.xs[g][k] = a.s.cand_h[(size_t)slot * 2 * HID + HID + k];
+    if (tid < gn) sm.g_slot[tid] = a.slot_of_b[sm.list[g0 + tid]];
+    __syncthreads();
+    for (int g = 0; g < gn; ++g) {
+        const float* src = a.s.cand_h + (size_t)sm.g_slot[g] * 2 * HID + HID;
+        for (int k = tid; k < HID; k += NT) sm.xs[g][k] = src[k];
     }
     __syncthreads();
     for (int j = j0 + warp; j < j1; j += NW) {
@@ -161,7 +167,7 @@ __device__ void pred_phase(const DecodeArgs& a, DecSmem& sm, int n, int nblk, in
         for (int g = 0; g < GS; ++g) acc[g] = g < gn ? dot_smem(w, sm.xs[g], lane) : 0.f;
         const float tot = reduce16(acc, lane);
         const int g = (lane >> 1) & 15;
-        if (!(lane & 1) && g < gn) a.s.dec_proj[(size_t)a.slot_of_b[sm.list[g0 + g]] * JOINT + j] = tot + bias;
+        if (!(lane & 1) && g < gn) a.s.dec_proj[(size_t)sm.g_slot[g] * JOINT + j] = tot + bias;
     }
 }
 
@@ -172,9 +178,11 @@ __device__ void joint_phase(const DecodeArgs& a, DecSmem& sm, int n, int nblk, i
     if (p.group >= p.n_groups) return;
     const int g0 = p.group * GS, gn = min(GS, n - g0);
     const int vpb = (VOCAB + p.n_rs - 1) / p.n_rs, v0 = min(VOCAB, p.rs * vpb), v1 = min(VOCAB, v0 + vpb);
-    for (int e = tid; e < gn * JOINT; e += NT) {                                  // z = relu(enc_proj + pred_proj)
-        const int g = e / JOINT, k = e % JOINT, b = sm.list[g0 + g], slot = a.slot_of_b[b];
-        sm.xs[g][k] = fmaxf(a.enc_proj[((size_t)b * a.T + a.frame_idx[b]) * JOINT + k] + a.s.dec_proj[(size_t)slot * JOINT + k], 0.f);
+    if (tid < gn) { const int b = sm.list[g0 + tid]; sm.g_slot[tid] = a.slot_of_b[b]; sm.g_aux[tid] = b * a.T + a.frame_idx[b]; }
+    __syncthreads();
+    for (int g = 0; g < gn; ++g) {                                                // z = relu(enc_proj + pred_proj)
+        const float* ep = a.enc_proj + (size_t)sm.g_aux[g] * JOINT; const float* dp = a.s.dec_proj + (size_t)sm.g_slot[g] * JOINT;
+        for (int k = tid; k < JOINT; k += NT) sm.xs[g][k] = fmaxf(ep[k] + dp[k], 0.f);
     }
     float bv = -INFINITY; int bi = 0x7fffffff;                                 // lane keeps the running best of stream g = (lane >> 1) & 15
     const int gl = (lane >> 1) & 15;
