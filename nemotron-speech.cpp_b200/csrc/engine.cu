@@ -230,10 +230,9 @@ void Engine::alloc_state() {
     conv_cache_.alloc((size_t)S * n_layers * (CONV_K - 1) * D_MODEL * 4);
     mel_hist_.alloc((size_t)S * PRE_CACHE * N_MELS * 4);                                 // 9 zero frames (:59-60)
     ring_pos_.alloc((size_t)S * 4); valid_len_.alloc((size_t)S * 4);
-    dec_h_.alloc((size_t)S * 2 * HID * 4); dec_c_.alloc((size_t)S * 2 * HID * 4);
-    cand_h_.alloc((size_t)S * 2 * HID * 4); cand_c_.alloc((size_t)S * 2 * HID * 4);
+    dec_h_.alloc((size_t)S * 4 * HID * 4); dec_c_.alloc((size_t)S * 4 * HID * 4);      // [S][2 parities][2 layers][640]
     dec_proj_.alloc((size_t)S * JOINT * 4);
-    prev_token_.alloc((size_t)S * 4); cand_valid_.alloc((size_t)S * 4);
+    prev_token_.alloc((size_t)S * 4); cand_valid_.alloc((size_t)S * 4); dec_par_.alloc((size_t)S * 4);
     hs_.assign(S, HostStream());
     for (int s = 0; s < S; ++s) zero_slot(s);
 
@@ -252,9 +251,7 @@ void Engine::alloc_state() {
     encp_.alloc(Mrows * JOINT * 4);
     part_.alloc((size_t)MAX_SPLITS * std::min<size_t>(Mrows, 1024) * D_MODEL * 4);       // split-K workspace (only used when rows <= 1024)
     out_tok_.alloc((size_t)S * MAX_SYMBOLS * T * 4); out_cnt_.alloc((size_t)S * 4);
-    frame_idx_.alloc((size_t)S * 4); sym_cnt_.alloc((size_t)S * 4); need_lstm_.alloc((size_t)S * 4);
-    const size_t parts = decode_scratch_parts(S);
-    part_val_.alloc(parts * 4); part_idx_.alloc(parts * 4); counters_.alloc(64);
+    dec_sync_.alloc(decode_sync_bytes(S));
     h_pcm_.alloc((size_t)S * rl_ * 2); h_slot_.alloc((size_t)S * 4);
     h_tok_.alloc((size_t)S * MAX_SYMBOLS * T * 4); h_cnt_.alloc((size_t)S * 4);
 }
@@ -266,8 +263,9 @@ void Engine::zero_slot(int s) {
     const size_t cb = (size_t)n_layers * (CONV_K - 1) * D_MODEL * 4;
     NSB_CUDA(cudaMemsetAsync((char*)conv_cache_.p + (size_t)s * cb, 0, cb, st_));
     NSB_CUDA(cudaMemsetAsync((char*)mel_hist_.p + (size_t)s * PRE_CACHE * N_MELS * 4, 0, (size_t)PRE_CACHE * N_MELS * 4, st_));
-    NSB_CUDA(cudaMemsetAsync((char*)dec_h_.p + (size_t)s * 2 * HID * 4, 0, (size_t)2 * HID * 4, st_));
-    NSB_CUDA(cudaMemsetAsync((char*)dec_c_.p + (size_t)s * 2 * HID * 4, 0, (size_t)2 * HID * 4, st_));
+    NSB_CUDA(cudaMemsetAsync((char*)dec_h_.p + (size_t)s * 4 * HID * 4, 0, (size_t)4 * HID * 4, st_));
+    NSB_CUDA(cudaMemsetAsync((char*)dec_c_.p + (size_t)s * 4 * HID * 4, 0, (size_t)4 * HID * 4, st_));
+    NSB_CUDA(cudaMemsetAsync((char*)dec_par_.p + (size_t)s * 4, 0, 4, st_));
     const int zero = 0, blank = BLANK;
     NSB_CUDA(cudaMemcpyAsync((char*)ring_pos_.p + (size_t)s * 4, &zero, 4, cudaMemcpyHostToDevice, st_));
     NSB_CUDA(cudaMemcpyAsync((char*)valid_len_.p + (size_t)s * 4, &zero, 4, cudaMemcpyHostToDevice, st_));
@@ -533,15 +531,13 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
     for (int l = 0; l < 2; ++l) { d.w.w_ih[l] = lstm_w_[2 * l].as<float>(); d.w.w_hh[l] = lstm_w_[2 * l + 1].as<float>();
                                   d.w.b_ih[l] = lstm_b_[2 * l].as<float>(); d.w.b_hh[l] = lstm_b_[2 * l + 1].as<float>(); }
     d.w.pred_w = pred_w_.as<float>(); d.w.pred_b = pred_b_.as<float>(); d.w.out_w = jout_w_.as<float>(); d.w.out_b = jout_b_.as<float>();
-    d.s.h = dec_h_.as<float>(); d.s.c = dec_c_.as<float>(); d.s.cand_h = cand_h_.as<float>(); d.s.cand_c = cand_c_.as<float>();
+    d.s.hbuf = dec_h_.as<float>(); d.s.cbuf = dec_c_.as<float>(); d.s.par = dec_par_.as<int>();
     d.s.dec_proj = dec_proj_.as<float>(); d.s.prev_token = prev_token_.as<int>(); d.s.cand_valid = cand_valid_.as<int>();
     d.enc_proj = encp_.as<float>(); d.slot_of_b = slot; d.B = B; d.T = T;
     d.out_tokens = out_tok_.as<int>(); d.out_count = out_cnt_.as<int>();
-    d.frame_idx = frame_idx_.as<int>(); d.sym_cnt = sym_cnt_.as<int>(); d.need_lstm = need_lstm_.as<int>();
-    d.part_val = part_val_.as<float>(); d.part_idx = part_idx_.as<int>(); d.counters = counters_.as<int>();
     d.logits_tap = debug_ ? dbg_logits_.as<float>() : nullptr; d.logits_tap_cap = debug_ ? MAX_SYMBOLS * T + T : 0;
     d.logits_tap_n = debug_ ? dbg_logits_n_.as<int>() : nullptr;
-    launch_decode(d, st_); count_launch();
+    launch_decode(d, dec_sync_.p, st_); count_launch();
 }
 
 // ------------------------------------------------------------------------------------------

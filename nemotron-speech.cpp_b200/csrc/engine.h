@@ -128,13 +128,13 @@ private:
     DevBuf conv_cache_;            // [S][layers][8][1024] f32
     DevBuf mel_hist_;              // [S][9][128]
     DevBuf ring_pos_, valid_len_;  // [S] int
-    DevBuf dec_h_, dec_c_, cand_h_, cand_c_, dec_proj_, prev_token_, cand_valid_;
+    DevBuf dec_h_, dec_c_, dec_par_, dec_proj_, prev_token_, cand_valid_;
     std::vector<HostStream> hs_;
 
     // ---- step workspace (batch-compact) ----
     int rl_ = 0;                   // PCM row length per stream-step
     DevBuf d_pcm_, d_slot_, mel_new_, c0_, dw_, pw_, x_, a_, big_, qkv_, pw1_, encp_, part_;
-    DevBuf out_tok_, out_cnt_, frame_idx_, sym_cnt_, need_lstm_, part_val_, part_idx_, counters_;
+    DevBuf out_tok_, out_cnt_, dec_sync_;
     HostPinned h_pcm_, h_slot_, h_tok_, h_cnt_;
 
     // ---- bench ----

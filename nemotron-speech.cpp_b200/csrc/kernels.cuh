@@ -80,9 +80,9 @@ struct DecodeWeights {
     const float* out_w; const float* out_b;   // [1025][640], [1025]
 };
 struct DecodeState {                          // slot-indexed, device
-    float* h; float* c;                       // [S][1280]
-    float* cand_h; float* cand_c;             // [S][1280]
-    float* dec_proj;                          // [S][640]
+    float* hbuf; float* cbuf;                 // [S][2 parities][2 layers * 640]: committed state at parity par[slot], candidate at the other
+    int* par;                                 // [S]
+    float* dec_proj;                          // [S][640] joint.pred projection of the candidate
     int* prev_token; int* cand_valid;         // [S]
 };
 struct DecodeArgs {
@@ -90,14 +90,11 @@ struct DecodeArgs {
     const float* enc_proj;                    // [B*T][640] (joint.enc applied, bias included)
     const int* slot_of_b; int B, T;
     int* out_tokens; int* out_count;          // [B][MAX_SYMBOLS*T], [B]
-    // scratch
-    int* frame_idx; int* sym_cnt; int* need_lstm;     // [B]
-    float* part_val; int* part_idx;           // [B][gridDim]
-    int* counters;                            // [4] : n_active, n_need_lstm (double-buffered)
+    unsigned* barrier; unsigned long long* best;   // filled by launch_decode from its sync buffer
     float* logits_tap; int logits_tap_cap; int* logits_tap_n;   // optional: logits of batch row 0 per evaluation
 };
-// cooperative persistent kernel; returns the grid size used
-int launch_decode(const DecodeArgs& a, cudaStream_t st);
-size_t decode_scratch_parts(int B);           // number of (val, idx) partial slots needed = B * grid
+// persistent kernel, one CTA per SM (cooperative launch); sync_buf holds decode_sync_bytes(B) bytes. Returns the grid size used
+int launch_decode(const DecodeArgs& a, void* sync_buf, cudaStream_t st);
+size_t decode_sync_bytes(int B);
 
 }  // namespace nsb

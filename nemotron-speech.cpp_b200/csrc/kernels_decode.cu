@@ -1,74 +1,76 @@
-// kernels_decode.cu -- batched RNN-T greedy decode as ONE persistent cooperative kernel (sm_100a).
+// kernels_decode.cu -- batched RNN-T greedy decode as ONE persistent kernel (sm_100a), one CTA per SM.
 //
 // Reference behaviour being replaced: decode_one_step + the per-frame loop of process_mel_chunk_streaming
 // (src/nemo-stream.cpp:788-878, :1035-1047) on top of build_decoder_step / build_lstm_cell / build_joint
 // (src/nemo-ggml.cpp:503-542, :1013-1100). The reference launches one graph and does 6-8 host<->device
-// copies PER SYMBOL PER STREAM; here all streams of a step are decoded by one kernel launch with no host
-// round-trips: the grid loops over "rounds" (one symbol evaluation for every still-active stream), with
-// grid-wide barriers between the phases.
+// copies PER SYMBOL PER STREAM; here all streams of a step are decoded by one launch with no host round-trips.
 //
 // Semantics kept exactly (nemo-stream.cpp:813-875): up to 10 symbols per encoder frame; argmax = lowest index
 // among maxima; blank => next frame, LSTM state untouched; non-blank => emit, prev_token = token, commit h', c'.
 // The reference re-runs the LSTM for every evaluation and throws the result away on blank; since
-// (prev_token, h, c) only change on emission the candidate (h', c', joint.pred projection) is cached per
-// stream and recomputed only after an emission -- arithmetic-identical.
+// (prev_token, h, c) only change on emission the candidate (h', c', joint.pred projection) is kept per stream and
+// recomputed only after an emission -- arithmetic-identical.
 //
-// Work split per phase: the streams that need the phase are compacted into a list and cut into groups of
-// GS = 16; the grid is arranged as (groups x row-slices). A CTA stages its group's input vectors in shared
-// memory once, then each warp streams weight rows of its row-slice from L2 (coalesced, read-only path) and
-// dots them against the 16 staged vectors. With few streams needing a phase (the common case after an
-// emission) there is one group and all CTAs split the weight rows, so every weight byte is read once.
-#include <cooperative_groups.h>
-
+// Structure. The grid advances in "rounds": one joint evaluation for every still-active stream, preceded by the
+// prediction network for the streams that emitted in the previous round. Every phase is a skinny fp32 GEMM
+//     OUT[stream][row] = sum_k X[stream][k] * W[row][k]          (streams <= 64 per block, K = 1280 or 640)
+// split over the grid by weight rows, so each weight byte is pulled from L2 once per round. Inside a CTA the 8 warps
+// split K; a lane owns an RPL x SPL (rows x streams) register tile and streams W and X as 16-byte vectors straight
+// from L2 (X is tiny and shared by the 4 row groups of a warp -> broadcast); partial tiles meet in shared memory.
+//   * per-stream control state (frame index, symbols at this frame, parity of the committed LSTM buffer, previous
+//     token) is REPLICATED in every CTA's shared memory and advanced identically from the broadcast argmax keys, so
+//     a round costs 4 grid barriers with the prediction network and 1 without;
+//   * the argmax across row slices is one 64-bit atomicMax per (CTA, stream): key = orderable(logit) << 32 | ~index
+//     (largest logit wins, ties go to the lowest index = "first max wins");
+//   * h/c are double-buffered per stream: the candidate is written to the other parity, committing = flipping the
+//     parity bit (no copy, no extra barrier);
+//   * the grid barrier is a monotonic counter in HBM (arrive = one atomicAdd, wait = ld.acquire spin, bounded).
 #include "kernels.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace nsb {
 
 namespace {
 constexpr int NT = 256, NW = NT / 32;
-constexpr int GS = 16;               // streams per group (staged in shared memory together)
-constexpr int UB = 32;               // hidden units per gate block (4 * UB gate rows buffered)
-constexpr int EL = HID / 32;         // 20 elements of a 640-vector per lane
+constexpr int SBLK = 64;             // streams per block of a phase
+constexpr int RSTR = 72;             // padded stream stride of the partial-tile buffers (conflict-free lane pattern)
+constexpr int RC_MAX = 20;           // weight rows per work item: 20 (LSTM: 5 units x 4 gates) or 8 (pred, joint)
 constexpr int MAXB = 1024;           // max streams per step
+constexpr int PAR_STRIDE = 2 * HID;  // one parity copy of (layer 0 | layer 1) h or c
 
 struct DecSmem {
-    float xs[GS][HID];               // staged input vectors (x or joint activations)
-    float hs[GS][HID];               // staged recurrent vectors
-    float gates[GS][4 * UB];
-    float w_val[NW][GS]; int w_idx[NW][GS];
-    int list[MAXB];                  // compacted stream list of the current phase
+    float red[NW][RC_MAX][RSTR];     // per-warp partial tiles
+    float sums[RC_MAX][RSTR];
+    int slot[MAXB], prev[MAXB], list[MAXB];
+    short fi[MAXB], oc[MAXB];        // frame index within the chunk, tokens emitted this step
+    unsigned char sc[MAXB], need[MAXB], par[MAXB];   // symbols at this frame, candidate stale, committed parity
     int warp_cnt[NW];
-    int g_slot[GS], g_aux[GS];       // per-group metadata hoisted out of the staging loops (slot; prev_token or frame row)
-    int n_list;
 };
 
-__device__ __forceinline__ void load_row_ro(const float* p, float (&r)[EL], int lane) {      // weights: read-only path
-#pragma unroll
-    for (int e = 0; e < EL; ++e) r[e] = __ldg(p + lane + 32 * e);
-}
-__device__ __forceinline__ float dot_smem(const float (&w)[EL], const float* x, int lane) {
-    float s = 0.f;
-#pragma unroll
-    for (int e = 0; e < EL; ++e) s = fmaf(w[e], x[lane + 32 * e], s);
-    return s;
+__device__ __forceinline__ float4 ld_w(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }      // weights: read-only
+__device__ __forceinline__ float4 ld_x(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }     // state written by other CTAs: L2
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
 
-// Sum 16 per-lane partials across the warp with 16 shuffles (instead of 16 x 5): every stage halves the values a lane
-// keeps. On return lane l holds the complete sum of v[(l >> 1) & 15] in the return value.
-__device__ __forceinline__ float reduce16(float (&v)[GS], int lane) {
-#pragma unroll
-    for (int half = 8, mask = 16; half >= 1; half >>= 1, mask >>= 1) {
-        const bool hi = (lane & mask) != 0;
-#pragma unroll
-        for (int i = 0; i < half; ++i) {
-            const float send = hi ? v[i] : v[i + half];
-            const float keep = hi ? v[i + half] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
-        }
+// grid-wide barrier: every CTA is resident (cooperative launch, one CTA per SM)
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& epoch, unsigned nblk) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        epoch += 1;
+        const unsigned target = epoch * nblk;
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        unsigned it = 0;
+        while (ld_acquire(ctr) < target) { if (++it > (1u << 26)) __trap(); }     // a protocol bug traps instead of hanging the GPU
+        __threadfence();
     }
-    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+    __syncthreads();
+}
+
+__device__ __forceinline__ unsigned long long argmax_key(float v, int idx) {
+    unsigned u = __float_as_uint(v);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);                              // monotone float -> uint
+    return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)idx);
 }
 
 // block-wide stable compaction of {b : pred(b)} into sm.list; returns the count (block-uniform)
@@ -91,194 +93,200 @@ __device__ int compact(DecSmem& sm, int B, Pred pred) {
     return base;
 }
 
-// grid arrangement for n listed streams: groups of GS x row slices
-struct Part { int group, n_groups, rs, n_rs; };
-__device__ __forceinline__ Part make_part(int n, int nblk, int blk) {
-    Part p; p.n_groups = (n + GS - 1) / GS; p.n_rs = max(1, nblk / max(1, p.n_groups));
-    p.group = blk / p.n_rs; p.rs = blk % p.n_rs; return p;
-}
+enum { MODE_LSTM = 0, MODE_PRED = 1, MODE_JOINT = 2 };
 
-// one LSTM layer for the listed streams (gate order i,f,g,o: nemo-ggml.cpp:518-541)
-__device__ void lstm_phase(const DecodeArgs& a, DecSmem& sm, int layer, int n, int nblk, int blk) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const Part p = make_part(n, nblk, blk);
-    if (p.group >= p.n_groups) return;
-    const int g0 = p.group * GS, gn = min(GS, n - g0);
-    const int upb = (HID + p.n_rs - 1) / p.n_rs, u0 = min(HID, p.rs * upb), u1 = min(HID, u0 + upb);
-    if (u0 >= u1) return;
-    if (tid < gn) { const int slot = a.slot_of_b[sm.list[g0 + tid]]; sm.g_slot[tid] = slot; sm.g_aux[tid] = a.s.prev_token[slot]; }
-    __syncthreads();
-    for (int g = 0; g < gn; ++g) {                                                // stage x and h (independent coalesced loads)
-        const int slot = sm.g_slot[g];
-        const float* xsrc = layer == 0 ? a.w.embed + (size_t)sm.g_aux[g] * HID                   // nemo-stream.cpp:825-828
-                                       : a.s.cand_h + (size_t)slot * 2 * HID;                    // layer-1 input = layer-0 h'
-        const float* hsrc = a.s.h + (size_t)slot * 2 * HID + layer * HID;
-        for (int k = tid; k < HID; k += NT) { sm.xs[g][k] = xsrc[k]; sm.hs[g][k] = hsrc[k]; }
-    }
-    __syncthreads();
-    for (int ub = u0; ub < u1; ub += UB) {
-        const int nu = min(UB, u1 - ub), nrows = 4 * nu;
-        for (int r = warp; r < nrows; r += NW) {
-            const int gate = r / nu, u = ub + r % nu, wrow = gate * HID + u;
-            float wi[EL], wh[EL];
-            load_row_ro(a.w.w_ih[layer] + (size_t)wrow * HID, wi, lane);
-            load_row_ro(a.w.w_hh[layer] + (size_t)wrow * HID, wh, lane);
-            const float b2 = __ldg(a.w.b_ih[layer] + wrow), b3 = __ldg(a.w.b_hh[layer] + wrow);
-            float acc[GS];
+// One phase over the n listed streams. RPL rows x SPL streams per lane; 4 row groups x 8 stream groups per warp.
+template <int RPL, int SPL, int MODE>
+__device__ void phase(const DecodeArgs& a, DecSmem& sm, int layer, int n, int round, int ne0) {
+    constexpr int RC = 4 * RPL;
+    constexpr int K = MODE == MODE_LSTM ? 2 * HID : HID;
+    constexpr int KW = K / NW;                                                    // k-slice of one warp (160 or 80)
+    const int n_chunks = MODE == MODE_LSTM ? HID / RPL : MODE == MODE_PRED ? JOINT / RC : (VOCAB + RC - 1) / RC;
+    const int n_sblk = (n + SBLK - 1) / SBLK;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, rg = lane >> 3, sg = lane & 7;
+    const int kbeg = warp * KW;
+    const bool second_half = MODE == MODE_LSTM && kbeg >= HID;                    // LSTM: k < 640 is the input, k >= 640 the recurrent part
+    const int koff = second_half ? kbeg - HID : kbeg;
+
+    for (int item = blockIdx.x; item < n_chunks * n_sblk; item += gridDim.x) {
+        const int chunk = item % n_chunks, s0 = (item / n_chunks) * SBLK, ns = min(SBLK, n - s0);
+        const float* wp[RPL];
 #pragma unroll
-            for (int g = 0; g < GS; ++g) acc[g] = g < gn ? dot_smem(wi, sm.xs[g], lane) + dot_smem(wh, sm.hs[g], lane) : 0.f;
-            const float tot = reduce16(acc, lane);
-            const int g = (lane >> 1) & 15;
-            if (!(lane & 1) && g < gn) sm.gates[g][gate * UB + (u - ub)] = (tot + b2) + b3;
+        for (int i = 0; i < RPL; ++i) {
+            if (MODE == MODE_LSTM) {                                              // row group = gate (i,f,g,o), i = unit within the chunk
+                const int row = rg * HID + chunk * RPL + i;
+                wp[i] = (second_half ? a.w.w_hh[layer] : a.w.w_ih[layer]) + (size_t)row * HID + koff;
+            } else if (MODE == MODE_PRED) {
+                wp[i] = a.w.pred_w + (size_t)(chunk * RC + rg * RPL + i) * HID + koff;
+            } else {
+                wp[i] = a.w.out_w + (size_t)min(chunk * RC + rg * RPL + i, VOCAB - 1) * JOINT + koff;
+            }
+        }
+        const float* xp[SPL]; const float* xp2[SPL];
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            const int g = sg + 8 * j, b = sm.list[s0 + (g < ns ? g : 0)], slot = sm.slot[b], par = sm.par[b];
+            const float* hb = a.s.hbuf + (size_t)slot * 2 * PAR_STRIDE;
+            xp2[j] = nullptr;
+            if (MODE == MODE_LSTM) {
+                if (layer == 0) xp[j] = second_half ? hb + par * PAR_STRIDE + koff                          // h0 (committed)
+                                                    : a.w.embed + (size_t)sm.prev[b] * HID + koff;          // nemo-stream.cpp:825-828
+                else xp[j] = second_half ? hb + par * PAR_STRIDE + HID + koff                               // h1 (committed)
+                                         : hb + (par ^ 1) * PAR_STRIDE + koff;                              // layer-1 input = layer-0 h'
+            } else if (MODE == MODE_PRED) {
+                xp[j] = hb + (par ^ 1) * PAR_STRIDE + HID + koff;                                           // candidate decoder output
+            } else {
+                xp[j] = a.enc_proj + ((size_t)b * a.T + sm.fi[b]) * JOINT + koff;
+                xp2[j] = a.s.dec_proj + (size_t)slot * JOINT + koff;
+            }
+        }
+        float acc[RPL][SPL];
+#pragma unroll
+        for (int i = 0; i < RPL; ++i)
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
+        for (int k = 0; k < KW; k += 4) {
+            float4 w[RPL], x[SPL];
+#pragma unroll
+            for (int i = 0; i < RPL; ++i) w[i] = ld_w(wp[i] + k);
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) {
+                x[j] = ld_x(xp[j] + k);
+                if (MODE == MODE_JOINT) {                                         // z = relu(enc_proj + pred_proj)  (nemo-ggml.cpp:1092-1094)
+                    const float4 d = ld_x(xp2[j] + k);
+                    x[j].x = fmaxf(x[j].x + d.x, 0.f); x[j].y = fmaxf(x[j].y + d.y, 0.f);
+                    x[j].z = fmaxf(x[j].z + d.z, 0.f); x[j].w = fmaxf(x[j].w + d.w, 0.f);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < RPL; ++i)
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) {
+                    acc[i][j] = fmaf(w[i].x, x[j].x, acc[i][j]); acc[i][j] = fmaf(w[i].y, x[j].y, acc[i][j]);
+                    acc[i][j] = fmaf(w[i].z, x[j].z, acc[i][j]); acc[i][j] = fmaf(w[i].w, x[j].w, acc[i][j]);
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < RPL; ++i)
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) sm.red[warp][rg * RPL + i][sg + 8 * j] = acc[i][j];
+        __syncthreads();
+        for (int e = tid; e < RC * ns; e += NT) {                                 // fixed warp order => deterministic sums
+            const int rr = e / ns, g = e % ns;
+            float s = sm.red[0][rr][g];
+#pragma unroll
+            for (int w8 = 1; w8 < NW; ++w8) s += sm.red[w8][rr][g];
+            sm.sums[rr][g] = s;
         }
         __syncthreads();
-        for (int e = tid; e < gn * nu; e += NT) {
-            const int g = e / nu, uu = e % nu, slot = sm.g_slot[g];
-            const float ig = sigmoid_exact(sm.gates[g][0 * UB + uu]), fg = sigmoid_exact(sm.gates[g][1 * UB + uu]);
-            const float gg = tanhf(sm.gates[g][2 * UB + uu]), og = sigmoid_exact(sm.gates[g][3 * UB + uu]);
-            const size_t o = (size_t)slot * 2 * HID + layer * HID + ub + uu;
-            const float cn = fg * a.s.c[o] + ig * gg;
-            a.s.cand_c[o] = cn; a.s.cand_h[o] = og * tanhf(cn);
+        if (MODE == MODE_LSTM) {                                                  // gate order i,f,g,o (nemo-ggml.cpp:518-541)
+            for (int e = tid; e < RPL * ns; e += NT) {
+                const int uu = e / ns, g = e % ns, b = sm.list[s0 + g], slot = sm.slot[b], par = sm.par[b];
+                const int u = chunk * RPL + uu;
+                float gate[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    gate[q] = (sm.sums[q * RPL + uu][g] + __ldg(a.w.b_ih[layer] + q * HID + u)) + __ldg(a.w.b_hh[layer] + q * HID + u);
+                const float ig = sigmoid_exact(gate[0]), fg = sigmoid_exact(gate[1]), gg = tanhf(gate[2]), og = sigmoid_exact(gate[3]);
+                const size_t o_old = (size_t)slot * 2 * PAR_STRIDE + par * PAR_STRIDE + layer * HID + u;
+                const size_t o_new = (size_t)slot * 2 * PAR_STRIDE + (par ^ 1) * PAR_STRIDE + layer * HID + u;
+                const float cn = fg * __ldcg(a.s.cbuf + o_old) + ig * gg;
+                a.s.cbuf[o_new] = cn; a.s.hbuf[o_new] = og * tanhf(cn);
+            }
+        } else if (MODE == MODE_PRED) {                                           // joint.pred (nemo-ggml.cpp:1086-1087)
+            for (int e = tid; e < RC * ns; e += NT) {
+                const int rr = e / ns, g = e % ns, j = chunk * RC + rr;
+                a.s.dec_proj[(size_t)sm.slot[sm.list[s0 + g]] * JOINT + j] = sm.sums[rr][g] + __ldg(a.w.pred_b + j);
+            }
+        } else {                                                                  // logits of this row slice -> argmax key
+            if (tid < ns) {
+                const int b = sm.list[s0 + tid];
+                float bv = -INFINITY; int bi = 0;
+#pragma unroll
+                for (int rr = 0; rr < RC; ++rr) {
+                    const int v = chunk * RC + rr;
+                    if (v < VOCAB) {
+                        const float s = sm.sums[rr][tid] + __ldg(a.w.out_b + v);
+                        if (s > bv) { bv = s; bi = v; }                           // ascending v, strict > : first max wins (:847-854)
+                        if (a.logits_tap && b == 0 && ne0 < a.logits_tap_cap) a.logits_tap[(size_t)ne0 * VOCAB + v] = s;
+                    }
+                }
+                atomicMax(a.best + (size_t)(round % 3) * a.B + b, argmax_key(bv, bi));
+            }
         }
-        __syncthreads();
+        __syncthreads();                                                          // red / sums are reused by the next item
     }
 }
 
-// joint.pred projection of the candidate decoder output (nemo-ggml.cpp:1086-1087)
-__device__ void pred_phase(const DecodeArgs& a, DecSmem& sm, int n, int nblk, int blk) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const Part p = make_part(n, nblk, blk);
-    if (p.group >= p.n_groups) return;
-    const int g0 = p.group * GS, gn = min(GS, n - g0);
-    const int rpb = (JOINT + p.n_rs - 1) / p.n_rs, j0 = min(JOINT, p.rs * rpb), j1 = min(JOINT, j0 + rpb);
-    if (j0 >= j1) return;
-    if (tid < gn) sm.g_slot[tid] = a.slot_of_b[sm.list[g0 + tid]];
-    __syncthreads();
-    for (int g = 0; g < gn; ++g) {
-        const float* src = a.s.cand_h + (size_t)sm.g_slot[g] * 2 * HID + HID;
-        for (int k = tid; k < HID; k += NT) sm.xs[g][k] = src[k];
-    }
-    __syncthreads();
-    for (int j = j0 + warp; j < j1; j += NW) {
-        float w[EL]; load_row_ro(a.w.pred_w + (size_t)j * HID, w, lane);
-        const float bias = __ldg(a.w.pred_b + j);
-        float acc[GS];
-#pragma unroll
-        for (int g = 0; g < GS; ++g) acc[g] = g < gn ? dot_smem(w, sm.xs[g], lane) : 0.f;
-        const float tot = reduce16(acc, lane);
-        const int g = (lane >> 1) & 15;
-        if (!(lane & 1) && g < gn) a.s.dec_proj[(size_t)sm.g_slot[g] * JOINT + j] = tot + bias;
-    }
-}
-
-// joint network + partial argmax for the listed (active) streams (nemo-ggml.cpp:1092-1097)
-__device__ void joint_phase(const DecodeArgs& a, DecSmem& sm, int n, int nblk, int blk) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const Part p = make_part(n, nblk, blk);
-    if (p.group >= p.n_groups) return;
-    const int g0 = p.group * GS, gn = min(GS, n - g0);
-    const int vpb = (VOCAB + p.n_rs - 1) / p.n_rs, v0 = min(VOCAB, p.rs * vpb), v1 = min(VOCAB, v0 + vpb);
-    if (tid < gn) { const int b = sm.list[g0 + tid]; sm.g_slot[tid] = a.slot_of_b[b]; sm.g_aux[tid] = b * a.T + a.frame_idx[b]; }
-    __syncthreads();
-    for (int g = 0; g < gn; ++g) {                                                // z = relu(enc_proj + pred_proj)
-        const float* ep = a.enc_proj + (size_t)sm.g_aux[g] * JOINT; const float* dp = a.s.dec_proj + (size_t)sm.g_slot[g] * JOINT;
-        for (int k = tid; k < JOINT; k += NT) sm.xs[g][k] = fmaxf(ep[k] + dp[k], 0.f);
-    }
-    float bv = -INFINITY; int bi = 0x7fffffff;                                 // lane keeps the running best of stream g = (lane >> 1) & 15
-    const int gl = (lane >> 1) & 15;
-    const bool tap = a.logits_tap && !(lane & 1) && gl < gn && sm.list[g0 + gl] == 0;
-    __syncthreads();
-    for (int v = v0 + warp; v < v1; v += NW) {                                    // v ascending per warp => first max wins
-        float w[EL]; load_row_ro(a.w.out_w + (size_t)v * JOINT, w, lane);
-        const float bias = __ldg(a.w.out_b + v);
-        float acc[GS];
-#pragma unroll
-        for (int g = 0; g < GS; ++g) acc[g] = g < gn ? dot_smem(w, sm.xs[g], lane) : 0.f;
-        const float s = reduce16(acc, lane) + bias;
-        if (s > bv) { bv = s; bi = v; }
-        if (tap) { const int ne = *a.logits_tap_n; if (ne < a.logits_tap_cap) a.logits_tap[(size_t)ne * VOCAB + v] = s; }
-    }
-    if (!(lane & 1)) { sm.w_val[warp][gl] = bv; sm.w_idx[warp][gl] = bi; }
-    __syncthreads();
-    if (tid < gn) {
-        float v = -INFINITY; int i = 0x7fffffff;
-#pragma unroll
-        for (int w8 = 0; w8 < NW; ++w8) {
-            const float vv = sm.w_val[w8][tid]; const int ii = sm.w_idx[w8][tid];
-            if (vv > v || (vv == v && ii < i)) { v = vv; i = ii; }
-        }
-        const int b = sm.list[g0 + tid];
-        a.part_val[(size_t)b * nblk + p.rs] = v; a.part_idx[(size_t)b * nblk + p.rs] = i;
-    }
+template <int MODE>
+__device__ __forceinline__ void phase_dispatch(const DecodeArgs& a, DecSmem& sm, int layer, int n, int round, int ne0) {
+    constexpr int RPL = MODE == MODE_LSTM ? 5 : 2;
+    const int m = min(n, SBLK);
+    if (m <= 8) phase<RPL, 1, MODE>(a, sm, layer, n, round, ne0);
+    else if (m <= 16) phase<RPL, 2, MODE>(a, sm, layer, n, round, ne0);
+    else if (m <= 32) phase<RPL, 4, MODE>(a, sm, layer, n, round, ne0);
+    else phase<RPL, 8, MODE>(a, sm, layer, n, round, ne0);
 }
 
 __global__ void __launch_bounds__(NT, 1) rnnt_decode_kernel(const DecodeArgs a) {
-    cg::grid_group grid = cg::this_grid();
-    extern __shared__ uint8_t dec_smem_raw[];
+    extern __shared__ __align__(16) uint8_t dec_smem_raw[];
     DecSmem& sm = *reinterpret_cast<DecSmem*>(dec_smem_raw);
-    const int nblk = gridDim.x, blk = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int B = a.B, T = a.T;
+    const int tid = threadIdx.x, B = a.B, T = a.T;
+    const unsigned nblk = gridDim.x;
+    unsigned epoch = 0;
+    int ne0 = 0;                                                                  // joint evaluations of batch row 0 so far (debug tap)
 
-    for (int b = blk * NT + tid; b < B; b += nblk * NT) {
-        a.frame_idx[b] = 0; a.sym_cnt[b] = 0; a.out_count[b] = 0;
-        a.need_lstm[b] = a.s.cand_valid[a.slot_of_b[b]] ? 0 : 1;
+    for (int b = tid; b < B; b += NT) {
+        const int slot = a.slot_of_b[b];
+        sm.slot[b] = slot; sm.prev[b] = a.s.prev_token[slot]; sm.par[b] = (unsigned char)(a.s.par[slot] & 1);
+        sm.need[b] = a.s.cand_valid[slot] ? 0 : 1;
+        sm.fi[b] = 0; sm.oc[b] = 0; sm.sc[b] = 0;
     }
-    if (blk == 0 && tid == 0 && a.logits_tap_n) *a.logits_tap_n = 0;
-    grid.sync();
+    __syncthreads();
 
-    for (;;) {
-        // ---------------- prediction network for streams whose candidate is stale ----------------
-        const int n_need = compact(sm, B, [&](int b) { return a.need_lstm[b] != 0; });
+    for (int round = 0;; ++round) {
+        // ---------------- prediction network for active streams whose candidate is stale ----------------
+        const int n_need = compact(sm, B, [&](int b) { return sm.need[b] != 0 && sm.fi[b] < T; });
         if (n_need > 0) {
-            lstm_phase(a, sm, 0, n_need, nblk, blk);
-            grid.sync();
-            lstm_phase(a, sm, 1, n_need, nblk, blk);
-            grid.sync();
-            pred_phase(a, sm, n_need, nblk, blk);
-            grid.sync();
-            if (blk == 0)
-                for (int i = tid; i < n_need; i += NT) { const int b = sm.list[i]; a.need_lstm[b] = 0; a.s.cand_valid[a.slot_of_b[b]] = 1; }
+            phase_dispatch<MODE_LSTM>(a, sm, 0, n_need, round, ne0);
+            grid_barrier(a.barrier, epoch, nblk);
+            phase_dispatch<MODE_LSTM>(a, sm, 1, n_need, round, ne0);
+            grid_barrier(a.barrier, epoch, nblk);
+            phase_dispatch<MODE_PRED>(a, sm, 0, n_need, round, ne0);
+            grid_barrier(a.barrier, epoch, nblk);
+            for (int i = tid; i < n_need; i += NT) sm.need[sm.list[i]] = 0;
             __syncthreads();
         }
-        // ---------------- joint + partial argmax ----------------
-        const int n_act = compact(sm, B, [&](int b) { return a.frame_idx[b] < T; });
-        if (n_act == 0) break;                                                    // uniform across the grid
-        joint_phase(a, sm, n_act, nblk, blk);
-        const int n_rs = make_part(n_act, nblk, blk).n_rs;
-        grid.sync();
-        // ---------------- decision: one warp per active stream ----------------
-        for (int li = blk * NW + warp; li < n_act; li += nblk * NW) {
-            const int b = sm.list[li];
-            float bv = -INFINITY; int bi = 0x7fffffff;
-            for (int q = lane; q < n_rs; q += 32) {
-                const float v = a.part_val[(size_t)b * nblk + q]; const int i = a.part_idx[(size_t)b * nblk + q];
-                if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float v = __shfl_xor_sync(0xffffffffu, bv, o); const int i = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
-            }
-            const int slot = a.slot_of_b[b];
-            if (bi != BLANK) {                                                    // emit: commit candidate state (:869-874)
-                for (int e = lane; e < 2 * HID; e += 32) {
-                    a.s.h[(size_t)slot * 2 * HID + e] = a.s.cand_h[(size_t)slot * 2 * HID + e];
-                    a.s.c[(size_t)slot * 2 * HID + e] = a.s.cand_c[(size_t)slot * 2 * HID + e];
-                }
-            }
-            if (lane == 0) {
-                if (b == 0 && a.logits_tap_n) *a.logits_tap_n += 1;
-                if (bi == BLANK) { a.frame_idx[b] += 1; a.sym_cnt[b] = 0; }       // blank: next frame, state untouched (:856-859)
-                else {
-                    const int n = a.out_count[b];
-                    a.out_tokens[(size_t)b * MAX_SYMBOLS * T + n] = bi; a.out_count[b] = n + 1;
-                    a.s.prev_token[slot] = bi; a.s.cand_valid[slot] = 0; a.need_lstm[b] = 1;
-                    const int sc = a.sym_cnt[b] + 1;
-                    if (sc >= MAX_SYMBOLS) { a.frame_idx[b] += 1; a.sym_cnt[b] = 0; } else a.sym_cnt[b] = sc;   // :813
-                }
+        // ---------------- joint + argmax ----------------
+        const int n_act = compact(sm, B, [&](int b) { return sm.fi[b] < T; });
+        if (n_act == 0) break;                                                    // identical in every CTA
+        phase_dispatch<MODE_JOINT>(a, sm, 0, n_act, round, ne0);
+        grid_barrier(a.barrier, epoch, nblk);
+        if (blockIdx.x == 0)                                                      // keys of round+2: everyone is done reading them (see header)
+            for (int b = tid; b < B; b += NT) a.best[(size_t)((round + 2) % 3) * B + b] = 0ull;
+        // ---------------- decision, replicated in every CTA (:856-874) ----------------
+        for (int i = tid; i < n_act; i += NT) {
+            const int b = sm.list[i];
+            const unsigned long long key = __ldcg(a.best + (size_t)(round % 3) * B + b);
+            const int tok = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+            if (tok == BLANK) { sm.fi[b] += 1; sm.sc[b] = 0; }                    // blank: next frame, state untouched
+            else {
+                if (blockIdx.x == 0) a.out_tokens[(size_t)b * MAX_SYMBOLS * T + sm.oc[b]] = tok;
+                sm.oc[b] += 1; sm.prev[b] = tok; sm.par[b] ^= 1; sm.need[b] = 1;  // emit: commit the candidate (parity flip)
+                if (sm.sc[b] + 1 >= MAX_SYMBOLS) { sm.fi[b] += 1; sm.sc[b] = 0; } else sm.sc[b] += 1;   // :813
             }
         }
-        grid.sync();
+        if (sm.list[0] == 0) ne0 += 1;                                            // list is ascending: row 0 is first whenever it was evaluated
+        __syncthreads();                                                          // state updates visible before the next compaction
+    }
+    if (blockIdx.x == 0) {
+        for (int b = tid; b < B; b += NT) {
+            const int slot = sm.slot[b];
+            a.s.prev_token[slot] = sm.prev[b]; a.s.par[slot] = sm.par[b]; a.s.cand_valid[slot] = sm.need[b] ? 0 : 1;
+            a.out_count[b] = sm.oc[b];
+        }
+        if (tid == 0 && a.logits_tap_n) *a.logits_tap_n = ne0;
     }
 }
 }  // namespace
@@ -296,11 +304,15 @@ static int decode_grid() {
     }
     return g_decode_grid;
 }
-size_t decode_scratch_parts(int B) { return (size_t)B * decode_grid(); }
+size_t decode_sync_bytes(int B) { return 16 + (size_t)3 * B * sizeof(unsigned long long); }
 
-int launch_decode(const DecodeArgs& a, cudaStream_t st) {
+int launch_decode(const DecodeArgs& a_in, void* sync_buf, cudaStream_t st) {
     const int grid = decode_grid();
-    if (a.B > MAXB) throw CudaError("decode: more than 1024 streams in one step");
+    if (a_in.B > MAXB) throw CudaError("decode: more than 1024 streams in one step");
+    DecodeArgs a = a_in;
+    a.barrier = reinterpret_cast<unsigned*>(sync_buf);
+    a.best = reinterpret_cast<unsigned long long*>((char*)sync_buf + 16);
+    NSB_CUDA(cudaMemsetAsync(sync_buf, 0, decode_sync_bytes(a.B), st));           // barrier counter + argmax keys
     void* args[] = {(void*)&a};
     NSB_CUDA(cudaLaunchCooperativeKernel((void*)rnnt_decode_kernel, dim3(grid), dim3(NT), args, sizeof(DecSmem), st));
     return grid;
