@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <stdexcept>
 #include <string>
+#include <utility>
 
 namespace nsb {
 
@@ -33,6 +34,29 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
             throw ::nsb::CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
                                    std::to_string(__LINE__) + ")");                                 \
     } while (0)
+
+// ------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL). Every kernel of a step is launched with the programmatic-stream-serialization
+// attribute: its CTAs may become resident (and run their input-independent prologue: barrier init, TMEM allocation,
+// tensor-map prefetch, weight-tile TMA) while the previous kernel drains. pdl_wait() blocks until the previous grid has
+// completed and its writes are visible -- it must precede the first access to anything a predecessor produces or still
+// reads; pdl_trigger() lets the NEXT grid start launching. Without the attribute both are no-ops.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();            // engine.cu (NSB_NO_PDL=1 disables)
+
+template <typename... P, typename... A>
+inline void launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    NSB_CUDA(cudaLaunchKernelEx(&cfg, kern, P(std::forward<A>(args))...));
+}
 
 // Epilogues shared by the SIMT and the tcgen05 GEMM
 enum Epi : int {

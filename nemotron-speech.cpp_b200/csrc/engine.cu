@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace nsb {
@@ -19,6 +20,11 @@ namespace nsb {
 void launch_gemm_tc(const GemmArgs& a, int in_type /*OUT_F16 | OUT_BF16*/, cudaStream_t st);
 
 constexpr int MAX_SPLITS = 8;
+
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("NSB_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
 
 namespace {
 

@@ -20,6 +20,7 @@ __device__ __forceinline__ const float* a_row_ptr(const GemmArgs& g, int m) {
 }
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmArgs g) {
+    pdl_wait(); pdl_trigger();
     __shared__ float As[2][BK][BM + PAD], Bs[2][BK][BN + PAD];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -77,7 +78,7 @@ void launch_gemm_simt(const GemmArgs& a, cudaStream_t st) {
     if (a.K % BK != 0 || (a.lda % 4) != 0 || (a.group_stride % 4) != 0)
         throw CudaError("gemm_simt: K must be a multiple of 16 and rows 16-byte aligned");
     dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM);
-    gemm_simt_kernel<<<grid, 256, 0, st>>>(a);
+    launch_k(gemm_simt_kernel, grid, dim3(256), 0, st, a);
 }
 
 }  // namespace nsb

@@ -139,11 +139,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s.tmem_slot;
+    if (threadIdx.x == 0) pdl_trigger();                        // the next kernel may start its own prologue / weight prefetch
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
-            for (int kb = 0; kb < nk; ++kb) {
+            // Weights do not depend on the previous kernel: fill the ring with W tiles BEFORE waiting for it (PDL), so
+            // HBM streaming of this GEMM overlaps the tail of its predecessor; A tiles follow after the wait.
+            const int pre = nk < STAGES ? nk : STAGES;
+            for (int kb = 0; kb < pre; ++kb) {
+                mbar_expect_tx(&s.full[kb], STAGE_BYTES);
+                tma_load_2d(s.b[kb], &tmB, &s.full[kb], (kb0 + kb) * BK, n0);
+            }
+            pdl_wait();
+            for (int kb = 0; kb < pre; ++kb) tma_load_2d(s.a[kb], &tmA, &s.full[kb], (kb0 + kb) * BK, m0);
+            for (int kb = pre; kb < nk; ++kb) {
                 const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&s.empty[st], ph ^ 1);
                 mbar_expect_tx(&s.full[st], STAGE_BYTES);
@@ -171,6 +181,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== epilogue (4 warps; TMEM lane quarter = warp % 4) =====================
         const int q = warp & 3;
         const int row = m0 + q * 32 + lane;
+        pdl_wait();                                             // C / bias may be produced (or still read) by the previous kernel
         mbar_wait(&s.tmem_full, 0);
         tc_fence_after();
 #pragma unroll 1
@@ -274,8 +285,7 @@ void launch_cfg(const GemmArgs& a, int fmt, cudaStream_t st) {
     const CUtensorMap tmB = make_map(a.W, a.N, a.K, a.K, BN, fmt);
     TcParams p{a.M, a.N, a.K, a.bias, a.C, a.ldc, a.epi, a.alpha, a.out_type, fmt};
     dim3 grid(a.N / BN, (a.M + BM - 1) / BM, a.splits);
-    gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
-    NSB_CUDA(cudaGetLastError());
+    launch_k(gemm_tc_kernel<BN, STAGES>, grid, dim3(TC_THREADS), smem, st, tmA, tmB, p);
 }
 }  // namespace
 
@@ -289,13 +299,13 @@ void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
     const int tiles_m = (a.M + BM - 1) / BM;
     if (a.splits > 1) {
         if (a.epi != EPI_PARTIAL || (a.K / BK) % a.splits != 0) throw CudaError("gemm_tc: bad split-K request");
-        if (a.N % 64 == 0 && a.K >= 4096) launch_cfg<64, 6>(a, fmt, st); else launch_cfg<32, 8>(a, fmt, st);
+        if (a.N % 64 == 0 && a.K >= 4096) launch_cfg<64, 4>(a, fmt, st); else launch_cfg<32, 5>(a, fmt, st);
         return;
     }
     // pick the widest N tile that still yields >= ~1 wave of CTAs (weight streaming needs many SMs pulling)
     if (a.N % 128 == 0 && (long long)tiles_m * (a.N / 128) >= 120) launch_cfg<128, 4>(a, fmt, st);
-    else if (a.N % 64 == 0 && (long long)tiles_m * (a.N / 64) >= 120) launch_cfg<64, 6>(a, fmt, st);
-    else launch_cfg<32, 8>(a, fmt, st);
+    else if (a.N % 64 == 0 && (long long)tiles_m * (a.N / 64) >= 120) launch_cfg<64, 4>(a, fmt, st);
+    else launch_cfg<32, 5>(a, fmt, st);
 }
 
 }  // namespace nsb

@@ -14,9 +14,12 @@
 // Structure. The grid advances in "rounds": one joint evaluation for every still-active stream, preceded by the
 // prediction network for the streams that emitted in the previous round. Every phase is a skinny fp32 GEMM
 //     OUT[stream][row] = sum_k X[stream][k] * W[row][k]          (streams <= 64 per block, K = 1280 or 640)
-// split over the grid by weight rows, so each weight byte is pulled from L2 once per round. Inside a CTA the 8 warps
-// split K; a lane owns an RPL x SPL (rows x streams) register tile and streams W and X as 16-byte vectors straight
-// from L2 (X is tiny and shared by the 4 row groups of a warp -> broadcast); partial tiles meet in shared memory.
+// split over the grid by weight rows, so each weight byte is pulled from L2 once per round and stream block. Inside
+// a CTA the 8 warps split K; every warp copies ITS k-slice of the weight rows and of the stream vectors into a private
+// shared-memory region with one burst of 16-byte cp.async (all requests in flight at once: one L2 latency per item,
+// no block-wide barrier), then a lane accumulates an RPL x SPL (rows x streams) register tile out of shared memory
+// (padded rows: conflict-free, W broadcast over the 8 stream groups, X over the 4 row groups); partial tiles of the
+// 8 warps meet in shared memory.
 //   * per-stream control state (frame index, symbols at this frame, parity of the committed LSTM buffer, previous
 //     token) is REPLICATED in every CTA's shared memory and advanced identically from the broadcast argmax keys, so
 //     a round costs 4 grid barriers with the prediction network and 1 without;
@@ -31,14 +34,16 @@ namespace nsb {
 
 namespace {
 constexpr int NT = 256, NW = NT / 32;
-constexpr int SBLK = 64;             // streams per block of a phase
-constexpr int RSTR = 72;             // padded stream stride of the partial-tile buffers (conflict-free lane pattern)
+constexpr int RSTR = 40;             // padded stream stride of the partial-tile buffers
 constexpr int RC_MAX = 20;           // weight rows per work item: 20 (LSTM: 5 units x 4 gates) or 8 (pred, joint)
 constexpr int MAXB = 1024;           // max streams per step
 constexpr int PAR_STRIDE = 2 * HID;  // one parity copy of (layer 0 | layer 1) h or c
+// per-warp staging region (floats): LSTM 20 rows + 16 streams of 160+4; joint 8 rows + 2 x 32 streams of 80+4
+constexpr int STAGE_FLOATS = 8 * 84 + 2 * 32 * 84;
+static_assert(STAGE_FLOATS >= (20 + 16) * 164, "staging region too small for the LSTM phase");
 
 struct DecSmem {
-    float red[NW][RC_MAX][RSTR];     // per-warp partial tiles
+    float stage[NW][STAGE_FLOATS];   // per-warp W / X slices; reused for the warp's partial tile
     float sums[RC_MAX][RSTR];
     int slot[MAXB], prev[MAXB], list[MAXB];
     short fi[MAXB], oc[MAXB];        // frame index within the chunk, tokens emitted this step
@@ -46,8 +51,13 @@ struct DecSmem {
     int warp_cnt[NW];
 };
 
-__device__ __forceinline__ float4 ld_w(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }      // weights: read-only
-__device__ __forceinline__ float4 ld_x(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }     // state written by other CTAs: L2
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {                     // L2 -> smem, bypasses L1
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
@@ -95,66 +105,77 @@ __device__ int compact(DecSmem& sm, int B, Pred pred) {
 
 enum { MODE_LSTM = 0, MODE_PRED = 1, MODE_JOINT = 2 };
 
-// One phase over the n listed streams. RPL rows x SPL streams per lane; 4 row groups x 8 stream groups per warp.
+// One phase over the n listed streams, in blocks of SB = 8 * SPL streams. RPL rows x SPL streams per lane;
+// 4 row groups x 8 stream groups per warp.
 template <int RPL, int SPL, int MODE>
 __device__ void phase(const DecodeArgs& a, DecSmem& sm, int layer, int n, int round, int ne0) {
-    constexpr int RC = 4 * RPL;
+    constexpr int RC = 4 * RPL, SB = 8 * SPL;
     constexpr int K = MODE == MODE_LSTM ? 2 * HID : HID;
     constexpr int KW = K / NW;                                                    // k-slice of one warp (160 or 80)
+    constexpr int WS = KW + 4, VPR = KW / 4;                                      // padded smem row stride; 16-byte vectors per row slice
+    static_assert((RC + (MODE == MODE_JOINT ? 2 : 1) * SB) * WS <= STAGE_FLOATS, "staging region overflow");
     const int n_chunks = MODE == MODE_LSTM ? HID / RPL : MODE == MODE_PRED ? JOINT / RC : (VOCAB + RC - 1) / RC;
-    const int n_sblk = (n + SBLK - 1) / SBLK;
+    const int n_sblk = (n + SB - 1) / SB;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, rg = lane >> 3, sg = lane & 7;
     const int kbeg = warp * KW;
     const bool second_half = MODE == MODE_LSTM && kbeg >= HID;                    // LSTM: k < 640 is the input, k >= 640 the recurrent part
     const int koff = second_half ? kbeg - HID : kbeg;
+    float* wsm = sm.stage[warp];
+    float* xsm = wsm + RC * WS;
+    float* dsm = xsm + SB * WS;                                                   // joint only
 
     for (int item = blockIdx.x; item < n_chunks * n_sblk; item += gridDim.x) {
-        const int chunk = item % n_chunks, s0 = (item / n_chunks) * SBLK, ns = min(SBLK, n - s0);
-        const float* wp[RPL];
-#pragma unroll
-        for (int i = 0; i < RPL; ++i) {
-            if (MODE == MODE_LSTM) {                                              // row group = gate (i,f,g,o), i = unit within the chunk
-                const int row = rg * HID + chunk * RPL + i;
-                wp[i] = (second_half ? a.w.w_hh[layer] : a.w.w_ih[layer]) + (size_t)row * HID + koff;
+        const int chunk = item % n_chunks, s0 = (item / n_chunks) * SB, ns = min(SB, n - s0);
+        // ---- stage this warp's k-slice: weight rows, then the stream vectors ----
+        for (int p = lane; p < RC * VPR; p += 32) {
+            const int r = p / VPR, c = (p % VPR) * 4;
+            const float* src;
+            if (MODE == MODE_LSTM) {                                              // row group = gate (i,f,g,o), RPL units per chunk
+                const int row = (r / RPL) * HID + chunk * RPL + (r % RPL);
+                src = (second_half ? a.w.w_hh[layer] : a.w.w_ih[layer]) + (size_t)row * HID + koff + c;
             } else if (MODE == MODE_PRED) {
-                wp[i] = a.w.pred_w + (size_t)(chunk * RC + rg * RPL + i) * HID + koff;
+                src = a.w.pred_w + (size_t)(chunk * RC + r) * HID + koff + c;
             } else {
-                wp[i] = a.w.out_w + (size_t)min(chunk * RC + rg * RPL + i, VOCAB - 1) * JOINT + koff;
+                src = a.w.out_w + (size_t)min(chunk * RC + r, VOCAB - 1) * JOINT + koff + c;
             }
+            cp_async16(wsm + r * WS + c, src);
         }
-        const float* xp[SPL]; const float* xp2[SPL];
-#pragma unroll
-        for (int j = 0; j < SPL; ++j) {
-            const int g = sg + 8 * j, b = sm.list[s0 + (g < ns ? g : 0)], slot = sm.slot[b], par = sm.par[b];
+        for (int p = lane; p < ns * VPR; p += 32) {
+            const int g = p / VPR, c = (p % VPR) * 4;
+            const int b = sm.list[s0 + g], slot = sm.slot[b], par = sm.par[b];
             const float* hb = a.s.hbuf + (size_t)slot * 2 * PAR_STRIDE;
-            xp2[j] = nullptr;
+            const float* src;
             if (MODE == MODE_LSTM) {
-                if (layer == 0) xp[j] = second_half ? hb + par * PAR_STRIDE + koff                          // h0 (committed)
-                                                    : a.w.embed + (size_t)sm.prev[b] * HID + koff;          // nemo-stream.cpp:825-828
-                else xp[j] = second_half ? hb + par * PAR_STRIDE + HID + koff                               // h1 (committed)
-                                         : hb + (par ^ 1) * PAR_STRIDE + koff;                              // layer-1 input = layer-0 h'
+                if (layer == 0) src = second_half ? hb + par * PAR_STRIDE                                   // h0 (committed)
+                                                  : a.w.embed + (size_t)sm.prev[b] * HID;                   // nemo-stream.cpp:825-828
+                else src = second_half ? hb + par * PAR_STRIDE + HID                                        // h1 (committed)
+                                       : hb + (par ^ 1) * PAR_STRIDE;                                       // layer-1 input = layer-0 h'
             } else if (MODE == MODE_PRED) {
-                xp[j] = hb + (par ^ 1) * PAR_STRIDE + HID + koff;                                           // candidate decoder output
+                src = hb + (par ^ 1) * PAR_STRIDE + HID;                                                    // candidate decoder output
             } else {
-                xp[j] = a.enc_proj + ((size_t)b * a.T + sm.fi[b]) * JOINT + koff;
-                xp2[j] = a.s.dec_proj + (size_t)slot * JOINT + koff;
+                src = a.enc_proj + ((size_t)b * a.T + sm.fi[b]) * JOINT;
+                cp_async16(dsm + g * WS + c, a.s.dec_proj + (size_t)slot * JOINT + koff + c);
             }
+            cp_async16(xsm + g * WS + c, src + koff + c);
         }
+        cp_async_wait_all();
+        __syncwarp();
+
         float acc[RPL][SPL];
 #pragma unroll
         for (int i = 0; i < RPL; ++i)
 #pragma unroll
             for (int j = 0; j < SPL; ++j) acc[i][j] = 0.f;
-#pragma unroll 2
+#pragma unroll 4
         for (int k = 0; k < KW; k += 4) {
             float4 w[RPL], x[SPL];
 #pragma unroll
-            for (int i = 0; i < RPL; ++i) w[i] = ld_w(wp[i] + k);
+            for (int i = 0; i < RPL; ++i) w[i] = *reinterpret_cast<const float4*>(wsm + (rg * RPL + i) * WS + k);
 #pragma unroll
             for (int j = 0; j < SPL; ++j) {
-                x[j] = ld_x(xp[j] + k);
+                x[j] = *reinterpret_cast<const float4*>(xsm + (sg + 8 * j) * WS + k);
                 if (MODE == MODE_JOINT) {                                         // z = relu(enc_proj + pred_proj)  (nemo-ggml.cpp:1092-1094)
-                    const float4 d = ld_x(xp2[j] + k);
+                    const float4 d = *reinterpret_cast<const float4*>(dsm + (sg + 8 * j) * WS + k);
                     x[j].x = fmaxf(x[j].x + d.x, 0.f); x[j].y = fmaxf(x[j].y + d.y, 0.f);
                     x[j].z = fmaxf(x[j].z + d.z, 0.f); x[j].w = fmaxf(x[j].w + d.w, 0.f);
                 }
@@ -167,16 +188,18 @@ __device__ void phase(const DecodeArgs& a, DecSmem& sm, int layer, int n, int ro
                     acc[i][j] = fmaf(w[i].z, x[j].z, acc[i][j]); acc[i][j] = fmaf(w[i].w, x[j].w, acc[i][j]);
                 }
         }
+        __syncwarp();                                                             // the warp's partial tile reuses its own staging region
+        float* red = sm.stage[warp];
 #pragma unroll
         for (int i = 0; i < RPL; ++i)
 #pragma unroll
-            for (int j = 0; j < SPL; ++j) sm.red[warp][rg * RPL + i][sg + 8 * j] = acc[i][j];
+            for (int j = 0; j < SPL; ++j) red[(rg * RPL + i) * RSTR + sg + 8 * j] = acc[i][j];
         __syncthreads();
         for (int e = tid; e < RC * ns; e += NT) {                                 // fixed warp order => deterministic sums
             const int rr = e / ns, g = e % ns;
-            float s = sm.red[0][rr][g];
+            float s = sm.stage[0][rr * RSTR + g];
 #pragma unroll
-            for (int w8 = 1; w8 < NW; ++w8) s += sm.red[w8][rr][g];
+            for (int w8 = 1; w8 < NW; ++w8) s += sm.stage[w8][rr * RSTR + g];
             sm.sums[rr][g] = s;
         }
         __syncthreads();
@@ -215,18 +238,16 @@ __device__ void phase(const DecodeArgs& a, DecSmem& sm, int layer, int n, int ro
                 atomicMax(a.best + (size_t)(round % 3) * a.B + b, argmax_key(bv, bi));
             }
         }
-        __syncthreads();                                                          // red / sums are reused by the next item
+        __syncthreads();                                                          // staging regions / sums are reused by the next item
     }
 }
 
 template <int MODE>
 __device__ __forceinline__ void phase_dispatch(const DecodeArgs& a, DecSmem& sm, int layer, int n, int round, int ne0) {
     constexpr int RPL = MODE == MODE_LSTM ? 5 : 2;
-    const int m = min(n, SBLK);
-    if (m <= 8) phase<RPL, 1, MODE>(a, sm, layer, n, round, ne0);
-    else if (m <= 16) phase<RPL, 2, MODE>(a, sm, layer, n, round, ne0);
-    else if (m <= 32) phase<RPL, 4, MODE>(a, sm, layer, n, round, ne0);
-    else phase<RPL, 8, MODE>(a, sm, layer, n, round, ne0);
+    if (n <= 8) phase<RPL, 1, MODE>(a, sm, layer, n, round, ne0);
+    else if constexpr (MODE == MODE_LSTM) phase<RPL, 2, MODE>(a, sm, layer, n, round, ne0);
+    else { if (n <= 16) phase<RPL, 2, MODE>(a, sm, layer, n, round, ne0); else phase<RPL, 4, MODE>(a, sm, layer, n, round, ne0); }
 }
 
 __global__ void __launch_bounds__(NT, 1) rnnt_decode_kernel(const DecodeArgs a) {

@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
                                                      const float* __restrict__ window, const float* __restrict__ cos_t,
                                                      const float* __restrict__ sin_t, const float* __restrict__ fb_t,
                                                      float* __restrict__ mel_out, size_t out_batch_stride) {
+    pdl_wait(); pdl_trigger();
     __shared__ float re[N_FFT], im[N_FFT], pw[N_BINS + 3];
     const int j = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
     const int16_t* row = pcm + (size_t)b * pcm_row_stride + (size_t)j * HOP;   // row[0] = sample before the frame
@@ -63,8 +64,8 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
 void launch_logmel(const int16_t* pcm, int pcm_row_stride, int B, int n_frames, const float* window512, const float* cos_t,
                    const float* sin_t, const float* fb_t, float* mel_out, size_t out_batch_stride, cudaStream_t st) {
     if (B <= 0 || n_frames <= 0) return;
-    logmel_kernel<<<dim3(n_frames, B), 256, 0, st>>>(pcm, pcm_row_stride, n_frames, window512, cos_t, sin_t, fb_t, mel_out,
-                                                     out_batch_stride);
+    launch_k(logmel_kernel, dim3(n_frames, B), dim3(256), 0, st, pcm, pcm_row_stride, n_frames, window512, cos_t, sin_t, fb_t, mel_out,
+             out_batch_stride);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -81,6 +82,7 @@ __device__ __forceinline__ float chunk_mel(const float* __restrict__ hist, const
 __global__ void __launch_bounds__(SUB_CH) conv0_kernel(const float* __restrict__ hist, const float* __restrict__ mel_new,
                                                        const int* __restrict__ slot_of_b, int T, const float* __restrict__ w_t,
                                                        const float* __restrict__ bias, float* __restrict__ out) {
+    pdl_wait(); pdl_trigger();
     const int ow = blockIdx.x, oh = blockIdx.y, b = blockIdx.z, oc = threadIdx.x;
     const int M = PRE_CACHE + 8 * T, t1 = gridDim.y, W1 = gridDim.x;
     const int slot = slot_of_b[b];
@@ -102,11 +104,12 @@ __global__ void __launch_bounds__(SUB_CH) conv0_kernel(const float* __restrict__
 void launch_conv0(const float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, const float* w_t,
                   const float* bias, float* out, cudaStream_t st) {
     const int M = PRE_CACHE + 8 * T, t1 = M / 2 + 1, W1 = N_MELS / 2 + 1;
-    conv0_kernel<<<dim3(W1, t1, B), SUB_CH, 0, st>>>(mel_hist, mel_new, slot_of_b, T, w_t, bias, out);
+    launch_k(conv0_kernel, dim3(W1, t1, B), dim3(SUB_CH), 0, st, mel_hist, mel_new, slot_of_b, T, w_t, bias, out);
 }
 
 __global__ void __launch_bounds__(N_MELS) mel_hist_update_kernel(float* __restrict__ hist, const float* __restrict__ mel_new,
                                                                  const int* __restrict__ slot_of_b, int T) {
+    pdl_wait(); pdl_trigger();
     const int b = blockIdx.x, m = threadIdx.x, slot = slot_of_b[b];
     float v[PRE_CACHE];
 #pragma unroll
@@ -115,21 +118,23 @@ __global__ void __launch_bounds__(N_MELS) mel_hist_update_kernel(float* __restri
     for (int f = 0; f < PRE_CACHE; ++f) hist[((size_t)slot * PRE_CACHE + f) * N_MELS + m] = v[f];
 }
 void launch_mel_hist_update(float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, cudaStream_t st) {
-    mel_hist_update_kernel<<<B, N_MELS, 0, st>>>(mel_hist, mel_new, slot_of_b, T);
+    launch_k(mel_hist_update_kernel, dim3(B), dim3(N_MELS), 0, st, mel_hist, mel_new, slot_of_b, T);
 }
 
 __global__ void __launch_bounds__(N_MELS) mel_gather_kernel(const float* __restrict__ hist, const float* __restrict__ mel_new,
                                                             const int* __restrict__ slot_of_b, int T, float* __restrict__ out) {
+    pdl_wait(); pdl_trigger();
     const int f = blockIdx.x, b = blockIdx.y, m = threadIdx.x, M = PRE_CACHE + 8 * T;
     out[((size_t)b * M + f) * N_MELS + m] = chunk_mel(hist, mel_new, slot_of_b[b], b, T, f, m);
 }
 void launch_mel_gather(const float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, float* out, cudaStream_t st) {
-    mel_gather_kernel<<<dim3(PRE_CACHE + 8 * T, B), N_MELS, 0, st>>>(mel_hist, mel_new, slot_of_b, T, out);
+    launch_k(mel_gather_kernel, dim3(PRE_CACHE + 8 * T, B), dim3(N_MELS), 0, st, mel_hist, mel_new, slot_of_b, T, out);
 }
 
 // depthwise 3x3 stride 2 (+bias, no activation), NHWC with C = 256: thread = channel.
 __global__ void __launch_bounds__(SUB_CH) dwconv_s2_kernel(const float* __restrict__ in, int H, int W, const float* __restrict__ w_t,
                                                            const float* __restrict__ bias, float* __restrict__ out) {
+    pdl_wait(); pdl_trigger();
     const int ow = blockIdx.x, oh = blockIdx.y, b = blockIdx.z, c = threadIdx.x;
     const int Ho = gridDim.y, Wo = gridDim.x;
     float acc = 0.0f;
@@ -147,7 +152,7 @@ __global__ void __launch_bounds__(SUB_CH) dwconv_s2_kernel(const float* __restri
     out[(((size_t)b * Ho + oh) * Wo + ow) * SUB_CH + c] = acc + bias[c];
 }
 void launch_dwconv_s2(const float* in, int B, int H, int W, const float* w_t, const float* bias, float* out, cudaStream_t st) {
-    dwconv_s2_kernel<<<dim3(W / 2 + 1, H / 2 + 1, B), SUB_CH, 0, st>>>(in, H, W, w_t, bias, out);
+    launch_k(dwconv_s2_kernel, dim3(W / 2 + 1, H / 2 + 1, B), dim3(SUB_CH), 0, st, in, H, W, w_t, bias, out);
 }
 
 }  // namespace nsb

@@ -46,6 +46,7 @@ __device__ __forceinline__ float4 load_x_reduced(float* x, size_t o, const Parti
 
 __global__ void __launch_bounds__(256) layernorm_kernel(float* x, const float* __restrict__ g,
                                                         const float* __restrict__ b, void* y, int out_type, const PartialSum ps) {
+    pdl_wait(); pdl_trigger();
     __shared__ float red[8];
     const int row = blockIdx.x, c = threadIdx.x * 4;
     const float4 v = load_x_reduced(x, (size_t)row * D_MODEL + c, ps, gridDim.x);
@@ -61,13 +62,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* x, const float* _
     else { __nv_bfloat162* p = (__nv_bfloat162*)((__nv_bfloat16*)y + o); p[0] = __floats2bfloat162_rn(o0, o1); p[1] = __floats2bfloat162_rn(o2, o3); }
 }
 void launch_layernorm(float* x, int rows, const float* g, const float* b, void* y, int out_type, const PartialSum& ps, cudaStream_t st) {
-    if (rows > 0) layernorm_kernel<<<rows, 256, 0, st>>>(x, g, b, y, out_type, ps);
+    if (rows > 0) launch_k(layernorm_kernel, dim3(rows), dim3(256), 0, st, x, g, b, y, out_type, ps);
 }
 
 // norm_out of layer l fused with norm_feed_forward1 of layer l+1: x <- LN1(x) (f32, in place); y2 <- LN2(x)
 __global__ void __launch_bounds__(256) layernorm2_kernel(float* x, const float* __restrict__ g1, const float* __restrict__ b1,
                                                          const float* __restrict__ g2, const float* __restrict__ b2,
                                                          void* y2, int out_type, const PartialSum ps) {
+    pdl_wait(); pdl_trigger();
     __shared__ float red[8];
     const int row = blockIdx.x, c = threadIdx.x * 4;
     const size_t o = (size_t)row * D_MODEL + c;
@@ -92,148 +94,210 @@ __global__ void __launch_bounds__(256) layernorm2_kernel(float* x, const float* 
 }
 void launch_layernorm2(float* x, int rows, const float* g1, const float* b1, const float* g2, const float* b2, void* y2, int out_type,
                        const PartialSum& ps, cudaStream_t st) {
-    if (rows > 0) layernorm2_kernel<<<rows, 256, 0, st>>>(x, g1, b1, g2, b2, y2, out_type, ps);
+    if (rows > 0) launch_k(layernorm2_kernel, dim3(rows), dim3(256), 0, st, x, g1, b1, g2, b2, y2, out_type, ps);
 }
 
 // ------------------------------------------------------------------------------------------
-// Cached relative-position attention. One CTA per (head, batch row); 256 threads.
+// Cached relative-position attention. One CTA per (head, batch row); 256 threads = 8 warps.
 //   keys j = 0..K-1 (K = L+T): j < L are ring rows (oldest first), j >= L are this chunk's new rows
 //   score[i][j] = ((q_i + u) . k_j + (q_i + v) . P[L + i - j]) / sqrt(128),  j >= L - valid_len
 //   ctx[i] = softmax_j(score[i]) . v_j
-// All global traffic happens in one bulk staging phase (K, V head slices of the ring, the head slice of the projected
-// positional table, q) with 16-byte loads and no dependent chains; scores / softmax / context then run out of shared
-// memory. Row strides are padded by 16 bytes so that 16-byte row-wise reads by consecutive threads are conflict-free.
-// The CTA also appends this chunk's K/V rows for its head to the ring (positions (w + i) mod (L+T)).
+// One memory round trip per CTA: the valid ring rows of K and V for this head (the only HBM traffic, each byte read
+// exactly once) are fetched with a single burst of 16-byte cp.async into shared memory; while they are in flight the
+// warps compute the positional term (q+v).P[r] straight from the L2-resident projected table (one row per warp step,
+// all rows of a warp requested before the first is used) and append this chunk's K/V rows to the ring (positions
+// (w + i) mod (L+T), replacing the reference's concat + roll, nemo-stream.cpp:465-484). Lanes hold 4 of the 128 head dims
+// of (q+u), (q+v) for up to TQ queries in registers. 16-bit K/V keep the CTA at ~44 KB of shared memory, so all
+// 8 x 64 CTAs of a 64-stream step are resident at once (4 per SM).
 // ------------------------------------------------------------------------------------------
 template <int KV> struct KvT { using type = float; };
 template <> struct KvT<1> { using type = __half; };
 template <> struct KvT<2> { using type = __nv_bfloat16; };
 
-template <typename E> struct AttnLayout {
-    static constexpr int EPV = 16 / sizeof(E);                 // elements per 16-byte vector
-    static constexpr int KSTR = D_HEAD + EPV;                  // padded row stride (elements) of K / V tiles
-    static constexpr int PSTR = D_HEAD + 4;                    // padded row stride (floats) of the P tile and q rows
+constexpr int ATT_MAX_T = 65, ATT_MAX_K = ATT_L + ATT_MAX_T + 1, ATT_MAX_REL = ATT_L + 2 * ATT_MAX_T;
+constexpr int ATT_PROWS = 5;                                     // positional rows per warp held in flight
+
+__device__ __forceinline__ void load4(const float* p, float (&f)[4]) {
+    const float4 v = *reinterpret_cast<const float4*>(p); f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+}
+__device__ __forceinline__ void load4(const __half* p, float (&f)[4]) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+__device__ __forceinline__ void load4(const __nv_bfloat16* p, float (&f)[4]) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+__device__ __forceinline__ void load2(const float* p, float (&f)[2]) { const float2 v = *reinterpret_cast<const float2*>(p); f[0] = v.x; f[1] = v.y; }
+__device__ __forceinline__ void load2(const __half* p, float (&f)[2]) { const float2 v = __half22float2(*reinterpret_cast<const __half2*>(p)); f[0] = v.x; f[1] = v.y; }
+__device__ __forceinline__ void load2(const __nv_bfloat16* p, float (&f)[2]) { const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); f[0] = v.x; f[1] = v.y; }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+template <int TQ> struct AttnSmemF {                             // fp32 part of the shared memory (K / V tiles follow)
+    float ac[TQ][ATT_MAX_K];                                     // (q+u).k, then probabilities
+    float bd[TQ][ATT_MAX_REL];                                   // (q+v).P[r]
+    float red[4][TQ][D_HEAD];
 };
 
-__device__ __forceinline__ void unpack16(const uint4& v, float (&f)[4], const float*) {
-    f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y); f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
-}
-__device__ __forceinline__ void unpack16(const uint4& v, float (&f)[8], const __half*) {
-    const __half2* h = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
-}
-__device__ __forceinline__ void unpack16(const uint4& v, float (&f)[8], const __nv_bfloat16*) {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
-}
-
-template <int KV>
-__global__ void __launch_bounds__(256) attention_kernel(const AttnArgs a) {
+template <int KV, int TQ>
+__global__ void __launch_bounds__(256, TQ <= 2 ? 4 : 2) attention_kernel(const AttnArgs a) {
     using E = typename KvT<KV>::type;
-    using Lay = AttnLayout<E>;
-    constexpr int EPV = Lay::EPV, KSTR = Lay::KSTR, PSTR = Lay::PSTR;
-    extern __shared__ __align__(16) uint8_t sm_raw[];
-    const int T = a.T, K = ATT_L + T, Cap = K, n_rel = ATT_L + 2 * T - 1;
-    E* Ks = reinterpret_cast<E*>(sm_raw);                       // [K][KSTR]
-    E* Vs = Ks + (size_t)K * KSTR;                              // [K][KSTR]
-    float* Ps = reinterpret_cast<float*>(Vs + (size_t)K * KSTR);   // [n_rel][PSTR]
-    float* qu = Ps + (size_t)n_rel * PSTR;                      // [T][PSTR]
-    float* qv = qu + (size_t)T * PSTR;                          // [T][PSTR]
-    float* sc = qv + (size_t)T * PSTR;                          // [T][K]
+    constexpr int EPV = 16 / sizeof(E), VPR = D_HEAD / EPV;                     // elements per 16-byte vector, vectors per row
+    extern __shared__ __align__(16) uint8_t att_smem[];
+    AttnSmemF<TQ>& sf = *reinterpret_cast<AttnSmemF<TQ>*>(att_smem);
+    const int T = a.T, K = ATT_L + T, Cap = K;
+    E* Ks = reinterpret_cast<E*>(att_smem + sizeof(AttnSmemF<TQ>));             // [K][128]
+    E* Vs = Ks + (size_t)K * D_HEAD;                                            // [K][128]
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_wait(); pdl_trigger();
     const int slot = a.slot_of_b[b], w = a.ring_pos[slot], valid = a.valid_len[slot];
     const int first = ATT_L - valid;                                           // keys j < first are not yet valid (:982-992)
-    const float* qkv = a.qkv + (size_t)b * T * 3 * D_MODEL;
-    const size_t ring_base = (size_t)slot * a.slot_stride + h * D_HEAD;
-    E* kring = reinterpret_cast<E*>(a.k_ring); E* vring = reinterpret_cast<E*>(a.v_ring);
+    const float* qkv = a.qkv + (size_t)b * T * 3 * D_MODEL + h * D_HEAD;
+    E* kring = reinterpret_cast<E*>(a.k_ring) + (size_t)slot * a.slot_stride + h * D_HEAD;
+    E* vring = reinterpret_cast<E*>(a.v_ring) + (size_t)slot * a.slot_stride + h * D_HEAD;
+    const float* P = a.pos_proj + h * D_HEAD;
+    auto ring_row = [&](int j) { return (size_t)((w + Cap - ATT_L + j) % Cap) * D_MODEL; };
 
-    // ---- bulk staging: cached K/V rows (16-byte loads), positional slice, q; new rows go to smem AND to the ring ----
-    constexpr int VPR = D_HEAD / EPV;                                          // 16-byte vectors per row
+    // ---- one burst: valid cached K / V rows -> shared memory ----
     for (int e = tid; e < (ATT_L - first) * VPR; e += 256) {
         const int j = first + e / VPR, c = (e % VPR) * EPV;
-        const int rrow = (w + Cap - ATT_L + j) % Cap;
-        const size_t g = ring_base + (size_t)rrow * D_MODEL + c;
-        *reinterpret_cast<uint4*>(Ks + (size_t)j * KSTR + c) = *reinterpret_cast<const uint4*>(kring + g);
-        *reinterpret_cast<uint4*>(Vs + (size_t)j * KSTR + c) = *reinterpret_cast<const uint4*>(vring + g);
+        const size_t g = ring_row(j) + c;
+        cp_async16(Ks + (size_t)j * D_HEAD + c, kring + g);
+        cp_async16(Vs + (size_t)j * D_HEAD + c, vring + g);
     }
-    for (int e = tid; e < n_rel * (D_HEAD / 4); e += 256) {
-        const int r = e / (D_HEAD / 4), c = (e % (D_HEAD / 4)) * 4;
-        *reinterpret_cast<float4*>(Ps + (size_t)r * PSTR + c) = *reinterpret_cast<const float4*>(a.pos_proj + (size_t)r * D_MODEL + h * D_HEAD + c);
-    }
-    for (int e = tid; e < T * D_HEAD; e += 256) {
-        const int i = e / D_HEAD, d = e % D_HEAD;
-        const float* row = qkv + (size_t)i * 3 * D_MODEL + h * D_HEAD + d;
-        const float q = row[0];
-        qu[i * PSTR + d] = q + a.bias_u[h * D_HEAD + d];                       // :503-507
-        qv[i * PSTR + d] = q + a.bias_v[h * D_HEAD + d];
-        const E kn = from_f32<E>(row[D_MODEL]), vn = from_f32<E>(row[2 * D_MODEL]);
-        Ks[(size_t)(ATT_L + i) * KSTR + d] = kn; Vs[(size_t)(ATT_L + i) * KSTR + d] = vn;
-        const size_t r = ring_base + (size_t)((w + i) % Cap) * D_MODEL + d;    // append (replaces concat + roll :465-484)
-        kring[r] = kn; vring[r] = vn;
-    }
-    __syncthreads();
-
-    // ---- scores: one thread per (query i, key j) pair, full 128-dim dot products out of shared memory ----
-    const float scale = 0.08838834764831845f;                                   // 1/sqrt(128) :517
-    const int nkeys = K - first;
-    for (int p = tid; p < T * nkeys; p += 256) {
-        const int i = p / nkeys, j = first + p % nkeys;
-        const E* kr = Ks + (size_t)j * KSTR;
-        const float* pr = Ps + (size_t)((ATT_L + i - j) + (T - 1)) * PSTR;      // rel = L + i - j
-        const float* qur = qu + i * PSTR; const float* qvr = qv + i * PSTR;
-        float s = 0.f;
-#pragma unroll 4
-        for (int c = 0; c < D_HEAD; c += EPV) {
-            float kf[EPV];
-            unpack16(*reinterpret_cast<const uint4*>(kr + c), kf, (const E*)nullptr);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // ---- this chunk's K / V rows (rounded to the ring dtype): shared memory AND ring append ----
+    for (int e = tid; e < T * (D_HEAD / 4); e += 256) {
+        const int i = e / (D_HEAD / 4), c = (e % (D_HEAD / 4)) * 4;
+        const float4 kn = *reinterpret_cast<const float4*>(qkv + (size_t)i * 3 * D_MODEL + D_MODEL + c);
+        const float4 vn = *reinterpret_cast<const float4*>(qkv + (size_t)i * 3 * D_MODEL + 2 * D_MODEL + c);
+        const E k4[4] = {from_f32<E>(kn.x), from_f32<E>(kn.y), from_f32<E>(kn.z), from_f32<E>(kn.w)};
+        const E v4[4] = {from_f32<E>(vn.x), from_f32<E>(vn.y), from_f32<E>(vn.z), from_f32<E>(vn.w)};
+        E* kd = kring + ring_row(ATT_L + i) + c; E* vd = vring + ring_row(ATT_L + i) + c;
+        E* ks = Ks + (size_t)(ATT_L + i) * D_HEAD + c; E* vs = Vs + (size_t)(ATT_L + i) * D_HEAD + c;
 #pragma unroll
-            for (int u = 0; u < EPV; u += 4) {
-                const float4 q4 = *reinterpret_cast<const float4*>(qur + c + u), v4 = *reinterpret_cast<const float4*>(qvr + c + u);
-                const float4 p4 = *reinterpret_cast<const float4*>(pr + c + u);
-                s = fmaf(q4.x, kf[u], s); s = fmaf(q4.y, kf[u + 1], s); s = fmaf(q4.z, kf[u + 2], s); s = fmaf(q4.w, kf[u + 3], s);
-                s = fmaf(v4.x, p4.x, s); s = fmaf(v4.y, p4.y, s); s = fmaf(v4.z, p4.z, s); s = fmaf(v4.w, p4.w, s);
+        for (int u = 0; u < 4; ++u) { kd[u] = k4[u]; vd[u] = v4[u]; ks[u] = k4[u]; vs[u] = v4[u]; }
+    }
+
+    const float scale = 0.08838834764831845f;                                   // 1/sqrt(128) :517
+    const int c4 = lane * 4;
+    float bu[4], bv[4];
+    load4(a.bias_u + h * D_HEAD + c4, bu); load4(a.bias_v + h * D_HEAD + c4, bv);
+    for (int q0 = 0; q0 < T; q0 += TQ) {
+        const int nq = min(TQ, T - q0);
+        float qu[TQ][4], qv[TQ][4];
+#pragma unroll
+        for (int i = 0; i < TQ; ++i) {
+            float q[4] = {0.f, 0.f, 0.f, 0.f};
+            if (i < nq) load4(qkv + (size_t)(q0 + i) * 3 * D_MODEL + c4, q);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { qu[i][u] = q[u] + bu[u]; qv[i][u] = q[u] + bv[u]; }   // :503-507
+        }
+        // ---- BD_raw[i][r] = (q_i + v) . P[r], r = rel + (T-1), from L2; overlaps the K / V burst of the first tile ----
+        const int r_end = ATT_L + T - 1 + (q0 + nq - 1) - first + 1;            // largest row index used + 1
+        for (int rb = 0; rb < r_end; rb += 8 * ATT_PROWS) {
+            float pf[ATT_PROWS][4];
+#pragma unroll
+            for (int r = 0; r < ATT_PROWS; ++r) { const int rr = rb + warp + 8 * r; if (rr < r_end) load4(P + (size_t)rr * D_MODEL + c4, pf[r]); }
+#pragma unroll
+            for (int r = 0; r < ATT_PROWS; ++r) {
+                const int rr = rb + warp + 8 * r;
+                if (rr < r_end) {
+#pragma unroll
+                    for (int i = 0; i < TQ; ++i) {
+                        float s = qv[i][0] * pf[r][0];
+                        s = fmaf(qv[i][1], pf[r][1], s); s = fmaf(qv[i][2], pf[r][2], s); s = fmaf(qv[i][3], pf[r][3], s);
+                        s = warp_sum(s);
+                        if (lane == 0) sf.bd[i][rr] = s;
+                    }
+                }
             }
         }
-        sc[i * K + j] = s * scale;
-    }
-    __syncthreads();
-    for (int i = warp; i < T; i += 8) {                                         // softmax over valid keys
-        float mx = -INFINITY;
-        for (int j = first + lane; j < K; j += 32) mx = fmaxf(mx, sc[i * K + j]);
-        mx = warp_max(mx);
-        float sum = 0.f;
-        for (int j = first + lane; j < K; j += 32) { const float e = expf(sc[i * K + j] - mx); sc[i * K + j] = e; sum += e; }
-        sum = warp_sum(sum);
-        const float inv = 1.0f / sum;
-        for (int j = first + lane; j < K; j += 32) sc[i * K + j] *= inv;
-    }
-    __syncthreads();
-    // ---- ctx[i][d] = sum_j p[i][j] v_j[d]; thread = (i parity, d) ----
-    const int d = tid & 127;
-    for (int i = tid >> 7; i < T; i += 2) {
-        float acc = 0.f;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                                          // K / V tiles, new rows and BD visible to all warps
+        // ---- AC[i][j] = (q_i + u) . k_j : one key row per warp step out of shared memory ----
+        for (int j = first + warp; j < K; j += 8) {
+            float kf[4];
+            load4(Ks + (size_t)j * D_HEAD + c4, kf);
+#pragma unroll
+            for (int i = 0; i < TQ; ++i) {
+                float s = qu[i][0] * kf[0];
+                s = fmaf(qu[i][1], kf[1], s); s = fmaf(qu[i][2], kf[2], s); s = fmaf(qu[i][3], kf[3], s);
+                s = warp_sum(s);
+                if (lane == 0) sf.ac[i][j] = s;
+            }
+        }
+        __syncthreads();
+        // ---- softmax over valid keys; rel-shift = index arithmetic: BD[i][j] = BD_raw[i][L + i - j + T-1] (:391-433) ----
+        for (int i = warp; i < nq; i += 8) {
+            const int qi = q0 + i;
+            float mx = -INFINITY;
+            for (int j = first + lane; j < K; j += 32) {
+                const float s = (sf.ac[i][j] + sf.bd[i][ATT_L + qi - j + T - 1]) * scale;
+                sf.ac[i][j] = s; mx = fmaxf(mx, s);
+            }
+            mx = warp_max(mx);
+            float sum = 0.f;
+            for (int j = first + lane; j < K; j += 32) { const float e = expf(sf.ac[i][j] - mx); sf.ac[i][j] = e; sum += e; }
+            sum = warp_sum(sum);
+            const float inv = 1.0f / sum;
+            for (int j = first + lane; j < K; j += 32) sf.ac[i][j] *= inv;
+        }
+        __syncthreads();
+        // ---- ctx[i][d] = sum_j p[i][j] v_j[d]; thread = (key group kg, 2 dims) ----
+        {
+            const int d2 = (tid & 63) * 2, kg = tid >> 6;
+            float acc[TQ][2];
+#pragma unroll
+            for (int i = 0; i < TQ; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
 #pragma unroll 4
-        for (int j = first; j < K; ++j) acc = fmaf(sc[i * K + j], to_f32(Vs[(size_t)j * KSTR + d]), acc);
-        store_out(a.ctx, ((size_t)b * T + i) * D_MODEL + h * D_HEAD + d, acc, a.out_type);
+            for (int j = first + kg; j < K; j += 4) {
+                float vf[2];
+                load2(Vs + (size_t)j * D_HEAD + d2, vf);
+#pragma unroll
+                for (int i = 0; i < TQ; ++i) {
+                    const float p = sf.ac[i][j];
+                    acc[i][0] = fmaf(p, vf[0], acc[i][0]); acc[i][1] = fmaf(p, vf[1], acc[i][1]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < TQ; ++i) { sf.red[kg][i][d2] = acc[i][0]; sf.red[kg][i][d2 + 1] = acc[i][1]; }
+        }
+        __syncthreads();
+        for (int e = tid; e < nq * D_HEAD; e += 256) {
+            const int i = e / D_HEAD, d = e % D_HEAD;
+            const float v = (sf.red[0][i][d] + sf.red[1][i][d]) + (sf.red[2][i][d] + sf.red[3][i][d]);
+            store_out(a.ctx, ((size_t)b * T + q0 + i) * D_MODEL + h * D_HEAD + d, v, a.out_type);
+        }
+        __syncthreads();                                                          // ac / bd / red are reused by the next query tile
     }
 }
 
-template <int KV>
-static void launch_attention_t(const AttnArgs& a, cudaStream_t st) {
+template <int KV, int TQ>
+static void launch_attention_tq(const AttnArgs& a, cudaStream_t st) {
     using E = typename KvT<KV>::type;
-    using Lay = AttnLayout<E>;
-    const int K = ATT_L + a.T, n_rel = ATT_L + 2 * a.T - 1;
-    const size_t smem = (size_t)2 * K * Lay::KSTR * sizeof(E) + (size_t)(n_rel + 2 * a.T) * Lay::PSTR * 4 + (size_t)a.T * K * 4;
+    const size_t smem = sizeof(AttnSmemF<TQ>) + (size_t)2 * (ATT_L + a.T) * D_HEAD * sizeof(E);
     static size_t configured = 0;
     if (smem > configured) {
-        NSB_CUDA(cudaFuncSetAttribute(attention_kernel<KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NSB_CUDA(cudaFuncSetAttribute(attention_kernel<KV, TQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    attention_kernel<KV><<<dim3(N_HEADS, a.B), 256, smem, st>>>(a);
+    launch_k(attention_kernel<KV, TQ>, dim3(N_HEADS, a.B), dim3(256), smem, st, a);
+}
+template <int KV>
+static void launch_attention_t(const AttnArgs& a, cudaStream_t st) {
+    if (a.T > ATT_MAX_T) throw CudaError("attention: att_right_context too large");
+    if (a.T == 1) launch_attention_tq<KV, 1>(a, st);
+    else if (a.T == 2) launch_attention_tq<KV, 2>(a, st);
+    else if (a.T <= 4) launch_attention_tq<KV, 4>(a, st);
+    else launch_attention_tq<KV, 8>(a, st);
 }
 void launch_attention(const AttnArgs& a, cudaStream_t st) {
+    if (a.B <= 0) return;
     if (a.kv_dtype == 0) launch_attention_t<0>(a, st);
     else if (a.kv_dtype == 1) launch_attention_t<1>(a, st);
     else launch_attention_t<2>(a, st);
@@ -244,6 +308,7 @@ void launch_attention(const AttnArgs& a, cudaStream_t st) {
 // One CTA per batch row (stream), 256 threads x 4 channels, a 9-deep register window slides over time.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv_module_kernel(const ConvModArgs a) {
+    pdl_wait(); pdl_trigger();
     __shared__ float red[8];
     const int b = blockIdx.x, c0 = threadIdx.x * 4, T = a.T;
     const int slot = a.slot_of_b[b];
@@ -294,10 +359,11 @@ __global__ void __launch_bounds__(256) conv_module_kernel(const ConvModArgs a) {
         *(float4*)(cache + (size_t)k * D_MODEL + c0) = make_float4(win[0][k], win[1][k], win[2][k], win[3][k]);
 }
 void launch_conv_module(const ConvModArgs& a, cudaStream_t st) {
-    if (a.B > 0) conv_module_kernel<<<a.B, 256, 0, st>>>(a);
+    if (a.B > 0) launch_k(conv_module_kernel, dim3(a.B), dim3(256), 0, st, a);
 }
 
 __global__ void advance_streams_kernel(const int* __restrict__ slot_of_b, int B, int T, int* ring_pos, int* valid_len) {
+    pdl_wait(); pdl_trigger();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int s = slot_of_b[b];
@@ -305,7 +371,7 @@ __global__ void advance_streams_kernel(const int* __restrict__ slot_of_b, int B,
     valid_len[s] = min(valid_len[s] + T, ATT_L);                                 // :1018
 }
 void launch_advance_streams(const int* slot_of_b, int B, int T, int* ring_pos, int* valid_len, cudaStream_t st) {
-    if (B > 0) advance_streams_kernel<<<(B + 127) / 128, 128, 0, st>>>(slot_of_b, B, T, ring_pos, valid_len);
+    if (B > 0) launch_k(advance_streams_kernel, dim3((B + 127) / 128), dim3(128), 0, st, slot_of_b, B, T, ring_pos, valid_len);
 }
 
 }  // namespace nsb

@@ -3,7 +3,8 @@
 TAG=${1:-r1}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-python -m pytest tests -m gpu -x -q > $OUT/pytest.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest.log; tail -3 $OUT/pytest.log
+python -m pytest tests -m gpu -x -q > $OUT/pytest.log 2>&1; RC=$?; echo "pytest rc=$RC" | tee -a $OUT/pytest.log; tail -3 $OUT/pytest.log
+if [ $RC -ne 0 ]; then NSB_NO_PDL=1 python -m pytest tests -m gpu -x -q > $OUT/pytest_nopdl.log 2>&1; echo "pytest (no PDL) rc=$?"; tail -3 $OUT/pytest_nopdl.log; fi
 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; cat $OUT/bench.json
 if [ "${NCU:-1}" = "1" ]; then
 python tools/ncu_step.py 2 > $OUT/plain.log 2>&1 &&
