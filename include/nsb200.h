@@ -118,6 +118,10 @@ int nsb_bench_step(nsb_engine* e, float* ms);
 #define NSB_PROFILE_CLASSES 8
 int nsb_bench_profile(nsb_engine* e, float* ms_per_class, int* launches_per_class, float* total_ms);
 
+/* tuning hook: `iters` passes over every layer's weight of one kind (0 ff1.linear1, 1 ff1.linear2, 2 qkv, 3 attn out, 4 pw1,
+ * 5 pw2) with an explicit tcgen05 tile config (bn, stages, split-K, k rotation); *us = mean device microseconds per GEMM */
+int nsb_bench_gemm(nsb_engine* e, int kind, int rows, int bn, int stages, int splits, int rotate, int iters, float* us);
+
 /* cudaProfilerStart / cudaProfilerStop, so that `ncu --profile-from-start off` captures only the steady-state steps */
 int nsb_profiler_range(int on);
 

@@ -42,7 +42,7 @@ EXPORTS = ["nsb_gguf_probe", "nsb_default_config", "nsb_engine_create", "nsb_eng
            "nsb_engine_vocab_size", "nsb_engine_vocab", "nsb_engine_chunk_samples", "nsb_engine_shift_samples", "nsb_engine_compute",
            "nsb_stream_open", "nsb_stream_close", "nsb_stream_reset", "nsb_stream_push_pcm", "nsb_stream_ready", "nsb_engine_step",
            "nsb_engine_drain", "nsb_stream_pop_tokens", "nsb_stream_chunks", "nsb_detokenize", "nsb_engine_get_stats",
-           "nsb_bench_prepare", "nsb_bench_step", "nsb_bench_profile", "nsb_profiler_range", "nsb_debug_enable", "nsb_debug_get", "nsb_debug_get_cache", "nsb_op_logmel",
+           "nsb_bench_prepare", "nsb_bench_step", "nsb_bench_profile", "nsb_profiler_range", "nsb_bench_gemm", "nsb_debug_enable", "nsb_debug_get", "nsb_debug_get_cache", "nsb_op_logmel",
            "nsb_op_gemm"]
 
 
@@ -86,6 +86,7 @@ def lib():
         L.nsb_bench_step.argtypes = [vp, C.POINTER(C.c_float)]
         L.nsb_bench_profile.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_float)]
         L.nsb_profiler_range.argtypes = [ci]
+        L.nsb_bench_gemm.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, C.POINTER(C.c_float)]
         L.nsb_debug_enable.argtypes = [vp, ci]
         L.nsb_debug_get.argtypes = [vp, C.c_char_p, _f32p, C.c_size_t]
         L.nsb_debug_get_cache.argtypes = [vp, ci, ci, ci, _f32p, C.c_size_t]
@@ -201,6 +202,11 @@ class Engine:
         tot = C.c_float()
         _check(lib().nsb_bench_profile(self.h, ms, n, C.byref(tot)))
         return {k: (ms[i], n[i]) for i, k in enumerate(self.PROFILE_CLASSES)}, tot.value
+
+    def bench_gemm(self, kind: int, rows: int, bn: int, stages: int, splits: int = 1, rotate: int = 1, iters: int = 5) -> float:
+        us = C.c_float()
+        _check(lib().nsb_bench_gemm(self.h, kind, rows, bn, stages, splits, rotate, iters, C.byref(us)))
+        return us.value
 
     # ---- debug / operators ----
     def debug_enable(self, on: bool = True):

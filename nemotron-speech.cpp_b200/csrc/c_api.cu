@@ -111,6 +111,9 @@ int nsb_bench_profile(nsb_engine* e, float* ms_per_class, int* launches_per_clas
     if (!e || !ms_per_class || !launches_per_class) return fail(NSB_ERR_ARG, "bad argument");
     NSB_TRY const float t = e->impl->bench_profile(ms_per_class, launches_per_class); if (total_ms) *total_ms = t; return NSB_OK; NSB_CATCH }
 
+int nsb_bench_gemm(nsb_engine* e, int kind, int rows, int bn, int stages, int splits, int rotate, int iters, float* us) {
+    if (!e || !us) return fail(NSB_ERR_ARG, "bad argument"); NSB_TRY *us = e->impl->bench_gemm(kind, rows, bn, stages, splits, rotate, iters); return NSB_OK; NSB_CATCH }
+
 int nsb_profiler_range(int on) { return (on ? cudaProfilerStart() : cudaProfilerStop()) == cudaSuccess ? NSB_OK : NSB_ERR_CUDA; }
 
 int nsb_debug_enable(nsb_engine* e, int on) { if (!e) return fail(NSB_ERR_ARG, "null engine"); NSB_TRY e->impl->debug_enable(on != 0); return NSB_OK; NSB_CATCH }

@@ -583,6 +583,32 @@ float Engine::bench_step() {
     return ms;
 }
 
+float Engine::bench_gemm(int kind, int rows, int bn, int stages, int splits, int rotate, int iters) {
+    if (compute == NSB_COMPUTE_F32) throw std::runtime_error("bench_gemm: tensor-core modes only");
+    if (rows < 1 || rows > max_streams * T || kind < 0 || kind > 5) throw std::invalid_argument("bench_gemm: bad arguments");
+    NSB_CUDA(cudaSetDevice(device_));
+    auto pick = [&](LayerW& L) -> Weight& { switch (kind) { case 0: return L.ff1a; case 1: return L.ff1b; case 2: return L.qkv; case 3: return L.out; case 4: return L.pw1; default: return L.pw2; } };
+    auto run = [&]() {
+        for (int l = 0; l < n_layers; ++l) {
+            Weight& W = pick(layers_[l]);
+            GemmArgs a; a.A = W.n_in == D_FF ? big_.p : a_.p; a.lda = W.n_in; a.W = W.data.p; a.M = rows; a.N = W.n_out; a.K = W.n_in;
+            a.force_bn = bn; a.force_stages = stages; a.rotate = rotate; a.splits = splits; a.ldc = W.n_out;
+            if (splits > 1) { a.C = part_.p; a.epi = EPI_PARTIAL; a.out_type = OUT_F32; }
+            else if (W.n_out == D_FF) { a.C = big_.p; a.epi = EPI_SILU; a.out_type = act_type(); }
+            else { a.C = qkv_.p; a.epi = EPI_NONE; a.out_type = OUT_F32; }
+            launch_gemm_tc(a, act_type(), st_);
+        }
+    };
+    if (splits > 1 && (size_t)splits * rows * pick(layers_[0]).n_out * 4 > part_.bytes) throw std::invalid_argument("bench_gemm: split workspace too small");
+    run();
+    NSB_CUDA(cudaEventRecord(ev0_, st_));
+    for (int i = 0; i < iters; ++i) run();
+    NSB_CUDA(cudaEventRecord(ev1_, st_));
+    NSB_CUDA(cudaEventSynchronize(ev1_));
+    float ms = 0.f; NSB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    return 1e3f * ms / (float)(iters * n_layers);
+}
+
 cudaEvent_t Engine::prof_event() {
     if (ev_used_ == ev_pool_.size()) { cudaEvent_t e; NSB_CUDA(cudaEventCreate(&e)); ev_pool_.push_back(e); }
     return ev_pool_[ev_used_++];

@@ -73,6 +73,9 @@ public:
     // one bench step with every launch bracketed by CUDA events; per-class device ms and launch counts
     enum { PC_MEL = 0, PC_SUBSAMPLE, PC_LAYERNORM, PC_GEMM, PC_ATTENTION, PC_CONVMOD, PC_DECODE, PC_MISC, PC_COUNT };
     float bench_profile(float* ms_per_class, int* launches_per_class);
+    // tuning: `iters` passes over all layers of one weight kind (0 ff1a,1 ff1b,2 qkv,3 out,4 pw1,5 pw2) with a forced tile config;
+    // returns mean device us per GEMM
+    float bench_gemm(int kind, int rows, int bn, int stages, int splits, int rotate, int iters);
 
     void debug_enable(bool on);
     long long debug_get(const std::string& name, float* out, size_t cap);

@@ -80,6 +80,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+          "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -99,7 +110,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt /*0 f16, 1 bf16*/, int
 
 struct TcParams {
     int M, N, K;
-    const float* bias; void* C; long long ldc; int epi; float alpha; int out_type; int fmt;
+    const float* bias; void* C; long long ldc; int epi; float alpha; int out_type; int fmt; int rot;
 };
 
 template <int BN, int STAGES>
@@ -122,6 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
     const int nk = p.K / BK / (int)gridDim.z;                                   // k-blocks of this split
     const int kb0 = (int)blockIdx.z * nk;
+    const int rot = p.rot ? (int)(blockIdx.x % (unsigned)nk) : 0;       // k-block visited at loop index kb: kb0 + (kb + rot) % nk
     constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
     constexpr uint32_t STAGE_BYTES = (BM + BN) * BK * 2;
 
@@ -149,16 +161,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int pre = nk < STAGES ? nk : STAGES;
             for (int kb = 0; kb < pre; ++kb) {
                 mbar_expect_tx(&s.full[kb], STAGE_BYTES);
-                tma_load_2d(s.b[kb], &tmB, &s.full[kb], (kb0 + kb) * BK, n0);
+                tma_load_2d(s.b[kb], &tmB, &s.full[kb], (kb0 + (kb + rot) % nk) * BK, n0);
             }
             pdl_wait();
-            for (int kb = 0; kb < pre; ++kb) tma_load_2d(s.a[kb], &tmA, &s.full[kb], (kb0 + kb) * BK, m0);
+            for (int kb = 0; kb < pre; ++kb) tma_load_2d(s.a[kb], &tmA, &s.full[kb], (kb0 + (kb + rot) % nk) * BK, m0);
             for (int kb = pre; kb < nk; ++kb) {
                 const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&s.empty[st], ph ^ 1);
                 mbar_expect_tx(&s.full[st], STAGE_BYTES);
-                tma_load_2d(s.a[st], &tmA, &s.full[st], (kb0 + kb) * BK, m0);
-                tma_load_2d(s.b[st], &tmB, &s.full[st], (kb0 + kb) * BK, n0);
+                const int kc = (kb0 + (kb + rot) % nk) * BK;
+                tma_load_2d(s.a[st], &tmA, &s.full[st], kc, m0);
+                tma_load_2d(s.b[st], &tmB, &s.full[st], kc, n0);
             }
         }
     } else if (warp == 1) {
@@ -185,55 +198,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&s.tmem_full, 0);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 16) {
-            uint32_t r[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+        for (int c = 0; c < BN; c += 32) {                      // 32 consecutive columns of this thread's row: full 32-byte sectors per store
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
             if (row < p.M) {
                 const int n = n0 + c;
-                float v[16];
+                float v[32];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
                 if (p.bias) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += p.bias[n + i];
+                    for (int i = 0; i < 32; ++i) v[i] += p.bias[n + i];
                 }
                 const size_t o = (size_t)row * p.ldc + n;
                 if (p.epi == EPI_PARTIAL) {
                     float4* dst = reinterpret_cast<float4*>((float*)p.C + (size_t)blockIdx.z * p.M * p.ldc + o);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 } else if (p.epi == EPI_RESID) {
                     float4* dst = reinterpret_cast<float4*>((float*)p.C + o);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < 8; ++i) {
                         float4 x = dst[i];
                         x.x += p.alpha * v[4 * i]; x.y += p.alpha * v[4 * i + 1]; x.z += p.alpha * v[4 * i + 2]; x.w += p.alpha * v[4 * i + 3];
                         dst[i] = x;
                     }
                 } else {
-                    if (p.epi == EPI_SILU) {
+                    if (p.epi == EPI_SILU) {                     // result is rounded to 16 bits: MUFU-based exp / reciprocal is exact enough
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = silu_exact(v[i]);
+                        for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
                     } else if (p.epi == EPI_RELU) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
                     if (p.out_type == OUT_F32) {
                         float4* dst = reinterpret_cast<float4*>((float*)p.C + o);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     } else if (p.out_type == OUT_F16) {
-                        __half2 h[8];
+                        __half2 h[16];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                        for (int i = 0; i < 16; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
                         uint4* dst = reinterpret_cast<uint4*>((__half*)p.C + o);
-                        dst[0] = *reinterpret_cast<uint4*>(&h[0]); dst[1] = *reinterpret_cast<uint4*>(&h[4]);
-                    } else {
-                        __nv_bfloat162 h[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                        for (int i = 0; i < 4; ++i) dst[i] = *reinterpret_cast<uint4*>(&h[4 * i]);
+                    } else {
+                        __nv_bfloat162 h[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
                         uint4* dst = reinterpret_cast<uint4*>((__nv_bfloat16*)p.C + o);
-                        dst[0] = *reinterpret_cast<uint4*>(&h[0]); dst[1] = *reinterpret_cast<uint4*>(&h[4]);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) dst[i] = *reinterpret_cast<uint4*>(&h[4 * i]);
                     }
                 }
             }
@@ -283,7 +298,7 @@ void launch_cfg(const GemmArgs& a, int fmt, cudaStream_t st) {
     }
     const CUtensorMap tmA = make_map(a.A, a.M, a.K, a.lda, BM, fmt);
     const CUtensorMap tmB = make_map(a.W, a.N, a.K, a.K, BN, fmt);
-    TcParams p{a.M, a.N, a.K, a.bias, a.C, a.ldc, a.epi, a.alpha, a.out_type, fmt};
+    TcParams p{a.M, a.N, a.K, a.bias, a.C, a.ldc, a.epi, a.alpha, a.out_type, fmt, a.rotate};
     dim3 grid(a.N / BN, (a.M + BM - 1) / BM, a.splits);
     launch_k(gemm_tc_kernel<BN, STAGES>, grid, dim3(TC_THREADS), smem, st, tmA, tmB, p);
 }
@@ -297,6 +312,23 @@ void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
         throw CudaError("gemm_tc: unsupported shape (need K % 64 == 0, N % 32 == 0, aligned rows)");
     const int fmt = in_type == OUT_BF16 ? 1 : 0;
     const int tiles_m = (a.M + BM - 1) / BM;
+    if (a.force_bn) {                                             // tuning hook
+        if (a.splits > 1 && (a.epi != EPI_PARTIAL || (a.K / BK) % a.splits != 0)) throw CudaError("gemm_tc: bad split-K request");
+        const int key = a.force_bn * 100 + a.force_stages;
+        switch (key) {
+            case 3204: launch_cfg<32, 4>(a, fmt, st); break;
+            case 3205: launch_cfg<32, 5>(a, fmt, st); break;
+            case 3208: launch_cfg<32, 8>(a, fmt, st); break;
+            case 6404: launch_cfg<64, 4>(a, fmt, st); break;
+            case 6406: launch_cfg<64, 6>(a, fmt, st); break;
+            case 12803: launch_cfg<128, 3>(a, fmt, st); break;
+            case 12804: launch_cfg<128, 4>(a, fmt, st); break;
+            case 25602: launch_cfg<256, 2>(a, fmt, st); break;
+            case 25603: launch_cfg<256, 3>(a, fmt, st); break;
+            default: throw CudaError("gemm_tc: tile config not instantiated");
+        }
+        return;
+    }
     if (a.splits > 1) {
         if (a.epi != EPI_PARTIAL || (a.K / BK) % a.splits != 0) throw CudaError("gemm_tc: bad split-K request");
         if (a.N % 64 == 0 && a.K >= 4096) launch_cfg<64, 4>(a, fmt, st); else launch_cfg<32, 5>(a, fmt, st);

@@ -35,6 +35,8 @@ struct GemmArgs {
     void* C = nullptr; long long ldc = 0;
     int epi = EPI_NONE; float alpha = 1.0f; int out_type = OUT_F32;
     int splits = 1;               // split-K factor (EPI_PARTIAL only): C is a [splits][M][N] f32 workspace
+    int force_bn = 0, force_stages = 0;   // tuning hooks (bench_gemm): pick the tile config explicitly
+    int rotate = 1;               // CTA n starts its k loop at k-block (n mod nk): de-synchronises the A-tile reads of the grid
 };
 void launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
 

@@ -68,11 +68,10 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& epoch, uns
     if (threadIdx.x == 0) {
         epoch += 1;
         const unsigned target = epoch * nblk;
-        __threadfence();
-        atomicAdd(ctr, 1u);
+        // release-arrive (orders every write of this CTA made before the bar.sync above), acquire-spin
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
         unsigned it = 0;
         while (ld_acquire(ctr) < target) { if (++it > (1u << 26)) __trap(); }     // a protocol bug traps instead of hanging the GPU
-        __threadfence();
     }
     __syncthreads();
 }
