@@ -160,7 +160,8 @@ def main():
     if world > 1:
         dist.barrier()
         path = synth.cached_model("f16", N_LAYERS, R=RIGHT_CONTEXT)
-    eng = nsb200.Engine(path, right_context=RIGHT_CONTEXT, max_streams=STREAMS, compute=nsb200.COMPUTE_BF16, kv_dtype=nsb200.KV_BF16, device=local)
+    eng = nsb200.Engine(path, right_context=RIGHT_CONTEXT, max_streams=STREAMS, compute=nsb200.COMPUTE_BF16, kv_dtype=nsb200.KV_BF16, device=local,
+                        cuda_graph=os.environ.get("NSB_BENCH_GRAPH", "1") != "0")
     shift = eng.shift_samples
     need = 160 * (8 * T * (WARM_CHUNKS + 1) - 1) + 256
     base = [synth.synth_pcm(1000 * rank + s, need / 16000.0 + 0.01)[:need] for s in range(8)]

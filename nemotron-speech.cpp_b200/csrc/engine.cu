@@ -444,6 +444,7 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
     const int rows = B * T, at = act_type();
     const int* slot = d_slot_.as<int>();
     float* x = x_.as<float>();
+    pending_ = PartialSum{};
 
     // P: log-mel of the 8T new frames per stream
     { ProfScope ps(this, PC_MEL);
@@ -457,19 +458,32 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
     launch_mel_hist_update(mel_hist_.as<float>(), mel_new_.as<float>(), slot, B, T, st_);
     launch_dwconv_s2(c0_.as<float>(), B, t1, 65, c2_w_.as<float>(), c2_b_.as<float>(), dw_.as<float>(), st_);
     count_launch(3);
+    // 1x1 convs + out projection: fp32 SIMT in strict-f32 mode, tcgen05 kind::tf32 otherwise (these matrices are F32 in every GGUF)
+    const bool tc = compute != NSB_COMPUTE_F32;
+    auto f32_gemm = [&](GemmArgs& g) { if (tc) launch_gemm_tc(g, OUT_F32, st_); else launch_gemm_simt(g, st_); count_launch(); };
     {
         GemmArgs g; g.A = dw_.p; g.lda = SUB_CH; g.W = c3_w_.data.p; g.M = B * t2 * 33; g.N = SUB_CH; g.K = SUB_CH; g.bias = c3_b_.as<float>();
-        g.C = pw_.p; g.ldc = SUB_CH; g.epi = EPI_RELU; launch_gemm_simt(g, st_); count_launch();
+        g.C = pw_.p; g.ldc = SUB_CH; g.epi = EPI_RELU; f32_gemm(g);
     }
     launch_dwconv_s2(pw_.as<float>(), B, t2, 33, c5_w_.as<float>(), c5_b_.as<float>(), dw_.as<float>(), st_); count_launch();
     {
         GemmArgs g; g.A = dw_.p; g.lda = SUB_CH; g.W = c6_w_.data.p; g.M = B * t3 * SUB_W; g.N = SUB_CH; g.K = SUB_CH; g.bias = c6_b_.as<float>();
-        g.C = pw_.p; g.ldc = SUB_CH; g.epi = EPI_RELU; launch_gemm_simt(g, st_); count_launch();
+        g.C = pw_.p; g.ldc = SUB_CH; g.epi = EPI_RELU; f32_gemm(g);
     }
     {   // flatten + out linear on the T kept frames (frames 0,1 of every stream are dropped: nemo-stream.cpp:136-144)
-        GemmArgs g; g.A = pw_.p; g.lda = SUB_W * SUB_CH; g.group = T; g.group_stride = (long long)t3 * SUB_W * SUB_CH; g.row_off = DROP_PRE;
-        g.W = sub_out_w_.data.p; g.M = rows; g.N = D_MODEL; g.K = SUB_W * SUB_CH; g.bias = out_b_.as<float>();
-        g.C = x; g.ldc = D_MODEL; g.epi = EPI_NONE; launch_gemm_simt(g, st_); count_launch();
+        GemmArgs g; g.W = sub_out_w_.data.p; g.N = D_MODEL; g.K = SUB_W * SUB_CH; g.bias = out_b_.as<float>(); g.ldc = D_MODEL; g.lda = SUB_W * SUB_CH;
+        g.A = pw_.p;
+        if (!tc) {                                                     // SIMT: gather only the kept rows
+            g.group = T; g.group_stride = (long long)t3 * SUB_W * SUB_CH; g.row_off = DROP_PRE; g.M = rows; g.C = x; g.epi = EPI_NONE;
+        } else {                                                       // tensor cores: all T+2 frames, dropped rows skipped by the epilogue row map
+            g.M = B * t3; g.c_group = t3; g.c_drop = DROP_PRE;
+            constexpr int SUB_SPLITS = 8;                              // K = 4352 = 136 k-blocks of 32; small batches need split-K to fill the SMs
+            if (!debug_ && rows <= 1024 && (size_t)(SUB_SPLITS - 1) * rows * D_MODEL * 4 <= part_.bytes) {
+                g.splits = SUB_SPLITS; g.epi = EPI_PARTIAL; g.C0 = x; g.C = part_.p;
+                pending_.part = part_.as<float>(); pending_.n = SUB_SPLITS - 1; pending_.alpha = 1.f;   // summed by the first LayerNorm
+            } else { g.C = x; g.epi = EPI_NONE; }
+        }
+        f32_gemm(g);
     }
     }   // PC_SUBSAMPLE
     if (debug_) NSB_CUDA(cudaMemcpyAsync(dbg_sub_.p, x, (size_t)rows * D_MODEL * 4, cudaMemcpyDeviceToDevice, st_));
@@ -477,7 +491,6 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
     // L: cache-aware conformer layers
     const long long kv_slot_stride = (long long)n_layers * 2 * (ATT_L + T) * D_MODEL;
     const long long cc_slot_stride = (long long)n_layers * (CONV_K - 1) * D_MODEL;
-    pending_ = PartialSum{};
     auto ln = [&](const float* g_, const float* b_) {
         ProfScope ps(this, PC_LAYERNORM); launch_layernorm(x, rows, g_, b_, a_.p, at, pending_, st_); count_launch(); pending_ = PartialSum{};
     };
@@ -530,7 +543,9 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
     ProfScope ps_dec(this, PC_DECODE);
     {
         GemmArgs g; g.A = x; g.lda = D_MODEL; g.W = joint_enc_w_.data.p; g.M = rows; g.N = JOINT; g.K = D_MODEL; g.bias = joint_enc_b_.as<float>();
-        g.C = encp_.p; g.ldc = JOINT; g.epi = EPI_NONE; launch_gemm_simt(g, st_); count_launch();
+        g.C = encp_.p; g.ldc = JOINT; g.epi = EPI_NONE;
+        if (compute != NSB_COMPUTE_F32) launch_gemm_tc(g, OUT_F32, st_); else launch_gemm_simt(g, st_);
+        count_launch();
     }
     DecodeArgs d{};
     d.w.embed = embed_.as<float>();

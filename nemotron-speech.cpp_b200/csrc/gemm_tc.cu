@@ -1,4 +1,4 @@
-// gemm_tc.cu -- tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T  (fp16 or bf16 operands, fp32 accumulate)
+// gemm_tc.cu -- tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T  (fp16 / bf16 / tf32 operands, fp32 accumulate)
 //
 // This is the kernel behind every per-layer weight matrix of the FastConformer block (FFN linear1/2, fused QKV,
 // attention out, conv pointwise 1/2) when the engine computes in F16 / BF16 / Q8_0 mode, i.e. what the reference
@@ -12,6 +12,9 @@
 //   warps 2-5: epilogue       -- tcgen05.ld the fp32 accumulator (each warp owns the TMEM lane quarter warp_id % 4),
 //                                apply bias / SiLU / residual and store (f32 or 16-bit)
 // Both operands are K-major, so the same shared-memory descriptor recipe serves A and W.
+// EB = 4 instantiates the same pipeline for fp32 operands as kind::tf32 (32 elements per 128-byte swizzle row, K = 8 per
+// MMA; TMA rounds fp32 -> tf32 on load): used by the 16-bit / Q8_0 engine modes for the matrices every GGUF keeps in F32
+// (subsampling 1x1 convs and out-projection = the implicit-GEMM half of the dw-striding stem, joint.enc).
 // Rows of A beyond M are zero-filled by TMA (tensor map extent = M), so small batches need no padding.
 #include <cuda.h>
 
@@ -23,7 +26,7 @@ namespace nsb {
 
 namespace {
 
-constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int BM = 128, ROW_BYTES = 128, UMMA_K_BYTES = 32;      // one k-block = one 128-byte swizzle row per tile row; 4 MMAs per k-block
 constexpr int TC_THREADS = 192;
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -69,6 +72,12 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t da, uint64_t 
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -103,27 +112,29 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
 }
-// cute::UMMA::InstrDescriptor for kind::f16: c=F32, a/b = F16 (0) or BF16 (1), K-major both, N>>3 @17, M>>4 @24
-__host__ __device__ constexpr uint32_t make_idesc(int fmt /*0 f16, 1 bf16*/, int n) {
+// cute::UMMA::InstrDescriptor: c=F32, a/b = F16 (0) / BF16 (1) for kind::f16, TF32 (2) for kind::tf32; K-major both, N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t make_idesc(int fmt /*0 f16, 1 bf16, 2 tf32*/, int n) {
     return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 struct TcParams {
     int M, N, K;
     const float* bias; void* C; long long ldc; int epi; float alpha; int out_type; int fmt; int rot;
+    int c_group, c_drop;       // output row map: row r -> (r / c_group) * (c_group - c_drop) + r % c_group - c_drop, rows with r % c_group < c_drop are dropped
+    void* C0; int m_out;       // EPI_PARTIAL: slice 0 (+bias) goes to C0 when set, slices z >= 1 to C + (z-1) * m_out * ldc
 };
 
 template <int BN, int STAGES>
 struct Smem {
-    alignas(1024) uint8_t a[STAGES][BM * BK * 2];
-    alignas(1024) uint8_t b[STAGES][BN * BK * 2];
+    alignas(1024) uint8_t a[STAGES][BM * ROW_BYTES];
+    alignas(1024) uint8_t b[STAGES][BN * ROW_BYTES];
     alignas(8) uint64_t full[STAGES];
     uint64_t empty[STAGES];
     uint64_t tmem_full;
     uint32_t tmem_slot;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -131,11 +142,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     S& s = *reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+    constexpr int BK = ROW_BYTES / EB;                                          // elements per k-block (64 for 16-bit, 32 for tf32)
     const int nk = p.K / BK / (int)gridDim.z;                                   // k-blocks of this split
     const int kb0 = (int)blockIdx.z * nk;
     const int rot = p.rot ? (int)(blockIdx.x % (unsigned)nk) : 0;       // k-block visited at loop index kb: kb0 + (kb + rot) % nk
     constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-    constexpr uint32_t STAGE_BYTES = (BM + BN) * BK * 2;
+    constexpr uint32_t STAGE_BYTES = (BM + BN) * ROW_BYTES;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
@@ -184,8 +196,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(s.a[st]), b_addr = smem_u32(s.b[st]);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k)
-                    umma_f16(tmem_base, make_desc(a_addr + k * UMMA_K * 2), make_desc(b_addr + k * UMMA_K * 2), idesc, (kb | k) ? 1u : 0u);
+                for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k) {
+                    if (EB == 4) umma_tf32(tmem_base, make_desc(a_addr + k * UMMA_K_BYTES), make_desc(b_addr + k * UMMA_K_BYTES), idesc, (kb | k) ? 1u : 0u);
+                    else umma_f16(tmem_base, make_desc(a_addr + k * UMMA_K_BYTES), make_desc(b_addr + k * UMMA_K_BYTES), idesc, (kb | k) ? 1u : 0u);
+                }
                 umma_commit(&s.empty[st]);                      // smem stage reusable once these MMAs retire
             }
             umma_commit(&s.tmem_full);                          // accumulator complete
@@ -201,18 +215,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int c = 0; c < BN; c += 32) {                      // 32 consecutive columns of this thread's row: full 32-byte sectors per store
             uint32_t r[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-            if (row < p.M) {
+            int orow = row;
+            bool live = row < p.M;
+            if (p.c_group > 0) { const int rr = row % p.c_group; orow = (row / p.c_group) * (p.c_group - p.c_drop) + rr - p.c_drop; live = live && rr >= p.c_drop; }
+            if (live) {
                 const int n = n0 + c;
                 float v[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                if (p.bias) {
+                if (p.bias && (p.epi != EPI_PARTIAL || blockIdx.z == 0)) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] += p.bias[n + i];
                 }
-                const size_t o = (size_t)row * p.ldc + n;
+                const size_t o = (size_t)orow * p.ldc + n;
                 if (p.epi == EPI_PARTIAL) {
-                    float4* dst = reinterpret_cast<float4*>((float*)p.C + (size_t)blockIdx.z * p.M * p.ldc + o);
+                    float* base = p.C0 ? (blockIdx.z == 0 ? (float*)p.C0 : (float*)p.C + (size_t)(blockIdx.z - 1) * p.m_out * p.ldc)
+                                       : (float*)p.C + (size_t)blockIdx.z * p.m_out * p.ldc;
+                    float4* dst = reinterpret_cast<float4*>(base + o);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 } else if (p.epi == EPI_RESID) {
@@ -277,40 +296,52 @@ EncodeTiledFn get_encode_fn() {
 // 2-D K-major tensor map: dims {K, rows}, row stride ld elements, box {64, box_rows}, 128-byte swizzle
 CUtensorMap make_map(const void* ptr, int rows, int K, long long ld, int box_rows, int fmt) {
     CUtensorMap m;
+    const int eb = fmt == 2 ? 4 : 2;
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * eb};
+    const cuuint32_t box[2] = {(cuuint32_t)(ROW_BYTES / eb), (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = get_encode_fn()(&m, fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr),
+    const CUtensorMapDataType dt = fmt == 2 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const CUresult r = get_encode_fn()(&m, dt, 2, const_cast<void*>(ptr),
                                        dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     return m;
 }
 
-template <int BN, int STAGES>
-void launch_cfg(const GemmArgs& a, int fmt, cudaStream_t st) {
+template <int BN, int STAGES, int EB>
+void launch_cfg_e(const GemmArgs& a, int fmt, cudaStream_t st) {
     static bool attr_set = false;
     const size_t smem = sizeof(Smem<BN, STAGES>) + 1024;
     if (!attr_set) {
-        NSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const CUtensorMap tmA = make_map(a.A, a.M, a.K, a.lda, BM, fmt);
     const CUtensorMap tmB = make_map(a.W, a.N, a.K, a.K, BN, fmt);
-    TcParams p{a.M, a.N, a.K, a.bias, a.C, a.ldc, a.epi, a.alpha, a.out_type, fmt, a.rotate};
+    const int m_out = a.c_group > 0 ? (a.M / a.c_group) * (a.c_group - a.c_drop) : a.M;
+    TcParams p{a.M, a.N, a.K, a.bias, a.C, a.ldc, a.epi, a.alpha, a.out_type, fmt, a.rotate, a.c_group, a.c_drop, a.C0, m_out};
     dim3 grid(a.N / BN, (a.M + BM - 1) / BM, a.splits);
-    launch_k(gemm_tc_kernel<BN, STAGES>, grid, dim3(TC_THREADS), smem, st, tmA, tmB, p);
+    launch_k(gemm_tc_kernel<BN, STAGES, EB>, grid, dim3(TC_THREADS), smem, st, tmA, tmB, p);
+}
+template <int BN, int STAGES>
+void launch_cfg(const GemmArgs& a, int fmt, cudaStream_t st) {
+    if (fmt == 2) {
+        if constexpr ((BN == 32 && STAGES == 5) || (BN == 64 && STAGES == 4) || (BN == 128 && STAGES == 4)) launch_cfg_e<BN, STAGES, 4>(a, fmt, st);
+        else throw CudaError("gemm_tc: tile config not instantiated for tf32");
+    } else launch_cfg_e<BN, STAGES, 2>(a, fmt, st);
 }
 }  // namespace
 
-// in_type: OUT_F16 or OUT_BF16 (type of A and W). Requires K % 64 == 0, N % 32 == 0, 16-byte aligned rows.
+// in_type: OUT_F16 / OUT_BF16 / OUT_F32 (= tf32) -- type of A and W. Requires K % 64 == 0 (tf32: 32), N % 32 == 0, 16-byte aligned rows.
 void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
     if (a.M <= 0) return;
     if (a.group != 0) throw CudaError("gemm_tc: row maps are not supported");
-    if (a.K % BK != 0 || a.N % 32 != 0 || (a.lda % 8) != 0 || (a.ldc % 4) != 0)
-        throw CudaError("gemm_tc: unsupported shape (need K % 64 == 0, N % 32 == 0, aligned rows)");
-    const int fmt = in_type == OUT_BF16 ? 1 : 0;
+    const int fmt = in_type == OUT_F32 ? 2 : in_type == OUT_BF16 ? 1 : 0;
+    const int BK = fmt == 2 ? 32 : 64;
+    if (a.K % BK != 0 || a.N % 32 != 0 || (a.lda % (fmt == 2 ? 4 : 8)) != 0 || (a.ldc % 4) != 0)
+        throw CudaError("gemm_tc: unsupported shape (need K % 64 == 0 (tf32: 32), N % 32 == 0, 16-byte aligned rows)");
+    if (a.c_group > 0 && a.M % a.c_group != 0) throw CudaError("gemm_tc: M must be a multiple of the output row group");
     const int tiles_m = (a.M + BM - 1) / BM;
     if (a.force_bn) {                                             // tuning hook
         if (a.splits > 1 && (a.epi != EPI_PARTIAL || (a.K / BK) % a.splits != 0)) throw CudaError("gemm_tc: bad split-K request");
@@ -331,6 +362,7 @@ void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
     }
     if (a.splits > 1) {
         if (a.epi != EPI_PARTIAL || (a.K / BK) % a.splits != 0) throw CudaError("gemm_tc: bad split-K request");
+        if (a.N % 128 == 0 && a.M > 128 && fmt == 2) { launch_cfg<128, 4>(a, fmt, st); return; }
         if (a.N % 64 == 0 && a.K >= 4096) launch_cfg<64, 4>(a, fmt, st); else launch_cfg<32, 5>(a, fmt, st);
         return;
     }

@@ -35,6 +35,9 @@ struct GemmArgs {
     void* C = nullptr; long long ldc = 0;
     int epi = EPI_NONE; float alpha = 1.0f; int out_type = OUT_F32;
     int splits = 1;               // split-K factor (EPI_PARTIAL only): C is a [splits][M][N] f32 workspace
+    // tensor-core kernel only: output row map (rows r with r % c_group < c_drop are not stored, the rest are compacted) and, for
+    // EPI_PARTIAL, an optional destination C0 for k-slice 0 (+bias); slices z >= 1 then go to C[z-1]
+    int c_group = 0, c_drop = 0; void* C0 = nullptr;
     int force_bn = 0, force_stages = 0;   // tuning hooks (bench_gemm): pick the tile config explicitly
     int rotate = 1;               // CTA n starts its k loop at k-block (n mod nk): de-synchronises the A-tile reads of the grid
 };
