@@ -58,6 +58,18 @@ inline void launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cud
     NSB_CUDA(cudaLaunchKernelEx(&cfg, kern, P(std::forward<A>(args))...));
 }
 
+// same, with a thread-block cluster of `cluster_x` CTAs along x
+template <typename... P, typename... A>
+inline void launch_k_cluster(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, A&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[2]; int n = 0;
+    if (cluster_x > 1) { at[n].id = cudaLaunchAttributeClusterDimension; at[n].val.clusterDim.x = cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1; ++n; }
+    if (pdl_enabled()) { at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
+    cfg.attrs = at; cfg.numAttrs = n;
+    NSB_CUDA(cudaLaunchKernelEx(&cfg, kern, P(std::forward<A>(args))...));
+}
+
 // Epilogues shared by the SIMT and the tcgen05 GEMM
 enum Epi : int {
     EPI_NONE = 0,      // C = acc (+bias)

@@ -140,6 +140,42 @@ void Engine::upload_weight(Weight& w, const std::string& name, const std::vector
     NSB_CUDA(cudaStreamSynchronize(st_));
 }
 
+// Q8_0 block = fp16 d + 32 x int8 along ne0 (scripts/convert_to_gguf.py:93-129). Split into planes; tensors of another type are
+// quantised here with the converter's rule (d = amax / 127 stored as fp16, q = round(x / fp16(d))).
+static void q8_planes(const GgufFile& g, const std::string& name, std::vector<int8_t>& q, std::vector<uint16_t>& d) {
+    const GgufTensor& t = g.require(name);
+    const size_t n = (size_t)t.n_elements(), nb = n / 32;
+    const size_t q0 = q.size(), d0 = d.size();
+    q.resize(q0 + n); d.resize(d0 + nb);
+    if (t.type == GGML_Q8_0) {
+        const std::vector<uint8_t> raw = g.read(t);
+        for (size_t b = 0; b < nb; ++b) { memcpy(&d[d0 + b], &raw[b * 34], 2); memcpy(&q[q0 + b * 32], &raw[b * 34 + 2], 32); }
+        return;
+    }
+    const std::vector<float> x = read_matrix_f32(g, name);
+    for (size_t b = 0; b < nb; ++b) {
+        float amax = 0.f; for (int i = 0; i < 32; ++i) amax = std::max(amax, std::fabs(x[b * 32 + i]));
+        const __half dh = __float2half_rn(amax / 127.0f); uint16_t bits; memcpy(&bits, &dh, 2); d[d0 + b] = bits;
+        const float df = __half2float(dh);
+        for (int i = 0; i < 32; ++i) q[q0 + b * 32 + i] = (int8_t)(df > 0.f ? std::nearbyint(x[b * 32 + i] / df) : 0.f);
+    }
+}
+
+void Engine::load_layer_matrix(Weight& w, const GgufFile& g, const std::string& out_name, const std::vector<std::string>& parts, int n_out, int n_in) {
+    if (compute != NSB_COMPUTE_Q8_0) {
+        std::vector<float> all;
+        for (const std::string& pn : parts) { std::vector<float> h = read_matrix_f32(g, pn); all.insert(all.end(), h.begin(), h.end()); }
+        upload_weight(w, out_name, all, n_out, n_in);
+        return;
+    }
+    std::vector<int8_t> q; std::vector<uint16_t> d;
+    for (const std::string& pn : parts) q8_planes(g, pn, q, d);
+    if (q.size() != (size_t)n_out * n_in || n_in % 64 != 0) throw std::runtime_error("shape mismatch for " + out_name);
+    w.name = out_name; w.n_out = n_out; w.n_in = n_in;
+    w.data.alloc(q.size(), false); h2d_sync(w.data.p, q.data(), q.size());
+    w.scales.alloc(d.size() * 2, false); h2d_sync(w.scales.p, d.data(), d.size() * 2);
+}
+
 void Engine::load_weights(const GgufFile& g) {
     auto vec = [&](DevBuf& d, const std::string& n, size_t expect) {
         std::vector<float> h = g.read_f32(n);
@@ -188,19 +224,17 @@ void Engine::load_weights(const GgufFile& g) {
         const std::string p = "encoder.layers." + std::to_string(l) + ".";
         const char* norms[5] = {"norm_feed_forward1", "norm_self_att", "norm_conv", "norm_feed_forward2", "norm_out"};
         for (int i = 0; i < 5; ++i) { vec(L.ln[2 * i], p + norms[i] + ".weight", D_MODEL); vec(L.ln[2 * i + 1], p + norms[i] + ".bias", D_MODEL); }
-        upload_weight(L.ff1a, p + "feed_forward1.linear1.weight", read_matrix_f32(g, p + "feed_forward1.linear1.weight"), D_FF, D_MODEL);
-        upload_weight(L.ff1b, p + "feed_forward1.linear2.weight", read_matrix_f32(g, p + "feed_forward1.linear2.weight"), D_MODEL, D_FF);
-        upload_weight(L.ff2a, p + "feed_forward2.linear1.weight", read_matrix_f32(g, p + "feed_forward2.linear1.weight"), D_FF, D_MODEL);
-        upload_weight(L.ff2b, p + "feed_forward2.linear2.weight", read_matrix_f32(g, p + "feed_forward2.linear2.weight"), D_MODEL, D_FF);
-        {   // q | k | v stacked along the output dim -> one GEMM with N = 3072
-            std::vector<float> q = read_matrix_f32(g, p + "self_attn.linear_q.weight"), k = read_matrix_f32(g, p + "self_attn.linear_k.weight"),
-                               v = read_matrix_f32(g, p + "self_attn.linear_v.weight");
-            q.insert(q.end(), k.begin(), k.end()); q.insert(q.end(), v.begin(), v.end());
-            upload_weight(L.qkv, p + "self_attn.linear_qkv.weight", q, 3 * D_MODEL, D_MODEL);
-        }
-        upload_weight(L.out, p + "self_attn.linear_out.weight", read_matrix_f32(g, p + "self_attn.linear_out.weight"), D_MODEL, D_MODEL);
-        upload_weight(L.pw1, p + "conv.pointwise_conv1.weight", read_matrix_f32(g, p + "conv.pointwise_conv1.weight"), 2 * D_MODEL, D_MODEL);
-        upload_weight(L.pw2, p + "conv.pointwise_conv2.weight", read_matrix_f32(g, p + "conv.pointwise_conv2.weight"), D_MODEL, D_MODEL);
+        auto mat = [&](Weight& w, const std::string& n, int n_out, int n_in) { load_layer_matrix(w, g, p + n, {p + n}, n_out, n_in); };
+        mat(L.ff1a, "feed_forward1.linear1.weight", D_FF, D_MODEL);
+        mat(L.ff1b, "feed_forward1.linear2.weight", D_MODEL, D_FF);
+        mat(L.ff2a, "feed_forward2.linear1.weight", D_FF, D_MODEL);
+        mat(L.ff2b, "feed_forward2.linear2.weight", D_MODEL, D_FF);
+        // q | k | v stacked along the output dim -> one GEMM with N = 3072
+        load_layer_matrix(L.qkv, g, p + "self_attn.linear_qkv.weight",
+                          {p + "self_attn.linear_q.weight", p + "self_attn.linear_k.weight", p + "self_attn.linear_v.weight"}, 3 * D_MODEL, D_MODEL);
+        mat(L.out, "self_attn.linear_out.weight", D_MODEL, D_MODEL);
+        mat(L.pw1, "conv.pointwise_conv1.weight", 2 * D_MODEL, D_MODEL);
+        mat(L.pw2, "conv.pointwise_conv2.weight", D_MODEL, D_MODEL);
         vec(L.bias_u, p + "self_attn.pos_bias_u", D_MODEL); vec(L.bias_v, p + "self_attn.pos_bias_v", D_MODEL);
         {
             const GgufTensor& dw = g.require(p + "conv.depthwise_conv.weight");       // ggml [1024, k]: tap-major
@@ -246,7 +280,6 @@ void Engine::alloc_state() {
     const size_t Mrows = (size_t)S * T;
     d_pcm_.alloc((size_t)S * rl_ * 2); d_slot_.alloc((size_t)S * 4);
     mel_new_.alloc((size_t)S * 8 * T * N_MELS * 4);
-    c0_.alloc((size_t)S * t1 * 65 * SUB_CH * 4);
     dw_.alloc((size_t)S * t2 * 33 * SUB_CH * 4);
     pw_.alloc((size_t)S * t2 * 33 * SUB_CH * 4);
     x_.alloc(Mrows * D_MODEL * 4);
@@ -292,7 +325,7 @@ void Engine::build_pos_tables(const GgufFile& g) {
     if (act_type() != OUT_F32) { d_a.alloc(tab.size() * 2, false); convert_to(d_tab.as<float>(), d_a.p, tab.size(), act_type(), st_); A = d_a.p; }
     for (int l = 0; l < n_layers; ++l) {
         const std::string n = "encoder.layers." + std::to_string(l) + ".self_attn.linear_pos.weight";
-        Weight wpos; upload_weight(wpos, n, read_matrix_f32(g, n), D_MODEL, D_MODEL);
+        Weight wpos; load_layer_matrix(wpos, g, n, {n}, D_MODEL, D_MODEL);
         layers_[l].pos_proj.alloc((size_t)n_rel * D_MODEL * 4, false);
         gemm(A, D_MODEL, wpos, n_rel, nullptr, layers_[l].pos_proj.p, D_MODEL, EPI_NONE, 1.f, OUT_F32);
         NSB_CUDA(cudaStreamSynchronize(st_));
@@ -301,7 +334,7 @@ void Engine::build_pos_tables(const GgufFile& g) {
 
 void Engine::gemm(const void* A, long long lda, const Weight& W, int M, const float* bias, void* C, long long ldc, int epi, float alpha,
                   int out_type) {
-    GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.M = M; a.N = W.n_out; a.K = W.n_in; a.bias = bias; a.C = C; a.ldc = ldc;
+    GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.w_scales = W.scales.p; a.M = M; a.N = W.n_out; a.K = W.n_in; a.bias = bias; a.C = C; a.ldc = ldc;
     a.epi = epi; a.alpha = alpha; a.out_type = out_type;
     ProfScope ps(this, PC_GEMM);
     if (compute == NSB_COMPUTE_F32) launch_gemm_simt(a, st_);
@@ -319,7 +352,7 @@ void Engine::gemm_residual(const void* A, long long lda, const Weight& W, int M,
         while (splits < MAX_SPLITS && tiles * splits < 120 && nk % (splits * 2) == 0 && nk / (splits * 2) >= 2) splits *= 2;
     }
     if (splits == 1) { gemm(A, lda, W, M, nullptr, x, D_MODEL, EPI_RESID, alpha, OUT_F32); return; }
-    GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.M = M; a.N = W.n_out; a.K = W.n_in; a.C = part_.p; a.ldc = D_MODEL;
+    GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.w_scales = W.scales.p; a.M = M; a.N = W.n_out; a.K = W.n_in; a.C = part_.p; a.ldc = D_MODEL;
     a.epi = EPI_PARTIAL; a.out_type = OUT_F32; a.splits = splits;
     { ProfScope ps(this, PC_GEMM); launch_gemm_tc(a, act_type(), st_); }
     count_launch();
@@ -439,7 +472,21 @@ void Engine::run_step(int B, const int16_t* d_pcm) {
 // ------------------------------------------------------------------------------------------
 // THE HOT PATH: one batched chunk for B streams, PCM already in HBM, tokens left in HBM.
 // ------------------------------------------------------------------------------------------
+// Diagnostic only (NSB_SKIP=ln,attn,conv,decode,ff,qkv,out,pw,sub,mel): leave kernel classes out of the step to read their
+// in-graph marginal cost off the step time. Results are meaningless with anything skipped.
+static unsigned skip_mask() {
+    static const unsigned m = [] {
+        unsigned v = 0; const char* e = getenv("NSB_SKIP"); if (!e) return v;
+        const char* names[] = {"ln", "attn", "conv", "decode", "ff", "qkv", "out", "pw", "sub", "mel"};
+        for (int i = 0; i < 10; ++i) if (strstr(e, names[i])) v |= 1u << i;
+        return v;
+    }();
+    return m;
+}
+enum { SK_LN = 1, SK_ATTN = 2, SK_CONV = 4, SK_DECODE = 8, SK_FF = 16, SK_QKV = 32, SK_OUT = 64, SK_PW = 128, SK_SUB = 256, SK_MEL = 512 };
+
 void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
+    const unsigned skip = skip_mask();
     const int M = PRE_CACHE + 8 * T, t1 = M / 2 + 1, t2 = t1 / 2 + 1, t3 = t2 / 2 + 1;
     const int rows = B * T, at = act_type();
     const int* slot = d_slot_.as<int>();
@@ -447,17 +494,17 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
     pending_ = PartialSum{};
 
     // P: log-mel of the 8T new frames per stream
-    { ProfScope ps(this, PC_MEL);
+    if (!(skip & SK_MEL)) { ProfScope ps(this, PC_MEL);
     launch_logmel(d_pcm, rl_, B, 8 * T, window_.as<float>(), cos_t_.as<float>(), sin_t_.as<float>(), fb_t_.as<float>(),
                   mel_new_.as<float>(), (size_t)8 * T * N_MELS, st_); }
     count_launch();
     if (debug_) { launch_mel_gather(mel_hist_.as<float>(), mel_new_.as<float>(), slot, B, T, dbg_mel_.as<float>(), st_); count_launch(); }
     // S: subsampling stem (NHWC)
-    { ProfScope ps(this, PC_SUBSAMPLE);
-    launch_conv0(mel_hist_.as<float>(), mel_new_.as<float>(), slot, B, T, c0_w_.as<float>(), c0_b_.as<float>(), c0_.as<float>(), st_);
+    if (!(skip & SK_SUB)) { ProfScope ps(this, PC_SUBSAMPLE);
+    launch_stem_conv0_dw(mel_hist_.as<float>(), mel_new_.as<float>(), slot, B, T, c0_w_.as<float>(), c0_b_.as<float>(), c2_w_.as<float>(),
+                         c2_b_.as<float>(), dw_.as<float>(), st_);
     launch_mel_hist_update(mel_hist_.as<float>(), mel_new_.as<float>(), slot, B, T, st_);
-    launch_dwconv_s2(c0_.as<float>(), B, t1, 65, c2_w_.as<float>(), c2_b_.as<float>(), dw_.as<float>(), st_);
-    count_launch(3);
+    count_launch(2);
     // 1x1 convs + out projection: fp32 SIMT in strict-f32 mode, tcgen05 kind::tf32 otherwise (these matrices are F32 in every GGUF)
     const bool tc = compute != NSB_COMPUTE_F32;
     auto f32_gemm = [&](GemmArgs& g) { if (tc) launch_gemm_tc(g, OUT_F32, st_); else launch_gemm_simt(g, st_); count_launch(); };
@@ -492,18 +539,20 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
     const long long kv_slot_stride = (long long)n_layers * 2 * (ATT_L + T) * D_MODEL;
     const long long cc_slot_stride = (long long)n_layers * (CONV_K - 1) * D_MODEL;
     auto ln = [&](const float* g_, const float* b_) {
+        if (skip & SK_LN) { pending_ = PartialSum{}; return; }
         ProfScope ps(this, PC_LAYERNORM); launch_layernorm(x, rows, g_, b_, a_.p, at, pending_, st_); count_launch(); pending_ = PartialSum{};
     };
     ln(layers_[0].ln[0].as<float>(), layers_[0].ln[1].as<float>());
     for (int l = 0; l < n_layers; ++l) {
         LayerW& L = layers_[l];
         // FFN1: x += 0.5 * W2 silu(W1 LN(x))                                        (nemo-stream.cpp:603-606)
+        if (!(skip & SK_FF)) {
         gemm(a_.p, D_MODEL, L.ff1a, rows, nullptr, big_.p, D_FF, EPI_SILU, 1.f, at);
-        gemm_residual(big_.p, D_FF, L.ff1b, rows, x, 0.5f);
+        gemm_residual(big_.p, D_FF, L.ff1b, rows, x, 0.5f); }
         // MHSA over the ring cache                                                  (:609-615)
         ln(L.ln[2].as<float>(), L.ln[3].as<float>());
-        gemm(a_.p, D_MODEL, L.qkv, rows, nullptr, qkv_.p, 3 * D_MODEL, EPI_NONE, 1.f, OUT_F32);
-        {
+        if (!(skip & SK_QKV)) gemm(a_.p, D_MODEL, L.qkv, rows, nullptr, qkv_.p, 3 * D_MODEL, EPI_NONE, 1.f, OUT_F32);
+        if (!(skip & SK_ATTN)) {
             AttnArgs aa; aa.qkv = qkv_.as<float>();
             const size_t es = kv_elem_size(kv_dtype);
             aa.k_ring = (char*)kv_.p + (size_t)l * 2 * (ATT_L + T) * D_MODEL * es;
@@ -513,24 +562,26 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
             aa.slot_of_b = slot; aa.ring_pos = ring_pos_.as<int>(); aa.valid_len = valid_len_.as<int>(); aa.B = B; aa.T = T;
             ProfScope ps(this, PC_ATTENTION); launch_attention(aa, st_); count_launch();
         }
-        gemm_residual(a_.p, D_MODEL, L.out, rows, x, 1.f);
+        if (!(skip & SK_OUT)) gemm_residual(a_.p, D_MODEL, L.out, rows, x, 1.f);
         // conv module                                                               (:618-651)
         ln(L.ln[4].as<float>(), L.ln[5].as<float>());
-        gemm(a_.p, D_MODEL, L.pw1, rows, nullptr, pw1_.p, 2 * D_MODEL, EPI_NONE, 1.f, OUT_F32);
-        {
+        if (!(skip & SK_PW)) gemm(a_.p, D_MODEL, L.pw1, rows, nullptr, pw1_.p, 2 * D_MODEL, EPI_NONE, 1.f, OUT_F32);
+        if (!(skip & SK_CONV)) {
             ConvModArgs ca; ca.pw1 = pw1_.as<float>(); ca.conv_cache = conv_cache_.as<float>() + (size_t)l * (CONV_K - 1) * D_MODEL;
             ca.slot_stride = cc_slot_stride; ca.dw_w = L.dw_w.as<float>(); ca.ln_g = L.cln_g.as<float>(); ca.ln_b = L.cln_b.as<float>();
             ca.out = a_.p; ca.out_type = at; ca.slot_of_b = slot; ca.B = B; ca.T = T;
             ProfScope ps(this, PC_CONVMOD); launch_conv_module(ca, st_); count_launch();
         }
-        gemm_residual(a_.p, D_MODEL, L.pw2, rows, x, 1.f);
+        if (!(skip & SK_PW)) gemm_residual(a_.p, D_MODEL, L.pw2, rows, x, 1.f);
         // FFN2                                                                      (:654-657)
         ln(L.ln[6].as<float>(), L.ln[7].as<float>());
+        if (!(skip & SK_FF)) {
         gemm(a_.p, D_MODEL, L.ff2a, rows, nullptr, big_.p, D_FF, EPI_SILU, 1.f, at);
-        gemm_residual(big_.p, D_FF, L.ff2b, rows, x, 0.5f);
+        gemm_residual(big_.p, D_FF, L.ff2b, rows, x, 0.5f); }
         // norm_out (:659) fused with the next layer's norm_feed_forward1
         const bool last = l + 1 == n_layers;
-        { ProfScope ps(this, PC_LAYERNORM);
+        if (skip & SK_LN) pending_ = PartialSum{};
+        else { ProfScope ps(this, PC_LAYERNORM);
           launch_layernorm2(x, rows, L.ln[8].as<float>(), L.ln[9].as<float>(), last ? nullptr : layers_[l + 1].ln[0].as<float>(),
                             last ? nullptr : layers_[l + 1].ln[1].as<float>(), last ? nullptr : a_.p, at, pending_, st_);
           count_launch(); pending_ = PartialSum{}; }
@@ -540,6 +591,7 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
     { ProfScope ps(this, PC_MISC); launch_advance_streams(slot, B, T, ring_pos_.as<int>(), valid_len_.as<int>(), st_); count_launch(); }
 
     // G/Y: joint.enc for all frames, then the persistent greedy-decode kernel
+    if (skip & SK_DECODE) return;
     ProfScope ps_dec(this, PC_DECODE);
     {
         GemmArgs g; g.A = x; g.lda = D_MODEL; g.W = joint_enc_w_.data.p; g.M = rows; g.N = JOINT; g.K = D_MODEL; g.bias = joint_enc_b_.as<float>();
@@ -606,7 +658,7 @@ float Engine::bench_gemm(int kind, int rows, int bn, int stages, int splits, int
     auto run = [&]() {
         for (int l = 0; l < n_layers; ++l) {
             Weight& W = pick(layers_[l]);
-            GemmArgs a; a.A = W.n_in == D_FF ? big_.p : a_.p; a.lda = W.n_in; a.W = W.data.p; a.M = rows; a.N = W.n_out; a.K = W.n_in;
+            GemmArgs a; a.A = W.n_in == D_FF ? big_.p : a_.p; a.lda = W.n_in; a.W = W.data.p; a.w_scales = W.scales.p; a.M = rows; a.N = W.n_out; a.K = W.n_in;
             a.force_bn = bn; a.force_stages = stages; a.rotate = rotate; a.splits = splits; a.ldc = W.n_out;
             if (splits > 1) { a.C = part_.p; a.epi = EPI_PARTIAL; a.out_type = OUT_F32; }
             else if (W.n_out == D_FF) { a.C = big_.p; a.epi = EPI_SILU; a.out_type = act_type(); }

@@ -38,7 +38,8 @@ struct HostPinned {
 // one GEMM weight in the engine's compute arithmetic
 struct Weight {
     std::string name; int n_out = 0, n_in = 0;
-    DevBuf data;            // f32 / f16 / bf16 [n_out][n_in]
+    DevBuf data;            // f32 / f16 / bf16 [n_out][n_in]; Q8_0 mode: int8 quants [n_out][n_in]
+    DevBuf scales;          // Q8_0 mode only: fp16 block scales [n_out][n_in / 32]
 };
 
 struct LayerW {
@@ -93,6 +94,8 @@ public:
 private:
     void load_weights(const GgufFile& g);
     void upload_weight(Weight& w, const std::string& name, const std::vector<float>& host, int n_out, int n_in);
+    // per-layer matrix straight from the file: Q8_0 tensors keep their quants in Q8_0 compute mode (fused-dequant GEMM)
+    void load_layer_matrix(Weight& w, const GgufFile& g, const std::string& out_name, const std::vector<std::string>& parts, int n_out, int n_in);
     void alloc_state();
     void zero_slot(int slot);
     void build_pos_tables(const GgufFile& g);
@@ -136,7 +139,7 @@ private:
 
     // ---- step workspace (batch-compact) ----
     int rl_ = 0;                   // PCM row length per stream-step
-    DevBuf d_pcm_, d_slot_, mel_new_, c0_, dw_, pw_, x_, a_, big_, qkv_, pw1_, encp_, part_;
+    DevBuf d_pcm_, d_slot_, mel_new_, dw_, pw_, x_, a_, big_, qkv_, pw1_, encp_, part_;
     DevBuf out_tok_, out_cnt_, dec_sync_;
     HostPinned h_pcm_, h_slot_, h_tok_, h_cnt_;
 

@@ -57,6 +57,21 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// ---- thread-block clusters: A-tile multicast (every CTA of a cluster row needs the same activation tile) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -80,14 +95,6 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -124,92 +131,14 @@ struct TcParams {
     void* C0; int m_out;       // EPI_PARTIAL: slice 0 (+bias) goes to C0 when set, slices z >= 1 to C + (z-1) * m_out * ldc
 };
 
-template <int BN, int STAGES>
-struct Smem {
-    alignas(1024) uint8_t a[STAGES][BM * ROW_BYTES];
-    alignas(1024) uint8_t b[STAGES][BN * ROW_BYTES];
-    alignas(8) uint64_t full[STAGES];
-    uint64_t empty[STAGES];
-    uint64_t tmem_full;
-    uint32_t tmem_slot;
-};
-
-template <int BN, int STAGES, int EB>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    using S = Smem<BN, STAGES>;
-    S& s = *reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
-    constexpr int BK = ROW_BYTES / EB;                                          // elements per k-block (64 for 16-bit, 32 for tf32)
-    const int nk = p.K / BK / (int)gridDim.z;                                   // k-blocks of this split
-    const int kb0 = (int)blockIdx.z * nk;
-    const int rot = p.rot ? (int)(blockIdx.x % (unsigned)nk) : 0;       // k-block visited at loop index kb: kb0 + (kb + rot) % nk
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-    constexpr uint32_t STAGE_BYTES = (BM + BN) * ROW_BYTES;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
-        mbar_init(&s.tmem_full, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    }
-    if (warp == 2) tmem_alloc(&s.tmem_slot, TMEM_COLS);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = s.tmem_slot;
-    if (threadIdx.x == 0) pdl_trigger();                        // the next kernel may start its own prologue / weight prefetch
-
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (elect_one()) {
-            // Weights do not depend on the previous kernel: fill the ring with W tiles BEFORE waiting for it (PDL), so
-            // HBM streaming of this GEMM overlaps the tail of its predecessor; A tiles follow after the wait.
-            const int pre = nk < STAGES ? nk : STAGES;
-            for (int kb = 0; kb < pre; ++kb) {
-                mbar_expect_tx(&s.full[kb], STAGE_BYTES);
-                tma_load_2d(s.b[kb], &tmB, &s.full[kb], (kb0 + (kb + rot) % nk) * BK, n0);
-            }
-            pdl_wait();
-            for (int kb = 0; kb < pre; ++kb) tma_load_2d(s.a[kb], &tmA, &s.full[kb], (kb0 + (kb + rot) % nk) * BK, m0);
-            for (int kb = pre; kb < nk; ++kb) {
-                const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&s.empty[st], ph ^ 1);
-                mbar_expect_tx(&s.full[st], STAGE_BYTES);
-                const int kc = (kb0 + (kb + rot) % nk) * BK;
-                tma_load_2d(s.a[st], &tmA, &s.full[st], kc, m0);
-                tma_load_2d(s.b[st], &tmB, &s.full[st], kc, n0);
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (elect_one()) {
-            const uint32_t idesc = make_idesc(p.fmt, BN);
-            for (int kb = 0; kb < nk; ++kb) {
-                const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&s.full[st], ph);
-                tc_fence_after();
-                const uint32_t a_addr = smem_u32(s.a[st]), b_addr = smem_u32(s.b[st]);
-#pragma unroll
-                for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k) {
-                    if (EB == 4) umma_tf32(tmem_base, make_desc(a_addr + k * UMMA_K_BYTES), make_desc(b_addr + k * UMMA_K_BYTES), idesc, (kb | k) ? 1u : 0u);
-                    else umma_f16(tmem_base, make_desc(a_addr + k * UMMA_K_BYTES), make_desc(b_addr + k * UMMA_K_BYTES), idesc, (kb | k) ? 1u : 0u);
-                }
-                umma_commit(&s.empty[st]);                      // smem stage reusable once these MMAs retire
-            }
-            umma_commit(&s.tmem_full);                          // accumulator complete
-        }
-    } else {
-        // ===================== epilogue (4 warps; TMEM lane quarter = warp % 4) =====================
+// Epilogue of one 128 x BN tile (4 warps; TMEM lane quarter = warp % 4): tcgen05.ld the fp32 accumulator, apply the fused
+// epilogue, store. Called by warps 2-5 after the accumulator barrier.
+template <int BN>
+__device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full, int warp, int lane, int m0, int n0) {
         const int q = warp & 3;
         const int row = m0 + q * 32 + lane;
         pdl_wait();                                             // C / bias may be produced (or still read) by the previous kernel
-        mbar_wait(&s.tmem_full, 0);
+        mbar_wait(tmem_full, 0);
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {                      // 32 consecutive columns of this thread's row: full 32-byte sectors per store
@@ -272,6 +201,242 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
+}
+
+template <int BN, int STAGES>
+struct Smem {
+    alignas(1024) uint8_t a[STAGES][BM * ROW_BYTES];
+    alignas(1024) uint8_t b[STAGES][BN * ROW_BYTES];
+    alignas(8) uint64_t full[STAGES];
+    uint64_t empty[STAGES];
+    uint64_t tmem_full;
+    uint32_t tmem_slot;
+};
+
+// CL > 1: clusters of CL CTAs along N. Each CTA fetches 1/CL of every A tile and multicasts it to the whole cluster, so the
+// activation tile crosses L2 -> SM once per cluster instead of once per CTA (at M = 128 the A re-reads, not the weights,
+// dominate L2 traffic). A stage is refilled only when ALL CTAs of the cluster have consumed it: the MMA warp's commit
+// arrives on the `empty` barrier of every CTA in the cluster (count CL).
+template <int BN, int STAGES, int EB, int CL>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    using S = Smem<BN, STAGES>;
+    S& s = *reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+    constexpr int BK = ROW_BYTES / EB;                                          // elements per k-block (64 for 16-bit, 32 for tf32)
+    const int nk = p.K / BK / (int)gridDim.z;                                   // k-blocks of this split
+    const int kb0 = (int)blockIdx.z * nk;
+    const int rot = p.rot ? (int)((blockIdx.x / CL) % (unsigned)nk) : 0;  // k-block visited at loop index kb: kb0 + (kb + rot) % nk (same for a whole cluster)
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr uint32_t STAGE_BYTES = (BM + BN) * ROW_BYTES;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], CL); }
+        mbar_init(&s.tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 2) tmem_alloc(&s.tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    if (CL > 1) cluster_sync_all();                             // peers' barriers are initialised before any multicast / remote arrive
+    tc_fence_after();
+    const uint32_t tmem_base = s.tmem_slot;
+    if (threadIdx.x == 0) pdl_trigger();                        // the next kernel may start its own prologue / weight prefetch
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+    constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
+    constexpr int A_SLICE_ROWS = BM / CL;
+    auto load_a = [&](int st, int kc) {
+        if (CL > 1) tma_load_2d_mc(s.a[st] + crank * A_SLICE_ROWS * ROW_BYTES, &tmA, &s.full[st], kc, m0 + (int)crank * A_SLICE_ROWS, MC_MASK);
+        else tma_load_2d(s.a[st], &tmA, &s.full[st], kc, m0);
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            // Weights do not depend on the previous kernel: fill the ring with W tiles BEFORE waiting for it (PDL), so
+            // HBM streaming of this GEMM overlaps the tail of its predecessor; A tiles follow after the wait.
+            const int pre = nk < STAGES ? nk : STAGES;
+            for (int kb = 0; kb < pre; ++kb) {
+                mbar_expect_tx(&s.full[kb], STAGE_BYTES);
+                tma_load_2d(s.b[kb], &tmB, &s.full[kb], (kb0 + (kb + rot) % nk) * BK, n0);
+            }
+            pdl_wait();
+            for (int kb = 0; kb < pre; ++kb) load_a(kb, (kb0 + (kb + rot) % nk) * BK);
+            for (int kb = pre; kb < nk; ++kb) {
+                const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&s.empty[st], ph ^ 1);
+                mbar_expect_tx(&s.full[st], STAGE_BYTES);
+                const int kc = (kb0 + (kb + rot) % nk) * BK;
+                load_a(st, kc);
+                tma_load_2d(s.b[st], &tmB, &s.full[st], kc, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc(p.fmt, BN);
+            for (int kb = 0; kb < nk; ++kb) {
+                const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&s.full[st], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(s.a[st]), b_addr = smem_u32(s.b[st]);
+#pragma unroll
+                for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k) {
+                    if (EB == 4) umma_tf32(tmem_base, make_desc(a_addr + k * UMMA_K_BYTES), make_desc(b_addr + k * UMMA_K_BYTES), idesc, (kb | k) ? 1u : 0u);
+                    else umma_f16(tmem_base, make_desc(a_addr + k * UMMA_K_BYTES), make_desc(b_addr + k * UMMA_K_BYTES), idesc, (kb | k) ? 1u : 0u);
+                }
+                if (CL > 1) umma_commit_mc(&s.empty[st], MC_MASK);   // stage reusable cluster-wide once these MMAs retire
+                else umma_commit(&s.empty[st]);                 // smem stage reusable once these MMAs retire
+            }
+            umma_commit(&s.tmem_full);                          // accumulator complete
+        }
+    } else {
+        // ===================== epilogue =====================
+        tc_epilogue<BN>(p, tmem_base, &s.tmem_full, warp, lane, m0, n0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (CL > 1) cluster_sync_all();                             // no CTA leaves while a peer's commit may still arrive on its barriers
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Q8_0 weights with the dequantisation fused into the operand path. The weight stays in HBM as the GGUF holds it, split
+// into two planes at load (int8 quants [N][K], fp16 block scales [N][K/32]; the 34-byte blocks are not TMA-friendly).
+// Per k-block: TMA brings the A tile (fp16, swizzled) and the RAW int8 W tile [BN][64]; warps 2-5 turn it into the fp16
+// K-major SWIZZLE_128B tile the tensor core reads -- value = fp16(d) * q rounded to fp16, exactly what a load-time
+// dequantisation to fp16 would hold -- fence it to the async proxy and signal the MMA warp. HBM traffic per weight is
+// 1.0625 bytes instead of 2. The same warps run the epilogue afterwards.
+// ------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct SmemQ8 {
+    alignas(1024) uint8_t a[STAGES][BM * ROW_BYTES];
+    alignas(1024) uint8_t b[STAGES][BN * ROW_BYTES];            // dequantised tile
+    alignas(128) uint8_t q[STAGES][BN * 64];                    // raw quants, row-major [BN][64]
+    alignas(16) __half sc[BN * 128];                            // block scales of this CTA's k range: [BN][2 * nk], nk <= 64
+    alignas(8) uint64_t full[STAGES];
+    uint64_t bready[STAGES];
+    uint64_t empty[STAGES];
+    uint64_t tmem_full;
+    uint32_t tmem_slot;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_q8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmQ, const __half* __restrict__ scales,
+               const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    using S = SmemQ8<BN, STAGES>;
+    S& s = *reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+    constexpr int BK = 64;
+    const int nk = p.K / BK / (int)gridDim.z;
+    const int kb0 = (int)blockIdx.z * nk;
+    const int rot = p.rot ? (int)(blockIdx.x % (unsigned)nk) : 0;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr uint32_t STAGE_BYTES = BM * ROW_BYTES + BN * 64;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.bready[i], 128); mbar_init(&s.empty[i], 1); }
+        mbar_init(&s.tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+    }
+    if (warp == 2) tmem_alloc(&s.tmem_slot, TMEM_COLS);
+    if (warp >= 2) {                                             // block scales of this tile's k range (static data: before the PDL wait)
+        const int t = threadIdx.x - 64, per_row = 2 * nk;
+        const __half* src0 = scales + (size_t)n0 * (p.K / 32) + (size_t)kb0 * 2;
+        if ((nk & 1) == 0) {                                     // 8-byte vectors: one round trip for the whole tile
+            const int vpr = per_row / 4;
+            for (int e = t; e < BN * vpr; e += 128) {
+                const int r = e / vpr, j = e % vpr;
+                *reinterpret_cast<uint2*>(&s.sc[r * per_row + j * 4]) = __ldg(reinterpret_cast<const uint2*>(src0 + (size_t)r * (p.K / 32) + j * 4));
+            }
+        } else {
+            for (int e = t; e < BN * per_row; e += 128) {
+                const int r = e / per_row, j = e % per_row;
+                s.sc[r * per_row + j] = src0[(size_t)r * (p.K / 32) + j];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s.tmem_slot;
+    if (threadIdx.x == 0) pdl_trigger();
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            const int pre = nk < STAGES ? nk : STAGES;
+            for (int kb = 0; kb < pre; ++kb) {
+                mbar_expect_tx(&s.full[kb], STAGE_BYTES);
+                tma_load_2d(s.q[kb], &tmQ, &s.full[kb], (kb0 + (kb + rot) % nk) * BK, n0);
+            }
+            pdl_wait();
+            for (int kb = 0; kb < pre; ++kb) tma_load_2d(s.a[kb], &tmA, &s.full[kb], (kb0 + (kb + rot) % nk) * BK, m0);
+            for (int kb = pre; kb < nk; ++kb) {
+                const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&s.empty[st], ph ^ 1);
+                mbar_expect_tx(&s.full[st], STAGE_BYTES);
+                const int kc = (kb0 + (kb + rot) % nk) * BK;
+                tma_load_2d(s.a[st], &tmA, &s.full[st], kc, m0);
+                tma_load_2d(s.q[st], &tmQ, &s.full[st], kc, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc(0, BN);
+            for (int kb = 0; kb < nk; ++kb) {
+                const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&s.full[st], ph);                     // A tile landed
+                mbar_wait(&s.bready[st], ph);                   // W tile dequantised
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(s.a[st]), b_addr = smem_u32(s.b[st]);
+#pragma unroll
+                for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k)
+                    umma_f16(tmem_base, make_desc(a_addr + k * UMMA_K_BYTES), make_desc(b_addr + k * UMMA_K_BYTES), idesc, (kb | k) ? 1u : 0u);
+                umma_commit(&s.empty[st]);
+            }
+            umma_commit(&s.tmem_full);
+        }
+    } else {
+        // ===================== dequantiser (then epilogue) =====================
+        const int t = threadIdx.x - 64;                          // 0..127: 32 rows x 4 sixteen-byte chunks per pass
+        const int c = t & 3, per_row = 2 * nk;
+        for (int kb = 0; kb < nk; ++kb) {
+            const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+            const int kk = (kb + rot) % nk;                     // k-block of this stage within the CTA's range
+            mbar_wait(&s.full[st], ph);
+#pragma unroll
+            for (int pz = 0; pz < BN / 32; ++pz) {
+                const int r = pz * 32 + (t >> 2);
+                const int4 raw = *reinterpret_cast<const int4*>(&s.q[st][r * 64 + c * 16]);
+                const float d = __half2float(s.sc[r * per_row + kk * 2 + (c >> 1)]);
+                const int8_t* qv = reinterpret_cast<const int8_t*>(&raw);
+                __half2 h[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(d * (float)qv[2 * i], d * (float)qv[2 * i + 1]);
+                uint8_t* row = &s.b[st][r * ROW_BYTES];
+                *reinterpret_cast<uint4*>(row + (((2 * c) ^ (r & 7)) << 4)) = *reinterpret_cast<uint4*>(&h[0]);      // SWIZZLE_128B: chunk ^= row % 8
+                *reinterpret_cast<uint4*>(row + (((2 * c + 1) ^ (r & 7)) << 4)) = *reinterpret_cast<uint4*>(&h[4]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to the tensor core
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s.bready[st])) : "memory");
+        }
+        tc_epilogue<BN>(p, tmem_base, &s.tmem_full, warp, lane, m0, n0);
     }
     tc_fence_before();
     __syncthreads();
@@ -309,20 +474,60 @@ CUtensorMap make_map(const void* ptr, int rows, int K, long long ld, int box_row
     return m;
 }
 
-template <int BN, int STAGES, int EB>
-void launch_cfg_e(const GemmArgs& a, int fmt, cudaStream_t st) {
+CUtensorMap make_map_u8(const void* ptr, int rows, int K, int box_rows) {
+    CUtensorMap m;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)K};
+    const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled (u8) failed (" + std::to_string((int)r) + ")");
+    return m;
+}
+
+template <int BN, int STAGES>
+void launch_cfg_q8(const GemmArgs& a, cudaStream_t st) {
+    static bool attr_set = false;
+    const size_t smem = sizeof(SmemQ8<BN, STAGES>) + 1024;
+    if (!attr_set) {
+        NSB_CUDA(cudaFuncSetAttribute(gemm_q8_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    if (a.K / 64 / a.splits > 64) throw CudaError("gemm_q8: k range per CTA too long for the scale buffer");
+    const CUtensorMap tmA = make_map(a.A, a.M, a.K, a.lda, BM, 0);
+    const CUtensorMap tmQ = make_map_u8(a.W, a.N, a.K, BN);
+    const int m_out = a.c_group > 0 ? (a.M / a.c_group) * (a.c_group - a.c_drop) : a.M;
+    TcParams p{a.M, a.N, a.K, a.bias, a.C, a.ldc, a.epi, a.alpha, a.out_type, 0, a.rotate, a.c_group, a.c_drop, a.C0, m_out};
+    dim3 grid(a.N / BN, (a.M + BM - 1) / BM, a.splits);
+    launch_k(gemm_q8_kernel<BN, STAGES>, grid, dim3(TC_THREADS), smem, st, tmA, tmQ, (const __half*)a.w_scales, p);
+}
+
+bool multicast_enabled() {
+    static const bool on = [] { const char* e = getenv("NSB_NO_MC"); return !(e && e[0] == '1'); }();
+    return on;
+}
+
+template <int BN, int STAGES, int EB, int CL>
+void launch_cfg_c(const GemmArgs& a, int fmt, cudaStream_t st) {
     static bool attr_set = false;
     const size_t smem = sizeof(Smem<BN, STAGES>) + 1024;
     if (!attr_set) {
-        NSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EB, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    const CUtensorMap tmA = make_map(a.A, a.M, a.K, a.lda, BM, fmt);
+    const CUtensorMap tmA = make_map(a.A, a.M, a.K, a.lda, BM / CL, fmt);
     const CUtensorMap tmB = make_map(a.W, a.N, a.K, a.K, BN, fmt);
     const int m_out = a.c_group > 0 ? (a.M / a.c_group) * (a.c_group - a.c_drop) : a.M;
     TcParams p{a.M, a.N, a.K, a.bias, a.C, a.ldc, a.epi, a.alpha, a.out_type, fmt, a.rotate, a.c_group, a.c_drop, a.C0, m_out};
     dim3 grid(a.N / BN, (a.M + BM - 1) / BM, a.splits);
-    launch_k(gemm_tc_kernel<BN, STAGES, EB>, grid, dim3(TC_THREADS), smem, st, tmA, tmB, p);
+    launch_k_cluster(gemm_tc_kernel<BN, STAGES, EB, CL>, grid, dim3(TC_THREADS), smem, st, CL, tmA, tmB, p);
+}
+template <int BN, int STAGES, int EB>
+void launch_cfg_e(const GemmArgs& a, int fmt, cudaStream_t st) {
+    if (a.multicast && multicast_enabled() && (a.N / BN) % 4 == 0) launch_cfg_c<BN, STAGES, EB, 4>(a, fmt, st);
+    else launch_cfg_c<BN, STAGES, EB, 1>(a, fmt, st);
 }
 template <int BN, int STAGES>
 void launch_cfg(const GemmArgs& a, int fmt, cudaStream_t st) {
@@ -343,6 +548,15 @@ void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
         throw CudaError("gemm_tc: unsupported shape (need K % 64 == 0 (tf32: 32), N % 32 == 0, 16-byte aligned rows)");
     if (a.c_group > 0 && a.M % a.c_group != 0) throw CudaError("gemm_tc: M must be a multiple of the output row group");
     const int tiles_m = (a.M + BM - 1) / BM;
+    if (a.w_scales) {                                             // Q8_0 planes: fused-dequant kernel (A is fp16)
+        if (fmt != 0) throw CudaError("gemm_q8: activations must be fp16");
+        if (a.splits > 1 && (a.epi != EPI_PARTIAL || (a.K / BK) % a.splits != 0)) throw CudaError("gemm_tc: bad split-K request");
+        if (a.splits > 1) { if (a.N % 64 == 0 && a.K >= 4096) launch_cfg_q8<64, 4>(a, st); else launch_cfg_q8<32, 5>(a, st); return; }
+        if (a.N % 128 == 0 && (long long)tiles_m * (a.N / 128) >= 120) launch_cfg_q8<128, 4>(a, st);
+        else if (a.N % 64 == 0 && (long long)tiles_m * (a.N / 64) >= 120) launch_cfg_q8<64, 4>(a, st);
+        else launch_cfg_q8<32, 5>(a, st);
+        return;
+    }
     if (a.force_bn) {                                             // tuning hook
         if (a.splits > 1 && (a.epi != EPI_PARTIAL || (a.K / BK) % a.splits != 0)) throw CudaError("gemm_tc: bad split-K request");
         const int key = a.force_bn * 100 + a.force_stages;

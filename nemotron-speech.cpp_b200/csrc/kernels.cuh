@@ -15,6 +15,9 @@ void launch_logmel(const int16_t* pcm, int pcm_row_stride, int B, int n_frames, 
 // from the per-slot history, the rest from mel_new. Output NHWC [B][t1][65][256].
 void launch_conv0(const float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, const float* w_t /*[9][256]*/,
                   const float* bias, float* out, cudaStream_t st);
+// conv0 + ReLU fused into the first depthwise conv: mel chunk -> [B][t2][33][256] (the conv0 image never reaches HBM)
+void launch_stem_conv0_dw(const float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, const float* w0_t,
+                          const float* b0, const float* w2_t, const float* b2, float* out, cudaStream_t st);
 // history = last 9 frames of [hist || new]
 void launch_mel_hist_update(float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, cudaStream_t st);
 // optional tap: full chunk image [B][M][128]
@@ -29,7 +32,8 @@ struct GemmArgs {
     long long lda = 0;            // elements
     // optional row map: A row(m) = (m / group) * group_stride + (m % group + row_off) * lda   (group == 0 -> m * lda)
     int group = 0; long long group_stride = 0; int row_off = 0;
-    const void* W = nullptr;      // [N, K] row-major
+    const void* W = nullptr;      // [N, K] row-major (Q8_0: the int8 quant plane)
+    const void* w_scales = nullptr;   // Q8_0 only: fp16 block scales [N][K/32]; selects the fused-dequant tensor-core kernel
     int M = 0, N = 0, K = 0;
     const float* bias = nullptr;  // [N] or null
     void* C = nullptr; long long ldc = 0;
@@ -39,6 +43,7 @@ struct GemmArgs {
     // EPI_PARTIAL, an optional destination C0 for k-slice 0 (+bias); slices z >= 1 then go to C[z-1]
     int c_group = 0, c_drop = 0; void* C0 = nullptr;
     int force_bn = 0, force_stages = 0;   // tuning hooks (bench_gemm): pick the tile config explicitly
+    int multicast = 1;            // A-tile multicast over clusters of 4 CTAs along N (when N / BN is a multiple of 4)
     int rotate = 1;               // CTA n starts its k loop at k-block (n mod nk): de-synchronises the A-tile reads of the grid
 };
 void launch_gemm_simt(const GemmArgs& a, cudaStream_t st);

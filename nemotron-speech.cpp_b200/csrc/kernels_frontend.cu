@@ -107,6 +107,69 @@ void launch_conv0(const float* mel_hist, const float* mel_new, const int* slot_o
     launch_k(conv0_kernel, dim3(W1, t1, B), dim3(SUB_CH), 0, st, mel_hist, mel_new, slot_of_b, T, w_t, bias, out);
 }
 
+// conv0 (+bias, ReLU) fused into the first depthwise 3x3 s2 conv (+bias): the [t1][65][256] conv0 image (55 MB per
+// 64-stream step) never goes to HBM. One CTA = one output row (b, oh2); thread = channel; the 7 mel rows the row depends
+// on sit in shared memory (broadcast reads); a 3x3 register window of conv0 values slides along the frequency axis, so
+// every conv0 value is computed once per output row. Same accumulation order as the two stand-alone kernels (bit-identical).
+__global__ void __launch_bounds__(SUB_CH) stem_conv0_dw_kernel(const float* __restrict__ hist, const float* __restrict__ mel_new,
+                                                               const int* __restrict__ slot_of_b, int T, const float* __restrict__ w0_t,
+                                                               const float* __restrict__ b0, const float* __restrict__ w2_t,
+                                                               const float* __restrict__ b2, float* __restrict__ out) {
+    __shared__ float mel[7][N_MELS];
+    pdl_wait(); pdl_trigger();
+    const int oh2 = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
+    const int M = PRE_CACHE + 8 * T, t1 = M / 2 + 1, t2 = gridDim.x;
+    constexpr int W1 = N_MELS / 2 + 1, W2 = W1 / 2 + 1;                         // 65, 33
+    const int slot = slot_of_b[b];
+    for (int e = c; e < 7 * N_MELS; e += SUB_CH) {
+        const int r = e / N_MELS, m = e % N_MELS, f = 4 * oh2 - 6 + r;          // mel rows 4 oh2 - 6 .. 4 oh2
+        mel[r][m] = (f >= 0 && f < M) ? chunk_mel(hist, mel_new, slot, b, T, f, m) : 0.0f;
+    }
+    float w0[9], w2[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { w0[k] = w0_t[k * SUB_CH + c]; w2[k] = w2_t[k * SUB_CH + c]; }
+    const float bias0 = b0[c], bias2 = b2[c];
+    __syncthreads();
+    // conv0 value at (row h = 2 oh2 - 2 + kh2, column w); zero outside the conv0 image (the depthwise conv's padding)
+    auto conv0_at = [&](int kh2, int w) -> float {
+        const int h = 2 * oh2 - 2 + kh2;
+        if (h < 0 || h >= t1 || w < 0 || w >= W1) return 0.0f;
+        float acc = 0.0f;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int iw = 2 * w + kw - 2;                                   // mel row 2h + kh - 2 = (4 oh2 - 6) + 2 kh2 + kh
+                const float x = (iw >= 0 && iw < N_MELS) ? mel[2 * kh2 + kh][iw] : 0.0f;
+                acc = fmaf(x, w0[kh * 3 + kw], acc);
+            }
+        }
+        return fmaxf(acc + bias0, 0.0f);
+    };
+    float win[3][3];
+#pragma unroll
+    for (int kh2 = 0; kh2 < 3; ++kh2) win[kh2][2] = conv0_at(kh2, -2);           // column 2*0 - 2 (out of range -> 0)
+    for (int ow2 = 0; ow2 < W2; ++ow2) {
+#pragma unroll
+        for (int kh2 = 0; kh2 < 3; ++kh2) {
+            win[kh2][0] = win[kh2][2];
+            win[kh2][1] = conv0_at(kh2, 2 * ow2 - 1);
+            win[kh2][2] = conv0_at(kh2, 2 * ow2);
+        }
+        float acc = 0.0f;
+#pragma unroll
+        for (int kh2 = 0; kh2 < 3; ++kh2)
+#pragma unroll
+            for (int kw2 = 0; kw2 < 3; ++kw2) acc = fmaf(win[kh2][kw2], w2[kh2 * 3 + kw2], acc);
+        out[(((size_t)b * t2 + oh2) * W2 + ow2) * SUB_CH + c] = acc + bias2;
+    }
+}
+void launch_stem_conv0_dw(const float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, const float* w0_t,
+                          const float* b0, const float* w2_t, const float* b2, float* out, cudaStream_t st) {
+    const int M = PRE_CACHE + 8 * T, t1 = M / 2 + 1, t2 = t1 / 2 + 1;
+    launch_k(stem_conv0_dw_kernel, dim3(t2, B), dim3(SUB_CH), 0, st, mel_hist, mel_new, slot_of_b, T, w0_t, b0, w2_t, b2, out);
+}
+
 __global__ void __launch_bounds__(N_MELS) mel_hist_update_kernel(float* __restrict__ hist, const float* __restrict__ mel_new,
                                                                  const int* __restrict__ slot_of_b, int T) {
     pdl_wait(); pdl_trigger();
