@@ -504,8 +504,11 @@ void launch_cfg_q8(const GemmArgs& a, cudaStream_t st) {
     launch_k(gemm_q8_kernel<BN, STAGES>, grid, dim3(TC_THREADS), smem, st, tmA, tmQ, (const __half*)a.w_scales, p);
 }
 
+// Experimental, off by default: on B200 the multicast variant measured SLOWER than per-CTA A loads at M = 128
+// (ff1a 7.7 vs 6.9 us, profiles/r01_notes.md) -- L2 already serves the shared tile well and the cluster-wide stage release
+// couples the CTAs -- and it is not covered by the parity suite.
 bool multicast_enabled() {
-    static const bool on = [] { const char* e = getenv("NSB_NO_MC"); return !(e && e[0] == '1'); }();
+    static const bool on = [] { const char* e = getenv("NSB_MC"); return e && e[0] == '1'; }();
     return on;
 }
 

@@ -43,7 +43,7 @@ struct GemmArgs {
     // EPI_PARTIAL, an optional destination C0 for k-slice 0 (+bias); slices z >= 1 then go to C[z-1]
     int c_group = 0, c_drop = 0; void* C0 = nullptr;
     int force_bn = 0, force_stages = 0;   // tuning hooks (bench_gemm): pick the tile config explicitly
-    int multicast = 1;            // A-tile multicast over clusters of 4 CTAs along N (when N / BN is a multiple of 4)
+    int multicast = 1;            // allow A-tile multicast over clusters of 4 CTAs along N (experimental, only with NSB_MC=1: measured slower)
     int rotate = 1;               // CTA n starts its k loop at k-block (n mod nk): de-synchronises the A-tile reads of the grid
 };
 void launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
