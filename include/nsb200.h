@@ -94,6 +94,11 @@ int nsb_stream_reset(nsb_engine* e, int stream);   /* re-zeroes caches too (the 
  *      split into push (buffer PCM, any length) / step (one batched chunk for every stream that
  *      has a full chunk buffered) / pop (token ids decoded so far). ------------------------- */
 int nsb_stream_push_pcm(nsb_engine* e, int stream, const int16_t* pcm, int n_samples);
+/* the same for many streams in one call (a serving loop feeds every stream once per chunk period): row i of `pcm`
+ * (row_stride samples apart) goes to streams[i]; tokens of streams[i] land in out[i * cap_per_stream ..], counts[i] = how many.
+ * pop returns the total number of tokens copied. */
+int nsb_push_pcm_batch(nsb_engine* e, int n_streams, const int32_t* streams, const int16_t* pcm, int row_stride, int n_samples);
+int nsb_pop_tokens_batch(nsb_engine* e, int n_streams, const int32_t* streams, int32_t* out, int cap_per_stream, int32_t* counts);
 int nsb_stream_ready(const nsb_engine* e, int stream); /* 1 if a full chunk is buffered */
 int nsb_engine_step(nsb_engine* e);                    /* returns #streams advanced (0 = nothing ready), <0 error */
 int nsb_engine_drain(nsb_engine* e);                   /* step until nothing is ready; returns total stream-chunks */

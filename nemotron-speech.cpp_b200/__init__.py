@@ -40,7 +40,7 @@ class ModelInfo(C.Structure):
 
 EXPORTS = ["nsb_gguf_probe", "nsb_default_config", "nsb_engine_create", "nsb_engine_destroy", "nsb_last_error", "nsb_engine_n_layers",
            "nsb_engine_vocab_size", "nsb_engine_vocab", "nsb_engine_chunk_samples", "nsb_engine_shift_samples", "nsb_engine_compute",
-           "nsb_stream_open", "nsb_stream_close", "nsb_stream_reset", "nsb_stream_push_pcm", "nsb_stream_ready", "nsb_engine_step",
+           "nsb_stream_open", "nsb_stream_close", "nsb_stream_reset", "nsb_stream_push_pcm", "nsb_push_pcm_batch", "nsb_pop_tokens_batch", "nsb_stream_ready", "nsb_engine_step",
            "nsb_engine_drain", "nsb_stream_pop_tokens", "nsb_stream_chunks", "nsb_detokenize", "nsb_engine_get_stats",
            "nsb_bench_prepare", "nsb_bench_step", "nsb_bench_profile", "nsb_profiler_range", "nsb_bench_gemm", "nsb_debug_enable", "nsb_debug_get", "nsb_debug_get_cache", "nsb_op_logmel",
            "nsb_op_gemm"]
@@ -80,6 +80,8 @@ def lib():
             getattr(L, n).argtypes = [vp, ci]
         L.nsb_stream_push_pcm.argtypes = [vp, ci, _i16p, ci]
         L.nsb_stream_pop_tokens.argtypes = [vp, ci, _i32p, ci]
+        L.nsb_push_pcm_batch.argtypes = [vp, ci, _i32p, _i16p, ci, ci]
+        L.nsb_pop_tokens_batch.argtypes = [vp, ci, _i32p, _i32p, ci, _i32p]
         L.nsb_detokenize.argtypes = [vp, _i32p, ci, C.c_char_p, ci]
         L.nsb_engine_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.nsb_bench_prepare.argtypes = [vp, ci, _i16p, ci, ci]
@@ -149,6 +151,22 @@ class Engine:
         pcm = np.ascontiguousarray(pcm, dtype=np.int16)
         if len(pcm):
             _check(lib().nsb_stream_push_pcm(self.h, s, pcm, len(pcm)))
+
+    def push_batch(self, streams, pcm: np.ndarray):
+        """pcm [n_streams, n_samples] int16: row i -> streams[i] (one C call)."""
+        ids = np.ascontiguousarray(streams, dtype=np.int32)
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        assert pcm.ndim == 2 and pcm.shape[0] == len(ids)
+        if pcm.shape[1]:
+            _check(lib().nsb_push_pcm_batch(self.h, len(ids), ids, pcm.reshape(-1), pcm.shape[1], pcm.shape[1]))
+
+    def pop_tokens_batch(self, streams, cap_per_stream: int = 256):
+        """-> (tokens [n_streams, cap], counts [n_streams]); call again while a count == cap."""
+        ids = np.ascontiguousarray(streams, dtype=np.int32)
+        out = np.empty((len(ids), cap_per_stream), dtype=np.int32)
+        cnt = np.empty(len(ids), dtype=np.int32)
+        _check(lib().nsb_pop_tokens_batch(self.h, len(ids), ids, out.reshape(-1), cap_per_stream, cnt))
+        return out, cnt
 
     def ready(self, s: int) -> bool:
         return _check(lib().nsb_stream_ready(self.h, s)) == 1

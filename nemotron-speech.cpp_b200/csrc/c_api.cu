@@ -85,6 +85,14 @@ int nsb_stream_close(nsb_engine* e, int s) { if (!e) return fail(NSB_ERR_ARG, "n
 int nsb_stream_reset(nsb_engine* e, int s) { if (!e) return fail(NSB_ERR_ARG, "null engine"); NSB_TRY e->impl->reset_stream(s); return NSB_OK; NSB_CATCH }
 int nsb_stream_push_pcm(nsb_engine* e, int s, const int16_t* pcm, int n) {
     if (!e) return fail(NSB_ERR_ARG, "null engine"); NSB_TRY e->impl->push_pcm(s, pcm, n); return NSB_OK; NSB_CATCH }
+int nsb_push_pcm_batch(nsb_engine* e, int n_streams, const int32_t* streams, const int16_t* pcm, int row_stride, int n_samples) {
+    if (!e || !streams || (!pcm && n_samples > 0) || n_streams < 0) return fail(NSB_ERR_ARG, "bad argument");
+    NSB_TRY for (int i = 0; i < n_streams; ++i) e->impl->push_pcm(streams[i], pcm + (size_t)i * row_stride, n_samples); return NSB_OK; NSB_CATCH }
+int nsb_pop_tokens_batch(nsb_engine* e, int n_streams, const int32_t* streams, int32_t* out, int cap_per_stream, int32_t* counts) {
+    if (!e || !streams || !out || !counts || cap_per_stream < 0) return fail(NSB_ERR_ARG, "bad argument");
+    NSB_TRY int total = 0;
+    for (int i = 0; i < n_streams; ++i) { counts[i] = e->impl->pop_tokens(streams[i], out + (size_t)i * cap_per_stream, cap_per_stream); total += counts[i]; }
+    return total; NSB_CATCH }
 int nsb_stream_ready(const nsb_engine* e, int s) { if (!e || s < 0 || s >= e->impl->max_streams) return NSB_ERR_ARG; return e->impl->ready(s) ? 1 : 0; }
 int nsb_engine_step(nsb_engine* e) { if (!e) return fail(NSB_ERR_ARG, "null engine"); NSB_TRY return e->impl->step(); NSB_CATCH }
 int nsb_engine_drain(nsb_engine* e) {

@@ -388,10 +388,9 @@ bool Engine::ready(int s) const {
 static void stage_row(const HostStream& h, int T, int rl, int16_t* dst) {
     // row = raw[start-1 .. start + 1280T + 352), start = 1280 T c - 256; negative indices are the 256-zero left pad / x[-1] = 0
     const long long start = 8LL * T * HOP * h.chunk_idx - N_FFT / 2 - 1;
-    for (int i = 0; i < rl; ++i) {
-        const long long idx = start + i;
-        dst[i] = idx < 0 ? (int16_t)0 : h.buf[(size_t)(idx - h.base)];
-    }
+    const int zeros = start < 0 ? (int)std::min<long long>(-start, rl) : 0;
+    if (zeros) memset(dst, 0, (size_t)zeros * sizeof(int16_t));
+    if (zeros < rl) memcpy(dst + zeros, h.buf.data() + (size_t)(start + zeros - h.base), (size_t)(rl - zeros) * sizeof(int16_t));
 }
 
 int Engine::step() {

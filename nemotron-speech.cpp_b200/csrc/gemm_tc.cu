@@ -535,7 +535,8 @@ void launch_cfg_e(const GemmArgs& a, int fmt, cudaStream_t st) {
 template <int BN, int STAGES>
 void launch_cfg(const GemmArgs& a, int fmt, cudaStream_t st) {
     if (fmt == 2) {
-        if constexpr ((BN == 32 && STAGES == 5) || (BN == 64 && STAGES == 4) || (BN == 128 && STAGES == 4)) launch_cfg_e<BN, STAGES, 4>(a, fmt, st);
+        if constexpr ((BN == 32 && STAGES == 5) || (BN == 64 && STAGES == 4) || (BN == 128 && (STAGES == 3 || STAGES == 4)) || (BN == 256 && STAGES == 2))
+            launch_cfg_e<BN, STAGES, 4>(a, fmt, st);
         else throw CudaError("gemm_tc: tile config not instantiated for tf32");
     } else launch_cfg_e<BN, STAGES, 2>(a, fmt, st);
 }
@@ -583,8 +584,13 @@ void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
         if (a.N % 64 == 0 && a.K >= 4096) launch_cfg<64, 4>(a, fmt, st); else launch_cfg<32, 5>(a, fmt, st);
         return;
     }
-    // pick the widest N tile that still yields >= ~1 wave of CTAs (weight streaming needs many SMs pulling)
-    if (a.N % 128 == 0 && (long long)tiles_m * (a.N / 128) >= 120) launch_cfg<128, 4>(a, fmt, st);
+    // Tile choice (profiles/r01_gemm_tile_sweep*.txt). Small batches stream weights: narrow tiles so that >= ~1 wave of CTAs pulls.
+    // Large batches are tensor-bound: wide tiles, and a shared-memory footprint <= ~100 KB so that two CTAs share an SM and one's
+    // epilogue overlaps the other's main loop (the kernel has a single TMEM accumulator per CTA).
+    const long long t256 = a.N % 256 == 0 ? (long long)tiles_m * (a.N / 256) : 0, t128 = a.N % 128 == 0 ? (long long)tiles_m * (a.N / 128) : 0;
+    if (t256 >= 200) launch_cfg<256, 2>(a, fmt, st);
+    else if (t128 >= 200) launch_cfg<128, 3>(a, fmt, st);
+    else if (t128 >= 100) launch_cfg<128, 4>(a, fmt, st);
     else if (a.N % 64 == 0 && (long long)tiles_m * (a.N / 64) >= 120) launch_cfg<64, 4>(a, fmt, st);
     else launch_cfg<32, 5>(a, fmt, st);
 }

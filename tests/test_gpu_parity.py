@@ -311,3 +311,33 @@ def test_reference_cli_dropin_end_to_end(built, tmp_path):
     text = om.detok(ref.tokens())
     assert r.stdout.decode() == text + text + "\n"
     assert f"Chunks processed:    {ref.chunks}" in r.stderr.decode()
+
+
+def test_batch_push_pop_equals_per_stream_calls(built):
+    """nsb_push_pcm_batch / nsb_pop_tokens_batch (one C call per serving tick) == the per-stream entry points."""
+    import nsb200
+    R = 1
+    path = synth.cached_model("f32", 2, R=R)
+    audio = np.stack([synth.synth_pcm(120 + s, 1.5) for s in range(6)])
+    a = nsb200.Engine(path, right_context=R, max_streams=6, compute=nsb200.COMPUTE_F32)
+    ids = [a.open_stream() for _ in range(6)]
+    for s in range(6):
+        a.push(ids[s], audio[s])
+    a.drain()
+    ref = [a.pop_tokens(i) for i in ids]
+    b = nsb200.Engine(path, right_context=R, max_streams=6, compute=nsb200.COMPUTE_F32)
+    ids2 = [b.open_stream() for _ in range(6)]
+    got = [[] for _ in range(6)]
+    step = b.shift_samples
+    for p in range(0, audio.shape[1], step):
+        b.push_batch(ids2, audio[:, p:p + step])
+        while b.step() > 0:
+            pass
+        toks, cnt = b.pop_tokens_batch(ids2, 64)
+        for s in range(6):
+            got[s] += toks[s, :cnt[s]].tolist()
+    for s in range(6):
+        assert got[s] == ref[s].tolist(), s
+    with pytest.raises(nsb200.NsbError):
+        b.push_batch([0, 99], audio[:2])                                 # bad stream id in the batch
+    a.close(); b.close()

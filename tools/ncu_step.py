@@ -24,7 +24,7 @@ WARM = 70 // T + 3
 
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-    wtype = "q8_0" if COMPUTE == 4 else "f16"
+    wtype = "q8_0" if COMPUTE == 4 else ("f32" if COMPUTE == 1 else "f16")
     path = synth.cached_model(wtype, N_LAYERS, R=R)
     eng = nsb200.Engine(path, right_context=R, max_streams=STREAMS, compute=COMPUTE, kv_dtype=KV)
     need = 160 * (8 * T * (WARM + 1) - 1) + 256
