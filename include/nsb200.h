@@ -127,6 +127,14 @@ int nsb_bench_profile(nsb_engine* e, float* ms_per_class, int* launches_per_clas
  * 5 pw2) with an explicit tcgen05 tile config (bn, stages, split-K, k rotation); *us = mean device microseconds per GEMM */
 int nsb_bench_gemm(nsb_engine* e, int kind, int rows, int bn, int stages, int splits, int rotate, int iters, float* us);
 
+/* ---- in-situ device trace: block 0 of every kernel stamps %globaltimer (ns) at start [0], after it stopped waiting for the
+ * previous kernel [1] (GEMM: prologue done [1], wait returned [2], accumulator complete [3], epilogue done [4]) and at its end [2].
+ * Works inside the CUDA graph, where ncu cannot look. tag: 1 log-mel, 2 stem, 3 dwconv, 4 mel history, 5 fp32 GEMM, 6 tcgen05 GEMM,
+ * 7 Q8_0 GEMM, 8 LayerNorm, 9 fused double LayerNorm, 10 attention, 11 conv module, 12 advance, 13 decode. capacity 0 = off. */
+typedef struct nsb_trace_record { uint64_t t[6]; int32_t tag; int32_t grid; } nsb_trace_record;
+int nsb_trace_enable(nsb_engine* e, int capacity);
+int nsb_trace_fetch(nsb_engine* e, nsb_trace_record* out, int cap); /* returns #records copied, resets the trace */
+
 /* cudaProfilerStart / cudaProfilerStop, so that `ncu --profile-from-start off` captures only the steady-state steps */
 int nsb_profiler_range(int on);
 

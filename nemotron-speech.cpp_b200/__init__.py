@@ -33,6 +33,14 @@ class Stats(C.Structure):
                 ("last_step_ms", C.c_double)]
 
 
+class TraceRecord(C.Structure):
+    _fields_ = [("t", C.c_uint64 * 6), ("tag", C.c_int32), ("grid", C.c_int32)]
+
+
+TRACE_TAGS = {1: "logmel", 2: "stem", 3: "dwconv", 4: "melhist", 5: "gemm_f32", 6: "gemm_tc", 7: "gemm_q8", 8: "ln", 9: "ln2", 10: "attn",
+              11: "convmod", 12: "advance", 13: "decode", 14: "other"}
+
+
 class ModelInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_mels", "d_model", "n_heads", "d_head", "d_ff", "n_layers", "kernel_size", "vocab_size",
                                          "decoder_dim", "joint_dim", "n_tensors", "weight_type")] + [("vocab", C.c_char * (1025 * 8))]
@@ -42,7 +50,7 @@ EXPORTS = ["nsb_gguf_probe", "nsb_default_config", "nsb_engine_create", "nsb_eng
            "nsb_engine_vocab_size", "nsb_engine_vocab", "nsb_engine_chunk_samples", "nsb_engine_shift_samples", "nsb_engine_compute",
            "nsb_stream_open", "nsb_stream_close", "nsb_stream_reset", "nsb_stream_push_pcm", "nsb_push_pcm_batch", "nsb_pop_tokens_batch", "nsb_stream_ready", "nsb_engine_step",
            "nsb_engine_drain", "nsb_stream_pop_tokens", "nsb_stream_chunks", "nsb_detokenize", "nsb_engine_get_stats",
-           "nsb_bench_prepare", "nsb_bench_step", "nsb_bench_profile", "nsb_profiler_range", "nsb_bench_gemm", "nsb_debug_enable", "nsb_debug_get", "nsb_debug_get_cache", "nsb_op_logmel",
+           "nsb_bench_prepare", "nsb_bench_step", "nsb_bench_profile", "nsb_profiler_range", "nsb_bench_gemm", "nsb_trace_enable", "nsb_trace_fetch", "nsb_debug_enable", "nsb_debug_get", "nsb_debug_get_cache", "nsb_op_logmel",
            "nsb_op_gemm"]
 
 
@@ -88,6 +96,8 @@ def lib():
         L.nsb_bench_step.argtypes = [vp, C.POINTER(C.c_float)]
         L.nsb_bench_profile.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_float)]
         L.nsb_profiler_range.argtypes = [ci]
+        L.nsb_trace_enable.argtypes = [vp, ci]
+        L.nsb_trace_fetch.argtypes = [vp, C.POINTER(TraceRecord), ci]
         L.nsb_bench_gemm.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, C.POINTER(C.c_float)]
         L.nsb_debug_enable.argtypes = [vp, ci]
         L.nsb_debug_get.argtypes = [vp, C.c_char_p, _f32p, C.c_size_t]
@@ -225,6 +235,14 @@ class Engine:
         us = C.c_float()
         _check(lib().nsb_bench_gemm(self.h, kind, rows, bn, stages, splits, rotate, iters, C.byref(us)))
         return us.value
+
+    def trace_enable(self, capacity: int):
+        _check(lib().nsb_trace_enable(self.h, capacity))
+
+    def trace_fetch(self, cap: int = 4096):
+        buf = (TraceRecord * cap)()
+        n = _check(lib().nsb_trace_fetch(self.h, buf, cap))
+        return [(TRACE_TAGS.get(buf[i].tag, str(buf[i].tag)), buf[i].grid, [int(x) for x in buf[i].t]) for i in range(n)]
 
     # ---- debug / operators ----
     def debug_enable(self, on: bool = True):

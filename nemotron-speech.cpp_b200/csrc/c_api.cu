@@ -122,6 +122,12 @@ int nsb_bench_profile(nsb_engine* e, float* ms_per_class, int* launches_per_clas
 int nsb_bench_gemm(nsb_engine* e, int kind, int rows, int bn, int stages, int splits, int rotate, int iters, float* us) {
     if (!e || !us) return fail(NSB_ERR_ARG, "bad argument"); NSB_TRY *us = e->impl->bench_gemm(kind, rows, bn, stages, splits, rotate, iters); return NSB_OK; NSB_CATCH }
 
+int nsb_trace_enable(nsb_engine* e, int capacity) { if (!e) return fail(NSB_ERR_ARG, "null engine"); NSB_TRY e->impl->trace_enable(capacity); return NSB_OK; NSB_CATCH }
+int nsb_trace_fetch(nsb_engine* e, nsb_trace_record* out, int cap) {
+    if (!e || (!out && cap > 0)) return fail(NSB_ERR_ARG, "bad argument");
+    static_assert(sizeof(nsb_trace_record) == sizeof(nsb::TraceRec), "trace record layout");
+    NSB_TRY return e->impl->trace_fetch(reinterpret_cast<nsb::TraceRec*>(out), cap); NSB_CATCH }
+
 int nsb_profiler_range(int on) { return (on ? cudaProfilerStart() : cudaProfilerStop()) == cudaSuccess ? NSB_OK : NSB_ERR_CUDA; }
 
 int nsb_debug_enable(nsb_engine* e, int on) { if (!e) return fail(NSB_ERR_ARG, "null engine"); NSB_TRY e->impl->debug_enable(on != 0); return NSB_OK; NSB_CATCH }

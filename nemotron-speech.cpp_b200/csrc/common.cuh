@@ -70,6 +70,38 @@ inline void launch_k_cluster(void (*kern)(P...), dim3 grid, dim3 block, size_t s
     NSB_CUDA(cudaLaunchKernelEx(&cfg, kern, P(std::forward<A>(args))...));
 }
 
+// ------------------------------------------------------------------------------------------
+// In-situ device tracing (nsb_trace_enable): thread 0 of block (0,0,0) of every kernel claims a record and stamps
+// %globaltimer at a few points. Unlike ncu (which serialises launches) this shows the timeline INSIDE the CUDA graph:
+// launch gaps, PDL overlap, how long a kernel sat in griddepcontrol.wait. Off = one constant-cache load per kernel.
+//   t[0] block 0 started   t[1] griddepcontrol.wait returned   t[2] block 0 finished
+//   GEMM: t[1] prologue done, t[2] wait returned (epilogue warp), t[3] accumulator complete, t[4] epilogue done
+// ------------------------------------------------------------------------------------------
+struct TraceRec { unsigned long long t[6]; int tag; int grid; };
+struct TraceBuf { unsigned n; unsigned cap; unsigned pad[2]; TraceRec rec[1]; };
+enum TraceTag : int { TR_LOGMEL = 1, TR_STEM, TR_DWCONV, TR_MELHIST, TR_GEMM_SIMT, TR_GEMM_TC, TR_GEMM_Q8, TR_LN, TR_LN2, TR_ATTN, TR_CONVMOD, TR_ADVANCE, TR_DECODE, TR_OTHER };
+static __constant__ TraceBuf* c_trace;          // one copy per translation unit, bound by NSB_DEFINE_TRACE_BINDER
+#define NSB_DEFINE_TRACE_BINDER(name) \
+    void name(TraceBuf* p) { NSB_CUDA(cudaMemcpyToSymbol(c_trace, &p, sizeof(p))); }
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ bool trace_thread() { return threadIdx.x == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0; }
+__device__ __forceinline__ int trace_begin(int tag) {
+    TraceBuf* tb = c_trace;
+    if (!tb) return -1;
+    const unsigned s = atomicAdd(&tb->n, 1u);
+    if (s >= tb->cap) return -1;
+    tb->rec[s].tag = tag; tb->rec[s].grid = (int)(gridDim.x * gridDim.y * gridDim.z); tb->rec[s].t[0] = gtime();
+    return (int)s;
+}
+__device__ __forceinline__ void trace_mark(int slot, int i) { if (slot >= 0) c_trace->rec[slot].t[i] = gtime(); }
+// the common prologue of a simple kernel: trace start, wait for the previous grid, let the next one launch
+#define NSB_KERNEL_PROLOGUE(tag)                                   \
+    int tr_slot = -1;                                              \
+    if (trace_thread()) tr_slot = trace_begin(tag);                \
+    pdl_wait(); pdl_trigger();                                     \
+    if (tr_slot >= 0) trace_mark(tr_slot, 1);
+#define NSB_KERNEL_EPILOGUE() do { if (tr_slot >= 0) trace_mark(tr_slot, 2); } while (0)
+
 // Epilogues shared by the SIMT and the tcgen05 GEMM
 enum Epi : int {
     EPI_NONE = 0,      // C = acc (+bias)

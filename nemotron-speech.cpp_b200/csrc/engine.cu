@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 
@@ -673,6 +674,33 @@ float Engine::bench_gemm(int kind, int rows, int bn, int stages, int splits, int
     NSB_CUDA(cudaEventSynchronize(ev1_));
     float ms = 0.f; NSB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
     return 1e3f * ms / (float)(iters * n_layers);
+}
+
+void Engine::trace_enable(int cap) {
+    NSB_CUDA(cudaSetDevice(device_));
+    NSB_CUDA(cudaStreamSynchronize(st_));
+    TraceBuf* p = nullptr;
+    if (cap > 0) {
+        trace_.alloc(sizeof(TraceBuf) + (size_t)cap * sizeof(TraceRec));
+        const unsigned hdr[4] = {0u, (unsigned)cap, 0u, 0u};
+        h2d_sync(trace_.p, hdr, sizeof(hdr));
+        p = trace_.as<TraceBuf>();
+    }
+    trace_cap_ = cap > 0 ? cap : 0;
+    trace_bind_frontend(p); trace_bind_layer(p); trace_bind_simt(p); trace_bind_gemm_tc(p); trace_bind_decode(p);
+    NSB_CUDA(cudaDeviceSynchronize());
+}
+
+int Engine::trace_fetch(TraceRec* out, int cap) {
+    if (!trace_cap_) return 0;
+    NSB_CUDA(cudaSetDevice(device_));
+    NSB_CUDA(cudaStreamSynchronize(st_));
+    unsigned n = 0;
+    NSB_CUDA(cudaMemcpy(&n, trace_.p, 4, cudaMemcpyDeviceToHost));
+    const int m = (int)std::min<unsigned>(std::min<unsigned>(n, (unsigned)trace_cap_), (unsigned)std::max(cap, 0));
+    if (m > 0) NSB_CUDA(cudaMemcpy(out, (char*)trace_.p + offsetof(TraceBuf, rec), (size_t)m * sizeof(TraceRec), cudaMemcpyDeviceToHost));
+    const unsigned zero = 0; h2d_sync(trace_.p, &zero, 4);
+    return m;
 }
 
 cudaEvent_t Engine::prof_event() {

@@ -78,6 +78,10 @@ public:
     // returns mean device us per GEMM
     float bench_gemm(int kind, int rows, int bn, int stages, int splits, int rotate, int iters);
 
+    // device tracing (common.cuh): cap records; fetch copies the records written so far (launch order) and resets the counter
+    void trace_enable(int cap);
+    int trace_fetch(TraceRec* out, int cap);
+
     void debug_enable(bool on);
     long long debug_get(const std::string& name, float* out, size_t cap);
     long long debug_get_cache(int stream, int which, int layer, float* out, size_t cap);
@@ -162,6 +166,7 @@ private:
     // ---- debug taps ----
     bool debug_ = false; int dbg_B_ = 0;
     DevBuf dbg_mel_, dbg_sub_, dbg_layers_, dbg_logits_, dbg_logits_n_;
+    DevBuf trace_; int trace_cap_ = 0;
 };
 
 }  // namespace nsb

@@ -10,6 +10,8 @@
 
 namespace nsb {
 
+NSB_DEFINE_TRACE_BINDER(trace_bind_simt)
+
 namespace {
 constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;
 
@@ -20,7 +22,7 @@ __device__ __forceinline__ const float* a_row_ptr(const GemmArgs& g, int m) {
 }
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmArgs g) {
-    pdl_wait(); pdl_trigger();
+    NSB_KERNEL_PROLOGUE(TR_GEMM_SIMT)
     __shared__ float As[2][BK][BM + PAD], Bs[2][BK][BN + PAD];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -70,6 +72,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmArgs g) {
             store_out(g.C, o, v, g.out_type);
         }
     }
+    NSB_KERNEL_EPILOGUE();
 }
 }  // namespace
 

@@ -24,6 +24,8 @@
 
 namespace nsb {
 
+NSB_DEFINE_TRACE_BINDER(trace_bind_gemm_tc)
+
 namespace {
 
 constexpr int BM = 128, ROW_BYTES = 128, UMMA_K_BYTES = 32;      // one k-block = one 128-byte swizzle row per tile row; 4 MMAs per k-block
@@ -134,12 +136,15 @@ struct TcParams {
 // Epilogue of one 128 x BN tile (4 warps; TMEM lane quarter = warp % 4): tcgen05.ld the fp32 accumulator, apply the fused
 // epilogue, store. Called by warps 2-5 after the accumulator barrier.
 template <int BN>
-__device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full, int warp, int lane, int m0, int n0) {
+__device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full, int warp, int lane, int m0, int n0, int trace_slot) {
+        const bool tracer = trace_slot >= 0 && threadIdx.x == 64;
         const int q = warp & 3;
         const int row = m0 + q * 32 + lane;
         pdl_wait();                                             // C / bias may be produced (or still read) by the previous kernel
+        if (tracer) trace_mark(trace_slot, 2);
         mbar_wait(tmem_full, 0);
         tc_fence_after();
+        if (tracer) trace_mark(trace_slot, 3);
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {                      // 32 consecutive columns of this thread's row: full 32-byte sectors per store
             uint32_t r[32];
@@ -201,6 +206,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
                 }
             }
         }
+        if (tracer) trace_mark(trace_slot, 4);
 }
 
 template <int BN, int STAGES>
@@ -211,6 +217,7 @@ struct Smem {
     uint64_t empty[STAGES];
     uint64_t tmem_full;
     uint32_t tmem_slot;
+    int trace_slot;
 };
 
 // CL > 1: clusters of CL CTAs along N. Each CTA fetches 1/CL of every A tile and multicasts it to the whole cluster, so the
@@ -233,6 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint32_t STAGE_BYTES = (BM + BN) * ROW_BYTES;
 
     if (threadIdx.x == 0) {
+        s.trace_slot = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 ? trace_begin(TR_GEMM_TC) : -1;
         for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], CL); }
         mbar_init(&s.tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -247,7 +255,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (CL > 1) cluster_sync_all();                             // peers' barriers are initialised before any multicast / remote arrive
     tc_fence_after();
     const uint32_t tmem_base = s.tmem_slot;
-    if (threadIdx.x == 0) pdl_trigger();                        // the next kernel may start its own prologue / weight prefetch
+    if (threadIdx.x == 0) { pdl_trigger(); trace_mark(s.trace_slot, 1); }   // the next kernel may start its own prologue / weight prefetch
     const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
     constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
     constexpr int A_SLICE_ROWS = BM / CL;
@@ -298,7 +306,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ===================== epilogue =====================
-        tc_epilogue<BN>(p, tmem_base, &s.tmem_full, warp, lane, m0, n0);
+        tc_epilogue<BN>(p, tmem_base, &s.tmem_full, warp, lane, m0, n0, s.trace_slot);
     }
     tc_fence_before();
     __syncthreads();
@@ -326,6 +334,7 @@ struct SmemQ8 {
     uint64_t empty[STAGES];
     uint64_t tmem_full;
     uint32_t tmem_slot;
+    int trace_slot;
 };
 
 template <int BN, int STAGES>
@@ -345,6 +354,7 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint32_t STAGE_BYTES = BM * ROW_BYTES + BN * 64;
 
     if (threadIdx.x == 0) {
+        s.trace_slot = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 ? trace_begin(TR_GEMM_Q8) : -1;
         for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.bready[i], 128); mbar_init(&s.empty[i], 1); }
         mbar_init(&s.tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -374,7 +384,7 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s.tmem_slot;
-    if (threadIdx.x == 0) pdl_trigger();
+    if (threadIdx.x == 0) { pdl_trigger(); trace_mark(s.trace_slot, 1); }
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -436,7 +446,7 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to the tensor core
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s.bready[st])) : "memory");
         }
-        tc_epilogue<BN>(p, tmem_base, &s.tmem_full, warp, lane, m0, n0);
+        tc_epilogue<BN>(p, tmem_base, &s.tmem_full, warp, lane, m0, n0, s.trace_slot);
     }
     tc_fence_before();
     __syncthreads();

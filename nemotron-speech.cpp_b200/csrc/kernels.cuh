@@ -4,6 +4,10 @@
 
 namespace nsb {
 
+// device tracing: every translation unit with kernels binds the trace buffer into its constant memory (common.cuh)
+void trace_bind_frontend(TraceBuf*); void trace_bind_layer(TraceBuf*); void trace_bind_simt(TraceBuf*);
+void trace_bind_gemm_tc(TraceBuf*); void trace_bind_decode(TraceBuf*);
+
 // ---------------------------------------------------------------- front-end (kernels_frontend.cu)
 // log-mel of n_frames frames per row. Row b of `pcm` holds [prev_sample, s_0, s_1, ...] of the
 // 256-zero-left-padded stream; frame j covers s[160 j .. 160 j + 512). Output row stride given.

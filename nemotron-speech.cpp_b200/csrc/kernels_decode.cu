@@ -32,6 +32,8 @@
 
 namespace nsb {
 
+NSB_DEFINE_TRACE_BINDER(trace_bind_decode)
+
 namespace {
 constexpr int NT = 256, NW = NT / 32;
 constexpr int RSTR = 40;             // padded stream stride of the partial-tile buffers
@@ -255,6 +257,8 @@ __global__ void __launch_bounds__(NT, 1) rnnt_decode_kernel(const DecodeArgs a) 
     const int tid = threadIdx.x, B = a.B, T = a.T;
     const unsigned nblk = gridDim.x;
     unsigned epoch = 0;
+    int tr_slot = -1;
+    if (trace_thread()) { tr_slot = trace_begin(TR_DECODE); trace_mark(tr_slot, 1); }
     int ne0 = 0;                                                                  // joint evaluations of batch row 0 so far (debug tap)
 
     for (int b = tid; b < B; b += NT) {
@@ -307,6 +311,7 @@ __global__ void __launch_bounds__(NT, 1) rnnt_decode_kernel(const DecodeArgs a) 
             a.out_count[b] = sm.oc[b];
         }
         if (tid == 0 && a.logits_tap_n) *a.logits_tap_n = ne0;
+        if (tid == 0) trace_mark(tr_slot, 2);
     }
 }
 }  // namespace

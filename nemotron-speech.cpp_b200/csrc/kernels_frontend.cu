@@ -9,6 +9,8 @@
 
 namespace nsb {
 
+NSB_DEFINE_TRACE_BINDER(trace_bind_frontend)
+
 // ------------------------------------------------------------------------------------------
 // log-mel: one CTA = one 512-sample frame. Shared-memory radix-2 DIT FFT (9 stages x 256
 // butterflies), power spectrum, 128x257 filterbank, log.
@@ -20,7 +22,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
                                                      const float* __restrict__ window, const float* __restrict__ cos_t,
                                                      const float* __restrict__ sin_t, const float* __restrict__ fb_t,
                                                      float* __restrict__ mel_out, size_t out_batch_stride) {
-    pdl_wait(); pdl_trigger();
+    NSB_KERNEL_PROLOGUE(TR_LOGMEL)
     __shared__ float re[N_FFT], im[N_FFT], pw[N_BINS + 3];
     const int j = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
     const int16_t* row = pcm + (size_t)b * pcm_row_stride + (size_t)j * HOP;   // row[0] = sample before the frame
@@ -59,6 +61,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
         const float v = __fadd_rn(sum, 5.960464477539063e-8f);
         mel_out[(size_t)b * out_batch_stride + (size_t)j * N_MELS + t] = (float)log((double)v);
     }
+    NSB_KERNEL_EPILOGUE();
 }
 
 void launch_logmel(const int16_t* pcm, int pcm_row_stride, int B, int n_frames, const float* window512, const float* cos_t,
@@ -82,7 +85,7 @@ __device__ __forceinline__ float chunk_mel(const float* __restrict__ hist, const
 __global__ void __launch_bounds__(SUB_CH) conv0_kernel(const float* __restrict__ hist, const float* __restrict__ mel_new,
                                                        const int* __restrict__ slot_of_b, int T, const float* __restrict__ w_t,
                                                        const float* __restrict__ bias, float* __restrict__ out) {
-    pdl_wait(); pdl_trigger();
+    NSB_KERNEL_PROLOGUE(TR_OTHER)
     const int ow = blockIdx.x, oh = blockIdx.y, b = blockIdx.z, oc = threadIdx.x;
     const int M = PRE_CACHE + 8 * T, t1 = gridDim.y, W1 = gridDim.x;
     const int slot = slot_of_b[b];
@@ -99,6 +102,7 @@ __global__ void __launch_bounds__(SUB_CH) conv0_kernel(const float* __restrict__
     }
     acc += bias[oc];
     out[(((size_t)b * t1 + oh) * W1 + ow) * SUB_CH + oc] = fmaxf(acc, 0.0f);
+    NSB_KERNEL_EPILOGUE();
 }
 
 void launch_conv0(const float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, const float* w_t,
@@ -116,7 +120,7 @@ __global__ void __launch_bounds__(SUB_CH) stem_conv0_dw_kernel(const float* __re
                                                                const float* __restrict__ b0, const float* __restrict__ w2_t,
                                                                const float* __restrict__ b2, float* __restrict__ out) {
     __shared__ float mel[7][N_MELS];
-    pdl_wait(); pdl_trigger();
+    NSB_KERNEL_PROLOGUE(TR_STEM)
     const int oh2 = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
     const int M = PRE_CACHE + 8 * T, t1 = M / 2 + 1, t2 = gridDim.x;
     constexpr int W1 = N_MELS / 2 + 1, W2 = W1 / 2 + 1;                         // 65, 33
@@ -163,6 +167,7 @@ __global__ void __launch_bounds__(SUB_CH) stem_conv0_dw_kernel(const float* __re
             for (int kw2 = 0; kw2 < 3; ++kw2) acc = fmaf(win[kh2][kw2], w2[kh2 * 3 + kw2], acc);
         out[(((size_t)b * t2 + oh2) * W2 + ow2) * SUB_CH + c] = acc + bias2;
     }
+    NSB_KERNEL_EPILOGUE();
 }
 void launch_stem_conv0_dw(const float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, const float* w0_t,
                           const float* b0, const float* w2_t, const float* b2, float* out, cudaStream_t st) {
@@ -172,13 +177,14 @@ void launch_stem_conv0_dw(const float* mel_hist, const float* mel_new, const int
 
 __global__ void __launch_bounds__(N_MELS) mel_hist_update_kernel(float* __restrict__ hist, const float* __restrict__ mel_new,
                                                                  const int* __restrict__ slot_of_b, int T) {
-    pdl_wait(); pdl_trigger();
+    NSB_KERNEL_PROLOGUE(TR_MELHIST)
     const int b = blockIdx.x, m = threadIdx.x, slot = slot_of_b[b];
     float v[PRE_CACHE];
 #pragma unroll
     for (int f = 0; f < PRE_CACHE; ++f) v[f] = chunk_mel(hist, mel_new, slot, b, T, 8 * T + f, m);   // last 9 of [hist || new]
 #pragma unroll
     for (int f = 0; f < PRE_CACHE; ++f) hist[((size_t)slot * PRE_CACHE + f) * N_MELS + m] = v[f];
+    NSB_KERNEL_EPILOGUE();
 }
 void launch_mel_hist_update(float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, cudaStream_t st) {
     launch_k(mel_hist_update_kernel, dim3(B), dim3(N_MELS), 0, st, mel_hist, mel_new, slot_of_b, T);
@@ -186,9 +192,10 @@ void launch_mel_hist_update(float* mel_hist, const float* mel_new, const int* sl
 
 __global__ void __launch_bounds__(N_MELS) mel_gather_kernel(const float* __restrict__ hist, const float* __restrict__ mel_new,
                                                             const int* __restrict__ slot_of_b, int T, float* __restrict__ out) {
-    pdl_wait(); pdl_trigger();
+    NSB_KERNEL_PROLOGUE(TR_OTHER)
     const int f = blockIdx.x, b = blockIdx.y, m = threadIdx.x, M = PRE_CACHE + 8 * T;
     out[((size_t)b * M + f) * N_MELS + m] = chunk_mel(hist, mel_new, slot_of_b[b], b, T, f, m);
+    NSB_KERNEL_EPILOGUE();
 }
 void launch_mel_gather(const float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, float* out, cudaStream_t st) {
     launch_k(mel_gather_kernel, dim3(PRE_CACHE + 8 * T, B), dim3(N_MELS), 0, st, mel_hist, mel_new, slot_of_b, T, out);
@@ -197,7 +204,7 @@ void launch_mel_gather(const float* mel_hist, const float* mel_new, const int* s
 // depthwise 3x3 stride 2 (+bias, no activation), NHWC with C = 256: thread = channel.
 __global__ void __launch_bounds__(SUB_CH) dwconv_s2_kernel(const float* __restrict__ in, int H, int W, const float* __restrict__ w_t,
                                                            const float* __restrict__ bias, float* __restrict__ out) {
-    pdl_wait(); pdl_trigger();
+    NSB_KERNEL_PROLOGUE(TR_DWCONV)
     const int ow = blockIdx.x, oh = blockIdx.y, b = blockIdx.z, c = threadIdx.x;
     const int Ho = gridDim.y, Wo = gridDim.x;
     float acc = 0.0f;
@@ -213,6 +220,7 @@ __global__ void __launch_bounds__(SUB_CH) dwconv_s2_kernel(const float* __restri
         }
     }
     out[(((size_t)b * Ho + oh) * Wo + ow) * SUB_CH + c] = acc + bias[c];
+    NSB_KERNEL_EPILOGUE();
 }
 void launch_dwconv_s2(const float* in, int B, int H, int W, const float* w_t, const float* bias, float* out, cudaStream_t st) {
     launch_k(dwconv_s2_kernel, dim3(W / 2 + 1, H / 2 + 1, B), dim3(SUB_CH), 0, st, in, H, W, w_t, bias, out);

@@ -13,6 +13,8 @@
 
 namespace nsb {
 
+NSB_DEFINE_TRACE_BINDER(trace_bind_layer)
+
 // ------------------------------------------------------------------------------------------
 // block-wide sum over 256 threads (8 warps)
 // ------------------------------------------------------------------------------------------
@@ -46,7 +48,7 @@ __device__ __forceinline__ float4 load_x_reduced(float* x, size_t o, const Parti
 
 __global__ void __launch_bounds__(256) layernorm_kernel(float* x, const float* __restrict__ g,
                                                         const float* __restrict__ b, void* y, int out_type, const PartialSum ps) {
-    pdl_wait(); pdl_trigger();
+    NSB_KERNEL_PROLOGUE(TR_LN)
     __shared__ float red[8];
     const int row = blockIdx.x, c = threadIdx.x * 4;
     const float4 v = load_x_reduced(x, (size_t)row * D_MODEL + c, ps, gridDim.x);
@@ -60,6 +62,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* x, const float* _
     if (out_type == OUT_F32) *(float4*)((float*)y + o) = make_float4(o0, o1, o2, o3);
     else if (out_type == OUT_F16) { __half2* p = (__half2*)((__half*)y + o); p[0] = __floats2half2_rn(o0, o1); p[1] = __floats2half2_rn(o2, o3); }
     else { __nv_bfloat162* p = (__nv_bfloat162*)((__nv_bfloat16*)y + o); p[0] = __floats2bfloat162_rn(o0, o1); p[1] = __floats2bfloat162_rn(o2, o3); }
+    NSB_KERNEL_EPILOGUE();
 }
 void launch_layernorm(float* x, int rows, const float* g, const float* b, void* y, int out_type, const PartialSum& ps, cudaStream_t st) {
     if (rows > 0) launch_k(layernorm_kernel, dim3(rows), dim3(256), 0, st, x, g, b, y, out_type, ps);
@@ -69,7 +72,7 @@ void launch_layernorm(float* x, int rows, const float* g, const float* b, void* 
 __global__ void __launch_bounds__(256) layernorm2_kernel(float* x, const float* __restrict__ g1, const float* __restrict__ b1,
                                                          const float* __restrict__ g2, const float* __restrict__ b2,
                                                          void* y2, int out_type, const PartialSum ps) {
-    pdl_wait(); pdl_trigger();
+    NSB_KERNEL_PROLOGUE(TR_LN2)
     __shared__ float red[8];
     const int row = blockIdx.x, c = threadIdx.x * 4;
     const size_t o = (size_t)row * D_MODEL + c;
@@ -91,6 +94,7 @@ __global__ void __launch_bounds__(256) layernorm2_kernel(float* x, const float* 
     if (out_type == OUT_F32) *(float4*)((float*)y2 + o) = make_float4(o0, o1, o2, o3);
     else if (out_type == OUT_F16) { __half2* p = (__half2*)((__half*)y2 + o); p[0] = __floats2half2_rn(o0, o1); p[1] = __floats2half2_rn(o2, o3); }
     else { __nv_bfloat162* p = (__nv_bfloat162*)((__nv_bfloat16*)y2 + o); p[0] = __floats2bfloat162_rn(o0, o1); p[1] = __floats2bfloat162_rn(o2, o3); }
+    NSB_KERNEL_EPILOGUE();
 }
 void launch_layernorm2(float* x, int rows, const float* g1, const float* b1, const float* g2, const float* b2, void* y2, int out_type,
                        const PartialSum& ps, cudaStream_t st) {
@@ -153,7 +157,7 @@ __global__ void __launch_bounds__(256, TQ <= 2 ? 4 : 2) attention_kernel(const A
     E* Ks = reinterpret_cast<E*>(att_smem + sizeof(AttnSmemF<TQ>));             // [K][128]
     E* Vs = Ks + (size_t)K * D_HEAD;                                            // [K][128]
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    pdl_wait(); pdl_trigger();
+    NSB_KERNEL_PROLOGUE(TR_ATTN)
     const int slot = a.slot_of_b[b], w = a.ring_pos[slot], valid = a.valid_len[slot];
     const int first = ATT_L - valid;                                           // keys j < first are not yet valid (:982-992)
     const float* qkv = a.qkv + (size_t)b * T * 3 * D_MODEL + h * D_HEAD;
@@ -275,6 +279,7 @@ __global__ void __launch_bounds__(256, TQ <= 2 ? 4 : 2) attention_kernel(const A
         }
         __syncthreads();                                                          // ac / bd / red are reused by the next query tile
     }
+    NSB_KERNEL_EPILOGUE();
 }
 
 template <int KV, int TQ>
@@ -308,7 +313,7 @@ void launch_attention(const AttnArgs& a, cudaStream_t st) {
 // One CTA per batch row (stream), 256 threads x 4 channels, a 9-deep register window slides over time.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv_module_kernel(const ConvModArgs a) {
-    pdl_wait(); pdl_trigger();
+    NSB_KERNEL_PROLOGUE(TR_CONVMOD)
     __shared__ float red[8];
     const int b = blockIdx.x, c0 = threadIdx.x * 4, T = a.T;
     const int slot = a.slot_of_b[b];
@@ -357,18 +362,20 @@ __global__ void __launch_bounds__(256) conv_module_kernel(const ConvModArgs a) {
 #pragma unroll
     for (int k = 0; k < CONV_K - 1; ++k)                                         // new cache = last 8 rows of xp :368-381
         *(float4*)(cache + (size_t)k * D_MODEL + c0) = make_float4(win[0][k], win[1][k], win[2][k], win[3][k]);
+    NSB_KERNEL_EPILOGUE();
 }
 void launch_conv_module(const ConvModArgs& a, cudaStream_t st) {
     if (a.B > 0) launch_k(conv_module_kernel, dim3(a.B), dim3(256), 0, st, a);
 }
 
 __global__ void advance_streams_kernel(const int* __restrict__ slot_of_b, int B, int T, int* ring_pos, int* valid_len) {
-    pdl_wait(); pdl_trigger();
+    NSB_KERNEL_PROLOGUE(TR_ADVANCE)
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int s = slot_of_b[b];
     ring_pos[s] = (ring_pos[s] + T) % (ATT_L + T);
     valid_len[s] = min(valid_len[s] + T, ATT_L);                                 // :1018
+    NSB_KERNEL_EPILOGUE();
 }
 void launch_advance_streams(const int* slot_of_b, int B, int T, int* ring_pos, int* valid_len, cudaStream_t st) {
     if (B > 0) launch_k(advance_streams_kernel, dim3((B + 127) / 128), dim3(128), 0, st, slot_of_b, B, T, ring_pos, valid_len);
