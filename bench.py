@@ -12,8 +12,9 @@ engine with no data-path collective ("weak" scaling); torch.distributed is used 
 max-over-ranks of the timed region.
 
   value : device-resident throughput -- PCM of the step already in HBM, CUDA events around the K steps
-  e2e   : the same K steps through the public C ABI with HOST buffers: nsb_stream_push_pcm (pinned staging +
-          H2D inside), nsb_engine_step, nsb_stream_pop_tokens (D2H of the token ids), wall clock
+  e2e   : the same K steps through the public C ABI with HOST buffers: nsb_push_pcm_batch, nsb_engine_step_begin
+          (pinned staging + H2D + kernels + D2H of the token ids enqueued), the next chunk pushed meanwhile,
+          nsb_engine_step_end, nsb_pop_tokens_batch; wall clock
 
 --impl reference times the CPU oracle port of the reference path (oracle/liboracle.so, all host threads) on a
 bounded sample of the same workload; the reference's own ggml build cannot be produced offline.
@@ -37,6 +38,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 N_LAYERS = int(os.environ.get("NSB_BENCH_LAYERS", 24))
 STREAMS = int(os.environ.get("NSB_BENCH_STREAMS", 64))
 RIGHT_CONTEXT = int(os.environ.get("NSB_BENCH_R", 1))
+PROFILE = os.environ.get("NSB_BENCH_PROFILE", "speech")   # synthetic-model calibration: "speech" = ~4.5 tokens per audio second, "parity" = the tests' dense emission
 WARM_CHUNKS = 40            # > 70/T: the 70-frame attention cache is full (steady state) before timing
 T = 1 + RIGHT_CONTEXT
 CHUNK_S = 0.08 * T
@@ -100,7 +102,7 @@ def cpu_baseline(threads: int | None, seconds: float = 1.6, streams: int = 2):
     if threads:
         O.lib().orc_set_threads(threads)
     cores = threads or O.lib().orc_get_max_threads()
-    path = synth.cached_model("f32", N_LAYERS, R=RIGHT_CONTEXT)
+    path = synth.cached_model("f32", N_LAYERS, R=RIGHT_CONTEXT, profile=PROFILE)
     m = O.Model(path, O.MM_REF)
     pcm = [synth.synth_pcm(s, seconds) for s in range(streams)]
     t0 = time.perf_counter()
@@ -156,10 +158,10 @@ def main():
 
     # synthetic model (f16 GGUF of the 24-layer architecture, cast to bf16 at load) + per-stream synthetic PCM
     if rank == 0 or world == 1:
-        path = synth.cached_model("f16", N_LAYERS, R=RIGHT_CONTEXT)
+        path = synth.cached_model("f16", N_LAYERS, R=RIGHT_CONTEXT, profile=PROFILE)
     if world > 1:
         dist.barrier()
-        path = synth.cached_model("f16", N_LAYERS, R=RIGHT_CONTEXT)
+        path = synth.cached_model("f16", N_LAYERS, R=RIGHT_CONTEXT, profile=PROFILE)
     eng = nsb200.Engine(path, right_context=RIGHT_CONTEXT, max_streams=STREAMS, compute=nsb200.COMPUTE_BF16, kv_dtype=nsb200.KV_BF16, device=local,
                         cuda_graph=os.environ.get("NSB_BENCH_GRAPH", "1") != "0")
     shift = eng.shift_samples
@@ -230,11 +232,12 @@ def main():
     t0 = time.perf_counter()
     ntok = 0
     for i in range(args.steps):
-        assert eng.step() == STREAMS                      # H2D of this step's PCM, all kernels, D2H of the token ids, inside
+        assert eng.step_begin() == STREAMS                # staging + H2D of this step's PCM + all kernels + D2H of the token ids enqueued
+        if i + 1 < args.steps:
+            feed(shift)                                   # the host hands over the NEXT 160 ms of every stream while the device works
+        assert eng.step_end() == STREAMS                  # wait for the step, queue its tokens
         _, cnt = eng.pop_tokens_batch(ids, 32 * T)
         ntok += int(cnt.sum())
-        if i + 1 < args.steps:
-            feed(shift)
     sync_all()
     e2e_wall = time.perf_counter() - t0
     t_e2e = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
@@ -256,7 +259,9 @@ def main():
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"nemotron-speech-streaming-en-0.6b architecture ({N_LAYERS} conformer layers, random-init synthetic weights), "
                                        f"bf16 tcgen05 GEMMs, bf16 K/V ring, {STREAMS} concurrent streams per GPU, 160 ms chunks (att_right_context={RIGHT_CONTEXT}), "
-                                       f"steady state after {WARM_CHUNKS} warm chunks",
+                                       f"steady state after {WARM_CHUNKS} warm chunks; joint blank bias calibrated to a speech-like token rate "
+                                       f"({e2e['tokens_per_audio_s']:.1f} tokens per audio second measured in the e2e leg)" if PROFILE == "speech" else
+                                       f"nemotron-speech-streaming-en-0.6b architecture ({N_LAYERS} layers, synthetic weights, parity-test calibration = dense emission), {STREAMS} streams, R={RIGHT_CONTEXT}",
                            "streams_per_gpu": STREAMS, "chunk_ms": int(CHUNK_S * 1000), "l2_policy": "per-step working set (weights 1.16 GB + K/V ring 0.45 GB) > 126 MB L2"},
                 "p50_chunk_latency_ms": lat_sorted[len(lat) // 2], "p99_chunk_latency_ms": lat_sorted[min(len(lat) - 1, int(0.99 * len(lat)))],
                 "wall_ms_per_step": 1e3 * wall_s / args.steps,

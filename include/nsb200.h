@@ -101,6 +101,12 @@ int nsb_push_pcm_batch(nsb_engine* e, int n_streams, const int32_t* streams, con
 int nsb_pop_tokens_batch(nsb_engine* e, int n_streams, const int32_t* streams, int32_t* out, int cap_per_stream, int32_t* counts);
 int nsb_stream_ready(const nsb_engine* e, int stream); /* 1 if a full chunk is buffered */
 int nsb_engine_step(nsb_engine* e);                    /* returns #streams advanced (0 = nothing ready), <0 error */
+/* step() split in two so that the host can feed the NEXT chunk while the device works on this one: begin stages the ready
+ * streams, enqueues the H2D copy, the step and the D2H copy of the token ids and returns; end waits for them and queues the
+ * tokens. At most one step in flight; push_pcm / pop_tokens are allowed in between, stream open / close / reset collect first.
+ * nsb_stream_ready() and nsb_stream_chunks() keep describing the state BEFORE the step in flight until end() returns. */
+int nsb_engine_step_begin(nsb_engine* e);              /* returns #streams in the launched step (0 = nothing ready), <0 error */
+int nsb_engine_step_end(nsb_engine* e);                /* returns #streams advanced (0 = no step in flight), <0 error */
 int nsb_engine_drain(nsb_engine* e);                   /* step until nothing is ready; returns total stream-chunks */
 int nsb_stream_pop_tokens(nsb_engine* e, int stream, int32_t* out, int cap); /* returns n copied (FIFO) */
 int nsb_stream_chunks(const nsb_engine* e, int stream);                      /* nemo_stream_context::total_chunks_processed */

@@ -48,7 +48,7 @@ class ModelInfo(C.Structure):
 
 EXPORTS = ["nsb_gguf_probe", "nsb_default_config", "nsb_engine_create", "nsb_engine_destroy", "nsb_last_error", "nsb_engine_n_layers",
            "nsb_engine_vocab_size", "nsb_engine_vocab", "nsb_engine_chunk_samples", "nsb_engine_shift_samples", "nsb_engine_compute",
-           "nsb_stream_open", "nsb_stream_close", "nsb_stream_reset", "nsb_stream_push_pcm", "nsb_push_pcm_batch", "nsb_pop_tokens_batch", "nsb_stream_ready", "nsb_engine_step",
+           "nsb_stream_open", "nsb_stream_close", "nsb_stream_reset", "nsb_stream_push_pcm", "nsb_push_pcm_batch", "nsb_pop_tokens_batch", "nsb_stream_ready", "nsb_engine_step", "nsb_engine_step_begin", "nsb_engine_step_end",
            "nsb_engine_drain", "nsb_stream_pop_tokens", "nsb_stream_chunks", "nsb_detokenize", "nsb_engine_get_stats",
            "nsb_bench_prepare", "nsb_bench_step", "nsb_bench_profile", "nsb_profiler_range", "nsb_bench_gemm", "nsb_trace_enable", "nsb_trace_fetch", "nsb_debug_enable", "nsb_debug_get", "nsb_debug_get_cache", "nsb_op_logmel",
            "nsb_op_gemm"]
@@ -80,7 +80,7 @@ def lib():
         L.nsb_engine_create.argtypes = [C.c_char_p, C.POINTER(EngineConfig), C.POINTER(vp)]
         L.nsb_engine_destroy.argtypes = [vp]
         for n in ("nsb_engine_n_layers", "nsb_engine_vocab_size", "nsb_engine_chunk_samples", "nsb_engine_shift_samples",
-                  "nsb_engine_compute", "nsb_stream_open", "nsb_engine_step", "nsb_engine_drain"):
+                  "nsb_engine_compute", "nsb_stream_open", "nsb_engine_step", "nsb_engine_step_begin", "nsb_engine_step_end", "nsb_engine_drain"):
             getattr(L, n).argtypes = [vp]
         L.nsb_engine_vocab.argtypes = [vp]
         L.nsb_engine_vocab.restype = vp
@@ -183,6 +183,12 @@ class Engine:
 
     def step(self) -> int:
         return _check(lib().nsb_engine_step(self.h))
+
+    def step_begin(self) -> int:
+        return _check(lib().nsb_engine_step_begin(self.h))
+
+    def step_end(self) -> int:
+        return _check(lib().nsb_engine_step_end(self.h))
 
     def drain(self) -> int:
         return _check(lib().nsb_engine_drain(self.h))

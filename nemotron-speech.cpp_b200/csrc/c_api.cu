@@ -95,6 +95,8 @@ int nsb_pop_tokens_batch(nsb_engine* e, int n_streams, const int32_t* streams, i
     return total; NSB_CATCH }
 int nsb_stream_ready(const nsb_engine* e, int s) { if (!e || s < 0 || s >= e->impl->max_streams) return NSB_ERR_ARG; return e->impl->ready(s) ? 1 : 0; }
 int nsb_engine_step(nsb_engine* e) { if (!e) return fail(NSB_ERR_ARG, "null engine"); NSB_TRY return e->impl->step(); NSB_CATCH }
+int nsb_engine_step_begin(nsb_engine* e) { if (!e) return fail(NSB_ERR_ARG, "null engine"); NSB_TRY return e->impl->step_begin(); NSB_CATCH }
+int nsb_engine_step_end(nsb_engine* e) { if (!e) return fail(NSB_ERR_ARG, "null engine"); NSB_TRY return e->impl->step_end(); NSB_CATCH }
 int nsb_engine_drain(nsb_engine* e) {
     if (!e) return fail(NSB_ERR_ARG, "null engine");
     NSB_TRY int total = 0; for (;;) { int n = e->impl->step(); if (n <= 0) break; total += n; } return total; NSB_CATCH }

@@ -94,12 +94,23 @@ __device__ __forceinline__ int trace_begin(int tag) {
     return (int)s;
 }
 __device__ __forceinline__ void trace_mark(int slot, int i) { if (slot >= 0) c_trace->rec[slot].t[i] = gtime(); }
-// the common prologue of a simple kernel: trace start, wait for the previous grid, let the next one launch
-#define NSB_KERNEL_PROLOGUE(tag)                                   \
+// The common prologue of a simple kernel, in two halves:
+//   NSB_KERNEL_BEGIN  trace start
+//   ... input-independent loads of this kernel go here (weights, K/V ring rows, conv state): they overlap the predecessor
+//       whenever this grid was launched early ...
+//   NSB_KERNEL_WAIT   griddepcontrol.wait (predecessor COMPLETE and flushed, hence transitively everything before it), then
+//                     launch_dependents. Measured (profiles/r01_notes.md): triggering at kernel ENTRY instead lets the whole
+//                     layer pile up on the SMs ~15 us ahead, which bought nothing and lengthened the completion -> release
+//                     gaps (19 -> 25 us per layer); triggering after the wait keeps the launch front one or two kernels ahead,
+//                     enough to hide the ~2 us launch latency behind this kernel's body. The GEMMs trigger right after their
+//                     prologue (they have real pre-wait work to overlap: the weight-slab prefetch).
+#define NSB_KERNEL_BEGIN(tag)                                      \
     int tr_slot = -1;                                              \
-    if (trace_thread()) tr_slot = trace_begin(tag);                \
+    if (trace_thread()) tr_slot = trace_begin(tag);
+#define NSB_KERNEL_WAIT()                                          \
     pdl_wait(); pdl_trigger();                                     \
     if (tr_slot >= 0) trace_mark(tr_slot, 1);
+#define NSB_KERNEL_PROLOGUE(tag) NSB_KERNEL_BEGIN(tag) NSB_KERNEL_WAIT()
 #define NSB_KERNEL_EPILOGUE() do { if (tr_slot >= 0) trace_mark(tr_slot, 2); } while (0)
 
 // Epilogues shared by the SIMT and the tcgen05 GEMM

@@ -194,6 +194,14 @@ void Engine::load_weights(const GgufFile& g) {
         memcpy(w512.data() + (N_FFT - WIN) / 2, win.data(), WIN * sizeof(float));
         for (int i = 0; i < N_FFT; ++i) { const float th = (2.0f * (float)M_PI * i) / N_FFT; s[i] = sinf(th); c[i] = cosf(th); }
         for (int m = 0; m < N_MELS; ++m) for (int k = 0; k < N_BINS; ++k) fbt[(size_t)k * N_MELS + m] = fb[(size_t)m * N_BINS + k];
+        // [257][128] transposed weights, then per mel bin the span [lo, hi) of its non-zero weights (2 x 128 ints)
+        fbt.resize((size_t)N_BINS * N_MELS + 2 * N_MELS);
+        for (int m = 0; m < N_MELS; ++m) {
+            int lo = N_BINS, hi = 0;
+            for (int k = 0; k < N_BINS; ++k) if (fb[(size_t)m * N_BINS + k] != 0.0f) { lo = std::min(lo, k); hi = k + 1; }
+            if (hi == 0) lo = 0;
+            memcpy(&fbt[(size_t)N_BINS * N_MELS + m], &lo, 4); memcpy(&fbt[(size_t)N_BINS * N_MELS + N_MELS + m], &hi, 4);
+        }
         upload(window_, w512); upload(cos_t_, c); upload(sin_t_, s); upload(fb_t_, fbt);
     }
     // ---- subsampling stem: always f32 (never quantised by the converter, convert_to_gguf.py:226) ----
@@ -327,8 +335,15 @@ void Engine::build_pos_tables(const GgufFile& g) {
     for (int l = 0; l < n_layers; ++l) {
         const std::string n = "encoder.layers." + std::to_string(l) + ".self_attn.linear_pos.weight";
         Weight wpos; load_layer_matrix(wpos, g, n, {n}, D_MODEL, D_MODEL);
-        layers_[l].pos_proj.alloc((size_t)n_rel * D_MODEL * 4, false);
-        gemm(A, D_MODEL, wpos, n_rel, nullptr, layers_[l].pos_proj.p, D_MODEL, EPI_NONE, 1.f, OUT_F32);
+        // kept in the K/V ring dtype: the attention kernel stages this head's rows in shared memory next to K and V
+        layers_[l].pos_proj.alloc((size_t)n_rel * D_MODEL * kv_elem_size(kv_dtype), false);
+        if (kv_dtype == 0) gemm(A, D_MODEL, wpos, n_rel, nullptr, layers_[l].pos_proj.p, D_MODEL, EPI_NONE, 1.f, OUT_F32);
+        else {
+            DevBuf tmp; tmp.alloc((size_t)n_rel * D_MODEL * 4, false);
+            gemm(A, D_MODEL, wpos, n_rel, nullptr, tmp.p, D_MODEL, EPI_NONE, 1.f, OUT_F32);
+            convert_to(tmp.as<float>(), layers_[l].pos_proj.p, (size_t)n_rel * D_MODEL, kv_dtype == 1 ? OUT_F16 : OUT_BF16, st_);
+            NSB_CUDA(cudaStreamSynchronize(st_));
+        }
         NSB_CUDA(cudaStreamSynchronize(st_));
     }
 }
@@ -364,12 +379,13 @@ void Engine::gemm_residual(const void* A, long long lda, const Weight& W, int M,
 // streams (host bookkeeping only; all arithmetic is on the device)
 // ------------------------------------------------------------------------------------------
 int Engine::open_stream() {
+    if (!inflight_.empty()) step_end();
     for (int s = 0; s < max_streams; ++s)
         if (!hs_[s].open) { zero_slot(s); hs_[s].open = true; return s; }
     throw std::runtime_error("no free stream slot (max_streams = " + std::to_string(max_streams) + ")");
 }
-void Engine::close_stream(int s) { if (s < 0 || s >= max_streams || !hs_[s].open) throw std::invalid_argument("bad stream id"); hs_[s].open = false; }
-void Engine::reset_stream(int s) { if (s < 0 || s >= max_streams || !hs_[s].open) throw std::invalid_argument("bad stream id"); zero_slot(s); }
+void Engine::close_stream(int s) { if (!inflight_.empty()) step_end(); if (s < 0 || s >= max_streams || !hs_[s].open) throw std::invalid_argument("bad stream id"); hs_[s].open = false; }
+void Engine::reset_stream(int s) { if (!inflight_.empty()) step_end(); if (s < 0 || s >= max_streams || !hs_[s].open) throw std::invalid_argument("bad stream id"); zero_slot(s); }
 
 void Engine::push_pcm(int s, const int16_t* pcm, int n) {
     if (s < 0 || s >= max_streams || !hs_[s].open) throw std::invalid_argument("bad stream id");
@@ -394,7 +410,8 @@ static void stage_row(const HostStream& h, int T, int rl, int16_t* dst) {
     if (zeros < rl) memcpy(dst + zeros, h.buf.data() + (size_t)(start + zeros - h.base), (size_t)(rl - zeros) * sizeof(int16_t));
 }
 
-int Engine::step() {
+int Engine::step_begin() {
+    if (!inflight_.empty()) throw std::runtime_error("step_begin: the previous step has not been collected (call step_end)");
     NSB_CUDA(cudaSetDevice(device_));
     std::vector<int> batch;
     for (int s = 0; s < max_streams; ++s) if (ready(s)) batch.push_back(s);
@@ -409,10 +426,26 @@ int Engine::step() {
     NSB_CUDA(cudaEventRecord(ev1_, st_));
     NSB_CUDA(cudaMemcpyAsync(h_cnt_.p, out_cnt_.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st_));
     NSB_CUDA(cudaMemcpyAsync(h_tok_.p, out_tok_.p, (size_t)B * MAX_SYMBOLS * T * 4, cudaMemcpyDeviceToHost, st_));
+    inflight_ = std::move(batch);
+    return B;
+}
+
+int Engine::step_end() {
+    if (inflight_.empty()) return 0;
+    NSB_CUDA(cudaSetDevice(device_));
+    const int B = (int)inflight_.size();
+    std::vector<int> batch = std::move(inflight_);
+    inflight_.clear();
     NSB_CUDA(cudaStreamSynchronize(st_));
     float ms = 0.f; NSB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
     stats.steps += 1; stats.chunks += B; stats.device_ms += ms; stats.last_step_ms = ms;
     collect_tokens(B, batch);
+    return B;
+}
+
+int Engine::step() {
+    const int B = step_begin();
+    if (B) step_end();
     return B;
 }
 
@@ -557,7 +590,7 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
             const size_t es = kv_elem_size(kv_dtype);
             aa.k_ring = (char*)kv_.p + (size_t)l * 2 * (ATT_L + T) * D_MODEL * es;
             aa.v_ring = (char*)aa.k_ring + (size_t)(ATT_L + T) * D_MODEL * es;
-            aa.slot_stride = kv_slot_stride; aa.kv_dtype = kv_dtype; aa.pos_proj = L.pos_proj.as<float>();
+            aa.slot_stride = kv_slot_stride; aa.kv_dtype = kv_dtype; aa.pos_proj = L.pos_proj.p;
             aa.bias_u = L.bias_u.as<float>(); aa.bias_v = L.bias_v.as<float>(); aa.ctx = a_.p; aa.out_type = at;
             aa.slot_of_b = slot; aa.ring_pos = ring_pos_.as<int>(); aa.valid_len = valid_len_.as<int>(); aa.B = B; aa.T = T;
             ProfScope ps(this, PC_ATTENTION); launch_attention(aa, st_); count_launch();
@@ -640,6 +673,7 @@ void Engine::bench_prepare(int n_streams, const int16_t* pcm, int samples_per_st
 
 float Engine::bench_step() {
     if (!bench_B_) throw std::runtime_error("bench_step before bench_prepare");
+    if (!inflight_.empty()) step_end();
     NSB_CUDA(cudaSetDevice(device_));
     NSB_CUDA(cudaEventRecord(ev0_, st_));
     run_step(bench_B_, bench_pcm_.as<int16_t>());

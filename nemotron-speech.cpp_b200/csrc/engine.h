@@ -46,7 +46,7 @@ struct LayerW {
     DevBuf ln[10];          // ff1 g,b | attn g,b | conv g,b | ff2 g,b | out g,b
     Weight ff1a, ff1b, qkv, out, pw1, pw2, ff2a, ff2b;
     DevBuf bias_u, bias_v, dw_w, cln_g, cln_b;
-    DevBuf pos_proj;        // [L+2T-1][1024] f32
+    DevBuf pos_proj;        // [L+2T-1][1024] in the K/V ring dtype
 };
 
 struct HostStream {
@@ -65,6 +65,10 @@ public:
     void push_pcm(int s, const int16_t* pcm, int n);
     bool ready(int s) const;
     int step();                       // returns #streams advanced
+    // split form of step(): begin stages the ready streams' PCM, enqueues H2D + the step graph + D2H and returns at once
+    // (the host can push the next chunk meanwhile); end waits and hands the tokens to the per-stream queues.
+    int step_begin();                 // returns #streams in the launched step (0 = nothing ready)
+    int step_end();                   // returns #streams advanced (0 = no step in flight)
     int pop_tokens(int s, int32_t* out, int cap);
     int chunks(int s) const;
     std::string detok(const int32_t* t, int n) const;
@@ -146,6 +150,7 @@ private:
     DevBuf d_pcm_, d_slot_, mel_new_, dw_, pw_, x_, a_, big_, qkv_, pw1_, encp_, part_;
     DevBuf out_tok_, out_cnt_, dec_sync_;
     HostPinned h_pcm_, h_slot_, h_tok_, h_cnt_;
+    std::vector<int> inflight_;       // batch -> stream slot of the step launched by step_begin()
 
     // ---- bench ----
     DevBuf bench_pcm_; int bench_B_ = 0;

@@ -59,6 +59,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// L2 prefetch of one tensor-map box (no shared-memory destination, no barrier): used before the dependency wait to start
+// HBM -> L2 streaming of the part of the weight slab that does not fit the shared-memory ring yet
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
+}
 // ---- thread-block clusters: A-tile multicast (every CTA of a cluster row needs the same activation tile) ----
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -274,6 +279,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_expect_tx(&s.full[kb], STAGE_BYTES);
                 tma_load_2d(s.b[kb], &tmB, &s.full[kb], (kb0 + (kb + rot) % nk) * BK, n0);
             }
+            for (int kb = pre; kb < nk; ++kb) tma_prefetch_2d(&tmB, (kb0 + (kb + rot) % nk) * BK, n0);   // rest of the slab: HBM -> L2 now
             pdl_wait();
             for (int kb = 0; kb < pre; ++kb) load_a(kb, (kb0 + (kb + rot) % nk) * BK);
             for (int kb = pre; kb < nk; ++kb) {
@@ -394,6 +400,7 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_expect_tx(&s.full[kb], STAGE_BYTES);
                 tma_load_2d(s.q[kb], &tmQ, &s.full[kb], (kb0 + (kb + rot) % nk) * BK, n0);
             }
+            for (int kb = pre; kb < nk; ++kb) tma_prefetch_2d(&tmQ, (kb0 + (kb + rot) % nk) * BK, n0);
             pdl_wait();
             for (int kb = 0; kb < pre; ++kb) tma_load_2d(s.a[kb], &tmA, &s.full[kb], (kb0 + (kb + rot) % nk) * BK, m0);
             for (int kb = pre; kb < nk; ++kb) {

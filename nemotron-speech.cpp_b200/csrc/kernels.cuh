@@ -65,7 +65,7 @@ struct AttnArgs {
     void* k_ring; void* v_ring;   // layer base; element (slot, r, c) at slot*slot_stride + r*1024 + c
     long long slot_stride;        // elements
     int kv_dtype;                 // 0 f32, 1 f16, 2 bf16
-    const float* pos_proj;        // [L + 2T - 1][1024], row = rel + (T-1)
+    const void* pos_proj;         // [L + 2T - 1][1024] in the K/V ring dtype, row = rel + (T-1)
     const float* bias_u; const float* bias_v;   // [1024]
     void* ctx; int out_type;      // [M][1024]
     const int* slot_of_b; const int* ring_pos; const int* valid_len;

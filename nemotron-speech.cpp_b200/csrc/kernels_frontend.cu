@@ -55,9 +55,14 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     }
     __syncthreads();
     if (t < N_MELS) {                                                                    // :374-383
+        // the filterbank rows are (nearly) banded: [lo, hi) = span of the non-zero weights of mel bin t, found at load time.
+        // Terms outside add +/-0 to a non-negative partial sum, so skipping them is bit-exact -- and takes the 131 KB table
+        // read per CTA down to the few KB that matter.
+        const int* rng = reinterpret_cast<const int*>(fb_t + N_BINS * N_MELS);
+        const int lo = rng[t], hi = rng[N_MELS + t];
         float sum = 0.0f;
 #pragma unroll 4
-        for (int k = 0; k < N_BINS; ++k) sum = __fadd_rn(sum, __fmul_rn(fb_t[k * N_MELS + t], pw[k]));
+        for (int k = lo; k < hi; ++k) sum = __fadd_rn(sum, __fmul_rn(fb_t[k * N_MELS + t], pw[k]));
         const float v = __fadd_rn(sum, 5.960464477539063e-8f);
         mel_out[(size_t)b * out_batch_stride + (size_t)j * N_MELS + t] = (float)log((double)v);
     }

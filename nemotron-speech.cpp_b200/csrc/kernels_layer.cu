@@ -35,11 +35,12 @@ __device__ __forceinline__ float block_sum_256(float v, float* red /*[8]*/) {
 __device__ __forceinline__ float4 load_x_reduced(float* x, size_t o, const PartialSum& ps, int rows) {
     float4 v = *(const float4*)(x + o);
     if (ps.n > 0) {                                                              // fold the split-K partials of the previous GEMM
+        float4 t[8];                                                             // all loads in flight at once; summed in slice order
+#pragma unroll
+        for (int s = 0; s < 8; ++s) if (s < ps.n) t[s] = __ldcg((const float4*)(ps.part + (size_t)s * rows * D_MODEL + o));
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = 0; s < ps.n; ++s) {
-            const float4 t = *(const float4*)(ps.part + (size_t)s * rows * D_MODEL + o);
-            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-        }
+#pragma unroll
+        for (int s = 0; s < 8; ++s) if (s < ps.n) { acc.x += t[s].x; acc.y += t[s].y; acc.z += t[s].z; acc.w += t[s].w; }
         v.x += ps.alpha * acc.x; v.y += ps.alpha * acc.y; v.z += ps.alpha * acc.z; v.w += ps.alpha * acc.w;
         *(float4*)(x + o) = v;
     }
@@ -48,15 +49,16 @@ __device__ __forceinline__ float4 load_x_reduced(float* x, size_t o, const Parti
 
 __global__ void __launch_bounds__(256) layernorm_kernel(float* x, const float* __restrict__ g,
                                                         const float* __restrict__ b, void* y, int out_type, const PartialSum ps) {
-    NSB_KERNEL_PROLOGUE(TR_LN)
+    NSB_KERNEL_BEGIN(TR_LN)
     __shared__ float red[8];
     const int row = blockIdx.x, c = threadIdx.x * 4;
+    const float4 gg = *(const float4*)(g + c), bb = *(const float4*)(b + c);    // static: before the dependency wait
+    NSB_KERNEL_WAIT()
     const float4 v = load_x_reduced(x, (size_t)row * D_MODEL + c, ps, gridDim.x);
     const float mean = block_sum_256(v.x + v.y + v.z + v.w, red) * (1.0f / D_MODEL);
     const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
     const float var = block_sum_256(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3, red) * (1.0f / D_MODEL);
     const float rs = 1.0f / sqrtf(var + 1e-5f);
-    const float4 gg = *(const float4*)(g + c), bb = *(const float4*)(b + c);
     const size_t o = (size_t)row * D_MODEL + c;
     const float o0 = d0 * rs * gg.x + bb.x, o1 = d1 * rs * gg.y + bb.y, o2 = d2 * rs * gg.z + bb.z, o3 = d3 * rs * gg.w + bb.w;
     if (out_type == OUT_F32) *(float4*)((float*)y + o) = make_float4(o0, o1, o2, o3);
@@ -72,24 +74,27 @@ void launch_layernorm(float* x, int rows, const float* g, const float* b, void* 
 __global__ void __launch_bounds__(256) layernorm2_kernel(float* x, const float* __restrict__ g1, const float* __restrict__ b1,
                                                          const float* __restrict__ g2, const float* __restrict__ b2,
                                                          void* y2, int out_type, const PartialSum ps) {
-    NSB_KERNEL_PROLOGUE(TR_LN2)
+    NSB_KERNEL_BEGIN(TR_LN2)
     __shared__ float red[8];
     const int row = blockIdx.x, c = threadIdx.x * 4;
     const size_t o = (size_t)row * D_MODEL + c;
+    float4 gg = *(const float4*)(g1 + c), bb = *(const float4*)(b1 + c);       // static: before the dependency wait
+    float4 gg2 = make_float4(0.f, 0.f, 0.f, 0.f), bb2 = gg2;
+    if (y2 != nullptr) { gg2 = *(const float4*)(g2 + c); bb2 = *(const float4*)(b2 + c); }
+    NSB_KERNEL_WAIT()
     float4 v = load_x_reduced(x, o, ps, gridDim.x);
     float mean = block_sum_256(v.x + v.y + v.z + v.w, red) * (1.0f / D_MODEL);
     float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
     float var = block_sum_256(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3, red) * (1.0f / D_MODEL);
     float rs = 1.0f / sqrtf(var + 1e-5f);
-    float4 gg = *(const float4*)(g1 + c), bb = *(const float4*)(b1 + c);
     v = make_float4(d0 * rs * gg.x + bb.x, d1 * rs * gg.y + bb.y, d2 * rs * gg.z + bb.z, d3 * rs * gg.w + bb.w);
     *(float4*)(x + o) = v;
-    if (y2 == nullptr) return;                                                   // last layer: no following norm (uniform branch)
+    if (y2 == nullptr) { NSB_KERNEL_EPILOGUE(); return; }                        // last layer: no following norm (uniform branch)
     mean = block_sum_256(v.x + v.y + v.z + v.w, red) * (1.0f / D_MODEL);
     d0 = v.x - mean; d1 = v.y - mean; d2 = v.z - mean; d3 = v.w - mean;
     var = block_sum_256(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3, red) * (1.0f / D_MODEL);
     rs = 1.0f / sqrtf(var + 1e-5f);
-    gg = *(const float4*)(g2 + c); bb = *(const float4*)(b2 + c);
+    gg = gg2; bb = bb2;
     const float o0 = d0 * rs * gg.x + bb.x, o1 = d1 * rs * gg.y + bb.y, o2 = d2 * rs * gg.z + bb.z, o3 = d3 * rs * gg.w + bb.w;
     if (out_type == OUT_F32) *(float4*)((float*)y2 + o) = make_float4(o0, o1, o2, o3);
     else if (out_type == OUT_F16) { __half2* p = (__half2*)((__half*)y2 + o); p[0] = __floats2half2_rn(o0, o1); p[1] = __floats2half2_rn(o2, o3); }
@@ -157,13 +162,15 @@ __global__ void __launch_bounds__(256, TQ <= 2 ? 4 : 2) attention_kernel(const A
     E* Ks = reinterpret_cast<E*>(att_smem + sizeof(AttnSmemF<TQ>));             // [K][128]
     E* Vs = Ks + (size_t)K * D_HEAD;                                            // [K][128]
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    NSB_KERNEL_PROLOGUE(TR_ATTN)
+    // Before the dependency wait: everything that does not depend on this step's QKV projection -- the cached K / V rows
+    // (written by this layer's attention kernel of EARLIER steps only), ring bookkeeping, the positional biases.
+    NSB_KERNEL_BEGIN(TR_ATTN)
     const int slot = a.slot_of_b[b], w = a.ring_pos[slot], valid = a.valid_len[slot];
     const int first = ATT_L - valid;                                           // keys j < first are not yet valid (:982-992)
     const float* qkv = a.qkv + (size_t)b * T * 3 * D_MODEL + h * D_HEAD;
     E* kring = reinterpret_cast<E*>(a.k_ring) + (size_t)slot * a.slot_stride + h * D_HEAD;
     E* vring = reinterpret_cast<E*>(a.v_ring) + (size_t)slot * a.slot_stride + h * D_HEAD;
-    const float* P = a.pos_proj + h * D_HEAD;
+    const E* P = reinterpret_cast<const E*>(a.pos_proj) + h * D_HEAD;           // L2-resident (146 KB per layer in 16-bit modes)
     auto ring_row = [&](int j) { return (size_t)((w + Cap - ATT_L + j) % Cap) * D_MODEL; };
 
     // ---- one burst: valid cached K / V rows -> shared memory ----
@@ -173,7 +180,11 @@ __global__ void __launch_bounds__(256, TQ <= 2 ? 4 : 2) attention_kernel(const A
         cp_async16(Ks + (size_t)j * D_HEAD + c, kring + g);
         cp_async16(Vs + (size_t)j * D_HEAD + c, vring + g);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    const float scale = 0.08838834764831845f;                                   // 1/sqrt(128) :517
+    const int c4 = lane * 4;
+    float bu[4], bv[4];
+    load4(a.bias_u + h * D_HEAD + c4, bu); load4(a.bias_v + h * D_HEAD + c4, bv);
+    NSB_KERNEL_WAIT()
     // ---- this chunk's K / V rows (rounded to the ring dtype): shared memory AND ring append ----
     for (int e = tid; e < T * (D_HEAD / 4); e += 256) {
         const int i = e / (D_HEAD / 4), c = (e % (D_HEAD / 4)) * 4;
@@ -187,10 +198,6 @@ __global__ void __launch_bounds__(256, TQ <= 2 ? 4 : 2) attention_kernel(const A
         for (int u = 0; u < 4; ++u) { kd[u] = k4[u]; vd[u] = v4[u]; ks[u] = k4[u]; vs[u] = v4[u]; }
     }
 
-    const float scale = 0.08838834764831845f;                                   // 1/sqrt(128) :517
-    const int c4 = lane * 4;
-    float bu[4], bv[4];
-    load4(a.bias_u + h * D_HEAD + c4, bu); load4(a.bias_v + h * D_HEAD + c4, bv);
     for (int q0 = 0; q0 < T; q0 += TQ) {
         const int nq = min(TQ, T - q0);
         float qu[TQ][4], qv[TQ][4];
@@ -201,7 +208,7 @@ __global__ void __launch_bounds__(256, TQ <= 2 ? 4 : 2) attention_kernel(const A
 #pragma unroll
             for (int u = 0; u < 4; ++u) { qu[i][u] = q[u] + bu[u]; qv[i][u] = q[u] + bv[u]; }   // :503-507
         }
-        // ---- BD_raw[i][r] = (q_i + v) . P[r], r = rel + (T-1), from L2; overlaps the K / V burst of the first tile ----
+        // ---- BD_raw[i][r] = (q_i + v) . P[r], r = rel + (T-1), from L2 (ATT_PROWS rows per warp in flight) ----
         const int r_end = ATT_L + T - 1 + (q0 + nq - 1) - first + 1;            // largest row index used + 1
         for (int rb = 0; rb < r_end; rb += 8 * ATT_PROWS) {
             float pf[ATT_PROWS][4];
@@ -223,6 +230,7 @@ __global__ void __launch_bounds__(256, TQ <= 2 ? 4 : 2) attention_kernel(const A
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                                                          // K / V tiles, new rows and BD visible to all warps
+        if (tr_slot >= 0 && q0 == 0) trace_mark(tr_slot, 3);                      // trace: BD + K/V landed
         // ---- AC[i][j] = (q_i + u) . k_j : one key row per warp step out of shared memory ----
         for (int j = first + warp; j < K; j += 8) {
             float kf[4];
@@ -252,6 +260,7 @@ __global__ void __launch_bounds__(256, TQ <= 2 ? 4 : 2) attention_kernel(const A
             for (int j = first + lane; j < K; j += 32) sf.ac[i][j] *= inv;
         }
         __syncthreads();
+        if (tr_slot >= 0 && q0 == 0) trace_mark(tr_slot, 4);                      // trace: AC + softmax done
         // ---- ctx[i][d] = sum_j p[i][j] v_j[d]; thread = (key group kg, 2 dims) ----
         {
             const int d2 = (tid & 63) * 2, kg = tid >> 6;
@@ -313,7 +322,7 @@ void launch_attention(const AttnArgs& a, cudaStream_t st) {
 // One CTA per batch row (stream), 256 threads x 4 channels, a 9-deep register window slides over time.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv_module_kernel(const ConvModArgs a) {
-    NSB_KERNEL_PROLOGUE(TR_CONVMOD)
+    NSB_KERNEL_BEGIN(TR_CONVMOD)                                                  // taps, conv state (written by this layer's kernel of earlier steps only), LN affine: pre-wait
     __shared__ float red[8];
     const int b = blockIdx.x, c0 = threadIdx.x * 4, T = a.T;
     const int slot = a.slot_of_b[b];
@@ -332,6 +341,7 @@ __global__ void __launch_bounds__(256) conv_module_kernel(const ConvModArgs a) {
     }
     const float4 g4 = *(const float4*)(a.ln_g + c0), b4 = *(const float4*)(a.ln_b + c0);
     const float lg[4] = {g4.x, g4.y, g4.z, g4.w}, lb[4] = {b4.x, b4.y, b4.z, b4.w};
+    NSB_KERNEL_WAIT()
     for (int t = 0; t < T; ++t) {
         const float* row = a.pw1 + ((size_t)b * T + t) * 2 * D_MODEL;
         const float4 av = *(const float4*)(row + c0), gv = *(const float4*)(row + D_MODEL + c0);

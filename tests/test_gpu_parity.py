@@ -341,3 +341,42 @@ def test_batch_push_pop_equals_per_stream_calls(built):
     with pytest.raises(nsb200.NsbError):
         b.push_batch([0, 99], audio[:2])                                 # bad stream id in the batch
     a.close(); b.close()
+
+
+@pytest.mark.gpu
+def test_split_step_overlapping_the_next_push_equals_plain_step(built):
+    """nsb_engine_step_begin / _end with the next chunk pushed while the step is in flight == nsb_engine_step."""
+    import nsb200
+    R = 1
+    path = synth.cached_model("f32", 2, R=R)
+    audio = np.stack([synth.synth_pcm(140 + s, 1.3) for s in range(5)])
+    a = nsb200.Engine(path, right_context=R, max_streams=5, compute=nsb200.COMPUTE_F32)
+    ids = [a.open_stream() for _ in range(5)]
+    for s in range(5):
+        a.push(ids[s], audio[s])
+    a.drain()
+    ref = [a.pop_tokens(i) for i in ids]
+    b = nsb200.Engine(path, right_context=R, max_streams=5, compute=nsb200.COMPUTE_F32)
+    ids2 = [b.open_stream() for _ in range(5)]
+    step = b.shift_samples
+    assert b.step_end() == 0                                             # nothing in flight
+    b.push_batch(ids2, audio[:, :step])
+    pos = step
+    got = [[] for _ in range(5)]
+    while True:
+        n = b.step_begin()
+        if pos < audio.shape[1]:
+            b.push_batch(ids2, audio[:, pos:pos + step]); pos += step    # overlaps the step in flight
+        if n:
+            with pytest.raises(nsb200.NsbError):
+                b.step_begin()                                           # at most one step in flight
+            assert b.step_end() == n
+        toks, cnt = b.pop_tokens_batch(ids2, 64)
+        for s in range(5):
+            got[s] += toks[s, :cnt[s]].tolist()
+        if n == 0 and pos >= audio.shape[1]:
+            break
+    for s in range(5):
+        assert got[s] == ref[s].tolist(), s
+        assert b.chunks(ids2[s]) == a.chunks(ids[s])
+    a.close(); b.close()

@@ -25,7 +25,7 @@ WARM = 70 // T + 3
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
     wtype = "q8_0" if COMPUTE == 4 else ("f32" if COMPUTE == 1 else "f16")
-    path = synth.cached_model(wtype, N_LAYERS, R=R)
+    path = synth.cached_model(wtype, N_LAYERS, R=R, profile=os.environ.get("NSB_BENCH_PROFILE", "speech"))
     eng = nsb200.Engine(path, right_context=R, max_streams=STREAMS, compute=COMPUTE, kv_dtype=KV)
     need = 160 * (8 * T * (WARM + 1) - 1) + 256
     base = [synth.synth_pcm(s, need / 16000.0 + 0.01)[:need] for s in range(8)]

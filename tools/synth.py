@@ -128,14 +128,29 @@ def mel_filterbank() -> np.ndarray:
     return fb.astype(np.float32)
 
 
-def load_calibration(seed: int, n_layers: int, R):
-    """(mu [1024] or None, blank_bias) for a (seed, n_layers, right_context) model; see tools/calibrate.py."""
+def load_calibration(seed: int, n_layers: int, R, profile: str = "parity"):
+    """(mu [1024] or None, blank_bias) for a (seed, n_layers, right_context) model; see tools/calibrate.py.
+    profile "parity": 25 % of the frames start an emission (dense decisions for the parity tests);
+    profile "speech": blank bias raised until the token rate is that of speech (~4.5 tokens per audio second) -- the bench
+    workload; falls back to the parity value (with a note on stderr) where no speech calibration is committed."""
     if R is not None:
         path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "calib", f"cal_s{seed}_L{n_layers}_R{R}.npz")
         if os.path.exists(path):
             z = np.load(path)
-            return z["mu"].astype(np.float32), float(z["blank_bias"])
+            bb = float(z["blank_bias"])
+            if profile == "speech":
+                if "blank_bias_speech" in z.files:
+                    bb = float(z["blank_bias_speech"])
+                else:
+                    import sys
+                    print(f"synth: no speech-rate calibration for L={n_layers} R={R}; using the parity blank bias", file=sys.stderr)
+            return z["mu"].astype(np.float32), bb
     return None, 2.8
+
+
+def has_speech_calibration(seed: int, n_layers: int, R) -> bool:
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "calib", f"cal_s{seed}_L{n_layers}_R{R}.npz")
+    return os.path.exists(path) and "blank_bias_speech" in np.load(path).files
 
 
 _CAL_MU = None   # set by write_gguf / write_nemo_bin while generating
@@ -245,10 +260,10 @@ def _wstr(f, s):
 
 
 def write_gguf(path: str, n_layers: int = 24, wtype: str = "f32", seed: int = 1234,
-               blank_bias: float | None = None, logit_gain: float = 1.0, R=None, mu=None) -> None:
+               blank_bias: float | None = None, logit_gain: float = 1.0, R=None, mu=None, profile: str = "parity") -> None:
     """R selects the committed calibration (mean encoder output + blank bias) of that latency mode."""
     global _CAL_MU
-    cal_mu, cal_bb = load_calibration(seed, n_layers, R)
+    cal_mu, cal_bb = load_calibration(seed, n_layers, R, profile)
     _CAL_MU = mu if mu is not None else cal_mu
     blank_bias = cal_bb if blank_bias is None else blank_bias
     specs = list(tensor_specs(n_layers))
@@ -373,18 +388,23 @@ def sine_pcm(seconds: float, freq: float = 440.0, sr: int = 16000) -> np.ndarray
     return (np.float32(0.5) * np.sin(np.float32(2.0 * np.pi * freq) * t) * np.float32(32767.0)).astype(np.int16)
 
 
-def cached_model(kind: str, n_layers: int, seed: int = 1234, cache_dir: str | None = None, R: int | None = 1) -> str:
+def cached_model(kind: str, n_layers: int, seed: int = 1234, cache_dir: str | None = None, R: int | None = 1,
+                 profile: str = "parity") -> str:
     """Materialise (once) and return the path of a synthetic model file. kind: f32|f16|q8_0|nemo.
-    R = latency mode whose calibration (tools/calib/) shapes joint.enc.bias and the blank bias."""
+    R = latency mode whose calibration (tools/calib/) shapes joint.enc.bias and the blank bias;
+    profile = "parity" (tests) | "speech" (bench: speech-like token rate, see load_calibration)."""
     cache_dir = cache_dir or os.environ.get("NSB_SYNTH_DIR", "/tmp/nsb200_synth")
     os.makedirs(cache_dir, exist_ok=True)
     ext = "bin" if kind == "nemo" else "gguf"
-    path = os.path.join(cache_dir, f"synth_s{seed}_L{n_layers}_R{R}_{kind}.{ext}")
+    tag = "" if profile == "parity" else f"_{profile}"
+    path = os.path.join(cache_dir, f"synth_s{seed}_L{n_layers}_R{R}{tag}_{kind}.{ext}")
     if not os.path.exists(path):
         if kind == "nemo":
+            if profile != "parity":
+                raise ValueError("NEMO bins are written with the parity calibration only")
             write_nemo_bin(path, n_layers, seed, R=R)
         else:
-            write_gguf(path, n_layers, kind, seed, R=R)
+            write_gguf(path, n_layers, kind, seed, R=R, profile=profile)
     return path
 
 

@@ -31,7 +31,7 @@ WARM = 70 // T + 3
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
     wtype = "q8_0" if COMPUTE == 4 else ("f32" if COMPUTE == 1 else "f16")
-    path = synth.cached_model(wtype, N_LAYERS, R=R)
+    path = synth.cached_model(wtype, N_LAYERS, R=R, profile=os.environ.get("NSB_BENCH_PROFILE", "speech"))
     eng = nsb200.Engine(path, right_context=R, max_streams=STREAMS, compute=COMPUTE, kv_dtype=KV)
     need = 160 * (8 * T * (WARM + 1) - 1) + 256
     base = [synth.synth_pcm(s, need / 16000.0 + 0.01)[:need] for s in range(8)]
@@ -57,6 +57,8 @@ def main():
             if tag in ("gemm_tc", "gemm_q8"):
                 pro = (t[1] - t[0]) / 1e3; wait = max(0, t[2] - t[1]) / 1e3; mma = max(0, t[3] - max(t[2], t[1])) / 1e3; body = (t[4] - t[3]) / 1e3
                 total = (t[4] - t[0]) / 1e3
+            elif tag == "attn" and t[3] and t[4]:        # pro = wait-return -> K/V + BD landed; mma = AC + softmax; body = PV + store
+                wait = (t[1] - t[0]) / 1e3; pro = (t[3] - t[1]) / 1e3; mma = (t[4] - t[3]) / 1e3; body = (t[2] - t[4]) / 1e3; total = (t[2] - t[0]) / 1e3
             else:
                 pro = 0.0; wait = (t[1] - t[0]) / 1e3; mma = 0.0; body = (t[2] - t[1]) / 1e3; total = (t[2] - t[0]) / 1e3
             key = f"{tag} g={grid}"
