@@ -9,6 +9,8 @@
 // term gather-indexes a pre-projected table instead of the pad/reshape shift; invalid cache slots are
 // skipped by count instead of a -1e9 additive mask; GLU + depthwise conv + LayerNorm + SiLU + cache
 // update are one kernel.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace nsb {
@@ -291,6 +293,167 @@ __global__ void __launch_bounds__(256, TQ <= 2 ? 4 : 2) attention_kernel(const A
     NSB_KERNEL_EPILOGUE();
 }
 
+// ------------------------------------------------------------------------------------------
+// Low-latency variant for T <= 2 with a 16-bit ring (the 80 / 160 ms modes): one CTA = one head x TWO streams, 512 threads
+// (each half of the CTA is the kernel above for one stream, synchronised by its own named barrier). What the pairing buys:
+// the positional rows P[r] of the head (73 x 128, the same for every stream) are staged ONCE per CTA in shared memory, by
+// cp.async issued BEFORE the dependency wait together with the K / V ring rows -- so after the QKV GEMM completes nothing
+// but q and this chunk's k / v rows (L2-hot, one round trip) stands between the wait and the arithmetic. In the one-stream
+// kernel the (q+v).P products wait for two dependent L2 round trips per warp AFTER the wait (7.4 of its 11 us, in-graph trace).
+// 104 KB of shared memory per CTA -> 2 CTAs per SM -> all 8 x B/2 CTAs of a 64-stream step in one wave.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void half_barrier(int half) { asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory"); }
+
+template <int KV, int TQ>
+__global__ void __launch_bounds__(512, 2) attention_pair_kernel(const AttnArgs a) {
+    using E = typename KvT<KV>::type;
+    constexpr int EPV = 16 / sizeof(E), VPR = D_HEAD / EPV;
+    extern __shared__ __align__(16) uint8_t att_smem[];
+    const int T = a.T, K = ATT_L + T, Cap = K, n_rel = ATT_L + 2 * T - 1;
+    const int tid = threadIdx.x, half = tid >> 8, t = tid & 255, warp = t >> 5, lane = t & 31;
+    const int h = blockIdx.x, b = blockIdx.y * 2 + half;
+    const bool active = b < a.B;
+    E* Ps = reinterpret_cast<E*>(att_smem);                                     // [n_rel][128], shared by both halves
+    uint8_t* hb = att_smem + (size_t)n_rel * D_HEAD * sizeof(E) + (size_t)half * (sizeof(AttnSmemF<TQ>) + (size_t)2 * K * D_HEAD * sizeof(E));
+    AttnSmemF<TQ>& sf = *reinterpret_cast<AttnSmemF<TQ>*>(hb);
+    E* Ks = reinterpret_cast<E*>(hb + sizeof(AttnSmemF<TQ>));                   // [K][128]
+    E* Vs = Ks + (size_t)K * D_HEAD;                                            // [K][128]
+    NSB_KERNEL_BEGIN(TR_ATTN)
+    // ---- before the dependency wait: positional rows, cached K / V rows, ring bookkeeping, biases ----
+    const E* P = reinterpret_cast<const E*>(a.pos_proj) + h * D_HEAD;
+    for (int e = tid; e < n_rel * VPR; e += 512) {
+        const int r = e / VPR, c = (e % VPR) * EPV;
+        cp_async16(Ps + (size_t)r * D_HEAD + c, P + (size_t)r * D_MODEL + c);
+    }
+    int slot = 0, w = 0, first = ATT_L;
+    if (active) { slot = a.slot_of_b[b]; w = a.ring_pos[slot]; first = ATT_L - a.valid_len[slot]; }   // keys j < first are not yet valid (:982-992)
+    const float* qkv = a.qkv + (size_t)b * T * 3 * D_MODEL + h * D_HEAD;
+    E* kring = reinterpret_cast<E*>(a.k_ring) + (size_t)slot * a.slot_stride + h * D_HEAD;
+    E* vring = reinterpret_cast<E*>(a.v_ring) + (size_t)slot * a.slot_stride + h * D_HEAD;
+    auto ring_row = [&](int j) { return (size_t)((w + Cap - ATT_L + j) % Cap) * D_MODEL; };
+    for (int e = t; e < (ATT_L - first) * VPR; e += 256) {
+        const int j = first + e / VPR, c = (e % VPR) * EPV;
+        const size_t g = ring_row(j) + c;
+        cp_async16(Ks + (size_t)j * D_HEAD + c, kring + g);
+        cp_async16(Vs + (size_t)j * D_HEAD + c, vring + g);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const float scale = 0.08838834764831845f;                                   // 1/sqrt(128) :517
+    const int c4 = lane * 4;
+    float bu[4], bv[4];
+    load4(a.bias_u + h * D_HEAD + c4, bu); load4(a.bias_v + h * D_HEAD + c4, bv);
+    NSB_KERNEL_WAIT()
+    float qu[TQ][4], qv[TQ][4];
+    if (active) {
+        // q of every query, and this chunk's K / V rows (rounded to the ring dtype): shared memory AND ring append
+#pragma unroll
+        for (int i = 0; i < TQ; ++i) {
+            float q[4] = {0.f, 0.f, 0.f, 0.f};
+            if (i < T) load4(qkv + (size_t)i * 3 * D_MODEL + c4, q);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { qu[i][u] = q[u] + bu[u]; qv[i][u] = q[u] + bv[u]; }   // :503-507
+        }
+        for (int e = t; e < T * (D_HEAD / 4); e += 256) {
+            const int i = e / (D_HEAD / 4), c = (e % (D_HEAD / 4)) * 4;
+            const float4 kn = *reinterpret_cast<const float4*>(qkv + (size_t)i * 3 * D_MODEL + D_MODEL + c);
+            const float4 vn = *reinterpret_cast<const float4*>(qkv + (size_t)i * 3 * D_MODEL + 2 * D_MODEL + c);
+            const E k4[4] = {from_f32<E>(kn.x), from_f32<E>(kn.y), from_f32<E>(kn.z), from_f32<E>(kn.w)};
+            const E v4[4] = {from_f32<E>(vn.x), from_f32<E>(vn.y), from_f32<E>(vn.z), from_f32<E>(vn.w)};
+            E* kd = kring + ring_row(ATT_L + i) + c; E* vd = vring + ring_row(ATT_L + i) + c;
+            E* ks = Ks + (size_t)(ATT_L + i) * D_HEAD + c; E* vs = Vs + (size_t)(ATT_L + i) * D_HEAD + c;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { kd[u] = k4[u]; vd[u] = v4[u]; ks[u] = k4[u]; vs[u] = v4[u]; }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                                              // the only CTA-wide barrier: P / K / V tiles and the new rows are in place
+    if (tr_slot >= 0) trace_mark(tr_slot, 3);
+    if (!active) return;                                                          // odd batch: the second half of the last CTA has no stream
+    // ---- BD_raw[i][r] = (q_i + v) . P[r] and AC[i][j] = (q_i + u) . k_j: one row per warp step, out of shared memory ----
+    const int r_end = ATT_L + 2 * T - 1 - first;                                  // largest positional row used + 1
+    for (int rr = warp; rr < r_end; rr += 8) {
+        float pf[4];
+        load4(Ps + (size_t)rr * D_HEAD + c4, pf);
+#pragma unroll
+        for (int i = 0; i < TQ; ++i) {
+            float s = qv[i][0] * pf[0];
+            s = fmaf(qv[i][1], pf[1], s); s = fmaf(qv[i][2], pf[2], s); s = fmaf(qv[i][3], pf[3], s);
+            s = warp_sum(s);
+            if (lane == 0) sf.bd[i][rr] = s;
+        }
+    }
+    for (int j = first + warp; j < K; j += 8) {
+        float kf[4];
+        load4(Ks + (size_t)j * D_HEAD + c4, kf);
+#pragma unroll
+        for (int i = 0; i < TQ; ++i) {
+            float s = qu[i][0] * kf[0];
+            s = fmaf(qu[i][1], kf[1], s); s = fmaf(qu[i][2], kf[2], s); s = fmaf(qu[i][3], kf[3], s);
+            s = warp_sum(s);
+            if (lane == 0) sf.ac[i][j] = s;
+        }
+    }
+    half_barrier(half);
+    // ---- softmax over valid keys; rel-shift = index arithmetic: BD[i][j] = BD_raw[i][L + i - j + T-1] (:391-433) ----
+    for (int i = warp; i < T; i += 8) {
+        float mx = -INFINITY;
+        for (int j = first + lane; j < K; j += 32) {
+            const float s = (sf.ac[i][j] + sf.bd[i][ATT_L + i - j + T - 1]) * scale;
+            sf.ac[i][j] = s; mx = fmaxf(mx, s);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = first + lane; j < K; j += 32) { const float e = expf(sf.ac[i][j] - mx); sf.ac[i][j] = e; sum += e; }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        for (int j = first + lane; j < K; j += 32) sf.ac[i][j] *= inv;
+    }
+    half_barrier(half);
+    if (tr_slot >= 0) trace_mark(tr_slot, 4);
+    // ---- ctx[i][d] = sum_j p[i][j] v_j[d]; thread = (key group kg, 2 dims) ----
+    {
+        const int d2 = (t & 63) * 2, kg = t >> 6;
+        float acc[TQ][2];
+#pragma unroll
+        for (int i = 0; i < TQ; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
+#pragma unroll 4
+        for (int j = first + kg; j < K; j += 4) {
+            float vf[2];
+            load2(Vs + (size_t)j * D_HEAD + d2, vf);
+#pragma unroll
+            for (int i = 0; i < TQ; ++i) {
+                const float p = sf.ac[i][j];
+                acc[i][0] = fmaf(p, vf[0], acc[i][0]); acc[i][1] = fmaf(p, vf[1], acc[i][1]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < TQ; ++i) { sf.red[kg][i][d2] = acc[i][0]; sf.red[kg][i][d2 + 1] = acc[i][1]; }
+    }
+    half_barrier(half);
+    for (int e = t; e < T * D_HEAD; e += 256) {
+        const int i = e / D_HEAD, d = e % D_HEAD;
+        const float v = (sf.red[0][i][d] + sf.red[1][i][d]) + (sf.red[2][i][d] + sf.red[3][i][d]);
+        store_out(a.ctx, ((size_t)b * T + i) * D_MODEL + h * D_HEAD + d, v, a.out_type);
+    }
+    NSB_KERNEL_EPILOGUE();
+}
+
+template <int KV, int TQ>
+static void launch_attention_pair(const AttnArgs& a, cudaStream_t st) {
+    using E = typename KvT<KV>::type;
+    const size_t smem = (size_t)(ATT_L + 2 * a.T - 1) * D_HEAD * sizeof(E) + 2 * (sizeof(AttnSmemF<TQ>) + (size_t)2 * (ATT_L + a.T) * D_HEAD * sizeof(E));
+    static bool configured = false;
+    if (!configured) {
+        NSB_CUDA(cudaFuncSetAttribute(attention_pair_kernel<KV, TQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    launch_k(attention_pair_kernel<KV, TQ>, dim3(N_HEADS, (a.B + 1) / 2), dim3(512), smem, st, a);
+}
+static bool attention_pair_enabled() {
+    static const bool on = [] { const char* e = getenv("NSB_ATT_PAIR"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 template <int KV, int TQ>
 static void launch_attention_tq(const AttnArgs& a, cudaStream_t st) {
     using E = typename KvT<KV>::type;
@@ -305,6 +468,9 @@ static void launch_attention_tq(const AttnArgs& a, cudaStream_t st) {
 template <int KV>
 static void launch_attention_t(const AttnArgs& a, cudaStream_t st) {
     if (a.T > ATT_MAX_T) throw CudaError("attention: att_right_context too large");
+    if constexpr (KV != 0) {                                                      // 16-bit ring, T <= 2: the paired low-latency kernel
+        if (a.T <= 2 && attention_pair_enabled()) { if (a.T == 1) launch_attention_pair<KV, 1>(a, st); else launch_attention_pair<KV, 2>(a, st); return; }
+    }
     if (a.T == 1) launch_attention_tq<KV, 1>(a, st);
     else if (a.T == 2) launch_attention_tq<KV, 2>(a, st);
     else if (a.T <= 4) launch_attention_tq<KV, 4>(a, st);

@@ -166,15 +166,16 @@ def test_streaming_parity_f32_full_24_layer_model(built):
     eng.close()
 
 
-@pytest.mark.parametrize("wtype,compute,kv,mm,okv,tol,band", [
-    ("f32", 2, 0, O.MM_F16, O.KV_F32, 3e-3, 2e-2),
-    ("f16", 0, 1, O.MM_REF, O.KV_F16, 3e-3, 2e-2),          # F16 GGUF -> ggml F16 semantics (+ fp16 K/V ring)
-    ("f32", 3, 2, O.MM_BF16, O.KV_BF16, 3e-2, 2e-1),
-    ("q8_0", 0, 0, O.MM_Q8FAST, O.KV_F32, 3e-3, 2e-2),
+@pytest.mark.parametrize("wtype,compute,kv,mm,okv,tol,band,R", [
+    ("f32", 2, 0, O.MM_F16, O.KV_F32, 3e-3, 2e-2, 1),
+    ("f16", 0, 1, O.MM_REF, O.KV_F16, 3e-3, 2e-2, 1),       # F16 GGUF -> ggml F16 semantics (+ fp16 K/V ring)
+    ("f32", 3, 2, O.MM_BF16, O.KV_BF16, 3e-2, 2e-1, 1),
+    ("q8_0", 0, 0, O.MM_Q8FAST, O.KV_F32, 3e-3, 2e-2, 1),
+    ("f16", 0, 1, O.MM_REF, O.KV_F16, 3e-3, 2e-2, 0),       # 80 ms mode (T = 1): paired attention kernel, odd batches
+    ("f16", 0, 1, O.MM_REF, O.KV_F16, 3e-3, 2e-2, 6),       # 560 ms mode (T = 7): tiled attention kernel with a 16-bit ring
 ])
-def test_streaming_parity_16bit_and_q8(built, wtype, compute, kv, mm, okv, tol, band):
+def test_streaming_parity_16bit_and_q8(built, wtype, compute, kv, mm, okv, tol, band, R):
     import nsb200
-    R = 1
     path = synth.cached_model(wtype, 2, R=R)
     eng = nsb200.Engine(path, right_context=R, max_streams=4, compute=compute, kv_dtype=kv)
     eng.debug_enable(True)
