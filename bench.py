@@ -11,7 +11,8 @@ N > 1 (torchrun, one rank per GPU): streams are independent, so every rank runs 
 engine with no data-path collective ("weak" scaling); torch.distributed is used only for the barrier and the
 max-over-ranks of the timed region.
 
-  value : device-resident throughput -- PCM of the step already in HBM, CUDA events around the K steps
+  value : device-resident throughput -- PCM of the step already in HBM, the K steps enqueued back to back on the engine's
+          stream, CUDA events around them (p50 / p99 chunk latency: single host-synchronised steps, outside the timed region)
   e2e   : the same K steps through the public C ABI with HOST buffers: nsb_push_pcm_batch, nsb_engine_step_begin
           (pinned staging + H2D + kernels + D2H of the token ids enqueued), the next chunk pushed meanwhile,
           nsb_engine_step_end, nsb_pop_tokens_batch; wall clock
@@ -205,15 +206,15 @@ def main():
     sampler = ClockSampler(local); sampler.start()
     sync_all()
     t0 = time.perf_counter()
-    dev_ms = 0.0; lat = []
-    for _ in range(args.steps):
-        ms = eng.bench_step(); dev_ms += ms; lat.append(ms)
+    dev_ms, per_step = eng.bench_steps(args.steps)        # K steps enqueued back to back, CUDA events on the engine stream
     sync_all()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
+    # per-chunk latency: one step at a time, host-synchronised (what a caller waiting for this chunk's tokens sees on the device)
     st1 = eng.stats()
     launches = int(st1.kernel_launches - st0.kernel_launches)
-    # device time of the K steps = sum of per-step event times on the engine stream; max over ranks
+    lat = [eng.bench_step() for _ in range(min(args.steps, 30))]
+    # device time of the K steps = first event -> last event on the engine stream; max over ranks
     t_dev = torch.tensor([dev_ms / 1e3, wall], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)

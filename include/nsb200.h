@@ -123,6 +123,9 @@ void nsb_engine_get_stats(const nsb_engine* e, nsb_stats* out);
  * advances; tokens are produced and discarded). Returns device ms of the step via *ms. */
 int nsb_bench_prepare(nsb_engine* e, int n_streams, const int16_t* pcm, int samples_per_stream, int warm_chunks);
 int nsb_bench_step(nsb_engine* e, float* ms);
+/* n steps enqueued back to back (no host synchronisation in between), one CUDA event between consecutive steps:
+ * ms_each[i] (optional, n floats) = device time of step i, *total_ms = first event -> last event */
+int nsb_bench_steps(nsb_engine* e, int n, float* ms_each, float* total_ms);
 /* one bench step with every kernel launch bracketed by CUDA events on the engine's stream; device ms and launch
  * count per kernel class: 0 log-mel, 1 subsampling, 2 layernorm, 3 layer GEMMs, 4 attention, 5 conv module,
  * 6 joint.enc + RNN-T decode, 7 misc. Arrays must hold NSB_PROFILE_CLASSES entries. */

@@ -50,7 +50,7 @@ EXPORTS = ["nsb_gguf_probe", "nsb_default_config", "nsb_engine_create", "nsb_eng
            "nsb_engine_vocab_size", "nsb_engine_vocab", "nsb_engine_chunk_samples", "nsb_engine_shift_samples", "nsb_engine_compute",
            "nsb_stream_open", "nsb_stream_close", "nsb_stream_reset", "nsb_stream_push_pcm", "nsb_push_pcm_batch", "nsb_pop_tokens_batch", "nsb_stream_ready", "nsb_engine_step", "nsb_engine_step_begin", "nsb_engine_step_end",
            "nsb_engine_drain", "nsb_stream_pop_tokens", "nsb_stream_chunks", "nsb_detokenize", "nsb_engine_get_stats",
-           "nsb_bench_prepare", "nsb_bench_step", "nsb_bench_profile", "nsb_profiler_range", "nsb_bench_gemm", "nsb_trace_enable", "nsb_trace_fetch", "nsb_debug_enable", "nsb_debug_get", "nsb_debug_get_cache", "nsb_op_logmel",
+           "nsb_bench_prepare", "nsb_bench_step", "nsb_bench_steps", "nsb_bench_profile", "nsb_profiler_range", "nsb_bench_gemm", "nsb_trace_enable", "nsb_trace_fetch", "nsb_debug_enable", "nsb_debug_get", "nsb_debug_get_cache", "nsb_op_logmel",
            "nsb_op_gemm"]
 
 
@@ -94,6 +94,7 @@ def lib():
         L.nsb_engine_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.nsb_bench_prepare.argtypes = [vp, ci, _i16p, ci, ci]
         L.nsb_bench_step.argtypes = [vp, C.POINTER(C.c_float)]
+        L.nsb_bench_steps.argtypes = [vp, ci, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.nsb_bench_profile.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_float)]
         L.nsb_profiler_range.argtypes = [ci]
         L.nsb_trace_enable.argtypes = [vp, ci]
@@ -226,6 +227,12 @@ class Engine:
         ms = C.c_float()
         _check(lib().nsb_bench_step(self.h, C.byref(ms)))
         return ms.value
+
+    def bench_steps(self, n: int):
+        """n steps enqueued back to back; returns (total device ms, per-step device ms)."""
+        per = (C.c_float * n)(); tot = C.c_float()
+        _check(lib().nsb_bench_steps(self.h, n, per, C.byref(tot)))
+        return tot.value, [float(x) for x in per]
 
     PROFILE_CLASSES = ("logmel", "subsampling", "layernorm", "layer_gemm", "attention", "conv_module", "decode", "misc")
 

@@ -117,6 +117,9 @@ int nsb_bench_prepare(nsb_engine* e, int n, const int16_t* pcm, int sps, int war
 int nsb_bench_step(nsb_engine* e, float* ms) {
     if (!e) return fail(NSB_ERR_ARG, "null engine"); NSB_TRY const float t = e->impl->bench_step(); if (ms) *ms = t; return NSB_OK; NSB_CATCH }
 
+int nsb_bench_steps(nsb_engine* e, int n, float* ms_each, float* total_ms) {
+    if (!e) return fail(NSB_ERR_ARG, "null engine"); NSB_TRY const float t = e->impl->bench_steps(n, ms_each); if (total_ms) *total_ms = t; return NSB_OK; NSB_CATCH }
+
 int nsb_bench_profile(nsb_engine* e, float* ms_per_class, int* launches_per_class, float* total_ms) {
     if (!e || !ms_per_class || !launches_per_class) return fail(NSB_ERR_ARG, "bad argument");
     NSB_TRY const float t = e->impl->bench_profile(ms_per_class, launches_per_class); if (total_ms) *total_ms = t; return NSB_OK; NSB_CATCH }

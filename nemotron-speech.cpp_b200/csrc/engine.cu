@@ -21,6 +21,7 @@ namespace nsb {
 void launch_gemm_tc(const GemmArgs& a, int in_type /*OUT_F16 | OUT_BF16*/, cudaStream_t st);
 
 constexpr int MAX_SPLITS = 8;
+constexpr size_t SPLIT_CONSUMER_MAX_ROWS = 256;   // up to this many token rows per step the QKV / pointwise-1 GEMMs are split-K as well
 
 bool pdl_enabled() {
     static const bool on = [] { const char* e = getenv("NSB_NO_PDL"); return !(e && e[0] == '1'); }();
@@ -294,8 +295,11 @@ void Engine::alloc_state() {
     x_.alloc(Mrows * D_MODEL * 4);
     a_.alloc(Mrows * D_MODEL * act_size());
     big_.alloc(Mrows * D_FF * act_size());
-    qkv_.alloc(Mrows * 3 * D_MODEL * 4);
-    pw1_.alloc(Mrows * 2 * D_MODEL * 4);
+    // small batches: the QKV / pointwise-1 GEMMs run split-K and leave their partial planes for the consumer kernel to sum
+    const size_t planes = Mrows <= SPLIT_CONSUMER_MAX_ROWS ? 4 : 1;
+    consumer_planes_ = (int)planes;
+    qkv_.alloc(planes * Mrows * 3 * D_MODEL * 4);
+    pw1_.alloc(planes * Mrows * 2 * D_MODEL * 4);
     encp_.alloc(Mrows * JOINT * 4);
     part_.alloc((size_t)MAX_SPLITS * std::min<size_t>(Mrows, 1024) * D_MODEL * 4);       // split-K workspace (only used when rows <= 1024)
     out_tok_.alloc((size_t)S * MAX_SYMBOLS * T * 4); out_cnt_.alloc((size_t)S * 4);
@@ -355,6 +359,19 @@ void Engine::gemm(const void* A, long long lda, const Weight& W, int M, const fl
     ProfScope ps(this, PC_GEMM);
     if (compute == NSB_COMPUTE_F32) launch_gemm_simt(a, st_);
     else launch_gemm_tc(a, act_type(), st_);
+    count_launch();
+}
+
+bool Engine::split_consumers(int rows) const {
+    static const bool off = [] { const char* e = getenv("NSB_NO_SPLIT_CONSUMERS"); return e && e[0] == '1'; }();
+    return !off && consumer_planes_ >= 4 && (compute == NSB_COMPUTE_F16 || compute == NSB_COMPUTE_BF16) && rows <= 128;
+}
+
+// split-K GEMM whose fp32 partial planes C[z][M][N] are left for the consumer kernel to sum (QKV -> attention, pointwise-1 -> conv module)
+void Engine::gemm_planes(const void* A, long long lda, const Weight& W, int M, void* C, int planes) {
+    GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.w_scales = W.scales.p; a.M = M; a.N = W.n_out; a.K = W.n_in; a.C = C; a.ldc = W.n_out;
+    a.epi = EPI_PARTIAL; a.out_type = OUT_F32; a.splits = planes; a.force_bn = 64; a.force_stages = 4;
+    { ProfScope ps(this, PC_GEMM); launch_gemm_tc(a, act_type(), st_); }
     count_launch();
 }
 
@@ -584,9 +601,16 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
         gemm_residual(big_.p, D_FF, L.ff1b, rows, x, 0.5f); }
         // MHSA over the ring cache                                                  (:609-615)
         ln(L.ln[2].as<float>(), L.ln[3].as<float>());
-        if (!(skip & SK_QKV)) gemm(a_.p, D_MODEL, L.qkv, rows, nullptr, qkv_.p, 3 * D_MODEL, EPI_NONE, 1.f, OUT_F32);
+        // Small batches (one 128-row tile): with full-K tiles every CTA pulls the whole activation tile (256 KB) and the launch is
+        // bound by per-SM L2->SM ingest. Split-K with 64-wide tiles cuts that to 128 + 64 KB (QKV, 2 slices) / 64 + 32 KB
+        // (pointwise-1, 4 slices); the fp32 partial planes are summed, in slice order, by the consumer kernel as it loads them.
+        const int qkv_planes = split_consumers(rows) ? 2 : 1, pw1_planes = split_consumers(rows) ? 4 : 1;
+        if (!(skip & SK_QKV)) {
+            if (qkv_planes == 1) gemm(a_.p, D_MODEL, L.qkv, rows, nullptr, qkv_.p, 3 * D_MODEL, EPI_NONE, 1.f, OUT_F32);
+            else gemm_planes(a_.p, D_MODEL, L.qkv, rows, qkv_.p, qkv_planes);
+        }
         if (!(skip & SK_ATTN)) {
-            AttnArgs aa; aa.qkv = qkv_.as<float>();
+            AttnArgs aa; aa.qkv = qkv_.as<float>(); aa.planes = qkv_planes; aa.plane_stride = (long long)rows * 3 * D_MODEL;
             const size_t es = kv_elem_size(kv_dtype);
             aa.k_ring = (char*)kv_.p + (size_t)l * 2 * (ATT_L + T) * D_MODEL * es;
             aa.v_ring = (char*)aa.k_ring + (size_t)(ATT_L + T) * D_MODEL * es;
@@ -598,9 +622,12 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
         if (!(skip & SK_OUT)) gemm_residual(a_.p, D_MODEL, L.out, rows, x, 1.f);
         // conv module                                                               (:618-651)
         ln(L.ln[4].as<float>(), L.ln[5].as<float>());
-        if (!(skip & SK_PW)) gemm(a_.p, D_MODEL, L.pw1, rows, nullptr, pw1_.p, 2 * D_MODEL, EPI_NONE, 1.f, OUT_F32);
+        if (!(skip & SK_PW)) {
+            if (pw1_planes == 1) gemm(a_.p, D_MODEL, L.pw1, rows, nullptr, pw1_.p, 2 * D_MODEL, EPI_NONE, 1.f, OUT_F32);
+            else gemm_planes(a_.p, D_MODEL, L.pw1, rows, pw1_.p, pw1_planes);
+        }
         if (!(skip & SK_CONV)) {
-            ConvModArgs ca; ca.pw1 = pw1_.as<float>(); ca.conv_cache = conv_cache_.as<float>() + (size_t)l * (CONV_K - 1) * D_MODEL;
+            ConvModArgs ca; ca.pw1 = pw1_.as<float>(); ca.planes = pw1_planes; ca.plane_stride = (long long)rows * 2 * D_MODEL; ca.conv_cache = conv_cache_.as<float>() + (size_t)l * (CONV_K - 1) * D_MODEL;
             ca.slot_stride = cc_slot_stride; ca.dw_w = L.dw_w.as<float>(); ca.ln_g = L.cln_g.as<float>(); ca.ln_b = L.cln_b.as<float>();
             ca.out = a_.p; ca.out_type = at; ca.slot_of_b = slot; ca.B = B; ca.T = T;
             ProfScope ps(this, PC_CONVMOD); launch_conv_module(ca, st_); count_launch();
@@ -682,6 +709,27 @@ float Engine::bench_step() {
     float ms = 0.f; NSB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
     stats.steps += 1; stats.chunks += bench_B_; stats.device_ms += ms; stats.last_step_ms = ms;
     return ms;
+}
+
+float Engine::bench_steps(int n, float* ms_each) {
+    if (!bench_B_) throw std::runtime_error("bench_steps before bench_prepare");
+    if (n < 1) throw std::invalid_argument("bench_steps: n < 1");
+    if (!inflight_.empty()) step_end();
+    NSB_CUDA(cudaSetDevice(device_));
+    ev_used_ = 0;
+    std::vector<cudaEvent_t> ev((size_t)n + 1);
+    for (int i = 0; i <= n; ++i) ev[i] = prof_event();
+    NSB_CUDA(cudaEventRecord(ev[0], st_));
+    for (int i = 0; i < n; ++i) { run_step(bench_B_, bench_pcm_.as<int16_t>()); NSB_CUDA(cudaEventRecord(ev[i + 1], st_)); }
+    NSB_CUDA(cudaEventSynchronize(ev[n]));
+    float total = 0.f; NSB_CUDA(cudaEventElapsedTime(&total, ev[0], ev[n]));
+    for (int i = 0; i < n; ++i) {
+        float ms = 0.f; NSB_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+        if (ms_each) ms_each[i] = ms;
+    }
+    stats.steps += n; stats.chunks += (long long)n * bench_B_; stats.device_ms += total; stats.last_step_ms = total / n;
+    ev_used_ = 0;
+    return total;
 }
 
 float Engine::bench_gemm(int kind, int rows, int bn, int stages, int splits, int rotate, int iters) {

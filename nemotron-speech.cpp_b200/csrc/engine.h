@@ -75,6 +75,9 @@ public:
 
     void bench_prepare(int n_streams, const int16_t* pcm, int samples_per_stream, int warm_chunks);
     float bench_step();
+    // n steps enqueued back to back (no host synchronisation in between: the launch of step i+1 overlaps step i), one event
+    // between consecutive steps; ms_each[i] = device time of step i, returns the total (first event -> last event)
+    float bench_steps(int n, float* ms_each);
     // one bench step with every launch bracketed by CUDA events; per-class device ms and launch counts
     enum { PC_MEL = 0, PC_SUBSAMPLE, PC_LAYERNORM, PC_GEMM, PC_ATTENTION, PC_CONVMOD, PC_DECODE, PC_MISC, PC_COUNT };
     float bench_profile(float* ms_per_class, int* launches_per_class);
@@ -111,6 +114,8 @@ private:
               int out_type);
     // x += alpha * A W^T. Small batches: split-K into the workspace, reduction folded into the next LayerNorm (pending_).
     void gemm_residual(const void* A, long long lda, const Weight& W, int M, float* x, float alpha);
+    bool split_consumers(int rows) const;
+    void gemm_planes(const void* A, long long lda, const Weight& W, int M, void* C, int planes);
     PartialSum pending_{};
     void run_step_kernels(int B, const int16_t* d_pcm);      // everything between PCM-in-HBM and tokens-in-HBM
     // run_step_kernels through a CUDA graph captured once per (batch size, PCM buffer): the ~350 launches of a step become
@@ -150,6 +155,7 @@ private:
     DevBuf d_pcm_, d_slot_, mel_new_, dw_, pw_, x_, a_, big_, qkv_, pw1_, encp_, part_;
     DevBuf out_tok_, out_cnt_, dec_sync_;
     HostPinned h_pcm_, h_slot_, h_tok_, h_cnt_;
+    int consumer_planes_ = 1;         // planes the qkv_ / pw1_ buffers were sized for (split-K partials summed by the consumer kernels)
     std::vector<int> inflight_;       // batch -> stream slot of the step launched by step_begin()
 
     // ---- bench ----

@@ -61,7 +61,8 @@ void launch_layernorm2(float* x, int rows, const float* g1, const float* b1, con
                        int out_type, const PartialSum& ps, cudaStream_t st);
 
 struct AttnArgs {
-    const float* qkv;             // [M][3072] f32 (q | k | v)
+    const float* qkv;             // [planes][M][3072] f32 (q | k | v); planes > 1 = split-K partials of the QKV GEMM, summed on load
+    int planes = 1; long long plane_stride = 0;   // elements between planes
     void* k_ring; void* v_ring;   // layer base; element (slot, r, c) at slot*slot_stride + r*1024 + c
     long long slot_stride;        // elements
     int kv_dtype;                 // 0 f32, 1 f16, 2 bf16
@@ -74,7 +75,8 @@ struct AttnArgs {
 void launch_attention(const AttnArgs& a, cudaStream_t st);
 
 struct ConvModArgs {
-    const float* pw1;             // [M][2048] f32  (a | gate)
+    const float* pw1;             // [planes][M][2048] f32  (a | gate); planes > 1 = split-K partials of the pointwise GEMM, summed on load
+    int planes = 1; long long plane_stride = 0;
     float* conv_cache;            // layer base; (slot, r, c) at slot*slot_stride + r*1024 + c, r in 0..7
     long long slot_stride;
     const float* dw_w;            // [9][1024] tap-major (GGUF layout)

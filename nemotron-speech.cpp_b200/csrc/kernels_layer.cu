@@ -148,6 +148,24 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 
+// f32 vector load that folds up to MAXP split-K partial planes (fixed order z = 0, 1, ...: deterministic), all loads issued first
+template <int MAXP>
+__device__ __forceinline__ float4 ld4_planes(const float* p, int planes, long long stride) {
+    float4 v = *reinterpret_cast<const float4*>(p);
+    if (planes > 1) {
+        float4 t[MAXP - 1];
+#pragma unroll
+        for (int z = 1; z < MAXP; ++z) if (z < planes) t[z - 1] = *reinterpret_cast<const float4*>(p + (size_t)z * stride);
+#pragma unroll
+        for (int z = 1; z < MAXP; ++z) if (z < planes) { v.x += t[z - 1].x; v.y += t[z - 1].y; v.z += t[z - 1].z; v.w += t[z - 1].w; }
+    }
+    return v;
+}
+constexpr int QKV_MAX_PLANES = 2, PW1_MAX_PLANES = 4;
+__device__ __forceinline__ void load4_planes(const float* p, int planes, long long stride, float (&f)[4]) {
+    const float4 v = ld4_planes<QKV_MAX_PLANES>(p, planes, stride); f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+}
+
 template <int TQ> struct AttnSmemF {                             // fp32 part of the shared memory (K / V tiles follow)
     float ac[TQ][ATT_MAX_K];                                     // (q+u).k, then probabilities
     float bd[TQ][ATT_MAX_REL];                                   // (q+v).P[r]
@@ -190,8 +208,8 @@ __global__ void __launch_bounds__(256, TQ <= 2 ? 4 : 2) attention_kernel(const A
     // ---- this chunk's K / V rows (rounded to the ring dtype): shared memory AND ring append ----
     for (int e = tid; e < T * (D_HEAD / 4); e += 256) {
         const int i = e / (D_HEAD / 4), c = (e % (D_HEAD / 4)) * 4;
-        const float4 kn = *reinterpret_cast<const float4*>(qkv + (size_t)i * 3 * D_MODEL + D_MODEL + c);
-        const float4 vn = *reinterpret_cast<const float4*>(qkv + (size_t)i * 3 * D_MODEL + 2 * D_MODEL + c);
+        const float4 kn = ld4_planes<QKV_MAX_PLANES>(qkv + (size_t)i * 3 * D_MODEL + D_MODEL + c, a.planes, a.plane_stride);
+        const float4 vn = ld4_planes<QKV_MAX_PLANES>(qkv + (size_t)i * 3 * D_MODEL + 2 * D_MODEL + c, a.planes, a.plane_stride);
         const E k4[4] = {from_f32<E>(kn.x), from_f32<E>(kn.y), from_f32<E>(kn.z), from_f32<E>(kn.w)};
         const E v4[4] = {from_f32<E>(vn.x), from_f32<E>(vn.y), from_f32<E>(vn.z), from_f32<E>(vn.w)};
         E* kd = kring + ring_row(ATT_L + i) + c; E* vd = vring + ring_row(ATT_L + i) + c;
@@ -206,7 +224,7 @@ __global__ void __launch_bounds__(256, TQ <= 2 ? 4 : 2) attention_kernel(const A
 #pragma unroll
         for (int i = 0; i < TQ; ++i) {
             float q[4] = {0.f, 0.f, 0.f, 0.f};
-            if (i < nq) load4(qkv + (size_t)(q0 + i) * 3 * D_MODEL + c4, q);
+            if (i < nq) load4_planes(qkv + (size_t)(q0 + i) * 3 * D_MODEL + c4, a.planes, a.plane_stride, q);
 #pragma unroll
             for (int u = 0; u < 4; ++u) { qu[i][u] = q[u] + bu[u]; qv[i][u] = q[u] + bv[u]; }   // :503-507
         }
@@ -349,14 +367,14 @@ __global__ void __launch_bounds__(512, 2) attention_pair_kernel(const AttnArgs a
 #pragma unroll
         for (int i = 0; i < TQ; ++i) {
             float q[4] = {0.f, 0.f, 0.f, 0.f};
-            if (i < T) load4(qkv + (size_t)i * 3 * D_MODEL + c4, q);
+            if (i < T) load4_planes(qkv + (size_t)i * 3 * D_MODEL + c4, a.planes, a.plane_stride, q);
 #pragma unroll
             for (int u = 0; u < 4; ++u) { qu[i][u] = q[u] + bu[u]; qv[i][u] = q[u] + bv[u]; }   // :503-507
         }
         for (int e = t; e < T * (D_HEAD / 4); e += 256) {
             const int i = e / (D_HEAD / 4), c = (e % (D_HEAD / 4)) * 4;
-            const float4 kn = *reinterpret_cast<const float4*>(qkv + (size_t)i * 3 * D_MODEL + D_MODEL + c);
-            const float4 vn = *reinterpret_cast<const float4*>(qkv + (size_t)i * 3 * D_MODEL + 2 * D_MODEL + c);
+            const float4 kn = ld4_planes<QKV_MAX_PLANES>(qkv + (size_t)i * 3 * D_MODEL + D_MODEL + c, a.planes, a.plane_stride);
+            const float4 vn = ld4_planes<QKV_MAX_PLANES>(qkv + (size_t)i * 3 * D_MODEL + 2 * D_MODEL + c, a.planes, a.plane_stride);
             const E k4[4] = {from_f32<E>(kn.x), from_f32<E>(kn.y), from_f32<E>(kn.z), from_f32<E>(kn.w)};
             const E v4[4] = {from_f32<E>(vn.x), from_f32<E>(vn.y), from_f32<E>(vn.z), from_f32<E>(vn.w)};
             E* kd = kring + ring_row(ATT_L + i) + c; E* vd = vring + ring_row(ATT_L + i) + c;
@@ -370,29 +388,37 @@ __global__ void __launch_bounds__(512, 2) attention_pair_kernel(const AttnArgs a
     if (tr_slot >= 0) trace_mark(tr_slot, 3);
     if (!active) return;                                                          // odd batch: the second half of the last CTA has no stream
     // ---- BD_raw[i][r] = (q_i + v) . P[r] and AC[i][j] = (q_i + u) . k_j: one row per warp step, out of shared memory ----
+    // four rows per warp step: 4 x TQ independent butterfly reductions in flight hide the shuffle latency
     const int r_end = ATT_L + 2 * T - 1 - first;                                  // largest positional row used + 1
-    for (int rr = warp; rr < r_end; rr += 8) {
-        float pf[4];
-        load4(Ps + (size_t)rr * D_HEAD + c4, pf);
+    auto dots4 = [&](const E* rows, int r0, int r_lim, const float (&qq)[TQ][4], float* out, int out_stride) {
+        float s[4][TQ];
 #pragma unroll
-        for (int i = 0; i < TQ; ++i) {
-            float s = qv[i][0] * pf[0];
-            s = fmaf(qv[i][1], pf[1], s); s = fmaf(qv[i][2], pf[2], s); s = fmaf(qv[i][3], pf[3], s);
-            s = warp_sum(s);
-            if (lane == 0) sf.bd[i][rr] = s;
-        }
-    }
-    for (int j = first + warp; j < K; j += 8) {
-        float kf[4];
-        load4(Ks + (size_t)j * D_HEAD + c4, kf);
+        for (int u = 0; u < 4; ++u) {
+            const int rr = r0 + 8 * u;
+            float f[4] = {0.f, 0.f, 0.f, 0.f};
+            if (rr < r_lim) load4(rows + (size_t)rr * D_HEAD + c4, f);
 #pragma unroll
-        for (int i = 0; i < TQ; ++i) {
-            float s = qu[i][0] * kf[0];
-            s = fmaf(qu[i][1], kf[1], s); s = fmaf(qu[i][2], kf[2], s); s = fmaf(qu[i][3], kf[3], s);
-            s = warp_sum(s);
-            if (lane == 0) sf.ac[i][j] = s;
+            for (int i = 0; i < TQ; ++i) {
+                float v = qq[i][0] * f[0];
+                v = fmaf(qq[i][1], f[1], v); v = fmaf(qq[i][2], f[2], v); v = fmaf(qq[i][3], f[3], v);
+                s[u][i] = v;
+            }
         }
-    }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < TQ; ++i) s[u][i] += __shfl_xor_sync(0xffffffffu, s[u][i], o);
+        if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < TQ; ++i) if (r0 + 8 * u < r_lim) out[i * out_stride + r0 + 8 * u] = s[u][i];
+        }
+    };
+    for (int r0 = warp; r0 < r_end; r0 += 32) dots4(Ps, r0, r_end, qv, &sf.bd[0][0], ATT_MAX_REL);
+    for (int j0 = first + warp; j0 < K; j0 += 32) dots4(Ks, j0, K, qu, &sf.ac[0][0], ATT_MAX_K);
     half_barrier(half);
     // ---- softmax over valid keys; rel-shift = index arithmetic: BD[i][j] = BD_raw[i][L + i - j + T-1] (:391-433) ----
     for (int i = warp; i < T; i += 8) {
@@ -510,7 +536,7 @@ __global__ void __launch_bounds__(256) conv_module_kernel(const ConvModArgs a) {
     NSB_KERNEL_WAIT()
     for (int t = 0; t < T; ++t) {
         const float* row = a.pw1 + ((size_t)b * T + t) * 2 * D_MODEL;
-        const float4 av = *(const float4*)(row + c0), gv = *(const float4*)(row + D_MODEL + c0);
+        const float4 av = ld4_planes<PW1_MAX_PLANES>(row + c0, a.planes, a.plane_stride), gv = ld4_planes<PW1_MAX_PLANES>(row + D_MODEL + c0, a.planes, a.plane_stride);
         win[0][8] = av.x * sigmoid_exact(gv.x); win[1][8] = av.y * sigmoid_exact(gv.y);   // GLU :629-636
         win[2][8] = av.z * sigmoid_exact(gv.z); win[3][8] = av.w * sigmoid_exact(gv.w);
         float cv[4];
