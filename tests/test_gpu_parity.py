@@ -81,8 +81,14 @@ def assert_tokens_match_up_to_near_ties(toks, orc, band):
             ev += 1
         # the divergent decision is evaluation ev (or an earlier blank/non-blank flip right before it): accept if ANY of the
         # evaluations since the last agreed emission has a top-2 gap inside the band
+        # ... or, when the same token is emitted several times in a row (random joint weights do that), anywhere in that run:
+        # one repetition more or fewer leaves the sequences identical until the run ends, so the first differing INDEX sits
+        # later than the flipped DECISION.
         lo = ev
         while lo > 0 and o.eval_token(lo - 1) == 1024:
+            lo -= 1
+        rep = o.eval_token(min(ev, o.n_evals() - 1))
+        while lo > 0 and (o.eval_token(lo - 1) == rep or o.eval_token(lo - 1) == 1024):
             lo -= 1
         gaps = []
         for e in range(lo, min(ev + 1, o.n_evals())):
