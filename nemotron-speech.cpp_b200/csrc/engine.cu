@@ -604,7 +604,8 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
         // Small batches (one 128-row tile): with full-K tiles every CTA pulls the whole activation tile (256 KB) and the launch is
         // bound by per-SM L2->SM ingest. Split-K with 64-wide tiles cuts that to 128 + 64 KB (QKV, 2 slices) / 64 + 32 KB
         // (pointwise-1, 4 slices); the fp32 partial planes are summed, in slice order, by the consumer kernel as it loads them.
-        const int qkv_planes = split_consumers(rows) ? 2 : 1, pw1_planes = split_consumers(rows) ? 4 : 1;
+        const int qkv_planes = split_consumers(rows) ? 2 : 1;
+        const int pw1_planes = 1;          // measured (r01_notes.md): 4 slices save 0.75 us in the GEMM and cost 1.2 us in the conv module -> off
         if (!(skip & SK_QKV)) {
             if (qkv_planes == 1) gemm(a_.p, D_MODEL, L.qkv, rows, nullptr, qkv_.p, 3 * D_MODEL, EPI_NONE, 1.f, OUT_F32);
             else gemm_planes(a_.p, D_MODEL, L.qkv, rows, qkv_.p, qkv_planes);
