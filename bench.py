@@ -122,9 +122,13 @@ def cpu_baseline(threads: int | None, seconds: float = 1.6, streams: int = 2):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
     import synth
-    if threads:
-        O.lib().orc_set_threads(threads)
-    cores = threads or O.lib().orc_get_max_threads()
+    if not threads:                                   # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1: ignore it)
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    O.lib().orc_set_threads(threads)
+    cores = threads
     path = synth.cached_model("f32", N_LAYERS, R=RIGHT_CONTEXT, profile=PROFILE)
     m = O.Model(path, O.MM_REF)
     pcm = [synth.synth_pcm(s, seconds) for s in range(streams)]

@@ -269,9 +269,13 @@ __global__ void __launch_bounds__(NT, 1) rnnt_decode_kernel(const DecodeArgs a) 
     }
     __syncthreads();
 
+    // trace (block 0 only): t[3] = ns spent in prediction-network phases (incl. their 3 grid barriers), t[4] = ns in joint + argmax
+    // phases, t[5] = rounds << 32 | rounds that ran the prediction network
+    unsigned long long tr_pred = 0, tr_joint = 0, tr_rounds = 0, tr_t = 0;
     for (int round = 0;; ++round) {
         // ---------------- prediction network for active streams whose candidate is stale ----------------
         const int n_need = compact(sm, B, [&](int b) { return sm.need[b] != 0 && sm.fi[b] < T; });
+        if (tr_slot >= 0) tr_t = gtime();
         if (n_need > 0) {
             phase_dispatch<MODE_LSTM>(a, sm, 0, n_need, round, ne0);
             grid_barrier(a.barrier, epoch, nblk);
@@ -281,6 +285,7 @@ __global__ void __launch_bounds__(NT, 1) rnnt_decode_kernel(const DecodeArgs a) 
             grid_barrier(a.barrier, epoch, nblk);
             for (int i = tid; i < n_need; i += NT) sm.need[sm.list[i]] = 0;
             __syncthreads();
+            if (tr_slot >= 0) { const unsigned long long t1 = gtime(); tr_pred += t1 - tr_t; tr_t = t1; tr_rounds += 1; }
         }
         // ---------------- joint + argmax ----------------
         const int n_act = compact(sm, B, [&](int b) { return sm.fi[b] < T; });
@@ -303,6 +308,7 @@ __global__ void __launch_bounds__(NT, 1) rnnt_decode_kernel(const DecodeArgs a) 
         }
         if (sm.list[0] == 0) ne0 += 1;                                            // list is ascending: row 0 is first whenever it was evaluated
         __syncthreads();                                                          // state updates visible before the next compaction
+        if (tr_slot >= 0) { tr_joint += gtime() - tr_t; tr_rounds += 1ull << 32; }
     }
     if (blockIdx.x == 0) {
         for (int b = tid; b < B; b += NT) {
@@ -311,7 +317,10 @@ __global__ void __launch_bounds__(NT, 1) rnnt_decode_kernel(const DecodeArgs a) 
             a.out_count[b] = sm.oc[b];
         }
         if (tid == 0 && a.logits_tap_n) *a.logits_tap_n = ne0;
-        if (tid == 0) trace_mark(tr_slot, 2);
+        if (tid == 0 && tr_slot >= 0) {
+            trace_mark(tr_slot, 2);
+            c_trace->rec[tr_slot].t[3] = tr_pred; c_trace->rec[tr_slot].t[4] = tr_joint; c_trace->rec[tr_slot].t[5] = tr_rounds;
+        }
     }
 }
 }  // namespace

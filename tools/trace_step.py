@@ -61,6 +61,9 @@ def main():
                 wait = (t[1] - t[0]) / 1e3; pro = (t[3] - t[1]) / 1e3; mma = (t[4] - t[3]) / 1e3; body = (t[2] - t[4]) / 1e3; total = (t[2] - t[0]) / 1e3
             else:
                 pro = 0.0; wait = (t[1] - t[0]) / 1e3; mma = 0.0; body = (t[2] - t[1]) / 1e3; total = (t[2] - t[0]) / 1e3
+            if tag == "decode" and verbose:
+                print(f"#    decode: {t[5] >> 32} rounds ({t[5] & 0xffffffff} with the prediction network): prediction-network phases {t[3] / 1e3:.1f} us, "
+                      f"joint + argmax phases {t[4] / 1e3:.1f} us")
             key = f"{tag} g={grid}"
             a = agg.setdefault(key, [0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0])
             a[0] += 1; a[1] += 0 if pitch != pitch else pitch; a[2] += pro; a[3] += wait; a[4] += mma; a[5] += body; a[6] += total
