@@ -355,7 +355,7 @@ void Engine::build_pos_tables(const GgufFile& g) {
 void Engine::gemm(const void* A, long long lda, const Weight& W, int M, const float* bias, void* C, long long ldc, int epi, float alpha,
                   int out_type) {
     GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.w_scales = W.scales.p; a.M = M; a.N = W.n_out; a.K = W.n_in; a.bias = bias; a.C = C; a.ldc = ldc;
-    a.epi = epi; a.alpha = alpha; a.out_type = out_type;
+    a.epi = epi; a.alpha = alpha; a.out_type = out_type; a.pair = 1;
     ProfScope ps(this, PC_GEMM);
     if (compute == NSB_COMPUTE_F32) launch_gemm_simt(a, st_);
     else launch_gemm_tc(a, act_type(), st_);
@@ -364,7 +364,7 @@ void Engine::gemm(const void* A, long long lda, const Weight& W, int M, const fl
 
 bool Engine::split_consumers(int rows) const {
     static const bool off = [] { const char* e = getenv("NSB_NO_SPLIT_CONSUMERS"); return e && e[0] == '1'; }();
-    return !off && consumer_planes_ >= 4 && (compute == NSB_COMPUTE_F16 || compute == NSB_COMPUTE_BF16) && rows <= 128;
+    return !off && !pair_gemm_enabled() && consumer_planes_ >= 4 && (compute == NSB_COMPUTE_F16 || compute == NSB_COMPUTE_BF16) && rows <= 128;
 }
 
 // split-K GEMM whose fp32 partial planes C[z][M][N] are left for the consumer kernel to sum (QKV -> attention, pointwise-1 -> conv module)
@@ -742,7 +742,7 @@ float Engine::bench_gemm(int kind, int rows, int bn, int stages, int splits, int
         for (int l = 0; l < n_layers; ++l) {
             Weight& W = pick(layers_[l]);
             GemmArgs a; a.A = W.n_in == D_FF ? big_.p : a_.p; a.lda = W.n_in; a.W = W.data.p; a.w_scales = W.scales.p; a.M = rows; a.N = W.n_out; a.K = W.n_in;
-            a.force_bn = bn; a.force_stages = stages; a.rotate = rotate; a.splits = splits; a.ldc = W.n_out;
+            a.force_bn = bn; a.force_stages = stages; a.rotate = rotate; a.splits = splits; a.ldc = W.n_out; a.pair = splits == 1;
             if (splits > 1) { a.C = part_.p; a.epi = EPI_PARTIAL; a.out_type = OUT_F32; }
             else if (W.n_out == D_FF) { a.C = big_.p; a.epi = EPI_SILU; a.out_type = act_type(); }
             else { a.C = qkv_.p; a.epi = EPI_NONE; a.out_type = OUT_F32; }

@@ -26,6 +26,11 @@ namespace nsb {
 
 NSB_DEFINE_TRACE_BINDER(trace_bind_gemm_tc)
 
+bool pair_gemm_enabled() {
+    static const bool on = [] { const char* e = getenv("NSB_PAIR_GEMM"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 namespace {
 
 constexpr int BM = 128, ROW_BYTES = 128, UMMA_K_BYTES = 32;      // one k-block = one 128-byte swizzle row per tile row; 4 MMAs per k-block
@@ -78,6 +83,30 @@ __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// ---- CTA pair (cta_group::2): one MMA spans two SMs; each CTA stages its half of both operands ----
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+    // executed by both CTAs; the peer bit of the barrier address is cleared so that the bytes are counted on CTA 0's barrier
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(0x1000000000000000ull) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {          // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
@@ -141,10 +170,19 @@ struct TcParams {
 // Epilogue of one 128 x BN tile (4 warps; TMEM lane quarter = warp % 4): tcgen05.ld the fp32 accumulator, apply the fused
 // epilogue, store. Called by warps 2-5 after the accumulator barrier.
 template <int BN>
+__device__ __forceinline__ void tc_epilogue_at(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full, int warp, int row, int n0, int trace_slot);
+
+template <int BN>
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full, int warp, int lane, int m0, int n0, int trace_slot) {
+    tc_epilogue_at<BN>(p, tmem_base, tmem_full, warp, m0 + (warp & 3) * 32 + lane, n0, trace_slot);
+}
+
+// row = global output row of this thread (its TMEM lane is (warp % 4) * 32 + lane), n0 = global column of TMEM column 0,
+// BN = number of accumulator columns this warp reads
+template <int BN>
+__device__ __forceinline__ void tc_epilogue_at(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full, int warp, int row, int n0, int trace_slot) {
         const bool tracer = trace_slot >= 0 && threadIdx.x == 64;
         const int q = warp & 3;
-        const int row = m0 + q * 32 + lane;
         pdl_wait();                                             // C / bias may be produced (or still read) by the previous kernel
         if (tracer) trace_mark(trace_slot, 2);
         mbar_wait(tmem_full, 0);
@@ -320,6 +358,111 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair variant for small batches (one or few 128-row tiles): a cluster of two CTAs on neighbouring SMs computes one
+// 128 x BN tile with tcgen05.mma.cta_group::2 (M = 128 across the pair). CTA r stages rows [64 r, 64 r + 64) of the activation
+// tile and rows [r BN/2, (r+1) BN/2) of the weight tile; the tensor cores of both SMs read both halves of W, each SM
+// accumulates its 64 rows. What this buys at M = 128: a CTA ingests HALF the activation tile (128 KB instead of 256 KB for
+// K = 1024), and L2 -> SM ingest per SM is what bounds these GEMMs.
+//   * the `full` barriers live in CTA 0: both CTAs' TMA loads complete_tx there (cta_group::2 TMA, peer bit of the barrier
+//     address cleared), CTA 0 arms them with the bytes of both halves and issues every MMA;
+//   * tcgen05.commit.cta_group::2 ... multicast arrives on the `empty` / `tmem_full` barriers of BOTH CTAs;
+//   * accumulator layout per CTA (cute tmem_frg_2sm, M_MMA = 64): lanes 0-63 = its 64 rows x columns [0, BN/2),
+//     lanes 64-127 = the same rows x columns [BN/2, BN), BN/2 TMEM columns.
+// ------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct SmemPair {
+    alignas(1024) uint8_t a[STAGES][64 * ROW_BYTES];
+    alignas(1024) uint8_t b[STAGES][(BN / 2) * ROW_BYTES];
+    alignas(8) uint64_t full[STAGES];
+    uint64_t empty[STAGES];
+    uint64_t tmem_full;
+    uint32_t tmem_slot;
+    int trace_slot;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    static_assert(BN % 64 == 0 && BN <= 256, "pair tile: BN/2 accumulator columns per lane half, read 32 at a time");
+    extern __shared__ uint8_t smem_raw[];
+    using S = SmemPair<BN, STAGES>;
+    S& s = *reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();                                    // 0 = leader (issues the MMAs, owns the full barriers)
+    const int n0 = (int)(blockIdx.x >> 1) * BN, m0 = blockIdx.y * BM;
+    constexpr int BK = ROW_BYTES / 2;                                           // 64 elements of 16 bits
+    const int nk = p.K / BK / (int)gridDim.z;
+    const int kb0 = (int)blockIdx.z * nk;
+    constexpr uint32_t TMEM_COLS = BN / 2 < 32 ? 32 : BN / 2;
+    constexpr uint32_t HALF_BYTES = (64 + BN / 2) * ROW_BYTES;                  // what ONE CTA stages per k-block
+
+    if (threadIdx.x == 0) {
+        s.trace_slot = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 ? trace_begin(TR_GEMM_TC) : -1;
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+        mbar_init(&s.tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 2) tmem_alloc_pair(&s.tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                                         // both CTAs' barriers and TMEM are set up before any cross-CTA traffic
+    tc_fence_after();
+    const uint32_t tmem_base = s.tmem_slot;
+    if (threadIdx.x == 0) { pdl_trigger(); trace_mark(s.trace_slot, 1); }
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs, each its halves) =====================
+        if (elect_one()) {
+            const int a_row = m0 + (int)rank * 64, b_row = n0 + (int)rank * (BN / 2);
+            const int pre = nk < STAGES ? nk : STAGES;
+            for (int kb = 0; kb < pre; ++kb) {                                  // weights first: they do not depend on the previous kernel
+                if (rank == 0) mbar_expect_tx(&s.full[kb], 2 * HALF_BYTES);
+                tma_load_2d_pair(s.b[kb], &tmB, &s.full[kb], (kb0 + kb) * BK, b_row);
+            }
+            for (int kb = pre; kb < nk; ++kb) tma_prefetch_2d(&tmB, (kb0 + kb) * BK, b_row);
+            pdl_wait();
+            for (int kb = 0; kb < pre; ++kb) tma_load_2d_pair(s.a[kb], &tmA, &s.full[kb], (kb0 + kb) * BK, a_row);
+            for (int kb = pre; kb < nk; ++kb) {
+                const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&s.empty[st], ph ^ 1);                                // released for both CTAs by the leader's multicast commit
+                if (rank == 0) mbar_expect_tx(&s.full[st], 2 * HALF_BYTES);
+                tma_load_2d_pair(s.a[st], &tmA, &s.full[st], (kb0 + kb) * BK, a_row);
+                tma_load_2d_pair(s.b[st], &tmB, &s.full[st], (kb0 + kb) * BK, b_row);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (rank == 0 && elect_one()) {
+            const uint32_t idesc = make_idesc(p.fmt, BN);                       // M = 128 across the pair, N = BN
+            for (int kb = 0; kb < nk; ++kb) {
+                const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&s.full[st], ph);                                     // both CTAs' halves of this k-block have landed
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(s.a[st]), b_addr = smem_u32(s.b[st]);
+#pragma unroll
+                for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k)
+                    umma_f16_pair(tmem_base, make_desc(a_addr + k * UMMA_K_BYTES), make_desc(b_addr + k * UMMA_K_BYTES), idesc, (kb | k) ? 1u : 0u);
+                umma_commit_pair(&s.empty[st]);
+            }
+            umma_commit_pair(&s.tmem_full);
+        }
+    } else {
+        // ===================== epilogue (both CTAs: 64 rows x BN columns each) =====================
+        const int q = warp & 3;
+        const int row = m0 + (int)rank * 64 + (q & 1) * 32 + lane;              // TMEM lane 32 q + lane
+        tc_epilogue_at<BN / 2>(p, tmem_base, &s.tmem_full, warp, row, n0 + (q >> 1) * (BN / 2), s.trace_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                                         // the peer's MMAs / commits may still touch this CTA's smem and barriers
+    if (warp == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+}
 
 // ------------------------------------------------------------------------------------------
 // Q8_0 weights with the dequantisation fused into the operand path. The weight stays in HBM as the GGUF holds it, split
@@ -544,6 +687,22 @@ void launch_cfg_c(const GemmArgs& a, int fmt, cudaStream_t st) {
     dim3 grid(a.N / BN, (a.M + BM - 1) / BM, a.splits);
     launch_k_cluster(gemm_tc_kernel<BN, STAGES, EB, CL>, grid, dim3(TC_THREADS), smem, st, CL, tmA, tmB, p);
 }
+template <int BN, int STAGES>
+void launch_cfg_pair(const GemmArgs& a, int fmt, cudaStream_t st) {
+    static bool attr_set = false;
+    const size_t smem = sizeof(SmemPair<BN, STAGES>) + 1024;
+    if (!attr_set) {
+        NSB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const CUtensorMap tmA = make_map(a.A, a.M, a.K, a.lda, 64, fmt);
+    const CUtensorMap tmB = make_map(a.W, a.N, a.K, a.K, BN / 2, fmt);
+    const int m_out = a.c_group > 0 ? (a.M / a.c_group) * (a.c_group - a.c_drop) : a.M;
+    TcParams p{a.M, a.N, a.K, a.bias, a.C, a.ldc, a.epi, a.alpha, a.out_type, fmt, 0, a.c_group, a.c_drop, a.C0, m_out};
+    dim3 grid(2 * (a.N / BN), (a.M + BM - 1) / BM, a.splits);
+    launch_k_cluster(gemm_tc_pair_kernel<BN, STAGES>, grid, dim3(TC_THREADS), smem, st, 2, tmA, tmB, p);
+}
+
 template <int BN, int STAGES, int EB>
 void launch_cfg_e(const GemmArgs& a, int fmt, cudaStream_t st) {
     if (a.multicast && multicast_enabled() && (a.N / BN) % 4 == 0) launch_cfg_c<BN, STAGES, EB, 4>(a, fmt, st);
@@ -586,6 +745,7 @@ void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
             case 3205: launch_cfg<32, 5>(a, fmt, st); break;
             case 3208: launch_cfg<32, 8>(a, fmt, st); break;
             case 6404: launch_cfg<64, 4>(a, fmt, st); break;
+            case 6498: if (fmt == 2) throw CudaError("gemm_tc: pair tiles are 16-bit only"); launch_cfg_pair<64, 8>(a, fmt, st); break;
             case 6406: launch_cfg<64, 6>(a, fmt, st); break;
             case 12803: launch_cfg<128, 3>(a, fmt, st); break;
             case 12804: launch_cfg<128, 4>(a, fmt, st); break;
@@ -604,6 +764,7 @@ void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
     // Tile choice (profiles/r01_gemm_tile_sweep*.txt). Small batches stream weights: narrow tiles so that >= ~1 wave of CTAs pulls.
     // Large batches are tensor-bound: wide tiles, and a shared-memory footprint <= ~100 KB so that two CTAs share an SM and one's
     // epilogue overlaps the other's main loop (the kernel has a single TMEM accumulator per CTA).
+    if (fmt != 2 && a.pair && pair_gemm_enabled() && tiles_m == 1 && a.N % 64 == 0) { launch_cfg_pair<64, 8>(a, fmt, st); return; }
     const long long t256 = a.N % 256 == 0 ? (long long)tiles_m * (a.N / 256) : 0, t128 = a.N % 128 == 0 ? (long long)tiles_m * (a.N / 128) : 0;
     if (t256 >= 200) launch_cfg<256, 2>(a, fmt, st);
     else if (t128 >= 200) launch_cfg<128, 3>(a, fmt, st);

@@ -46,7 +46,8 @@ struct GemmArgs {
     // tensor-core kernel only: output row map (rows r with r % c_group < c_drop are not stored, the rest are compacted) and, for
     // EPI_PARTIAL, an optional destination C0 for k-slice 0 (+bias); slices z >= 1 then go to C[z-1]
     int c_group = 0, c_drop = 0; void* C0 = nullptr;
-    int force_bn = 0, force_stages = 0;   // tuning hooks (bench_gemm): pick the tile config explicitly
+    int force_bn = 0, force_stages = 0;   // tuning hooks (bench_gemm): pick the tile config explicitly (stages 98 = CTA-pair tile)
+    int pair = 0;                 // allow the CTA-pair (cta_group::2) tile when the batch is a single 128-row tile
     int multicast = 1;            // allow A-tile multicast over clusters of 4 CTAs along N (experimental, only with NSB_MC=1: measured slower)
     int rotate = 1;               // CTA n starts its k loop at k-block (n mod nk): de-synchronises the A-tile reads of the grid
 };
@@ -73,6 +74,7 @@ struct AttnArgs {
     int B, T;
 };
 void launch_attention(const AttnArgs& a, cudaStream_t st);
+bool pair_gemm_enabled();         // gemm_tc.cu: CTA-pair tiles on (default) / off (NSB_PAIR_GEMM=0)
 
 struct ConvModArgs {
     const float* pw1;             // [planes][M][2048] f32  (a | gate); planes > 1 = split-K partials of the pointwise GEMM, summed on load
