@@ -764,6 +764,8 @@ void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
     // Tile choice (profiles/r01_gemm_tile_sweep*.txt). Small batches stream weights: narrow tiles so that >= ~1 wave of CTAs pulls.
     // Large batches are tensor-bound: wide tiles, and a shared-memory footprint <= ~100 KB so that two CTAs share an SM and one's
     // epilogue overlaps the other's main loop (the kernel has a single TMEM accumulator per CTA).
+    // single 128-row tile, 16-bit operands: CTA-pair tiles (8 stages; 12 / 16 measured slower in the step: the main loop does not
+    // speed up and the next kernel loses its early residency, profiles/r01_notes.md)
     if (fmt != 2 && a.pair && pair_gemm_enabled() && tiles_m == 1 && a.N % 64 == 0) { launch_cfg_pair<64, 8>(a, fmt, st); return; }
     const long long t256 = a.N % 256 == 0 ? (long long)tiles_m * (a.N / 256) : 0, t128 = a.N % 128 == 0 ? (long long)tiles_m * (a.N / 128) : 0;
     if (t256 >= 200) launch_cfg<256, 2>(a, fmt, st);
