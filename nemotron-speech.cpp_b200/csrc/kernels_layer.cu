@@ -166,6 +166,36 @@ __device__ __forceinline__ void load4_planes(const float* p, int planes, long lo
     const float4 v = ld4_planes<QKV_MAX_PLANES>(p, planes, stride); f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
 }
 
+// Sum NV per-lane partial values over the warp by recursive halving: at every exchange the lanes split the values between
+// them, so NV sums cost (NV - 1) + (5 - log2 NV) shuffles instead of 5 NV. On return lane L holds the complete sum of value
+// `idx` (its top log2 NV lane bits, MSB first); lanes that differ only in the lower bits hold copies -- `owner` marks one.
+template <int NV>
+__device__ __forceinline__ float warp_sum_halving(float (&s)[NV], int lane, int& idx, bool& owner) {
+    static_assert(NV == 1 || NV == 2 || NV == 4 || NV == 8 || NV == 16, "power of two");
+    int n = NV, bit = 16;
+    idx = 0;
+#pragma unroll
+    for (int step = 0; step < 5; ++step) {
+        if (n > 1) {
+            const bool hi = (lane & bit) != 0;
+            n >>= 1;
+#pragma unroll
+            for (int k = 0; k < NV / 2; ++k) {
+                if (k < n) {
+                    const float send = hi ? s[k] : s[k + n], keep = hi ? s[k + n] : s[k];
+                    s[k] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+                }
+            }
+            idx = idx * 2 + (hi ? 1 : 0);
+        } else {
+            s[0] += __shfl_xor_sync(0xffffffffu, s[0], bit);
+        }
+        bit >>= 1;
+    }
+    owner = (lane & (32 / NV - 1)) == 0;
+    return s[0];
+}
+
 template <int TQ> struct AttnSmemF {                             // fp32 part of the shared memory (K / V tiles follow)
     float ac[TQ][ATT_MAX_K];                                     // (q+u).k, then probabilities
     float bd[TQ][ATT_MAX_REL];                                   // (q+v).P[r]
@@ -238,12 +268,24 @@ __global__ void __launch_bounds__(256, TQ <= 2 ? 4 : 2) attention_kernel(const A
             for (int r = 0; r < ATT_PROWS; ++r) {
                 const int rr = rb + warp + 8 * r;
                 if (rr < r_end) {
+                    if constexpr (KV == 0) {                                      // strict fp32 mode keeps the original summation order
 #pragma unroll
-                    for (int i = 0; i < TQ; ++i) {
-                        float s = qv[i][0] * pf[r][0];
-                        s = fmaf(qv[i][1], pf[r][1], s); s = fmaf(qv[i][2], pf[r][2], s); s = fmaf(qv[i][3], pf[r][3], s);
-                        s = warp_sum(s);
-                        if (lane == 0) sf.bd[i][rr] = s;
+                        for (int i = 0; i < TQ; ++i) {
+                            float s = qv[i][0] * pf[r][0];
+                            s = fmaf(qv[i][1], pf[r][1], s); s = fmaf(qv[i][2], pf[r][2], s); s = fmaf(qv[i][3], pf[r][3], s);
+                            s = warp_sum(s);
+                            if (lane == 0) sf.bd[i][rr] = s;
+                        }
+                    } else {                                                      // TQ sums per row by recursive halving (the kernel was shuffle-issue bound)
+                        float sv[TQ];
+#pragma unroll
+                        for (int i = 0; i < TQ; ++i) {
+                            float s = qv[i][0] * pf[r][0];
+                            s = fmaf(qv[i][1], pf[r][1], s); s = fmaf(qv[i][2], pf[r][2], s); sv[i] = fmaf(qv[i][3], pf[r][3], s);
+                        }
+                        int idx; bool owner;
+                        const float v = warp_sum_halving<TQ>(sv, lane, idx, owner);
+                        if (owner) sf.bd[idx][rr] = v;
                     }
                 }
             }
@@ -255,12 +297,24 @@ __global__ void __launch_bounds__(256, TQ <= 2 ? 4 : 2) attention_kernel(const A
         for (int j = first + warp; j < K; j += 8) {
             float kf[4];
             load4(Ks + (size_t)j * D_HEAD + c4, kf);
+            if constexpr (KV == 0) {
 #pragma unroll
-            for (int i = 0; i < TQ; ++i) {
-                float s = qu[i][0] * kf[0];
-                s = fmaf(qu[i][1], kf[1], s); s = fmaf(qu[i][2], kf[2], s); s = fmaf(qu[i][3], kf[3], s);
-                s = warp_sum(s);
-                if (lane == 0) sf.ac[i][j] = s;
+                for (int i = 0; i < TQ; ++i) {
+                    float s = qu[i][0] * kf[0];
+                    s = fmaf(qu[i][1], kf[1], s); s = fmaf(qu[i][2], kf[2], s); s = fmaf(qu[i][3], kf[3], s);
+                    s = warp_sum(s);
+                    if (lane == 0) sf.ac[i][j] = s;
+                }
+            } else {
+                float sv[TQ];
+#pragma unroll
+                for (int i = 0; i < TQ; ++i) {
+                    float s = qu[i][0] * kf[0];
+                    s = fmaf(qu[i][1], kf[1], s); s = fmaf(qu[i][2], kf[2], s); sv[i] = fmaf(qu[i][3], kf[3], s);
+                }
+                int idx; bool owner;
+                const float v = warp_sum_halving<TQ>(sv, lane, idx, owner);
+                if (owner) sf.ac[idx][j] = v;
             }
         }
         __syncthreads();
