@@ -549,6 +549,217 @@ static bool attention_pair_enabled() {
     return on;
 }
 
+// ------------------------------------------------------------------------------------------
+// Tensor-core attention for a 16-bit ring and T <= 16 (all four latency modes). The three small GEMMs of a (head, stream) --
+//   AC = (q+u) K^T  [T x K],   BD_raw = (q+v) P^T  [T x (L+2T-1)],   ctx = softmax(..) V  [T x 128]
+// -- run as mma.sync.m16n8k16 (the T query rows sit in one 16-row tile, rows >= T read a shared zero row) with fp32
+// accumulation; operands come out of shared memory with ldmatrix (rows padded to 272 bytes: conflict-free). The scalar kernels
+// above spend ~600 instructions per warp on per-lane partial dot products and warp reductions (issue bound; at T = 7 the
+// 2048 CTAs of a 256-stream step take 90 us per layer); here a stream needs ~250 HMMA in total.
+// (q+u), (q+v) and the probabilities are rounded to the ring dtype before they enter the tensor core -- the same precision
+// class as K, V and P themselves. One CTA = one head x NS streams (NS = 2 for T <= 2: the positional rows are staged once per
+// CTA), 4 warps per stream; everything that does not depend on this step's QKV GEMM is fetched before the dependency wait.
+// ------------------------------------------------------------------------------------------
+constexpr int ATT_RS = D_HEAD + 8;                                // padded row stride (elements) of the 16-bit tiles: 272 bytes
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t (&r)[2], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+                 : "=r"(r[0]), "=r"(r[1]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+template <typename E> __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
+template <> __device__ __forceinline__ void mma_16816<__half>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <> __device__ __forceinline__ void mma_16816<__nv_bfloat16>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void group_barrier(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+struct AttnMmaLayout {                                            // byte offsets inside the dynamic shared memory
+    int kpad, rpad, n_rel;                                        // keys padded to 16, positional rows padded to 8
+    size_t ps, zero, per_stream, ks, vs, qu, qv, pat, ac, bd, total;
+    __host__ __device__ AttnMmaLayout(int T, int ns) {
+        const int K = ATT_L + T;
+        n_rel = ATT_L + 2 * T - 1; kpad = (K + 15) & ~15; rpad = (n_rel + 7) & ~7;
+        const size_t row = ATT_RS * 2;
+        ps = 0; zero = ps + (size_t)rpad * row;
+        const size_t base = zero + row;
+        ks = 0; vs = ks + (size_t)kpad * row; qu = vs + (size_t)kpad * row; qv = qu + (size_t)T * row; pat = qv + (size_t)T * row;
+        ac = pat + (size_t)T * (kpad + 8) * 2; ac = (ac + 15) & ~(size_t)15;
+        bd = ac + (size_t)T * kpad * 4; per_stream = bd + (size_t)T * rpad * 4; per_stream = (per_stream + 15) & ~(size_t)15;
+        ks += base; vs += base; qu += base; qv += base; pat += base; ac += base; bd += base;
+        total = base + (size_t)ns * per_stream;
+    }
+};
+
+template <int KV, int NS>
+__global__ void __launch_bounds__(128 * NS, NS == 2 ? 2 : 3) attention_mma_kernel(const AttnArgs a) {
+    using E = typename KvT<KV>::type;
+    static_assert(KV != 0, "16-bit ring only");
+    constexpr int EPV = 8, VPR = D_HEAD / EPV;                                  // 16-byte vectors: 8 elements, 16 per row
+    extern __shared__ __align__(16) uint8_t att_smem[];
+    const int T = a.T, K = ATT_L + T, Cap = K;
+    const AttnMmaLayout lay(T, NS);
+    const int tid = threadIdx.x, half = NS == 2 ? tid >> 7 : 0, t = tid & 127, warp = t >> 5, lane = t & 31;
+    const int h = blockIdx.x, b = blockIdx.y * NS + half;
+    const bool active = b < a.B;
+    uint8_t* hb = att_smem + (size_t)half * lay.per_stream;
+    E* Ps = reinterpret_cast<E*>(att_smem + lay.ps);                            // [rpad][ATT_RS], shared by the streams of the CTA
+    E* Zero = reinterpret_cast<E*>(att_smem + lay.zero);                        // one all-zero row
+    E* Ks = reinterpret_cast<E*>(hb + lay.ks);                                  // [kpad][ATT_RS]
+    E* Vs = reinterpret_cast<E*>(hb + lay.vs);
+    E* Qu = reinterpret_cast<E*>(hb + lay.qu);                                  // [T][ATT_RS]  (q + pos_bias_u), rounded
+    E* Qv = reinterpret_cast<E*>(hb + lay.qv);
+    E* Pat = reinterpret_cast<E*>(hb + lay.pat);                                // [T][kpad + 8] probabilities, rounded
+    float* Ac = reinterpret_cast<float*>(hb + lay.ac);                          // [T][kpad]
+    float* Bd = reinterpret_cast<float*>(hb + lay.bd);                          // [T][rpad]
+    const int kpad = lay.kpad, rpad = lay.rpad, n_rel = lay.n_rel, pat_rs = kpad + 8;
+    NSB_KERNEL_BEGIN(TR_ATTN)
+    // ---- before the dependency wait: positional rows, cached K / V rows, zero fills ----
+    const E* P = reinterpret_cast<const E*>(a.pos_proj) + h * D_HEAD;
+    for (int e = tid; e < rpad * VPR; e += 128 * NS) {
+        const int r = e / VPR, c = (e % VPR) * EPV;
+        if (r < n_rel) cp_async16(Ps + (size_t)r * ATT_RS + c, P + (size_t)r * D_MODEL + c);
+        else *reinterpret_cast<uint4*>(Ps + (size_t)r * ATT_RS + c) = make_uint4(0, 0, 0, 0);
+    }
+    for (int e = tid; e < VPR; e += 128 * NS) *reinterpret_cast<uint4*>(Zero + e * EPV) = make_uint4(0, 0, 0, 0);
+    int slot = 0, w = 0, first = ATT_L;
+    if (active) { slot = a.slot_of_b[b]; w = a.ring_pos[slot]; first = ATT_L - a.valid_len[slot]; }   // keys j < first are not yet valid (:982-992)
+    const float* qkv = a.qkv + (size_t)b * T * 3 * D_MODEL + h * D_HEAD;
+    E* kring = reinterpret_cast<E*>(a.k_ring) + (size_t)slot * a.slot_stride + h * D_HEAD;
+    E* vring = reinterpret_cast<E*>(a.v_ring) + (size_t)slot * a.slot_stride + h * D_HEAD;
+    auto ring_row = [&](int j) { return (size_t)((w + Cap - ATT_L + j) % Cap) * D_MODEL; };
+    if (active) {
+        for (int e = t; e < kpad * VPR; e += 128) {
+            const int j = e / VPR, c = (e % VPR) * EPV;
+            if (j >= first && j < ATT_L) {
+                const size_t g = ring_row(j) + c;
+                cp_async16(Ks + (size_t)j * ATT_RS + c, kring + g);
+                cp_async16(Vs + (size_t)j * ATT_RS + c, vring + g);
+            } else if (j < first || j >= K) {                                    // not yet valid / padding: zeros (0 x garbage must not be NaN)
+                *reinterpret_cast<uint4*>(Ks + (size_t)j * ATT_RS + c) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(Vs + (size_t)j * ATT_RS + c) = make_uint4(0, 0, 0, 0);
+            }
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const float bu = a.bias_u[h * D_HEAD + t], bv = a.bias_v[h * D_HEAD + t];   // thread t owns head dim t in the staging loops
+    NSB_KERNEL_WAIT()
+    if (active) {
+        for (int i = 0; i < T; ++i) {                                            // q (+ biases) and this chunk's K / V rows: one head dim per thread
+            const float* row = qkv + (size_t)i * 3 * D_MODEL + t;
+            float q = row[0], kn = row[D_MODEL], vn = row[2 * D_MODEL];
+            for (int z = 1; z < a.planes; ++z) {                                 // split-K partial planes of the QKV GEMM, in slice order
+                const float* rz = row + (size_t)z * a.plane_stride;
+                q += rz[0]; kn += rz[D_MODEL]; vn += rz[2 * D_MODEL];
+            }
+            Qu[(size_t)i * ATT_RS + t] = from_f32<E>(q + bu);                    // :503-507
+            Qv[(size_t)i * ATT_RS + t] = from_f32<E>(q + bv);
+            const E ke = from_f32<E>(kn), ve = from_f32<E>(vn);
+            Ks[(size_t)(ATT_L + i) * ATT_RS + t] = ke; Vs[(size_t)(ATT_L + i) * ATT_RS + t] = ve;
+            kring[ring_row(ATT_L + i) + t] = ke; vring[ring_row(ATT_L + i) + t] = ve;   // ring append (replaces concat + roll, :465-484)
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                                              // the only CTA-wide barrier: P / K / V tiles, q and the new rows are in place
+    if (tr_slot >= 0) trace_mark(tr_slot, 3);
+    if (!active) return;
+    const int g = lane >> 2, tq = lane & 3;                                       // mma fragment coordinates
+    // per-lane ldmatrix row addresses of the A operand (16 x 16 tile): row = lane % 8 + 8 * (lane / 8 % 2), column block = lane / 16
+    const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_col = (lane >> 4) * 8;
+    // ---- AC = Qu K^T and BD_raw = Qv P^T: 8-wide column tiles round-robin over the 4 warps ----
+    {
+        const int nt_ac = (K + 7) / 8, nt_bd = rpad / 8;
+        const E* qa_u = a_row < T ? Qu + (size_t)a_row * ATT_RS + a_col : Zero + a_col;
+        const E* qa_v = a_row < T ? Qv + (size_t)a_row * ATT_RS + a_col : Zero + a_col;
+        for (int tile = warp; tile < nt_ac + nt_bd; tile += 4) {
+            const bool is_ac = tile < nt_ac;
+            const int n0 = (is_ac ? tile : tile - nt_ac) * 8;
+            const E* Brows = is_ac ? Ks : Ps;
+            const E* qa = is_ac ? qa_u : qa_v;
+            // B operand: lanes 0-7 -> rows n0.., k 0-7; 8-15 -> k 8-15; 16-23 -> k 16-23; 24-31 -> k 24-31 (two k-steps per ldmatrix.x4)
+            const E* bp = Brows + (size_t)(n0 + (lane & 7)) * ATT_RS + (lane >> 3) * 8;
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ks = 0; ks < D_HEAD / 32; ++ks) {
+                uint32_t bf[4], a0[4], a1[4];
+                ldsm_x4(bf, bp + ks * 32);
+                ldsm_x4(a0, qa + ks * 32);
+                ldsm_x4(a1, qa + ks * 32 + 16);
+                mma_16816<E>(c, a0, bf[0], bf[1]);
+                mma_16816<E>(c, a1, bf[2], bf[3]);
+            }
+            float* out = is_ac ? Ac : Bd;
+            const int ld = is_ac ? kpad : rpad;
+            if (g < T) { out[g * ld + n0 + 2 * tq] = c[0]; out[g * ld + n0 + 2 * tq + 1] = c[1]; }
+            if (g + 8 < T) { out[(g + 8) * ld + n0 + 2 * tq] = c[2]; out[(g + 8) * ld + n0 + 2 * tq + 1] = c[3]; }
+        }
+    }
+    group_barrier(1 + half, 128);
+    // ---- softmax over valid keys; rel-shift = index arithmetic: BD[i][j] = BD_raw[i][L + i - j + T-1] (:391-433) ----
+    const float scale = 0.08838834764831845f;                                   // 1/sqrt(128) :517
+    for (int i = warp; i < T; i += 4) {
+        float mx = -INFINITY;
+        for (int j = first + lane; j < K; j += 32) {
+            const float sc = (Ac[i * kpad + j] + Bd[i * rpad + ATT_L + i - j + T - 1]) * scale;
+            Ac[i * kpad + j] = sc; mx = fmaxf(mx, sc);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = first + lane; j < K; j += 32) { const float e = expf(Ac[i * kpad + j] - mx); Ac[i * kpad + j] = e; sum += e; }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        for (int j = lane; j < kpad; j += 32)
+            Pat[(size_t)i * pat_rs + j] = from_f32<E>(j >= first && j < K ? Ac[i * kpad + j] * inv : 0.f);
+    }
+    group_barrier(1 + half, 128);
+    if (tr_slot >= 0) trace_mark(tr_slot, 4);
+    // ---- ctx = P V: 16 output tiles of 8 head dims, 4 per warp; k runs over the (padded) keys ----
+    {
+        const E* pa = a_row < T ? Pat + (size_t)a_row * pat_rs + a_col : Zero + a_col;   // zero row is 136 elements: a_col + 16 ks stays inside for kpad <= 96
+        for (int tile = warp; tile < D_HEAD / 8; tile += 4) {
+            const int n0 = tile * 8;
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int ks = 0; ks < kpad / 16; ++ks) {
+                uint32_t af[4], bf[2];
+                ldsm_x4(af, pa + ks * 16);
+                ldsm_x2_trans(bf, Vs + (size_t)(ks * 16 + (lane & 15)) * ATT_RS + n0);      // lanes 0-7: keys k0..k0+7, lanes 8-15: k0+8..k0+15
+                mma_16816<E>(c, af, bf[0], bf[1]);
+            }
+            if (g < T) {
+                const size_t o = ((size_t)b * T + g) * D_MODEL + h * D_HEAD + n0 + 2 * tq;
+                store_out(a.ctx, o, c[0], a.out_type); store_out(a.ctx, o + 1, c[1], a.out_type);
+            }
+            if (g + 8 < T) {
+                const size_t o = ((size_t)b * T + g + 8) * D_MODEL + h * D_HEAD + n0 + 2 * tq;
+                store_out(a.ctx, o, c[2], a.out_type); store_out(a.ctx, o + 1, c[3], a.out_type);
+            }
+        }
+    }
+    NSB_KERNEL_EPILOGUE();
+}
+
+template <int KV, int NS>
+static void launch_attention_mma(const AttnArgs& a, cudaStream_t st) {
+    const AttnMmaLayout lay(a.T, NS);
+    static size_t configured = 0;
+    if (lay.total > configured) {
+        NSB_CUDA(cudaFuncSetAttribute(attention_mma_kernel<KV, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+        configured = lay.total;
+    }
+    launch_k(attention_mma_kernel<KV, NS>, dim3(N_HEADS, (a.B + NS - 1) / NS), dim3(128 * NS), lay.total, st, a);
+}
+static bool attention_mma_enabled() {
+    static const bool on = [] { const char* e = getenv("NSB_ATT_MMA"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 template <int KV, int TQ>
 static void launch_attention_tq(const AttnArgs& a, cudaStream_t st) {
     using E = typename KvT<KV>::type;
@@ -563,7 +774,8 @@ static void launch_attention_tq(const AttnArgs& a, cudaStream_t st) {
 template <int KV>
 static void launch_attention_t(const AttnArgs& a, cudaStream_t st) {
     if (a.T > ATT_MAX_T) throw CudaError("attention: att_right_context too large");
-    if constexpr (KV != 0) {                                                      // 16-bit ring, T <= 2: the paired low-latency kernel
+    if constexpr (KV != 0) {                                                      // 16-bit ring: tensor-core kernel (T <= 16), else the paired / tiled scalar kernels
+        if (a.T <= 16 && attention_mma_enabled()) { if (a.T <= 2) launch_attention_mma<KV, 2>(a, st); else launch_attention_mma<KV, 1>(a, st); return; }
         if (a.T <= 2 && attention_pair_enabled()) { if (a.T == 1) launch_attention_pair<KV, 1>(a, st); else launch_attention_pair<KV, 2>(a, st); return; }
     }
     if (a.T == 1) launch_attention_tq<KV, 1>(a, st);
