@@ -652,6 +652,7 @@ __global__ void __launch_bounds__(128 * NS, NS == 2 ? 2 : 3) attention_mma_kerne
     const float bu = a.bias_u[h * D_HEAD + t], bv = a.bias_v[h * D_HEAD + t];   // thread t owns head dim t in the staging loops
     NSB_KERNEL_WAIT()
     if (active) {
+#pragma unroll 2
         for (int i = 0; i < T; ++i) {                                            // q (+ biases) and this chunk's K / V rows: one head dim per thread
             const float* row = qkv + (size_t)i * 3 * D_MODEL + t;
             float q = row[0], kn = row[D_MODEL], vn = row[2 * D_MODEL];
@@ -678,27 +679,44 @@ __global__ void __launch_bounds__(128 * NS, NS == 2 ? 2 : 3) attention_mma_kerne
         const int nt_ac = (K + 7) / 8, nt_bd = rpad / 8;
         const E* qa_u = a_row < T ? Qu + (size_t)a_row * ATT_RS + a_col : Zero + a_col;
         const E* qa_v = a_row < T ? Qv + (size_t)a_row * ATT_RS + a_col : Zero + a_col;
-        for (int tile = warp; tile < nt_ac + nt_bd; tile += 4) {
-            const bool is_ac = tile < nt_ac;
-            const int n0 = (is_ac ? tile : tile - nt_ac) * 8;
-            const E* Brows = is_ac ? Ks : Ps;
-            const E* qa = is_ac ? qa_u : qa_v;
-            // B operand: lanes 0-7 -> rows n0.., k 0-7; 8-15 -> k 8-15; 16-23 -> k 16-23; 24-31 -> k 24-31 (two k-steps per ldmatrix.x4)
-            const E* bp = Brows + (size_t)(n0 + (lane & 7)) * ATT_RS + (lane >> 3) * 8;
-            float c[4] = {0.f, 0.f, 0.f, 0.f};
+        // two column tiles per warp step: two independent accumulator chains hide the ldmatrix / mma latency
+        const int ntot = nt_ac + nt_bd;
+        for (int tile0 = warp; tile0 < ntot; tile0 += 8) {
+            float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+            const E* bp[2]; const E* qa[2]; bool live[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int tile = tile0 + 4 * u;
+                live[u] = tile < ntot;
+                const bool is_ac = tile < nt_ac;
+                const int n0 = live[u] ? (is_ac ? tile : tile - nt_ac) * 8 : 0;
+                // B operand: lanes 0-7 -> rows n0.., k 0-7; 8-15 -> k 8-15; 16-23 -> k 16-23; 24-31 -> k 24-31 (two k-steps per ldmatrix.x4)
+                bp[u] = (is_ac ? Ks : Ps) + (size_t)(n0 + (lane & 7)) * ATT_RS + (lane >> 3) * 8;
+                qa[u] = is_ac ? qa_u : qa_v;
+            }
 #pragma unroll
             for (int ks = 0; ks < D_HEAD / 32; ++ks) {
-                uint32_t bf[4], a0[4], a1[4];
-                ldsm_x4(bf, bp + ks * 32);
-                ldsm_x4(a0, qa + ks * 32);
-                ldsm_x4(a1, qa + ks * 32 + 16);
-                mma_16816<E>(c, a0, bf[0], bf[1]);
-                mma_16816<E>(c, a1, bf[2], bf[3]);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    uint32_t bf[4], a0[4], a1[4];
+                    ldsm_x4(bf, bp[u] + ks * 32);
+                    ldsm_x4(a0, qa[u] + ks * 32);
+                    ldsm_x4(a1, qa[u] + ks * 32 + 16);
+                    mma_16816<E>(c[u], a0, bf[0], bf[1]);
+                    mma_16816<E>(c[u], a1, bf[2], bf[3]);
+                }
             }
-            float* out = is_ac ? Ac : Bd;
-            const int ld = is_ac ? kpad : rpad;
-            if (g < T) { out[g * ld + n0 + 2 * tq] = c[0]; out[g * ld + n0 + 2 * tq + 1] = c[1]; }
-            if (g + 8 < T) { out[(g + 8) * ld + n0 + 2 * tq] = c[2]; out[(g + 8) * ld + n0 + 2 * tq + 1] = c[3]; }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int tile = tile0 + 4 * u;
+                if (!live[u]) continue;
+                const bool is_ac = tile < nt_ac;
+                const int n0 = (is_ac ? tile : tile - nt_ac) * 8;
+                float* out = is_ac ? Ac : Bd;
+                const int ld = is_ac ? kpad : rpad;
+                if (g < T) { out[g * ld + n0 + 2 * tq] = c[u][0]; out[g * ld + n0 + 2 * tq + 1] = c[u][1]; }
+                if (g + 8 < T) { out[(g + 8) * ld + n0 + 2 * tq] = c[u][2]; out[(g + 8) * ld + n0 + 2 * tq + 1] = c[u][3]; }
+            }
         }
     }
     group_barrier(1 + half, 128);
@@ -723,22 +741,30 @@ __global__ void __launch_bounds__(128 * NS, NS == 2 ? 2 : 3) attention_mma_kerne
     // ---- ctx = P V: 16 output tiles of 8 head dims, 4 per warp; k runs over the (padded) keys ----
     {
         const E* pa = a_row < T ? Pat + (size_t)a_row * pat_rs + a_col : Zero + a_col;   // zero row is 136 elements: a_col + 16 ks stays inside for kpad <= 96
-        for (int tile = warp; tile < D_HEAD / 8; tile += 4) {
-            const int n0 = tile * 8;
-            float c[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int ks = 0; ks < kpad / 16; ++ks) {
-                uint32_t af[4], bf[2];
-                ldsm_x4(af, pa + ks * 16);
-                ldsm_x2_trans(bf, Vs + (size_t)(ks * 16 + (lane & 15)) * ATT_RS + n0);      // lanes 0-7: keys k0..k0+7, lanes 8-15: k0+8..k0+15
-                mma_16816<E>(c, af, bf[0], bf[1]);
+        // the warp's four output tiles (head dims 8 (warp + 4 u) ..) together: the probability fragment is loaded once per k-step
+        float c[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { c[u][0] = 0.f; c[u][1] = 0.f; c[u][2] = 0.f; c[u][3] = 0.f; }
+        for (int ks = 0; ks < kpad / 16; ++ks) {
+            uint32_t af[4];
+            ldsm_x4(af, pa + ks * 16);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                uint32_t bf[2];
+                ldsm_x2_trans(bf, Vs + (size_t)(ks * 16 + (lane & 15)) * ATT_RS + (warp + 4 * u) * 8);   // lanes 0-7: keys k0..k0+7, lanes 8-15: k0+8..k0+15
+                mma_16816<E>(c[u], af, bf[0], bf[1]);
             }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int n0 = (warp + 4 * u) * 8;
             if (g < T) {
                 const size_t o = ((size_t)b * T + g) * D_MODEL + h * D_HEAD + n0 + 2 * tq;
-                store_out(a.ctx, o, c[0], a.out_type); store_out(a.ctx, o + 1, c[1], a.out_type);
+                store_out(a.ctx, o, c[u][0], a.out_type); store_out(a.ctx, o + 1, c[u][1], a.out_type);
             }
             if (g + 8 < T) {
                 const size_t o = ((size_t)b * T + g + 8) * D_MODEL + h * D_HEAD + n0 + 2 * tq;
-                store_out(a.ctx, o, c[2], a.out_type); store_out(a.ctx, o + 1, c[3], a.out_type);
+                store_out(a.ctx, o, c[u][2], a.out_type); store_out(a.ctx, o + 1, c[u][3], a.out_type);
             }
         }
     }
