@@ -32,6 +32,38 @@ __device__ __forceinline__ float block_sum_256(float v, float* red /*[8]*/) {
     return t;
 }
 
+// Mean and (biased) variance of the 1024 values a block of 256 threads holds 4 apiece, in ONE block-wide reduction: Chan's
+// pairwise merge of (mean, M2) for equal group sizes -- as accurate as the two-pass form (no E[x^2] - mean^2 cancellation) at
+// half the barriers. Used by the 16-bit engine modes; strict fp32 keeps the reference's two-pass order.
+__device__ __forceinline__ void block_mean_var_256(float v0, float v1, float v2, float v3, float* red /*[16]*/, float& mean, float& var) {
+    float m = ((v0 + v1) + (v2 + v3)) * 0.25f;
+    float M2 = (v0 - m) * (v0 - m) + (v1 - m) * (v1 - m) + (v2 - m) * (v2 - m) + (v3 - m) * (v3 - m);
+    float half_n = 2.0f;                                                          // n / 2 of each of the two groups being merged
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float mo = __shfl_xor_sync(0xffffffffu, m, o), M2o = __shfl_xor_sync(0xffffffffu, M2, o);
+        const float d = mo - m;
+        M2 = (M2 + M2o) + d * d * half_n; m = m + 0.5f * d; half_n *= 2.0f;
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();                                                              // protect red[] reuse
+    if (l == 0) { red[2 * w] = m; red[2 * w + 1] = M2; }
+    __syncthreads();
+    float mm[8], MM[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { mm[i] = red[2 * i]; MM[i] = red[2 * i + 1]; }
+#pragma unroll
+    for (int n = 8; n > 1; n >>= 1) {                                             // 8 warps of 128 values -> 4 x 256 -> 2 x 512 -> 1024
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float d = mm[2 * i + 1] - mm[2 * i];
+            MM[i] = (MM[2 * i] + MM[2 * i + 1]) + d * d * half_n; mm[i] = mm[2 * i] + 0.5f * d;
+        }
+        half_n *= 2.0f;
+    }
+    mean = mm[0]; var = MM[0] * (1.0f / D_MODEL);
+}
+
 // LayerNorm over rows of 1024, eps 1e-5, two-pass (mean, then variance of centred values) like ggml_norm.
 // One CTA (256 threads x 4 channels) per row.
 __device__ __forceinline__ float4 load_x_reduced(float* x, size_t o, const PartialSum& ps, int rows) {
@@ -52,14 +84,18 @@ __device__ __forceinline__ float4 load_x_reduced(float* x, size_t o, const Parti
 __global__ void __launch_bounds__(256) layernorm_kernel(float* x, const float* __restrict__ g,
                                                         const float* __restrict__ b, void* y, int out_type, const PartialSum ps) {
     NSB_KERNEL_BEGIN(TR_LN)
-    __shared__ float red[8];
+    __shared__ float red[16];
     const int row = blockIdx.x, c = threadIdx.x * 4;
     const float4 gg = *(const float4*)(g + c), bb = *(const float4*)(b + c);    // static: before the dependency wait
     NSB_KERNEL_WAIT()
     const float4 v = load_x_reduced(x, (size_t)row * D_MODEL + c, ps, gridDim.x);
-    const float mean = block_sum_256(v.x + v.y + v.z + v.w, red) * (1.0f / D_MODEL);
+    float mean, var;
+    if (out_type == OUT_F32) {
+        mean = block_sum_256(v.x + v.y + v.z + v.w, red) * (1.0f / D_MODEL);
+        const float e0 = v.x - mean, e1 = v.y - mean, e2 = v.z - mean, e3 = v.w - mean;
+        var = block_sum_256(e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3, red) * (1.0f / D_MODEL);
+    } else block_mean_var_256(v.x, v.y, v.z, v.w, red, mean, var);
     const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
-    const float var = block_sum_256(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3, red) * (1.0f / D_MODEL);
     const float rs = 1.0f / sqrtf(var + 1e-5f);
     const size_t o = (size_t)row * D_MODEL + c;
     const float o0 = d0 * rs * gg.x + bb.x, o1 = d1 * rs * gg.y + bb.y, o2 = d2 * rs * gg.z + bb.z, o3 = d3 * rs * gg.w + bb.w;
@@ -77,24 +113,31 @@ __global__ void __launch_bounds__(256) layernorm2_kernel(float* x, const float* 
                                                          const float* __restrict__ g2, const float* __restrict__ b2,
                                                          void* y2, int out_type, const PartialSum ps) {
     NSB_KERNEL_BEGIN(TR_LN2)
-    __shared__ float red[8];
+    __shared__ float red[16];
     const int row = blockIdx.x, c = threadIdx.x * 4;
     const size_t o = (size_t)row * D_MODEL + c;
+    const bool one_pass = out_type != OUT_F32;
     float4 gg = *(const float4*)(g1 + c), bb = *(const float4*)(b1 + c);       // static: before the dependency wait
     float4 gg2 = make_float4(0.f, 0.f, 0.f, 0.f), bb2 = gg2;
     if (y2 != nullptr) { gg2 = *(const float4*)(g2 + c); bb2 = *(const float4*)(b2 + c); }
     NSB_KERNEL_WAIT()
     float4 v = load_x_reduced(x, o, ps, gridDim.x);
-    float mean = block_sum_256(v.x + v.y + v.z + v.w, red) * (1.0f / D_MODEL);
-    float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
-    float var = block_sum_256(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3, red) * (1.0f / D_MODEL);
+    float mean, var, d0, d1, d2, d3;
+    auto stats = [&]() {
+        if (one_pass) block_mean_var_256(v.x, v.y, v.z, v.w, red, mean, var);
+        else {
+            mean = block_sum_256(v.x + v.y + v.z + v.w, red) * (1.0f / D_MODEL);
+            const float e0 = v.x - mean, e1 = v.y - mean, e2 = v.z - mean, e3 = v.w - mean;
+            var = block_sum_256(e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3, red) * (1.0f / D_MODEL);
+        }
+        d0 = v.x - mean; d1 = v.y - mean; d2 = v.z - mean; d3 = v.w - mean;
+    };
+    stats();
     float rs = 1.0f / sqrtf(var + 1e-5f);
     v = make_float4(d0 * rs * gg.x + bb.x, d1 * rs * gg.y + bb.y, d2 * rs * gg.z + bb.z, d3 * rs * gg.w + bb.w);
     *(float4*)(x + o) = v;
     if (y2 == nullptr) { NSB_KERNEL_EPILOGUE(); return; }                        // last layer: no following norm (uniform branch)
-    mean = block_sum_256(v.x + v.y + v.z + v.w, red) * (1.0f / D_MODEL);
-    d0 = v.x - mean; d1 = v.y - mean; d2 = v.z - mean; d3 = v.w - mean;
-    var = block_sum_256(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3, red) * (1.0f / D_MODEL);
+    stats();
     rs = 1.0f / sqrtf(var + 1e-5f);
     gg = gg2; bb = bb2;
     const float o0 = d0 * rs * gg.x + bb.x, o1 = d1 * rs * gg.y + bb.y, o2 = d2 * rs * gg.z + bb.z, o3 = d3 * rs * gg.w + bb.w;
@@ -822,7 +865,7 @@ void launch_attention(const AttnArgs& a, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv_module_kernel(const ConvModArgs a) {
     NSB_KERNEL_BEGIN(TR_CONVMOD)                                                  // taps, conv state (written by this layer's kernel of earlier steps only), LN affine: pre-wait
-    __shared__ float red[8];
+    __shared__ float red[16];
     const int b = blockIdx.x, c0 = threadIdx.x * 4, T = a.T;
     const int slot = a.slot_of_b[b];
     float* cache = a.conv_cache + (size_t)slot * a.slot_stride;
@@ -841,9 +884,14 @@ __global__ void __launch_bounds__(256) conv_module_kernel(const ConvModArgs a) {
     const float4 g4 = *(const float4*)(a.ln_g + c0), b4 = *(const float4*)(a.ln_b + c0);
     const float lg[4] = {g4.x, g4.y, g4.z, g4.w}, lb[4] = {b4.x, b4.y, b4.z, b4.w};
     NSB_KERNEL_WAIT()
+    const float* row0 = a.pw1 + (size_t)b * T * 2 * D_MODEL;
+    float4 av = ld4_planes<PW1_MAX_PLANES>(row0 + c0, a.planes, a.plane_stride), gv = ld4_planes<PW1_MAX_PLANES>(row0 + D_MODEL + c0, a.planes, a.plane_stride);
     for (int t = 0; t < T; ++t) {
-        const float* row = a.pw1 + ((size_t)b * T + t) * 2 * D_MODEL;
-        const float4 av = ld4_planes<PW1_MAX_PLANES>(row + c0, a.planes, a.plane_stride), gv = ld4_planes<PW1_MAX_PLANES>(row + D_MODEL + c0, a.planes, a.plane_stride);
+        float4 av_n = av, gv_n = gv;
+        if (t + 1 < T) {                                                         // next row's loads overlap this row's reductions
+            const float* rn = row0 + (size_t)(t + 1) * 2 * D_MODEL;
+            av_n = ld4_planes<PW1_MAX_PLANES>(rn + c0, a.planes, a.plane_stride); gv_n = ld4_planes<PW1_MAX_PLANES>(rn + D_MODEL + c0, a.planes, a.plane_stride);
+        }
         win[0][8] = av.x * sigmoid_exact(gv.x); win[1][8] = av.y * sigmoid_exact(gv.y);   // GLU :629-636
         win[2][8] = av.z * sigmoid_exact(gv.z); win[3][8] = av.w * sigmoid_exact(gv.w);
         float cv[4];
@@ -854,11 +902,16 @@ __global__ void __launch_bounds__(256) conv_module_kernel(const ConvModArgs a) {
             for (int k = 1; k < CONV_K; ++k) acc = fmaf(win[u][k], wk[u][k], acc);
             cv[u] = acc;
         }
-        const float mean = block_sum_256(cv[0] + cv[1] + cv[2] + cv[3], red) * (1.0f / D_MODEL);     // LN :643-645
-        float dd[4]; float sq = 0.f;
+        float mean, var, dd[4];                                                  // LN :643-645
+        if (a.out_type == OUT_F32) {
+            mean = block_sum_256(cv[0] + cv[1] + cv[2] + cv[3], red) * (1.0f / D_MODEL);
+            float sq = 0.f;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { dd[u] = cv[u] - mean; sq += dd[u] * dd[u]; }
-        const float var = block_sum_256(sq, red) * (1.0f / D_MODEL);
+            for (int u = 0; u < 4; ++u) { const float e = cv[u] - mean; sq += e * e; }
+            var = block_sum_256(sq, red) * (1.0f / D_MODEL);
+        } else block_mean_var_256(cv[0], cv[1], cv[2], cv[3], red, mean, var);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dd[u] = cv[u] - mean;
         const float rs = 1.0f / sqrtf(var + 1e-5f);
         const size_t o = ((size_t)b * T + t) * D_MODEL + c0;
 #pragma unroll
@@ -867,6 +920,7 @@ __global__ void __launch_bounds__(256) conv_module_kernel(const ConvModArgs a) {
         for (int u = 0; u < 4; ++u)
 #pragma unroll
             for (int k = 0; k < CONV_K - 1; ++k) win[u][k] = win[u][k + 1];
+        av = av_n; gv = gv_n;
     }
 #pragma unroll
     for (int k = 0; k < CONV_K - 1; ++k)                                         // new cache = last 8 rows of xp :368-381
