@@ -118,9 +118,9 @@ void nsb_engine_get_stats(const nsb_engine* e, nsb_stats* out);
 
 /* ---- benchmarking hooks (device-resident inputs; no PCIe inside the timed region) --------
  * nsb_bench_prepare: open `n_streams` streams, warm their caches by running `warm_chunks` chunks
- * of synthetic audio, and stage one more chunk of PCM per stream in HBM.
- * nsb_bench_step: run ONE batched step over all those streams from the staged PCM (state
- * advances; tokens are produced and discarded). Returns device ms of the step via *ms. */
+ * of synthetic audio, and stage every further full chunk of PCM the caller supplied (at least one, at most 16) in HBM.
+ * nsb_bench_step: run ONE batched step over all those streams from the staged PCM, cycling through the staged chunks
+ * (state advances; tokens are produced and discarded). Returns device ms of the step via *ms. */
 int nsb_bench_prepare(nsb_engine* e, int n_streams, const int16_t* pcm, int samples_per_stream, int warm_chunks);
 int nsb_bench_step(nsb_engine* e, float* ms);
 /* n steps enqueued back to back (no host synchronisation in between), one CUDA event between consecutive steps:

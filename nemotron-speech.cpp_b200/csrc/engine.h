@@ -159,7 +159,8 @@ private:
     std::vector<int> inflight_;       // batch -> stream slot of the step launched by step_begin()
 
     // ---- bench ----
-    DevBuf bench_pcm_; int bench_B_ = 0;
+    DevBuf bench_pcm_; int bench_B_ = 0, bench_n_ = 1; long long bench_i_ = 0;   // [bench_n_][bench_B_][rl_] staged chunks, cycled
+    const int16_t* bench_next_pcm();
     // ---- per-launch profiling (bench_profile only) ----
     struct ProfRec { int cls; cudaEvent_t a, b; };
     bool profiling_ = false; std::vector<ProfRec> prof_; std::vector<cudaEvent_t> ev_pool_; size_t ev_used_ = 0;
