@@ -583,12 +583,21 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int pz = 0; pz < BN / 32; ++pz) {
                 const int r = pz * 32 + (t >> 2);
-                const int4 raw = *reinterpret_cast<const int4*>(&s.q[st][r * 64 + c * 16]);
-                const float d = __half2float(s.sc[r * per_row + kk * 2 + (c >> 1)]);
-                const int8_t* qv = reinterpret_cast<const int8_t*>(&raw);
+                const uint4 raw = *reinterpret_cast<const uint4*>(&s.q[st][r * 64 + c * 16]);
+                const __half2 d2 = __half2half2(s.sc[r * per_row + kk * 2 + (c >> 1)]);
+                // int8 -> fp16 without integer conversions: q + 128 as the low mantissa bits of 1024.0 (0x6400 | byte), minus 1152;
+                // then ONE fp16 multiply by the block scale = fp16(d) * q rounded once, exactly the value a load-time dequantisation
+                // to fp16 holds. 7 instructions per 4 weights (the conversion path was what bound this kernel).
+                const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+                const __half2 off = __floats2half2_rn(1152.0f, 1152.0f);
                 __half2 h[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(d * (float)qv[2 * i], d * (float)qv[2 * i + 1]);
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t x = w4[i] ^ 0x80808080u;
+                    const uint32_t lo = __byte_perm(x, 0x64646464u, 0x5140), hi = __byte_perm(x, 0x64646464u, 0x5342);
+                    h[2 * i] = __hmul2(__hsub2(*reinterpret_cast<const __half2*>(&lo), off), d2);
+                    h[2 * i + 1] = __hmul2(__hsub2(*reinterpret_cast<const __half2*>(&hi), off), d2);
+                }
                 uint8_t* row = &s.b[st][r * ROW_BYTES];
                 *reinterpret_cast<uint4*>(row + (((2 * c) ^ (r & 7)) << 4)) = *reinterpret_cast<uint4*>(&h[0]);      // SWIZZLE_128B: chunk ^= row % 8
                 *reinterpret_cast<uint4*>(row + (((2 * c + 1) ^ (r & 7)) << 4)) = *reinterpret_cast<uint4*>(&h[4]);
