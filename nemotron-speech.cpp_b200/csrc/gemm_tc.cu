@@ -35,6 +35,7 @@ namespace {
 
 constexpr int BM = 128, ROW_BYTES = 128, UMMA_K_BYTES = 32;      // one k-block = one 128-byte swizzle row per tile row; 4 MMAs per k-block
 constexpr int TC_THREADS = 192;
+constexpr int Q8_THREADS = 320, Q8_DEQ = 256;                    // Q8_0 kernel: warps 2-9 dequantise (warps 2-5 also run the epilogue)
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -487,7 +488,7 @@ struct SmemQ8 {
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(Q8_THREADS, 1)
 gemm_q8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmQ, const __half* __restrict__ scales,
                const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -504,7 +505,7 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (threadIdx.x == 0) {
         s.trace_slot = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 ? trace_begin(TR_GEMM_Q8) : -1;
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.bready[i], 128); mbar_init(&s.empty[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.bready[i], Q8_DEQ); mbar_init(&s.empty[i], 1); }
         mbar_init(&s.tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -518,12 +519,12 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const __half* src0 = scales + (size_t)n0 * (p.K / 32) + (size_t)kb0 * 2;
         if ((nk & 1) == 0) {                                     // 8-byte vectors: one round trip for the whole tile
             const int vpr = per_row / 4;
-            for (int e = t; e < BN * vpr; e += 128) {
+            for (int e = t; e < BN * vpr; e += Q8_DEQ) {
                 const int r = e / vpr, j = e % vpr;
                 *reinterpret_cast<uint2*>(&s.sc[r * per_row + j * 4]) = __ldg(reinterpret_cast<const uint2*>(src0 + (size_t)r * (p.K / 32) + j * 4));
             }
         } else {
-            for (int e = t; e < BN * per_row; e += 128) {
+            for (int e = t; e < BN * per_row; e += Q8_DEQ) {
                 const int r = e / per_row, j = e % per_row;
                 s.sc[r * per_row + j] = src0[(size_t)r * (p.K / 32) + j];
             }
@@ -574,15 +575,16 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ===================== dequantiser (then epilogue) =====================
-        const int t = threadIdx.x - 64;                          // 0..127: 32 rows x 4 sixteen-byte chunks per pass
+        const int t = threadIdx.x - 64;                          // 0..255: 64 rows x 4 sixteen-byte chunks per pass
         const int c = t & 3, per_row = 2 * nk;
         for (int kb = 0; kb < nk; ++kb) {
             const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
             const int kk = (kb + rot) % nk;                     // k-block of this stage within the CTA's range
             mbar_wait(&s.full[st], ph);
 #pragma unroll
-            for (int pz = 0; pz < BN / 32; ++pz) {
-                const int r = pz * 32 + (t >> 2);
+            for (int pz = 0; pz < (BN + 63) / 64; ++pz) {
+                const int r = pz * 64 + (t >> 2);
+                if (BN % 64 != 0 && r >= BN) continue;                             // BN = 32: only the first 128 threads have a row
                 const uint4 raw = *reinterpret_cast<const uint4*>(&s.q[st][r * 64 + c * 16]);
                 const __half2 d2 = __half2half2(s.sc[r * per_row + kk * 2 + (c >> 1)]);
                 // int8 -> fp16 without integer conversions: q + 128 as the low mantissa bits of 1024.0 (0x6400 | byte), minus 1152;
@@ -605,7 +607,7 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to the tensor core
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s.bready[st])) : "memory");
         }
-        tc_epilogue<BN>(p, tmem_base, &s.tmem_full, warp, lane, m0, n0, s.trace_slot);
+        if (warp < 6) tc_epilogue<BN>(p, tmem_base, &s.tmem_full, warp, lane, m0, n0, s.trace_slot);
     }
     tc_fence_before();
     __syncthreads();
@@ -670,7 +672,7 @@ void launch_cfg_q8(const GemmArgs& a, cudaStream_t st) {
     const int m_out = a.c_group > 0 ? (a.M / a.c_group) * (a.c_group - a.c_drop) : a.M;
     TcParams p{a.M, a.N, a.K, a.bias, a.C, a.ldc, a.epi, a.alpha, a.out_type, 0, a.rotate, a.c_group, a.c_drop, a.C0, m_out};
     dim3 grid(a.N / BN, (a.M + BM - 1) / BM, a.splits);
-    launch_k(gemm_q8_kernel<BN, STAGES>, grid, dim3(TC_THREADS), smem, st, tmA, tmQ, (const __half*)a.w_scales, p);
+    launch_k(gemm_q8_kernel<BN, STAGES>, grid, dim3(Q8_THREADS), smem, st, tmA, tmQ, (const __half*)a.w_scales, p);
 }
 
 // Experimental, off by default: on B200 the multicast variant measured SLOWER than per-CTA A loads at M = 128
