@@ -298,6 +298,7 @@ void Engine::alloc_state() {
     // small batches: the QKV / pointwise-1 GEMMs run split-K and leave their partial planes for the consumer kernel to sum
     const size_t planes = Mrows <= SPLIT_CONSUMER_MAX_ROWS ? 4 : 1;
     consumer_planes_ = (int)planes;
+    if (compute == NSB_COMPUTE_Q8_0) wscratch_.alloc((size_t)D_FF * D_MODEL * 2, false);   // largest layer matrix as fp16 (q8_predequant)
     qkv_.alloc(planes * Mrows * 3 * D_MODEL * 4);
     pw1_.alloc(planes * Mrows * 2 * D_MODEL * 4);
     encp_.alloc(Mrows * JOINT * 4);
@@ -357,9 +358,22 @@ void Engine::gemm(const void* A, long long lda, const Weight& W, int M, const fl
     GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.w_scales = W.scales.p; a.M = M; a.N = W.n_out; a.K = W.n_in; a.bias = bias; a.C = C; a.ldc = ldc;
     a.epi = epi; a.alpha = alpha; a.out_type = out_type; a.pair = 1;
     ProfScope ps(this, PC_GEMM);
+    q8_predequant(W, M, a);
     if (compute == NSB_COMPUTE_F32) launch_gemm_simt(a, st_);
     else launch_gemm_tc(a, act_type(), st_);
     count_launch();
+}
+
+// Q8_0 mode, batches of >= 4 row tiles: dequantise the matrix once into an fp16 scratch (L2-resident hand-over to the GEMM that
+// follows) instead of once per m-tile inside the fused kernel. Small batches keep the fused operand path (weight streaming).
+void Engine::q8_predequant(const Weight& W, int M, GemmArgs& a) {
+    static const int min_rows = [] { const char* e = getenv("NSB_Q8_PREDEQUANT_ROWS"); return e ? atoi(e) : 512; }();
+    if (compute != NSB_COMPUTE_Q8_0 || !W.scales.p || M < min_rows) return;
+    const size_t bytes = (size_t)W.n_out * W.n_in * 2;
+    if (wscratch_.bytes < bytes) throw std::runtime_error("q8_predequant: scratch not allocated");   // sized in alloc_state (no allocation inside a graph capture)
+    launch_dequant_q8(W.data.p, W.scales.p, wscratch_.p, W.n_out, W.n_in, st_);
+    count_launch();
+    a.W = wscratch_.p; a.w_scales = nullptr; a.w_dynamic = 1; a.pair = 0;
 }
 
 bool Engine::split_consumers(int rows) const {
@@ -387,7 +401,7 @@ void Engine::gemm_residual(const void* A, long long lda, const Weight& W, int M,
     if (splits == 1) { gemm(A, lda, W, M, nullptr, x, D_MODEL, EPI_RESID, alpha, OUT_F32); return; }
     GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.w_scales = W.scales.p; a.M = M; a.N = W.n_out; a.K = W.n_in; a.C = part_.p; a.ldc = D_MODEL;
     a.epi = EPI_PARTIAL; a.out_type = OUT_F32; a.splits = splits;
-    { ProfScope ps(this, PC_GEMM); launch_gemm_tc(a, act_type(), st_); }
+    { ProfScope ps(this, PC_GEMM); q8_predequant(W, M, a); launch_gemm_tc(a, act_type(), st_); }
     count_launch();
     pending_.part = part_.as<float>(); pending_.n = splits; pending_.alpha = alpha;
 }

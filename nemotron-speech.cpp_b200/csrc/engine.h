@@ -115,6 +115,7 @@ private:
     // x += alpha * A W^T. Small batches: split-K into the workspace, reduction folded into the next LayerNorm (pending_).
     void gemm_residual(const void* A, long long lda, const Weight& W, int M, float* x, float alpha);
     bool split_consumers(int rows) const;
+    void q8_predequant(const Weight& W, int M, GemmArgs& a);
     void gemm_planes(const void* A, long long lda, const Weight& W, int M, void* C, int planes);
     PartialSum pending_{};
     void run_step_kernels(int B, const int16_t* d_pcm);      // everything between PCM-in-HBM and tokens-in-HBM
@@ -159,6 +160,7 @@ private:
     std::vector<int> inflight_;       // batch -> stream slot of the step launched by step_begin()
 
     // ---- bench ----
+    DevBuf wscratch_;                 // fp16 copy of ONE Q8_0 matrix (large batches), rewritten before every GEMM that uses it
     DevBuf bench_pcm_; int bench_B_ = 0, bench_n_ = 1; long long bench_i_ = 0;   // [bench_n_][bench_B_][rl_] staged chunks, cycled
     const int16_t* bench_next_pcm();
     // ---- per-launch profiling (bench_profile only) ----

@@ -18,6 +18,7 @@
 // Rows of A beyond M are zero-filled by TMA (tensor map extent = M), so small batches need no padding.
 #include <cuda.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "kernels.cuh"
@@ -166,6 +167,7 @@ struct TcParams {
     const float* bias; void* C; long long ldc; int epi; float alpha; int out_type; int fmt; int rot;
     int c_group, c_drop;       // output row map: row r -> (r / c_group) * (c_group - c_drop) + r % c_group - c_drop, rows with r % c_group < c_drop are dropped
     void* C0; int m_out;       // EPI_PARTIAL: slice 0 (+bias) goes to C0 when set, slices z >= 1 to C + (z-1) * m_out * ldc
+    int w_dyn = 0;             // W is produced by the previous kernel (Q8_0 weights dequantised once per launch): no weight TMA before the dependency wait
 };
 
 // Epilogue of one 128 x BN tile (4 warps; TMEM lane quarter = warp % 4): tcgen05.ld the fp32 accumulator, apply the fused
@@ -314,12 +316,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // Weights do not depend on the previous kernel: fill the ring with W tiles BEFORE waiting for it (PDL), so
             // HBM streaming of this GEMM overlaps the tail of its predecessor; A tiles follow after the wait.
             const int pre = nk < STAGES ? nk : STAGES;
+            if (p.w_dyn) pdl_wait();
             for (int kb = 0; kb < pre; ++kb) {
                 mbar_expect_tx(&s.full[kb], STAGE_BYTES);
                 tma_load_2d(s.b[kb], &tmB, &s.full[kb], (kb0 + (kb + rot) % nk) * BK, n0);
             }
-            for (int kb = pre; kb < nk; ++kb) tma_prefetch_2d(&tmB, (kb0 + (kb + rot) % nk) * BK, n0);   // rest of the slab: HBM -> L2 now
-            pdl_wait();
+            if (!p.w_dyn) {
+                for (int kb = pre; kb < nk; ++kb) tma_prefetch_2d(&tmB, (kb0 + (kb + rot) % nk) * BK, n0);   // rest of the slab: HBM -> L2 now
+                pdl_wait();
+            }
             for (int kb = 0; kb < pre; ++kb) load_a(kb, (kb0 + (kb + rot) % nk) * BK);
             for (int kb = pre; kb < nk; ++kb) {
                 const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
@@ -694,7 +699,7 @@ void launch_cfg_c(const GemmArgs& a, int fmt, cudaStream_t st) {
     const CUtensorMap tmA = make_map(a.A, a.M, a.K, a.lda, BM / CL, fmt);
     const CUtensorMap tmB = make_map(a.W, a.N, a.K, a.K, BN, fmt);
     const int m_out = a.c_group > 0 ? (a.M / a.c_group) * (a.c_group - a.c_drop) : a.M;
-    TcParams p{a.M, a.N, a.K, a.bias, a.C, a.ldc, a.epi, a.alpha, a.out_type, fmt, a.rotate, a.c_group, a.c_drop, a.C0, m_out};
+    TcParams p{a.M, a.N, a.K, a.bias, a.C, a.ldc, a.epi, a.alpha, a.out_type, fmt, a.rotate, a.c_group, a.c_drop, a.C0, m_out, a.w_dynamic};
     dim3 grid(a.N / BN, (a.M + BM - 1) / BM, a.splits);
     launch_k_cluster(gemm_tc_kernel<BN, STAGES, EB, CL>, grid, dim3(TC_THREADS), smem, st, CL, tmA, tmB, p);
 }
@@ -728,6 +733,41 @@ void launch_cfg(const GemmArgs& a, int fmt, cudaStream_t st) {
     } else launch_cfg_e<BN, STAGES, 2>(a, fmt, st);
 }
 }  // namespace
+
+// Q8_0 planes -> fp16 [N][K], once per GEMM launch, for batches of many 128-row tiles: there every m-tile CTA of the fused
+// kernel repeats the dequantisation of the same weight tile (14x at 1792 rows) and the dequant warps, not HBM, set the pace.
+// The 2-8 MB fp16 copy is consumed by the next kernel straight out of L2; HBM still only sees the int8 + scale planes.
+// Same arithmetic as the fused path (fp16(d) * q, one rounding): bit-identical operand values.
+namespace {
+__global__ void __launch_bounds__(256) dequant_q8_kernel(const uint4* __restrict__ q, const __half* __restrict__ sc, uint4* __restrict__ out,
+                                                         size_t n_vec, int K) {
+    NSB_KERNEL_PROLOGUE(TR_OTHER)                                                 // the scratch may still be read by the previous GEMM
+    const __half2 off = __floats2half2_rn(1152.0f, 1152.0f);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 raw = q[i];
+        const size_t e0 = i * 16, row = e0 / (size_t)K, col = e0 % (size_t)K;
+        const __half2 d2 = __half2half2(sc[row * (size_t)(K / 32) + col / 32]);
+        const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+        __half2 h[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t x = w4[j] ^ 0x80808080u;
+            const uint32_t lo = __byte_perm(x, 0x64646464u, 0x5140), hi = __byte_perm(x, 0x64646464u, 0x5342);
+            h[2 * j] = __hmul2(__hsub2(*reinterpret_cast<const __half2*>(&lo), off), d2);
+            h[2 * j + 1] = __hmul2(__hsub2(*reinterpret_cast<const __half2*>(&hi), off), d2);
+        }
+        out[2 * i] = *reinterpret_cast<uint4*>(&h[0]);
+        out[2 * i + 1] = *reinterpret_cast<uint4*>(&h[4]);
+    }
+    NSB_KERNEL_EPILOGUE();
+}
+}  // namespace
+void launch_dequant_q8(const void* q, const void* scales, void* out_f16, int N, int K, cudaStream_t st) {
+    if (K % 32 != 0) throw CudaError("dequant_q8: K must be a multiple of 32");
+    const size_t n_vec = (size_t)N * K / 16;
+    const int blocks = (int)std::min<size_t>((n_vec + 255) / 256, 148 * 8);
+    launch_k(dequant_q8_kernel, dim3(blocks), dim3(256), 0, st, (const uint4*)q, (const __half*)scales, (uint4*)out_f16, n_vec, K);
+}
 
 // in_type: OUT_F16 / OUT_BF16 / OUT_F32 (= tf32) -- type of A and W. Requires K % 64 == 0 (tf32: 32), N % 32 == 0, 16-byte aligned rows.
 void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
@@ -777,7 +817,7 @@ void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
     // epilogue overlaps the other's main loop (the kernel has a single TMEM accumulator per CTA).
     // single 128-row tile, 16-bit operands: CTA-pair tiles (8 stages; 12 / 16 measured slower in the step: the main loop does not
     // speed up and the next kernel loses its early residency, profiles/r01_notes.md)
-    if (fmt != 2 && a.pair && pair_gemm_enabled() && tiles_m == 1 && a.N % 64 == 0) { launch_cfg_pair<64, 8>(a, fmt, st); return; }
+    if (fmt != 2 && a.pair && !a.w_dynamic && pair_gemm_enabled() && tiles_m == 1 && a.N % 64 == 0) { launch_cfg_pair<64, 8>(a, fmt, st); return; }
     const long long t256 = a.N % 256 == 0 ? (long long)tiles_m * (a.N / 256) : 0, t128 = a.N % 128 == 0 ? (long long)tiles_m * (a.N / 128) : 0;
     if (t256 >= 200) launch_cfg<256, 2>(a, fmt, st);
     else if (t128 >= 200) launch_cfg<128, 3>(a, fmt, st);

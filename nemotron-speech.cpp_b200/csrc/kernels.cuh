@@ -48,6 +48,7 @@ struct GemmArgs {
     int c_group = 0, c_drop = 0; void* C0 = nullptr;
     int force_bn = 0, force_stages = 0;   // tuning hooks (bench_gemm): pick the tile config explicitly (stages 98 = CTA-pair tile)
     int pair = 0;                 // allow the CTA-pair (cta_group::2) tile when the batch is a single 128-row tile
+    int w_dynamic = 0;            // W was written by the previous kernel (per-launch Q8_0 dequantisation): no weight loads before the dependency wait
     int multicast = 1;            // allow A-tile multicast over clusters of 4 CTAs along N (experimental, only with NSB_MC=1: measured slower)
     int rotate = 1;               // CTA n starts its k loop at k-block (n mod nk): de-synchronises the A-tile reads of the grid
 };
@@ -74,6 +75,7 @@ struct AttnArgs {
     int B, T;
 };
 void launch_attention(const AttnArgs& a, cudaStream_t st);
+void launch_dequant_q8(const void* q, const void* scales, void* out_f16, int N, int K, cudaStream_t st);   // gemm_tc.cu
 bool pair_gemm_enabled();         // gemm_tc.cu: CTA-pair tiles on (default) / off (NSB_PAIR_GEMM=0)
 
 struct ConvModArgs {
