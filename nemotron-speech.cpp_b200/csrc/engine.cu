@@ -782,11 +782,26 @@ float Engine::bench_gemm(int kind, int rows, int bn, int stages, int splits, int
     };
     if (splits > 1 && (size_t)splits * rows * pick(layers_[0]).n_out * 4 > part_.bytes) throw std::invalid_argument("bench_gemm: split workspace too small");
     run();
+    // One pass over the layers is captured into a CUDA graph, as the step is: stream launches of ~3 us kernels (two tensor-map
+    // encodes + cudaLaunchKernelEx each) would time the host, not the kernel. NSB_BENCH_GEMM_GRAPH=0: plain stream launches.
+    static const bool use_graph = [] { const char* e = getenv("NSB_BENCH_GEMM_GRAPH"); return !(e && e[0] == '0'); }();
+    cudaGraphExec_t exec = nullptr;
+    if (use_graph) {
+        cudaGraph_t graph = nullptr;
+        NSB_CUDA(cudaStreamBeginCapture(st_, cudaStreamCaptureModeRelaxed));
+        try { run(); } catch (...) { cudaStreamEndCapture(st_, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+        NSB_CUDA(cudaStreamEndCapture(st_, &graph));
+        const cudaError_t err = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (err != cudaSuccess) throw CudaError(std::string("bench_gemm: cudaGraphInstantiate: ") + cudaGetErrorString(err));
+        NSB_CUDA(cudaGraphLaunch(exec, st_));
+    }
     NSB_CUDA(cudaEventRecord(ev0_, st_));
-    for (int i = 0; i < iters; ++i) run();
+    for (int i = 0; i < iters; ++i) { if (exec) { NSB_CUDA(cudaGraphLaunch(exec, st_)); } else { run(); } }
     NSB_CUDA(cudaEventRecord(ev1_, st_));
     NSB_CUDA(cudaEventSynchronize(ev1_));
     float ms = 0.f; NSB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    if (exec) cudaGraphExecDestroy(exec);
     return 1e3f * ms / (float)(iters * n_layers);
 }
 

@@ -32,6 +32,16 @@ bool pair_gemm_enabled() {
     return on;
 }
 
+static bool pair256_enabled() {
+    static const bool on = [] { const char* e = getenv("NSB_PAIR256"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+static int pair256_min_tiles() {
+    static const int v = [] { const char* e = getenv("NSB_PAIR256_MIN_TILES"); return e ? atoi(e) : 4; }();
+    return v;
+}
+
 namespace {
 
 constexpr int BM = 128, ROW_BYTES = 128, UMMA_K_BYTES = 32;      // one k-block = one 128-byte swizzle row per tile row; 4 MMAs per k-block
@@ -158,9 +168,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
            ((uint64_t)2 << 61);
 }
 // cute::UMMA::InstrDescriptor: c=F32, a/b = F16 (0) / BF16 (1) for kind::f16, TF32 (2) for kind::tf32; K-major both, N>>3 @17, M>>4 @24
-__host__ __device__ constexpr uint32_t make_idesc(int fmt /*0 f16, 1 bf16, 2 tf32*/, int n) {
-    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int fmt /*0 f16, 1 bf16, 2 tf32*/, int n, int m = BM) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// TMEM allocations are powers of two >= 32 columns
+__host__ __device__ constexpr uint32_t tmem_cols_for(int n) { return n <= 32 ? 32u : n <= 64 ? 64u : n <= 128 ? 128u : n <= 256 ? 256u : 512u; }
 
 struct TcParams {
     int M, N, K;
@@ -172,91 +184,134 @@ struct TcParams {
 
 // Epilogue of one 128 x BN tile (4 warps; TMEM lane quarter = warp % 4): tcgen05.ld the fp32 accumulator, apply the fused
 // epilogue, store. Called by warps 2-5 after the accumulator barrier.
-template <int BN>
-__device__ __forceinline__ void tc_epilogue_at(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full, int warp, int row, int n0, int trace_slot);
+//
+// tcgen05.ld hands thread l of a warp ROW l of the tile (32 consecutive columns per step). Stored that way a warp-wide
+// st.global.v4 touches 32 different rows = 32 separate 16-byte pieces per instruction, and at large batches the epilogue, not the
+// main loop, set the GEMM's pace (profiles/r01_notes.md). So each 32 x 32 chunk is transposed through a warp-private shared-memory
+// patch (row stride 36 floats: conflict-free both ways): 8 lanes then cover 128 contiguous bytes of one output row, 4 rows per
+// instruction. The patch lives in the first pipeline stages of the A ring, which are idle once the accumulator barrier has fired
+// (every TMA write landed, every MMA read retired).
+constexpr int EPI_RS = 36;                                       // floats per staged row
+constexpr int EPI_STAGE_BYTES = 4 * 32 * EPI_RS * 4;             // 4 epilogue warps
 
+// row0 = global output row of lane 0 of this warp (its TMEM lanes are (warp % 4) * 32 ..), n0 = global column of TMEM column 0,
+// BN = number of accumulator columns this warp reads, stage = this CTA's staging area (EPI_STAGE_BYTES, 16-byte aligned)
 template <int BN>
-__device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full, int warp, int lane, int m0, int n0, int trace_slot) {
-    tc_epilogue_at<BN>(p, tmem_base, tmem_full, warp, m0 + (warp & 3) * 32 + lane, n0, trace_slot);
-}
-
-// row = global output row of this thread (its TMEM lane is (warp % 4) * 32 + lane), n0 = global column of TMEM column 0,
-// BN = number of accumulator columns this warp reads
-template <int BN>
-__device__ __forceinline__ void tc_epilogue_at(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full, int warp, int row, int n0, int trace_slot) {
+__device__ __forceinline__ void tc_epilogue_at(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full, int warp, int row0, int n0, int trace_slot,
+                                               uint8_t* stage_base) {
         const bool tracer = trace_slot >= 0 && threadIdx.x == 64;
-        const int q = warp & 3;
+        const int q = warp & 3, lane = threadIdx.x & 31;
+        float* stage = reinterpret_cast<float*>(stage_base) + q * 32 * EPI_RS;
+        const int r4 = lane >> 3, c4 = (lane & 7) * 4;          // transposed mapping: pass i covers rows 4 i + r4, this lane columns c4 .. c4 + 3
+        // output rows of this lane's 8 passes (-1 = dropped / beyond M)
+        int orow[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = row0 + 4 * i + r4;
+            int o = row; bool live = row < p.M;
+            if (p.c_group > 0) { const int rr = row % p.c_group; o = (row / p.c_group) * (p.c_group - p.c_drop) + rr - p.c_drop; live = live && rr >= p.c_drop; }
+            orow[i] = live ? o : -1;
+        }
+        float* part_base = nullptr;
+        if (p.epi == EPI_PARTIAL)
+            part_base = p.C0 ? (blockIdx.z == 0 ? (float*)p.C0 : (float*)p.C + (size_t)(blockIdx.z - 1) * p.m_out * p.ldc)
+                             : (float*)p.C + (size_t)blockIdx.z * p.m_out * p.ldc;
+        const bool add_bias = p.bias && (p.epi != EPI_PARTIAL || blockIdx.z == 0);
+        const bool out16 = p.epi != EPI_PARTIAL && p.epi != EPI_RESID && p.out_type != OUT_F32;
+        int orow_own = -1;                                      // output row of this thread's own TMEM lane (16-bit path)
+        {
+            const int row = row0 + lane;
+            int o = row; bool live = row < p.M;
+            if (p.c_group > 0) { const int rr = row % p.c_group; o = (row / p.c_group) * (p.c_group - p.c_drop) + rr - p.c_drop; live = live && rr >= p.c_drop; }
+            if (live) orow_own = o;
+        }
         pdl_wait();                                             // C / bias may be produced (or still read) by the previous kernel
         if (tracer) trace_mark(trace_slot, 2);
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         if (tracer) trace_mark(trace_slot, 3);
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {                      // 32 consecutive columns of this thread's row: full 32-byte sectors per store
+        for (int c = 0; c < BN; c += 32) {
+            // columns of this chunk inside the tile and the matrix: 32, or 16 when BN is an odd multiple of 16 / the last tile overhangs N
+            const int nv = min(32, min(BN - c, p.N - (n0 + c)));
+            if (nv <= 0) break;                                 // warp-uniform
             uint32_t r[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-            int orow = row;
-            bool live = row < p.M;
-            if (p.c_group > 0) { const int rr = row % p.c_group; orow = (row / p.c_group) * (p.c_group - p.c_drop) + rr - p.c_drop; live = live && rr >= p.c_drop; }
-            if (live) {
-                const int n = n0 + c;
-                float v[32];
+            const int n = n0 + c;
+            float v[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                if (p.bias && (p.epi != EPI_PARTIAL || blockIdx.z == 0)) {
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            if (add_bias) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] += p.bias[n + i];
-                }
-                const size_t o = (size_t)orow * p.ldc + n;
-                if (p.epi == EPI_PARTIAL) {
-                    float* base = p.C0 ? (blockIdx.z == 0 ? (float*)p.C0 : (float*)p.C + (size_t)(blockIdx.z - 1) * p.m_out * p.ldc)
-                                       : (float*)p.C + (size_t)blockIdx.z * p.m_out * p.ldc;
-                    float4* dst = reinterpret_cast<float4*>(base + o);
+                for (int i = 0; i < 32; ++i) if (i < nv) v[i] += p.bias[n + i];
+            }
+            if (p.epi == EPI_SILU) {                            // result is rounded to 16 bits: MUFU-based exp / reciprocal is exact enough
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                } else if (p.epi == EPI_RESID) {
-                    float4* dst = reinterpret_cast<float4*>((float*)p.C + o);
+                for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+            } else if (p.epi == EPI_RELU) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float4 x = dst[i];
-                        x.x += p.alpha * v[4 * i]; x.y += p.alpha * v[4 * i + 1]; x.z += p.alpha * v[4 * i + 2]; x.w += p.alpha * v[4 * i + 3];
-                        dst[i] = x;
-                    }
-                } else {
-                    if (p.epi == EPI_SILU) {                     // result is rounded to 16 bits: MUFU-based exp / reciprocal is exact enough
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
-                    } else if (p.epi == EPI_RELU) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-                    }
-                    if (p.out_type == OUT_F32) {
-                        float4* dst = reinterpret_cast<float4*>((float*)p.C + o);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    } else if (p.out_type == OUT_F16) {
+                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (out16) {
+                // 16-bit results: a thread's 32 columns are 64 contiguous bytes = two full sectors; stored straight from the row-per-thread
+                // layout (the transpose below costs more shared-memory traffic than it saves here: measured, profiles/r01_notes.md)
+                if (orow_own >= 0) {
+                    const size_t o = (size_t)orow_own * p.ldc + n;
+                    if (p.out_type == OUT_F16) {
                         __half2 h[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
                         uint4* dst = reinterpret_cast<uint4*>((__half*)p.C + o);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) dst[i] = *reinterpret_cast<uint4*>(&h[4 * i]);
+                        for (int i = 0; i < 4; ++i) if (8 * i < nv) dst[i] = *reinterpret_cast<uint4*>(&h[4 * i]);
                     } else {
                         __nv_bfloat162 h[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
                         uint4* dst = reinterpret_cast<uint4*>((__nv_bfloat16*)p.C + o);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) dst[i] = *reinterpret_cast<uint4*>(&h[4 * i]);
+                        for (int i = 0; i < 4; ++i) if (8 * i < nv) dst[i] = *reinterpret_cast<uint4*>(&h[4 * i]);
                     }
+                }
+                continue;
+            }
+            __syncwarp();                                       // the previous chunk's reads of the patch are done
+#pragma unroll
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(stage + lane * EPI_RS + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+            if (c4 < nv) {
+                float4 t[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t[i] = *reinterpret_cast<const float4*>(stage + (4 * i + r4) * EPI_RS + c4);
+                float* cbase = (p.epi == EPI_PARTIAL ? part_base : (float*)p.C) + n + c4;
+                if (p.epi == EPI_RESID) {                       // x += alpha * t: all eight row loads in flight before the first store
+                    float4 x[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) if (orow[i] >= 0) x[i] = *reinterpret_cast<const float4*>(cbase + (size_t)orow[i] * p.ldc);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (orow[i] < 0) continue;
+                        x[i].x += p.alpha * t[i].x; x[i].y += p.alpha * t[i].y; x[i].z += p.alpha * t[i].z; x[i].w += p.alpha * t[i].w;
+                        *reinterpret_cast<float4*>(cbase + (size_t)orow[i] * p.ldc) = x[i];
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) if (orow[i] >= 0) *reinterpret_cast<float4*>(cbase + (size_t)orow[i] * p.ldc) = t[i];
                 }
             }
         }
         if (tracer) trace_mark(trace_slot, 4);
 }
 
+template <int BN>
+__device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full, int warp, int lane, int m0, int n0, int trace_slot,
+                                            uint8_t* stage_base) {
+    tc_epilogue_at<BN>(p, tmem_base, tmem_full, warp, m0 + (warp & 3) * 32, n0, trace_slot, stage_base);
+}
+
 template <int BN, int STAGES>
 struct Smem {
+    static_assert(STAGES * BM * ROW_BYTES >= EPI_STAGE_BYTES, "the epilogue patch lives in the A ring");
     alignas(1024) uint8_t a[STAGES][BM * ROW_BYTES];
     alignas(1024) uint8_t b[STAGES][BN * ROW_BYTES];
     alignas(8) uint64_t full[STAGES];
@@ -282,7 +337,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int nk = p.K / BK / (int)gridDim.z;                                   // k-blocks of this split
     const int kb0 = (int)blockIdx.z * nk;
     const int rot = p.rot ? (int)((blockIdx.x / CL) % (unsigned)nk) : 0;  // k-block visited at loop index kb: kb0 + (kb + rot) % nk (same for a whole cluster)
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr uint32_t TMEM_COLS = tmem_cols_for(BN);
     constexpr uint32_t STAGE_BYTES = (BM + BN) * ROW_BYTES;
 
     if (threadIdx.x == 0) {
@@ -356,7 +411,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ===================== epilogue =====================
-        tc_epilogue<BN>(p, tmem_base, &s.tmem_full, warp, lane, m0, n0, s.trace_slot);
+        tc_epilogue<BN>(p, tmem_base, &s.tmem_full, warp, lane, m0, n0, s.trace_slot, s.a[0]);
     }
     tc_fence_before();
     __syncthreads();
@@ -379,6 +434,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------
 template <int BN, int STAGES>
 struct SmemPair {
+    static_assert(STAGES * 64 * ROW_BYTES >= EPI_STAGE_BYTES, "the epilogue patch lives in the A ring");
     alignas(1024) uint8_t a[STAGES][64 * ROW_BYTES];
     alignas(1024) uint8_t b[STAGES][(BN / 2) * ROW_BYTES];
     alignas(8) uint64_t full[STAGES];
@@ -461,8 +517,111 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else {
         // ===================== epilogue (both CTAs: 64 rows x BN columns each) =====================
         const int q = warp & 3;
-        const int row = m0 + (int)rank * 64 + (q & 1) * 32 + lane;              // TMEM lane 32 q + lane
-        tc_epilogue_at<BN / 2>(p, tmem_base, &s.tmem_full, warp, row, n0 + (q >> 1) * (BN / 2), s.trace_slot);
+        const int row0 = m0 + (int)rank * 64 + (q & 1) * 32;                    // TMEM lanes 32 q ..
+        tc_epilogue_at<BN / 2>(p, tmem_base, &s.tmem_full, warp, row0, n0 + (q >> 1) * (BN / 2), s.trace_slot, s.a[0]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                                         // the peer's MMAs / commits may still touch this CTA's smem and barriers
+    if (warp == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair variant for LARGE batches (>= ~4 row tiles; configs 3 and 5): a cluster of two CTAs computes one 256 x BN tile with
+// tcgen05.mma.cta_group::2 at M = 256. CTA r stages rows [128 r, 128 r + 128) of the activation tile and rows
+// [r BN/2, (r+1) BN/2) of the weight tile, and accumulates its 128 rows x BN columns (TMEM lane = row, as in the single-CTA tile).
+// Why: at these batch sizes the single-CTA 128 x BN tile is bound by L2 -> SM ingest, not by the tensor pipe -- it pulls
+// (128 + BN) x 128 B per k-block for 2 BN tensor-core clocks (96 B/clk at BN = 256, against ~60 B/clk that an SM sustains from L2:
+// the 128 x 256 tile tops out near 64 % of the tensor peak). The pair tile pulls (128 + BN/2) x 128 B for the same 2 BN clocks
+// per SM (64 B/clk at BN = 256). BN is any multiple of 16 (the epilogue masks the overhang of the last tile along N), chosen
+// per shape so that the number of pair tiles lands just under a multiple of the 74 SM pairs (launch_gemm_tc). Stage counts keep
+// the footprint <= ~107 KB: two CTAs of different pairs share an SM, one's epilogue hides behind the other's main loop.
+// Barrier protocol = gemm_tc_pair_kernel's.
+// ------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct SmemPair2 {
+    alignas(1024) uint8_t a[STAGES][BM * ROW_BYTES];
+    alignas(1024) uint8_t b[STAGES][(BN / 2) * ROW_BYTES];
+    alignas(8) uint64_t full[STAGES];
+    uint64_t empty[STAGES];
+    uint64_t tmem_full;
+    uint32_t tmem_slot;
+    int trace_slot;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_pair256_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "pair256 tile: UMMA N is a multiple of 16 up to 256");
+    extern __shared__ uint8_t smem_raw[];
+    using S = SmemPair2<BN, STAGES>;
+    S& s = *reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();                                    // 0 = leader (issues the MMAs, owns the full barriers)
+    const int n0 = (int)(blockIdx.x >> 1) * BN, m0 = blockIdx.y * (2 * BM);
+    constexpr int BK = ROW_BYTES / 2;                                           // 64 elements of 16 bits
+    const int nk = p.K / BK / (int)gridDim.z;
+    const int kb0 = (int)blockIdx.z * nk;
+    constexpr uint32_t TMEM_COLS = tmem_cols_for(BN);
+    constexpr uint32_t HALF_BYTES = (BM + BN / 2) * ROW_BYTES;                  // what ONE CTA stages per k-block
+
+    if (threadIdx.x == 0) {
+        s.trace_slot = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 ? trace_begin(TR_GEMM_TC) : -1;
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+        mbar_init(&s.tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 2) tmem_alloc_pair(&s.tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                                         // both CTAs' barriers and TMEM are set up before any cross-CTA traffic
+    tc_fence_after();
+    const uint32_t tmem_base = s.tmem_slot;
+    if (threadIdx.x == 0) { pdl_trigger(); trace_mark(s.trace_slot, 1); }
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs, each its halves) =====================
+        if (elect_one()) {
+            const int a_row = m0 + (int)rank * BM, b_row = n0 + (int)rank * (BN / 2);
+            const int pre = nk < STAGES ? nk : STAGES;
+            if (p.w_dyn) pdl_wait();                                            // W written by the previous kernel (Q8_0 pre-dequantisation)
+            for (int kb = 0; kb < pre; ++kb) {                                  // weights first: they do not depend on the previous kernel
+                if (rank == 0) mbar_expect_tx(&s.full[kb], 2 * HALF_BYTES);
+                tma_load_2d_pair(s.b[kb], &tmB, &s.full[kb], (kb0 + kb) * BK, b_row);
+            }
+            if (!p.w_dyn) pdl_wait();
+            for (int kb = 0; kb < pre; ++kb) tma_load_2d_pair(s.a[kb], &tmA, &s.full[kb], (kb0 + kb) * BK, a_row);
+            for (int kb = pre; kb < nk; ++kb) {
+                const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&s.empty[st], ph ^ 1);                                // released for both CTAs by the leader's multicast commit
+                if (rank == 0) mbar_expect_tx(&s.full[st], 2 * HALF_BYTES);
+                tma_load_2d_pair(s.a[st], &tmA, &s.full[st], (kb0 + kb) * BK, a_row);
+                tma_load_2d_pair(s.b[st], &tmB, &s.full[st], (kb0 + kb) * BK, b_row);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (rank == 0 && elect_one()) {
+            const uint32_t idesc = make_idesc(p.fmt, BN, 2 * BM);               // M = 256 across the pair, N = BN
+            for (int kb = 0; kb < nk; ++kb) {
+                const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&s.full[st], ph);                                     // both CTAs' halves of this k-block have landed
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(s.a[st]), b_addr = smem_u32(s.b[st]);
+#pragma unroll
+                for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k)
+                    umma_f16_pair(tmem_base, make_desc(a_addr + k * UMMA_K_BYTES), make_desc(b_addr + k * UMMA_K_BYTES), idesc, (kb | k) ? 1u : 0u);
+                umma_commit_pair(&s.empty[st]);
+            }
+            umma_commit_pair(&s.tmem_full);
+        }
+    } else {
+        // ===================== epilogue (both CTAs: 128 rows x BN columns each) =====================
+        tc_epilogue_at<BN>(p, tmem_base, &s.tmem_full, warp, m0 + (int)rank * BM + (warp & 3) * 32, n0, s.trace_slot, s.a[0]);
     }
     tc_fence_before();
     __syncthreads();
@@ -612,7 +771,7 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to the tensor core
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s.bready[st])) : "memory");
         }
-        if (warp < 6) tc_epilogue<BN>(p, tmem_base, &s.tmem_full, warp, lane, m0, n0, s.trace_slot);
+        if (warp < 6) tc_epilogue<BN>(p, tmem_base, &s.tmem_full, warp, lane, m0, n0, s.trace_slot, s.a[0]);
     }
     tc_fence_before();
     __syncthreads();
@@ -719,6 +878,49 @@ void launch_cfg_pair(const GemmArgs& a, int fmt, cudaStream_t st) {
     launch_k_cluster(gemm_tc_pair_kernel<BN, STAGES>, grid, dim3(TC_THREADS), smem, st, 2, tmA, tmB, p);
 }
 
+template <int BN, int STAGES>
+void launch_cfg_pair256(const GemmArgs& a, int fmt, cudaStream_t st) {
+    static bool attr_set = false;
+    const size_t smem = sizeof(SmemPair2<BN, STAGES>) + 1024;
+    if (!attr_set) {
+        NSB_CUDA(cudaFuncSetAttribute(gemm_tc_pair256_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const CUtensorMap tmA = make_map(a.A, a.M, a.K, a.lda, BM, fmt);
+    const CUtensorMap tmB = make_map(a.W, a.N, a.K, a.K, BN / 2, fmt);
+    const int m_out = a.c_group > 0 ? (a.M / a.c_group) * (a.c_group - a.c_drop) : a.M;
+    TcParams p{a.M, a.N, a.K, a.bias, a.C, a.ldc, a.epi, a.alpha, a.out_type, fmt, 0, a.c_group, a.c_drop, a.C0, m_out, a.w_dynamic};
+    dim3 grid(2 * ((a.N + BN - 1) / BN), (a.M + 2 * BM - 1) / (2 * BM), a.splits);
+    launch_k_cluster(gemm_tc_pair256_kernel<BN, STAGES>, grid, dim3(TC_THREADS), smem, st, 2, tmA, tmB, p);
+}
+// Pair tiles for large batches: BN per shape so that the pair tiles fill whole waves of the 74 SM pairs. Per-SM cost of a tile
+// ~ the bytes it stages per k-block, (128 + BN/2) rows (+ a fixed share for prologue / epilogue that does not overlap).
+int pick_pair256_bn(int M, int N) {
+    // Measured (profiles/r01_gemm_large_*.txt): a pair tile's main loop is latency-bound on its own (3-4 stages of ~25 KB against
+    // ~1.5 us of L2 -> SM latency under load), so what pays is many tiles with two co-resident CTAs per SM: the SMALLEST BN whose
+    // pair tiles still fit the 148 co-resident pair slots (74 SM pairs x 2). Not worth it when even BN = 112 leaves the machine
+    // short of tiles (returns 0: the single-CTA tiles win there).
+    const int tiles_m = (M + 2 * BM - 1) / (2 * BM);
+    auto tiles = [&](int bn) { return (long long)tiles_m * ((N + bn - 1) / bn); };
+    if (tiles(112) < 100) return 0;
+    for (int bn : {112, 160, 208, 256}) if (tiles(bn) <= 148) return bn;
+    int best = 256; long long best_cost = 0;
+    for (int bn : {256, 208, 160, 112}) {
+        const long long cost = ((tiles(bn) + 147) / 148) * (BM + bn / 2);
+        if (!best_cost || cost < best_cost) { best = bn; best_cost = cost; }
+    }
+    return best;
+}
+void launch_pair256(const GemmArgs& a, int fmt, int bn, cudaStream_t st) {
+    switch (bn) {
+        case 256: launch_cfg_pair256<256, 3>(a, fmt, st); break;
+        case 208: launch_cfg_pair256<208, 3>(a, fmt, st); break;
+        case 160: launch_cfg_pair256<160, 4>(a, fmt, st); break;
+        case 112: launch_cfg_pair256<112, 4>(a, fmt, st); break;
+        default: throw CudaError("gemm_tc: pair256 tile not instantiated");
+    }
+}
+
 template <int BN, int STAGES, int EB>
 void launch_cfg_e(const GemmArgs& a, int fmt, cudaStream_t st) {
     if (a.multicast && multicast_enabled() && (a.N / BN) % 4 == 0) launch_cfg_c<BN, STAGES, EB, 4>(a, fmt, st);
@@ -790,6 +992,7 @@ void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
     }
     if (a.force_bn) {                                             // tuning hook
         if (a.splits > 1 && (a.epi != EPI_PARTIAL || (a.K / BK) % a.splits != 0)) throw CudaError("gemm_tc: bad split-K request");
+        if (a.force_stages == 97) { if (fmt == 2) throw CudaError("gemm_tc: pair tiles are 16-bit only"); launch_pair256(a, fmt, a.force_bn, st); return; }
         const int key = a.force_bn * 100 + a.force_stages;
         switch (key) {
             case 3204: launch_cfg<32, 4>(a, fmt, st); break;
@@ -818,6 +1021,11 @@ void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
     // single 128-row tile, 16-bit operands: CTA-pair tiles (8 stages; 12 / 16 measured slower in the step: the main loop does not
     // speed up and the next kernel loses its early residency, profiles/r01_notes.md)
     if (fmt != 2 && a.pair && !a.w_dynamic && pair_gemm_enabled() && tiles_m == 1 && a.N % 64 == 0) { launch_cfg_pair<64, 8>(a, fmt, st); return; }
+    // >= 4 row tiles, 16-bit operands: 256-row CTA-pair tiles (the single-CTA tile is L2 -> SM ingest bound there)
+    if (fmt != 2 && tiles_m >= pair256_min_tiles() && pair256_enabled()) {
+        const int bn = pick_pair256_bn(a.M, a.N);
+        if (bn) { launch_pair256(a, fmt, bn, st); return; }
+    }
     const long long t256 = a.N % 256 == 0 ? (long long)tiles_m * (a.N / 256) : 0, t128 = a.N % 128 == 0 ? (long long)tiles_m * (a.N / 128) : 0;
     if (t256 >= 200) launch_cfg<256, 2>(a, fmt, st);
     else if (t128 >= 200) launch_cfg<128, 3>(a, fmt, st);

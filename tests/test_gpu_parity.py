@@ -141,6 +141,30 @@ def test_tcgen05_gemm_parity(built, wtype, compute, mm):
     eng.close()
 
 
+@pytest.mark.parametrize("wtype,compute,mm", [("f32", 2, O.MM_F16), ("f32", 3, O.MM_BF16), ("q8_0", 0, O.MM_Q8FAST)])
+def test_tcgen05_gemm_large_batch_pair_tiles(built, wtype, compute, mm):
+    """>= 4 row tiles: 256-row CTA-pair tiles (cta_group::2, M = 256) with BN in {256, 208, 160, 112} chosen per shape -- every
+    BN, the overhang of the last tile along N (4096 = 19 x 208 + 144), a ragged last row tile (900 = 3 x 256 + 132), and in
+    Q8_0 mode the per-launch dequantisation into the fp16 scratch in front of it."""
+    import nsb200
+    path = synth.cached_model(wtype, 2, R=0)
+    eng = nsb200.Engine(path, right_context=0, max_streams=1, compute=compute)
+    om = O.Model(path, mm)
+    rng = np.random.default_rng(1)
+    P = "encoder.layers.1."
+    for rows in (1792, 900):
+        for name, k in (("feed_forward1.linear1.weight", 1024), ("feed_forward2.linear2.weight", 4096), ("conv.pointwise_conv1.weight", 1024),
+                        ("self_attn.linear_qkv.weight", 1024)):
+            x = rng.standard_normal((rows, k)).astype(np.float32)
+            if "qkv" in name:
+                ref = np.concatenate([om.matmul(P + f"self_attn.linear_{c}.weight", x) for c in "qkv"], axis=1)
+            else:
+                ref = om.matmul(P + name, x)
+            y = eng.op_gemm(P + name, x)
+            assert y.shape == ref.shape and rel(y, ref) < 3e-5, (name, rows)
+    eng.close()
+
+
 @pytest.mark.parametrize("R", [0, 1, 6, 13])
 def test_streaming_parity_f32_all_latency_modes(built, R):
     import nsb200

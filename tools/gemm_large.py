@@ -1,0 +1,20 @@
+#!/usr/bin/env python3
+"""Layer GEMM shapes at a large batch (ROWS token rows, default 1792 = 256 streams x 560 ms): us and TFLOP/s per tile config.
+bn = 0 / stages = 0 is the engine's own choice. Timed as in bench.py (24 layers x iters launches, one CUDA graph per pass)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
+import nsb200, synth
+ROWS = int(os.environ.get("ROWS", 1792)); R = 6; T = 7
+CFGS = [tuple(int(v) for v in c.split(":")) for c in os.environ.get("CFGS", "0:0,256:2,256:3,128:3,128:4,128:6,64:4").split(",")]
+eng = nsb200.Engine(synth.cached_model("f16", 24, R=R), right_context=R, max_streams=(ROWS + T - 1) // T, compute=nsb200.COMPUTE_BF16, kv_dtype=nsb200.KV_BF16)
+KIND = {0: ("ff_up", 4096, 1024), 1: ("ff_down", 1024, 4096), 2: ("qkv", 3072, 1024), 3: ("out", 1024, 1024), 4: ("pw1", 2048, 1024)}
+for kind, (nm, N, K) in KIND.items():
+    for bn, st in CFGS:
+        if bn and st != 97 and N % bn: continue
+        try:
+            us = eng.bench_gemm(kind, ROWS, bn, st, 1, 1, 10)
+        except Exception as ex:
+            print(nm, bn, st, "ERR", ex); continue
+        print(f"{nm:7s} N={N} K={K} rows={ROWS} bn={bn:3d} st={st}: {us:7.2f} us  {2.0 * ROWS * N * K / us / 1e6:7.1f} TFLOP/s", flush=True)
+eng.close()
