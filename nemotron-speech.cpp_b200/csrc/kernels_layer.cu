@@ -627,28 +627,31 @@ __device__ __forceinline__ void group_barrier(int id, int n) { asm volatile("bar
 struct AttnMmaLayout {                                            // byte offsets inside the dynamic shared memory
     int kpad, rpad, n_rel;                                        // keys padded to 16, positional rows padded to 8
     size_t ps, zero, per_stream, ks, vs, qu, qv, pat, ac, bd, total;
-    __host__ __device__ AttnMmaLayout(int T, int ns) {
+    // dv (single-stream CTAs): the V tile is loaded AFTER the two score GEMMs into the space of the positional tile, which is dead
+    // by then -- 54 KB instead of 77 KB per CTA = 4 resident CTAs per SM instead of 2 (vs is then an absolute offset)
+    __host__ __device__ AttnMmaLayout(int T, int ns, bool dv) {
         const int K = ATT_L + T;
         n_rel = ATT_L + 2 * T - 1; kpad = (K + 15) & ~15; rpad = (n_rel + 7) & ~7;
         const size_t row = ATT_RS * 2;
-        ps = 0; zero = ps + (size_t)rpad * row;
+        ps = 0; zero = ps + (size_t)(rpad > kpad ? rpad : kpad) * row;
         const size_t base = zero + row;
-        ks = 0; vs = ks + (size_t)kpad * row; qu = vs + (size_t)kpad * row; qv = qu + (size_t)T * row; pat = qv + (size_t)T * row;
+        ks = 0; vs = ks + (size_t)kpad * row; qu = dv ? vs : vs + (size_t)kpad * row; qv = qu + (size_t)T * row; pat = qv + (size_t)T * row;
         ac = pat + (size_t)T * (kpad + 8) * 2; ac = (ac + 15) & ~(size_t)15;
         bd = ac + (size_t)T * kpad * 4; per_stream = bd + (size_t)T * rpad * 4; per_stream = (per_stream + 15) & ~(size_t)15;
-        ks += base; vs += base; qu += base; qv += base; pat += base; ac += base; bd += base;
+        ks += base; vs = dv ? ps : vs + base; qu += base; qv += base; pat += base; ac += base; bd += base;
         total = base + (size_t)ns * per_stream;
     }
 };
 
 template <int KV, int NS>
-__global__ void __launch_bounds__(128 * NS, NS == 2 ? 2 : 3) attention_mma_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(128 * NS, NS == 2 ? 2 : 4) attention_mma_kernel(const AttnArgs a) {
+    constexpr bool DV = NS == 1;                                                // deferred V tile (see AttnMmaLayout)
     using E = typename KvT<KV>::type;
     static_assert(KV != 0, "16-bit ring only");
     constexpr int EPV = 8, VPR = D_HEAD / EPV;                                  // 16-byte vectors: 8 elements, 16 per row
     extern __shared__ __align__(16) uint8_t att_smem[];
     const int T = a.T, K = ATT_L + T, Cap = K;
-    const AttnMmaLayout lay(T, NS);
+    const AttnMmaLayout lay(T, NS, DV);
     const int tid = threadIdx.x, half = NS == 2 ? tid >> 7 : 0, t = tid & 127, warp = t >> 5, lane = t & 31;
     const int h = blockIdx.x, b = blockIdx.y * NS + half;
     const bool active = b < a.B;
@@ -656,7 +659,7 @@ __global__ void __launch_bounds__(128 * NS, NS == 2 ? 2 : 3) attention_mma_kerne
     E* Ps = reinterpret_cast<E*>(att_smem + lay.ps);                            // [rpad][ATT_RS], shared by the streams of the CTA
     E* Zero = reinterpret_cast<E*>(att_smem + lay.zero);                        // one all-zero row
     E* Ks = reinterpret_cast<E*>(hb + lay.ks);                                  // [kpad][ATT_RS]
-    E* Vs = reinterpret_cast<E*>(hb + lay.vs);
+    E* Vs = reinterpret_cast<E*>((DV ? att_smem : hb) + lay.vs);
     E* Qu = reinterpret_cast<E*>(hb + lay.qu);                                  // [T][ATT_RS]  (q + pos_bias_u), rounded
     E* Qv = reinterpret_cast<E*>(hb + lay.qv);
     E* Pat = reinterpret_cast<E*>(hb + lay.pat);                                // [T][kpad + 8] probabilities, rounded
@@ -677,37 +680,55 @@ __global__ void __launch_bounds__(128 * NS, NS == 2 ? 2 : 3) attention_mma_kerne
     const float* qkv = a.qkv + (size_t)b * T * 3 * D_MODEL + h * D_HEAD;
     E* kring = reinterpret_cast<E*>(a.k_ring) + (size_t)slot * a.slot_stride + h * D_HEAD;
     E* vring = reinterpret_cast<E*>(a.v_ring) + (size_t)slot * a.slot_stride + h * D_HEAD;
-    auto ring_row = [&](int j) { return (size_t)((w + Cap - ATT_L + j) % Cap) * D_MODEL; };
+    const int rbase = w + Cap - ATT_L;                                            // ring row of key j: (rbase + j) mod Cap, without a division
+    auto ring_row = [&](int j) { int r = rbase + j; r -= r >= Cap ? Cap : 0; r -= r >= Cap ? Cap : 0; return (size_t)r * D_MODEL; };
     if (active) {
         for (int e = t; e < kpad * VPR; e += 128) {
             const int j = e / VPR, c = (e % VPR) * EPV;
             if (j >= first && j < ATT_L) {
                 const size_t g = ring_row(j) + c;
                 cp_async16(Ks + (size_t)j * ATT_RS + c, kring + g);
-                cp_async16(Vs + (size_t)j * ATT_RS + c, vring + g);
+                if (!DV) cp_async16(Vs + (size_t)j * ATT_RS + c, vring + g);
+                else if ((c & 63) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(vring + g));   // V rows: HBM -> L2 now, shared memory after the score GEMMs
             } else if (j < first || j >= K) {                                    // not yet valid / padding: zeros (0 x garbage must not be NaN)
                 *reinterpret_cast<uint4*>(Ks + (size_t)j * ATT_RS + c) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(Vs + (size_t)j * ATT_RS + c) = make_uint4(0, 0, 0, 0);
+                if (!DV) *reinterpret_cast<uint4*>(Vs + (size_t)j * ATT_RS + c) = make_uint4(0, 0, 0, 0);
             }
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    const float bu = a.bias_u[h * D_HEAD + t], bv = a.bias_v[h * D_HEAD + t];   // thread t owns head dim t in the staging loops
+    // q / k / v staging: a thread owns two adjacent head dims (t2) of every second row (rsel)
+    struct alignas(4) E2 { E a, b; };
+    const int t2 = (t & 63) * 2, rsel = t >> 6;
+    const float2 bu = *reinterpret_cast<const float2*>(a.bias_u + h * D_HEAD + t2), bv = *reinterpret_cast<const float2*>(a.bias_v + h * D_HEAD + t2);
     NSB_KERNEL_WAIT()
     if (active) {
-#pragma unroll 2
-        for (int i = 0; i < T; ++i) {                                            // q (+ biases) and this chunk's K / V rows: one head dim per thread
-            const float* row = qkv + (size_t)i * 3 * D_MODEL + t;
-            float q = row[0], kn = row[D_MODEL], vn = row[2 * D_MODEL];
-            for (int z = 1; z < a.planes; ++z) {                                 // split-K partial planes of the QKV GEMM, in slice order
-                const float* rz = row + (size_t)z * a.plane_stride;
-                q += rz[0]; kn += rz[D_MODEL]; vn += rz[2 * D_MODEL];
+        for (int i0 = 0; i0 < T; i0 += 8) {                                      // 4 rows per thread = 12 loads in flight
+            float2 q[4], kn[4], vn[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + rsel + 2 * u;
+                if (i >= T) continue;
+                const float* row = qkv + (size_t)i * 3 * D_MODEL + t2;
+                q[u] = *reinterpret_cast<const float2*>(row); kn[u] = *reinterpret_cast<const float2*>(row + D_MODEL); vn[u] = *reinterpret_cast<const float2*>(row + 2 * D_MODEL);
+                for (int z = 1; z < a.planes; ++z) {                             // split-K partial planes of the QKV GEMM, in slice order
+                    const float* rz = row + (size_t)z * a.plane_stride;
+                    const float2 q2 = *reinterpret_cast<const float2*>(rz), k2 = *reinterpret_cast<const float2*>(rz + D_MODEL), v2 = *reinterpret_cast<const float2*>(rz + 2 * D_MODEL);
+                    q[u].x += q2.x; q[u].y += q2.y; kn[u].x += k2.x; kn[u].y += k2.y; vn[u].x += v2.x; vn[u].y += v2.y;
+                }
             }
-            Qu[(size_t)i * ATT_RS + t] = from_f32<E>(q + bu);                    // :503-507
-            Qv[(size_t)i * ATT_RS + t] = from_f32<E>(q + bv);
-            const E ke = from_f32<E>(kn), ve = from_f32<E>(vn);
-            Ks[(size_t)(ATT_L + i) * ATT_RS + t] = ke; Vs[(size_t)(ATT_L + i) * ATT_RS + t] = ve;
-            kring[ring_row(ATT_L + i) + t] = ke; vring[ring_row(ATT_L + i) + t] = ve;   // ring append (replaces concat + roll, :465-484)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + rsel + 2 * u;
+                if (i >= T) continue;
+                *reinterpret_cast<E2*>(Qu + (size_t)i * ATT_RS + t2) = E2{from_f32<E>(q[u].x + bu.x), from_f32<E>(q[u].y + bu.y)};   // :503-507
+                *reinterpret_cast<E2*>(Qv + (size_t)i * ATT_RS + t2) = E2{from_f32<E>(q[u].x + bv.x), from_f32<E>(q[u].y + bv.y)};
+                const E2 ke{from_f32<E>(kn[u].x), from_f32<E>(kn[u].y)}, ve{from_f32<E>(vn[u].x), from_f32<E>(vn[u].y)};
+                *reinterpret_cast<E2*>(Ks + (size_t)(ATT_L + i) * ATT_RS + t2) = ke;
+                if (!DV) *reinterpret_cast<E2*>(Vs + (size_t)(ATT_L + i) * ATT_RS + t2) = ve;
+                const size_t g = ring_row(ATT_L + i) + t2;                       // ring append (replaces concat + roll, :465-484)
+                *reinterpret_cast<E2*>(kring + g) = ke; *reinterpret_cast<E2*>(vring + g) = ve;
+            }
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -763,6 +784,14 @@ __global__ void __launch_bounds__(128 * NS, NS == 2 ? 2 : 3) attention_mma_kerne
         }
     }
     group_barrier(1 + half, 128);
+    if (DV) {                                                                     // the positional tile is dead: V (cached rows + this chunk's rows, now in the ring) takes its place
+        for (int e = t; e < kpad * VPR; e += 128) {
+            const int j = e / VPR, c = (e % VPR) * EPV;
+            if (j >= first && j < K) cp_async16(Vs + (size_t)j * ATT_RS + c, vring + ring_row(j) + c);
+            else *reinterpret_cast<uint4*>(Vs + (size_t)j * ATT_RS + c) = make_uint4(0, 0, 0, 0);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     // ---- softmax over valid keys; rel-shift = index arithmetic: BD[i][j] = BD_raw[i][L + i - j + T-1] (:391-433) ----
     const float scale = 0.08838834764831845f;                                   // 1/sqrt(128) :517
     for (int i = warp; i < T; i += 4) {
@@ -779,6 +808,7 @@ __global__ void __launch_bounds__(128 * NS, NS == 2 ? 2 : 3) attention_mma_kerne
         for (int j = lane; j < kpad; j += 32)
             Pat[(size_t)i * pat_rs + j] = from_f32<E>(j >= first && j < K ? Ac[i * kpad + j] * inv : 0.f);
     }
+    if (DV) asm volatile("cp.async.wait_group 0;" ::: "memory");
     group_barrier(1 + half, 128);
     if (tr_slot >= 0) trace_mark(tr_slot, 4);
     // ---- ctx = P V: 16 output tiles of 8 head dims, 4 per warp; k runs over the (padded) keys ----
@@ -816,10 +846,12 @@ __global__ void __launch_bounds__(128 * NS, NS == 2 ? 2 : 3) attention_mma_kerne
 
 template <int KV, int NS>
 static void launch_attention_mma(const AttnArgs& a, cudaStream_t st) {
-    const AttnMmaLayout lay(a.T, NS);
+    const AttnMmaLayout lay(a.T, NS, NS == 1);
     static size_t configured = 0;
     if (lay.total > configured) {
         NSB_CUDA(cudaFuncSetAttribute(attention_mma_kernel<KV, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+        // largest shared-memory carve-out: the resident CTAs per SM are limited by shared memory, not by L1
+        NSB_CUDA(cudaFuncSetAttribute(attention_mma_kernel<KV, NS>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         configured = lay.total;
     }
     launch_k(attention_mma_kernel<KV, NS>, dim3(N_HEADS, (a.B + NS - 1) / NS), dim3(128 * NS), lay.total, st, a);
