@@ -124,46 +124,53 @@ __global__ void __launch_bounds__(SUB_CH) stem_conv0_dw_kernel(const float* __re
                                                                const int* __restrict__ slot_of_b, int T, const float* __restrict__ w0_t,
                                                                const float* __restrict__ b0, const float* __restrict__ w2_t,
                                                                const float* __restrict__ b2, float* __restrict__ out) {
-    __shared__ float mel[7][N_MELS];
+    // mel column iw lives at index iw + 4: the five columns 4 ow2 - 4 .. 4 ow2 one output column needs start 16-byte aligned
+    // (one LDS.128 + one LDS.32 per row instead of 18 scalar broadcast loads: the kernel was bound by shared-memory issue)
+    constexpr int MS = N_MELS + 8;
+    __shared__ __align__(16) float mel[7][MS];
     NSB_KERNEL_PROLOGUE(TR_STEM)
     const int oh2 = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
     const int M = PRE_CACHE + 8 * T, t1 = M / 2 + 1, t2 = gridDim.x;
     constexpr int W1 = N_MELS / 2 + 1, W2 = W1 / 2 + 1;                         // 65, 33
     const int slot = slot_of_b[b];
-    for (int e = c; e < 7 * N_MELS; e += SUB_CH) {
-        const int r = e / N_MELS, m = e % N_MELS, f = 4 * oh2 - 6 + r;          // mel rows 4 oh2 - 6 .. 4 oh2
-        mel[r][m] = (f >= 0 && f < M) ? chunk_mel(hist, mel_new, slot, b, T, f, m) : 0.0f;
+    for (int e = c; e < 7 * MS; e += SUB_CH) {
+        const int r = e / MS, m = e % MS - 4, f = 4 * oh2 - 6 + r;              // mel rows 4 oh2 - 6 .. 4 oh2, columns -4 .. 131 (zero outside the image)
+        mel[r][m + 4] = (f >= 0 && f < M && m >= 0 && m < N_MELS) ? chunk_mel(hist, mel_new, slot, b, T, f, m) : 0.0f;
     }
     float w0[9], w2[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) { w0[k] = w0_t[k * SUB_CH + c]; w2[k] = w2_t[k * SUB_CH + c]; }
     const float bias0 = b0[c], bias2 = b2[c];
     __syncthreads();
-    // conv0 value at (row h = 2 oh2 - 2 + kh2, column w); zero outside the conv0 image (the depthwise conv's padding)
-    auto conv0_at = [&](int kh2, int w) -> float {
-        const int h = 2 * oh2 - 2 + kh2;
-        if (h < 0 || h >= t1 || w < 0 || w >= W1) return 0.0f;
-        float acc = 0.0f;
+    bool hvalid[3];                                                             // conv0 rows 2 oh2 - 2 + kh2 inside the conv0 image (else: the depthwise conv's zero padding)
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const int iw = 2 * w + kw - 2;                                   // mel row 2h + kh - 2 = (4 oh2 - 6) + 2 kh2 + kh
-                const float x = (iw >= 0 && iw < N_MELS) ? mel[2 * kh2 + kh][iw] : 0.0f;
-                acc = fmaf(x, w0[kh * 3 + kw], acc);
-            }
-        }
-        return fmaxf(acc + bias0, 0.0f);
-    };
+    for (int kh2 = 0; kh2 < 3; ++kh2) { const int h = 2 * oh2 - 2 + kh2; hvalid[kh2] = h >= 0 && h < t1; }
     float win[3][3];
 #pragma unroll
-    for (int kh2 = 0; kh2 < 3; ++kh2) win[kh2][2] = conv0_at(kh2, -2);           // column 2*0 - 2 (out of range -> 0)
+    for (int kh2 = 0; kh2 < 3; ++kh2) win[kh2][2] = 0.0f;                        // conv0 column -2: out of range
     for (int ow2 = 0; ow2 < W2; ++ow2) {
+        float m[7][5];                                                          // mel rows x columns 4 ow2 - 4 .. 4 ow2
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+            const float4 v = *reinterpret_cast<const float4*>(&mel[r][4 * ow2]);
+            m[r][0] = v.x; m[r][1] = v.y; m[r][2] = v.z; m[r][3] = v.w; m[r][4] = mel[r][4 * ow2 + 4];
+        }
 #pragma unroll
         for (int kh2 = 0; kh2 < 3; ++kh2) {
+            // conv0 at columns w = 2 ow2 - 1 (mel columns 4 ow2 - 4 ..) and w = 2 ow2 (mel columns 4 ow2 - 2 ..); rows 2 kh2 + kh.
+            // Same tap order as the stand-alone conv0 kernel; out-of-image taps contribute fma(0, w, acc) = acc there too.
+            float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    a0 = fmaf(m[2 * kh2 + kh][kw], w0[kh * 3 + kw], a0);
+                    a1 = fmaf(m[2 * kh2 + kh][kw + 2], w0[kh * 3 + kw], a1);
+                }
+            }
             win[kh2][0] = win[kh2][2];
-            win[kh2][1] = conv0_at(kh2, 2 * ow2 - 1);
-            win[kh2][2] = conv0_at(kh2, 2 * ow2);
+            win[kh2][1] = (hvalid[kh2] && ow2 >= 1) ? fmaxf(a0 + bias0, 0.0f) : 0.0f;
+            win[kh2][2] = hvalid[kh2] ? fmaxf(a1 + bias0, 0.0f) : 0.0f;
         }
         float acc = 0.0f;
 #pragma unroll
