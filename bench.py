@@ -13,7 +13,7 @@ max-over-ranks of the timed region.
 
   value : device-resident throughput -- PCM of the step already in HBM, the K steps enqueued back to back on the engine's
           stream, CUDA events around them (p50 / p99 chunk latency: single host-synchronised steps, outside the timed region)
-  e2e   : the same K steps through the public C ABI with HOST buffers: nsb_push_pcm_batch, nsb_engine_step_begin
+  e2e   : the same K steps through the public C ABI with HOST buffers (two steps in flight): nsb_push_pcm_batch, nsb_engine_step_begin
           (pinned staging + H2D + kernels + D2H of the token ids enqueued), the next chunk pushed meanwhile,
           nsb_engine_step_end, nsb_pop_tokens_batch; wall clock
 
@@ -296,11 +296,14 @@ def main():
     sync_all()
     t0 = time.perf_counter()
     ntok = 0
+    # two steps in flight: while the device runs step i the host hands over the next 160 ms of every stream and stages + enqueues
+    # step i+1 (pinned staging, H2D, all kernels, D2H of the token ids), then waits for step i and pops its tokens
+    assert eng.step_begin() == STREAMS
     for i in range(args.steps):
-        assert eng.step_begin() == STREAMS                # staging + H2D of this step's PCM + all kernels + D2H of the token ids enqueued
         if i + 1 < args.steps:
-            feed(shift)                                   # the host hands over the NEXT 160 ms of every stream while the device works
-        assert eng.step_end() == STREAMS                  # wait for the step, queue its tokens
+            feed(shift)
+            assert eng.step_begin() == STREAMS
+        assert eng.step_end() == STREAMS                  # wait for the OLDEST step in flight, queue its tokens
         _, cnt = eng.pop_tokens_batch(ids, 32 * T)
         ntok += int(cnt.sum())
     sync_all()

@@ -93,6 +93,7 @@ Engine::Engine(const std::string& path, const nsb_engine_config& cfg) : cfg_(cfg
     NSB_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     NSB_CUDA(cudaEventCreate(&ev0_));
     NSB_CUDA(cudaEventCreate(&ev1_));
+    for (StepIO& io : io_) { NSB_CUDA(cudaEventCreate(&io.ev0)); NSB_CUDA(cudaEventCreate(&io.ev1)); NSB_CUDA(cudaEventCreateWithFlags(&io.done, cudaEventDisableTiming)); }
 
     R = cfg.att_right_context;
     if (R < 0 || R > 64) throw std::invalid_argument("att_right_context out of range");
@@ -128,6 +129,7 @@ Engine::~Engine() {
     for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
+    for (StepIO& io : io_) { if (io.ev0) cudaEventDestroy(io.ev0); if (io.ev1) cudaEventDestroy(io.ev1); if (io.done) cudaEventDestroy(io.done); }
     if (st_) cudaStreamDestroy(st_);
 }
 
@@ -305,8 +307,10 @@ void Engine::alloc_state() {
     part_.alloc((size_t)MAX_SPLITS * std::min<size_t>(Mrows, 1024) * D_MODEL * 4);       // split-K workspace (only used when rows <= 1024)
     out_tok_.alloc((size_t)S * MAX_SYMBOLS * T * 4); out_cnt_.alloc((size_t)S * 4);
     dec_sync_.alloc(decode_sync_bytes(S));
-    h_pcm_.alloc((size_t)S * rl_ * 2); h_slot_.alloc((size_t)S * 4);
-    h_tok_.alloc((size_t)S * MAX_SYMBOLS * T * 4); h_cnt_.alloc((size_t)S * 4);
+    for (StepIO& io : io_) {
+        io.h_pcm.alloc((size_t)S * rl_ * 2); io.h_slot.alloc((size_t)S * 4);
+        io.h_tok.alloc((size_t)S * MAX_SYMBOLS * T * 4); io.h_cnt.alloc((size_t)S * 4);
+    }
 }
 
 void Engine::zero_slot(int s) {
@@ -325,7 +329,7 @@ void Engine::zero_slot(int s) {
     NSB_CUDA(cudaMemcpyAsync((char*)cand_valid_.p + (size_t)s * 4, &zero, 4, cudaMemcpyHostToDevice, st_));
     NSB_CUDA(cudaMemcpyAsync((char*)prev_token_.p + (size_t)s * 4, &blank, 4, cudaMemcpyHostToDevice, st_));   // prev_token = blank (:41-42)
     NSB_CUDA(cudaStreamSynchronize(st_));
-    hs_[s].buf.clear(); hs_[s].base = 0; hs_[s].n_pushed = 0; hs_[s].chunk_idx = 0; hs_[s].tokens.clear();
+    hs_[s].buf.clear(); hs_[s].base = 0; hs_[s].n_pushed = 0; hs_[s].chunk_idx = 0; hs_[s].chunks_done = 0; hs_[s].tokens.clear();
 }
 
 // P_l = linear_pos(pos_emb rows) for the L+2T-1 relative positions a chunk can touch, once, at load.
@@ -398,6 +402,10 @@ void Engine::gemm_residual(const void* A, long long lda, const Weight& W, int M,
         const int nk = W.n_in / 64;
         while (splits < MAX_SPLITS && tiles * splits < 120 && nk % (splits * 2) == 0 && nk / (splits * 2) >= 2) splits *= 2;
     }
+    // Large batches, K = 4096 (FFN down-projections): with 14 x 8 tiles the N = 1024 GEMM cannot fill the machine with tiles wide
+    // enough to stay off the L2 -> SM ingest limit; two K slices on 256-row pair tiles can (experimental: NSB_FFDOWN_SPLIT=2).
+    static const int big_split = [] { const char* e = getenv("NSB_FFDOWN_SPLIT"); return e ? atoi(e) : 1; }();
+    if (compute != NSB_COMPUTE_F32 && M > 1024 && W.n_in >= 4096 && big_split > 1 && (size_t)big_split * M * D_MODEL * 4 <= part_.bytes) splits = big_split;
     if (splits == 1) { gemm(A, lda, W, M, nullptr, x, D_MODEL, EPI_RESID, alpha, OUT_F32); return; }
     GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.w_scales = W.scales.p; a.M = M; a.N = W.n_out; a.K = W.n_in; a.C = part_.p; a.ldc = D_MODEL;
     a.epi = EPI_PARTIAL; a.out_type = OUT_F32; a.splits = splits;
@@ -410,13 +418,13 @@ void Engine::gemm_residual(const void* A, long long lda, const Weight& W, int M,
 // streams (host bookkeeping only; all arithmetic is on the device)
 // ------------------------------------------------------------------------------------------
 int Engine::open_stream() {
-    if (!inflight_.empty()) step_end();
+    collect_all();
     for (int s = 0; s < max_streams; ++s)
         if (!hs_[s].open) { zero_slot(s); hs_[s].open = true; return s; }
     throw std::runtime_error("no free stream slot (max_streams = " + std::to_string(max_streams) + ")");
 }
-void Engine::close_stream(int s) { if (!inflight_.empty()) step_end(); if (s < 0 || s >= max_streams || !hs_[s].open) throw std::invalid_argument("bad stream id"); hs_[s].open = false; }
-void Engine::reset_stream(int s) { if (!inflight_.empty()) step_end(); if (s < 0 || s >= max_streams || !hs_[s].open) throw std::invalid_argument("bad stream id"); zero_slot(s); }
+void Engine::close_stream(int s) { collect_all(); if (s < 0 || s >= max_streams || !hs_[s].open) throw std::invalid_argument("bad stream id"); hs_[s].open = false; }
+void Engine::reset_stream(int s) { collect_all(); if (s < 0 || s >= max_streams || !hs_[s].open) throw std::invalid_argument("bad stream id"); zero_slot(s); }
 
 void Engine::push_pcm(int s, const int16_t* pcm, int n) {
     if (s < 0 || s >= max_streams || !hs_[s].open) throw std::invalid_argument("bad stream id");
@@ -441,54 +449,69 @@ static void stage_row(const HostStream& h, int T, int rl, int16_t* dst) {
     if (zeros < rl) memcpy(dst + zeros, h.buf.data() + (size_t)(start + zeros - h.base), (size_t)(rl - zeros) * sizeof(int16_t));
 }
 
+// Up to two steps in flight: step i+1 is staged and enqueued while step i runs, so the device never waits for the host between
+// steps. Host buffers (pinned PCM rows, slots, token ids) are double-buffered; the device-side step workspace is shared --
+// everything is ordered on the engine stream.
 int Engine::step_begin() {
-    if (!inflight_.empty()) throw std::runtime_error("step_begin: the previous step has not been collected (call step_end)");
+    if (n_inflight_ == 2) throw std::runtime_error("step_begin: two steps are already in flight (call step_end)");
     NSB_CUDA(cudaSetDevice(device_));
     std::vector<int> batch;
     for (int s = 0; s < max_streams; ++s) if (ready(s)) batch.push_back(s);
     const int B = (int)batch.size();
     if (!B) return 0;
-    int16_t* hp = h_pcm_.as<int16_t>(); int* hsl = h_slot_.as<int>();
-    for (int b = 0; b < B; ++b) { stage_row(hs_[batch[b]], T, rl_, hp + (size_t)b * rl_); hsl[b] = batch[b]; }
+    StepIO& io = io_[io_next_];
+    int16_t* hp = io.h_pcm.as<int16_t>(); int* hsl = io.h_slot.as<int>();
+    for (int b = 0; b < B; ++b) {
+        HostStream& h = hs_[batch[b]];
+        stage_row(h, T, rl_, hp + (size_t)b * rl_); hsl[b] = batch[b];
+        h.chunk_idx += 1;                                                 // launched: ready() now asks for the NEXT chunk
+        // drop samples no later chunk needs: next row starts at 1280 T c' - 257
+        const long long keep_from = std::max(0LL, 8LL * T * HOP * h.chunk_idx - N_FFT / 2 - 1);
+        if (keep_from > h.base) { h.buf.erase(h.buf.begin(), h.buf.begin() + (size_t)(keep_from - h.base)); h.base = keep_from; }
+    }
     NSB_CUDA(cudaMemcpyAsync(d_pcm_.p, hp, (size_t)B * rl_ * 2, cudaMemcpyHostToDevice, st_));
     NSB_CUDA(cudaMemcpyAsync(d_slot_.p, hsl, (size_t)B * 4, cudaMemcpyHostToDevice, st_));
-    NSB_CUDA(cudaEventRecord(ev0_, st_));
+    NSB_CUDA(cudaEventRecord(io.ev0, st_));
     run_step(B, d_pcm_.as<int16_t>());
-    NSB_CUDA(cudaEventRecord(ev1_, st_));
-    NSB_CUDA(cudaMemcpyAsync(h_cnt_.p, out_cnt_.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st_));
-    NSB_CUDA(cudaMemcpyAsync(h_tok_.p, out_tok_.p, (size_t)B * MAX_SYMBOLS * T * 4, cudaMemcpyDeviceToHost, st_));
-    inflight_ = std::move(batch);
+    NSB_CUDA(cudaEventRecord(io.ev1, st_));
+    NSB_CUDA(cudaMemcpyAsync(io.h_cnt.p, out_cnt_.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st_));
+    NSB_CUDA(cudaMemcpyAsync(io.h_tok.p, out_tok_.p, (size_t)B * MAX_SYMBOLS * T * 4, cudaMemcpyDeviceToHost, st_));
+    NSB_CUDA(cudaEventRecord(io.done, st_));
+    io.batch = std::move(batch);
+    io_next_ ^= 1; n_inflight_ += 1;
     return B;
 }
 
 int Engine::step_end() {
-    if (inflight_.empty()) return 0;
+    if (n_inflight_ == 0) return 0;
     NSB_CUDA(cudaSetDevice(device_));
-    const int B = (int)inflight_.size();
-    std::vector<int> batch = std::move(inflight_);
-    inflight_.clear();
-    NSB_CUDA(cudaStreamSynchronize(st_));
-    float ms = 0.f; NSB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    StepIO& io = io_[n_inflight_ == 2 ? io_next_ : io_next_ ^ 1];         // the OLDEST step in flight
+    n_inflight_ -= 1;
+    const int B = (int)io.batch.size();
+    NSB_CUDA(cudaEventSynchronize(io.done));
+    float ms = 0.f; NSB_CUDA(cudaEventElapsedTime(&ms, io.ev0, io.ev1));
     stats.steps += 1; stats.chunks += B; stats.device_ms += ms; stats.last_step_ms = ms;
-    collect_tokens(B, batch);
+    collect_tokens(io);
+    io.batch.clear();
     return B;
 }
 
+void Engine::collect_all() { while (n_inflight_) step_end(); }
+
 int Engine::step() {
+    collect_all();
     const int B = step_begin();
     if (B) step_end();
     return B;
 }
 
-void Engine::collect_tokens(int B, const std::vector<int>& batch) {
-    const int* cnt = h_cnt_.as<int>(); const int* tok = h_tok_.as<int>();
+void Engine::collect_tokens(StepIO& io) {
+    const int* cnt = io.h_cnt.as<int>(); const int* tok = io.h_tok.as<int>();
+    const int B = (int)io.batch.size();
     for (int b = 0; b < B; ++b) {
-        HostStream& h = hs_[batch[b]];
+        HostStream& h = hs_[io.batch[b]];
         for (int i = 0; i < cnt[b] && i < MAX_SYMBOLS * T; ++i) h.tokens.push_back(tok[(size_t)b * MAX_SYMBOLS * T + i]);
-        h.chunk_idx += 1;
-        // drop samples no later chunk needs: next row starts at 1280 T c' - 257
-        const long long keep_from = std::max(0LL, 8LL * T * HOP * h.chunk_idx - N_FFT / 2 - 1);
-        if (keep_from > h.base) { h.buf.erase(h.buf.begin(), h.buf.begin() + (size_t)(keep_from - h.base)); h.base = keep_from; }
+        h.chunks_done += 1;
     }
 }
 
@@ -498,7 +521,7 @@ int Engine::pop_tokens(int s, int32_t* out, int cap) {
     while (n < cap && !h.tokens.empty()) { out[n++] = h.tokens.front(); h.tokens.pop_front(); }
     return n;
 }
-int Engine::chunks(int s) const { if (s < 0 || s >= max_streams) throw std::invalid_argument("bad stream id"); return (int)hs_[s].chunk_idx; }
+int Engine::chunks(int s) const { if (s < 0 || s >= max_streams) throw std::invalid_argument("bad stream id"); return (int)hs_[s].chunks_done; }
 
 // tokens_to_text (src/nemo-ggml.cpp:1432-1458, timestamps off): piece starting with U+2581 -> ' ' + rest
 std::string Engine::detok(const int32_t* t, int n) const {
@@ -708,7 +731,7 @@ void Engine::bench_prepare(int n_streams, const int16_t* pcm, int samples_per_st
     const long long need_stage = (long long)HOP * (8LL * T * (warm_chunks + n_chunks) - 1) + N_FFT / 2;
     for (int i = 0; i < n_streams; ++i) push_pcm(ids[i], pcm + (size_t)i * samples_per_stream + need_warm, (int)(need_stage - need_warm));
     bench_pcm_.alloc((size_t)n_chunks * n_streams * rl_ * 2, false);
-    int16_t* hp = h_pcm_.as<int16_t>(); int* hsl = h_slot_.as<int>();
+    int16_t* hp = io_[0].h_pcm.as<int16_t>(); int* hsl = io_[0].h_slot.as<int>();
     for (int k = 0; k < n_chunks; ++k) {
         for (int b = 0; b < n_streams; ++b) {
             HostStream& h = hs_[ids[b]];
@@ -732,7 +755,7 @@ const int16_t* Engine::bench_next_pcm() {
 
 float Engine::bench_step() {
     if (!bench_B_) throw std::runtime_error("bench_step before bench_prepare");
-    if (!inflight_.empty()) step_end();
+    collect_all();
     NSB_CUDA(cudaSetDevice(device_));
     NSB_CUDA(cudaEventRecord(ev0_, st_));
     run_step(bench_B_, bench_next_pcm());
@@ -746,7 +769,7 @@ float Engine::bench_step() {
 float Engine::bench_steps(int n, float* ms_each) {
     if (!bench_B_) throw std::runtime_error("bench_steps before bench_prepare");
     if (n < 1) throw std::invalid_argument("bench_steps: n < 1");
-    if (!inflight_.empty()) step_end();
+    collect_all();
     NSB_CUDA(cudaSetDevice(device_));
     ev_used_ = 0;
     std::vector<cudaEvent_t> ev((size_t)n + 1);

@@ -52,7 +52,7 @@ struct LayerW {
 struct HostStream {
     bool open = false;
     std::vector<int16_t> buf;      // raw samples from absolute index `base`
-    long long base = 0, n_pushed = 0, chunk_idx = 0;
+    long long base = 0, n_pushed = 0, chunk_idx = 0, chunks_done = 0;   // chunk_idx: next chunk to LAUNCH; chunks_done: chunks whose tokens were collected
     std::deque<int32_t> tokens;
 };
 
@@ -66,8 +66,10 @@ public:
     bool ready(int s) const;
     int step();                       // returns #streams advanced
     // split form of step(): begin stages the ready streams' PCM, enqueues H2D + the step graph + D2H and returns at once
-    // (the host can push the next chunk meanwhile); end waits and hands the tokens to the per-stream queues.
-    int step_begin();                 // returns #streams in the launched step (0 = nothing ready)
+    // (the host can push the next chunk meanwhile); end waits for the OLDEST step in flight and hands its tokens to the
+    // per-stream queues. Up to two steps may be in flight (begin, begin, end, begin, end, ...): the device then goes from one
+    // step straight into the next.
+    int step_begin();                 // returns #streams in the launched step (0 = nothing ready); throws with two steps in flight
     int step_end();                   // returns #streams advanced (0 = no step in flight)
     int pop_tokens(int s, int32_t* out, int cap);
     int chunks(int s) const;
@@ -124,7 +126,14 @@ private:
     void run_step(int B, const int16_t* d_pcm);
     struct StepGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; };
     std::map<std::pair<int, const void*>, StepGraph> graphs_;
-    void collect_tokens(int B, const std::vector<int>& batch);
+    struct StepIO {                   // host side of one step in flight
+        HostPinned h_pcm, h_slot, h_tok, h_cnt;
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
+        std::vector<int> batch;       // batch row -> stream slot
+    };
+    StepIO io_[2]; int io_next_ = 0, n_inflight_ = 0;
+    void collect_tokens(StepIO& io);
+    void collect_all();               // step_end() until nothing is in flight
     int act_type() const { return compute == NSB_COMPUTE_F32 ? OUT_F32 : (compute == NSB_COMPUTE_BF16 ? OUT_BF16 : OUT_F16); }
     size_t act_size() const { return compute == NSB_COMPUTE_F32 ? 4 : 2; }
     void count_launch(int n = 1) { stats.kernel_launches += n; }
@@ -155,9 +164,7 @@ private:
     int rl_ = 0;                   // PCM row length per stream-step
     DevBuf d_pcm_, d_slot_, mel_new_, dw_, pw_, x_, a_, big_, qkv_, pw1_, encp_, part_;
     DevBuf out_tok_, out_cnt_, dec_sync_;
-    HostPinned h_pcm_, h_slot_, h_tok_, h_cnt_;
     int consumer_planes_ = 1;         // planes the qkv_ / pw1_ buffers were sized for (split-K partials summed by the consumer kernels)
-    std::vector<int> inflight_;       // batch -> stream slot of the step launched by step_begin()
 
     // ---- bench ----
     DevBuf wscratch_;                 // fp16 copy of ONE Q8_0 matrix (large batches), rewritten before every GEMM that uses it

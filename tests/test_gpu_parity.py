@@ -398,8 +398,6 @@ def test_split_step_overlapping_the_next_push_equals_plain_step(built):
         if pos < audio.shape[1]:
             b.push_batch(ids2, audio[:, pos:pos + step]); pos += step    # overlaps the step in flight
         if n:
-            with pytest.raises(nsb200.NsbError):
-                b.step_begin()                                           # at most one step in flight
             assert b.step_end() == n
         toks, cnt = b.pop_tokens_batch(ids2, 64)
         for s in range(5):
@@ -409,6 +407,56 @@ def test_split_step_overlapping_the_next_push_equals_plain_step(built):
     for s in range(5):
         assert got[s] == ref[s].tolist(), s
         assert b.chunks(ids2[s]) == a.chunks(ids[s])
+    a.close(); b.close()
+
+
+@pytest.mark.gpu
+def test_two_steps_in_flight_equal_plain_steps(built):
+    """begin, begin, end, begin, end, ...: step i+1 is staged and enqueued while step i runs (double-buffered host side);
+    tokens, their order and the chunk counts equal the one-step-at-a-time run; a third begin is an error; ready() counts
+    launched chunks, chunks() collected ones; reset while two steps are in flight collects them first."""
+    import nsb200
+    R = 1
+    path = synth.cached_model("f32", 2, R=R)
+    audio = np.stack([synth.synth_pcm(150 + s, 1.5) for s in range(4)])
+    a = nsb200.Engine(path, right_context=R, max_streams=4, compute=nsb200.COMPUTE_F32)
+    ids = [a.open_stream() for _ in range(4)]
+    for s in range(4):
+        a.push(ids[s], audio[s])
+    a.drain()
+    ref = [a.pop_tokens(i) for i in ids]
+    b = nsb200.Engine(path, right_context=R, max_streams=4, compute=nsb200.COMPUTE_F32)
+    ids2 = [b.open_stream() for _ in range(4)]
+    b.push_batch(ids2, audio)                                            # everything up front: many chunks ready
+    got = [[] for _ in range(4)]
+    def collect():
+        toks, cnt = b.pop_tokens_batch(ids2, 64)
+        for s in range(4):
+            got[s] += toks[s, :cnt[s]].tolist()
+    assert b.step_begin() == 4
+    assert b.chunks(ids2[0]) == 0                                        # launched, not collected
+    n_launched = 1
+    while True:
+        n = b.step_begin()                                               # second step in flight
+        if n:
+            n_launched += 1
+            with pytest.raises(nsb200.NsbError):
+                b.step_begin()                                           # at most two
+        assert b.step_end() == 4                                         # the OLDEST one
+        collect()
+        if n == 0:
+            break
+    assert b.step_end() == 0
+    for s in range(4):
+        assert got[s] == ref[s].tolist(), s
+        assert b.chunks(ids2[s]) == a.chunks(ids[s]) == n_launched
+    # reset with steps in flight: collected first, then the slot starts over
+    b.reset_stream(ids2[0]); b.push(ids2[0], audio[0])
+    assert b.step_begin() == 1 and b.step_begin() == 1
+    b.reset_stream(ids2[0])
+    assert b.chunks(ids2[0]) == 0 and b.step_end() == 0
+    b.push(ids2[0], audio[0]); b.drain()
+    assert b.pop_tokens(ids2[0]).tolist() == ref[0].tolist()
     a.close(); b.close()
 
 

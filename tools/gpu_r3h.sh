@@ -1,0 +1,10 @@
+#!/bin/bash
+OUT=gpurun_out/${TAG:-r3h}; mkdir -p $OUT
+timeout 400 python -m pytest tests -m gpu -q -x > $OUT/pytest.log 2>&1; echo "pytest rc=$?"; tail -4 $OUT/pytest.log
+timeout 200 python bench.py --steps 50 --no-cpu-baseline > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; python -c "
+import json; d=json.load(open('$OUT/bench.json')); print('value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'], 'p50', d['p50_chunk_latency_ms'])"
+export NSB_BENCH_STREAMS=256 NSB_BENCH_R=6 NSB_BENCH_COMPUTE=f16 NSB_BENCH_KV=f16
+timeout 100 python tools/trace_step.py 2 2>&1 | head -1
+NSB_FFDOWN_SPLIT=2 NSB_SPLIT_BN=208 timeout 100 python tools/trace_step.py 2 2>&1 | head -1
+NSB_FFDOWN_SPLIT=2 NSB_SPLIT_BN=256 timeout 100 python tools/trace_step.py 2 > $OUT/trace_cfg3_split256.txt 2>&1; head -1 $OUT/trace_cfg3_split256.txt; grep -A8 'per kernel class' $OUT/trace_cfg3_split256.txt | cut -c1-180
+NSB_FFDOWN_SPLIT=4 NSB_SPLIT_BN=256 timeout 100 python tools/trace_step.py 2 2>&1 | head -1
