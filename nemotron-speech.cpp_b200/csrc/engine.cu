@@ -403,9 +403,11 @@ void Engine::gemm_residual(const void* A, long long lda, const Weight& W, int M,
         while (splits < MAX_SPLITS && tiles * splits < 120 && nk % (splits * 2) == 0 && nk / (splits * 2) >= 2) splits *= 2;
     }
     // Large batches, K = 4096 (FFN down-projections): with 14 x 8 tiles the N = 1024 GEMM cannot fill the machine with tiles wide
-    // enough to stay off the L2 -> SM ingest limit; two K slices on 256-row pair tiles can (experimental: NSB_FFDOWN_SPLIT=2).
-    static const int big_split = [] { const char* e = getenv("NSB_FFDOWN_SPLIT"); return e ? atoi(e) : 1; }();
-    if (compute != NSB_COMPUTE_F32 && M > 1024 && W.n_in >= 4096 && big_split > 1 && (size_t)big_split * M * D_MODEL * 4 <= part_.bytes) splits = big_split;
+    // enough to stay off the L2 -> SM ingest limit; four K slices on 256 x 256 pair tiles can (4 x 7 x 4 = 112 pairs). Measured at
+    // 256 streams x 560 ms: step 7.39 -> 7.23 ms with 4 slices (2 slices: 7.35 at BN = 208, 7.56 at BN = 256). NSB_FFDOWN_SPLIT=1: off.
+    static const int big_split = [] { const char* e = getenv("NSB_FFDOWN_SPLIT"); return e ? atoi(e) : 4; }();
+    // (not in Q8_0 mode: behind the per-launch dequantisation the split measured slower, 7.83 -> 7.96 ms)
+    if ((compute == NSB_COMPUTE_F16 || compute == NSB_COMPUTE_BF16) && M > 1024 && W.n_in >= 4096 && big_split > 1 && (size_t)big_split * M * D_MODEL * 4 <= part_.bytes) splits = big_split;
     if (splits == 1) { gemm(A, lda, W, M, nullptr, x, D_MODEL, EPI_RESID, alpha, OUT_F32); return; }
     GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.w_scales = W.scales.p; a.M = M; a.N = W.n_out; a.K = W.n_in; a.C = part_.p; a.ldc = D_MODEL;
     a.epi = EPI_PARTIAL; a.out_type = OUT_F32; a.splits = splits;

@@ -1012,7 +1012,7 @@ void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
     if (a.splits > 1) {
         if (a.epi != EPI_PARTIAL || (a.K / BK) % a.splits != 0) throw CudaError("gemm_tc: bad split-K request");
         if (fmt != 2 && tiles_m >= 8 && pair256_enabled()) {            // large-batch split-K (FFN down): wide pair tiles
-            static const int bn = [] { const char* e = getenv("NSB_SPLIT_BN"); return e ? atoi(e) : 208; }();
+            static const int bn = [] { const char* e = getenv("NSB_SPLIT_BN"); return e ? atoi(e) : 256; }();
             launch_pair256(a, fmt, bn, st); return;
         }
         if (a.N % 128 == 0 && a.M > 128 && fmt == 2) { launch_cfg<128, 4>(a, fmt, st); return; }
