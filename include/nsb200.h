@@ -65,7 +65,7 @@ typedef struct nsb_stats {
 typedef struct nsb_model_info {
     int32_t n_mels, d_model, n_heads, d_head, d_ff, n_layers, kernel_size, vocab_size, decoder_dim, joint_dim;
     int32_t n_tensors;
-    int32_t weight_type;      /* ggml type of the per-layer matrices: 0 F32, 1 F16, 8 Q8_0 */
+    int32_t weight_type;      /* ggml type of the per-layer matrices: 0 F32, 1 F16, 2 Q4_0, 8 Q8_0 */
     char vocab[1025 * 8];     /* char8 pieces, NUL padded (bounded copy + zero fill)        */
 } nsb_model_info;
 int nsb_gguf_probe(const char* gguf_path, nsb_model_info* info);

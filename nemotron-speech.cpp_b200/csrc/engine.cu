@@ -53,6 +53,13 @@ std::vector<float> read_matrix_f32(const GgufFile& g, const std::string& name) {
             const int8_t* q = (const int8_t*)&raw[b * 34 + 2];
             for (int i = 0; i < 32; ++i) out[b * 32 + i] = d * (float)q[i];
         }
+    } else if (t.type == GGML_Q4_0) {                     // block = fp16 d + 16 nibble bytes: element i = low nibble of byte i, i + 16 = high nibble;
+        const size_t nb = out.size() / 32;                // value = d * (q - 8) (convert_to_gguf.py:132-179)
+        for (size_t b = 0; b < nb; ++b) {
+            uint16_t h; memcpy(&h, &raw[b * 18], 2); const float d = half_bits_to_float(h);
+            const uint8_t* q = &raw[b * 18 + 2];
+            for (int i = 0; i < 16; ++i) { out[b * 32 + i] = d * (float)((int)(q[i] & 0x0F) - 8); out[b * 32 + 16 + i] = d * (float)((int)(q[i] >> 4) - 8); }
+        }
     } else throw std::runtime_error("unsupported tensor type for " + name);
     return out;
 }
@@ -114,7 +121,8 @@ Engine::Engine(const std::string& path, const nsb_engine_config& cfg) : cfg_(cfg
     compute = cfg.compute;
     if (compute == NSB_COMPUTE_AUTO) {
         const int t = g.require("encoder.layers.0.feed_forward1.linear1.weight").type;
-        compute = t == GGML_F32 ? NSB_COMPUTE_F32 : t == GGML_F16 ? NSB_COMPUTE_F16 : NSB_COMPUTE_Q8_0;
+        // Q4_0 files: the matrices are expanded to fp16 at load (d * (q - 8) rounded once) and run on the fp16 tcgen05 path
+        compute = t == GGML_F32 ? NSB_COMPUTE_F32 : (t == GGML_F16 || t == GGML_Q4_0) ? NSB_COMPUTE_F16 : NSB_COMPUTE_Q8_0;
     }
     load_weights(g);
     alloc_state();

@@ -96,8 +96,11 @@ void GgufFile::open(const std::string& p) {
             case GGML_Q8_0:
                 if (t.ne.empty() || t.ne[0] % 32) throw std::runtime_error("gguf: Q8_0 tensor '" + t.name + "' ne0 % 32 != 0");
                 t.nbytes = (size_t)n / 32 * 34; break;
+            case GGML_Q4_0:
+                if (t.ne.empty() || t.ne[0] % 32) throw std::runtime_error("gguf: Q4_0 tensor '" + t.name + "' ne0 % 32 != 0");
+                t.nbytes = (size_t)n / 32 * 18; break;
             default: throw std::runtime_error("gguf: tensor '" + t.name + "' has unsupported type " + std::to_string(t.type) +
-                                              " (supported: F32, F16, Q8_0)");
+                                              " (supported: F32, F16, Q8_0, Q4_0)");
         }
         tensors[t.name] = t;
     }

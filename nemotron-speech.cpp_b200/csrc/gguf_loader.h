@@ -1,7 +1,7 @@
 // gguf_loader.h -- minimal GGUF v3 reader for the nemotron-speech weight layout.
 // Replaces the gguf_* / ggml_dup_tensor / fread loop of the reference loader
 // (src/nemo-ggml.cpp:83-256); file layout per scripts/convert_to_gguf.py:407-447 and
-// docs/TENSOR_SHAPES.md. Tensor bytes are kept exactly as stored (F32 / F16 / Q8_0).
+// docs/TENSOR_SHAPES.md. Tensor bytes are kept exactly as stored (F32 / F16 / Q8_0 / Q4_0).
 #pragma once
 #include <cstdint>
 #include <map>

@@ -56,7 +56,7 @@ inline float siluf_(float x) { return x / (1.0f + expf(-x)); }           // ggml
 
 enum { MM_REF = 0, MM_F16 = 1, MM_BF16 = 2, MM_Q8FAST = 3 };
 enum { KV_F32 = 0, KV_F16 = 1, KV_BF16 = 2 };
-enum { GT_F32 = 0, GT_F16 = 1, GT_Q8_0 = 8 };
+enum { GT_F32 = 0, GT_F16 = 1, GT_Q4_0 = 2, GT_Q8_0 = 8 };
 
 // One weight matrix [n_out, n_in] (ggml ne0 = n_in contiguous).
 struct Mat {
@@ -136,7 +136,7 @@ Model* load_model(const char* path, int mm_mode, int kv_mode) {
     uint64_t pos = (uint64_t)ftell(f); uint64_t data0 = (pos + align - 1) / align * align;
     for (auto& t : ti) {
         int64_t n = 1; for (auto d : t.ne) n *= d;
-        size_t nbytes = t.type == GT_F32 ? (size_t)n * 4 : t.type == GT_F16 ? (size_t)n * 2 : t.type == GT_Q8_0 ? (size_t)n / 32 * 34 : 0;
+        size_t nbytes = t.type == GT_F32 ? (size_t)n * 4 : t.type == GT_F16 ? (size_t)n * 2 : t.type == GT_Q8_0 ? (size_t)n / 32 * 34 : t.type == GT_Q4_0 ? (size_t)n / 32 * 18 : 0;
         if (!nbytes) { fprintf(stderr, "oracle: unsupported tensor type %d (%s)\n", t.type, t.name.c_str()); fclose(f); delete m; return nullptr; }
         std::vector<uint8_t> raw(nbytes);
         fseek(f, (long)(data0 + t.off), SEEK_SET);
@@ -157,6 +157,15 @@ Model* load_model(const char* path, int mm_mode, int kv_mode) {
         if (t.type == GT_F32) { M.w.resize((size_t)n); memcpy(M.w.data(), raw.data(), nbytes); M.act = 0; }
         else if (t.type == GT_F16) { M.w.resize((size_t)n);
             for (int64_t i = 0; i < n; ++i) { uint16_t h; memcpy(&h, &raw[2 * i], 2); M.w[i] = f16_bits_to_f32(h); } M.act = 1; }
+        else if (t.type == GT_Q4_0) {
+            // Q4_0 block = fp16 d + 16 nibble bytes, element i = low nibble of byte i, element i + 16 = high nibble, value d * (q - 8)
+            // (convert_to_gguf.py:132-179). ggml dots it against Q8_0-quantised activations with integer block sums
+            // (vec_dot_q4_0_q8_0): the same arithmetic as the Q8_0 path below with quants q - 8 in [-8, 7].
+            size_t nb = (size_t)n / 32; M.q.resize((size_t)n); M.d.resize(nb);
+            for (size_t b = 0; b < nb; ++b) { uint16_t h; memcpy(&h, &raw[b * 18], 2); M.d[b] = f16_bits_to_f32(h);
+                for (int i = 0; i < 16; ++i) { const uint8_t v = raw[b * 18 + 2 + i];
+                    M.q[b * 32 + i] = (int8_t)((int)(v & 0x0F) - 8); M.q[b * 32 + 16 + i] = (int8_t)((int)(v >> 4) - 8); } }
+            M.act = 3; }
         else { size_t nb = (size_t)n / 32; M.q.resize((size_t)n); M.d.resize(nb);
             for (size_t b = 0; b < nb; ++b) { uint16_t h; memcpy(&h, &raw[b * 34], 2); M.d[b] = f16_bits_to_f32(h);
                 memcpy(&M.q[b * 32], &raw[b * 34 + 2], 32); } M.act = 3; }

@@ -200,6 +200,7 @@ def test_streaming_parity_f32_full_24_layer_model(built):
     ("f16", 0, 1, O.MM_REF, O.KV_F16, 3e-3, 2e-2, 1),       # F16 GGUF -> ggml F16 semantics (+ fp16 K/V ring)
     ("f32", 3, 2, O.MM_BF16, O.KV_BF16, 3e-2, 2e-1, 1),
     ("q8_0", 0, 0, O.MM_Q8FAST, O.KV_F32, 3e-3, 2e-2, 1),
+    ("q4_0", 0, 0, O.MM_Q8FAST, O.KV_F32, 3e-3, 2e-2, 1),    # Q4_0 GGUF: matrices expanded to fp16 at load, fp16 tcgen05 path
     ("f16", 0, 1, O.MM_REF, O.KV_F16, 3e-3, 2e-2, 0),       # 80 ms mode (T = 1): paired attention kernel, odd batches
     ("f16", 0, 1, O.MM_REF, O.KV_F16, 3e-3, 2e-2, 6),       # 560 ms mode (T = 7): tiled attention kernel with a 16-bit ring
 ])

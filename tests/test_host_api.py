@@ -44,6 +44,7 @@ def test_gguf_probe_and_errors(built, tmp_path):
     info = nsb200.probe(synth.cached_model("q8_0", 2, R=0))
     assert (info.n_layers, info.d_model, info.vocab_size, info.n_tensors, info.weight_type) == (2, 1024, 1025, 81, 8)
     assert nsb200.probe(synth.cached_model("f32", 2, R=0)).weight_type == 0
+    assert nsb200.probe(synth.cached_model("q4_0", 2, R=0)).weight_type == 2          # Q4_0 blocks (18 bytes per 32 weights) are sized and located
     with pytest.raises(nsb200.NsbError, match="cannot open"):
         nsb200.probe(str(tmp_path / "missing.gguf"))
     bad = tmp_path / "bad.gguf"

@@ -164,16 +164,42 @@ def test_q8_0_activation_quantisation_matches_gguf_package(built):
     assert np.abs(y - ref).max() <= 2e-6 * np.abs(ref).max()
 
 
+def test_q4_0_weights_match_gguf_package(built):
+    """Q4_0 files (the converter's other quantised type, convert_to_gguf.py:132-179): the synthetic writer's blocks dequantise
+    to the same values as the gguf package's (nibble order, d = amax / 7), and the oracle's ggml-semantics matmul
+    (Q8_0-quantised activations x Q4_0 weights, integer block dots) agrees with that arithmetic done in numpy."""
+    import gguf
+    from gguf import quants
+    path = synth.cached_model("q4_0", 2, R=0)
+    r = gguf.GGUFReader(path)
+    name = "encoder.layers.0.self_attn.linear_q.weight"
+    t = [t for t in r.tensors if t.name == name][0]
+    assert t.tensor_type.name == "Q4_0"
+    w = quants.dequantize(t.data, t.tensor_type).astype(np.float64)                     # d_w * (q_w - 8)
+    wf = [t for t in gguf.GGUFReader(synth.cached_model("f32", 2, R=0)).tensors if t.name == name][0].data.astype(np.float64)
+    assert np.abs(w - wf.reshape(w.shape)).max() <= np.abs(wf).max() / 7.0 * 0.51 + 1e-6  # within half a quantisation step (+ fp16 d)
+    m = O.Model(path, O.MM_REF)
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((3, 1024)).astype(np.float32)
+    y = m.matmul(name, x)
+    xq = quants.dequantize(quants.quantize(x, gguf.GGMLQuantizationType.Q8_0), gguf.GGMLQuantizationType.Q8_0).astype(np.float64)
+    ref = xq @ w.T
+    assert np.abs(y - ref).max() <= 2e-6 * np.abs(ref).max()
+    # engine-mirror arithmetic (weights expanded to fp16 once, fp16 activations): close to the exact product of the dequantised values
+    y2 = O.Model(path, O.MM_Q8FAST).matmul(name, x)
+    assert np.abs(y2 - x.astype(np.float64) @ w.T).max() <= 3e-3 * np.abs(ref).max()
+
+
 def test_synthetic_gguf_layout_is_readable_by_gguf_package(built):
     import gguf
-    for kind in ("f32", "f16", "q8_0"):
+    for kind in ("f32", "f16", "q8_0", "q4_0"):
         r = gguf.GGUFReader(synth.cached_model(kind, 2, R=0))
         assert len(r.tensors) == 12 + 2 * 26 + 9 + 6 + 2
         names = {t.name: t for t in r.tensors}
         dw = names["encoder.layers.0.conv.depthwise_conv.weight"]
         assert list(dw.shape) == [1024, 9] and dw.tensor_type.name == "F32"          # tap-major, never quantised
         lin = names["encoder.layers.1.feed_forward1.linear1.weight"]
-        assert lin.tensor_type.name == {"f32": "F32", "f16": "F16", "q8_0": "Q8_0"}[kind]
+        assert lin.tensor_type.name == {"f32": "F32", "f16": "F16", "q8_0": "Q8_0", "q4_0": "Q4_0"}[kind]
         assert names["joint.enc.weight"].tensor_type.name == "F32"
         assert names["encoder.pre_encode.out.weight"].tensor_type.name == "F32"
         keys = list(r.fields.keys())

@@ -30,7 +30,7 @@ GGUF_MAGIC = b"GGUF"
 GGUF_VERSION = 3
 ALIGN = 32
 T_U32, T_STR = 4, 8
-GGML_F32, GGML_F16, GGML_Q8_0 = 0, 1, 8
+GGML_F32, GGML_F16, GGML_Q4_0, GGML_Q8_0 = 0, 1, 2, 8
 
 D_MODEL, D_FF, N_HEADS, D_HEAD = 1024, 4096, 8, 128
 N_MELS, N_BINS, WIN = 128, 257, 400
@@ -237,6 +237,22 @@ def quantize_q8_0(data: np.ndarray) -> bytes:
     return blk.tobytes()
 
 
+def quantize_q4_0(data: np.ndarray) -> bytes:
+    """Q4_0 block = fp16 d + 16 bytes of nibbles (convert_to_gguf.py:132-179): d = amax/7, q = clip(round(x / fp16(d)), -8, 7) + 8;
+    byte i of a block holds element i in its low nibble and element i + 16 in its high nibble."""
+    flat = np.ascontiguousarray(data, dtype=np.float32).reshape(-1, 32)
+    amax = np.max(np.abs(flat), axis=1)
+    scales = np.where(amax != 0, amax / 7.0, 0.0).astype(np.float16)
+    sf = scales.astype(np.float32)[:, None]
+    safe = np.where(sf != 0, sf, 1.0)
+    q = np.clip(np.round(flat / safe), -8, 7)
+    q = (np.where(sf != 0, q, 0) + 8).astype(np.uint8)
+    blk = np.empty(flat.shape[0], dtype=np.dtype([("d", np.float16), ("q", np.uint8, 16)]))
+    blk["d"] = scales
+    blk["q"] = (q[:, :16] & 0x0F) | (q[:, 16:] << 4)
+    return blk.tobytes()
+
+
 def gguf_prepare(name: str, data: np.ndarray, wtype: str):
     """Apply the converter's reshape + quantise decision. Returns (dims_reversed, ggml_type, bytes)."""
     if PW_RE.search(name) and data.ndim == 3:
@@ -250,6 +266,8 @@ def gguf_prepare(name: str, data: np.ndarray, wtype: str):
         return dims, GGML_F16, data.astype(np.float16).tobytes()
     if do_q and wtype == "q8_0":
         return dims, GGML_Q8_0, quantize_q8_0(data)
+    if do_q and wtype == "q4_0":
+        return dims, GGML_Q4_0, quantize_q4_0(data)
     return dims, GGML_F32, np.ascontiguousarray(data, dtype=np.float32).tobytes()
 
 
@@ -326,6 +344,8 @@ def _prepared_size(name, shape, wtype):
         return dims, GGML_F16, n * 2
     if do_q and wtype == "q8_0":
         return dims, GGML_Q8_0, n // 32 * 34
+    if do_q and wtype == "q4_0":
+        return dims, GGML_Q4_0, n // 32 * 18
     return dims, GGML_F32, n * 4
 
 
@@ -390,7 +410,7 @@ def sine_pcm(seconds: float, freq: float = 440.0, sr: int = 16000) -> np.ndarray
 
 def cached_model(kind: str, n_layers: int, seed: int = 1234, cache_dir: str | None = None, R: int | None = 1,
                  profile: str = "parity") -> str:
-    """Materialise (once) and return the path of a synthetic model file. kind: f32|f16|q8_0|nemo.
+    """Materialise (once) and return the path of a synthetic model file. kind: f32|f16|q8_0|q4_0|nemo.
     R = latency mode whose calibration (tools/calib/) shapes joint.enc.bias and the blank bias;
     profile = "parity" (tests) | "speech" (bench: speech-like token rate, see load_calibration)."""
     cache_dir = cache_dir or os.environ.get("NSB_SYNTH_DIR", "/tmp/nsb200_synth")
@@ -411,7 +431,7 @@ def cached_model(kind: str, n_layers: int, seed: int = 1234, cache_dir: str | No
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("out")
-    ap.add_argument("--type", default="f32", choices=["f32", "f16", "q8_0", "nemo"])
+    ap.add_argument("--type", default="f32", choices=["f32", "f16", "q8_0", "q4_0", "nemo"])
     ap.add_argument("--layers", type=int, default=24)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--right-context", type=int, default=1)
