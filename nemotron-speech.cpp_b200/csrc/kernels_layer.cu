@@ -876,7 +876,11 @@ template <int KV>
 static void launch_attention_t(const AttnArgs& a, cudaStream_t st) {
     if (a.T > ATT_MAX_T) throw CudaError("attention: att_right_context too large");
     if constexpr (KV != 0) {                                                      // 16-bit ring: tensor-core kernel (T <= 16), else the paired / tiled scalar kernels
-        if (a.T <= 16 && attention_mma_enabled()) { if (a.T <= 2) launch_attention_mma<KV, 2>(a, st); else launch_attention_mma<KV, 1>(a, st); return; }
+        if (a.T <= 16 && attention_mma_enabled()) {
+            static const bool ns1 = [] { const char* e = getenv("NSB_ATT_NS1"); return e && e[0] == '1'; }();   // experiment: single-stream CTAs for T <= 2 too
+            if (a.T <= 2 && !ns1) launch_attention_mma<KV, 2>(a, st); else launch_attention_mma<KV, 1>(a, st);
+            return;
+        }
         if (a.T <= 2 && attention_pair_enabled()) { if (a.T == 1) launch_attention_pair<KV, 1>(a, st); else launch_attention_pair<KV, 2>(a, st); return; }
     }
     if (a.T == 1) launch_attention_tq<KV, 1>(a, st);
