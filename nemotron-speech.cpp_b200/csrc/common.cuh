@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <stdexcept>
@@ -68,6 +69,21 @@ inline void launch_k_cluster(void (*kern)(P...), dim3 grid, dim3 block, size_t s
     if (pdl_enabled()) { at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
     cfg.attrs = at; cfg.numAttrs = n;
     NSB_CUDA(cudaLaunchKernelEx(&cfg, kern, P(std::forward<A>(args))...));
+}
+
+// cudaFuncSetAttribute acts on the CURRENT device only. One process may hold one engine per GPU (one host thread each), so the
+// "already configured" memo of a kernel is kept per device ordinal, never per process: `slots` is a function-local
+// `static std::atomic<size_t> [MAX_DEVICES]` (zero-initialised), raised to the largest dynamic shared-memory size asked for so far.
+constexpr int MAX_DEVICES = 64;
+template <typename K>
+inline void ensure_dyn_smem(K kern, size_t bytes, std::atomic<size_t>* slots, bool max_carveout = false) {
+    int dev = 0;
+    NSB_CUDA(cudaGetDevice(&dev));
+    std::atomic<size_t>& done = slots[dev & (MAX_DEVICES - 1)];
+    if (bytes <= done.load(std::memory_order_acquire)) return;
+    NSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (max_carveout) NSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    done.store(bytes, std::memory_order_release);
 }
 
 // ------------------------------------------------------------------------------------------

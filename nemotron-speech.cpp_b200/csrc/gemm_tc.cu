@@ -824,12 +824,9 @@ CUtensorMap make_map_u8(const void* ptr, int rows, int K, int box_rows) {
 
 template <int BN, int STAGES>
 void launch_cfg_q8(const GemmArgs& a, cudaStream_t st) {
-    static bool attr_set = false;
+    static std::atomic<size_t> attr_set[MAX_DEVICES];
     const size_t smem = sizeof(SmemQ8<BN, STAGES>) + 1024;
-    if (!attr_set) {
-        NSB_CUDA(cudaFuncSetAttribute(gemm_q8_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    ensure_dyn_smem(gemm_q8_kernel<BN, STAGES>, smem, attr_set);
     if (a.K / 64 / a.splits > 64) throw CudaError("gemm_q8: k range per CTA too long for the scale buffer");
     const CUtensorMap tmA = make_map(a.A, a.M, a.K, a.lda, BM, 0);
     const CUtensorMap tmQ = make_map_u8(a.W, a.N, a.K, BN);
@@ -849,12 +846,9 @@ bool multicast_enabled() {
 
 template <int BN, int STAGES, int EB, int CL>
 void launch_cfg_c(const GemmArgs& a, int fmt, cudaStream_t st) {
-    static bool attr_set = false;
+    static std::atomic<size_t> attr_set[MAX_DEVICES];
     const size_t smem = sizeof(Smem<BN, STAGES>) + 1024;
-    if (!attr_set) {
-        NSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EB, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    ensure_dyn_smem(gemm_tc_kernel<BN, STAGES, EB, CL>, smem, attr_set);
     const CUtensorMap tmA = make_map(a.A, a.M, a.K, a.lda, BM / CL, fmt);
     const CUtensorMap tmB = make_map(a.W, a.N, a.K, a.K, BN, fmt);
     const int m_out = a.c_group > 0 ? (a.M / a.c_group) * (a.c_group - a.c_drop) : a.M;
@@ -864,12 +858,9 @@ void launch_cfg_c(const GemmArgs& a, int fmt, cudaStream_t st) {
 }
 template <int BN, int STAGES>
 void launch_cfg_pair(const GemmArgs& a, int fmt, cudaStream_t st) {
-    static bool attr_set = false;
+    static std::atomic<size_t> attr_set[MAX_DEVICES];
     const size_t smem = sizeof(SmemPair<BN, STAGES>) + 1024;
-    if (!attr_set) {
-        NSB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    ensure_dyn_smem(gemm_tc_pair_kernel<BN, STAGES>, smem, attr_set);
     const CUtensorMap tmA = make_map(a.A, a.M, a.K, a.lda, 64, fmt);
     const CUtensorMap tmB = make_map(a.W, a.N, a.K, a.K, BN / 2, fmt);
     const int m_out = a.c_group > 0 ? (a.M / a.c_group) * (a.c_group - a.c_drop) : a.M;
@@ -880,12 +871,9 @@ void launch_cfg_pair(const GemmArgs& a, int fmt, cudaStream_t st) {
 
 template <int BN, int STAGES>
 void launch_cfg_pair256(const GemmArgs& a, int fmt, cudaStream_t st) {
-    static bool attr_set = false;
+    static std::atomic<size_t> attr_set[MAX_DEVICES];
     const size_t smem = sizeof(SmemPair2<BN, STAGES>) + 1024;
-    if (!attr_set) {
-        NSB_CUDA(cudaFuncSetAttribute(gemm_tc_pair256_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    ensure_dyn_smem(gemm_tc_pair256_kernel<BN, STAGES>, smem, attr_set);
     const CUtensorMap tmA = make_map(a.A, a.M, a.K, a.lda, BM, fmt);
     const CUtensorMap tmB = make_map(a.W, a.N, a.K, a.K, BN / 2, fmt);
     const int m_out = a.c_group > 0 ? (a.M / a.c_group) * (a.c_group - a.c_drop) : a.M;

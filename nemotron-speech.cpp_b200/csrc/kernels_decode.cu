@@ -325,18 +325,20 @@ __global__ void __launch_bounds__(NT, 1) rnnt_decode_kernel(const DecodeArgs a) 
 }
 }  // namespace
 
-static int g_decode_grid = 0;
-static int decode_grid() {
-    if (g_decode_grid == 0) {
-        int dev = 0, sms = 0, per_sm = 0;
-        NSB_CUDA(cudaGetDevice(&dev));
+static int decode_grid() {                 // per device ordinal: the attribute below and the SM count belong to the CURRENT device
+    static std::atomic<int> grids[MAX_DEVICES];
+    int dev = 0;
+    NSB_CUDA(cudaGetDevice(&dev));
+    std::atomic<int>& g = grids[dev & (MAX_DEVICES - 1)];
+    if (g.load(std::memory_order_acquire) == 0) {
+        int sms = 0, per_sm = 0;
         NSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         NSB_CUDA(cudaFuncSetAttribute(rnnt_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem)));
         NSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rnnt_decode_kernel, NT, sizeof(DecSmem)));
         if (per_sm < 1) throw CudaError("decode kernel cannot be resident");
-        g_decode_grid = sms;                                                      // one CTA per SM: co-residency guaranteed
+        g.store(sms, std::memory_order_release);                                  // one CTA per SM: co-residency guaranteed
     }
-    return g_decode_grid;
+    return g.load(std::memory_order_acquire);
 }
 size_t decode_sync_bytes(int B) { return 16 + (size_t)3 * B * sizeof(unsigned long long); }
 

@@ -580,11 +580,8 @@ template <int KV, int TQ>
 static void launch_attention_pair(const AttnArgs& a, cudaStream_t st) {
     using E = typename KvT<KV>::type;
     const size_t smem = (size_t)(ATT_L + 2 * a.T - 1) * D_HEAD * sizeof(E) + 2 * (sizeof(AttnSmemF<TQ>) + (size_t)2 * (ATT_L + a.T) * D_HEAD * sizeof(E));
-    static bool configured = false;
-    if (!configured) {
-        NSB_CUDA(cudaFuncSetAttribute(attention_pair_kernel<KV, TQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static std::atomic<size_t> configured[MAX_DEVICES];
+    ensure_dyn_smem(attention_pair_kernel<KV, TQ>, smem, configured);
     launch_k(attention_pair_kernel<KV, TQ>, dim3(N_HEADS, (a.B + 1) / 2), dim3(512), smem, st, a);
 }
 static bool attention_pair_enabled() {
@@ -847,13 +844,9 @@ __global__ void __launch_bounds__(128 * NS, NS == 2 ? 2 : 4) attention_mma_kerne
 template <int KV, int NS>
 static void launch_attention_mma(const AttnArgs& a, cudaStream_t st) {
     const AttnMmaLayout lay(a.T, NS, NS == 1);
-    static size_t configured = 0;
-    if (lay.total > configured) {
-        NSB_CUDA(cudaFuncSetAttribute(attention_mma_kernel<KV, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
-        // largest shared-memory carve-out: the resident CTAs per SM are limited by shared memory, not by L1
-        NSB_CUDA(cudaFuncSetAttribute(attention_mma_kernel<KV, NS>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        configured = lay.total;
-    }
+    static std::atomic<size_t> configured[MAX_DEVICES];
+    // largest shared-memory carve-out: the resident CTAs per SM are limited by shared memory, not by L1
+    ensure_dyn_smem(attention_mma_kernel<KV, NS>, lay.total, configured, true);
     launch_k(attention_mma_kernel<KV, NS>, dim3(N_HEADS, (a.B + NS - 1) / NS), dim3(128 * NS), lay.total, st, a);
 }
 static bool attention_mma_enabled() {
@@ -865,11 +858,8 @@ template <int KV, int TQ>
 static void launch_attention_tq(const AttnArgs& a, cudaStream_t st) {
     using E = typename KvT<KV>::type;
     const size_t smem = sizeof(AttnSmemF<TQ>) + (size_t)2 * (ATT_L + a.T) * D_HEAD * sizeof(E);
-    static size_t configured = 0;
-    if (smem > configured) {
-        NSB_CUDA(cudaFuncSetAttribute(attention_kernel<KV, TQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static std::atomic<size_t> configured[MAX_DEVICES];
+    ensure_dyn_smem(attention_kernel<KV, TQ>, smem, configured);
     launch_k(attention_kernel<KV, TQ>, dim3(N_HEADS, a.B), dim3(256), smem, st, a);
 }
 template <int KV>

@@ -1,0 +1,120 @@
+"""nemotron-asr-serve (csrc/serve_main.cpp): the multi-stream / multi-GPU host program over the C ABI.
+CPU: argument handling and the reference CLI's failure behaviour (exit code 1 + "Failed to load model" / "Failed to open audio
+file", transcribe_stream.cpp:102-105,131-137), no CPU fallback. GPU: transcripts of ragged streams run in waves through the
+batched engine == the oracle's per-stream transcripts; --flush == the oracle on zero-padded audio; --realtime == throughput mode."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "nemotron-speech.cpp_b200", "nemotron-asr-serve")
+
+
+@pytest.fixture(scope="module")
+def exe(built):
+    if not os.path.exists(EXE):
+        subprocess.check_call(["make", "-C", os.path.dirname(EXE), "nemotron-asr-serve"], stdout=subprocess.DEVNULL)
+    return EXE
+
+
+def run(exe, *args, timeout=300):
+    return subprocess.run([exe, *map(str, args)], capture_output=True, text=True, timeout=timeout)
+
+
+def test_usage_and_load_failures(exe, tmp_path):
+    r = run(exe)
+    assert r.returncode == 1 and "Usage:" in r.stderr
+    r = run(exe, tmp_path / "none.gguf", tmp_path / "a.pcm")
+    assert r.returncode == 1 and "Failed to load model" in r.stderr and "cannot open" in r.stderr
+    model = synth.cached_model("f32", 2, R=1)
+    r = run(exe, model)                                              # no input at all
+    assert r.returncode == 1 and "Usage:" in r.stderr
+    r = run(exe, model, tmp_path / "missing.pcm")
+    assert r.returncode == 1 and "Failed to open audio file" in r.stderr
+    r = run(exe, model, "--compute", "int3", "--synthetic", "1", "1")
+    assert r.returncode == 1 and "Usage:" in r.stderr
+    r = run(exe, model, "--bogus")
+    assert r.returncode == 1 and "unknown option" in r.stderr
+
+
+def test_no_cpu_fallback(exe):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the -m gpu tests")
+    r = run(exe, synth.cached_model("f32", 2, R=1), "--right-context", "1", "--synthetic", "3", "0.5", "--gpus", "2")
+    assert r.returncode == 1 and r.stdout == ""
+    assert "GPU 0: Failed to load model: no CUDA device" in r.stderr and "GPU 1: Failed to load model" in r.stderr
+
+
+def _oracle_tokens(path, R, pcm):
+    import oracle as O
+    om = O.Model(path)
+    st = O.Stream(om, R)
+    st.push(pcm)
+    return om, st.tokens(), st.chunks
+
+
+def _parse(stdout):
+    rows = {}
+    for line in stdout.splitlines():
+        idx, name, text, toks = (line.split("\t") + [""])[:4]
+        rows[int(idx)] = (name, text, [int(t) for t in toks.split()] if toks else [])
+    return rows
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra", [[], ["--realtime"]])
+def test_ragged_streams_in_waves_match_the_oracle(exe, tmp_path, extra):
+    """5 streams of different lengths (one shorter than a chunk, one empty) over 2 stream slots = 3 waves with slot reuse."""
+    R = 1
+    path = synth.cached_model("f32", 2, R=R)
+    secs = [1.3, 0.9, 0.1, 2.0, 0.0]
+    if extra:
+        secs = [0.7, 0.5, 0.1]                                        # real-time pacing: keep it short
+    files, want = [], []
+    for i, s in enumerate(secs):
+        pcm = synth.synth_pcm(300 + i, s) if s > 0 else np.zeros(0, np.int16)
+        f = tmp_path / f"s{i}.pcm"
+        pcm.tofile(f)
+        files.append(f)
+        om, toks, chunks = _oracle_tokens(path, R, pcm) if s > 0 else (None, np.zeros(0, np.int32), 0)
+        want.append((list(map(int, toks)), chunks))
+    om = _oracle_tokens(path, R, synth.synth_pcm(300, 0.2))[0]
+    lst = tmp_path / "list.txt"
+    lst.write_text("\n".join(map(str, files[2:])) + "\n")
+    r = run(exe, path, "--right-context", R, "--compute", "f32", "--max-streams", 2, "--tokens", *extra, files[0], files[1], "--list", lst)
+    assert r.returncode == 0, r.stderr
+    rows = _parse(r.stdout)
+    assert sorted(rows) == list(range(len(secs)))
+    for i, (toks, chunks) in enumerate(want):
+        assert rows[i][0] == str(files[i])
+        assert rows[i][2] == toks, (i, rows[i][2], toks)
+        assert rows[i][1] == om.detok(np.asarray(toks, np.int32))
+    assert f"Chunks processed:    {sum(c for _, c in want)}" in r.stderr
+    assert ("Chunk latency:" in r.stderr) == bool(extra)
+
+
+@pytest.mark.gpu
+def test_flush_decodes_the_tail_like_zero_padded_audio(exe, tmp_path):
+    R = 6
+    path = synth.cached_model("f32", 2, R=R)
+    T, n = R + 1, int(1.9 * 16000)
+    pcm = synth.synth_pcm(77, 1.9)[:n]
+    f = tmp_path / "a.pcm"
+    pcm.tofile(f)
+    plain = run(exe, path, "--right-context", R, "--compute", "f32", "--tokens", f)
+    flushed = run(exe, path, "--right-context", R, "--compute", "f32", "--tokens", "--flush", f)
+    assert plain.returncode == 0 and flushed.returncode == 0, plain.stderr + flushed.stderr
+    frames = (n - 1) // 160 + 1
+    chunks = -(-frames // (8 * T))
+    padded = np.concatenate([pcm, np.zeros(1280 * T * chunks + 96 - n, np.int16)])
+    _, toks_plain, c_plain = _oracle_tokens(path, R, pcm)
+    _, toks_pad, c_pad = _oracle_tokens(path, R, padded)
+    assert c_pad == chunks and c_pad > c_plain
+    assert _parse(plain.stdout)[0][2] == list(map(int, toks_plain))
+    assert _parse(flushed.stdout)[0][2] == list(map(int, toks_pad))
+    assert f"Chunks processed:    {c_pad}" in flushed.stderr
