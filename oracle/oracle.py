@@ -224,6 +224,7 @@ def ref():
         R.ref_weights_free.argtypes = [C.c_void_p]
         R.ref_subsampling.argtypes = [C.c_void_p, _f32p, C.c_int, _f32p, C.c_int]
         R.ref_layer_forward.argtypes = [C.c_void_p, C.c_int, _f32p, C.c_int, _f32p]
+        R.ref_cached_layer_step.argtypes = [C.c_void_p, C.c_int, _f32p, C.c_int, _f32p, C.c_int, _f32p, C.c_int, _f32p, _f32p, _f32p]
         R.ref_greedy.argtypes = [C.c_void_p, _f32p, C.c_int, _i32p, C.c_int]
         R.ref_joint_logits.argtypes = [C.c_void_p, _f32p, C.c_int, _f32p]
         _ref = R
@@ -266,6 +267,18 @@ class RefWeights:
         y = np.empty_like(x)
         ref().ref_layer_forward(self.h, l, x.reshape(-1), x.shape[0], y.reshape(-1))
         return y
+
+    def cached_layer_step(self, l: int, x: np.ndarray, att_hist: np.ndarray, conv_hist: np.ndarray):
+        """One cached streaming step of layer l from the reference's compiled modules (ref_shim.cpp:ref_cached_layer_step).
+        Returns (y, histories rolled forward: last 70 attention-input rows, last 8 conv-input rows)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        att_hist = np.ascontiguousarray(att_hist, dtype=np.float32).reshape(-1, 1024)
+        conv_hist = np.ascontiguousarray(conv_hist, dtype=np.float32).reshape(-1, 1024)
+        y, an, cn = np.empty_like(x), np.empty_like(x), np.empty_like(x)
+        dummy = np.zeros(1, np.float32)
+        ref().ref_cached_layer_step(self.h, l, x.reshape(-1), x.shape[0], att_hist.reshape(-1) if len(att_hist) else dummy, len(att_hist),
+                                    conv_hist.reshape(-1) if len(conv_hist) else dummy, len(conv_hist), y.reshape(-1), an.reshape(-1), cn.reshape(-1))
+        return y, np.concatenate([att_hist, an])[-70:], np.concatenate([conv_hist, cn])[-8:]
 
     def greedy(self, enc: np.ndarray) -> np.ndarray:
         enc = np.ascontiguousarray(enc, dtype=np.float32)

@@ -11,15 +11,17 @@
 // sits on ggml (ggml-org/ggml, un-vendored, unpinned HEAD, absent here, no network), so it
 // cannot be compiled. What DOES compile from /root/reference (src/preprocessor.cpp and the
 // naive src/reference/*.cpp model) is built into oracle/_ref/libnemo_ref.so by oracle/Makefile
-// and is used by tests/test_oracle_vs_ref.py to pin this file:
+// and is used by tests/test_oracle.py to pin this file:
 //   * log-mel                      == src/preprocessor.cpp              (bit-exact)
 //   * subsampling / conformer layer / LSTM / joint / greedy  == src/reference/*.cpp (<=1e-4)
 //   * first streaming chunk (cache empty => fully masked) == non-cached encoder of src/reference
-// PARITY PINNING STATUS: pinned for mel, subsampling, layer math, decoder, joint, greedy against
-// the reference's own code run here; the *cache carry-over across chunks*, the F16 and the Q8_0
-// matmul numerics are restated from source reading (nemo-stream.cpp) / upstream ggml semantics
-// and are pinned only by self-consistency properties (chunked == unchunked conv, ring == roll) --
-// "parity unpinned" at that boundary, exactly as SURVEY.md 8(c) states.
+//   * the CACHED step in f32, every latency mode, whole streams past the roll of the 70-row cache == the reference's compiled
+//     modules run on [history | chunk] windows (oracle/ref_shim.cpp:ref_cached_layer_step; tokens identical, tensors 2e-6)
+// PARITY PINNING STATUS: the f32 streaming path is pinned end to end against the reference's own code run here (committed
+// fixtures: tests/golden/). What stays "parity unpinned", exactly as SURVEY.md 8(c) states: ggml itself (src/nemo-stream.cpp
+// cannot be compiled, so the cached GRAPH is checked through src/reference, which the reference's tests/test_compute.cpp holds
+// equal to its ggml graphs for the non-cached modules) and the F16 / Q8_0 / Q4_0 matmul numerics, restated from upstream ggml
+// semantics and checked against the gguf package's quantisers only.
 //
 // Every function cites the reference file:line it follows (paths relative to /root/reference).
 // Build: see oracle/Makefile (-O2 -ffp-contract=off so f32 arithmetic is mul-then-add like the

@@ -293,6 +293,23 @@ def test_first_chunk_matches_reference_golden(built):
     eng.close()
 
 
+@pytest.mark.parametrize("R,secs", [(0, 6.0), (1, 6.6), (6, 7.5), (13, 9.0)])
+def test_cached_streaming_matches_reference_golden(built, R, secs):
+    """tests/golden/cached_ref_L2.npz: whole streams run past the roll of the 70-row cache on the reference's own compiled
+    modules (tools/make_golden.py section 3). The CUDA path, strict fp32: identical greedy tokens, last chunk's encoder output
+    <= 1e-4 relative."""
+    import nsb200
+    g = np.load(os.path.join(GOLD, "cached_ref_L2.npz"))
+    eng = nsb200.Engine(synth.cached_model("f32", 2, R=0), right_context=R, max_streams=1, compute=nsb200.COMPUTE_F32)
+    eng.debug_enable(True)
+    s = eng.open_stream()
+    eng.push(s, synth.synth_pcm(11, secs))
+    assert eng.drain() == int(g[f"chunks_R{R}"]) == eng.chunks(s)
+    assert rel(eng.debug_get("enc", 1), g[f"enc_last_R{R}"]) < 1e-4
+    assert np.array_equal(eng.pop_tokens(s), g[f"tokens_R{R}"])
+    eng.close()
+
+
 def test_ring_cache_equals_rolled_cache_and_reset(built):
     import nsb200
     R = 6

@@ -15,6 +15,7 @@ import oracle as O  # noqa: E402
 import synth  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
+CACHED_CASES = [(0, 6.0), (1, 6.6), (6, 7.5), (13, 9.0)]       # (att_right_context, seconds of synth_pcm(11, .)): 74 / 82 / 91 / 112 encoder frames
 
 
 def main():
@@ -43,6 +44,28 @@ def main():
     logits0 = rw.joint_logits(x[0], 1024)
     np.savez_compressed(os.path.join(OUT, "model_ref_L2.npz"), chunk=chunk, sub=sub, layer0=layers[0], layer1=layers[1],
                         tokens=toks.astype(np.int32), logits0=logits0)
+    # 3. CACHED streaming past the cache roll, every latency mode, free-running on the reference's compiled modules only
+    #    (ConvSubsampling::forward per chunk, oracle/ref_shim.cpp:ref_cached_layer_step per layer, GreedyDecoder::decode over all
+    #    frames): all tokens + the encoder output of the last chunk (the cache has rolled by then)
+    gold = {}
+    for R, secs in CACHED_CASES:
+        T = 1 + R
+        pcm = synth.synth_pcm(11, secs)
+        m = O.RefPreproc(fb, win).process(pcm)
+        att = [np.zeros((0, 1024), np.float32) for _ in range(2)]
+        conv = [np.zeros((0, 1024), np.float32) for _ in range(2)]
+        carry, encs = np.zeros((9, 128), np.float32), []
+        for c in range(len(m) // (8 * T)):
+            ch = np.concatenate([carry, m[8 * T * c:8 * T * (c + 1)]]); carry = ch[-9:]
+            x = rw.subsampling(ch)[2:]
+            for l in range(2):
+                x, att[l], conv[l] = rw.cached_layer_step(l, x, att[l], conv[l])
+            encs.append(x)
+        assert len(encs) * T > 70 + T
+        gold[f"tokens_R{R}"] = rw.greedy(np.concatenate(encs)).astype(np.int32)
+        gold[f"enc_last_R{R}"] = encs[-1]
+        gold[f"chunks_R{R}"] = np.int32(len(encs))
+    np.savez_compressed(os.path.join(OUT, "cached_ref_L2.npz"), **gold)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
