@@ -118,3 +118,38 @@ def test_flush_decodes_the_tail_like_zero_padded_audio(exe, tmp_path):
     assert _parse(plain.stdout)[0][2] == list(map(int, toks_plain))
     assert _parse(flushed.stdout)[0][2] == list(map(int, toks_pad))
     assert f"Chunks processed:    {c_pad}" in flushed.stderr
+
+
+@pytest.mark.gpu
+def test_two_gpus_in_one_process(exe, tmp_path):
+    """One process, one engine + one host thread per GPU (stream s on GPU s mod 2). Strict fp32: every stream == the oracle.
+    bf16 (tcgen05 GEMMs, tensor-core attention, per-device kernel configuration): the concurrent 2-GPU run == the same streams run
+    on each device alone (same batches, deterministic kernels)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    R = 1
+    path = synth.cached_model("f32", 2, R=R)
+    secs = [1.3, 0.9, 1.1, 2.0, 0.6, 1.6]
+    files, want = [], []
+    for i, s in enumerate(secs):
+        pcm = synth.synth_pcm(400 + i, s)
+        f = tmp_path / f"t{i}.pcm"
+        pcm.tofile(f)
+        files.append(f)
+        want.append(list(map(int, _oracle_tokens(path, R, pcm)[1])))
+    r = run(exe, path, "--right-context", R, "--compute", "f32", "--gpus", 2, "--max-streams", 2, "--tokens", *files)
+    assert r.returncode == 0, r.stderr
+    assert "GPU 0: 3 streams in 2 wave(s)" in r.stderr and "GPU 1: 3 streams in 2 wave(s)" in r.stderr
+    rows = _parse(r.stdout)
+    for i in range(len(secs)):
+        assert rows[i][2] == want[i], i
+    both = run(exe, path, "--right-context", R, "--compute", "bf16", "--gpus", 2, "--tokens", *files)
+    assert both.returncode == 0, both.stderr
+    got = _parse(both.stdout)
+    for dev in (0, 1):
+        alone = run(exe, path, "--right-context", R, "--compute", "bf16", "--devices", dev, "--tokens", *files[dev::2])
+        assert alone.returncode == 0, alone.stderr
+        solo = _parse(alone.stdout)
+        for k, i in enumerate(range(dev, len(secs), 2)):
+            assert len(solo[k][2]) > 0 and solo[k][2] == got[i][2], (dev, i)
