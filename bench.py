@@ -45,6 +45,24 @@ T = 1 + RIGHT_CONTEXT
 CHUNK_S = 0.08 * T
 
 
+# BASELINE.json configs by number (configs[0] is the CPU case = --impl reference). The driver's default run is config 2;
+# the others are selected with --config N for the per-config evidence under profiles/ (same timing legs, same JSON line).
+#        streams/GPU, att_right_context, GGUF type, compute, K/V ring
+CONFIGS = {2: (64, 1, "f16", "bf16", "bf16"),
+           3: (256, 6, "q8_0", "q8_0", "f16"),
+           4: (128, 0, "f16", "bf16", "bf16"),
+           5: (64, 13, "f16", "bf16", "bf16")}
+WEIGHTS, COMPUTE, KV = "f16", "bf16", "bf16"
+
+
+def select_config(n: int):
+    global STREAMS, RIGHT_CONTEXT, T, CHUNK_S, WEIGHTS, COMPUTE, KV, WARM_CHUNKS
+    STREAMS, RIGHT_CONTEXT, WEIGHTS, COMPUTE, KV = CONFIGS[n]
+    T = 1 + RIGHT_CONTEXT
+    CHUNK_S = 0.08 * T
+    WARM_CHUNKS = max(8, 70 // T + 3)                  # > 70 / T: the attention cache is full before timing
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -127,7 +145,7 @@ def gemm_algorithmic_bytes(rows: int, elem: int = 2):
     return total * N_LAYERS, len(shapes) * N_LAYERS
 
 
-def gemm_roofline(eng, rows: int, elem: int = 2, iters: int = 10):
+def gemm_roofline(eng, rows: int, elem: int = 2, iters: int = 10, w_elem: float | None = None):
     """Dominant kernel = the tcgen05 layer GEMM (8 launches per conformer layer). Timed live, alone: for each of the six
     distinct shapes, 24 layers x `iters` launches back to back on the engine's stream (every launch on a different layer's
     weights: 24 x 2-8 MB > L2, so weights stream from HBM), CUDA events around the loop; same tile / split-K choice as the
@@ -135,18 +153,22 @@ def gemm_roofline(eng, rows: int, elem: int = 2, iters: int = 10):
     often each shape occurs in a layer."""
     # kind: (N, K, bytes per C element incl. read-modify-write, occurrences per layer)
     kinds = {0: (4096, 1024, elem, 2), 1: (1024, 4096, 8, 2), 2: (3072, 1024, 4, 1), 3: (1024, 1024, 8, 1), 4: (2048, 1024, 4, 1), 5: (1024, 1024, 8, 1)}
-    tot_us = tot_bytes = 0.0; n = 0; per = {}
+    w_elem = elem if w_elem is None else w_elem       # HBM bytes per weight (Q8_0 blocks: 34 / 32)
+    tot_us = tot_bytes = tot_flops = 0.0; n = 0; per = {}
     for kind, (N, K, cb, occ) in kinds.items():
         splits = 1
         if N == 1024 and rows <= 1024:                        # Engine::gemm_residual's split-K rule
             tiles = ((rows + 127) // 128) * (N // (64 if K >= 4096 else 32)); nk = K // 64
             while splits < 8 and tiles * splits < 120 and nk % (splits * 2) == 0 and nk // (splits * 2) >= 2:
                 splits *= 2
+        elif N == 1024 and K >= 4096 and rows > 1024 and w_elem == elem:
+            splits = 4                                            # Engine::gemm_residual: FFN down-projection on 4 K slices of 256 x 256 pair tiles
         us = eng.bench_gemm(kind, rows, 0, 0, splits, 0, iters)
-        b = N * K * elem + rows * K * elem + rows * N * cb
-        per[("ff_up", "ff_down", "qkv", "attn_out", "pw1", "pw2")[kind]] = {"us": round(us, 2), "GBps": round(b / us / 1e3, 1), "splits": splits}
-        tot_us += us * occ; tot_bytes += b * occ; n += occ
-    return tot_bytes / n, tot_us / n, per
+        b = N * K * w_elem + rows * K * elem + rows * N * cb
+        per[("ff_up", "ff_down", "qkv", "attn_out", "pw1", "pw2")[kind]] = {"us": round(us, 2), "GBps": round(b / us / 1e3, 1),
+                                                                           "TFLOPs": round(2.0 * rows * N * K / us / 1e6, 1), "splits": splits}
+        tot_us += us * occ; tot_bytes += b * occ; tot_flops += 2.0 * rows * N * K * occ; n += occ
+    return tot_bytes / n, tot_us / n, per, tot_flops / n
 
 
 def cpu_baseline(threads: int | None, seconds: float = 1.6, streams: int = 2):
@@ -198,7 +220,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config number (default 2 = the headline)")
     args = ap.parse_args()
+    if args.config != 2:
+        select_config(args.config)
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         run_reference(args, rank)
@@ -217,11 +242,13 @@ def main():
 
     # synthetic model (f16 GGUF of the 24-layer architecture, cast to bf16 at load) + per-stream synthetic PCM
     if rank == 0 or world == 1:
-        path = synth.cached_model("f16", N_LAYERS, R=RIGHT_CONTEXT, profile=PROFILE)
+        path = synth.cached_model(WEIGHTS, N_LAYERS, R=RIGHT_CONTEXT, profile=PROFILE)
     if world > 1:
         dist.barrier()
-        path = synth.cached_model("f16", N_LAYERS, R=RIGHT_CONTEXT, profile=PROFILE)
-    eng = nsb200.Engine(path, right_context=RIGHT_CONTEXT, max_streams=STREAMS, compute=nsb200.COMPUTE_BF16, kv_dtype=nsb200.KV_BF16, device=local,
+        path = synth.cached_model(WEIGHTS, N_LAYERS, R=RIGHT_CONTEXT, profile=PROFILE)
+    compute = {"f16": nsb200.COMPUTE_F16, "bf16": nsb200.COMPUTE_BF16, "q8_0": nsb200.COMPUTE_Q8_0}[COMPUTE]
+    kv = {"f16": nsb200.KV_F16, "bf16": nsb200.KV_BF16}[KV]
+    eng = nsb200.Engine(path, right_context=RIGHT_CONTEXT, max_streams=STREAMS, compute=compute, kv_dtype=kv, device=local,
                         cuda_graph=os.environ.get("NSB_BENCH_GRAPH", "1") != "0")
     shift = eng.shift_samples
     BENCH_CHUNKS = 8                                       # distinct chunks staged in HBM; the timed steps cycle through them
@@ -262,9 +289,10 @@ def main():
     # ---- per-kernel-class breakdown + roofline of the dominant kernel (layer GEMMs) ----
     prof, prof_total = eng.bench_profile()
     g_ms, g_n = prof["layer_gemm"]
-    b_launch, us_launch, per_shape = gemm_roofline(eng, STREAMS * T)
+    rows = STREAMS * T
+    b_launch, us_launch, per_shape, f_launch = gemm_roofline(eng, rows, w_elem=34.0 / 32.0 if COMPUTE == "q8_0" else None)
     achieved = b_launch / us_launch / 1e3
-    roofline = {"bound": "hbm", "kernel": "gemm_tc_kernel (tcgen05 layer GEMMs, 8 launches per conformer layer, M = 128 token rows)",
+    roofline = {"bound": "hbm", "kernel": f"gemm_tc_kernel (tcgen05 layer GEMMs, 8 launches per conformer layer, M = {rows} token rows)",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch, occurrence-weighted over the 8 launches of a layer, from the
                 # ncu --set full capture profiles/r01_ncu_full_gemm_summary.txt (A / C stay in L2, so it sits below the algorithmic bytes)
@@ -273,6 +301,12 @@ def main():
                 "algorithmic_bytes_per_launch": b_launch, "avg_launch_us": us_launch, "per_shape": per_shape,
                 "how": "CUDA events on the engine stream around 24 layers x 10 back-to-back launches per shape (kernel timed alone, weights from HBM)",
                 "note": "at 128 token rows every CTA re-reads the whole activation tile: the kernel is bound by per-SM L2->SM ingest (~75 GB/s per SM measured), not by HBM or the tensor pipe; DESIGN.md section 5"}
+    if rows >= 512:
+        # configs 3 and 5: past the ridge (~208 rows at 2-byte weights) the layer GEMMs are bound by the tensor pipe, not by HBM
+        tf = f_launch / us_launch / 1e6
+        roofline.update({"bound": "tensor", "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf / tf_peak, "traffic": None,
+                         "traffic_source": None, "algorithmic_flops_per_launch": f_launch,
+                         "note": "mean over the 8 layer GEMMs weighted by occurrence; per-shape TFLOP/s in per_shape (DESIGN.md section 5)"})
     breakdown = {k: {"ms": round(v[0], 4), "launches": v[1]} for k, v in prof.items()}
 
     # ---- end to end through the public C ABI with host buffers ----
@@ -324,13 +358,14 @@ def main():
         lat_sorted = sorted(lat)
         line = {"metric": "rtfx", "value": value, "unit": "audio_s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * t_dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16", "data": "synthetic",
+                "dtype": COMPUTE, "data": "synthetic",
                 "config": {"workload": f"nemotron-speech-streaming-en-0.6b architecture ({N_LAYERS} conformer layers, random-init synthetic weights), "
-                                       f"bf16 tcgen05 GEMMs, bf16 K/V ring, {STREAMS} concurrent streams per GPU, 160 ms chunks (att_right_context={RIGHT_CONTEXT}), "
+                                       f"{COMPUTE} tcgen05 GEMMs, {KV} K/V ring, {STREAMS} concurrent streams per GPU, {int(CHUNK_S * 1000)} ms chunks (att_right_context={RIGHT_CONTEXT}), "
                                        f"steady state after {WARM_CHUNKS} warm chunks; joint blank bias calibrated to a speech-like token rate "
                                        f"({e2e['tokens_per_audio_s']:.1f} tokens per audio second measured in the e2e leg)" if PROFILE == "speech" else
                                        f"nemotron-speech-streaming-en-0.6b architecture ({N_LAYERS} layers, synthetic weights, parity-test calibration = dense emission), {STREAMS} streams, R={RIGHT_CONTEXT}",
-                           "streams_per_gpu": STREAMS, "chunk_ms": int(CHUNK_S * 1000), "l2_policy": "per-step working set (weights 1.16 GB + K/V ring 0.45 GB) > 126 MB L2", "token_profile": PROFILE,
+                           "baseline_config": args.config, "streams_per_gpu": STREAMS, "chunk_ms": int(CHUNK_S * 1000),
+                           "l2_policy": f"per-step working set (weights {0.62 if COMPUTE == 'q8_0' else 1.16} GB + K/V ring {STREAMS * 6.88e-3:.2f} GB) > 126 MB L2", "token_profile": PROFILE,
                            "device_resident_input": f"{BENCH_CHUNKS} consecutive chunks per stream staged in HBM, cycled"},
                 "p50_chunk_latency_ms": lat_sorted[len(lat) // 2], "p99_chunk_latency_ms": lat_sorted[min(len(lat) - 1, int(0.99 * len(lat)))],
                 "wall_ms_per_step": 1e3 * wall_s / args.steps,

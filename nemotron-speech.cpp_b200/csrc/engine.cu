@@ -810,6 +810,7 @@ float Engine::bench_gemm(int kind, int rows, int bn, int stages, int splits, int
             if (splits > 1) { a.C = part_.p; a.epi = EPI_PARTIAL; a.out_type = OUT_F32; }
             else if (W.n_out == D_FF) { a.C = big_.p; a.epi = EPI_SILU; a.out_type = act_type(); }
             else { a.C = qkv_.p; a.epi = EPI_NONE; a.out_type = OUT_F32; }
+            q8_predequant(W, rows, a);                    // Q8_0 mode, >= 512 rows: the dequantisation pass is part of the launch, as in the step
             launch_gemm_tc(a, act_type(), st_);
         }
     };

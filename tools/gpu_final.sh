@@ -5,6 +5,7 @@ TAG=${1:-final}; OUT=gpurun_out/$TAG; mkdir -p $OUT
 timeout 600 python -m pytest tests -m gpu -q > $OUT/pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $OUT/smoke.log
 timeout 400 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; cut -c1-260 $OUT/bench.json
+for c in 3 4 5; do timeout 300 python bench.py --config $c --no-cpu-baseline > $OUT/bench_cfg$c.json 2> $OUT/bench_cfg$c.err; echo "bench cfg$c rc=$?"; cut -c1-200 $OUT/bench_cfg$c.json; done
 timeout 400 python bench.py --impl reference > $OUT/bench_reference.json 2> $OUT/bench_reference.err; echo "reference rc=$?"; cut -c1-200 $OUT/bench_reference.json
 timeout 200 python tools/ncu_step.py 2 > $OUT/plain.log 2>&1 &&
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $OUT/launches.csv python tools/ncu_step.py 2 > $OUT/ncu_launches.log 2>&1
