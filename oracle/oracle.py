@@ -69,6 +69,7 @@ def lib():
         L.orc_last_layer.argtypes = [C.c_void_p, C.c_int, _f32p, C.c_int]
         L.orc_get_cache.argtypes = [C.c_void_p, C.c_int, C.c_int, _f32p, C.c_int]
         L.orc_detok.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_char_p, C.c_int]
+        L.orc_transcribe_full.argtypes = [C.c_void_p, _f32p, C.c_int, _f32p, C.c_int, _i32p, _i32p, C.c_int, C.POINTER(C.c_int)]
         L.orc_set_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
@@ -100,6 +101,17 @@ class Model:
         rows = lib().orc_subsampling(self.h, mel, mel.shape[0], out, out.shape[0])
         assert rows > 0
         return out[:rows].copy()
+
+    def transcribe_full(self, mel: np.ndarray):
+        """Non-streaming batch path (nemo_encode, nemo-ggml.cpp:1467-1535) on a whole mel [M,128]:
+        returns (encoder output [T,1024], token ids, encoder frame of each token)."""
+        mel = np.ascontiguousarray(mel, dtype=np.float32)
+        cap_rows = mel.shape[0] // 8 + 4
+        enc = np.empty((cap_rows, 1024), dtype=np.float32)
+        toks = np.empty(cap_rows * 10, dtype=np.int32); frames = np.empty_like(toks); n = C.c_int(0)
+        T = lib().orc_transcribe_full(self.h, mel.reshape(-1), mel.shape[0], enc.reshape(-1), cap_rows, toks, frames, len(toks), C.byref(n))
+        assert T >= 0, T
+        return enc[:T].copy(), toks[:n.value].copy(), frames[:n.value].copy()
 
     def detok(self, toks) -> str:
         t = np.ascontiguousarray(toks, dtype=np.int32)

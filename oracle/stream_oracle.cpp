@@ -645,6 +645,30 @@ int orc_get_cache(void* sp, int which, int layer, float* out, int cap) {
     memcpy(out, &src[layer * per], per * 4); return (int)per; }
 
 // tokens_to_text (nemo-ggml.cpp:1432-1458, no timestamps): piece starting with E2 96 81 -> ' ' + rest
+// ---- non-streaming batch path: nemo_encode (nemo-ggml.cpp:1467-1535) = build_encoder (:961-1003: conv
+// subsampling of the WHOLE mel with no carried frames and no dropped frames, positional window of 2T-1 rows, non-cached layers)
+// + greedy_decode (:1109-1258, tokens stamped with their encoder frame, :1240). The non-cached layer is the cached one with an
+// empty cache: the 70 cache slots are masked (-1e9 -> exp underflows to exactly 0), the conv cache is the 8 zero rows of the
+// causal pad (:706-707), so one "chunk" of T = all frames through cached_layer IS build_conformer_layer (:768-818).
+// Returns T (encoder frames); enc_out [T,1024] (optional), toks / frames (optional, up to cap) with *n_tokens.
+int orc_transcribe_full(void* model, const float* mel, int M, float* enc_out, int cap_rows, int32_t* toks, int32_t* frames, int cap, int* n_tokens) {
+    const Model& m = *(Model*)model;
+    if (M <= 0) return 0;
+    std::vector<float> x; const int T = subsampling(m, mel, M, x);
+    Stream s; s.m = &m; s.T = T; s.R = T - 1; s.M = M; s.K = s.L + T;
+    init_stream(s);
+    for (int l = 0; l < m.n_layers; ++l) cached_layer(s, l, x);
+    if (enc_out) { if (T > cap_rows) return -T; memcpy(enc_out, x.data(), (size_t)T * 1024 * 4); }
+    int n = 0;
+    for (int t = 0; t < T; ++t) {
+        const size_t before = s.tokens.size();
+        decode_frame(s, &x[(size_t)t * 1024]);
+        for (size_t i = before; i < s.tokens.size(); ++i, ++n) if (n < cap) { if (toks) toks[n] = s.tokens[i]; if (frames) frames[n] = t; }
+    }
+    if (n_tokens) *n_tokens = n;
+    return T;
+}
+
 int orc_detok(void* model, const int32_t* toks, int n, char* out, int cap) {
     auto* m = (Model*)model; std::string r; int nv = (int)m->vocab.size() / 8;
     for (int i = 0; i < n; ++i) { int id = toks[i]; if (id < 0 || id >= nv) continue;

@@ -147,6 +147,33 @@ def test_cached_streaming_matches_reference_golden(built, model2, R, secs):
     assert np.array_equal(s.tokens(), g[f"tokens_R{R}"])
 
 
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref/libnemo_ref.so not built (needs /root/reference)")
+def test_batch_path_matches_compiled_reference(built, model2):
+    """SURVEY 8f.1, oracle side only (no CUDA batch path yet): the non-streaming nemo_encode path -- whole-utterance subsampling
+    with no carried / dropped frames, non-cached layers, greedy from a fresh decoder state -- against the reference's compiled
+    ConvSubsampling / ConformerLayer / GreedyDecoder."""
+    pcm = synth.synth_pcm(21, 3.0)
+    mel = O.Preproc(model=model2).process(pcm)
+    enc, toks, frames = model2.transcribe_full(mel)
+    rw = O.RefWeights(synth.cached_model("nemo", 2, R=0))
+    x = rw.subsampling(mel)
+    assert x.shape[0] == enc.shape[0] == ((len(mel) // 2 + 1) // 2 + 1) // 2 + 1            # three stride-2 convs with (2, 1) padding
+    for l in range(2):
+        x = rw.layer(l, x)
+    assert np.abs(enc - x).max() <= 1e-4 * np.abs(x).max()
+    assert len(toks) > 0 and np.array_equal(toks, rw.greedy(x))
+    assert np.all(np.diff(frames) >= 0) and frames.max() < enc.shape[0] and np.bincount(frames).max() <= 10
+
+
+def test_batch_path_matches_reference_golden(built, model2):
+    g = np.load(os.path.join(GOLD, "batch_ref_L2.npz"))              # tools/make_golden.py section 4
+    mel = O.Preproc(model=model2).process(synth.synth_pcm(21, 3.0))
+    assert len(mel) == int(g["n_mel"])
+    enc, toks, _ = model2.transcribe_full(mel)
+    assert np.abs(enc[::4] - g["enc_every4"]).max() <= 1e-4 * np.abs(g["enc_every4"]).max()
+    assert np.array_equal(toks, g["tokens"])
+
+
 def test_chunk_arithmetic_matches_reference_worked_example(built, model2):
     # SURVEY 8(a) row D (from nemo-stream.h:65-100, nemo-stream.cpp:1094-1127): 10 s, R = 13 -> 999 mel frames, 8 chunks
     pcm = synth.synth_pcm(1, 10.0)

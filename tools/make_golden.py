@@ -66,6 +66,13 @@ def main():
         gold[f"enc_last_R{R}"] = encs[-1]
         gold[f"chunks_R{R}"] = np.int32(len(encs))
     np.savez_compressed(os.path.join(OUT, "cached_ref_L2.npz"), **gold)
+    # 4. non-streaming batch path (nemo_encode): 3 s utterance, whole-mel subsampling + non-cached layers + greedy from a fresh state
+    pcm = synth.synth_pcm(21, 3.0)
+    m = O.RefPreproc(fb, win).process(pcm)
+    x = rw.subsampling(m)
+    for l in range(2):
+        x = rw.layer(l, x)
+    np.savez_compressed(os.path.join(OUT, "batch_ref_L2.npz"), n_mel=np.int32(len(m)), enc_every4=x[::4], tokens=rw.greedy(x).astype(np.int32))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
