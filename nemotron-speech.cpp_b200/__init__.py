@@ -51,7 +51,7 @@ EXPORTS = ["nsb_gguf_probe", "nsb_default_config", "nsb_engine_create", "nsb_eng
            "nsb_stream_open", "nsb_stream_close", "nsb_stream_reset", "nsb_stream_push_pcm", "nsb_push_pcm_batch", "nsb_pop_tokens_batch", "nsb_stream_ready", "nsb_engine_step", "nsb_engine_step_begin", "nsb_engine_step_end",
            "nsb_engine_drain", "nsb_stream_pop_tokens", "nsb_stream_chunks", "nsb_detokenize", "nsb_engine_get_stats",
            "nsb_bench_prepare", "nsb_bench_step", "nsb_bench_steps", "nsb_bench_profile", "nsb_profiler_range", "nsb_bench_gemm", "nsb_trace_enable", "nsb_trace_fetch", "nsb_debug_enable", "nsb_debug_get", "nsb_debug_get_cache", "nsb_op_logmel",
-           "nsb_op_gemm"]
+           "nsb_op_gemm", "nsb_transcribe_full"]
 
 
 def build(force: bool = False) -> str:
@@ -105,6 +105,7 @@ def lib():
         L.nsb_debug_get_cache.argtypes = [vp, ci, ci, ci, _f32p, C.c_size_t]
         L.nsb_op_logmel.argtypes = [vp, _i16p, ci, ci, _f32p, C.c_size_t]
         L.nsb_op_gemm.argtypes = [vp, C.c_char_p, _f32p, ci, _f32p, C.c_size_t]
+        L.nsb_transcribe_full.argtypes = [vp, _i16p, ci, _i32p, ci, C.POINTER(C.c_int), C.c_void_p, C.c_size_t]
         _lib = L
     return _lib
 
@@ -298,3 +299,15 @@ class Engine:
         y = np.empty((x.shape[0], 4096), dtype=np.float32)
         n_out = _check(lib().nsb_op_gemm(self.h, weight_name.encode(), x, x.shape[0], y.reshape(-1), y.size))
         return y.reshape(-1)[: x.shape[0] * n_out].reshape(x.shape[0], n_out).copy()
+
+    def transcribe_full(self, pcm: np.ndarray, want_enc: bool = True):
+        """Non-streaming batch path (nsb_transcribe_full; EXPERIMENTAL, see include/nsb200.h): one whole utterance ->
+        (token ids, encoder output [frames, 1024] or None)."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        frames_cap = len(pcm) // 1280 + 8
+        toks = np.empty(10 * frames_cap, dtype=np.int32)
+        enc = np.empty((frames_cap, 1024), dtype=np.float32) if want_enc else None
+        nf = C.c_int(0)
+        n = _check(lib().nsb_transcribe_full(self.h, pcm, len(pcm), toks, len(toks), C.byref(nf),
+                                             enc.ctypes.data_as(C.c_void_p) if want_enc else None, enc.size if want_enc else 0))
+        return toks[:n].copy(), (enc[:nf.value].copy() if want_enc else None)

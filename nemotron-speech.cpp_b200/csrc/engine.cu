@@ -88,7 +88,7 @@ void pos_emb_row(int p_int, float* row) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
-Engine::Engine(const std::string& path, const nsb_engine_config& cfg) : cfg_(cfg) {
+Engine::Engine(const std::string& path, const nsb_engine_config& cfg) : cfg_(cfg), gguf_path_(path) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         throw CudaError("no CUDA device available (this engine has no CPU fallback)");
@@ -967,6 +967,148 @@ long long Engine::op_logmel(const int16_t* pcm, int n_streams, int n_samples, fl
     NSB_CUDA(cudaStreamSynchronize(st_));
     NSB_CUDA(cudaMemcpy(out, d_out.p, d_out.bytes, cudaMemcpyDeviceToHost));
     return n_frames;
+}
+
+// ------------------------------------------------------------------------------------------
+// Non-streaming batch path. EXPERIMENTAL: written after this round's GPU budget was spent -- compiled, checked against
+// nothing on hardware yet (the checker exists: orc_transcribe_full + tests/golden/batch_ref_L2.npz). Everything except the full-
+// context attention kernel and the un-chunked stem variant is the streaming step's own kernels: a non-cached conformer layer is the
+// cached one with an empty cache (zeroed conv state = the causal pad of nemo-ggml.cpp:706-707).
+// ------------------------------------------------------------------------------------------
+void Engine::ensure_full_pos(int frames) {
+    if (frames <= full_pos_cap_) return;
+    const int cap = std::max(frames, 256), n_rel = 2 * cap - 1;                  // row r <-> relative position r - (cap - 1) = query - key
+    GgufFile g; g.open(gguf_path_);
+    std::vector<float> tab((size_t)n_rel * D_MODEL);
+    for (int r = 0; r < n_rel; ++r) pos_emb_row(r - (cap - 1), &tab[(size_t)r * D_MODEL]);
+    DevBuf d_tab; upload(d_tab, tab);
+    DevBuf d_a; const void* A = d_tab.p;
+    if (act_type() != OUT_F32) { d_a.alloc(tab.size() * 2, false); convert_to(d_tab.as<float>(), d_a.p, tab.size(), act_type(), st_); A = d_a.p; }
+    full_pos_.clear(); full_pos_.resize((size_t)n_layers);
+    DevBuf tmp; if (kv_dtype != 0) tmp.alloc((size_t)n_rel * D_MODEL * 4, false);
+    for (int l = 0; l < n_layers; ++l) {
+        const std::string n = "encoder.layers." + std::to_string(l) + ".self_attn.linear_pos.weight";
+        Weight wpos; load_layer_matrix(wpos, g, n, {n}, D_MODEL, D_MODEL);
+        full_pos_[l].alloc((size_t)n_rel * D_MODEL * kv_elem_size(kv_dtype), false);
+        gemm(A, D_MODEL, wpos, n_rel, nullptr, kv_dtype == 0 ? full_pos_[l].p : tmp.p, D_MODEL, EPI_NONE, 1.f, OUT_F32);
+        if (kv_dtype != 0) convert_to(tmp.as<float>(), full_pos_[l].p, (size_t)n_rel * D_MODEL, kv_dtype == 1 ? OUT_F16 : OUT_BF16, st_);
+        NSB_CUDA(cudaStreamSynchronize(st_));                                     // wpos dies at the end of the iteration
+    }
+    full_pos_cap_ = cap;
+}
+
+long long Engine::transcribe_full(const int16_t* pcm, int n_samples, int32_t* tokens, int cap, int* n_frames, float* enc_out, size_t enc_cap) {
+    if (!pcm || n_samples < 1 || (!tokens && cap > 0) || cap < 0) throw std::invalid_argument("transcribe_full: bad arguments");
+    collect_all();
+    NSB_CUDA(cudaSetDevice(device_));
+    if (n_frames) *n_frames = 0;
+    const long long avail = N_FFT / 2 + (long long)n_samples;
+    const int M = avail < N_FFT ? 0 : (int)((avail - N_FFT + HOP) / HOP);         // preprocessor.cpp:320-328
+    if (M == 0) return 0;
+    const int t1 = M / 2 + 1, t2 = t1 / 2 + 1, t3 = t2 / 2 + 1, Tq = t3;          // three 3x3 s2 convs with (2, 1) padding (nemo-ggml.cpp:828-836)
+    if (Tq > 2048) throw std::invalid_argument("transcribe_full: more than 2048 encoder frames (the reference's positional table, nemo-ggml.cpp:196)");
+    if ((size_t)Tq > (size_t)max_streams * T || (size_t)t2 * 33 * SUB_CH * 4 > dw_.bytes)
+        throw std::invalid_argument("transcribe_full: " + std::to_string(Tq) + " encoder frames do not fit this engine's workspace of max_streams x (att_right_context + 1) = " +
+                                    std::to_string((long long)max_streams * T) + " rows");
+    if (enc_out && enc_cap < (size_t)Tq * D_MODEL) return -(long long)((size_t)Tq * D_MODEL);
+    ensure_full_pos(Tq);
+    const int slot = open_stream();                                               // zeroed conv state, decoder state, prev_token = blank
+    struct Release { Engine* e; int s; ~Release() { e->hs_[s].open = false; } } release{this, slot};
+
+    // P: log-mel of the whole utterance (row = x[-1] = 0, the 256-zero left pad, the samples: preprocessor.cpp:220-221,349-356)
+    const int row = 1 + N_FFT / 2 + n_samples;
+    std::vector<int16_t> h((size_t)row, 0);
+    memcpy(&h[1 + N_FFT / 2], pcm, (size_t)n_samples * 2);
+    DevBuf d_in, d_mel; d_in.alloc(h.size() * 2, false); d_mel.alloc((size_t)M * N_MELS * 4, false);
+    h2d_sync(d_in.p, h.data(), h.size() * 2);
+    h2d_sync(d_slot_.p, &slot, 4);
+    launch_logmel(d_in.as<int16_t>(), row, 1, M, window_.as<float>(), cos_t_.as<float>(), sin_t_.as<float>(), fb_t_.as<float>(), d_mel.as<float>(),
+                  (size_t)M * N_MELS, st_);
+    count_launch();
+
+    // S: subsampling of the whole image, no carried frames, nothing dropped (build_conv_subsampling, nemo-ggml.cpp:877-952)
+    const int at = act_type(), rows = Tq;
+    const int* slot_dev = d_slot_.as<int>();
+    float* x = x_.as<float>();
+    pending_ = PartialSum{};
+    launch_stem_conv0_dw_full(d_mel.as<float>(), 1, M, c0_w_.as<float>(), c0_b_.as<float>(), c2_w_.as<float>(), c2_b_.as<float>(), dw_.as<float>(), st_);
+    count_launch();
+    const bool tc = compute != NSB_COMPUTE_F32;
+    auto f32_gemm = [&](GemmArgs& g) { if (tc) launch_gemm_tc(g, OUT_F32, st_); else launch_gemm_simt(g, st_); count_launch(); };
+    {
+        GemmArgs g; g.A = dw_.p; g.lda = SUB_CH; g.W = c3_w_.data.p; g.M = t2 * 33; g.N = SUB_CH; g.K = SUB_CH; g.bias = c3_b_.as<float>();
+        g.C = pw_.p; g.ldc = SUB_CH; g.epi = EPI_RELU; f32_gemm(g);
+    }
+    launch_dwconv_s2(pw_.as<float>(), 1, t2, 33, c5_w_.as<float>(), c5_b_.as<float>(), dw_.as<float>(), st_); count_launch();
+    {
+        GemmArgs g; g.A = dw_.p; g.lda = SUB_CH; g.W = c6_w_.data.p; g.M = t3 * SUB_W; g.N = SUB_CH; g.K = SUB_CH; g.bias = c6_b_.as<float>();
+        g.C = pw_.p; g.ldc = SUB_CH; g.epi = EPI_RELU; f32_gemm(g);
+    }
+    {
+        GemmArgs g; g.A = pw_.p; g.lda = SUB_W * SUB_CH; g.W = sub_out_w_.data.p; g.M = rows; g.N = D_MODEL; g.K = SUB_W * SUB_CH; g.bias = out_b_.as<float>();
+        g.C = x; g.ldc = D_MODEL; g.epi = EPI_NONE; f32_gemm(g);
+    }
+
+    // L: the layers of build_conformer_layer (nemo-ggml.cpp:768-818) on the cached-layer kernels
+    const long long cc_slot_stride = (long long)n_layers * (CONV_K - 1) * D_MODEL;
+    auto ln = [&](const float* g_, const float* b_) { launch_layernorm(x, rows, g_, b_, a_.p, at, pending_, st_); count_launch(); pending_ = PartialSum{}; };
+    ln(layers_[0].ln[0].as<float>(), layers_[0].ln[1].as<float>());
+    for (int l = 0; l < n_layers; ++l) {
+        LayerW& L = layers_[l];
+        gemm(a_.p, D_MODEL, L.ff1a, rows, nullptr, big_.p, D_FF, EPI_SILU, 1.f, at);
+        gemm_residual(big_.p, D_FF, L.ff1b, rows, x, 0.5f);
+        ln(L.ln[2].as<float>(), L.ln[3].as<float>());
+        gemm(a_.p, D_MODEL, L.qkv, rows, nullptr, qkv_.p, 3 * D_MODEL, EPI_NONE, 1.f, OUT_F32);
+        {
+            AttnFullArgs fa; fa.qkv = qkv_.as<float>(); fa.pos_proj = full_pos_[l].p; fa.pos_center = full_pos_cap_ - 1; fa.kv_dtype = kv_dtype;
+            fa.bias_u = L.bias_u.as<float>(); fa.bias_v = L.bias_v.as<float>(); fa.ctx = a_.p; fa.out_type = at; fa.T = rows;
+            launch_attention_full(fa, st_); count_launch();
+        }
+        gemm_residual(a_.p, D_MODEL, L.out, rows, x, 1.f);
+        ln(L.ln[4].as<float>(), L.ln[5].as<float>());
+        gemm(a_.p, D_MODEL, L.pw1, rows, nullptr, pw1_.p, 2 * D_MODEL, EPI_NONE, 1.f, OUT_F32);
+        {
+            ConvModArgs ca; ca.pw1 = pw1_.as<float>(); ca.planes = 1; ca.plane_stride = (long long)rows * 2 * D_MODEL;
+            ca.conv_cache = conv_cache_.as<float>() + (size_t)l * (CONV_K - 1) * D_MODEL; ca.slot_stride = cc_slot_stride;
+            ca.dw_w = L.dw_w.as<float>(); ca.ln_g = L.cln_g.as<float>(); ca.ln_b = L.cln_b.as<float>();
+            ca.out = a_.p; ca.out_type = at; ca.slot_of_b = slot_dev; ca.B = 1; ca.T = rows;
+            launch_conv_module(ca, st_); count_launch();
+        }
+        gemm_residual(a_.p, D_MODEL, L.pw2, rows, x, 1.f);
+        ln(L.ln[6].as<float>(), L.ln[7].as<float>());
+        gemm(a_.p, D_MODEL, L.ff2a, rows, nullptr, big_.p, D_FF, EPI_SILU, 1.f, at);
+        gemm_residual(big_.p, D_FF, L.ff2b, rows, x, 0.5f);
+        const bool last = l + 1 == n_layers;
+        launch_layernorm2(x, rows, L.ln[8].as<float>(), L.ln[9].as<float>(), last ? nullptr : layers_[l + 1].ln[0].as<float>(),
+                          last ? nullptr : layers_[l + 1].ln[1].as<float>(), last ? nullptr : a_.p, at, pending_, st_);
+        count_launch(); pending_ = PartialSum{};
+    }
+
+    // G/Y: greedy_decode (nemo-ggml.cpp:1109-1258) from a fresh decoder state over all frames
+    {
+        GemmArgs g; g.A = x; g.lda = D_MODEL; g.W = joint_enc_w_.data.p; g.M = rows; g.N = JOINT; g.K = D_MODEL; g.bias = joint_enc_b_.as<float>();
+        g.C = encp_.p; g.ldc = JOINT; g.epi = EPI_NONE; f32_gemm(g);
+    }
+    DecodeArgs d{};
+    d.w.embed = embed_.as<float>();
+    for (int l = 0; l < 2; ++l) { d.w.w_ih[l] = lstm_w_[2 * l].as<float>(); d.w.w_hh[l] = lstm_w_[2 * l + 1].as<float>();
+                                  d.w.b_ih[l] = lstm_b_[2 * l].as<float>(); d.w.b_hh[l] = lstm_b_[2 * l + 1].as<float>(); }
+    d.w.pred_w = pred_w_.as<float>(); d.w.pred_b = pred_b_.as<float>(); d.w.out_w = jout_w_.as<float>(); d.w.out_b = jout_b_.as<float>();
+    d.s.hbuf = dec_h_.as<float>(); d.s.cbuf = dec_c_.as<float>(); d.s.par = dec_par_.as<int>();
+    d.s.dec_proj = dec_proj_.as<float>(); d.s.prev_token = prev_token_.as<int>(); d.s.cand_valid = cand_valid_.as<int>();
+    d.enc_proj = encp_.as<float>(); d.slot_of_b = slot_dev; d.B = 1; d.T = rows;
+    d.out_tokens = out_tok_.as<int>(); d.out_count = out_cnt_.as<int>();
+    launch_decode(d, dec_sync_.p, st_); count_launch();
+    NSB_CUDA(cudaStreamSynchronize(st_));
+
+    int n_tok = 0;
+    NSB_CUDA(cudaMemcpy(&n_tok, out_cnt_.p, 4, cudaMemcpyDeviceToHost));
+    n_tok = std::max(0, std::min(n_tok, MAX_SYMBOLS * rows));
+    if (std::min(n_tok, cap) > 0) NSB_CUDA(cudaMemcpy(tokens, out_tok_.p, (size_t)std::min(n_tok, cap) * 4, cudaMemcpyDeviceToHost));
+    if (enc_out) NSB_CUDA(cudaMemcpy(enc_out, x, (size_t)rows * D_MODEL * 4, cudaMemcpyDeviceToHost));
+    if (n_frames) *n_frames = rows;
+    stats.chunks += 1;
+    return n_tok;
 }
 
 long long Engine::op_gemm(const std::string& name, const float* xh, int rows, float* y, size_t cap) {

@@ -96,6 +96,11 @@ public:
     long long debug_get_cache(int stream, int which, int layer, float* out, size_t cap);
     long long op_logmel(const int16_t* pcm, int n_streams, int n_samples, float* out, size_t cap);
     long long op_gemm(const std::string& name, const float* x, int rows, float* y, size_t cap);
+    // Non-streaming batch path (nemo_encode, reference src/nemo-ggml.cpp:1467-1535) for one utterance: whole-utterance log-mel ->
+    // un-chunked subsampling -> non-cached layers with full-context rel-pos attention -> greedy decode from a fresh decoder state.
+    // Borrows one free stream slot and the step workspace: the utterance must fit (frames <= max_streams * (att_right_context + 1)).
+    // Returns the number of tokens (copies min(n, cap)); *n_frames = encoder frames; enc_out (optional) [frames][1024].
+    long long transcribe_full(const int16_t* pcm, int n_samples, int32_t* tokens, int cap, int* n_frames, float* enc_out, size_t enc_cap);
 
     // facts
     int n_layers = 0, T = 1, R = 0, compute = NSB_COMPUTE_F32, kv_dtype = NSB_KV_F32, max_streams = 0;
@@ -112,6 +117,9 @@ private:
     void alloc_state();
     void zero_slot(int slot);
     void build_pos_tables(const GgufFile& g);
+    void ensure_full_pos(int frames);  // positional projections for relative positions -(cap-1) .. cap-1 of the batch path, built on first use
+    std::string gguf_path_;
+    std::vector<DevBuf> full_pos_; int full_pos_cap_ = 0;
     void gemm(const void* A, long long lda, const Weight& W, int M, const float* bias, void* C, long long ldc, int epi, float alpha,
               int out_type);
     // x += alpha * A W^T. Small batches: split-K into the workspace, reduction folded into the next LayerNorm (pending_).

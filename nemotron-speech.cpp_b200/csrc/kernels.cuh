@@ -22,6 +22,9 @@ void launch_conv0(const float* mel_hist, const float* mel_new, const int* slot_o
 // conv0 + ReLU fused into the first depthwise conv: mel chunk -> [B][t2][33][256] (the conv0 image never reaches HBM)
 void launch_stem_conv0_dw(const float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, const float* w0_t,
                           const float* b0, const float* w2_t, const float* b2, float* out, cudaStream_t st);
+// the same on a whole mel image [B][M][128] of any length M (non-streaming batch path): -> [B][t2][33][256], t2 = (M/2+1)/2+1
+void launch_stem_conv0_dw_full(const float* mel, int B, int M, const float* w0_t, const float* b0, const float* w2_t, const float* b2,
+                               float* out, cudaStream_t st);
 // history = last 9 frames of [hist || new]
 void launch_mel_hist_update(float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, cudaStream_t st);
 // optional tap: full chunk image [B][M][128]
@@ -75,6 +78,14 @@ struct AttnArgs {
     int B, T;
 };
 void launch_attention(const AttnArgs& a, cudaStream_t st);
+// Full-context rel-pos attention of the non-streaming batch path (build_rel_pos_mha, nemo-ggml.cpp:591-680): one utterance,
+// T frames, every query sees every key, no cache. qkv [T][3072] f32 (q | k | v); pos_proj rows in the K/V dtype with row
+// (rel + pos_center) <-> relative position rel = query - key in [-(T-1), T-1]; ctx [T][1024] in out_type.
+struct AttnFullArgs {
+    const float* qkv; const void* pos_proj; int pos_center; int kv_dtype;
+    const float* bias_u; const float* bias_v; void* ctx; int out_type; int T;
+};
+void launch_attention_full(const AttnFullArgs& a, cudaStream_t st);
 void launch_dequant_q8(const void* q, const void* scales, void* out_f16, int N, int K, cudaStream_t st);   // gemm_tc.cu
 bool pair_gemm_enabled();         // gemm_tc.cu: CTA-pair tiles on (default) / off (NSB_PAIR_GEMM=0)
 

@@ -120,6 +120,9 @@ void launch_conv0(const float* mel_hist, const float* mel_new, const int* slot_o
 // 64-stream step) never goes to HBM. One CTA = one output row (b, oh2); thread = channel; the 7 mel rows the row depends
 // on sit in shared memory (broadcast reads); a 3x3 register window of conv0 values slides along the frequency axis, so
 // every conv0 value is computed once per output row. Same accumulation order as the two stand-alone kernels (bit-identical).
+// FULL = the non-streaming batch path (nemo_encode, nemo-ggml.cpp:961-1003): `hist` is a flat mel image [B][M][128] and `T` carries
+// M itself (any length; the chunk variant derives M = 9 + 8T and reads [9 history frames | 8T new frames]).
+template <bool FULL>
 __global__ void __launch_bounds__(SUB_CH) stem_conv0_dw_kernel(const float* __restrict__ hist, const float* __restrict__ mel_new,
                                                                const int* __restrict__ slot_of_b, int T, const float* __restrict__ w0_t,
                                                                const float* __restrict__ b0, const float* __restrict__ w2_t,
@@ -130,12 +133,14 @@ __global__ void __launch_bounds__(SUB_CH) stem_conv0_dw_kernel(const float* __re
     __shared__ __align__(16) float mel[7][MS];
     NSB_KERNEL_PROLOGUE(TR_STEM)
     const int oh2 = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
-    const int M = PRE_CACHE + 8 * T, t1 = M / 2 + 1, t2 = gridDim.x;
+    const int M = FULL ? T : PRE_CACHE + 8 * T, t1 = M / 2 + 1, t2 = gridDim.x;
     constexpr int W1 = N_MELS / 2 + 1, W2 = W1 / 2 + 1;                         // 65, 33
-    const int slot = slot_of_b[b];
+    const int slot = FULL ? 0 : slot_of_b[b];
     for (int e = c; e < 7 * MS; e += SUB_CH) {
         const int r = e / MS, m = e % MS - 4, f = 4 * oh2 - 6 + r;              // mel rows 4 oh2 - 6 .. 4 oh2, columns -4 .. 131 (zero outside the image)
-        mel[r][m + 4] = (f >= 0 && f < M && m >= 0 && m < N_MELS) ? chunk_mel(hist, mel_new, slot, b, T, f, m) : 0.0f;
+        float v = 0.0f;
+        if (f >= 0 && f < M && m >= 0 && m < N_MELS) v = FULL ? hist[((size_t)b * M + f) * N_MELS + m] : chunk_mel(hist, mel_new, slot, b, T, f, m);
+        mel[r][m + 4] = v;
     }
     float w0[9], w2[9];
 #pragma unroll
@@ -184,7 +189,12 @@ __global__ void __launch_bounds__(SUB_CH) stem_conv0_dw_kernel(const float* __re
 void launch_stem_conv0_dw(const float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, const float* w0_t,
                           const float* b0, const float* w2_t, const float* b2, float* out, cudaStream_t st) {
     const int M = PRE_CACHE + 8 * T, t1 = M / 2 + 1, t2 = t1 / 2 + 1;
-    launch_k(stem_conv0_dw_kernel, dim3(t2, B), dim3(SUB_CH), 0, st, mel_hist, mel_new, slot_of_b, T, w0_t, b0, w2_t, b2, out);
+    launch_k(stem_conv0_dw_kernel<false>, dim3(t2, B), dim3(SUB_CH), 0, st, mel_hist, mel_new, slot_of_b, T, w0_t, b0, w2_t, b2, out);
+}
+void launch_stem_conv0_dw_full(const float* mel, int B, int M, const float* w0_t, const float* b0, const float* w2_t, const float* b2,
+                               float* out, cudaStream_t st) {
+    const int t1 = M / 2 + 1, t2 = t1 / 2 + 1;
+    launch_k(stem_conv0_dw_kernel<true>, dim3(t2, B), dim3(SUB_CH), 0, st, mel, (const float*)nullptr, (const int*)nullptr, M, w0_t, b0, w2_t, b2, out);
 }
 
 __global__ void __launch_bounds__(N_MELS) mel_hist_update_kernel(float* __restrict__ hist, const float* __restrict__ mel_new,

@@ -970,4 +970,66 @@ void launch_advance_streams(const int* slot_of_b, int B, int T, int* ring_pos, i
     if (B > 0) launch_k(advance_streams_kernel, dim3((B + 127) / 128), dim3(128), 0, st, slot_of_b, B, T, ring_pos, valid_len);
 }
 
+// ------------------------------------------------------------------------------------------
+// Full-context rel-pos attention of the non-streaming batch path (build_rel_pos_mha + build_rel_shift, nemo-ggml.cpp:548-680).
+// EXPERIMENTAL: written after this round's GPU budget was spent, not yet validated on hardware; correctness-
+// first SIMT. One warp = one (head, query row i), lane l owns head dims 4l .. 4l+3.
+//   pass 1: S[j] = ((q_i + u).k_j + (q_i + v).P[i - j]) / sqrt(128) for all T keys into shared memory -- the pad / reshape / drop
+//           rel-shift is index arithmetic: BD[i, j] = BD_raw[i, j + T - 1 - i] <-> relative position i - j;
+//   pass 2: softmax over the row (max-subtract, expf, sum), as ggml_soft_max;
+//   pass 3: ctx_i = sum_j p_j v_j in key order.
+// K, V and P are read at the K/V dtype's precision, as the streaming ring stores them.
+// ------------------------------------------------------------------------------------------
+constexpr int ATTF_WARPS = 4;
+__global__ void __launch_bounds__(32 * ATTF_WARPS) attention_full_kernel(const AttnFullArgs a) {
+    extern __shared__ float attf_sc[];                                           // [ATTF_WARPS][T]
+    NSB_KERNEL_PROLOGUE(TR_ATTN)
+    const int h = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, T = a.T, kv = a.kv_dtype;
+    const int i = blockIdx.y * ATTF_WARPS + warp;
+    if (i < T) {                                                                 // warp-uniform; no block-wide barrier below
+        float* sc = attf_sc + (size_t)warp * T;
+        const int c = h * D_HEAD + lane * 4;
+        const float4 q4 = *(const float4*)(a.qkv + (size_t)i * 3 * D_MODEL + c);
+        const float4 u4 = *(const float4*)(a.bias_u + c), w4 = *(const float4*)(a.bias_v + c);
+        const float qu[4] = {q4.x + u4.x, q4.y + u4.y, q4.z + u4.z, q4.w + u4.w};
+        const float qv[4] = {q4.x + w4.x, q4.y + w4.y, q4.z + w4.z, q4.w + w4.w};
+        const float scale = 1.0f / sqrtf((float)D_HEAD);
+        for (int j = 0; j < T; ++j) {
+            const float4 k4 = *(const float4*)(a.qkv + (size_t)j * 3 * D_MODEL + D_MODEL + c);
+            const size_t pr = (size_t)(i - j + a.pos_center) * D_MODEL + c;
+            float ac = round_kv(k4.x, kv) * qu[0];
+            ac = fmaf(round_kv(k4.y, kv), qu[1], ac); ac = fmaf(round_kv(k4.z, kv), qu[2], ac); ac = fmaf(round_kv(k4.w, kv), qu[3], ac);
+            float bd = load_kv(a.pos_proj, pr, kv) * qv[0];
+            bd = fmaf(load_kv(a.pos_proj, pr + 1, kv), qv[1], bd); bd = fmaf(load_kv(a.pos_proj, pr + 2, kv), qv[2], bd);
+            bd = fmaf(load_kv(a.pos_proj, pr + 3, kv), qv[3], bd);
+            ac = warp_sum(ac); bd = warp_sum(bd);
+            if (lane == 0) sc[j] = (ac + bd) * scale;
+        }
+        __syncwarp();
+        float mx = -INFINITY;
+        for (int j = lane; j < T; j += 32) mx = fmaxf(mx, sc[j]);
+        mx = warp_max(mx);
+        float sum = 0.0f;
+        for (int j = lane; j < T; j += 32) { const float e = expf(sc[j] - mx); sc[j] = e; sum += e; }
+        sum = warp_sum(sum);
+        __syncwarp();
+        const float inv = 1.0f / sum;
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (int j = 0; j < T; ++j) {
+            const float p = sc[j] * inv;
+            const float4 v4 = *(const float4*)(a.qkv + (size_t)j * 3 * D_MODEL + 2 * D_MODEL + c);
+            acc[0] = fmaf(round_kv(v4.x, kv), p, acc[0]); acc[1] = fmaf(round_kv(v4.y, kv), p, acc[1]);
+            acc[2] = fmaf(round_kv(v4.z, kv), p, acc[2]); acc[3] = fmaf(round_kv(v4.w, kv), p, acc[3]);
+        }
+        const size_t o = (size_t)i * D_MODEL + c;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) store_out(a.ctx, o + u, acc[u], a.out_type);
+    }
+    NSB_KERNEL_EPILOGUE();
+}
+void launch_attention_full(const AttnFullArgs& a, cudaStream_t st) {
+    if (a.T < 1 || a.T > 2048) throw CudaError("attention_full: 1 <= frames <= 2048 (the reference's positional table, nemo-ggml.cpp:196)");
+    launch_k(attention_full_kernel, dim3(N_HEADS, (a.T + ATTF_WARPS - 1) / ATTF_WARPS), dim3(32 * ATTF_WARPS), (size_t)ATTF_WARPS * a.T * sizeof(float), st, a);
+}
+
 }  // namespace nsb
