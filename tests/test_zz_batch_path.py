@@ -53,6 +53,16 @@ rel16 = float(np.abs(enc16 - enc_o).max() / np.abs(enc_o).max())
 print("fp16: encoder rel err vs the f32 oracle", rel16)
 assert rel16 < 1e-2, rel16
 e16.close()
+# the reference's own src/transcribe.cpp (byte-identical, oracle/Makefile) on the drop-in library: stdout carries the transcript
+cli = os.path.join(ROOT, "oracle", "_ref", "nemotron-asr-batch-dropin")
+if os.path.exists(cli):
+    import subprocess, tempfile
+    with tempfile.TemporaryDirectory() as d:
+        f = os.path.join(d, "a.pcm"); pcm.tofile(f)
+        r = subprocess.run([cli, path, f], capture_output=True, text=True, timeout=120, env=dict(os.environ, NSB_COMPUTE="1"))
+    assert r.returncode == 0, r.stderr
+    assert "=== Transcription ===\n" + om.detok(toks_o) + "\n" in r.stdout, r.stdout
+    print("batch CLI drop-in ok")
 print("BATCH PATH OK")
 """
 
