@@ -114,3 +114,64 @@ def test_reference_batch_cli_compiles_unmodified_against_dropin_headers(built, t
     assert r.returncode == 1
     r = subprocess.run([str(exe), str(tmp_path / "none.gguf"), str(tmp_path / "a.pcm")], capture_output=True, text=True)
     assert r.returncode == 1 and "Failed to load model" in r.stderr
+
+
+HEADER_PROBE = r"""
+#include "nemo-stream.h"
+#include <cstdio>
+int main() {
+    const nemo_cache_config modes[] = {nemo_cache_config::default_config(), nemo_cache_config::pure_causal(), nemo_cache_config::ultra_low_latency(),
+                                       nemo_cache_config::low_latency(), nemo_cache_config::balanced(),
+                                       nemo_cache_config::with_latency(nemo_latency_mode::LOW)};
+    for (const nemo_cache_config& c : modes)
+        printf("cfg R=%d L=%d chunk_mel=%zu shift_mel=%zu samples=%d latency_ms=%d valid_out=%d k=%d cc=%d drop=%d pre=%d blank=%d vocab=%d hop=%d sr=%d\n",
+               (int)c.att_right_context, (int)c.att_left_context, (size_t)c.get_chunk_mel_frames(), (size_t)c.get_shift_mel_frames(),
+               (int)c.get_chunk_samples(), (int)c.get_latency_ms(), (int)c.get_valid_out_len(), (int)c.conv_kernel_size, (int)c.conv_cache_size,
+               (int)c.drop_extra_pre_encoded, (int)c.pre_encode_cache_size, (int)c.blank_token, (int)c.vocab_size, (int)c.hop_length, (int)c.sample_rate);
+    printf("modes %d %d %d %d\n", (int)nemo_latency_mode::PURE_CAUSAL, (int)nemo_latency_mode::ULTRA_LOW, (int)nemo_latency_mode::LOW, (int)nemo_latency_mode::DEFAULT);
+    nemo_decoder_state d;
+    printf("dec fresh init=%d prev=%d\n", (int)d.is_initialized(), d.prev_token);
+    d.init(2, 640); d.prev_token = 7; d.h[5] = 1.5f; d.c[700] = -2.f; d.frame_offset = 9;
+    printf("dec set init=%d h=%zu c=%zu hl1=%ld\n", (int)d.is_initialized(), d.h.size(), d.c.size(), (long)(d.h_layer(1) - d.h.data()));
+    d.reset(1024);
+    printf("dec reset prev=%d h5=%g c700=%g off=%ld init=%d\n", d.prev_token, d.h[5], d.c[700], (long)d.frame_offset, (int)d.is_initialized());
+    d.reset();
+    printf("dec reset0 prev=%d init=%d\n", d.prev_token, (int)d.is_initialized());
+    timed_token t(42, 25);
+    printf("tok %d %ld %.4f %.4f\n", t.token_id, (long)t.frame_idx, t.to_seconds(), t.to_seconds(640, 8000));
+    nemo_hparams hp;
+    printf("hp %d %d %d %d %d %d %d %d\n", hp.n_mels, hp.d_model, hp.n_heads, hp.d_head, hp.d_ff, hp.n_layers, hp.vocab_size, hp.joint_dim);
+    printf("backend %d %d %d %d\n", (int)NEMO_BACKEND_CPU, (int)NEMO_BACKEND_CUDA, (int)NEMO_BACKEND_METAL, (int)NEMO_BACKEND_AUTO);
+    return 0;
+}
+"""
+
+GGML_STUB = """#pragma once
+#include <cstddef>
+#include <cstdint>
+struct ggml_tensor; struct ggml_context; struct ggml_cgraph; struct gguf_context;
+typedef struct ggml_backend* ggml_backend_t; typedef struct ggml_backend_buffer* ggml_backend_buffer_t; typedef struct ggml_gallocr* ggml_gallocr_t;
+"""
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/nemo-stream.h"), reason="reference sources not present")
+def test_dropin_headers_agree_with_the_reference_headers(tmp_path):
+    """Differential test of the host-side logic that lives in the headers (what the reference's tests/test_streaming.cpp unit
+    tests poke: chunk / shift / latency arithmetic of every latency mode and factory, nemo_decoder_state init / reset,
+    timed_token::to_seconds, hparams defaults, enum values): the same probe is compiled once against the REFERENCE's own
+    src/nemo-stream.h + src/nemo-ggml.h (ggml's headers replaced by empty forward-declaration stubs; header-only, nothing of the
+    reference is linked) and once against include/, and must print the same."""
+    stub = tmp_path / "stub"; stub.mkdir()
+    (stub / "ggml.h").write_text(GGML_STUB)
+    for h in ("ggml-cpu.h", "ggml-alloc.h", "ggml-backend.h", "gguf.h"):
+        (stub / h).write_text("#pragma once\n")
+    src = tmp_path / "probe.cpp"
+    src.write_text(HEADER_PROBE)
+    outs = []
+    for name, incs in (("ref", [str(stub), "/root/reference/src"]), ("ours", [os.path.join(ROOT, "include")])):
+        exe = tmp_path / f"probe_{name}"
+        cmd = ["/usr/bin/g++", "-std=c++17", "-O1"] + [f"-I{i}" for i in incs] + [str(src), "-o", str(exe)]
+        subprocess.check_call(cmd)
+        outs.append(subprocess.check_output([str(exe)], text=True))
+    assert outs[0] == outs[1], "\n--- reference headers\n" + outs[0] + "--- drop-in headers\n" + outs[1]
+    assert "chunk_mel=121" in outs[1] and "samples=19360" in outs[1] and "latency_ms=1210" in outs[1]      # R = 13 (SURVEY appendix B)
