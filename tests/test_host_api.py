@@ -175,3 +175,32 @@ def test_dropin_headers_agree_with_the_reference_headers(tmp_path):
         outs.append(subprocess.check_output([str(exe)], text=True))
     assert outs[0] == outs[1], "\n--- reference headers\n" + outs[0] + "--- drop-in headers\n" + outs[1]
     assert "chunk_mel=121" in outs[1] and "samples=19360" in outs[1] and "latency_ms=1210" in outs[1]      # R = 13
+
+
+DETOK_PROBE = r"""
+#include "nemo-ggml.h"
+#include <cstdio>
+#include <cstring>
+int main() {
+    const char* pieces[] = {"\xe2\x96\x81he", "llo", "\xe2\x96\x81wor", "ld", "abcdefgh", "\xe2\x96\x81", ""};
+    std::vector<char8> vocab(7);
+    for (int i = 0; i < 7; ++i) { memset(vocab[i].data, 0, 8); memcpy(vocab[i].data, pieces[i], strlen(pieces[i]) > 8 ? 8 : strlen(pieces[i])); }
+    std::vector<timed_token> t = {{0, 0}, {1, 1}, {2, 12}, {3, 13}, {-1, 14}, {99, 15}, {4, 16}, {5, 20}, {6, 21}};
+    printf("[%s]\n[%s]\n", tokens_to_text(t, vocab, false).c_str(), tokens_to_text(t, vocab, true).c_str());
+    return 0;
+}
+"""
+
+
+def test_tokens_to_text_of_the_shim(built, tmp_path):
+    """tokens_to_text (src/nemo-ggml.cpp:1432-1458) as exported by the drop-in library: U+2581 -> space, out-of-range ids skipped,
+    "{seconds}" after the space in timestamp mode (frame * 1280 / 16000), and an 8-byte piece without a NUL does not run on into
+    its neighbour (the reference reads it as a C string)."""
+    pkg = os.path.join(ROOT, "nemotron-speech.cpp_b200")
+    src = tmp_path / "detok.cpp"; src.write_text(DETOK_PROBE)
+    exe = tmp_path / "detok"
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), str(src), "-L", pkg, "-lnsb200",
+                           f"-Wl,-rpath,{pkg}", "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).splitlines()
+    assert out[0] == "[ hello worldabcdefgh ]"
+    assert out[1] == "[ {0.00}hello {0.96}worldabcdefgh {1.60}]"
