@@ -296,7 +296,7 @@ void Engine::alloc_state() {
     hs_.assign(S, HostStream());
     for (int s = 0; s < S; ++s) zero_slot(s);
 
-    rl_ = 8 * T * HOP + (N_FFT - HOP) + 1;                                                // 1280 T + 353 samples per stream-step
+    rl_ = hs_row_len(T);                                                                  // 1280 T + 353 samples per stream-step
     const size_t Mrows = (size_t)S * T;
     d_pcm_.alloc((size_t)S * rl_ * 2); d_slot_.alloc((size_t)S * 4);
     mel_new_.alloc((size_t)S * 8 * T * N_MELS * 4);
@@ -337,7 +337,7 @@ void Engine::zero_slot(int s) {
     NSB_CUDA(cudaMemcpyAsync((char*)cand_valid_.p + (size_t)s * 4, &zero, 4, cudaMemcpyHostToDevice, st_));
     NSB_CUDA(cudaMemcpyAsync((char*)prev_token_.p + (size_t)s * 4, &blank, 4, cudaMemcpyHostToDevice, st_));   // prev_token = blank (:41-42)
     NSB_CUDA(cudaStreamSynchronize(st_));
-    hs_[s].buf.clear(); hs_[s].base = 0; hs_[s].n_pushed = 0; hs_[s].chunk_idx = 0; hs_[s].chunks_done = 0; hs_[s].tokens.clear();
+    hs_clear(hs_[s]);
 }
 
 // P_l = linear_pos(pos_emb rows) for the L+2T-1 relative positions a chunk can touch, once, at load.
@@ -439,25 +439,11 @@ void Engine::reset_stream(int s) { collect_all(); if (s < 0 || s >= max_streams 
 void Engine::push_pcm(int s, const int16_t* pcm, int n) {
     if (s < 0 || s >= max_streams || !hs_[s].open) throw std::invalid_argument("bad stream id");
     if (!pcm || n <= 0) return;                                        // reference returns "" on null/<=0 (nemo-stream.cpp:1079)
-    HostStream& h = hs_[s];
-    h.buf.insert(h.buf.end(), pcm, pcm + n);
-    h.n_pushed += n;
+    hs_push(hs_[s], pcm, n);
 }
 
-// Chunk c needs mel frames up to 8T(c+1)-1, i.e. padded samples up to 160*(8T(c+1)-1)+512, i.e. raw samples
-// n >= 160*(8T(c+1)-1) + 256  (preprocessor.cpp:320-328 frame count + nemo-stream.cpp:1094-1102 chunk gate)
-bool Engine::ready(int s) const {
-    const HostStream& h = hs_[s];
-    return h.open && h.n_pushed >= (long long)HOP * (8LL * T * (h.chunk_idx + 1) - 1) + N_FFT / 2;
-}
-
-static void stage_row(const HostStream& h, int T, int rl, int16_t* dst) {
-    // row = raw[start-1 .. start + 1280T + 352), start = 1280 T c - 256; negative indices are the 256-zero left pad / x[-1] = 0
-    const long long start = 8LL * T * HOP * h.chunk_idx - N_FFT / 2 - 1;
-    const int zeros = start < 0 ? (int)std::min<long long>(-start, rl) : 0;
-    if (zeros) memset(dst, 0, (size_t)zeros * sizeof(int16_t));
-    if (zeros < rl) memcpy(dst + zeros, h.buf.data() + (size_t)(start + zeros - h.base), (size_t)(rl - zeros) * sizeof(int16_t));
-}
+// chunk gate and PCM row of a stream: host_stream.h (pure host code, driven on CPU by tests/test_host_api.py)
+bool Engine::ready(int s) const { return hs_ready(hs_[s], T); }
 
 // Up to two steps in flight: step i+1 is staged and enqueued while step i runs, so the device never waits for the host between
 // steps. Host buffers (pinned PCM rows, slots, token ids) are double-buffered; the device-side step workspace is shared --
@@ -473,11 +459,8 @@ int Engine::step_begin() {
     int16_t* hp = io.h_pcm.as<int16_t>(); int* hsl = io.h_slot.as<int>();
     for (int b = 0; b < B; ++b) {
         HostStream& h = hs_[batch[b]];
-        stage_row(h, T, rl_, hp + (size_t)b * rl_); hsl[b] = batch[b];
-        h.chunk_idx += 1;                                                 // launched: ready() now asks for the NEXT chunk
-        // drop samples no later chunk needs: next row starts at 1280 T c' - 257
-        const long long keep_from = std::max(0LL, 8LL * T * HOP * h.chunk_idx - N_FFT / 2 - 1);
-        if (keep_from > h.base) { h.buf.erase(h.buf.begin(), h.buf.begin() + (size_t)(keep_from - h.base)); h.base = keep_from; }
+        hs_stage_row(h, T, rl_, hp + (size_t)b * rl_); hsl[b] = batch[b];
+        hs_launched(h, T);                                                // ready() now asks for the NEXT chunk; samples no later chunk needs are dropped
     }
     NSB_CUDA(cudaMemcpyAsync(d_pcm_.p, hp, (size_t)B * rl_ * 2, cudaMemcpyHostToDevice, st_));
     NSB_CUDA(cudaMemcpyAsync(d_slot_.p, hsl, (size_t)B * 4, cudaMemcpyHostToDevice, st_));
@@ -747,7 +730,7 @@ void Engine::bench_prepare(int n_streams, const int16_t* pcm, int samples_per_st
             HostStream& h = hs_[ids[b]];
             if (k == 0 && !ready(ids[b])) throw std::runtime_error("bench: stream not ready after staging");
             h.chunk_idx += k;                                                     // row of chunk (current + k); host state is restored right away
-            stage_row(h, T, rl_, hp + (size_t)b * rl_);
+            hs_stage_row(h, T, rl_, hp + (size_t)b * rl_);
             h.chunk_idx -= k;
             hsl[b] = ids[b];
         }

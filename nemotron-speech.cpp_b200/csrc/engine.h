@@ -8,6 +8,7 @@
 
 #include "../../include/nsb200.h"
 #include "gguf_loader.h"
+#include "host_stream.h"
 #include "kernels.cuh"
 
 namespace nsb {
@@ -47,13 +48,6 @@ struct LayerW {
     Weight ff1a, ff1b, qkv, out, pw1, pw2, ff2a, ff2b;
     DevBuf bias_u, bias_v, dw_w, cln_g, cln_b;
     DevBuf pos_proj;        // [L+2T-1][1024] in the K/V ring dtype
-};
-
-struct HostStream {
-    bool open = false;
-    std::vector<int16_t> buf;      // raw samples from absolute index `base`
-    long long base = 0, n_pushed = 0, chunk_idx = 0, chunks_done = 0;   // chunk_idx: next chunk to LAUNCH; chunks_done: chunks whose tokens were collected
-    std::deque<int32_t> tokens;
 };
 
 class Engine {

@@ -204,3 +204,67 @@ def test_tokens_to_text_of_the_shim(built, tmp_path):
     out = subprocess.check_output([str(exe)], text=True).splitlines()
     assert out[0] == "[ hello worldabcdefgh ]"
     assert out[1] == "[ {0.00}hello {0.96}worldabcdefgh {1.60}]"
+
+
+HOST_STREAM_PROBE = r"""
+#include "host_stream.h"
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+using namespace nsb;
+// usage: probe T n_samples seed  -> pushes a seeded PCM stream in ragged pieces, stages every due chunk's row, checks it against
+// the definition (raw[1280 T c - 257 + k], zeros before the stream start) and prints the number of chunks
+int main(int argc, char** argv) {
+    const int T = atoi(argv[1]); const long long n = atoll(argv[2]); std::mt19937 rng(atoi(argv[3]));
+    std::vector<int16_t> pcm((size_t)n);
+    for (auto& v : pcm) v = (int16_t)(rng() % 65536 - 32768);
+    HostStream h; h.open = true;
+    const int rl = hs_row_len(T);
+    if (rl != 1280 * T + 353) { printf("FAIL row_len\n"); return 1; }
+    std::vector<int16_t> row((size_t)rl);
+    long long pos = 0; int chunks = 0; size_t max_buf = 0;
+    while (pos < n) {
+        const long long k = std::min<long long>(n - pos, 1 + rng() % 5000);
+        hs_push(h, pcm.data() + pos, (int)k); pos += k;
+        while (hs_ready(h, T)) {
+            hs_stage_row(h, T, rl, row.data());
+            const long long start = 1280LL * T * chunks - 257;
+            for (int i = 0; i < rl; ++i) {
+                const long long idx = start + i;
+                const int16_t want = idx < 0 ? 0 : pcm[(size_t)idx];
+                if (idx >= pos) { printf("FAIL chunk %d reads sample %lld beyond the %lld pushed\n", chunks, idx, pos); return 1; }
+                if (row[i] != want) { printf("FAIL chunk %d sample %d\n", chunks, i); return 1; }
+            }
+            hs_launched(h, T); ++chunks;
+            max_buf = std::max(max_buf, h.buf.size());
+        }
+    }
+    // the gate is tight: one more chunk needs exactly 160 (8T (c+1) - 1) + 256 samples
+    if (n >= 160LL * (8LL * T * (chunks + 1) - 1) + 256) { printf("FAIL gate\n"); return 1; }
+    printf("%d %zu\n", chunks, max_buf);
+    return 0;
+}
+"""
+
+
+def test_host_stream_bookkeeping_against_the_oracle(built, tmp_path):
+    """csrc/host_stream.h is the engine's host-side chunk gate + PCM staging (pure C++): ragged pushes, every staged row checked
+    against its definition, chunk counts == the oracle's streaming driver (nemo-stream.cpp:1094-1127) for the same lengths, and the
+    retained buffer stays bounded (one row + one push)."""
+    import oracle as O
+    src = tmp_path / "hs.cpp"; src.write_text(HOST_STREAM_PROBE)
+    exe = tmp_path / "hs"
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "nemotron-speech.cpp_b200", "csrc"), str(src), "-o", str(exe)])
+    om = O.Model(synth.cached_model("f32", 2, R=0))
+    rng = np.random.default_rng(5)
+    for R in (0, 1, 6, 13):
+        T = R + 1
+        for n in [95, 1280 * T + 95, 1280 * T + 96, 1280 * T + 97, int(rng.integers(20000, 60000)), 160 * (8 * T * 3 - 1) + 256]:
+            out = subprocess.check_output([str(exe), str(T), str(n), str(R * 7 + 1)], text=True).split()
+            assert out[0] != "FAIL", (R, n, out)
+            chunks, max_buf = int(out[0]), int(out[1])
+            assert max_buf <= (1280 * T + 353) + 5000 + 1280 * T
+            if n <= 30000:                                               # the oracle runs the model: keep its share small
+                st = O.Stream(om, R); st.push(np.zeros(n, np.int16))
+                assert st.chunks == chunks, (R, n, st.chunks, chunks)
+            assert chunks == max(0, (n - 96) // (1280 * T))
