@@ -69,6 +69,10 @@ typedef struct nsb_model_info {
     char vocab[1025 * 8];     /* char8 pieces, NUL padded (bounded copy + zero fill)        */
 } nsb_model_info;
 int nsb_gguf_probe(const char* gguf_path, nsb_model_info* info);
+/* One tensor of the file as floats, as the engine's loader sees it (F32 / F16 as stored, Q8_0 / Q4_0 dequantised like ggml's
+ * dequantize_row_*; scripts/convert_to_gguf.py:93-179), also without a GPU. Returns the element count (out == NULL: query only), or
+ * <0 with nsb_last_error() (missing tensor, unsupported type, buffer too small); *ggml_type (optional) = the stored type. */
+long long nsb_gguf_read_tensor(const char* gguf_path, const char* tensor_name, float* out, size_t cap_floats, int* ggml_type);
 
 /* ---- engine lifetime: replaces nemo_init_with_backend / nemo_model_load / nemo_free
  *      (src/nemo-ggml.h:231-242, src/nemo-ggml.cpp:83-463) --------------------------------- */

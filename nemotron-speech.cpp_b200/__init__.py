@@ -46,7 +46,7 @@ class ModelInfo(C.Structure):
                                          "decoder_dim", "joint_dim", "n_tensors", "weight_type")] + [("vocab", C.c_char * (1025 * 8))]
 
 
-EXPORTS = ["nsb_gguf_probe", "nsb_default_config", "nsb_engine_create", "nsb_engine_destroy", "nsb_last_error", "nsb_engine_n_layers",
+EXPORTS = ["nsb_gguf_probe", "nsb_gguf_read_tensor", "nsb_default_config", "nsb_engine_create", "nsb_engine_destroy", "nsb_last_error", "nsb_engine_n_layers",
            "nsb_engine_vocab_size", "nsb_engine_vocab", "nsb_engine_chunk_samples", "nsb_engine_shift_samples", "nsb_engine_compute",
            "nsb_stream_open", "nsb_stream_close", "nsb_stream_reset", "nsb_stream_push_pcm", "nsb_push_pcm_batch", "nsb_pop_tokens_batch", "nsb_stream_ready", "nsb_engine_step", "nsb_engine_step_begin", "nsb_engine_step_end",
            "nsb_engine_drain", "nsb_stream_pop_tokens", "nsb_stream_chunks", "nsb_detokenize", "nsb_engine_get_stats",
@@ -76,6 +76,8 @@ def lib():
         vp, ci = C.c_void_p, C.c_int
         L.nsb_last_error.restype = C.c_char_p
         L.nsb_gguf_probe.argtypes = [C.c_char_p, C.POINTER(ModelInfo)]
+        L.nsb_gguf_read_tensor.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]
+        L.nsb_gguf_read_tensor.restype = C.c_longlong
         L.nsb_default_config.argtypes = [C.POINTER(EngineConfig)]
         L.nsb_engine_create.argtypes = [C.c_char_p, C.POINTER(EngineConfig), C.POINTER(vp)]
         L.nsb_engine_destroy.argtypes = [vp]
@@ -120,6 +122,15 @@ def probe(path: str) -> ModelInfo:
     info = ModelInfo()
     _check(lib().nsb_gguf_probe(path.encode(), C.byref(info)))
     return info
+
+
+def read_tensor(path: str, name: str):
+    """(floats, ggml type) of one tensor as the engine's loader sees it (no GPU needed)."""
+    t = C.c_int(0)
+    n = _check(int(lib().nsb_gguf_read_tensor(path.encode(), name.encode(), None, 0, C.byref(t))))
+    out = np.empty(n, dtype=np.float32)
+    _check(int(lib().nsb_gguf_read_tensor(path.encode(), name.encode(), out.ctypes.data_as(C.c_void_p), out.size, C.byref(t))))
+    return out, t.value
 
 
 class Engine:

@@ -49,6 +49,24 @@ int nsb_gguf_probe(const char* path, nsb_model_info* info) {
     }
 }
 
+long long nsb_gguf_read_tensor(const char* path, const char* name, float* out, size_t cap, int* type) {
+    if (!path || !name) return fail(NSB_ERR_ARG, "null argument");
+    try {
+        nsb::GgufFile g; g.open(path);
+        const nsb::GgufTensor& t = g.require(name);
+        if (type) *type = t.type;
+        const long long n = (long long)t.n_elements();
+        if (!out) return n;                                   // query: element count only
+        if ((size_t)n > cap) return fail(NSB_ERR_ARG, "nsb_gguf_read_tensor: buffer too small for " + std::to_string(n) + " elements");
+        const std::vector<float> v = g.read_dequant(name);
+        memcpy(out, v.data(), v.size() * sizeof(float));
+        return n;
+    } catch (const std::exception& e) {
+        const std::string m = e.what();
+        return fail(m.find("cannot open") != std::string::npos ? NSB_ERR_IO : NSB_ERR_FORMAT, m);
+    }
+}
+
 void nsb_default_config(nsb_engine_config* c) {
     if (!c) return;
     memset(c, 0, sizeof(*c));

@@ -40,29 +40,8 @@ void convert_to(const float* d_in, void* d_out, size_t n, int out_type, cudaStre
     convert_kernel<<<blocks, 256, 0, st>>>(d_in, d_out, n, out_type);
 }
 
-std::vector<float> read_matrix_f32(const GgufFile& g, const std::string& name) {
-    const GgufTensor& t = g.require(name);
-    std::vector<uint8_t> raw = g.read(t);
-    std::vector<float> out((size_t)t.n_elements());
-    if (t.type == GGML_F32) memcpy(out.data(), raw.data(), raw.size());
-    else if (t.type == GGML_F16) { for (size_t i = 0; i < out.size(); ++i) { uint16_t h; memcpy(&h, &raw[2 * i], 2); out[i] = half_bits_to_float(h); } }
-    else if (t.type == GGML_Q8_0) {                       // block = fp16 d + 32 x int8 along ne0 (convert_to_gguf.py:93-129)
-        const size_t nb = out.size() / 32;
-        for (size_t b = 0; b < nb; ++b) {
-            uint16_t h; memcpy(&h, &raw[b * 34], 2); const float d = half_bits_to_float(h);
-            const int8_t* q = (const int8_t*)&raw[b * 34 + 2];
-            for (int i = 0; i < 32; ++i) out[b * 32 + i] = d * (float)q[i];
-        }
-    } else if (t.type == GGML_Q4_0) {                     // block = fp16 d + 16 nibble bytes: element i = low nibble of byte i, i + 16 = high nibble;
-        const size_t nb = out.size() / 32;                // value = d * (q - 8) (convert_to_gguf.py:132-179)
-        for (size_t b = 0; b < nb; ++b) {
-            uint16_t h; memcpy(&h, &raw[b * 18], 2); const float d = half_bits_to_float(h);
-            const uint8_t* q = &raw[b * 18 + 2];
-            for (int i = 0; i < 16; ++i) { out[b * 32 + i] = d * (float)((int)(q[i] & 0x0F) - 8); out[b * 32 + 16 + i] = d * (float)((int)(q[i] >> 4) - 8); }
-        }
-    } else throw std::runtime_error("unsupported tensor type for " + name);
-    return out;
-}
+// any per-layer matrix as floats (F32 / F16 as stored, Q8_0 / Q4_0 dequantised): gguf_loader.cpp, pure host code tested on CPU
+std::vector<float> read_matrix_f32(const GgufFile& g, const std::string& name) { return g.read_dequant(name); }
 
 // Host -> device copy that is COMPLETE on return. cudaMemcpy from pageable memory may return while the DMA from the
 // staging buffer is still in flight, and the engine's kernels run on a non-blocking stream that is not ordered after

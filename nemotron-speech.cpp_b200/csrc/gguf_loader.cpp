@@ -133,4 +133,28 @@ std::vector<float> GgufFile::read_f32(const std::string& name) const {
     return out;
 }
 
+std::vector<float> GgufFile::read_dequant(const std::string& name) const {
+    const GgufTensor& t = require(name);
+    std::vector<uint8_t> raw = read(t);
+    std::vector<float> out((size_t)t.n_elements());
+    if (t.type == GGML_F32) memcpy(out.data(), raw.data(), raw.size());
+    else if (t.type == GGML_F16) { for (size_t i = 0; i < out.size(); ++i) { uint16_t h; memcpy(&h, &raw[2 * i], 2); out[i] = half_bits_to_float(h); } }
+    else if (t.type == GGML_Q8_0) {                       // block = fp16 d + 32 x int8 along ne0 (convert_to_gguf.py:93-129)
+        const size_t nb = out.size() / 32;
+        for (size_t b = 0; b < nb; ++b) {
+            uint16_t h; memcpy(&h, &raw[b * 34], 2); const float d = half_bits_to_float(h);
+            const int8_t* q = (const int8_t*)&raw[b * 34 + 2];
+            for (int i = 0; i < 32; ++i) out[b * 32 + i] = d * (float)q[i];
+        }
+    } else if (t.type == GGML_Q4_0) {                     // block = fp16 d + 16 nibble bytes: element i = low nibble of byte i, i + 16 = high nibble;
+        const size_t nb = out.size() / 32;                // value = d * (q - 8) (convert_to_gguf.py:132-179)
+        for (size_t b = 0; b < nb; ++b) {
+            uint16_t h; memcpy(&h, &raw[b * 18], 2); const float d = half_bits_to_float(h);
+            const uint8_t* q = &raw[b * 18 + 2];
+            for (int i = 0; i < 16; ++i) { out[b * 32 + i] = d * (float)((int)(q[i] & 0x0F) - 8); out[b * 32 + 16 + i] = d * (float)((int)(q[i] >> 4) - 8); }
+        }
+    } else throw std::runtime_error("unsupported tensor type for " + name);
+    return out;
+}
+
 }  // namespace nsb

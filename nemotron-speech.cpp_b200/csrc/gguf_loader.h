@@ -35,6 +35,10 @@ struct GgufFile {
     const GgufTensor& require(const std::string& name) const;
     // Reads a tensor that must be F32 (or F16, widened) into floats.
     std::vector<float> read_f32(const std::string& name) const;
+    // Reads any supported tensor as floats: F32 / F16 as stored; Q8_0 blocks (fp16 d + 32 x int8 along ne0) as d * q; Q4_0 blocks
+    // (fp16 d + 16 nibble bytes: element i = low nibble of byte i, element i + 16 = high nibble) as d * (q - 8)
+    // (scripts/convert_to_gguf.py:93-179; what ggml's dequantize_row_q8_0 / _q4_0 return).
+    std::vector<float> read_dequant(const std::string& name) const;
 };
 
 // fp16 bits -> float (host)

@@ -268,3 +268,23 @@ def test_host_stream_bookkeeping_against_the_oracle(built, tmp_path):
                 st = O.Stream(om, R); st.push(np.zeros(n, np.int16))
                 assert st.chunks == chunks, (R, n, st.chunks, chunks)
             assert chunks == max(0, (n - 96) // (1280 * T))
+
+
+@pytest.mark.parametrize("kind", ["f16", "q8_0", "q4_0"])
+def test_product_loader_dequantisation_matches_gguf_package(built, kind):
+    """The engine's own GGUF reader (csrc/gguf_loader.cpp through nsb_gguf_read_tensor, no GPU): every tensor of a synthetic file
+    of each weight type, bit for bit against the gguf package's reader + dequantiser (documented bit-exact with ggml-quants.c)."""
+    import gguf
+    import nsb200
+    path = synth.cached_model(kind, 2, R=0)
+    rd = gguf.GGUFReader(path)
+    seen = set()
+    for t in rd.tensors:
+        want = gguf.quants.dequantize(np.asarray(t.data), t.tensor_type).astype(np.float32).reshape(-1)
+        got, ty = nsb200.read_tensor(path, t.name)
+        assert ty == int(t.tensor_type) and got.shape == want.shape, t.name
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), t.name
+        seen.add(ty)
+    assert {"f16": 1, "q8_0": 8, "q4_0": 2}[kind] in seen and 0 in seen
+    with pytest.raises(nsb200.NsbError, match="missing tensor"):
+        nsb200.read_tensor(path, "encoder.layers.99.nope")
