@@ -16,6 +16,8 @@
 //                            per-chunk latency (last sample handed over -> token ids back on the host)
 //     --flush                zero-pad each stream's tail up to the next chunk boundary so that the last partial chunk is
 //                            decoded (the reference drops it: transcribe_stream.cpp:143-166 never pads, nemo-stream.cpp:1102)
+//     --warmup               before a wave starts, run one chunk of silence through all its streams and reset them: the step's CUDA
+//                            graph for that batch size is captured outside the measured run (off by default)
 //     --tokens               print token ids after the text
 // stdout: "<index>\t<name>\t<transcript>" per stream, input order. stderr: per-GPU and total statistics.
 // Exit code 1 on usage / load / open failure (transcribe_stream.cpp:53-56,102-105,131-137), 2 on an engine error mid-run.
@@ -51,7 +53,7 @@ struct Options {
     std::string model;
     int right_context = 13, compute = NSB_COMPUTE_AUTO, kv = -1, max_streams = 256;
     std::vector<int> devices{0};
-    bool realtime = false, flush = false, print_tokens = false;
+    bool realtime = false, flush = false, print_tokens = false, warmup = false;
 };
 struct WorkerStats {
     int device = 0, streams = 0, waves = 0;
@@ -64,7 +66,7 @@ struct WorkerStats {
 int usage(const char* argv0) {
     fprintf(stderr,
             "Usage: %s model.gguf [--right-context 0|1|6|13] [--compute auto|f32|f16|bf16|q8_0] [--kv f32|f16|bf16]\n"
-            "          [--gpus G | --devices 0,1,..] [--max-streams N] [--realtime] [--flush] [--tokens]\n"
+            "          [--gpus G | --devices 0,1,..] [--max-streams N] [--realtime] [--flush] [--warmup] [--tokens]\n"
             "          [--list FILE] [--synthetic N SECONDS] [audio.pcm ...]\n"
             "  audio: raw 16 kHz s16le mono, one stream per file\n",
             argv0);
@@ -159,6 +161,16 @@ void run_worker(const Options& opt, int device, const std::vector<Input>& inputs
         }
         if (!ws.error.empty()) break;
         static const std::vector<int16_t> zeros(1 << 16, 0);
+        if (opt.warmup) {                                                         // capture the graph of an n-stream step on silence, then start over
+            for (int i = 0; i < n && ws.error.empty(); ++i)
+                for (int left = chunk; left > 0 && ws.error.empty(); left -= (int)zeros.size())
+                    if (nsb_stream_push_pcm(e, ids[i], zeros.data(), std::min<int>(left, (int)zeros.size())) != NSB_OK) fail("nsb_stream_push_pcm");
+            if (ws.error.empty() && nsb_engine_step(e) < 0) fail("nsb_engine_step");
+            for (int i = 0; i < n && ws.error.empty(); ++i) if (nsb_stream_reset(e, ids[i]) != NSB_OK) fail("nsb_stream_reset");   // caches, decoder state, queued tokens
+            if (!ws.error.empty()) break;
+        }
+        nsb_stats st0;
+        nsb_engine_get_stats(e, &st0);                                            // statistics of the wave exclude the warm-up step
         // hand stream i its next `want` samples (real audio first, then the flush padding); returns samples handed over
         auto feed_one = [&](int i, int want) -> int {
             const std::vector<int16_t>& pcm = inputs[mine[w0 + i]].pcm;
@@ -231,6 +243,10 @@ void run_worker(const Options& opt, int device, const std::vector<Input>& inputs
         }
         if (!ws.error.empty()) break;
         if (!pop_all()) break;
+        nsb_stats st1;
+        nsb_engine_get_stats(e, &st1);
+        ws.chunks += st1.chunks - st0.chunks; ws.steps += st1.steps - st0.steps; ws.launches += st1.kernel_launches - st0.kernel_launches;
+        ws.device_ms += st1.device_ms - st0.device_ms;
         for (int i = 0; i < n; ++i) {
             Result& r = results[mine[w0 + i]];
             r.chunks = nsb_stream_chunks(e, ids[i]);
@@ -243,9 +259,6 @@ void run_worker(const Options& opt, int device, const std::vector<Input>& inputs
         }
     }
     ws.wall_s = seconds_since(t_run);
-    nsb_stats st;
-    nsb_engine_get_stats(e, &st);
-    ws.chunks = st.chunks; ws.steps = st.steps; ws.launches = st.kernel_launches; ws.device_ms = st.device_ms;
     nsb_engine_destroy(e);
 }
 
@@ -275,6 +288,7 @@ int main(int argc, char** argv) {
         else if (a == "--max-streams") { opt.max_streams = atoi(next("--max-streams")); if (opt.max_streams < 1) return usage(argv[0]); }
         else if (a == "--realtime") opt.realtime = true;
         else if (a == "--flush") opt.flush = true;
+        else if (a == "--warmup") opt.warmup = true;
         else if (a == "--tokens") opt.print_tokens = true;
         else if (a == "--list") {
             const char* p = next("--list");

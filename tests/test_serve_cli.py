@@ -67,13 +67,14 @@ def _parse(stdout):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("extra", [[], ["--realtime"]])
+@pytest.mark.parametrize("extra", [[], ["--realtime"], pytest.param(["--warmup"], marks=pytest.mark.xfail(
+    strict=False, reason="--warmup was added after the round's GPU budget was spent: not yet run on hardware"))])
 def test_ragged_streams_in_waves_match_the_oracle(exe, tmp_path, extra):
     """5 streams of different lengths (one shorter than a chunk, one empty) over 2 stream slots = 3 waves with slot reuse."""
     R = 1
     path = synth.cached_model("f32", 2, R=R)
     secs = [1.3, 0.9, 0.1, 2.0, 0.0]
-    if extra:
+    if extra == ["--realtime"]:
         secs = [0.7, 0.5, 0.1]                                        # real-time pacing: keep it short
     files, want = [], []
     for i, s in enumerate(secs):
@@ -95,7 +96,7 @@ def test_ragged_streams_in_waves_match_the_oracle(exe, tmp_path, extra):
         assert rows[i][2] == toks, (i, rows[i][2], toks)
         assert rows[i][1] == om.detok(np.asarray(toks, np.int32))
     assert f"Chunks processed:    {sum(c for _, c in want)}" in r.stderr
-    assert ("Chunk latency:" in r.stderr) == bool(extra)
+    assert ("Chunk latency:" in r.stderr) == (extra == ["--realtime"])
 
 
 @pytest.mark.gpu
