@@ -154,3 +154,67 @@ def test_two_gpus_in_one_process(exe, tmp_path):
         solo = _parse(alone.stdout)
         for k, i in enumerate(range(dev, len(secs), 2)):
             assert len(solo[k][2]) > 0 and solo[k][2] == got[i][2], (dev, i)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The serve program's host loop on CPU, against a test double of the C ABI (tests/mock_nsb200.cpp: the engine's own chunk gate,
+# one token = chunk index per processed chunk). Covers what the GPU cases cannot enumerate: every latency mode x ragged lengths x
+# waves x GPUs x flush / realtime / warmup, with no chunk lost, duplicated or reordered.
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def mock_exe(tmp_path_factory):
+    d = tmp_path_factory.mktemp("mock")
+    exe = d / "serve_mock"
+    csrc = os.path.join(ROOT, "nemotron-speech.cpp_b200", "csrc")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-pthread", "-I", os.path.join(ROOT, "include"), "-I", csrc,
+                           os.path.join(csrc, "serve_main.cpp"), os.path.join(ROOT, "tests", "mock_nsb200.cpp"), "-o", str(exe)])
+    return str(exe)
+
+
+def _expected_chunks(n, T, flush):
+    if flush and n > 0:
+        frames = (n - 1) // 160 + 1
+        return -(-frames // (8 * T))
+    return max(0, (n - 96) // (1280 * T))
+
+
+@pytest.mark.parametrize("R", [0, 1, 6, 13])
+@pytest.mark.parametrize("mode", ["plain", "flush", "warmup", "gpus3"])
+def test_serve_host_loop_on_the_mock_engine(mock_exe, tmp_path, R, mode):
+    T = R + 1
+    rng = np.random.default_rng(100 + R)
+    lens = [0, 95, 1280 * T + 95, 1280 * T + 96, 3 * 1280 * T + 96, int(rng.integers(20000, 90000)), int(rng.integers(20000, 90000))]
+    files = []
+    for i, n in enumerate(lens):
+        f = tmp_path / f"m{i}.pcm"
+        rng.integers(-3000, 3000, n).astype(np.int16).tofile(f)
+        files.append(f)
+    args = [tmp_path / "model.gguf", "--right-context", R, "--tokens", "--max-streams", 3]
+    args += {"plain": [], "flush": ["--flush"], "warmup": ["--warmup"], "gpus3": ["--gpus", 3, "--max-streams", 2]}[mode]
+    r = run(mock_exe, *args, *files)
+    assert r.returncode == 0, r.stderr
+    rows = _parse(r.stdout)
+    total = 0
+    for i, n in enumerate(lens):
+        c = _expected_chunks(n, T, mode == "flush")
+        assert rows[i][2] == list(range(c)), (mode, R, i, n, rows[i][2][:5], c)       # every chunk once, in order, nothing after a reset
+        total += c
+    assert f"Chunks processed:    {total}\n" in r.stderr
+    if mode == "gpus3":
+        assert "GPU 0: 3 streams in 2 wave(s)" in r.stderr and "GPU 2: 2 streams in 1 wave(s)" in r.stderr
+
+
+def test_serve_realtime_on_the_mock_engine(mock_exe, tmp_path):
+    R, T = 0, 1
+    lens = [16000, 9000, 12345]
+    files = []
+    for i, n in enumerate(lens):
+        f = tmp_path / f"r{i}.pcm"; np.zeros(n, np.int16).tofile(f); files.append(f)
+    r = run(mock_exe, tmp_path / "model.gguf", "--right-context", R, "--tokens", "--realtime", *files)
+    assert r.returncode == 0, r.stderr
+    rows = _parse(r.stdout)
+    for i, n in enumerate(lens):
+        assert rows[i][2] == list(range(_expected_chunks(n, T, False)))
+    assert "Chunk latency:" in r.stderr and "real-time pacing" in r.stderr
+    wall = float(r.stderr.split("Processing time:")[1].split("sec")[0])
+    assert 0.8 <= wall <= 1.6                                            # 1 s of audio paced at audio rate
