@@ -25,7 +25,9 @@ const char* nsb_last_error(void) { return g_err.c_str(); }
 int nsb_gguf_probe(const char* p, nsb_model_info* info) {
     if (!p || !info) return fail(NSB_ERR_ARG, "null argument");
     if (strstr(p, "missing")) return fail(NSB_ERR_IO, "gguf: cannot open (mock)");
-    memset(info, 0, sizeof(*info)); info->n_layers = 2; info->vocab_size = 1025; return NSB_OK;
+    memset(info, 0, sizeof(*info)); info->n_layers = 2; info->vocab_size = 1025; info->d_model = 1024; info->n_heads = 8; info->d_head = 128;
+    for (int i = 0; i < 1025; ++i) snprintf(info->vocab + 8 * i, 8, "%d,", i);                 // piece of token i = "i,"
+    return NSB_OK;
 }
 void nsb_default_config(nsb_engine_config* c) { memset(c, 0, sizeof(*c)); c->max_streams = 1; c->use_cuda_graph = 1; }
 int nsb_engine_create(const char*, const nsb_engine_config* cfg, nsb_engine** out) {
@@ -86,4 +88,8 @@ int nsb_detokenize(const nsb_engine*, const int32_t* t, int n, char* out, int ca
     memcpy(out, r.c_str(), r.size() + 1); return (int)r.size();
 }
 void nsb_engine_get_stats(const nsb_engine* e, nsb_stats* out) { *out = e->st; }
+int nsb_stream_ready(const nsb_engine* e, int s) { return s >= 0 && s < e->max_streams && nsb::hs_ready(e->hs[s], e->T) ? 1 : 0; }
+// referenced by the drop-in shim (csrc/nemo_shim.cpp) but not part of what the double models
+int nsb_op_logmel(nsb_engine*, const int16_t*, int, int, float*, size_t) { return fail(NSB_ERR_STATE, "mock: no log-mel"); }
+int nsb_transcribe_full(nsb_engine*, const int16_t*, int, int32_t*, int, int*, float*, size_t) { return fail(NSB_ERR_STATE, "mock: no batch path"); }
 }

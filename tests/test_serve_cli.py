@@ -218,3 +218,28 @@ def test_serve_realtime_on_the_mock_engine(mock_exe, tmp_path):
     assert "Chunk latency:" in r.stderr and "real-time pacing" in r.stderr
     wall = float(r.stderr.split("Processing time:")[1].split("sec")[0])
     assert 0.8 <= wall <= 1.6                                            # 1 s of audio paced at audio rate
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/transcribe_stream.cpp"), reason="reference sources not present")
+@pytest.mark.parametrize("R", [0, 1, 6, 13])
+def test_reference_cli_on_the_shim_and_the_mock_engine(tmp_path, R):
+    """The reference's own streaming CLI (byte-identical) + the drop-in shim (csrc/nemo_shim.cpp) + the test double of the C ABI, on
+    CPU: the shim's push -> step-until-drained -> pop loop (nemo-stream.cpp:1074-1134) emits every chunk once and in order although
+    the CLI reads 160 (9 + 8T) samples per call and a chunk consumes only 1280 T (some calls run two chunks, SURVEY appendix A);
+    stdout = incremental pieces + the whole transcript + newline; stderr carries the chunk count."""
+    T = R + 1
+    csrc = os.path.join(ROOT, "nemotron-speech.cpp_b200", "csrc")
+    src = tmp_path / "transcribe_stream.cpp"
+    src.write_bytes(open("/root/reference/src/transcribe_stream.cpp", "rb").read())
+    exe = tmp_path / "cli_mock"
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), "-I", csrc, str(src),
+                           os.path.join(csrc, "nemo_shim.cpp"), os.path.join(ROOT, "tests", "mock_nsb200.cpp"), "-o", str(exe)])
+    n = 16000 * 9 + 777
+    f = tmp_path / "a.pcm"
+    np.zeros(n, np.int16).tofile(f)
+    r = subprocess.run([str(exe), str(tmp_path / "model.gguf"), str(f), "70", str(R)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    chunks = _expected_chunks(n, T, False)                              # the trailing partial read is processed too (transcribe_stream.cpp:145-166)
+    text = "".join(f"{c}," for c in range(chunks))
+    assert r.stdout == text + text + "\n", (r.stdout[:200], chunks)
+    assert f"Chunks processed:    {chunks}" in r.stderr
