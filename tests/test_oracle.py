@@ -295,3 +295,24 @@ def test_detokeniser(built, model2):
     ids = [i for i in range(50)] + [1024, 5000, -1]
     expect = "".join((" " + p[1:]) if p.startswith("▁") else p for p in (pieces[i] for i in range(50)))
     assert model2.detok(ids) == expect
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/scripts/compare_tensors.py"), reason="reference scripts not present")
+def test_encoder_dump_is_readable_by_the_reference_compare_script(built, model2, tmp_path):
+    """tools/dump_encoder_out.py writes per-chunk encoder output in the reference's own dump format (nemo-stream.cpp:886-958); the
+    reference's scripts/compare_tensors.py must load it (its loader reads the first chunk) and report it identical to itself."""
+    import importlib.util
+    import subprocess
+    import sys
+    pcm = synth.synth_pcm(4, 1.2)
+    f = tmp_path / "a.pcm"; pcm.tofile(f)
+    out = tmp_path / "enc.bin"
+    tool = os.path.join(os.path.dirname(GOLD), "..", "tools", "dump_encoder_out.py")
+    subprocess.check_call([sys.executable, tool, "--impl", "oracle", synth.cached_model("f32", 2, R=0), str(f), "6", str(out)])
+    spec = importlib.util.spec_from_file_location("ref_compare_tensors", "/root/reference/scripts/compare_tensors.py")
+    ref = importlib.util.module_from_spec(spec); spec.loader.exec_module(ref)
+    t = ref.load_tensor(str(out))
+    s = O.Stream(model2, 6, trace=True); s.push(pcm)
+    assert s.chunks == 2 and t.shape == (7, 1024)
+    assert np.array_equal(t, s.trace_enc(0))
+    assert os.path.getsize(out) == 32 + s.chunks * 7 * 1024 * 4
