@@ -288,3 +288,21 @@ def test_product_loader_dequantisation_matches_gguf_package(built, kind):
     assert {"f16": 1, "q8_0": 8, "q4_0": 2}[kind] in seen and 0 in seen
     with pytest.raises(nsb200.NsbError, match="missing tensor"):
         nsb200.read_tensor(path, "encoder.layers.99.nope")
+
+
+def test_c_abi_header_is_plain_c_and_the_example_runs_on_the_test_double(tmp_path):
+    """include/nsb200.h must be consumable from plain C (the boundary other hosts bind: cgo, JNI, N-API ... all speak C):
+    examples/minimal.c compiles as strict C99 (-pedantic -Werror) and, linked against the test double of the library
+    (tests/mock_nsb200.cpp), runs the push / step / pop / detokenise sequence."""
+    obj = tmp_path / "minimal.o"
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), "-c",
+                           os.path.join(ROOT, "examples", "minimal.c"), "-o", str(obj)])
+    exe = tmp_path / "minimal"
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), "-I",
+                           os.path.join(ROOT, "nemotron-speech.cpp_b200", "csrc"), str(obj), os.path.join(ROOT, "tests", "mock_nsb200.cpp"), "-o", str(exe)])
+    f = tmp_path / "a.pcm"
+    np.zeros(16000 * 3, np.int16).tofile(f)
+    r = subprocess.run([str(exe), str(tmp_path / "model.gguf"), str(f), "1"], capture_output=True, text=True)
+    chunks = (48000 - 96) // 2560
+    assert r.returncode == 0 and r.stdout == "".join(f"<{c}>" for c in range(chunks)) + "\n", (r.stdout, r.stderr)
+    assert f"{chunks} chunks, {chunks} tokens" in r.stderr
