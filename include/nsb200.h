@@ -36,7 +36,10 @@ enum nsb_compute {
     NSB_COMPUTE_F32 = 1,  /* SIMT fp32 GEMM (strict parity with the f32 reference path)                   */
     NSB_COMPUTE_F16 = 2,  /* tcgen05 kind::f16, fp16 operands, fp32 TMEM accumulate                       */
     NSB_COMPUTE_BF16 = 3, /* tcgen05 kind::f16, bf16 operands, fp32 TMEM accumulate                       */
-    NSB_COMPUTE_Q8_0 = 4  /* Q8_0 weights resident in HBM, dequantised to fp16 in the operand producer    */
+    NSB_COMPUTE_Q8_0 = 4, /* Q8_0 weights resident in HBM, dequantised to fp16 in the operand producer    */
+    NSB_COMPUTE_Q8_0_STRICT = 5 /* the reference's own Q8_0 arithmetic (ggml_mul_mat on a Q8_0 src0): activation rows quantised
+                                   per 32 (d = amax/127 as fp16, q = roundf(x/d)), exact integer block dots on the tensor cores
+                                   (mma s8), f32 scale-accumulate in block order; everything else as NSB_COMPUTE_F32. Parity mode */
 };
 enum nsb_kv_dtype { NSB_KV_F32 = 0, NSB_KV_F16 = 1, NSB_KV_BF16 = 2 };
 
@@ -88,6 +91,9 @@ const char* nsb_engine_vocab(const nsb_engine* e); /* vocab_size * 8 bytes, NUL 
 int nsb_engine_chunk_samples(const nsb_engine* e); /* nemo_cache_config::get_chunk_samples (nemo-stream.h:85-87) */
 int nsb_engine_shift_samples(const nsb_engine* e); /* 160 * get_shift_mel_frames (nemo-stream.h:76-81)          */
 int nsb_engine_compute(const nsb_engine* e);       /* resolved enum nsb_compute                                  */
+/* switch CUDA-graph replay of the step on / off at run time (nsb_engine_config::use_cuda_graph is the initial value). Both ways
+ * launch the same kernels with the same arguments: results are bit-identical (bench.py checks a token checksum across the two). */
+int nsb_engine_set_cuda_graph(nsb_engine* e, int on);
 
 /* ---- streams: replaces nemo_stream_init / reset / free (src/nemo-stream.h:262-312) ------- */
 int nsb_stream_open(nsb_engine* e);                /* returns stream id >= 0, or <0 */
@@ -157,7 +163,9 @@ int nsb_profiler_range(int on);
  * When enabled, the engine keeps the tensors of the LAST step: names
  *   "mel" [B, M, 128]  "sub" [B*T, 1024]  "layer.<l>" [B*T, 1024]  "enc" [B*T, 1024]
  * and, for decode, every joint evaluation's logits of batch row 0 ("logits", up to cap evals).
- * Rows are ordered by the step's batch order = ascending stream id. */
+ * Rows are ordered by the step's batch order = ascending stream id.
+ * One name works WITHOUT tap mode: "x" [B*T, 1024] = encoder output of the most recently launched step, copied out of the step
+ * workspace after the step -- it observes the production path (CUDA graph, no taps) unchanged. */
 int nsb_debug_enable(nsb_engine* e, int on);
 int nsb_debug_get(nsb_engine* e, const char* name, float* out, size_t cap_floats); /* returns #floats or <0 */
 int nsb_debug_get_cache(nsb_engine* e, int stream, int which /*0=k,1=v,2=conv*/, int layer, float* out, size_t cap);

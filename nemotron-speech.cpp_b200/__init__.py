@@ -15,7 +15,7 @@ import numpy as np
 _DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_DIR, "libnsb200.so")
 
-COMPUTE_AUTO, COMPUTE_F32, COMPUTE_F16, COMPUTE_BF16, COMPUTE_Q8_0 = 0, 1, 2, 3, 4
+COMPUTE_AUTO, COMPUTE_F32, COMPUTE_F16, COMPUTE_BF16, COMPUTE_Q8_0, COMPUTE_Q8_0_STRICT = 0, 1, 2, 3, 4, 5
 KV_F32, KV_F16, KV_BF16 = 0, 1, 2
 
 
@@ -47,7 +47,7 @@ class ModelInfo(C.Structure):
 
 
 EXPORTS = ["nsb_gguf_probe", "nsb_gguf_read_tensor", "nsb_default_config", "nsb_engine_create", "nsb_engine_destroy", "nsb_last_error", "nsb_engine_n_layers",
-           "nsb_engine_vocab_size", "nsb_engine_vocab", "nsb_engine_chunk_samples", "nsb_engine_shift_samples", "nsb_engine_compute",
+           "nsb_engine_vocab_size", "nsb_engine_vocab", "nsb_engine_chunk_samples", "nsb_engine_shift_samples", "nsb_engine_compute", "nsb_engine_set_cuda_graph",
            "nsb_stream_open", "nsb_stream_close", "nsb_stream_reset", "nsb_stream_push_pcm", "nsb_push_pcm_batch", "nsb_pop_tokens_batch", "nsb_stream_ready", "nsb_engine_step", "nsb_engine_step_begin", "nsb_engine_step_end",
            "nsb_engine_drain", "nsb_stream_pop_tokens", "nsb_stream_chunks", "nsb_detokenize", "nsb_engine_get_stats",
            "nsb_bench_prepare", "nsb_bench_step", "nsb_bench_steps", "nsb_bench_profile", "nsb_profiler_range", "nsb_bench_gemm", "nsb_trace_enable", "nsb_trace_fetch", "nsb_debug_enable", "nsb_debug_get", "nsb_debug_get_cache", "nsb_op_logmel",
@@ -85,6 +85,7 @@ def lib():
                   "nsb_engine_compute", "nsb_stream_open", "nsb_engine_step", "nsb_engine_step_begin", "nsb_engine_step_end", "nsb_engine_drain"):
             getattr(L, n).argtypes = [vp]
         L.nsb_engine_vocab.argtypes = [vp]
+        L.nsb_engine_set_cuda_graph.argtypes = [vp, ci]
         L.nsb_engine_vocab.restype = vp
         for n in ("nsb_stream_close", "nsb_stream_reset", "nsb_stream_ready", "nsb_stream_chunks"):
             getattr(L, n).argtypes = [vp, ci]
@@ -159,6 +160,9 @@ class Engine:
             self.h = None
 
     __del__ = close
+
+    def set_cuda_graph(self, on: bool):
+        _check(lib().nsb_engine_set_cuda_graph(self.h, 1 if on else 0))
 
     # ---- streams ----
     def open_stream(self) -> int:

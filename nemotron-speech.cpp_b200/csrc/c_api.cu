@@ -98,6 +98,8 @@ int nsb_engine_chunk_samples(const nsb_engine* e) { return e ? e->impl->chunk_sa
 int nsb_engine_shift_samples(const nsb_engine* e) { return e ? e->impl->shift_samples() : NSB_ERR_ARG; }
 int nsb_engine_compute(const nsb_engine* e) { return e ? e->impl->compute : NSB_ERR_ARG; }
 
+int nsb_engine_set_cuda_graph(nsb_engine* e, int on) { if (!e) return fail(NSB_ERR_ARG, "null engine"); NSB_TRY e->impl->set_cuda_graph(on != 0); return NSB_OK; NSB_CATCH }
+
 int nsb_stream_open(nsb_engine* e) { if (!e) return fail(NSB_ERR_ARG, "null engine"); NSB_TRY return e->impl->open_stream(); NSB_CATCH }
 int nsb_stream_close(nsb_engine* e, int s) { if (!e) return fail(NSB_ERR_ARG, "null engine"); NSB_TRY e->impl->close_stream(s); return NSB_OK; NSB_CATCH }
 int nsb_stream_reset(nsb_engine* e, int s) { if (!e) return fail(NSB_ERR_ARG, "null engine"); NSB_TRY e->impl->reset_stream(s); return NSB_OK; NSB_CATCH }

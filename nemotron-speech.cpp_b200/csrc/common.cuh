@@ -186,6 +186,17 @@ __device__ __forceinline__ void store_kv(void* p, size_t i, float v, int kv) {
     else if (kv == 1) ((__half*)p)[i] = __float2half_rn(v);
     else ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(v);
 }
+// 3xTF32: v = hi + lo with hi, lo exactly representable in tf32 (10 explicit mantissa bits); the dropped remainder is <= 2^-22 |v|.
+// a . w ~= a_hi w_hi + a_hi w_lo + a_lo w_hi on kind::tf32 tensor cores with fp32 accumulation: fp32-class accuracy for the
+// matrices every GGUF keeps in F32 (subsampling stem, joint.enc), which the reference multiplies in fp32.
+__device__ __forceinline__ float to_tf32(float v) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); return __uint_as_float(r); }
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) { hi = to_tf32(v); lo = to_tf32(v - hi); }
+// NHWC pixel store, C = 256: plain, or [hi (256) | lo (256)] for a 3xTF32 consumer
+__device__ __forceinline__ void store_pixel(float* out, size_t pix, int c, float v, int split) {
+    if (!split) { out[pix * 256 + c] = v; return; }
+    float hi, lo; split_tf32(v, hi, lo);
+    out[pix * 512 + c] = hi; out[pix * 512 + 256 + c] = lo;
+}
 inline size_t kv_elem_size(int kv) { return kv == 0 ? 4 : 2; }
 inline size_t out_elem_size(int ot) { return ot == OUT_F32 ? 4 : 2; }
 

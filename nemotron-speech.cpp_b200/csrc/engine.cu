@@ -23,6 +23,10 @@ void launch_gemm_tc(const GemmArgs& a, int in_type /*OUT_F16 | OUT_BF16*/, cudaS
 constexpr int MAX_SPLITS = 8;
 constexpr size_t SPLIT_CONSUMER_MAX_ROWS = 256;   // up to this many token rows per step the QKV / pointwise-1 GEMMs are split-K as well
 
+bool tf32x3_enabled() {
+    static const bool on = [] { const char* e = getenv("NSB_STEM_TF32"); return !(e && e[0] == '1'); }();
+    return on;
+}
 bool pdl_enabled() {
     static const bool on = [] { const char* e = getenv("NSB_NO_PDL"); return !(e && e[0] == '1'); }();
     return on;
@@ -55,6 +59,24 @@ void upload(DevBuf& d, const std::vector<float>& h) {
     h2d_sync(d.p, h.data(), h.size() * sizeof(float));
 }
 
+// 3xTF32 weight layout (common.cuh: split_tf32): [n_out][hi (K) | lo (K) | hi (K)], rounding = cvt.rna.tf32 (nearest, ties away)
+float host_to_tf32(float v) {
+    uint32_t u; memcpy(&u, &v, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return v;                 // inf / nan
+    u = (u + 0x1000u) & ~0x1fffu;
+    float r; memcpy(&r, &u, 4); return r;
+}
+std::vector<float> tf32x3_weight(const std::vector<float>& w, int n_out, int n_in) {
+    std::vector<float> o((size_t)n_out * 3 * n_in);
+    for (int n = 0; n < n_out; ++n)
+        for (int k = 0; k < n_in; ++k) {
+            const float v = w[(size_t)n * n_in + k], hi = host_to_tf32(v), lo = host_to_tf32(v - hi);
+            float* r = &o[(size_t)n * 3 * n_in];
+            r[k] = hi; r[n_in + k] = lo; r[2 * n_in + k] = hi;
+        }
+    return o;
+}
+
 // positional table row for relative position p (src/nemo-ggml.cpp:17-32)
 void pos_emb_row(int p_int, float* row) {
     const float p = (float)p_int;
@@ -76,6 +98,7 @@ Engine::Engine(const std::string& path, const nsb_engine_config& cfg) : cfg_(cfg
     cudaDeviceProp prop{};
     NSB_CUDA(cudaGetDeviceProperties(&prop, device_));
     if (prop.major != 10) throw CudaError(std::string("device '") + prop.name + "' is not sm_100 (kernels are built for sm_100a only)");
+    try {
     NSB_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     NSB_CUDA(cudaEventCreate(&ev0_));
     NSB_CUDA(cudaEventCreate(&ev1_));
@@ -107,18 +130,27 @@ Engine::Engine(const std::string& path, const nsb_engine_config& cfg) : cfg_(cfg
     alloc_state();
     build_pos_tables(g);
     NSB_CUDA(cudaStreamSynchronize(st_));
+    } catch (...) { release_handles(); throw; }                    // a throwing constructor runs no destructor: free the stream and events here
 }
 
-Engine::~Engine() {
+void Engine::release_handles() {
     cudaSetDevice(device_);
     cudaDeviceSynchronize();
     for (auto& g : graphs_) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+    graphs_.clear();
     for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
-    if (ev0_) cudaEventDestroy(ev0_);
-    if (ev1_) cudaEventDestroy(ev1_);
-    for (StepIO& io : io_) { if (io.ev0) cudaEventDestroy(io.ev0); if (io.ev1) cudaEventDestroy(io.ev1); if (io.done) cudaEventDestroy(io.done); }
-    if (st_) cudaStreamDestroy(st_);
+    ev_pool_.clear();
+    if (ev0_) { cudaEventDestroy(ev0_); ev0_ = nullptr; }
+    if (ev1_) { cudaEventDestroy(ev1_); ev1_ = nullptr; }
+    for (StepIO& io : io_) {
+        if (io.ev0) { cudaEventDestroy(io.ev0); io.ev0 = nullptr; }
+        if (io.ev1) { cudaEventDestroy(io.ev1); io.ev1 = nullptr; }
+        if (io.done) { cudaEventDestroy(io.done); io.done = nullptr; }
+    }
+    if (st_) { cudaStreamDestroy(st_); st_ = nullptr; }
 }
+
+Engine::~Engine() { release_handles(); }
 
 void Engine::upload_weight(Weight& w, const std::string& name, const std::vector<float>& host, int n_out, int n_in) {
     w.name = name; w.n_out = n_out; w.n_in = n_in;
@@ -153,7 +185,7 @@ static void q8_planes(const GgufFile& g, const std::string& name, std::vector<in
 }
 
 void Engine::load_layer_matrix(Weight& w, const GgufFile& g, const std::string& out_name, const std::vector<std::string>& parts, int n_out, int n_in) {
-    if (compute != NSB_COMPUTE_Q8_0) {
+    if (!q8_planes_mode()) {
         std::vector<float> all;
         for (const std::string& pn : parts) { std::vector<float> h = read_matrix_f32(g, pn); all.insert(all.end(), h.begin(), h.end()); }
         upload_weight(w, out_name, all, n_out, n_in);
@@ -173,8 +205,11 @@ void Engine::load_weights(const GgufFile& g) {
         if (h.size() != expect) throw std::runtime_error("unexpected size for " + n);
         upload(d, h);
     };
+    // matrices every GGUF keeps in F32: fp32 SIMT in strict mode; on the tensor cores (16-bit / Q8_0 modes) as 3xTF32 -- the
+    // split copy [hi | lo | hi] goes to `scales` (NSB_STEM_TF32=1: single-pass tf32 on the plain copy, for A/B measurements)
     auto f32_weight = [&](Weight& w, const std::string& n, int n_out, int n_in, std::vector<float> h) {
         w.name = n; w.n_out = n_out; w.n_in = n_in; upload(w.data, h);
+        if (!strict() && tf32x3_enabled()) upload(w.scales, tf32x3_weight(h, n_out, n_in));
     };
     // ---- front-end tables (src/preprocessor.cpp:80-110, :296-299) ----
     {
@@ -277,10 +312,13 @@ void Engine::alloc_state() {
 
     rl_ = hs_row_len(T);                                                                  // 1280 T + 353 samples per stream-step
     const size_t Mrows = (size_t)S * T;
+    ensure_q8s_scratch((int)std::max<size_t>(Mrows, ATT_L + 2 * T));
     d_pcm_.alloc((size_t)S * rl_ * 2); d_slot_.alloc((size_t)S * 4);
     mel_new_.alloc((size_t)S * 8 * T * N_MELS * 4);
-    dw_.alloc((size_t)S * t2 * 33 * SUB_CH * 4);
+    const size_t sp = (!strict() && tf32x3_enabled()) ? 2 : 1;        // 3xTF32: stem activations as [hi | lo] pixels
+    dw_.alloc(sp * S * t2 * 33 * SUB_CH * 4);
     pw_.alloc((size_t)S * t2 * 33 * SUB_CH * 4);
+    if (sp == 2) a3_.alloc(std::max((size_t)S * t3 * SUB_W * SUB_CH, (size_t)S * T * D_MODEL) * 2 * 4, false);   // split A of the stem projection / joint.enc
     x_.alloc(Mrows * D_MODEL * 4);
     a_.alloc(Mrows * D_MODEL * act_size());
     big_.alloc(Mrows * D_FF * act_size());
@@ -301,6 +339,7 @@ void Engine::alloc_state() {
 }
 
 void Engine::zero_slot(int s) {
+    NSB_CUDA(cudaSetDevice(device_));
     const int Cap = ATT_L + T;
     const size_t kvb = (size_t)n_layers * 2 * Cap * D_MODEL * kv_elem_size(kv_dtype);
     NSB_CUDA(cudaMemsetAsync((char*)kv_.p + (size_t)s * kvb, 0, kvb, st_));
@@ -350,9 +389,33 @@ void Engine::gemm(const void* A, long long lda, const Weight& W, int M, const fl
     a.epi = epi; a.alpha = alpha; a.out_type = out_type; a.pair = 1;
     ProfScope ps(this, PC_GEMM);
     q8_predequant(W, M, a);
-    if (compute == NSB_COMPUTE_F32) launch_gemm_simt(a, st_);
+    if (compute == NSB_COMPUTE_Q8_0_STRICT) { launch_gemm_q8_strict(a, q8s_scratch_.p, q8s_scratch_.bytes, st_); count_launch(); }
+    else if (compute == NSB_COMPUTE_F32) launch_gemm_simt(a, st_);
     else launch_gemm_tc(a, act_type(), st_);
     count_launch();
+}
+
+void Engine::ensure_q8s_scratch(int rows) {
+    if (compute != NSB_COMPUTE_Q8_0_STRICT) return;
+    const size_t need = q8_strict_scratch_bytes(rows, D_FF);
+    if (q8s_scratch_.bytes < need) { NSB_CUDA(cudaStreamSynchronize(st_)); q8s_scratch_.alloc(need, false); }
+}
+
+// GEMM on a matrix every GGUF keeps in F32 (stem 1x1 convs, stem projection, joint.enc). Strict mode: fp32 SIMT. Tensor-core
+// modes: 3xTF32 -- W = [hi | lo | hi] (load time), A = [hi | lo] written by the producer kernel (a_presplit) or by a split pass
+// into a3_; NSB_STEM_TF32=1 falls back to single-pass tf32 on the plain fp32 operands.
+void Engine::gemm_f32w(GemmArgs& g, const Weight& W, bool a_presplit) {
+    if (strict()) { launch_gemm_simt(g, st_); count_launch(); return; }
+    if (W.scales.p) {
+        const int K = W.n_in;
+        if (!a_presplit) {
+            if (g.lda != K || (size_t)g.M * 2 * K * 4 > a3_.bytes) throw std::runtime_error("gemm_f32w: split scratch too small / strided A");
+            launch_split_tf32((const float*)g.A, a3_.as<float>(), (size_t)g.M, K, st_); count_launch();
+            g.A = a3_.p;
+        }
+        g.lda = 2 * K; g.a_fold = K; g.K = 3 * K; g.W = W.scales.p;
+    }
+    launch_gemm_tc(g, OUT_F32, st_); count_launch();
 }
 
 // Q8_0 mode, batches of >= 4 row tiles: dequantise the matrix once into an fp16 scratch (L2-resident hand-over to the GEMM that
@@ -384,7 +447,7 @@ void Engine::gemm_residual(const void* A, long long lda, const Weight& W, int M,
     // The N = 1024 GEMMs have few output tiles: with <= 1024 token rows the K dimension is split across CTAs so that
     // >= ~1 wave of SMs pulls weights; the fp32 partials land in part_ and the NEXT LayerNorm kernel adds them to x.
     int splits = 1;
-    if (compute != NSB_COMPUTE_F32 && M <= 1024) {
+    if (!strict() && M <= 1024) {
         const int tiles = ((M + 127) / 128) * (W.n_out / (W.n_in >= 4096 ? 64 : 32));
         const int nk = W.n_in / 64;
         while (splits < MAX_SPLITS && tiles * splits < 120 && nk % (splits * 2) == 0 && nk / (splits * 2) >= 2) splits *= 2;
@@ -412,7 +475,7 @@ int Engine::open_stream() {
         if (!hs_[s].open) { zero_slot(s); hs_[s].open = true; return s; }
     throw std::runtime_error("no free stream slot (max_streams = " + std::to_string(max_streams) + ")");
 }
-void Engine::close_stream(int s) { collect_all(); if (s < 0 || s >= max_streams || !hs_[s].open) throw std::invalid_argument("bad stream id"); hs_[s].open = false; }
+void Engine::close_stream(int s) { collect_all(); if (s < 0 || s >= max_streams || !hs_[s].open) throw std::invalid_argument("bad stream id"); hs_release_pcm(hs_[s]); hs_[s].open = false; }
 void Engine::reset_stream(int s) { collect_all(); if (s < 0 || s >= max_streams || !hs_[s].open) throw std::invalid_argument("bad stream id"); zero_slot(s); }
 
 void Engine::push_pcm(int s, const int16_t* pcm, int n) {
@@ -509,6 +572,7 @@ std::string Engine::detok(const int32_t* t, int n) const {
 }
 
 void Engine::run_step(int B, const int16_t* d_pcm) {
+    last_B_ = B;
     if (!cfg_.use_cuda_graph || debug_ || profiling_) { run_step_kernels(B, d_pcm); return; }
     StepGraph& g = graphs_[{B, (const void*)d_pcm}];
     if (!g.exec) {
@@ -559,22 +623,22 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
     count_launch();
     if (debug_) { launch_mel_gather(mel_hist_.as<float>(), mel_new_.as<float>(), slot, B, T, dbg_mel_.as<float>(), st_); count_launch(); }
     // S: subsampling stem (NHWC)
+    const bool tc = !strict();
+    const int split = tc && c3_w_.scales.p ? 1 : 0;                    // stem producers write [hi | lo] pixels for the 3xTF32 GEMMs
     if (!(skip & SK_SUB)) { ProfScope ps(this, PC_SUBSAMPLE);
     launch_stem_conv0_dw(mel_hist_.as<float>(), mel_new_.as<float>(), slot, B, T, c0_w_.as<float>(), c0_b_.as<float>(), c2_w_.as<float>(),
-                         c2_b_.as<float>(), dw_.as<float>(), st_);
+                         c2_b_.as<float>(), dw_.as<float>(), st_, split);
     launch_mel_hist_update(mel_hist_.as<float>(), mel_new_.as<float>(), slot, B, T, st_);
     count_launch(2);
-    // 1x1 convs + out projection: fp32 SIMT in strict-f32 mode, tcgen05 kind::tf32 otherwise (these matrices are F32 in every GGUF)
-    const bool tc = compute != NSB_COMPUTE_F32;
-    auto f32_gemm = [&](GemmArgs& g) { if (tc) launch_gemm_tc(g, OUT_F32, st_); else launch_gemm_simt(g, st_); count_launch(); };
+    // 1x1 convs + out projection: fp32 SIMT in strict-f32 mode, 3xTF32 on tcgen05 otherwise (these matrices are F32 in every GGUF)
     {
         GemmArgs g; g.A = dw_.p; g.lda = SUB_CH; g.W = c3_w_.data.p; g.M = B * t2 * 33; g.N = SUB_CH; g.K = SUB_CH; g.bias = c3_b_.as<float>();
-        g.C = pw_.p; g.ldc = SUB_CH; g.epi = EPI_RELU; f32_gemm(g);
+        g.C = pw_.p; g.ldc = SUB_CH; g.epi = EPI_RELU; gemm_f32w(g, c3_w_, split);
     }
-    launch_dwconv_s2(pw_.as<float>(), B, t2, 33, c5_w_.as<float>(), c5_b_.as<float>(), dw_.as<float>(), st_); count_launch();
+    launch_dwconv_s2(pw_.as<float>(), B, t2, 33, c5_w_.as<float>(), c5_b_.as<float>(), dw_.as<float>(), st_, split); count_launch();
     {
         GemmArgs g; g.A = dw_.p; g.lda = SUB_CH; g.W = c6_w_.data.p; g.M = B * t3 * SUB_W; g.N = SUB_CH; g.K = SUB_CH; g.bias = c6_b_.as<float>();
-        g.C = pw_.p; g.ldc = SUB_CH; g.epi = EPI_RELU; f32_gemm(g);
+        g.C = pw_.p; g.ldc = SUB_CH; g.epi = EPI_RELU; gemm_f32w(g, c6_w_, split);
     }
     {   // flatten + out linear on the T kept frames (frames 0,1 of every stream are dropped: nemo-stream.cpp:136-144)
         GemmArgs g; g.W = sub_out_w_.data.p; g.N = D_MODEL; g.K = SUB_W * SUB_CH; g.bias = out_b_.as<float>(); g.ldc = D_MODEL; g.lda = SUB_W * SUB_CH;
@@ -583,16 +647,15 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
             g.group = T; g.group_stride = (long long)t3 * SUB_W * SUB_CH; g.row_off = DROP_PRE; g.M = rows; g.C = x; g.epi = EPI_NONE;
         } else {                                                       // tensor cores: all T+2 frames, dropped rows skipped by the epilogue row map
             g.M = B * t3; g.c_group = t3; g.c_drop = DROP_PRE;
-            constexpr int SUB_SPLITS = 8;                              // K = 4352 = 136 k-blocks of 32; small batches need split-K to fill the SMs
-            if (!debug_ && rows <= 1024 && (size_t)(SUB_SPLITS - 1) * rows * D_MODEL * 4 <= part_.bytes) {
+            constexpr int SUB_SPLITS = 8;                              // K = 4352 = 136 k-blocks of 32 (x3 as 3xTF32); small batches need split-K to fill the SMs
+            if (rows <= 1024 && (size_t)(SUB_SPLITS - 1) * rows * D_MODEL * 4 <= part_.bytes) {
                 g.splits = SUB_SPLITS; g.epi = EPI_PARTIAL; g.C0 = x; g.C = part_.p;
                 pending_.part = part_.as<float>(); pending_.n = SUB_SPLITS - 1; pending_.alpha = 1.f;   // summed by the first LayerNorm
             } else { g.C = x; g.epi = EPI_NONE; }
         }
-        f32_gemm(g);
+        gemm_f32w(g, sub_out_w_, false);
     }
     }   // PC_SUBSAMPLE
-    if (debug_) NSB_CUDA(cudaMemcpyAsync(dbg_sub_.p, x, (size_t)rows * D_MODEL * 4, cudaMemcpyDeviceToDevice, st_));
 
     // L: cache-aware conformer layers
     const long long kv_slot_stride = (long long)n_layers * 2 * (ATT_L + T) * D_MODEL;
@@ -602,6 +665,9 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
         ProfScope ps(this, PC_LAYERNORM); launch_layernorm(x, rows, g_, b_, a_.p, at, pending_, st_); count_launch(); pending_ = PartialSum{};
     };
     ln(layers_[0].ln[0].as<float>(), layers_[0].ln[1].as<float>());
+    // "sub" tap: taken AFTER the first LayerNorm, which folds the split-K planes of the stem projection back into x -- so the
+    // tapped run executes exactly the arithmetic of the untapped one (taps only add copies)
+    if (debug_) NSB_CUDA(cudaMemcpyAsync(dbg_sub_.p, x, (size_t)rows * D_MODEL * 4, cudaMemcpyDeviceToDevice, st_));
     for (int l = 0; l < n_layers; ++l) {
         LayerW& L = layers_[l];
         // FFN1: x += 0.5 * W2 silu(W1 LN(x))                                        (nemo-stream.cpp:603-606)
@@ -666,8 +732,7 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
     {
         GemmArgs g; g.A = x; g.lda = D_MODEL; g.W = joint_enc_w_.data.p; g.M = rows; g.N = JOINT; g.K = D_MODEL; g.bias = joint_enc_b_.as<float>();
         g.C = encp_.p; g.ldc = JOINT; g.epi = EPI_NONE;
-        if (compute != NSB_COMPUTE_F32) launch_gemm_tc(g, OUT_F32, st_); else launch_gemm_simt(g, st_);
-        count_launch();
+        gemm_f32w(g, joint_enc_w_, false);
     }
     DecodeArgs d{};
     d.w.embed = embed_.as<float>();
@@ -760,13 +825,27 @@ float Engine::bench_steps(int n, float* ms_each) {
 }
 
 float Engine::bench_gemm(int kind, int rows, int bn, int stages, int splits, int rotate, int iters) {
-    if (compute == NSB_COMPUTE_F32) throw std::runtime_error("bench_gemm: tensor-core modes only");
+    if (strict()) throw std::runtime_error("bench_gemm: tensor-core modes only");
     if (rows < 1 || rows > max_streams * T || kind < 0 || kind > 5) throw std::invalid_argument("bench_gemm: bad arguments");
     NSB_CUDA(cudaSetDevice(device_));
     auto pick = [&](LayerW& L) -> Weight& { switch (kind) { case 0: return L.ff1a; case 1: return L.ff1b; case 2: return L.qkv; case 3: return L.out; case 4: return L.pw1; default: return L.pw2; } };
     auto run = [&]() {
         for (int l = 0; l < n_layers; ++l) {
             Weight& W = pick(layers_[l]);
+            if (splits < 0) {
+                // the step's own launch for this matrix: same tile choice, split-K rule, epilogue and (Q8_0 mode) dequantisation pass
+                switch (kind) {
+                    case 0: gemm(a_.p, D_MODEL, W, rows, nullptr, big_.p, D_FF, EPI_SILU, 1.f, act_type()); break;
+                    case 2: if (split_consumers(rows)) gemm_planes(a_.p, D_MODEL, W, rows, qkv_.p, 2);
+                            else gemm(a_.p, D_MODEL, W, rows, nullptr, qkv_.p, 3 * D_MODEL, EPI_NONE, 1.f, OUT_F32);
+                            break;
+                    case 4: gemm(a_.p, D_MODEL, W, rows, nullptr, pw1_.p, 2 * D_MODEL, EPI_NONE, 1.f, OUT_F32); break;
+                    case 1: gemm_residual(big_.p, D_FF, W, rows, x_.as<float>(), 0.5f); break;
+                    default: gemm_residual(a_.p, D_MODEL, W, rows, x_.as<float>(), 1.f); break;
+                }
+                pending_ = PartialSum{};
+                continue;
+            }
             GemmArgs a; a.A = W.n_in == D_FF ? big_.p : a_.p; a.lda = W.n_in; a.W = W.data.p; a.w_scales = W.scales.p; a.M = rows; a.N = W.n_out; a.K = W.n_in;
             a.force_bn = bn; a.force_stages = stages; a.rotate = rotate; a.splits = splits; a.ldc = W.n_out; a.pair = splits == 1;
             if (splits > 1) { a.C = part_.p; a.epi = EPI_PARTIAL; a.out_type = OUT_F32; }
@@ -852,6 +931,7 @@ float Engine::bench_profile(float* ms_per_class, int* launches_per_class) {
 // debug taps + stand-alone operators
 // ------------------------------------------------------------------------------------------
 void Engine::debug_enable(bool on) {
+    NSB_CUDA(cudaSetDevice(device_));
     debug_ = on;
     if (!on) return;
     dbg_B_ = max_streams;
@@ -864,7 +944,19 @@ void Engine::debug_enable(bool on) {
 }
 
 long long Engine::debug_get(const std::string& name, float* out, size_t cap) {
+    if (name == "x") {
+        // Encoder output of the most recently LAUNCHED step, read straight out of the step workspace: needs no tap mode, so it
+        // observes the production path (CUDA graph replay, PDL, split-K folded into LayerNorm) unchanged. Rows = that step's batch
+        // order. The caller must read it before launching the next step.
+        NSB_CUDA(cudaSetDevice(device_));
+        NSB_CUDA(cudaStreamSynchronize(st_));
+        const size_t n = std::min((size_t)last_B_ * T * D_MODEL, cap);
+        if (n) NSB_CUDA(cudaMemcpy(out, x_.p, n * 4, cudaMemcpyDeviceToHost));
+        return (long long)n;
+    }
     if (!debug_) throw std::runtime_error("debug taps are not enabled");
+    NSB_CUDA(cudaSetDevice(device_));
+    NSB_CUDA(cudaStreamSynchronize(st_));
     const void* src = nullptr; size_t n = 0;
     const size_t rows_all = (size_t)dbg_B_ * T;
     if (name == "mel") { src = dbg_mel_.p; n = (size_t)dbg_B_ * (PRE_CACHE + 8 * T) * N_MELS; }
@@ -886,6 +978,7 @@ long long Engine::debug_get(const std::string& name, float* out, size_t cap) {
 
 long long Engine::debug_get_cache(int stream, int which, int layer, float* out, size_t cap) {
     if (stream < 0 || stream >= max_streams || layer < 0 || layer >= n_layers) throw std::invalid_argument("bad stream/layer");
+    NSB_CUDA(cudaSetDevice(device_));
     NSB_CUDA(cudaStreamSynchronize(st_));
     if (which == 2) {
         const size_t n = (size_t)(CONV_K - 1) * D_MODEL; if (cap < n) return -(long long)n;
@@ -914,6 +1007,7 @@ long long Engine::debug_get_cache(int stream, int which, int layer, float* out, 
 
 long long Engine::op_logmel(const int16_t* pcm, int n_streams, int n_samples, float* out, size_t cap) {
     if (n_streams < 1 || n_samples < 1) throw std::invalid_argument("op_logmel: empty input");
+    NSB_CUDA(cudaSetDevice(device_));
     const long long avail = N_FFT / 2 + (long long)n_samples;
     const int n_frames = avail < N_FFT ? 0 : (int)((avail - N_FFT + HOP) / HOP);     // preprocessor.cpp:320-328
     if (n_frames == 0) return 0;
@@ -939,7 +1033,8 @@ long long Engine::op_logmel(const int16_t* pcm, int n_streams, int n_samples, fl
 // ------------------------------------------------------------------------------------------
 void Engine::ensure_full_pos(int frames) {
     if (frames <= full_pos_cap_) return;
-    const int cap = std::max(frames, 256), n_rel = 2 * cap - 1;                  // row r <-> relative position r - (cap - 1) = query - key
+    const int cap = std::max(frames, 256), n_rel = 2 * cap - 1;
+    ensure_q8s_scratch(n_rel);                  // row r <-> relative position r - (cap - 1) = query - key
     GgufFile g; g.open(gguf_path_);
     std::vector<float> tab((size_t)n_rel * D_MODEL);
     for (int r = 0; r < n_rel; ++r) pos_emb_row(r - (cap - 1), &tab[(size_t)r * D_MODEL]);
@@ -969,7 +1064,7 @@ long long Engine::transcribe_full(const int16_t* pcm, int n_samples, int32_t* to
     if (M == 0) return 0;
     const int t1 = M / 2 + 1, t2 = t1 / 2 + 1, t3 = t2 / 2 + 1, Tq = t3;          // three 3x3 s2 convs with (2, 1) padding (nemo-ggml.cpp:828-836)
     if (Tq > 2048) throw std::invalid_argument("transcribe_full: more than 2048 encoder frames (the reference's positional table, nemo-ggml.cpp:196)");
-    if ((size_t)Tq > (size_t)max_streams * T || (size_t)t2 * 33 * SUB_CH * 4 > dw_.bytes)
+    if ((size_t)Tq > (size_t)max_streams * T || (size_t)t2 * 33 * SUB_CH * 4 > pw_.bytes)
         throw std::invalid_argument("transcribe_full: " + std::to_string(Tq) + " encoder frames do not fit this engine's workspace of max_streams x (att_right_context + 1) = " +
                                     std::to_string((long long)max_streams * T) + " rows");
     if (enc_out && enc_cap < (size_t)Tq * D_MODEL) return -(long long)((size_t)Tq * D_MODEL);
@@ -993,22 +1088,22 @@ long long Engine::transcribe_full(const int16_t* pcm, int n_samples, int32_t* to
     const int* slot_dev = d_slot_.as<int>();
     float* x = x_.as<float>();
     pending_ = PartialSum{};
-    launch_stem_conv0_dw_full(d_mel.as<float>(), 1, M, c0_w_.as<float>(), c0_b_.as<float>(), c2_w_.as<float>(), c2_b_.as<float>(), dw_.as<float>(), st_);
+    const bool tc = !strict();
+    const int split = tc && c3_w_.scales.p ? 1 : 0;
+    launch_stem_conv0_dw_full(d_mel.as<float>(), 1, M, c0_w_.as<float>(), c0_b_.as<float>(), c2_w_.as<float>(), c2_b_.as<float>(), dw_.as<float>(), st_, split);
     count_launch();
-    const bool tc = compute != NSB_COMPUTE_F32;
-    auto f32_gemm = [&](GemmArgs& g) { if (tc) launch_gemm_tc(g, OUT_F32, st_); else launch_gemm_simt(g, st_); count_launch(); };
     {
         GemmArgs g; g.A = dw_.p; g.lda = SUB_CH; g.W = c3_w_.data.p; g.M = t2 * 33; g.N = SUB_CH; g.K = SUB_CH; g.bias = c3_b_.as<float>();
-        g.C = pw_.p; g.ldc = SUB_CH; g.epi = EPI_RELU; f32_gemm(g);
+        g.C = pw_.p; g.ldc = SUB_CH; g.epi = EPI_RELU; gemm_f32w(g, c3_w_, split);
     }
-    launch_dwconv_s2(pw_.as<float>(), 1, t2, 33, c5_w_.as<float>(), c5_b_.as<float>(), dw_.as<float>(), st_); count_launch();
+    launch_dwconv_s2(pw_.as<float>(), 1, t2, 33, c5_w_.as<float>(), c5_b_.as<float>(), dw_.as<float>(), st_, split); count_launch();
     {
         GemmArgs g; g.A = dw_.p; g.lda = SUB_CH; g.W = c6_w_.data.p; g.M = t3 * SUB_W; g.N = SUB_CH; g.K = SUB_CH; g.bias = c6_b_.as<float>();
-        g.C = pw_.p; g.ldc = SUB_CH; g.epi = EPI_RELU; f32_gemm(g);
+        g.C = pw_.p; g.ldc = SUB_CH; g.epi = EPI_RELU; gemm_f32w(g, c6_w_, split);
     }
     {
         GemmArgs g; g.A = pw_.p; g.lda = SUB_W * SUB_CH; g.W = sub_out_w_.data.p; g.M = rows; g.N = D_MODEL; g.K = SUB_W * SUB_CH; g.bias = out_b_.as<float>();
-        g.C = x; g.ldc = D_MODEL; g.epi = EPI_NONE; f32_gemm(g);
+        g.C = x; g.ldc = D_MODEL; g.epi = EPI_NONE; gemm_f32w(g, sub_out_w_, false);
     }
 
     // L: the layers of build_conformer_layer (nemo-ggml.cpp:768-818) on the cached-layer kernels
@@ -1049,7 +1144,7 @@ long long Engine::transcribe_full(const int16_t* pcm, int n_samples, int32_t* to
     // G/Y: greedy_decode (nemo-ggml.cpp:1109-1258) from a fresh decoder state over all frames
     {
         GemmArgs g; g.A = x; g.lda = D_MODEL; g.W = joint_enc_w_.data.p; g.M = rows; g.N = JOINT; g.K = D_MODEL; g.bias = joint_enc_b_.as<float>();
-        g.C = encp_.p; g.ldc = JOINT; g.epi = EPI_NONE; f32_gemm(g);
+        g.C = encp_.p; g.ldc = JOINT; g.epi = EPI_NONE; gemm_f32w(g, joint_enc_w_, false);
     }
     DecodeArgs d{};
     d.w.embed = embed_.as<float>();
@@ -1076,8 +1171,10 @@ long long Engine::transcribe_full(const int16_t* pcm, int n_samples, int32_t* to
 long long Engine::op_gemm(const std::string& name, const float* xh, int rows, float* y, size_t cap) {
     auto it = named_.find(name);
     if (it == named_.end()) throw std::invalid_argument("op_gemm: unknown weight '" + name + "'");
+    NSB_CUDA(cudaSetDevice(device_));
     const Weight& W = *it->second;
     if (cap < (size_t)rows * W.n_out) return -(long long)((size_t)rows * W.n_out);
+    ensure_q8s_scratch(rows);
     DevBuf dx, da, dy; dx.alloc((size_t)rows * W.n_in * 4, false); dy.alloc((size_t)rows * W.n_out * 4, false);
     h2d_sync(dx.p, xh, dx.bytes);
     const void* A = dx.p;

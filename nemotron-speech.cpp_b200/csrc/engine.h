@@ -85,6 +85,7 @@ public:
     void trace_enable(int cap);
     int trace_fetch(TraceRec* out, int cap);
 
+    void set_cuda_graph(bool on) { collect_all(); cfg_.use_cuda_graph = on ? 1 : 0; }
     void debug_enable(bool on);
     long long debug_get(const std::string& name, float* out, size_t cap);
     long long debug_get_cache(int stream, int which, int layer, float* out, size_t cap);
@@ -109,6 +110,7 @@ private:
     // per-layer matrix straight from the file: Q8_0 tensors keep their quants in Q8_0 compute mode (fused-dequant GEMM)
     void load_layer_matrix(Weight& w, const GgufFile& g, const std::string& out_name, const std::vector<std::string>& parts, int n_out, int n_in);
     void alloc_state();
+    void release_handles();            // graphs, events, stream (destructor and failed constructor)
     void zero_slot(int slot);
     void build_pos_tables(const GgufFile& g);
     void ensure_full_pos(int frames);  // positional projections for relative positions -(cap-1) .. cap-1 of the batch path, built on first use
@@ -120,6 +122,7 @@ private:
     void gemm_residual(const void* A, long long lda, const Weight& W, int M, float* x, float alpha);
     bool split_consumers(int rows) const;
     void q8_predequant(const Weight& W, int M, GemmArgs& a);
+    void gemm_f32w(GemmArgs& g, const Weight& W, bool a_presplit);   // matrices kept in F32 by every GGUF: SIMT fp32 / 3xTF32
     void gemm_planes(const void* A, long long lda, const Weight& W, int M, void* C, int planes);
     PartialSum pending_{};
     void run_step_kernels(int B, const int16_t* d_pcm);      // everything between PCM-in-HBM and tokens-in-HBM
@@ -136,8 +139,13 @@ private:
     StepIO io_[2]; int io_next_ = 0, n_inflight_ = 0;
     void collect_tokens(StepIO& io);
     void collect_all();               // step_end() until nothing is in flight
-    int act_type() const { return compute == NSB_COMPUTE_F32 ? OUT_F32 : (compute == NSB_COMPUTE_BF16 ? OUT_BF16 : OUT_F16); }
-    size_t act_size() const { return compute == NSB_COMPUTE_F32 ? 4 : 2; }
+    // strict modes keep every activation in f32 and run no tcgen05 kernel: NSB_COMPUTE_F32 (f32 weights, SIMT) and
+    // NSB_COMPUTE_Q8_0_STRICT (the reference's Q8_0 x Q8_0 block arithmetic for the per-layer matrices, SIMT f32 for the rest)
+    bool strict() const { return compute == NSB_COMPUTE_F32 || compute == NSB_COMPUTE_Q8_0_STRICT; }
+    bool q8_planes_mode() const { return compute == NSB_COMPUTE_Q8_0 || compute == NSB_COMPUTE_Q8_0_STRICT; }
+    int act_type() const { return strict() ? OUT_F32 : (compute == NSB_COMPUTE_BF16 ? OUT_BF16 : OUT_F16); }
+    size_t act_size() const { return strict() ? 4 : 2; }
+    void ensure_q8s_scratch(int rows);       // activation-quantiser scratch of the strict Q8_0 GEMM (never called inside a graph capture)
     void count_launch(int n = 1) { stats.kernel_launches += n; }
 
     nsb_engine_config cfg_{};
@@ -150,7 +158,7 @@ private:
     std::map<std::string, Weight*> named_;   // for op_gemm
     DevBuf window_, cos_t_, sin_t_, fb_t_;
     DevBuf c0_w_, c0_b_, c2_w_, c2_b_, c3_b_, c5_w_, c5_b_, c6_b_, out_b_;
-    Weight c3_w_, c6_w_, sub_out_w_;         // always f32 (SIMT)
+    Weight c3_w_, c6_w_, sub_out_w_;         // always f32: .data plain (SIMT strict mode), .scales = 3xTF32 split copy [hi | lo | hi] (tensor-core modes)
     Weight joint_enc_w_; DevBuf joint_enc_b_;
     DevBuf embed_, lstm_w_[4], lstm_b_[4], pred_w_, pred_b_, jout_w_, jout_b_;
 
@@ -164,11 +172,12 @@ private:
 
     // ---- step workspace (batch-compact) ----
     int rl_ = 0;                   // PCM row length per stream-step
-    DevBuf d_pcm_, d_slot_, mel_new_, dw_, pw_, x_, a_, big_, qkv_, pw1_, encp_, part_;
+    DevBuf d_pcm_, d_slot_, mel_new_, dw_, pw_, a3_, x_, a_, big_, qkv_, pw1_, encp_, part_;
     DevBuf out_tok_, out_cnt_, dec_sync_;
     int consumer_planes_ = 1;         // planes the qkv_ / pw1_ buffers were sized for (split-K partials summed by the consumer kernels)
 
     // ---- bench ----
+    DevBuf q8s_scratch_;              // strict Q8_0: int8 rows + block scales of the A operand of one GEMM
     DevBuf wscratch_;                 // fp16 copy of ONE Q8_0 matrix (large batches), rewritten before every GEMM that uses it
     DevBuf bench_pcm_; int bench_B_ = 0, bench_n_ = 1; long long bench_i_ = 0;   // [bench_n_][bench_B_][rl_] staged chunks, cycled
     const int16_t* bench_next_pcm();
@@ -187,7 +196,7 @@ private:
     };
 
     // ---- debug taps ----
-    bool debug_ = false; int dbg_B_ = 0;
+    bool debug_ = false; int dbg_B_ = 0, last_B_ = 0;
     DevBuf dbg_mel_, dbg_sub_, dbg_layers_, dbg_logits_, dbg_logits_n_;
     DevBuf trace_; int trace_cap_ = 0;
 };

@@ -180,6 +180,8 @@ struct TcParams {
     int c_group, c_drop;       // output row map: row r -> (r / c_group) * (c_group - c_drop) + r % c_group - c_drop, rows with r % c_group < c_drop are dropped
     void* C0; int m_out;       // EPI_PARTIAL: slice 0 (+bias) goes to C0 when set, slices z >= 1 to C + (z-1) * m_out * ldc
     int w_dyn = 0;             // W is produced by the previous kernel (Q8_0 weights dequantised once per launch): no weight TMA before the dependency wait
+    int a_fold = 0;            // 3xTF32 (kind::tf32 only): W holds [hi | lo | hi] along K' = 3 a_fold, A holds [hi | lo] (2 a_fold columns):
+                               // the A column of k index kc is kc (kc < a_fold) or kc - a_fold
 };
 
 // Epilogue of one 128 x BN tile (4 warps; TMEM lane quarter = warp % 4): tcgen05.ld the fp32 accumulator, apply the fused
@@ -361,6 +363,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
     constexpr int A_SLICE_ROWS = BM / CL;
     auto load_a = [&](int st, int kc) {
+        if (EB == 4 && p.a_fold) kc = kc < p.a_fold ? kc : kc - p.a_fold;
         if (CL > 1) tma_load_2d_mc(s.a[st] + crank * A_SLICE_ROWS * ROW_BYTES, &tmA, &s.full[st], kc, m0 + (int)crank * A_SLICE_ROWS, MC_MASK);
         else tma_load_2d(s.a[st], &tmA, &s.full[st], kc, m0);
     };
@@ -849,10 +852,10 @@ void launch_cfg_c(const GemmArgs& a, int fmt, cudaStream_t st) {
     static std::atomic<size_t> attr_set[MAX_DEVICES];
     const size_t smem = sizeof(Smem<BN, STAGES>) + 1024;
     ensure_dyn_smem(gemm_tc_kernel<BN, STAGES, EB, CL>, smem, attr_set);
-    const CUtensorMap tmA = make_map(a.A, a.M, a.K, a.lda, BM / CL, fmt);
+    const CUtensorMap tmA = make_map(a.A, a.M, a.a_fold ? 2 * a.a_fold : a.K, a.lda, BM / CL, fmt);
     const CUtensorMap tmB = make_map(a.W, a.N, a.K, a.K, BN, fmt);
     const int m_out = a.c_group > 0 ? (a.M / a.c_group) * (a.c_group - a.c_drop) : a.M;
-    TcParams p{a.M, a.N, a.K, a.bias, a.C, a.ldc, a.epi, a.alpha, a.out_type, fmt, a.rotate, a.c_group, a.c_drop, a.C0, m_out, a.w_dynamic};
+    TcParams p{a.M, a.N, a.K, a.bias, a.C, a.ldc, a.epi, a.alpha, a.out_type, fmt, a.rotate, a.c_group, a.c_drop, a.C0, m_out, a.w_dynamic, a.a_fold};
     dim3 grid(a.N / BN, (a.M + BM - 1) / BM, a.splits);
     launch_k_cluster(gemm_tc_kernel<BN, STAGES, EB, CL>, grid, dim3(TC_THREADS), smem, st, CL, tmA, tmB, p);
 }
@@ -968,6 +971,7 @@ void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
     if (a.K % BK != 0 || a.N % 32 != 0 || (a.lda % (fmt == 2 ? 4 : 8)) != 0 || (a.ldc % 4) != 0)
         throw CudaError("gemm_tc: unsupported shape (need K % 64 == 0 (tf32: 32), N % 32 == 0, 16-byte aligned rows)");
     if (a.c_group > 0 && a.M % a.c_group != 0) throw CudaError("gemm_tc: M must be a multiple of the output row group");
+    if (a.a_fold && (fmt != 2 || a.K != 3 * a.a_fold || a.a_fold % BK != 0)) throw CudaError("gemm_tc: 3xTF32 needs fp32 operands and K = 3 x the folded width");
     const int tiles_m = (a.M + BM - 1) / BM;
     if (a.w_scales) {                                             // Q8_0 planes: fused-dequant kernel (A is fp16)
         if (fmt != 0) throw CudaError("gemm_q8: activations must be fp16");

@@ -21,17 +21,20 @@ void launch_conv0(const float* mel_hist, const float* mel_new, const int* slot_o
                   const float* bias, float* out, cudaStream_t st);
 // conv0 + ReLU fused into the first depthwise conv: mel chunk -> [B][t2][33][256] (the conv0 image never reaches HBM)
 void launch_stem_conv0_dw(const float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, const float* w0_t,
-                          const float* b0, const float* w2_t, const float* b2, float* out, cudaStream_t st);
+                          const float* b0, const float* w2_t, const float* b2, float* out, cudaStream_t st, int split = 0);
 // the same on a whole mel image [B][M][128] of any length M (non-streaming batch path): -> [B][t2][33][256], t2 = (M/2+1)/2+1
 void launch_stem_conv0_dw_full(const float* mel, int B, int M, const float* w0_t, const float* b0, const float* w2_t, const float* b2,
-                               float* out, cudaStream_t st);
+                               float* out, cudaStream_t st, int split = 0);
 // history = last 9 frames of [hist || new]
 void launch_mel_hist_update(float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, cudaStream_t st);
 // optional tap: full chunk image [B][M][128]
 void launch_mel_gather(const float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, float* out, cudaStream_t st);
-// depthwise 3x3 s2 (+bias), NHWC, C = 256
+// depthwise 3x3 s2 (+bias), NHWC, C = 256. split = 1 (also launch_stem_conv0_dw): every output pixel is written as 512 floats
+// [tf32 hi (256) | tf32 lo (256)] -- the A operand layout of the 3xTF32 tensor-core GEMM that follows (GemmArgs::a_fold)
 void launch_dwconv_s2(const float* in, int B, int H, int W, const float* w_t /*[9][256]*/, const float* bias, float* out,
-                      cudaStream_t st);
+                      cudaStream_t st, int split = 0);
+// rows x K fp32 -> rows x [hi (K) | lo (K)]: v = hi + lo (+ <= 2^-22 |v|), both exactly representable in tf32
+void launch_split_tf32(const float* in, float* out, size_t rows, int K, cudaStream_t st);
 
 // ---------------------------------------------------------------- SIMT fp32 GEMM (gemm_simt.cu)
 struct GemmArgs {
@@ -53,9 +56,13 @@ struct GemmArgs {
     int pair = 0;                 // allow the CTA-pair (cta_group::2) tile when the batch is a single 128-row tile
     int w_dynamic = 0;            // W was written by the previous kernel (per-launch Q8_0 dequantisation): no weight loads before the dependency wait
     int multicast = 1;            // allow A-tile multicast over clusters of 4 CTAs along N (experimental, only with NSB_MC=1: measured slower)
+    int a_fold = 0;               // 3xTF32 (fp32 operands on the tensor cores, launch_gemm_tc with OUT_F32 inputs): K = 3 a_fold, W = [hi | lo | hi], A = [hi | lo] (lda >= 2 a_fold)
     int rotate = 1;               // CTA n starts its k loop at k-block (n mod nk): de-synchronises the A-tile reads of the grid
 };
 void launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
+// Q8_0 x Q8_0 with the reference's arithmetic (gemm_q8_strict.cu): quantises the f32 rows of A into `scratch`, then integer block dots
+void launch_gemm_q8_strict(const GemmArgs& a, void* scratch, size_t scratch_bytes, cudaStream_t st);
+size_t q8_strict_scratch_bytes(int rows, int K);
 
 // ---------------------------------------------------------------- layer kernels (kernels_layer.cu)
 // Pending split-K reduction folded into a LayerNorm kernel: x += alpha * sum_s part[s] (fixed order => deterministic)

@@ -126,7 +126,7 @@ template <bool FULL>
 __global__ void __launch_bounds__(SUB_CH) stem_conv0_dw_kernel(const float* __restrict__ hist, const float* __restrict__ mel_new,
                                                                const int* __restrict__ slot_of_b, int T, const float* __restrict__ w0_t,
                                                                const float* __restrict__ b0, const float* __restrict__ w2_t,
-                                                               const float* __restrict__ b2, float* __restrict__ out) {
+                                                               const float* __restrict__ b2, float* __restrict__ out, int split) {
     // mel column iw lives at index iw + 4: the five columns 4 ow2 - 4 .. 4 ow2 one output column needs start 16-byte aligned
     // (one LDS.128 + one LDS.32 per row instead of 18 scalar broadcast loads: the kernel was bound by shared-memory issue)
     constexpr int MS = N_MELS + 8;
@@ -182,19 +182,19 @@ __global__ void __launch_bounds__(SUB_CH) stem_conv0_dw_kernel(const float* __re
         for (int kh2 = 0; kh2 < 3; ++kh2)
 #pragma unroll
             for (int kw2 = 0; kw2 < 3; ++kw2) acc = fmaf(win[kh2][kw2], w2[kh2 * 3 + kw2], acc);
-        out[(((size_t)b * t2 + oh2) * W2 + ow2) * SUB_CH + c] = acc + bias2;
+        store_pixel(out, ((size_t)b * t2 + oh2) * W2 + ow2, c, acc + bias2, split);
     }
     NSB_KERNEL_EPILOGUE();
 }
 void launch_stem_conv0_dw(const float* mel_hist, const float* mel_new, const int* slot_of_b, int B, int T, const float* w0_t,
-                          const float* b0, const float* w2_t, const float* b2, float* out, cudaStream_t st) {
+                          const float* b0, const float* w2_t, const float* b2, float* out, cudaStream_t st, int split) {
     const int M = PRE_CACHE + 8 * T, t1 = M / 2 + 1, t2 = t1 / 2 + 1;
-    launch_k(stem_conv0_dw_kernel<false>, dim3(t2, B), dim3(SUB_CH), 0, st, mel_hist, mel_new, slot_of_b, T, w0_t, b0, w2_t, b2, out);
+    launch_k(stem_conv0_dw_kernel<false>, dim3(t2, B), dim3(SUB_CH), 0, st, mel_hist, mel_new, slot_of_b, T, w0_t, b0, w2_t, b2, out, split);
 }
 void launch_stem_conv0_dw_full(const float* mel, int B, int M, const float* w0_t, const float* b0, const float* w2_t, const float* b2,
-                               float* out, cudaStream_t st) {
+                               float* out, cudaStream_t st, int split) {
     const int t1 = M / 2 + 1, t2 = t1 / 2 + 1;
-    launch_k(stem_conv0_dw_kernel<true>, dim3(t2, B), dim3(SUB_CH), 0, st, mel, (const float*)nullptr, (const int*)nullptr, M, w0_t, b0, w2_t, b2, out);
+    launch_k(stem_conv0_dw_kernel<true>, dim3(t2, B), dim3(SUB_CH), 0, st, mel, (const float*)nullptr, (const int*)nullptr, M, w0_t, b0, w2_t, b2, out, split);
 }
 
 __global__ void __launch_bounds__(N_MELS) mel_hist_update_kernel(float* __restrict__ hist, const float* __restrict__ mel_new,
@@ -227,7 +227,7 @@ void launch_mel_gather(const float* mel_hist, const float* mel_new, const int* s
 // register window slides along the row (6 new loads per output instead of 9, and 17x fewer CTAs than one per output pixel:
 // at 256 streams that was 39 168 one-pixel CTAs). Taps outside the image are skipped, in the (kh, kw) order of the reference loop.
 __global__ void __launch_bounds__(SUB_CH) dwconv_s2_kernel(const float* __restrict__ in, int H, int W, const float* __restrict__ w_t,
-                                                           const float* __restrict__ bias, float* __restrict__ out) {
+                                                           const float* __restrict__ bias, float* __restrict__ out, int split) {
     NSB_KERNEL_PROLOGUE(TR_DWCONV)
     const int oh = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
     const int Ho = gridDim.x, Wo = W / 2 + 1;
@@ -263,12 +263,32 @@ __global__ void __launch_bounds__(SUB_CH) dwconv_s2_kernel(const float* __restri
             if (v1) acc = fmaf(win[kh][1], w[kh * 3 + 1], acc);
             if (v2) acc = fmaf(win[kh][2], w[kh * 3 + 2], acc);
         }
-        out[(((size_t)b * Ho + oh) * Wo + ow) * SUB_CH + c] = acc + bs;
+        store_pixel(out, ((size_t)b * Ho + oh) * Wo + ow, c, acc + bs, split);
     }
     NSB_KERNEL_EPILOGUE();
 }
-void launch_dwconv_s2(const float* in, int B, int H, int W, const float* w_t, const float* bias, float* out, cudaStream_t st) {
-    launch_k(dwconv_s2_kernel, dim3(H / 2 + 1, B), dim3(SUB_CH), 0, st, in, H, W, w_t, bias, out);
+void launch_dwconv_s2(const float* in, int B, int H, int W, const float* w_t, const float* bias, float* out, cudaStream_t st, int split) {
+    launch_k(dwconv_s2_kernel, dim3(H / 2 + 1, B), dim3(SUB_CH), 0, st, in, H, W, w_t, bias, out, split);
+}
+
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restrict__ in, float* __restrict__ out, size_t n_vec, int K) {
+    NSB_KERNEL_PROLOGUE(TR_OTHER)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = in[i];
+        const size_t e = i * 4, row = e / (size_t)K, col = e % (size_t)K;
+        float4 hi, lo;
+        split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+        float* o = out + row * 2 * (size_t)K + col;
+        *reinterpret_cast<float4*>(o) = hi; *reinterpret_cast<float4*>(o + K) = lo;
+    }
+    NSB_KERNEL_EPILOGUE();
+}
+void launch_split_tf32(const float* in, float* out, size_t rows, int K, cudaStream_t st) {
+    if (K % 4 != 0) throw CudaError("split_tf32: K must be a multiple of 4");
+    const size_t n_vec = rows * (size_t)K / 4;
+    if (!n_vec) return;
+    const int blocks = (int)std::min<size_t>((n_vec + 255) / 256, 148 * 8);
+    launch_k(split_tf32_kernel, dim3(blocks), dim3(256), 0, st, (const float4*)in, out, n_vec, K);
 }
 
 }  // namespace nsb

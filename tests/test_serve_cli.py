@@ -67,8 +67,7 @@ def _parse(stdout):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("extra", [[], ["--realtime"], pytest.param(["--warmup"], marks=pytest.mark.xfail(
-    strict=False, reason="--warmup was added after the round's GPU budget was spent: not yet run on hardware"))])
+@pytest.mark.parametrize("extra", [[], ["--realtime"], ["--warmup"]])
 def test_ragged_streams_in_waves_match_the_oracle(exe, tmp_path, extra):
     """5 streams of different lengths (one shorter than a chunk, one empty) over 2 stream slots = 3 waves with slot reuse."""
     R = 1

@@ -277,58 +277,103 @@ def _wstr(f, s):
     f.write(b)
 
 
-def write_gguf(path: str, n_layers: int = 24, wtype: str = "f32", seed: int = 1234,
-               blank_bias: float | None = None, logit_gain: float = 1.0, R=None, mu=None, profile: str = "parity") -> None:
-    """R selects the committed calibration (mean encoder output + blank bias) of that latency mode."""
-    global _CAL_MU
-    cal_mu, cal_bb = load_calibration(seed, n_layers, R, profile)
-    _CAL_MU = mu if mu is not None else cal_mu
-    blank_bias = cal_bb if blank_bias is None else blank_bias
+VARIANT_TENSORS = ("joint.enc.bias", "joint.joint_net.2.bias")   # the only tensors that depend on (R, profile): calibration mean, blank bias
+
+
+def _gguf_header(n_layers: int, wtype: str, seed: int):
+    """(header bytes incl. alignment padding, [(name, dims, type, offset in the data section, nbytes)]) of a synthetic file."""
+    import io
     specs = list(tensor_specs(n_layers))
     hparams = [("nemo.n_mels", N_MELS), ("nemo.d_model", D_MODEL), ("nemo.n_heads", N_HEADS),
                ("nemo.d_head", D_HEAD), ("nemo.d_ff", D_FF), ("nemo.n_layers", n_layers),
                ("nemo.kernel_size", 31), ("nemo.vocab_size", VOCAB), ("nemo.decoder_dim", 320),
                ("nemo.joint_dim", JOINT)]  # kernel_size=31 / decoder_dim=320 are the converter's (ignored) values
-    # pass 1: sizes/offsets without keeping data
     infos, off = [], 0
     for name, shape, kind in specs:
         dims, ttype, nbytes = _prepared_size(name, shape, wtype)
         aligned = (off + ALIGN - 1) // ALIGN * ALIGN
         infos.append((name, dims, ttype, aligned, nbytes))
         off = aligned + nbytes
-    tmp = path + ".tmp"
-    with open(tmp, "wb") as f:
-        f.write(GGUF_MAGIC)
-        f.write(struct.pack("<I", GGUF_VERSION))
-        f.write(struct.pack("<q", len(infos)))
-        f.write(struct.pack("<q", len(hparams) + 3))
-        for k, v in (("general.architecture", "nemo"), ("general.name", "nemotron-speech-streaming-en-0.6b"),
-                     ("tokenizer.vocab", make_vocab(seed))):
-            _wstr(f, k)
-            f.write(struct.pack("<i", T_STR))
-            _wstr(f, v)
-        for k, v in hparams:
-            _wstr(f, k)
-            f.write(struct.pack("<i", T_U32))
-            f.write(struct.pack("<I", v))
-        for name, dims, ttype, aligned, _ in infos:
-            _wstr(f, name)
-            f.write(struct.pack("<I", len(dims)))
-            for d in dims:
-                f.write(struct.pack("<q", d))
-            f.write(struct.pack("<i", ttype))
-            f.write(struct.pack("<Q", aligned))
-        pos = f.tell()
-        f.write(b"\x00" * ((pos + ALIGN - 1) // ALIGN * ALIGN - pos))
+    f = io.BytesIO()
+    f.write(GGUF_MAGIC)
+    f.write(struct.pack("<I", GGUF_VERSION))
+    f.write(struct.pack("<q", len(infos)))
+    f.write(struct.pack("<q", len(hparams) + 3))
+    for k, v in (("general.architecture", "nemo"), ("general.name", "nemotron-speech-streaming-en-0.6b"),
+                 ("tokenizer.vocab", make_vocab(seed))):
+        _wstr(f, k)
+        f.write(struct.pack("<i", T_STR))
+        _wstr(f, v)
+    for k, v in hparams:
+        _wstr(f, k)
+        f.write(struct.pack("<i", T_U32))
+        f.write(struct.pack("<I", v))
+    for name, dims, ttype, aligned, _ in infos:
+        _wstr(f, name)
+        f.write(struct.pack("<I", len(dims)))
+        for d in dims:
+            f.write(struct.pack("<q", d))
+        f.write(struct.pack("<i", ttype))
+        f.write(struct.pack("<Q", aligned))
+    pos = f.tell()
+    f.write(b"\x00" * ((pos + ALIGN - 1) // ALIGN * ALIGN - pos))
+    return f.getvalue(), infos
+
+
+def write_gguf(path: str, n_layers: int = 24, wtype: str = "f32", seed: int = 1234,
+               blank_bias: float | None = None, logit_gain: float = 1.0, R=None, mu=None, profile: str = "parity") -> None:
+    """R selects the committed calibration (mean encoder output + blank bias) of that latency mode. Tensors are generated on a
+    thread pool (per-tensor seeds: order-independent) and written in file order."""
+    global _CAL_MU
+    from concurrent.futures import ThreadPoolExecutor
+    cal_mu, cal_bb = load_calibration(seed, n_layers, R, profile)
+    _CAL_MU = mu if mu is not None else cal_mu
+    blank_bias = cal_bb if blank_bias is None else blank_bias
+    specs = list(tensor_specs(n_layers))
+    header, infos = _gguf_header(n_layers, wtype, seed)
+
+    def make(i):
+        name, shape, kind = specs[i]
+        _, ttype2, raw = gguf_prepare(name, gen_tensor(name, shape, kind, seed, blank_bias, logit_gain), wtype)
+        assert ttype2 == infos[i][2] and len(raw) == infos[i][4], name
+        return raw
+
+    workers = max(1, min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
+    tmp = path + f".tmp{os.getpid()}"
+    with open(tmp, "wb") as f, ThreadPoolExecutor(workers) as ex:
+        f.write(header)
         data_start = f.tell()
-        for (name, shape, kind), (_, dims, ttype, aligned, nbytes) in zip(specs, infos):
-            t = gen_tensor(name, shape, kind, seed, blank_bias, logit_gain)
-            _, ttype2, raw = gguf_prepare(name, t, wtype)
-            assert ttype2 == ttype and len(raw) == nbytes, name
+        pending, nxt, depth = {}, 0, 4 * workers                     # bounded look-ahead: at most `depth` tensors in memory
+        for i in range(len(specs)):
+            while nxt < len(specs) and nxt < i + depth:
+                pending[nxt] = ex.submit(make, nxt); nxt += 1
+            raw = pending.pop(i).result()
             cur = f.tell()
-            f.write(b"\x00" * (data_start + aligned - cur))
+            f.write(b"\x00" * (data_start + infos[i][3] - cur))
             f.write(raw)
     os.replace(tmp, path)
+
+
+def derive_gguf_variant(src: str, dst: str, n_layers: int, wtype: str, seed: int, R, profile: str) -> None:
+    """Same (seed, layers, type), another latency mode / token-rate profile: only VARIANT_TENSORS differ (both stored F32), so copy the
+    file and rewrite those two in place instead of regenerating 0.6 G parameters."""
+    global _CAL_MU
+    import shutil
+    _CAL_MU, blank_bias = load_calibration(seed, n_layers, R, profile)
+    header, infos = _gguf_header(n_layers, wtype, seed)
+    specs = {name: (shape, kind) for name, shape, kind in tensor_specs(n_layers)}
+    tmp = dst + f".tmp{os.getpid()}"
+    shutil.copyfile(src, tmp)
+    with open(tmp, "r+b") as f:
+        assert f.read(len(header)) == header, "derive_gguf_variant: source layout differs"
+        for name, dims, ttype, aligned, nbytes in infos:
+            if name in VARIANT_TENSORS:
+                shape, kind = specs[name]
+                _, t2, raw = gguf_prepare(name, gen_tensor(name, shape, kind, seed, blank_bias, 1.0), wtype)
+                assert t2 == ttype == GGML_F32 and len(raw) == nbytes, name
+                f.seek(len(header) + aligned)
+                f.write(raw)
+    os.replace(tmp, dst)
 
 
 def _prepared_size(name, shape, wtype):
@@ -424,7 +469,12 @@ def cached_model(kind: str, n_layers: int, seed: int = 1234, cache_dir: str | No
                 raise ValueError("NEMO bins are written with the parity calibration only")
             write_nemo_bin(path, n_layers, seed, R=R)
         else:
-            write_gguf(path, n_layers, kind, seed, R=R, profile=profile)
+            import glob
+            sibs = sorted(glob.glob(os.path.join(cache_dir, f"synth_s{seed}_L{n_layers}_R*_{kind}.gguf")))
+            if sibs:
+                derive_gguf_variant(sibs[0], path, n_layers, kind, seed, R, profile)
+            else:
+                write_gguf(path, n_layers, kind, seed, R=R, profile=profile)
     return path
 
 
