@@ -66,7 +66,7 @@ struct nemo_context {             // src/nemo-ggml.h:217-227
     // engines keyed by att_right_context (created on the first nemo_stream_init with that value)
     std::map<int, struct nsb_engine*> engines;
     int max_streams = 8;          // stream slots per engine; override with NSB_MAX_STREAMS
-    struct nsb_engine* batch_engine = nullptr; int batch_rows = 0;   // nemo_transcribe_audio: engine sized for the longest utterance so far
+    struct nsb_engine* batch_engine = nullptr; int batch_rows = 0;   // nemo_transcribe_audio: created on first use (its batch workspace grows with the utterance)
 };
 
 struct nemo_context* nemo_init(const char* model_path);                                       // :231
@@ -95,8 +95,10 @@ struct nemo_decoder_state {       // src/nemo-ggml.h:358-398
     const float* c_layer(int l) const { return c.data() + (size_t)l * hidden_size; }
 };
 
-// src/nemo-ggml.h:336-339, src/nemo-ggml.cpp:1585-1600: the non-streaming batch path for one utterance (what src/transcribe.cpp
-// calls). EXPERIMENTAL in this round (nsb_transcribe_full, include/nsb200.h): "" on failure, like the reference.
+// src/nemo-ggml.h:330-339, src/nemo-ggml.cpp:1554-1600: the non-streaming batch path for one utterance (what src/transcribe.cpp
+// calls), on nsb_transcribe_full (include/nsb200.h). nemo_encode_audio returns the tokens with their encoder frame
+// (timed_token::frame_idx, for tokens_to_text(..., timestamp_words = true)); empty / "" on failure, like the reference.
+std::vector<timed_token> nemo_encode_audio(struct nemo_context* ctx, std::vector<int16_t>& audio_data);
 std::string nemo_transcribe_audio(struct nemo_context* ctx, std::vector<int16_t>& audio_data);
 
 // src/nemo-ggml.cpp:1432-1458

@@ -181,14 +181,15 @@ int nsb_op_gemm(nsb_engine* e, const char* weight_name, const float* x, int rows
 
 /* ---- non-streaming batch path: replaces nemo_encode_audio / nemo_transcribe_audio (src/nemo-ggml.cpp:1467-1600) for ONE
  * utterance: whole-utterance log-mel -> subsampling with no carried / dropped frames -> non-cached conformer layers with
- * full-context rel-pos attention -> greedy decode from a fresh decoder state. EXPERIMENTAL in this round: compiled and wired, its
- * parity test (against the CPU checker and the fixture generated by the reference's compiled modules) has not run on hardware yet.
- * Borrows one free stream slot and the engine's step workspace: the utterance's encoder frames (about 12.5 per second) must not
- * exceed max_streams * (att_right_context + 1), and 2048 (the reference's positional table). Returns the number of tokens decoded
- * (min(n, cap) are copied), <0 on error; *n_frames = encoder frames; enc_out (optional) receives [n_frames][1024] floats
- * (returns -needed when enc_cap_floats is too small). */
-int nsb_transcribe_full(nsb_engine* e, const int16_t* pcm, int n_samples, int32_t* tokens, int cap, int* n_frames, float* enc_out,
-                        size_t enc_cap_floats);
+ * full-context rel-pos attention -> greedy decode from a fresh decoder state. Validated on hardware against the CPU checker and the
+ * fixture generated by the reference's compiled modules (tests/test_zz_batch_path.py). Borrows one free stream slot (decoder / conv
+ * state); its activations live in a workspace of their own that grows to the longest utterance seen, so any engine -- whatever
+ * max_streams -- takes up to 2048 encoder frames (the reference's positional table, nemo-ggml.cpp:196; about 164 s of audio).
+ * Returns the number of tokens decoded (min(n, cap) are copied), <0 on error; token_frames (optional, cap entries) = encoder frame of
+ * each token = timed_token::frame_idx (nemo-ggml.cpp:1240; seconds = frame * 1280 / 16000); *n_frames = encoder frames; enc_out
+ * (optional) receives [n_frames][1024] floats (returns -needed when enc_cap_floats is too small). */
+int nsb_transcribe_full(nsb_engine* e, const int16_t* pcm, int n_samples, int32_t* tokens, int32_t* token_frames, int cap, int* n_frames,
+                        float* enc_out, size_t enc_cap_floats);
 
 #ifdef __cplusplus
 }

@@ -108,7 +108,7 @@ def lib():
         L.nsb_debug_get_cache.argtypes = [vp, ci, ci, ci, _f32p, C.c_size_t]
         L.nsb_op_logmel.argtypes = [vp, _i16p, ci, ci, _f32p, C.c_size_t]
         L.nsb_op_gemm.argtypes = [vp, C.c_char_p, _f32p, ci, _f32p, C.c_size_t]
-        L.nsb_transcribe_full.argtypes = [vp, _i16p, ci, _i32p, ci, C.POINTER(C.c_int), C.c_void_p, C.c_size_t]
+        L.nsb_transcribe_full.argtypes = [vp, _i16p, ci, _i32p, _i32p, ci, C.POINTER(C.c_int), C.c_void_p, C.c_size_t]
         _lib = L
     return _lib
 
@@ -315,14 +315,16 @@ class Engine:
         n_out = _check(lib().nsb_op_gemm(self.h, weight_name.encode(), x, x.shape[0], y.reshape(-1), y.size))
         return y.reshape(-1)[: x.shape[0] * n_out].reshape(x.shape[0], n_out).copy()
 
-    def transcribe_full(self, pcm: np.ndarray, want_enc: bool = True):
-        """Non-streaming batch path (nsb_transcribe_full; EXPERIMENTAL, see include/nsb200.h): one whole utterance ->
-        (token ids, encoder output [frames, 1024] or None)."""
+    def transcribe_full(self, pcm: np.ndarray, want_enc: bool = True, want_frames: bool = False):
+        """Non-streaming batch path (nsb_transcribe_full, include/nsb200.h): one whole utterance ->
+        (token ids, encoder output [frames, 1024] or None[, encoder frame of each token])."""
         pcm = np.ascontiguousarray(pcm, dtype=np.int16)
         frames_cap = len(pcm) // 1280 + 8
         toks = np.empty(10 * frames_cap, dtype=np.int32)
+        frm = np.empty(10 * frames_cap, dtype=np.int32)
         enc = np.empty((frames_cap, 1024), dtype=np.float32) if want_enc else None
         nf = C.c_int(0)
-        n = _check(lib().nsb_transcribe_full(self.h, pcm, len(pcm), toks, len(toks), C.byref(nf),
+        n = _check(lib().nsb_transcribe_full(self.h, pcm, len(pcm), toks, frm, len(toks), C.byref(nf),
                                              enc.ctypes.data_as(C.c_void_p) if want_enc else None, enc.size if want_enc else 0))
-        return toks[:n].copy(), (enc[:nf.value].copy() if want_enc else None)
+        out = (toks[:n].copy(), (enc[:nf.value].copy() if want_enc else None))
+        return out + (frm[:n].copy(),) if want_frames else out

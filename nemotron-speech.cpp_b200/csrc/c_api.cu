@@ -166,7 +166,7 @@ int nsb_op_logmel(nsb_engine* e, const int16_t* pcm, int ns, int n, float* out, 
 int nsb_op_gemm(nsb_engine* e, const char* name, const float* x, int rows, float* y, size_t cap) {
     if (!e || !name || !x || !y) return fail(NSB_ERR_ARG, "bad argument"); NSB_TRY return (int)e->impl->op_gemm(name, x, rows, y, cap); NSB_CATCH }
 
-int nsb_transcribe_full(nsb_engine* e, const int16_t* pcm, int n, int32_t* tokens, int cap, int* n_frames, float* enc_out, size_t enc_cap) {
-    if (!e || !pcm) return fail(NSB_ERR_ARG, "bad argument"); NSB_TRY return (int)e->impl->transcribe_full(pcm, n, tokens, cap, n_frames, enc_out, enc_cap); NSB_CATCH }
+int nsb_transcribe_full(nsb_engine* e, const int16_t* pcm, int n, int32_t* tokens, int32_t* token_frames, int cap, int* n_frames, float* enc_out, size_t enc_cap) {
+    if (!e || !pcm) return fail(NSB_ERR_ARG, "bad argument"); NSB_TRY return (int)e->impl->transcribe_full(pcm, n, tokens, token_frames, cap, n_frames, enc_out, enc_cap); NSB_CATCH }
 
 }  // extern "C"

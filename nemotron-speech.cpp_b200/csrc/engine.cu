@@ -1054,7 +1054,27 @@ void Engine::ensure_full_pos(int frames) {
     full_pos_cap_ = cap;
 }
 
-long long Engine::transcribe_full(const int16_t* pcm, int n_samples, int32_t* tokens, int cap, int* n_frames, float* enc_out, size_t enc_cap) {
+void Engine::ensure_batch_work(int rows, int t2) {
+    const size_t sp = (!strict() && tf32x3_enabled()) ? 2 : 1;
+    const size_t pix = (size_t)t2 * 33 * SUB_CH * 4;
+    if (rows <= bw_.rows && bw_.pw.bytes >= pix) return;
+    NSB_CUDA(cudaStreamSynchronize(st_));
+    const size_t r = (size_t)std::max(rows, 64);
+    bw_.dw.alloc(sp * pix, false); bw_.pw.alloc(pix, false);
+    if (sp == 2) bw_.a3.alloc(r * SUB_W * SUB_CH * 2 * 4, false);
+    bw_.x.alloc(r * D_MODEL * 4, false); bw_.a.alloc(r * D_MODEL * act_size(), false); bw_.big.alloc(r * D_FF * act_size(), false);
+    bw_.qkv.alloc(r * 3 * D_MODEL * 4, false); bw_.pw1.alloc(r * 2 * D_MODEL * 4, false); bw_.encp.alloc(r * JOINT * 4, false);
+    bw_.part.alloc(std::max((size_t)MAX_SPLITS * std::min<size_t>(r, 1024), 4 * r) * D_MODEL * 4, false);
+    bw_.out_tok.alloc(r * MAX_SYMBOLS * 4, false); bw_.out_frm.alloc(r * MAX_SYMBOLS * 4, false);
+    bw_.rows = (int)r;
+    ensure_q8s_scratch((int)r);
+}
+void Engine::swap_batch_work() {
+    std::swap(dw_, bw_.dw); std::swap(pw_, bw_.pw); std::swap(a3_, bw_.a3); std::swap(x_, bw_.x); std::swap(a_, bw_.a); std::swap(big_, bw_.big);
+    std::swap(qkv_, bw_.qkv); std::swap(pw1_, bw_.pw1); std::swap(encp_, bw_.encp); std::swap(part_, bw_.part); std::swap(out_tok_, bw_.out_tok);
+}
+
+long long Engine::transcribe_full(const int16_t* pcm, int n_samples, int32_t* tokens, int32_t* token_frames, int cap, int* n_frames, float* enc_out, size_t enc_cap) {
     if (!pcm || n_samples < 1 || (!tokens && cap > 0) || cap < 0) throw std::invalid_argument("transcribe_full: bad arguments");
     collect_all();
     NSB_CUDA(cudaSetDevice(device_));
@@ -1064,13 +1084,12 @@ long long Engine::transcribe_full(const int16_t* pcm, int n_samples, int32_t* to
     if (M == 0) return 0;
     const int t1 = M / 2 + 1, t2 = t1 / 2 + 1, t3 = t2 / 2 + 1, Tq = t3;          // three 3x3 s2 convs with (2, 1) padding (nemo-ggml.cpp:828-836)
     if (Tq > 2048) throw std::invalid_argument("transcribe_full: more than 2048 encoder frames (the reference's positional table, nemo-ggml.cpp:196)");
-    if ((size_t)Tq > (size_t)max_streams * T || (size_t)t2 * 33 * SUB_CH * 4 > pw_.bytes)
-        throw std::invalid_argument("transcribe_full: " + std::to_string(Tq) + " encoder frames do not fit this engine's workspace of max_streams x (att_right_context + 1) = " +
-                                    std::to_string((long long)max_streams * T) + " rows");
     if (enc_out && enc_cap < (size_t)Tq * D_MODEL) return -(long long)((size_t)Tq * D_MODEL);
     ensure_full_pos(Tq);
+    ensure_batch_work(Tq, t2);
     const int slot = open_stream();                                               // zeroed conv state, decoder state, prev_token = blank
-    struct Release { Engine* e; int s; ~Release() { e->hs_[s].open = false; } } release{this, slot};
+    swap_batch_work();                                                            // the step workspace (and the graphs captured on it) stays untouched
+    struct Release { Engine* e; int s; ~Release() { e->swap_batch_work(); e->hs_[s].open = false; } } release{this, slot};
 
     // P: log-mel of the whole utterance (row = x[-1] = 0, the 256-zero left pad, the samples: preprocessor.cpp:220-221,349-356)
     const int row = 1 + N_FFT / 2 + n_samples;
@@ -1154,7 +1173,7 @@ long long Engine::transcribe_full(const int16_t* pcm, int n_samples, int32_t* to
     d.s.hbuf = dec_h_.as<float>(); d.s.cbuf = dec_c_.as<float>(); d.s.par = dec_par_.as<int>();
     d.s.dec_proj = dec_proj_.as<float>(); d.s.prev_token = prev_token_.as<int>(); d.s.cand_valid = cand_valid_.as<int>();
     d.enc_proj = encp_.as<float>(); d.slot_of_b = slot_dev; d.B = 1; d.T = rows;
-    d.out_tokens = out_tok_.as<int>(); d.out_count = out_cnt_.as<int>();
+    d.out_tokens = out_tok_.as<int>(); d.out_count = out_cnt_.as<int>(); d.out_frames = bw_.out_frm.as<int>();
     launch_decode(d, dec_sync_.p, st_); count_launch();
     NSB_CUDA(cudaStreamSynchronize(st_));
 
@@ -1162,6 +1181,7 @@ long long Engine::transcribe_full(const int16_t* pcm, int n_samples, int32_t* to
     NSB_CUDA(cudaMemcpy(&n_tok, out_cnt_.p, 4, cudaMemcpyDeviceToHost));
     n_tok = std::max(0, std::min(n_tok, MAX_SYMBOLS * rows));
     if (std::min(n_tok, cap) > 0) NSB_CUDA(cudaMemcpy(tokens, out_tok_.p, (size_t)std::min(n_tok, cap) * 4, cudaMemcpyDeviceToHost));
+    if (token_frames && std::min(n_tok, cap) > 0) NSB_CUDA(cudaMemcpy(token_frames, bw_.out_frm.p, (size_t)std::min(n_tok, cap) * 4, cudaMemcpyDeviceToHost));
     if (enc_out) NSB_CUDA(cudaMemcpy(enc_out, x, (size_t)rows * D_MODEL * 4, cudaMemcpyDeviceToHost));
     if (n_frames) *n_frames = rows;
     stats.chunks += 1;

@@ -93,9 +93,10 @@ public:
     long long op_gemm(const std::string& name, const float* x, int rows, float* y, size_t cap);
     // Non-streaming batch path (nemo_encode, reference src/nemo-ggml.cpp:1467-1535) for one utterance: whole-utterance log-mel ->
     // un-chunked subsampling -> non-cached layers with full-context rel-pos attention -> greedy decode from a fresh decoder state.
-    // Borrows one free stream slot and the step workspace: the utterance must fit (frames <= max_streams * (att_right_context + 1)).
+    // Borrows one free stream slot (decoder / conv state); the activations live in a workspace of their own, grown to the longest
+    // utterance seen (any engine, whatever max_streams, takes up to 2048 encoder frames).
     // Returns the number of tokens (copies min(n, cap)); *n_frames = encoder frames; enc_out (optional) [frames][1024].
-    long long transcribe_full(const int16_t* pcm, int n_samples, int32_t* tokens, int cap, int* n_frames, float* enc_out, size_t enc_cap);
+    long long transcribe_full(const int16_t* pcm, int n_samples, int32_t* tokens, int32_t* token_frames, int cap, int* n_frames, float* enc_out, size_t enc_cap);
 
     // facts
     int n_layers = 0, T = 1, R = 0, compute = NSB_COMPUTE_F32, kv_dtype = NSB_KV_F32, max_streams = 0;
@@ -174,6 +175,10 @@ private:
     int rl_ = 0;                   // PCM row length per stream-step
     DevBuf d_pcm_, d_slot_, mel_new_, dw_, pw_, a3_, x_, a_, big_, qkv_, pw1_, encp_, part_;
     DevBuf out_tok_, out_cnt_, dec_sync_;
+    // workspace of the non-streaming batch path (swapped in for the duration of transcribe_full)
+    struct BatchWork { DevBuf dw, pw, a3, x, a, big, qkv, pw1, encp, part, out_tok, out_frm; int rows = 0; } bw_;
+    void ensure_batch_work(int rows, int t2);
+    void swap_batch_work();
     int consumer_planes_ = 1;         // planes the qkv_ / pw1_ buffers were sized for (split-K partials summed by the consumer kernels)
 
     // ---- bench ----

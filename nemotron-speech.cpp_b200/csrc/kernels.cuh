@@ -128,6 +128,7 @@ struct DecodeArgs {
     const float* enc_proj;                    // [B*T][640] (joint.enc applied, bias included)
     const int* slot_of_b; int B, T;
     int* out_tokens; int* out_count;          // [B][MAX_SYMBOLS*T], [B]
+    int* out_frames;                          // optional [B][MAX_SYMBOLS*T]: encoder frame (within this call's T) each token was emitted at (timed_token::frame_idx)
     unsigned* barrier; unsigned long long* best;   // filled by launch_decode from its sync buffer
     float* logits_tap; int logits_tap_cap; int* logits_tap_n;   // optional: logits of batch row 0 per evaluation
 };

@@ -301,7 +301,10 @@ __global__ void __launch_bounds__(NT, 1) rnnt_decode_kernel(const DecodeArgs a) 
             const int tok = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
             if (tok == BLANK) { sm.fi[b] += 1; sm.sc[b] = 0; }                    // blank: next frame, state untouched
             else {
-                if (blockIdx.x == 0) a.out_tokens[(size_t)b * MAX_SYMBOLS * T + sm.oc[b]] = tok;
+                if (blockIdx.x == 0) {
+                    a.out_tokens[(size_t)b * MAX_SYMBOLS * T + sm.oc[b]] = tok;
+                    if (a.out_frames) a.out_frames[(size_t)b * MAX_SYMBOLS * T + sm.oc[b]] = sm.fi[b];   // nemo-ggml.cpp:1240 tokens.push_back({best_token, t})
+                }
                 sm.oc[b] += 1; sm.prev[b] = tok; sm.par[b] ^= 1; sm.need[b] = 1;  // emit: commit the candidate (parity flip)
                 if (sm.sc[b] + 1 >= MAX_SYMBOLS) { sm.fi[b] += 1; sm.sc[b] = 0; } else sm.sc[b] += 1;   // :813
             }

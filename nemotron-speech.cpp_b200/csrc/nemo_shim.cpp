@@ -111,34 +111,37 @@ std::string tokens_to_text(const std::vector<timed_token>& tokens, const std::ve
     return r;
 }
 
-// nemo_transcribe_audio (src/nemo-ggml.cpp:1585-1600): mel of the whole utterance -> nemo_encode -> tokens_to_text. Here one call
-// into the engine's batch path (EXPERIMENTAL, nsb200.h). The engine lends its step workspace, so it is created (or re-created)
-// with enough rows for the utterance: streams x 14 rows at att_right_context = 13.
-std::string nemo_transcribe_audio(struct nemo_context* ctx, std::vector<int16_t>& audio) {
-    if (!ctx || audio.empty()) return "";
+// nemo_encode_audio / nemo_transcribe_audio (src/nemo-ggml.cpp:1554-1600): mel of the whole utterance -> nemo_encode -> timed tokens
+// (-> tokens_to_text). Here one call into the engine's batch path, whose workspace grows with the utterance: one engine serves every
+// length up to the reference's own limit of 2048 encoder frames.
+std::vector<timed_token> nemo_encode_audio(struct nemo_context* ctx, std::vector<int16_t>& audio) {
+    std::vector<timed_token> toks;
+    if (!ctx || audio.empty()) return toks;
     const long long avail = 256 + (long long)audio.size();
     const long long mel = avail < 512 ? 0 : (avail - 512 + 160) / 160;            // preprocessor.cpp:320-328
-    if (mel <= 0) return "";
+    if (mel <= 0) return toks;
     const int frames = (int)(((mel / 2 + 1) / 2 + 1) / 2 + 1);                     // three stride-2 convs, (2, 1) padding (nemo-ggml.cpp:828-836)
-    if (!ctx->batch_engine || ctx->batch_rows < frames) {
-        if (ctx->batch_engine) { nsb_engine_destroy(ctx->batch_engine); ctx->batch_engine = nullptr; ctx->batch_rows = 0; }
+    if (!ctx->batch_engine) {
         nsb_engine_config ec; nsb_default_config(&ec);
-        ec.att_right_context = 13; ec.max_streams = std::max(2, (frames + 13) / 14 + 1);
+        ec.att_right_context = 13; ec.max_streams = 1;
         if (const char* e = getenv("NSB_COMPUTE")) ec.compute = atoi(e);
         if (const char* e = getenv("NSB_KV_DTYPE")) ec.kv_dtype = atoi(e);
         if (const char* e = getenv("NSB_DEVICE")) ec.device = atoi(e);
         if (nsb_engine_create(ctx->model.path.c_str(), &ec, &ctx->batch_engine) != NSB_OK) {
             fprintf(stderr, "[ERROR] Failed to create engine: %s\n", nsb_last_error());
-            ctx->batch_engine = nullptr; return "";
+            ctx->batch_engine = nullptr; return toks;
         }
-        ctx->batch_rows = ec.max_streams * 14;
     }
-    std::vector<int32_t> ids((size_t)frames * 10 + 1);                              // <= 10 symbols per frame (nemo-ggml.cpp:1132)
+    std::vector<int32_t> ids((size_t)frames * 10 + 1), frm((size_t)frames * 10 + 1);   // <= 10 symbols per frame (nemo-ggml.cpp:1132)
     int nf = 0;
-    const int n = nsb_transcribe_full(ctx->batch_engine, audio.data(), (int)audio.size(), ids.data(), (int)ids.size(), &nf, nullptr, 0);
-    if (n < 0) { fprintf(stderr, "[ERROR] nemo_transcribe_audio: %s\n", nsb_last_error()); return ""; }
-    std::vector<timed_token> toks;
-    for (int i = 0; i < n && i < (int)ids.size(); ++i) toks.push_back({ids[i], 0});
+    const int n = nsb_transcribe_full(ctx->batch_engine, audio.data(), (int)audio.size(), ids.data(), frm.data(), (int)ids.size(), &nf, nullptr, 0);
+    if (n < 0) { fprintf(stderr, "[ERROR] nemo_encode_audio: %s\n", nsb_last_error()); return toks; }
+    for (int i = 0; i < n && i < (int)ids.size(); ++i) toks.push_back({ids[i], frm[i]});   // frame index -> timed_token::to_seconds (nemo-ggml.cpp:1240)
+    return toks;
+}
+std::string nemo_transcribe_audio(struct nemo_context* ctx, std::vector<int16_t>& audio) {
+    if (!ctx) return "";
+    const std::vector<timed_token> toks = nemo_encode_audio(ctx, audio);
     return toks.empty() ? std::string() : tokens_to_text(toks, ctx->model.vocab, false);
 }
 

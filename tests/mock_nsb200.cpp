@@ -91,5 +91,5 @@ void nsb_engine_get_stats(const nsb_engine* e, nsb_stats* out) { *out = e->st; }
 int nsb_stream_ready(const nsb_engine* e, int s) { return s >= 0 && s < e->max_streams && nsb::hs_ready(e->hs[s], e->T) ? 1 : 0; }
 // referenced by the drop-in shim (csrc/nemo_shim.cpp) but not part of what the double models
 int nsb_op_logmel(nsb_engine*, const int16_t*, int, int, float*, size_t) { return fail(NSB_ERR_STATE, "mock: no log-mel"); }
-int nsb_transcribe_full(nsb_engine*, const int16_t*, int, int32_t*, int, int*, float*, size_t) { return fail(NSB_ERR_STATE, "mock: no batch path"); }
+int nsb_transcribe_full(nsb_engine*, const int16_t*, int, int32_t*, int32_t*, int, int*, float*, size_t) { return fail(NSB_ERR_STATE, "mock: no batch path"); }
 }

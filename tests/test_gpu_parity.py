@@ -57,15 +57,22 @@ def run_engine_vs_oracle(eng, om, R, audio, read=None, taps=True):
     return toks, orc, worst, ids
 
 
-def assert_tokens_match_up_to_near_ties(toks, orc, band):
+def assert_tokens_match_up_to_near_ties(toks, orc, band, details=None):
     """Identical token sequences, except that a stream may diverge at a decision whose top-2 gap in the ORACLE is
     below `band` (numerical noise of 16-bit activations); nothing can be said after such a point (the LSTM state
-    differs from there on). Returns the number of fully identical streams."""
+    differs from there on). Returns the number of fully identical streams. `details` (a dict) receives what the comparison saw:
+    decisions compared (joint evaluations of the oracle up to each stream's first divergence), the divergences with the smallest
+    top-2 gap in their window, and how common gaps below `band` are among ALL oracle decisions (how much the rule lets through)."""
     identical = 0
+    n_dec, n_small, n_all, flips = 0, 0, 0, []
     for s, (tg, o) in enumerate(zip(toks, orc)):
         to = o.tokens()
+        if details is not None:
+            for e in range(o.n_evals()):
+                lg = np.sort(o.trace_logits(e)); n_all += 1; n_small += int(lg[-1] - lg[-2] < band)
         if len(tg) == len(to) and np.array_equal(tg, to):
             identical += 1
+            n_dec += o.n_evals()
             continue
         # walk the oracle's evaluations to the first decision that differs
         k = next((i for i in range(min(len(tg), len(to))) if tg[i] != to[i]), min(len(tg), len(to)))
@@ -92,7 +99,12 @@ def assert_tokens_match_up_to_near_ties(toks, orc, band):
         gaps = []
         for e in range(lo, min(ev + 1, o.n_evals())):
             lg = np.sort(o.trace_logits(e)); gaps.append(float(lg[-1] - lg[-2]))
+        n_dec += min(ev + 1, o.n_evals())
+        flips.append({"stream": s, "token_index": k, "min_gap": min(gaps) if gaps else None})
         assert gaps and min(gaps) < band, f"stream {s}: tokens diverge at {k} with oracle top-2 gaps {gaps} (band {band})"
+    if details is not None:
+        details.update(decisions_compared=n_dec, divergences=flips, flip_rate=len(flips) / max(n_dec, 1),
+                       fraction_of_oracle_decisions_with_gap_below_band=n_small / max(n_all, 1))
     return identical
 
 
