@@ -25,7 +25,7 @@ class NsbError(RuntimeError):
 
 class EngineConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("compute", C.c_int32), ("kv_dtype", C.c_int32), ("att_right_context", C.c_int32),
-                ("max_streams", C.c_int32), ("use_cuda_graph", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("max_streams", C.c_int32), ("use_cuda_graph", C.c_int32), ("decode_overlap", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class Stats(C.Structure):
@@ -138,12 +138,13 @@ class Engine:
     """One engine per GPU: weights + per-stream caches resident in HBM; streams are slots."""
 
     def __init__(self, gguf_path: str, right_context: int = 0, max_streams: int = 1, compute: int = COMPUTE_AUTO,
-                 kv_dtype: int = KV_F32, device: int = 0, cuda_graph: bool = True):
+                 kv_dtype: int = KV_F32, device: int = 0, cuda_graph: bool = True, decode_overlap: int = 0):
         cfg = EngineConfig()
         lib().nsb_default_config(C.byref(cfg))
         cfg.device, cfg.compute, cfg.kv_dtype = device, compute, kv_dtype
         cfg.att_right_context, cfg.max_streams = right_context, max_streams
         cfg.use_cuda_graph = 1 if cuda_graph else 0
+        cfg.decode_overlap = decode_overlap                    # 0 auto (<= 128 token rows), 1 always, 2 never
         h = C.c_void_p()
         _check(lib().nsb_engine_create(gguf_path.encode(), C.byref(cfg), C.byref(h)))
         self.h = h

@@ -44,6 +44,49 @@ void convert_to(const float* d_in, void* d_out, size_t n, int out_type, cudaStre
     convert_kernel<<<blocks, 256, 0, st>>>(d_in, d_out, n, out_type);
 }
 
+// ---- load-time unpacking of raw GGUF tensor bytes ON THE DEVICE (the host only moves bytes: mmap -> pinned chunk -> async H2D) ----
+__global__ void cvt_f16_kernel(const __half* __restrict__ in, void* __restrict__ out, size_t n, int out_type) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        store_out(out, i, __half2float(in[i]), out_type);           // fp16 -> f32 exact, then one rounding (bf16) like the host path
+}
+// Q8_0 blocks (fp16 d + 32 x int8, 34 bytes, 2-byte aligned) -> int8 plane + fp16 scale plane; one thread per block
+__global__ void unpack_q8_planes_kernel(const uint16_t* __restrict__ raw, int8_t* __restrict__ q, uint16_t* __restrict__ d, size_t nb) {
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (size_t)gridDim.x * blockDim.x) {
+        const uint16_t* p = raw + b * 17;
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = (uint32_t)p[1 + 2 * i] | ((uint32_t)p[2 + 2 * i] << 16);
+        d[b] = p[0];
+        uint4* dst = reinterpret_cast<uint4*>(q + b * 32);
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]); dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
+// Q8_0 / Q4_0 blocks -> dense values d * q (exact in f32), rounded once to out_type: what ggml's dequantize_row_* returns
+__global__ void dequant_blocks_kernel(const uint16_t* __restrict__ raw, void* __restrict__ out, size_t nb, int q4, int out_type) {
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (size_t)gridDim.x * blockDim.x) {
+        const uint16_t* p = raw + b * (q4 ? 9 : 17);
+        const float d = __half2float(__ushort_as_half(p[0]));
+        if (q4) {                                                   // byte i: element i = low nibble, element i + 16 = high nibble, value d * (q - 8)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t v = p[1 + i];
+                store_out(out, b * 32 + 2 * i, d * (float)((int)(v & 0xF) - 8), out_type);
+                store_out(out, b * 32 + 2 * i + 1, d * (float)((int)((v >> 8) & 0xF) - 8), out_type);
+                store_out(out, b * 32 + 16 + 2 * i, d * (float)((int)((v >> 4) & 0xF) - 8), out_type);
+                store_out(out, b * 32 + 16 + 2 * i + 1, d * (float)((int)(v >> 12) - 8), out_type);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint32_t v = p[1 + i];
+                store_out(out, b * 32 + 2 * i, d * (float)(int8_t)(v & 0xFF), out_type);
+                store_out(out, b * 32 + 2 * i + 1, d * (float)(int8_t)(v >> 8), out_type);
+            }
+        }
+    }
+}
+int grid_for(size_t n) { return (int)std::min<size_t>((n + 255) / 256, 148 * 8); }
+
 // any per-layer matrix as floats (F32 / F16 as stored, Q8_0 / Q4_0 dequantised): gguf_loader.cpp, pure host code tested on CPU
 std::vector<float> read_matrix_f32(const GgufFile& g, const std::string& name) { return g.read_dequant(name); }
 
@@ -100,6 +143,8 @@ Engine::Engine(const std::string& path, const nsb_engine_config& cfg) : cfg_(cfg
     if (prop.major != 10) throw CudaError(std::string("device '") + prop.name + "' is not sm_100 (kernels are built for sm_100a only)");
     try {
     NSB_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+    NSB_CUDA(cudaStreamCreateWithFlags(&st_dec_, cudaStreamNonBlocking));
+    for (Side& sd : side_) { NSB_CUDA(cudaEventCreateWithFlags(&sd.enc_done, cudaEventDisableTiming)); NSB_CUDA(cudaEventCreateWithFlags(&sd.dec_done, cudaEventDisableTiming)); }
     NSB_CUDA(cudaEventCreate(&ev0_));
     NSB_CUDA(cudaEventCreate(&ev1_));
     for (StepIO& io : io_) { NSB_CUDA(cudaEventCreate(&io.ev0)); NSB_CUDA(cudaEventCreate(&io.ev1)); NSB_CUDA(cudaEventCreateWithFlags(&io.done, cudaEventDisableTiming)); }
@@ -130,6 +175,9 @@ Engine::Engine(const std::string& path, const nsb_engine_config& cfg) : cfg_(cfg
     alloc_state();
     build_pos_tables(g);
     NSB_CUDA(cudaStreamSynchronize(st_));
+    NSB_CUDA(cudaGetLastError());
+    d_raw_ = DevBuf();                                             // load-time staging: released
+    for (int i = 0; i < 2; ++i) { up_[i].alloc(0); if (up_ev_[i]) { cudaEventDestroy(up_ev_[i]); up_ev_[i] = nullptr; } }
     } catch (...) { release_handles(); throw; }                    // a throwing constructor runs no destructor: free the stream and events here
 }
 
@@ -138,6 +186,10 @@ void Engine::release_handles() {
     cudaDeviceSynchronize();
     for (auto& g : graphs_) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     graphs_.clear();
+    for (auto& g : dec_graphs_) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+    dec_graphs_.clear();
+    for (Side& sd : side_) { if (sd.enc_done) { cudaEventDestroy(sd.enc_done); sd.enc_done = nullptr; } if (sd.dec_done) { cudaEventDestroy(sd.dec_done); sd.dec_done = nullptr; } }
+    if (st_dec_) { cudaStreamDestroy(st_dec_); st_dec_ = nullptr; }
     for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
     ev_pool_.clear();
     if (ev0_) { cudaEventDestroy(ev0_); ev0_ = nullptr; }
@@ -147,6 +199,7 @@ void Engine::release_handles() {
         if (io.ev1) { cudaEventDestroy(io.ev1); io.ev1 = nullptr; }
         if (io.done) { cudaEventDestroy(io.done); io.done = nullptr; }
     }
+    for (int i = 0; i < 2; ++i) if (up_ev_[i]) { cudaEventDestroy(up_ev_[i]); up_ev_[i] = nullptr; }
     if (st_) { cudaStreamDestroy(st_); st_ = nullptr; }
 }
 
@@ -184,19 +237,67 @@ static void q8_planes(const GgufFile& g, const std::string& name, std::vector<in
     }
 }
 
+// Chunked asynchronous host -> device copy out of the mapped file: the bytes go mmap -> one of two pinned chunks -> cudaMemcpyAsync on
+// the engine stream; while chunk i is in flight the host fills chunk i + 1. Returns once everything is ENQUEUED (src is no longer
+// read); consumers are ordered behind it on the same stream.
+void Engine::stream_upload(void* dst, const uint8_t* src, size_t bytes) {
+    constexpr size_t CHUNK = 16u << 20;
+    if (!up_[0].p) for (int i = 0; i < 2; ++i) { up_[i].alloc(CHUNK); NSB_CUDA(cudaEventCreateWithFlags(&up_ev_[i], cudaEventDisableTiming)); }
+    for (size_t off = 0; off < bytes; off += CHUNK) {
+        const size_t n = std::min(CHUNK, bytes - off);
+        NSB_CUDA(cudaEventSynchronize(up_ev_[up_k_]));              // the copy that last used this chunk has finished
+        memcpy(up_[up_k_].p, src + off, n);
+        NSB_CUDA(cudaMemcpyAsync((char*)dst + off, up_[up_k_].p, n, cudaMemcpyHostToDevice, st_));
+        NSB_CUDA(cudaEventRecord(up_ev_[up_k_], st_));
+        up_k_ ^= 1;
+    }
+}
+
 void Engine::load_layer_matrix(Weight& w, const GgufFile& g, const std::string& out_name, const std::vector<std::string>& parts, int n_out, int n_in) {
-    if (!q8_planes_mode()) {
-        std::vector<float> all;
-        for (const std::string& pn : parts) { std::vector<float> h = read_matrix_f32(g, pn); all.insert(all.end(), h.begin(), h.end()); }
-        upload_weight(w, out_name, all, n_out, n_in);
+    w.name = out_name; w.n_out = n_out; w.n_in = n_in;
+    if (n_out % (int)parts.size() != 0 || n_in % 64 != 0) throw std::runtime_error("shape mismatch for " + out_name);
+    const size_t rows = (size_t)n_out / parts.size(), part_elems = rows * n_in;
+    // tensor-type / shape validation with the tensor's name in the message (the reference's loader only checks presence, nemo-ggml.cpp:362-384)
+    for (const std::string& pn : parts) {
+        const GgufTensor& t = g.require(pn);
+        const bool squeezed3d = t.ne.size() == 3 && t.ne[0] == 1 && t.ne[1] == n_in;        // pointwise conv kept as (out, in, 1) by an older converter
+        if ((size_t)t.n_elements() != part_elems || !(t.ne.size() >= 2 && (t.ne[0] == n_in || squeezed3d))) {
+            std::string dims; for (auto d : t.ne) dims += (dims.empty() ? "" : ", ") + std::to_string(d);
+            throw std::runtime_error("gguf: tensor '" + pn + "' has shape [" + dims + "], expected [" + std::to_string(n_in) + ", " + std::to_string(rows) + "] (ne0 = input features)");
+        }
+        if (t.type != GGML_F32 && t.type != GGML_F16 && t.type != GGML_Q8_0 && t.type != GGML_Q4_0)
+            throw std::runtime_error("gguf: tensor '" + pn + "' has type " + std::to_string(t.type) + "; per-layer matrices must be F32, F16, Q8_0 or Q4_0");
+    }
+    if (d_raw_.bytes < part_elems * 4) { NSB_CUDA(cudaStreamSynchronize(st_)); d_raw_.alloc((size_t)D_FF * D_MODEL * 4, false); }
+    if (q8_planes_mode()) {
+        w.data.alloc((size_t)n_out * n_in, false); w.scales.alloc((size_t)n_out * (n_in / 32) * 2, false);
+        for (size_t i = 0; i < parts.size(); ++i) {
+            const GgufTensor& t = g.require(parts[i]);
+            int8_t* qd = w.data.as<int8_t>() + i * part_elems; uint16_t* dd = w.scales.as<uint16_t>() + i * (part_elems / 32);
+            if (t.type == GGML_Q8_0) {                              // stays quantised: raw blocks up, split into planes on the device
+                stream_upload(d_raw_.p, g.data(t), t.nbytes);
+                unpack_q8_planes_kernel<<<grid_for(part_elems / 32), 256, 0, st_>>>(d_raw_.as<uint16_t>(), qd, dd, part_elems / 32);
+            } else {                                                // another stored type: quantised here with the converter's rule (host)
+                std::vector<int8_t> q; std::vector<uint16_t> d; q8_planes(g, parts[i], q, d);
+                NSB_CUDA(cudaStreamSynchronize(st_));
+                h2d_sync(qd, q.data(), q.size()); h2d_sync(dd, d.data(), d.size() * 2);
+            }
+        }
         return;
     }
-    std::vector<int8_t> q; std::vector<uint16_t> d;
-    for (const std::string& pn : parts) q8_planes(g, pn, q, d);
-    if (q.size() != (size_t)n_out * n_in || n_in % 64 != 0) throw std::runtime_error("shape mismatch for " + out_name);
-    w.name = out_name; w.n_out = n_out; w.n_in = n_in;
-    w.data.alloc(q.size(), false); h2d_sync(w.data.p, q.data(), q.size());
-    w.scales.alloc(d.size() * 2, false); h2d_sync(w.scales.p, d.data(), d.size() * 2);
+    const int at = act_type();
+    const size_t es = act_size();
+    w.data.alloc((size_t)n_out * n_in * es, false);
+    for (size_t i = 0; i < parts.size(); ++i) {
+        const GgufTensor& t = g.require(parts[i]);
+        void* dst = (char*)w.data.p + i * part_elems * es;
+        const bool direct = (t.type == GGML_F32 && at == OUT_F32) || (t.type == GGML_F16 && at == OUT_F16);
+        stream_upload(direct ? dst : d_raw_.p, g.data(t), t.nbytes);
+        if (direct) continue;
+        if (t.type == GGML_F32) convert_kernel<<<grid_for(part_elems), 256, 0, st_>>>(d_raw_.as<float>(), dst, part_elems, at);
+        else if (t.type == GGML_F16) cvt_f16_kernel<<<grid_for(part_elems), 256, 0, st_>>>(d_raw_.as<__half>(), dst, part_elems, at);
+        else dequant_blocks_kernel<<<grid_for(part_elems / 32), 256, 0, st_>>>(d_raw_.as<uint16_t>(), dst, part_elems / 32, t.type == GGML_Q4_0 ? 1 : 0, at);
+    }
 }
 
 void Engine::load_weights(const GgufFile& g) {
@@ -332,6 +433,10 @@ void Engine::alloc_state() {
     part_.alloc((size_t)MAX_SPLITS * std::min<size_t>(Mrows, 1024) * D_MODEL * 4);       // split-K workspace (only used when rows <= 1024)
     out_tok_.alloc((size_t)S * MAX_SYMBOLS * T * 4); out_cnt_.alloc((size_t)S * 4);
     dec_sync_.alloc(decode_sync_bytes(S));
+    for (Side& sd : side_) {                                                             // hand-over buffers of a step, double-buffered (decode overlap)
+        sd.slot.alloc((size_t)S * 4); sd.encp.alloc(Mrows * JOINT * 4); sd.out_tok.alloc((size_t)S * MAX_SYMBOLS * T * 4);
+        sd.out_cnt.alloc((size_t)S * 4); sd.sync.alloc(decode_sync_bytes(S));
+    }
     for (StepIO& io : io_) {
         io.h_pcm.alloc((size_t)S * rl_ * 2); io.h_slot.alloc((size_t)S * 4);
         io.h_tok.alloc((size_t)S * MAX_SYMBOLS * T * 4); io.h_cnt.alloc((size_t)S * 4);
@@ -340,6 +445,7 @@ void Engine::alloc_state() {
 
 void Engine::zero_slot(int s) {
     NSB_CUDA(cudaSetDevice(device_));
+    join_decode_stream();                                                      // decoder state of the slot: no decode may still be running
     const int Cap = ATT_L + T;
     const size_t kvb = (size_t)n_layers * 2 * Cap * D_MODEL * kv_elem_size(kv_dtype);
     NSB_CUDA(cudaMemsetAsync((char*)kv_.p + (size_t)s * kvb, 0, kvb, st_));
@@ -504,14 +610,17 @@ int Engine::step_begin() {
         hs_stage_row(h, T, rl_, hp + (size_t)b * rl_); hsl[b] = batch[b];
         hs_launched(h, T);                                                // ready() now asks for the NEXT chunk; samples no later chunk needs are dropped
     }
+    const int side = side_acquire();
     NSB_CUDA(cudaMemcpyAsync(d_pcm_.p, hp, (size_t)B * rl_ * 2, cudaMemcpyHostToDevice, st_));
-    NSB_CUDA(cudaMemcpyAsync(d_slot_.p, hsl, (size_t)B * 4, cudaMemcpyHostToDevice, st_));
+    NSB_CUDA(cudaMemcpyAsync(side_[side].slot.p, hsl, (size_t)B * 4, cudaMemcpyHostToDevice, st_));
     NSB_CUDA(cudaEventRecord(io.ev0, st_));
-    run_step(B, d_pcm_.as<int16_t>());
-    NSB_CUDA(cudaEventRecord(io.ev1, st_));
-    NSB_CUDA(cudaMemcpyAsync(io.h_cnt.p, out_cnt_.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st_));
-    NSB_CUDA(cudaMemcpyAsync(io.h_tok.p, out_tok_.p, (size_t)B * MAX_SYMBOLS * T * 4, cudaMemcpyDeviceToHost, st_));
-    NSB_CUDA(cudaEventRecord(io.done, st_));
+    run_step(B, d_pcm_.as<int16_t>(), side);
+    cudaStream_t tail = tail_stream(B * T);                               // the decode's stream: its tokens go home behind it
+    NSB_CUDA(cudaEventRecord(io.ev1, tail));
+    NSB_CUDA(cudaMemcpyAsync(io.h_cnt.p, side_[side].out_cnt.p, (size_t)B * 4, cudaMemcpyDeviceToHost, tail));
+    NSB_CUDA(cudaMemcpyAsync(io.h_tok.p, side_[side].out_tok.p, (size_t)B * MAX_SYMBOLS * T * 4, cudaMemcpyDeviceToHost, tail));
+    NSB_CUDA(cudaEventRecord(io.done, tail));
+    if (tail != st_) { NSB_CUDA(cudaEventRecord(side_[side].dec_done, tail)); }   // the side is free again once its tokens have left
     io.batch = std::move(batch);
     io_next_ ^= 1; n_inflight_ += 1;
     return B;
@@ -571,30 +680,6 @@ std::string Engine::detok(const int32_t* t, int n) const {
     return r;
 }
 
-void Engine::run_step(int B, const int16_t* d_pcm) {
-    last_B_ = B;
-    if (!cfg_.use_cuda_graph || debug_ || profiling_) { run_step_kernels(B, d_pcm); return; }
-    StepGraph& g = graphs_[{B, (const void*)d_pcm}];
-    if (!g.exec) {
-        const long long before = stats.kernel_launches;
-        cudaGraph_t graph = nullptr;
-        NSB_CUDA(cudaStreamBeginCapture(st_, cudaStreamCaptureModeRelaxed));
-        try { run_step_kernels(B, d_pcm); }
-        catch (...) { cudaStreamEndCapture(st_, &graph); if (graph) cudaGraphDestroy(graph); graphs_.erase({B, (const void*)d_pcm}); throw; }
-        NSB_CUDA(cudaStreamEndCapture(st_, &graph));
-        const cudaError_t err = cudaGraphInstantiate(&g.exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (err != cudaSuccess) { graphs_.erase({B, (const void*)d_pcm}); throw CudaError(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(err)); }
-        g.launches = stats.kernel_launches - before;
-        stats.kernel_launches = before;                                         // capture launched nothing yet
-    }
-    NSB_CUDA(cudaGraphLaunch(g.exec, st_));
-    stats.kernel_launches += g.launches;
-}
-
-// ------------------------------------------------------------------------------------------
-// THE HOT PATH: one batched chunk for B streams, PCM already in HBM, tokens left in HBM.
-// ------------------------------------------------------------------------------------------
 // Diagnostic only (NSB_SKIP=ln,attn,conv,decode,ff,qkv,out,pw,sub,mel): leave kernel classes out of the step to read their
 // in-graph marginal cost off the step time. Results are meaningless with anything skipped.
 static unsigned skip_mask() {
@@ -608,11 +693,71 @@ static unsigned skip_mask() {
 }
 enum { SK_LN = 1, SK_ATTN = 2, SK_CONV = 4, SK_DECODE = 8, SK_FF = 16, SK_QKV = 32, SK_OUT = 64, SK_PW = 128, SK_SUB = 256, SK_MEL = 512 };
 
-void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
+// Decode overlap: on for batches of <= 128 token rows (every encoder kernel then launches <= 128 CTAs on the 148 SMs; NSB_DECODE_OVERLAP=0/1
+// forces it), off while taps / per-launch profiling are on (they read decode-side buffers behind a sync of st_ only).
+bool Engine::overlap_decode(int rows) const {
+    static const int env = [] { const char* e = getenv("NSB_DECODE_OVERLAP"); return e ? atoi(e) : -1; }();     // 0 / 1 override the config
+    const int mode = env == 0 ? 2 : env == 1 ? 1 : cfg_.decode_overlap;
+    if (debug_ || profiling_ || strict() || mode == 2) return false;
+    return mode == 1 || rows <= 128;
+}
+
+void Engine::join_decode_stream() {
+    for (Side& q : side_) if (q.dec_pending) { NSB_CUDA(cudaStreamWaitEvent(st_, q.dec_done, 0)); q.dec_pending = false; }
+}
+
+int Engine::side_acquire() {
+    const int p = side_next_;
+    if (side_[p].dec_pending) { NSB_CUDA(cudaStreamWaitEvent(st_, side_[p].dec_done, 0)); side_[p].dec_pending = false; }
+    return p;
+}
+
+template <class Key, class Fn>
+void Engine::run_graphed(std::map<Key, StepGraph>& cache, const Key& key, cudaStream_t s, Fn&& body) {
+    if (!cfg_.use_cuda_graph || debug_ || profiling_) { body(); return; }
+    StepGraph& g = cache[key];
+    if (!g.exec) {
+        const long long before = stats.kernel_launches;
+        cudaGraph_t graph = nullptr;
+        NSB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+        try { body(); }
+        catch (...) { cudaStreamEndCapture(s, &graph); if (graph) cudaGraphDestroy(graph); cache.erase(key); throw; }
+        NSB_CUDA(cudaStreamEndCapture(s, &graph));
+        const cudaError_t err = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (err != cudaSuccess) { cache.erase(key); throw CudaError(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(err)); }
+        g.launches = stats.kernel_launches - before;
+        stats.kernel_launches = before;                                         // capture launched nothing yet
+    }
+    NSB_CUDA(cudaGraphLaunch(g.exec, s));
+    stats.kernel_launches += g.launches;
+}
+
+void Engine::run_step(int B, const int16_t* d_pcm, int side) {
+    last_B_ = B;
+    const bool ov = overlap_decode(B * T);
+    Side& sd = side_[side];
+    if (!ov) join_decode_stream();                                              // decode on st_: behind any decode still running on the other stream
+    run_graphed(graphs_, std::make_tuple(B, (const void*)d_pcm, side), st_, [&] { run_encoder_kernels(B, d_pcm, side); });
+    if (ov) {
+        NSB_CUDA(cudaEventRecord(sd.enc_done, st_));
+        NSB_CUDA(cudaStreamWaitEvent(st_dec_, sd.enc_done, 0));
+    }
+    cudaStream_t s = ov ? st_dec_ : st_;
+    if (!(skip_mask() & 8u /* SK_DECODE */))
+        run_graphed(dec_graphs_, std::make_tuple(B, side, ov ? 1 : 0), s, [&] { run_decode_kernels(B, side, s, ov); });
+    if (ov) { NSB_CUDA(cudaEventRecord(sd.dec_done, st_dec_)); sd.dec_pending = true; }
+    side_next_ = side ^ 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// THE HOT PATH: one batched chunk for B streams, PCM already in HBM, tokens left in HBM.
+// ------------------------------------------------------------------------------------------
+void Engine::run_encoder_kernels(int B, const int16_t* d_pcm, int side) {
     const unsigned skip = skip_mask();
     const int M = PRE_CACHE + 8 * T, t1 = M / 2 + 1, t2 = t1 / 2 + 1, t3 = t2 / 2 + 1;
     const int rows = B * T, at = act_type();
-    const int* slot = d_slot_.as<int>();
+    const int* slot = side_[side].slot.as<int>();
     float* x = x_.as<float>();
     pending_ = PartialSum{};
 
@@ -726,14 +871,18 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
     }
     { ProfScope ps(this, PC_MISC); launch_advance_streams(slot, B, T, ring_pos_.as<int>(), valid_len_.as<int>(), st_); count_launch(); }
 
-    // G/Y: joint.enc for all frames, then the persistent greedy-decode kernel
+    // G: joint.enc for all frames (the decode kernel reads them from this side's buffer)
     if (skip & SK_DECODE) return;
     ProfScope ps_dec(this, PC_DECODE);
-    {
-        GemmArgs g; g.A = x; g.lda = D_MODEL; g.W = joint_enc_w_.data.p; g.M = rows; g.N = JOINT; g.K = D_MODEL; g.bias = joint_enc_b_.as<float>();
-        g.C = encp_.p; g.ldc = JOINT; g.epi = EPI_NONE;
-        gemm_f32w(g, joint_enc_w_, false);
-    }
+    GemmArgs g; g.A = x; g.lda = D_MODEL; g.W = joint_enc_w_.data.p; g.M = rows; g.N = JOINT; g.K = D_MODEL; g.bias = joint_enc_b_.as<float>();
+    g.C = side_[side].encp.p; g.ldc = JOINT; g.epi = EPI_NONE;
+    gemm_f32w(g, joint_enc_w_, false);
+}
+
+// Y: the persistent greedy-decode kernel on stream `s`; narrow = a handful of CTA pairs instead of one CTA per SM (decode overlap)
+void Engine::run_decode_kernels(int B, int side, cudaStream_t s, bool narrow) {
+    ProfScope ps_dec(this, PC_DECODE);
+    Side& sd = side_[side];
     DecodeArgs d{};
     d.w.embed = embed_.as<float>();
     for (int l = 0; l < 2; ++l) { d.w.w_ih[l] = lstm_w_[2 * l].as<float>(); d.w.w_hh[l] = lstm_w_[2 * l + 1].as<float>();
@@ -741,11 +890,11 @@ void Engine::run_step_kernels(int B, const int16_t* d_pcm) {
     d.w.pred_w = pred_w_.as<float>(); d.w.pred_b = pred_b_.as<float>(); d.w.out_w = jout_w_.as<float>(); d.w.out_b = jout_b_.as<float>();
     d.s.hbuf = dec_h_.as<float>(); d.s.cbuf = dec_c_.as<float>(); d.s.par = dec_par_.as<int>();
     d.s.dec_proj = dec_proj_.as<float>(); d.s.prev_token = prev_token_.as<int>(); d.s.cand_valid = cand_valid_.as<int>();
-    d.enc_proj = encp_.as<float>(); d.slot_of_b = slot; d.B = B; d.T = T;
-    d.out_tokens = out_tok_.as<int>(); d.out_count = out_cnt_.as<int>();
+    d.enc_proj = sd.encp.as<float>(); d.slot_of_b = sd.slot.as<int>(); d.B = B; d.T = T;
+    d.out_tokens = sd.out_tok.as<int>(); d.out_count = sd.out_cnt.as<int>();
     d.logits_tap = debug_ ? dbg_logits_.as<float>() : nullptr; d.logits_tap_cap = debug_ ? MAX_SYMBOLS * T + T : 0;
     d.logits_tap_n = debug_ ? dbg_logits_n_.as<int>() : nullptr;
-    launch_decode(d, dec_sync_.p, st_); count_launch();
+    launch_decode(d, sd.sync.p, s, narrow ? decode_narrow_ctas() : 0); count_launch();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -780,7 +929,7 @@ void Engine::bench_prepare(int n_streams, const int16_t* pcm, int samples_per_st
         }
         h2d_sync((char*)bench_pcm_.p + (size_t)k * n_streams * rl_ * 2, hp, (size_t)n_streams * rl_ * 2);
     }
-    h2d_sync(d_slot_.p, hsl, (size_t)n_streams * 4);
+    for (Side& sd : side_) h2d_sync(sd.slot.p, hsl, (size_t)n_streams * 4);
     bench_B_ = n_streams; bench_n_ = n_chunks; bench_i_ = 0;
 }
 
@@ -795,8 +944,8 @@ float Engine::bench_step() {
     collect_all();
     NSB_CUDA(cudaSetDevice(device_));
     NSB_CUDA(cudaEventRecord(ev0_, st_));
-    run_step(bench_B_, bench_next_pcm());
-    NSB_CUDA(cudaEventRecord(ev1_, st_));
+    run_step(bench_B_, bench_next_pcm(), side_acquire());
+    NSB_CUDA(cudaEventRecord(ev1_, tail_stream(bench_B_ * T)));
     NSB_CUDA(cudaEventSynchronize(ev1_));
     float ms = 0.f; NSB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
     stats.steps += 1; stats.chunks += bench_B_; stats.device_ms += ms; stats.last_step_ms = ms;
@@ -812,7 +961,8 @@ float Engine::bench_steps(int n, float* ms_each) {
     std::vector<cudaEvent_t> ev((size_t)n + 1);
     for (int i = 0; i <= n; ++i) ev[i] = prof_event();
     NSB_CUDA(cudaEventRecord(ev[0], st_));
-    for (int i = 0; i < n; ++i) { run_step(bench_B_, bench_next_pcm()); NSB_CUDA(cudaEventRecord(ev[i + 1], st_)); }
+    // with decode overlap the event after step i sits behind its DECODE (other stream): the encoder of step i + 1 is already running
+    for (int i = 0; i < n; ++i) { run_step(bench_B_, bench_next_pcm(), side_acquire()); NSB_CUDA(cudaEventRecord(ev[i + 1], tail_stream(bench_B_ * T))); }
     NSB_CUDA(cudaEventSynchronize(ev[n]));
     float total = 0.f; NSB_CUDA(cudaEventElapsedTime(&total, ev[0], ev[n]));
     for (int i = 0; i < n; ++i) {
@@ -915,9 +1065,10 @@ cudaEvent_t Engine::prof_event() {
 float Engine::bench_profile(float* ms_per_class, int* launches_per_class) {
     if (!bench_B_) throw std::runtime_error("bench_profile before bench_prepare");
     NSB_CUDA(cudaSetDevice(device_));
+    join_decode_stream();
     prof_.clear(); ev_used_ = 0; profiling_ = true;
     NSB_CUDA(cudaEventRecord(ev0_, st_));
-    run_step_kernels(bench_B_, bench_pcm_.as<int16_t>());
+    { const int side = side_acquire(); run_encoder_kernels(bench_B_, bench_pcm_.as<int16_t>(), side); run_decode_kernels(bench_B_, side, st_, false); side_next_ = side ^ 1; }
     NSB_CUDA(cudaEventRecord(ev1_, st_));
     profiling_ = false;
     NSB_CUDA(cudaEventSynchronize(ev1_));
@@ -932,6 +1083,7 @@ float Engine::bench_profile(float* ms_per_class, int* launches_per_class) {
 // ------------------------------------------------------------------------------------------
 void Engine::debug_enable(bool on) {
     NSB_CUDA(cudaSetDevice(device_));
+    collect_all(); join_decode_stream();
     debug_ = on;
     if (!on) return;
     dbg_B_ = max_streams;
@@ -1085,6 +1237,7 @@ long long Engine::transcribe_full(const int16_t* pcm, int n_samples, int32_t* to
     const int t1 = M / 2 + 1, t2 = t1 / 2 + 1, t3 = t2 / 2 + 1, Tq = t3;          // three 3x3 s2 convs with (2, 1) padding (nemo-ggml.cpp:828-836)
     if (Tq > 2048) throw std::invalid_argument("transcribe_full: more than 2048 encoder frames (the reference's positional table, nemo-ggml.cpp:196)");
     if (enc_out && enc_cap < (size_t)Tq * D_MODEL) return -(long long)((size_t)Tq * D_MODEL);
+    join_decode_stream();
     ensure_full_pos(Tq);
     ensure_batch_work(Tq, t2);
     const int slot = open_stream();                                               // zeroed conv state, decoder state, prev_token = blank

@@ -4,6 +4,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/nsb200.h"
@@ -111,6 +112,8 @@ private:
     // per-layer matrix straight from the file: Q8_0 tensors keep their quants in Q8_0 compute mode (fused-dequant GEMM)
     void load_layer_matrix(Weight& w, const GgufFile& g, const std::string& out_name, const std::vector<std::string>& parts, int n_out, int n_in);
     void alloc_state();
+    void stream_upload(void* dst, const uint8_t* src, size_t bytes);   // mmap -> pinned chunks -> async H2D on st_
+    HostPinned up_[2]; cudaEvent_t up_ev_[2] = {nullptr, nullptr}; int up_k_ = 0; DevBuf d_raw_;   // load-time staging
     void release_handles();            // graphs, events, stream (destructor and failed constructor)
     void zero_slot(int slot);
     void build_pos_tables(const GgufFile& g);
@@ -126,12 +129,27 @@ private:
     void gemm_f32w(GemmArgs& g, const Weight& W, bool a_presplit);   // matrices kept in F32 by every GGUF: SIMT fp32 / 3xTF32
     void gemm_planes(const void* A, long long lda, const Weight& W, int M, void* C, int planes);
     PartialSum pending_{};
-    void run_step_kernels(int B, const int16_t* d_pcm);      // everything between PCM-in-HBM and tokens-in-HBM
-    // run_step_kernels through a CUDA graph captured once per (batch size, PCM buffer): the ~350 launches of a step become
-    // one cudaGraphLaunch (cfg.use_cuda_graph; bypassed while debug taps or per-launch profiling are on)
-    void run_step(int B, const int16_t* d_pcm);
+    // Everything between PCM-in-HBM and tokens-in-HBM, in two halves: the encoder (log-mel ... joint.enc projections) and the RNN-T
+    // decode kernel. `side` selects one of two sets of hand-over buffers (stream slots of the batch, joint.enc projections, token ids).
+    void run_encoder_kernels(int B, const int16_t* d_pcm, int side);
+    void run_decode_kernels(int B, int side, cudaStream_t s, bool narrow);
+    // Each half through a CUDA graph captured once per (batch size, PCM buffer, side): the ~350 launches of a step become two
+    // cudaGraphLaunch calls (cfg.use_cuda_graph; bypassed while debug taps or per-launch profiling are on).
+    // Decode overlap (small batches): the decode of step i runs on its own stream, on a handful of SMs, UNDER the encoder of step
+    // i + 1 -- its per-symbol rounds are latency-bound and need no more, while the encoder's kernels at <= 128 token rows launch
+    // <= 128 CTAs and leave those SMs idle anyway. Same kernel, same arithmetic, same tokens; the sides are what makes it safe.
+    void join_decode_stream();                               // st_ waits for whatever the decode stream still runs
+    int side_acquire();                                      // next side; orders st_ behind the decode that last read its buffers
+    void run_step(int B, const int16_t* d_pcm, int side);
+    bool overlap_decode(int rows) const;
+    cudaStream_t tail_stream(int rows) const { return overlap_decode(rows) ? st_dec_ : st_; }   // where a step's tokens become available
     struct StepGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; };
-    std::map<std::pair<int, const void*>, StepGraph> graphs_;
+    std::map<std::tuple<int, const void*, int>, StepGraph> graphs_;      // encoder halves
+    std::map<std::tuple<int, int, int>, StepGraph> dec_graphs_;           // decode halves: (batch, side, narrow)
+    template <class Key, class Fn> void run_graphed(std::map<Key, StepGraph>& cache, const Key& key, cudaStream_t s, Fn&& body);
+    struct Side { DevBuf slot, encp, out_tok, out_cnt, sync; cudaEvent_t enc_done = nullptr, dec_done = nullptr; bool dec_pending = false; };
+    Side side_[2]; int side_next_ = 0;
+    cudaStream_t st_dec_ = nullptr;
     struct StepIO {                   // host side of one step in flight
         HostPinned h_pcm, h_slot, h_tok, h_cnt;
         cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;

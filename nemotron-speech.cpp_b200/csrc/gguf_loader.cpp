@@ -5,6 +5,11 @@
 #include <cstring>
 #include <stdexcept>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 namespace nsb {
 
 namespace {
@@ -44,6 +49,13 @@ float half_bits_to_float(uint16_t h) {
     } else if (exp == 31) f = (sign << 31) | 0x7f800000u | (man << 13);
     else f = (sign << 31) | ((exp + 127 - 15) << 23) | (man << 13);
     float out; memcpy(&out, &f, 4); return out;
+}
+
+GgufFile::~GgufFile() { if (map) munmap(const_cast<uint8_t*>(map), map_size); }
+
+const uint8_t* GgufFile::data(const GgufTensor& t) const {
+    if (!map || data_start + t.offset + t.nbytes > map_size) throw std::runtime_error("gguf: tensor '" + t.name + "' lies outside the file");
+    return map + data_start + t.offset;
 }
 
 void GgufFile::open(const std::string& p) {
@@ -106,6 +118,23 @@ void GgufFile::open(const std::string& p) {
     }
     uint64_t pos = (uint64_t)ftell(f);
     data_start = (pos + alignment - 1) / alignment * alignment;
+    // map the file and make sure every tensor is inside it (a truncated download fails here, by name, not in the middle of a load)
+    const int fd = ::open(p.c_str(), O_RDONLY);
+    struct stat sb;
+    if (fd < 0 || fstat(fd, &sb) != 0) { if (fd >= 0) ::close(fd); throw std::runtime_error("gguf: cannot open '" + p + "'"); }
+    map_size = (size_t)sb.st_size;
+    void* m = map_size ? mmap(nullptr, map_size, PROT_READ, MAP_PRIVATE, fd, 0) : MAP_FAILED;
+    ::close(fd);
+    if (m == MAP_FAILED) { map_size = 0; throw std::runtime_error("gguf: cannot map '" + p + "'"); }
+    map = (const uint8_t*)m;
+    madvise(m, map_size, MADV_SEQUENTIAL);
+    for (const auto& kv : tensors) {
+        const GgufTensor& t = kv.second;
+        if (t.offset % alignment != 0) throw std::runtime_error("gguf: tensor '" + t.name + "' is not aligned to " + std::to_string(alignment) + " bytes");
+        if (data_start + t.offset + t.nbytes > map_size)
+            throw std::runtime_error("gguf: file truncated: tensor '" + t.name + "' needs bytes up to " + std::to_string(data_start + t.offset + t.nbytes) +
+                                     " but the file has " + std::to_string(map_size));
+    }
 }
 
 const GgufTensor& GgufFile::require(const std::string& name) const {
@@ -115,12 +144,8 @@ const GgufTensor& GgufFile::require(const std::string& name) const {
 }
 
 std::vector<uint8_t> GgufFile::read(const GgufTensor& t) const {
-    File fh(path);
-    if (!fh.f) throw std::runtime_error("gguf: cannot reopen '" + path + "'");
-    std::vector<uint8_t> buf(t.nbytes);
-    if (fseek(fh.f, (long)(data_start + t.offset), SEEK_SET) != 0 || fread(buf.data(), 1, t.nbytes, fh.f) != t.nbytes)
-        throw std::runtime_error("gguf: failed to read tensor '" + t.name + "'");
-    return buf;
+    const uint8_t* p = data(t);
+    return std::vector<uint8_t>(p, p + t.nbytes);
 }
 
 std::vector<float> GgufFile::read_f32(const std::string& name) const {

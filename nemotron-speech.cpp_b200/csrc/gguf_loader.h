@@ -22,13 +22,20 @@ struct GgufTensor {
 };
 
 struct GgufFile {
+    GgufFile() = default;
+    GgufFile(const GgufFile&) = delete; GgufFile& operator=(const GgufFile&) = delete;
+    ~GgufFile();
     std::string path;
+    // the whole file, mapped read-only (open): tensor bytes are consumed straight out of the page cache -- by the host-side
+    // dequantisers below and by the engine's chunked asynchronous upload -- never through a per-tensor fopen / fread
+    const uint8_t* map = nullptr; size_t map_size = 0;
+    const uint8_t* data(const GgufTensor& t) const;     // bounds-checked pointer to the tensor's bytes inside the mapping
     std::map<std::string, uint32_t> u32;      // nemo.* hparams
     std::string vocab_raw;                    // tokenizer.vocab bytes
     std::map<std::string, GgufTensor> tensors;
     uint64_t data_start = 0;
 
-    // Parses header + tensor infos. Throws std::runtime_error with a readable message.
+    // Parses header + tensor infos, maps the file, checks that every tensor lies inside it. Throws std::runtime_error with a readable message.
     void open(const std::string& path);
     // Reads the raw bytes of one tensor.
     std::vector<uint8_t> read(const GgufTensor& t) const;

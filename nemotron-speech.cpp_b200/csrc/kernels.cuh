@@ -132,8 +132,10 @@ struct DecodeArgs {
     unsigned* barrier; unsigned long long* best;   // filled by launch_decode from its sync buffer
     float* logits_tap; int logits_tap_cap; int* logits_tap_n;   // optional: logits of batch row 0 per evaluation
 };
-// persistent kernel, one CTA per SM (cooperative launch); sync_buf holds decode_sync_bytes(B) bytes. Returns the grid size used
-int launch_decode(const DecodeArgs& a, void* sync_buf, cudaStream_t st);
+// persistent kernel; sync_buf holds decode_sync_bytes(B) bytes. narrow_ctas = 0: one CTA per SM (cooperative launch); > 0: that many CTAs
+// as CTA pairs, sharing the GPU with other kernels (decode overlap). Returns the grid size used
+int launch_decode(const DecodeArgs& a, void* sync_buf, cudaStream_t st, int narrow_ctas = 0);
+int decode_narrow_ctas();          // NSB_DECODE_CTAS, default 16
 size_t decode_sync_bytes(int B);
 
 }  // namespace nsb

@@ -28,6 +28,9 @@
 //   * h/c are double-buffered per stream: the candidate is written to the other parity, committing = flipping the
 //     parity bit (no copy, no extra barrier);
 //   * the grid barrier is a monotonic counter in HBM (arrive = one atomicAdd, wait = ld.acquire spin, bounded).
+#include <algorithm>
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace nsb {
@@ -345,16 +348,34 @@ static int decode_grid() {                 // per device ordinal: the attribute 
 }
 size_t decode_sync_bytes(int B) { return 16 + (size_t)3 * B * sizeof(unsigned long long); }
 
-int launch_decode(const DecodeArgs& a_in, void* sync_buf, cudaStream_t st) {
-    const int grid = decode_grid();
+int decode_narrow_ctas() {
+    static const int n = [] { const char* e = getenv("NSB_DECODE_CTAS"); const int v = e ? atoi(e) : 16; return std::max(2, v & ~1); }();
+    return n;
+}
+
+// narrow_ctas = 0: one CTA per SM, cooperative launch (the decode has the GPU to itself). narrow_ctas > 0: that many CTAs, launched as
+// CTA pairs (clusters of 2: a pair takes one TPC, so the CTA-pair GEMMs of a concurrently running encoder keep their TPCs whole) with a
+// plain launch: the kernel then shares the GPU with the next step's encoder. Its grid barrier needs every CTA resident at some
+// point, which a grid this small reaches as soon as a few SMs are free -- nothing the other kernels run ever waits on this one.
+int launch_decode(const DecodeArgs& a_in, void* sync_buf, cudaStream_t st, int narrow_ctas) {
+    const int full = decode_grid();
     if (a_in.B > MAXB) throw CudaError("decode: more than 1024 streams in one step");
     DecodeArgs a = a_in;
     a.barrier = reinterpret_cast<unsigned*>(sync_buf);
     a.best = reinterpret_cast<unsigned long long*>((char*)sync_buf + 16);
     NSB_CUDA(cudaMemsetAsync(sync_buf, 0, decode_sync_bytes(a.B), st));           // barrier counter + argmax keys
+    if (narrow_ctas > 0 && narrow_ctas < full) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(narrow_ctas); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = sizeof(DecSmem); cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        NSB_CUDA(cudaLaunchKernelEx(&cfg, rnnt_decode_kernel, a));
+        return narrow_ctas;
+    }
     void* args[] = {(void*)&a};
-    NSB_CUDA(cudaLaunchCooperativeKernel((void*)rnnt_decode_kernel, dim3(grid), dim3(NT), args, sizeof(DecSmem), st));
-    return grid;
+    NSB_CUDA(cudaLaunchCooperativeKernel((void*)rnnt_decode_kernel, dim3(full), dim3(NT), args, sizeof(DecSmem), st));
+    return full;
 }
 
 }  // namespace nsb

@@ -374,6 +374,26 @@ def test_api_edge_cases(built):
     eng.close()
 
 
+def test_loader_rejects_mis_shaped_and_mis_typed_matrices_by_name(built, tmp_path):
+    """Tensor-type / shape validation of the per-layer matrices (the reference's loader checks presence only, nemo-ggml.cpp:362-384):
+    a [4096, 1024] matrix stored as [1024, 4096], and a matrix of an unsupported ggml type, are refused with the tensor's name."""
+    import struct
+    import nsb200
+    raw = bytearray(open(synth.cached_model("f16", 2, R=0), "rb").read())
+    name = b"encoder.layers.1.feed_forward1.linear2.weight"
+    at = raw.index(struct.pack("<Q", len(name)) + name) + 8 + len(name)
+    nd, d0, d1, typ = struct.unpack_from("<IqqI", raw, at)
+    assert (nd, d0, d1, typ) == (2, 4096, 1024, 1)
+    bad = bytearray(raw); struct.pack_into("<Iqq", bad, at, 2, 1024, 4096)
+    f = tmp_path / "swapped.gguf"; f.write_bytes(bad)
+    with pytest.raises(nsb200.NsbError, match=r"feed_forward1.linear2.weight' has shape \[1024, 4096\], expected \[4096, 1024\]"):
+        nsb200.Engine(str(f), right_context=0, max_streams=1)
+    bad = bytearray(raw); struct.pack_into("<I", bad, at + 20, 12)         # type 12 = Q4_K: not a type the converter writes
+    f = tmp_path / "q4k.gguf"; f.write_bytes(bad)
+    with pytest.raises(nsb200.NsbError, match="feed_forward1.linear2.weight' has unsupported type 12"):
+        nsb200.Engine(str(f), right_context=0, max_streams=1)
+
+
 def test_many_streams_batch_invariance(built):
     """A stream's tokens must not depend on which other streams share its batch (64 streams vs alone)."""
     import nsb200

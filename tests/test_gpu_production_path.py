@@ -214,6 +214,36 @@ def test_graph_replay_equals_direct_launches_equals_tapped_run(built):
             assert np.array_equal(outs[0][1][s], outs[k][1][s]), (k, s)
 
 
+def test_decode_overlap_gives_the_same_tokens_as_inline_decode(built):
+    """Decode overlap (the decode of step i on its own stream and 16 CTAs, under the encoder of step i + 1; automatic at <= 128 token
+    rows = the bench's config 2 / 4) against the inline full-width decode: identical tokens and identical encoder output, with two
+    steps in flight and with single steps, bf16, 24 layers, 64 streams."""
+    import nsb200
+    R, T, n, chunks = 1, 2, 64, 12
+    path = synth.cached_model("f16", 24, R=R)
+    secs = (160 * (8 * T * chunks - 1) + 256) / 16000.0
+    base = [synth.synth_pcm(840 + s, secs + 0.01) for s in range(8)]
+    L = min(len(b) for b in base)
+    audio = np.stack([np.roll(base[s % 8][:L], 173 * (s // 8)) for s in range(n)])
+    res = []
+    for ov in (2, 1):
+        eng = nsb200.Engine(path, right_context=R, max_streams=n, compute=nsb200.COMPUTE_BF16, kv_dtype=nsb200.KV_BF16, decode_overlap=ov)
+        _, got, steps = run_two_in_flight(eng, audio)
+        x = eng.debug_get("x", n)
+        for s in range(n):
+            eng.reset_stream(s)
+        eng.push_batch(np.arange(n, dtype=np.int32), audio)
+        assert eng.drain() == n * steps
+        got1 = [eng.pop_tokens(s).tolist() for s in range(n)]
+        res.append((got, got1, x, steps))
+        eng.close()
+    assert res[0][3] == res[1][3] == chunks
+    assert sum(len(g) for g in res[0][0]) > 100
+    for s in range(n):
+        assert res[0][0][s] == res[1][0][s] == res[0][1][s] == res[1][1][s], s
+    assert np.array_equal(res[0][2].view(np.uint32), res[1][2].view(np.uint32))
+
+
 @pytest.mark.parametrize("mode,wtype,compute,kv,mm,okv", [
     ("f16_f32ring", "f16", 0, 0, O.MM_REF, O.KV_F32),      # the reference's F16 arithmetic proper: fp16 activations x fp16 weights, f32 K/V cache
     ("f16", "f16", 0, 1, O.MM_REF, O.KV_F16),

@@ -55,6 +55,12 @@ def test_gguf_probe_and_errors(built, tmp_path):
     trunc.write_bytes(open(synth.cached_model("f32", 2, R=0), "rb").read(3000))
     with pytest.raises(nsb200.NsbError):
         nsb200.probe(str(trunc))
+    # complete header, tensor data cut short (an interrupted download): refused at open, naming the first tensor that does not fit
+    full = open(synth.cached_model("f32", 2, R=0), "rb").read()
+    cut = tmp_path / "cut.gguf"
+    cut.write_bytes(full[:len(full) - 4096])
+    with pytest.raises(nsb200.NsbError, match="file truncated: tensor '"):
+        nsb200.probe(str(cut))
 
 
 def test_no_cpu_fallback(built):
