@@ -47,6 +47,11 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 bool pdl_enabled();            // engine.cu (NSB_NO_PDL=1 disables)
+// The first kernel behind a cross-stream event wait is launched WITHOUT the programmatic attribute (a plain, full dependency on
+// everything before it): pdl_skip_next() arms a one-shot, per-thread switch that the next launch_k / launch_k_cluster consumes.
+inline bool& pdl_skip_flag() { static thread_local bool f = false; return f; }
+inline void pdl_skip_next() { pdl_skip_flag() = true; }
+inline bool pdl_take() { bool& f = pdl_skip_flag(); const bool on = pdl_enabled() && !f; f = false; return on; }
 
 template <typename... P, typename... A>
 inline void launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
@@ -55,7 +60,7 @@ inline void launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cud
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = pdl_take() ? 1 : 0;
     NSB_CUDA(cudaLaunchKernelEx(&cfg, kern, P(std::forward<A>(args))...));
 }
 
@@ -66,7 +71,7 @@ inline void launch_k_cluster(void (*kern)(P...), dim3 grid, dim3 block, size_t s
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[2]; int n = 0;
     if (cluster_x > 1) { at[n].id = cudaLaunchAttributeClusterDimension; at[n].val.clusterDim.x = cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1; ++n; }
-    if (pdl_enabled()) { at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
+    if (pdl_take()) { at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
     cfg.attrs = at; cfg.numAttrs = n;
     NSB_CUDA(cudaLaunchKernelEx(&cfg, kern, P(std::forward<A>(args))...));
 }

@@ -45,6 +45,20 @@ void convert_to(const float* d_in, void* d_out, size_t n, int out_type, cudaStre
 }
 
 // ---- load-time unpacking of raw GGUF tensor bytes ON THE DEVICE (the host only moves bytes: mmap -> pinned chunk -> async H2D) ----
+// out[i] += sum of n_planes split-K planes (fixed order): the reduction of a split-K GEMM that no LayerNorm follows (joint.enc)
+__global__ void __launch_bounds__(256) add_planes_kernel(float* __restrict__ out, const float* __restrict__ part, int n_planes, size_t plane, size_t n4) {
+    NSB_KERNEL_PROLOGUE(TR_OTHER)
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) {
+        float4 v = reinterpret_cast<const float4*>(out)[i];
+        for (int z = 0; z < n_planes; ++z) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(part + (size_t)z * plane) + i);
+            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        }
+        reinterpret_cast<float4*>(out)[i] = v;
+    }
+    NSB_KERNEL_EPILOGUE();
+}
 __global__ void cvt_f16_kernel(const __half* __restrict__ in, void* __restrict__ out, size_t n, int out_type) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         store_out(out, i, __half2float(in[i]), out_type);           // fp16 -> f32 exact, then one rounding (bf16) like the host path
@@ -190,6 +204,10 @@ void Engine::release_handles() {
     dec_graphs_.clear();
     for (Side& sd : side_) { if (sd.enc_done) { cudaEventDestroy(sd.enc_done); sd.enc_done = nullptr; } if (sd.dec_done) { cudaEventDestroy(sd.dec_done); sd.dec_done = nullptr; } }
     if (st_dec_) { cudaStreamDestroy(st_dec_); st_dec_ = nullptr; }
+    for (cudaEvent_t e : ev_deq_) cudaEventDestroy(e);
+    for (cudaEvent_t e : ev_lstart_) cudaEventDestroy(e);
+    ev_deq_.clear(); ev_lstart_.clear();
+    if (st_deq_) { cudaStreamDestroy(st_deq_); st_deq_ = nullptr; }
     for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
     ev_pool_.clear();
     if (ev0_) { cudaEventDestroy(ev0_); ev0_ = nullptr; }
@@ -379,6 +397,7 @@ void Engine::load_weights(const GgufFile& g) {
         }
         vec(L.cln_g, p + "conv.batch_norm.weight", D_MODEL); vec(L.cln_b, p + "conv.batch_norm.bias", D_MODEL);
         for (Weight* w : {&L.ff1a, &L.ff1b, &L.ff2a, &L.ff2b, &L.qkv, &L.out, &L.pw1, &L.pw2}) named_[w->name] = w;
+        { int k = 0; for (Weight* w : {&L.ff1a, &L.ff1b, &L.qkv, &L.out, &L.pw1, &L.pw2, &L.ff2a, &L.ff2b}) w->shadow_slot = k++; }
     }
     // ---- decoder + joint: always f32 ----
     {
@@ -401,15 +420,18 @@ void Engine::alloc_state() {
     const int S = max_streams, Cap = ATT_L + T, M = PRE_CACHE + 8 * T;
     const int t1 = M / 2 + 1, t2 = t1 / 2 + 1, t3 = t2 / 2 + 1;
     if (t3 != T + DROP_PRE) throw std::runtime_error("unexpected subsampling length");
-    kv_.alloc((size_t)S * n_layers * 2 * Cap * D_MODEL * kv_elem_size(kv_dtype));       // zero-initialised (nemo-stream.cpp:292-297)
-    conv_cache_.alloc((size_t)S * n_layers * (CONV_K - 1) * D_MODEL * 4);
-    mel_hist_.alloc((size_t)S * PRE_CACHE * N_MELS * 4);                                 // 9 zero frames (:59-60)
-    ring_pos_.alloc((size_t)S * 4); valid_len_.alloc((size_t)S * 4);
-    dec_h_.alloc((size_t)S * 4 * HID * 4); dec_c_.alloc((size_t)S * 4 * HID * 4);      // [S][2 parities][2 layers][640]
-    dec_proj_.alloc((size_t)S * JOINT * 4);
-    prev_token_.alloc((size_t)S * 4); cand_valid_.alloc((size_t)S * 4); dec_par_.alloc((size_t)S * 4);
+    // per-slot state: max_streams stream slots + ONE private slot (index max_streams) for the non-streaming batch path, which needs
+    // conv / decoder state of its own whatever the streams are doing
+    const size_t SS = (size_t)S + 1;
+    kv_.alloc(SS * n_layers * 2 * Cap * D_MODEL * kv_elem_size(kv_dtype));               // zero-initialised (nemo-stream.cpp:292-297)
+    conv_cache_.alloc(SS * n_layers * (CONV_K - 1) * D_MODEL * 4);
+    mel_hist_.alloc(SS * PRE_CACHE * N_MELS * 4);                                         // 9 zero frames (:59-60)
+    ring_pos_.alloc(SS * 4); valid_len_.alloc(SS * 4);
+    dec_h_.alloc(SS * 4 * HID * 4); dec_c_.alloc(SS * 4 * HID * 4);                      // [S][2 parities][2 layers][640]
+    dec_proj_.alloc(SS * JOINT * 4);
+    prev_token_.alloc(SS * 4); cand_valid_.alloc(SS * 4); dec_par_.alloc(SS * 4);
     hs_.assign(S, HostStream());
-    for (int s = 0; s < S; ++s) zero_slot(s);
+    for (int s = 0; s <= S; ++s) zero_slot(s);
 
     rl_ = hs_row_len(T);                                                                  // 1280 T + 353 samples per stream-step
     const size_t Mrows = (size_t)S * T;
@@ -426,7 +448,18 @@ void Engine::alloc_state() {
     // small batches: the QKV / pointwise-1 GEMMs run split-K and leave their partial planes for the consumer kernel to sum
     const size_t planes = Mrows <= SPLIT_CONSUMER_MAX_ROWS ? 4 : 1;
     consumer_planes_ = (int)planes;
-    if (compute == NSB_COMPUTE_Q8_0) wscratch_.alloc((size_t)D_FF * D_MODEL * 2, false);   // largest layer matrix as fp16 (q8_predequant)
+    if (compute == NSB_COMPUTE_Q8_0) wscratch_.alloc((size_t)D_FF * D_MODEL * 2, false);   // largest layer matrix as fp16 (q8_predequant: op_gemm / bench_gemm)
+    if (compute == NSB_COMPUTE_Q8_0 && Mrows >= 512) {                                     // layer-ahead fp16 shadows (see engine.h)
+        const size_t sz[8] = {(size_t)D_FF * D_MODEL, (size_t)D_MODEL * D_FF, (size_t)3 * D_MODEL * D_MODEL, (size_t)D_MODEL * D_MODEL,
+                              (size_t)2 * D_MODEL * D_MODEL, (size_t)D_MODEL * D_MODEL, (size_t)D_FF * D_MODEL, (size_t)D_MODEL * D_FF};
+        size_t off = 0; for (int k = 0; k < 8; ++k) { shadow_off_[k] = off; off += sz[k] * 2; }
+        shadow_bytes_ = off;
+        for (DevBuf& b : shadow_) b.alloc(off, false);
+        NSB_CUDA(cudaStreamCreateWithFlags(&st_deq_, cudaStreamNonBlocking));
+        ev_deq_.resize(n_layers); ev_lstart_.resize(n_layers + 1);
+        for (cudaEvent_t& e : ev_deq_) NSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (cudaEvent_t& e : ev_lstart_) NSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     qkv_.alloc(planes * Mrows * 3 * D_MODEL * 4);
     pw1_.alloc(planes * Mrows * 2 * D_MODEL * 4);
     encp_.alloc(Mrows * JOINT * 4);
@@ -461,7 +494,7 @@ void Engine::zero_slot(int s) {
     NSB_CUDA(cudaMemcpyAsync((char*)cand_valid_.p + (size_t)s * 4, &zero, 4, cudaMemcpyHostToDevice, st_));
     NSB_CUDA(cudaMemcpyAsync((char*)prev_token_.p + (size_t)s * 4, &blank, 4, cudaMemcpyHostToDevice, st_));   // prev_token = blank (:41-42)
     NSB_CUDA(cudaStreamSynchronize(st_));
-    hs_clear(hs_[s]);
+    if (s < max_streams) hs_clear(hs_[s]);
 }
 
 // P_l = linear_pos(pos_emb rows) for the L+2T-1 relative positions a chunk can touch, once, at load.
@@ -494,7 +527,8 @@ void Engine::gemm(const void* A, long long lda, const Weight& W, int M, const fl
     GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.w_scales = W.scales.p; a.M = M; a.N = W.n_out; a.K = W.n_in; a.bias = bias; a.C = C; a.ldc = ldc;
     a.epi = epi; a.alpha = alpha; a.out_type = out_type; a.pair = 1;
     ProfScope ps(this, PC_GEMM);
-    q8_predequant(W, M, a);
+    if (cur_shadow_ && W.shadow_slot >= 0) { a.W = cur_shadow_ + shadow_off_[W.shadow_slot]; a.w_scales = nullptr; }   // dequantised a layer ahead
+    else q8_predequant(W, M, a);
     if (compute == NSB_COMPUTE_Q8_0_STRICT) { launch_gemm_q8_strict(a, q8s_scratch_.p, q8s_scratch_.bytes, st_); count_launch(); }
     else if (compute == NSB_COMPUTE_F32) launch_gemm_simt(a, st_);
     else launch_gemm_tc(a, act_type(), st_);
@@ -536,6 +570,21 @@ void Engine::q8_predequant(const Weight& W, int M, GemmArgs& a) {
     a.W = wscratch_.p; a.w_scales = nullptr; a.w_dynamic = 1; a.pair = 0;
 }
 
+bool Engine::shadow_mode(int rows) const {
+    static const bool off = [] { const char* e = getenv("NSB_Q8_SHADOW"); return e && e[0] == '0'; }();
+    static const int min_rows = [] { const char* e = getenv("NSB_Q8_PREDEQUANT_ROWS"); return e ? atoi(e) : 512; }();
+    return !off && compute == NSB_COMPUTE_Q8_0 && shadow_bytes_ && rows >= min_rows && !profiling_;
+}
+// all 8 matrices of layer l -> fp16 in shadow_[l % 2], on stream s (same fp16(d) * q values as the fused operand path)
+void Engine::dequant_layer_async(int l, cudaStream_t s) {
+    LayerW& L = layers_[l];
+    char* base = shadow_[l & 1].as<char>();
+    for (Weight* w : {&L.ff1a, &L.ff1b, &L.qkv, &L.out, &L.pw1, &L.pw2, &L.ff2a, &L.ff2b}) {
+        launch_dequant_q8(w->data.p, w->scales.p, base + shadow_off_[w->shadow_slot], w->n_out, w->n_in, s);
+        count_launch();
+    }
+}
+
 bool Engine::split_consumers(int rows) const {
     static const bool off = [] { const char* e = getenv("NSB_NO_SPLIT_CONSUMERS"); return e && e[0] == '1'; }();
     return !off && !pair_gemm_enabled() && consumer_planes_ >= 4 && (compute == NSB_COMPUTE_F16 || compute == NSB_COMPUTE_BF16) && rows <= 128;
@@ -567,7 +616,9 @@ void Engine::gemm_residual(const void* A, long long lda, const Weight& W, int M,
     if (splits == 1) { gemm(A, lda, W, M, nullptr, x, D_MODEL, EPI_RESID, alpha, OUT_F32); return; }
     GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.w_scales = W.scales.p; a.M = M; a.N = W.n_out; a.K = W.n_in; a.C = part_.p; a.ldc = D_MODEL;
     a.epi = EPI_PARTIAL; a.out_type = OUT_F32; a.splits = splits;
-    { ProfScope ps(this, PC_GEMM); q8_predequant(W, M, a); launch_gemm_tc(a, act_type(), st_); }
+    { ProfScope ps(this, PC_GEMM);
+      if (cur_shadow_ && W.shadow_slot >= 0) { a.W = cur_shadow_ + shadow_off_[W.shadow_slot]; a.w_scales = nullptr; } else q8_predequant(W, M, a);
+      launch_gemm_tc(a, act_type(), st_); }
     count_launch();
     pending_.part = part_.as<float>(); pending_.n = splits; pending_.alpha = alpha;
 }
@@ -693,13 +744,14 @@ static unsigned skip_mask() {
 }
 enum { SK_LN = 1, SK_ATTN = 2, SK_CONV = 4, SK_DECODE = 8, SK_FF = 16, SK_QKV = 32, SK_OUT = 64, SK_PW = 128, SK_SUB = 256, SK_MEL = 512 };
 
-// Decode overlap: on for batches of <= 128 token rows (every encoder kernel then launches <= 128 CTAs on the 148 SMs; NSB_DECODE_OVERLAP=0/1
-// forces it), off while taps / per-launch profiling are on (they read decode-side buffers behind a sync of st_ only).
+// Decode overlap (nsb_engine_config::decode_overlap; NSB_DECODE_OVERLAP=0/1 overrides): meant for batches of <= 128 token rows, where
+// every encoder kernel launches <= 128 CTAs on the 148 SMs. Off while taps / per-launch profiling are on (they read decode-side
+// buffers behind a sync of st_ only). Automatic mode = decode_auto_overlap(): see there for when it pays.
 bool Engine::overlap_decode(int rows) const {
     static const int env = [] { const char* e = getenv("NSB_DECODE_OVERLAP"); return e ? atoi(e) : -1; }();     // 0 / 1 override the config
     const int mode = env == 0 ? 2 : env == 1 ? 1 : cfg_.decode_overlap;
     if (debug_ || profiling_ || strict() || mode == 2) return false;
-    return mode == 1 || rows <= 128;
+    return mode == 1 || (rows <= 128 && decode_auto_overlap());
 }
 
 void Engine::join_decode_stream() {
@@ -755,6 +807,7 @@ void Engine::run_step(int B, const int16_t* d_pcm, int side) {
 // ------------------------------------------------------------------------------------------
 void Engine::run_encoder_kernels(int B, const int16_t* d_pcm, int side) {
     const unsigned skip = skip_mask();
+    cur_shadow_ = nullptr;
     const int M = PRE_CACHE + 8 * T, t1 = M / 2 + 1, t2 = t1 / 2 + 1, t3 = t2 / 2 + 1;
     const int rows = B * T, at = act_type();
     const int* slot = side_[side].slot.as<int>();
@@ -809,12 +862,32 @@ void Engine::run_encoder_kernels(int B, const int16_t* d_pcm, int side) {
         if (skip & SK_LN) { pending_ = PartialSum{}; return; }
         ProfScope ps(this, PC_LAYERNORM); launch_layernorm(x, rows, g_, b_, a_.p, at, pending_, st_); count_launch(); pending_ = PartialSum{};
     };
+    // Q8_0 at large batches: dequantisation runs one layer ahead on its own stream (fork / join through events; inside a graph
+    // capture these become plain dependency edges). Layer 0 is dequantised under the front end.
+    const bool shadow = shadow_mode(rows);
+    if (shadow) {
+        NSB_CUDA(cudaEventRecord(ev_lstart_[n_layers], st_));                     // everything of the previous step that read the shadows is behind us
+        NSB_CUDA(cudaStreamWaitEvent(st_deq_, ev_lstart_[n_layers], 0));
+        pdl_skip_next(); dequant_layer_async(0, st_deq_);
+        NSB_CUDA(cudaEventRecord(ev_deq_[0], st_deq_));
+    }
     ln(layers_[0].ln[0].as<float>(), layers_[0].ln[1].as<float>());
     // "sub" tap: taken AFTER the first LayerNorm, which folds the split-K planes of the stem projection back into x -- so the
     // tapped run executes exactly the arithmetic of the untapped one (taps only add copies)
     if (debug_) NSB_CUDA(cudaMemcpyAsync(dbg_sub_.p, x, (size_t)rows * D_MODEL * 4, cudaMemcpyDeviceToDevice, st_));
     for (int l = 0; l < n_layers; ++l) {
         LayerW& L = layers_[l];
+        if (shadow) {
+            NSB_CUDA(cudaEventRecord(ev_lstart_[l], st_));                        // layer l - 1 (the other shadow's reader) is complete at this point
+            if (l + 1 < n_layers) {
+                NSB_CUDA(cudaStreamWaitEvent(st_deq_, ev_lstart_[l], 0));
+                pdl_skip_next(); dequant_layer_async(l + 1, st_deq_);
+                NSB_CUDA(cudaEventRecord(ev_deq_[l + 1], st_deq_));
+            }
+            NSB_CUDA(cudaStreamWaitEvent(st_, ev_deq_[l], 0));                    // this layer's fp16 weights are in place
+            cur_shadow_ = shadow_[l & 1].as<char>();
+            pdl_skip_next();                                                      // the layer's first GEMM: full dependency (it sits behind a cross-stream wait)
+        }
         // FFN1: x += 0.5 * W2 silu(W1 LN(x))                                        (nemo-stream.cpp:603-606)
         if (!(skip & SK_FF)) {
         gemm(a_.p, D_MODEL, L.ff1a, rows, nullptr, big_.p, D_FF, EPI_SILU, 1.f, at);
@@ -869,6 +942,7 @@ void Engine::run_encoder_kernels(int B, const int16_t* d_pcm, int side) {
         if (debug_) NSB_CUDA(cudaMemcpyAsync(dbg_layers_.as<float>() + (size_t)l * dbg_B_ * T * D_MODEL, x, (size_t)rows * D_MODEL * 4,
                                              cudaMemcpyDeviceToDevice, st_));
     }
+    cur_shadow_ = nullptr;
     { ProfScope ps(this, PC_MISC); launch_advance_streams(slot, B, T, ring_pos_.as<int>(), valid_len_.as<int>(), st_); count_launch(); }
 
     // G: joint.enc for all frames (the decode kernel reads them from this side's buffer)
@@ -876,7 +950,18 @@ void Engine::run_encoder_kernels(int B, const int16_t* d_pcm, int side) {
     ProfScope ps_dec(this, PC_DECODE);
     GemmArgs g; g.A = x; g.lda = D_MODEL; g.W = joint_enc_w_.data.p; g.M = rows; g.N = JOINT; g.K = D_MODEL; g.bias = joint_enc_b_.as<float>();
     g.C = side_[side].encp.p; g.ldc = JOINT; g.epi = EPI_NONE;
+    // small batches, 3xTF32 (K' = 3072): 20 column tiles cannot keep the machine busy -- six K slices, slice 0 (+ bias) straight into the
+    // destination, the other five summed onto it by a small kernel (measured: 25.7 -> ~8 us at 128 rows)
+    constexpr int JS = 6;
+    const bool jsplit = !strict() && joint_enc_w_.scales.p && rows <= 256 && (size_t)(JS - 1) * rows * JOINT * 4 <= part_.bytes;
+    if (jsplit) { g.splits = JS; g.epi = EPI_PARTIAL; g.C0 = side_[side].encp.p; g.C = part_.p; }
     gemm_f32w(g, joint_enc_w_, false);
+    if (jsplit) {
+        const size_t n4 = (size_t)rows * JOINT / 4;
+        launch_k(add_planes_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st_, side_[side].encp.as<float>(), part_.as<const float>(), JS - 1,
+                 (size_t)rows * JOINT, n4);
+        count_launch();
+    }
 }
 
 // Y: the persistent greedy-decode kernel on stream `s`; narrow = a handful of CTA pairs instead of one CTA per SM (decode overlap)
@@ -978,12 +1063,15 @@ float Engine::bench_gemm(int kind, int rows, int bn, int stages, int splits, int
     if (strict()) throw std::runtime_error("bench_gemm: tensor-core modes only");
     if (rows < 1 || rows > max_streams * T || kind < 0 || kind > 5) throw std::invalid_argument("bench_gemm: bad arguments");
     NSB_CUDA(cudaSetDevice(device_));
+    const bool use_shadow = splits < 0 && shadow_mode(rows) && n_layers >= 2;
     auto pick = [&](LayerW& L) -> Weight& { switch (kind) { case 0: return L.ff1a; case 1: return L.ff1b; case 2: return L.qkv; case 3: return L.out; case 4: return L.pw1; default: return L.pw2; } };
     auto run = [&]() {
         for (int l = 0; l < n_layers; ++l) {
             Weight& W = pick(layers_[l]);
             if (splits < 0) {
-                // the step's own launch for this matrix: same tile choice, split-K rule, epilogue and (Q8_0 mode) dequantisation pass
+                // the step's own launch for this matrix: same tile choice, split-K rule and epilogue; Q8_0 at large batches: on the fp16
+                // shadow a layer-ahead dequantisation leaves (two shadows, filled once below: these launches time the GEMM alone)
+                if (use_shadow) cur_shadow_ = shadow_[l & 1].as<char>();
                 switch (kind) {
                     case 0: gemm(a_.p, D_MODEL, W, rows, nullptr, big_.p, D_FF, EPI_SILU, 1.f, act_type()); break;
                     case 2: if (split_consumers(rows)) gemm_planes(a_.p, D_MODEL, W, rows, qkv_.p, 2);
@@ -993,7 +1081,7 @@ float Engine::bench_gemm(int kind, int rows, int bn, int stages, int splits, int
                     case 1: gemm_residual(big_.p, D_FF, W, rows, x_.as<float>(), 0.5f); break;
                     default: gemm_residual(a_.p, D_MODEL, W, rows, x_.as<float>(), 1.f); break;
                 }
-                pending_ = PartialSum{};
+                pending_ = PartialSum{}; cur_shadow_ = nullptr;
                 continue;
             }
             GemmArgs a; a.A = W.n_in == D_FF ? big_.p : a_.p; a.lda = W.n_in; a.W = W.data.p; a.w_scales = W.scales.p; a.M = rows; a.N = W.n_out; a.K = W.n_in;
@@ -1006,6 +1094,7 @@ float Engine::bench_gemm(int kind, int rows, int bn, int stages, int splits, int
         }
     };
     if (splits > 1 && (size_t)splits * rows * pick(layers_[0]).n_out * 4 > part_.bytes) throw std::invalid_argument("bench_gemm: split workspace too small");
+    if (use_shadow) { collect_all(); join_decode_stream(); dequant_layer_async(0, st_); dequant_layer_async(1, st_); NSB_CUDA(cudaStreamSynchronize(st_)); }
     run();
     // One pass over the layers is captured into a CUDA graph, as the step is: stream launches of ~3 us kernels (two tensor-map
     // encodes + cudaLaunchKernelEx each) would time the host, not the kernel. NSB_BENCH_GEMM_GRAPH=0: plain stream launches.
@@ -1240,9 +1329,10 @@ long long Engine::transcribe_full(const int16_t* pcm, int n_samples, int32_t* to
     join_decode_stream();
     ensure_full_pos(Tq);
     ensure_batch_work(Tq, t2);
-    const int slot = open_stream();                                               // zeroed conv state, decoder state, prev_token = blank
+    const int slot = max_streams;                                                 // the batch path's private slot
+    zero_slot(slot);                                                              // zeroed conv state, decoder state, prev_token = blank
     swap_batch_work();                                                            // the step workspace (and the graphs captured on it) stays untouched
-    struct Release { Engine* e; int s; ~Release() { e->swap_batch_work(); e->hs_[s].open = false; } } release{this, slot};
+    struct Release { Engine* e; ~Release() { e->swap_batch_work(); } } release{this};
 
     // P: log-mel of the whole utterance (row = x[-1] = 0, the 256-zero left pad, the samples: preprocessor.cpp:220-221,349-356)
     const int row = 1 + N_FFT / 2 + n_samples;

@@ -40,6 +40,7 @@ struct HostPinned {
 // one GEMM weight in the engine's compute arithmetic
 struct Weight {
     std::string name; int n_out = 0, n_in = 0;
+    int shadow_slot = -1;   // Q8_0 mode: which of the layer's 8 matrices this is (offset into the fp16 shadow of the layer, see Engine::shadow_)
     DevBuf data;            // f32 / f16 / bf16 [n_out][n_in]; Q8_0 mode: int8 quants [n_out][n_in]
     DevBuf scales;          // Q8_0 mode only: fp16 block scales [n_out][n_in / 32]
 };
@@ -201,6 +202,14 @@ private:
 
     // ---- bench ----
     DevBuf q8s_scratch_;              // strict Q8_0: int8 rows + block scales of the A operand of one GEMM
+    // Q8_0 mode, large batches (>= 512 token rows: tensor-bound, every m-tile CTA of the fused kernel would repeat the dequantisation of
+    // the same weight tile): the layer's 8 matrices are dequantised ONE LAYER AHEAD on a side stream into one of two fp16 shadows
+    // (46 MB each), under the previous layer's kernels; HBM keeps holding (and streaming) the Q8_0 planes only.
+    DevBuf shadow_[2]; size_t shadow_off_[8] = {}; size_t shadow_bytes_ = 0;
+    cudaStream_t st_deq_ = nullptr; std::vector<cudaEvent_t> ev_deq_, ev_lstart_;
+    const char* cur_shadow_ = nullptr;                       // shadow of the layer whose GEMMs are being launched (nullptr: not in shadow mode)
+    bool shadow_mode(int rows) const;
+    void dequant_layer_async(int l, cudaStream_t s);
     DevBuf wscratch_;                 // fp16 copy of ONE Q8_0 matrix (large batches), rewritten before every GEMM that uses it
     DevBuf bench_pcm_; int bench_B_ = 0, bench_n_ = 1; long long bench_i_ = 0;   // [bench_n_][bench_B_][rl_] staged chunks, cycled
     const int16_t* bench_next_pcm();

@@ -136,6 +136,7 @@ struct DecodeArgs {
 // as CTA pairs, sharing the GPU with other kernels (decode overlap). Returns the grid size used
 int launch_decode(const DecodeArgs& a, void* sync_buf, cudaStream_t st, int narrow_ctas = 0);
 int decode_narrow_ctas();          // NSB_DECODE_CTAS, default 16
+bool decode_auto_overlap();        // whether the narrow decode is fast enough for the overlap to pay at <= 128 token rows (kernels_decode.cu)
 size_t decode_sync_bytes(int B);
 
 }  // namespace nsb

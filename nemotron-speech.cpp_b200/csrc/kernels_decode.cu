@@ -348,6 +348,11 @@ static int decode_grid() {                 // per device ordinal: the attribute 
 }
 size_t decode_sync_bytes(int B) { return 16 + (size_t)3 * B * sizeof(unsigned long long); }
 
+// Measured (profiles/r02_trace_overlap.txt): this kernel on 16 CTAs takes ~7x longer per round than on 148 (its items are staged one
+// at a time: a narrow grid walks 8 items per phase, each exposing one L2 round trip), i.e. 2-3 ms per step against a 1.7 ms encoder:
+// the overlap would make the decode the bottleneck. Automatic mode therefore stays off.
+bool decode_auto_overlap() { return false; }
+
 int decode_narrow_ctas() {
     static const int n = [] { const char* e = getenv("NSB_DECODE_CTAS"); const int v = e ? atoi(e) : 16; return std::max(2, v & ~1); }();
     return n;
