@@ -130,6 +130,7 @@ struct DecodeArgs {
     int* out_tokens; int* out_count;          // [B][MAX_SYMBOLS*T], [B]
     int* out_frames;                          // optional [B][MAX_SYMBOLS*T]: encoder frame (within this call's T) each token was emitted at (timed_token::frame_idx)
     unsigned* barrier; unsigned long long* best;   // filled by launch_decode from its sync buffer
+    int pipe_min_n;                           // filled by launch_decode: streams per phase from which the full-width grid uses the pipelined tiles
     float* logits_tap; int logits_tap_cap; int* logits_tap_n;   // optional: logits of batch row 0 per evaluation
 };
 // persistent kernel; sync_buf holds decode_sync_bytes(B) bytes. narrow_ctas = 0: one CTA per SM (cooperative launch); > 0: that many CTAs

@@ -48,7 +48,8 @@ constexpr int STAGE_FLOATS = 8 * 84 + 2 * 32 * 84;
 static_assert(STAGE_FLOATS >= (20 + 16) * 164, "staging region too small for the LSTM phase");
 
 struct DecSmem {
-    float stage[NW][STAGE_FLOATS];   // per-warp W / X slices; reused for the warp's partial tile
+    float stage[NW][STAGE_FLOATS];   // phase(): per-warp W / X slices, reused for the warp's partial tile; phase_pipe(): one flat ring of stages
+    unsigned long long keys[NW][32]; // phase_pipe() joint: per-warp argmax keys of a tile
     float sums[RC_MAX][RSTR];
     int slot[MAXB], prev[MAXB], list[MAXB];
     short fi[MAXB], oc[MAXB];        // frame index within the chunk, tokens emitted this step
@@ -246,12 +247,202 @@ __device__ void phase(const DecodeArgs& a, DecSmem& sm, int layer, int n, int ro
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// phase_pipe(): the same three skinny GEMMs as phase(), organised as a CTA-tiled SIMT GEMM behind a multi-stage cp.async ring.
+// phase() stages ONE item (a row slab x a stream block) per round trip to L2, which is fine when a CTA has one or two items per
+// phase (148 CTAs, a handful of streams) and poor otherwise: on a narrow grid (decode overlap: ~20 CTAs walk 8 items per phase) and
+// at large batches (many stream blocks per row slab) every item exposes its own L2 latency. Here the CTA walks a flat sequence of
+// (item, K chunk) steps; the loads of step q + NST - 1 are issued while step q is computed, across item boundaries, so L2 -> SM
+// streaming never stops inside a phase.
+//   tile: RT = 32 RPL weight rows x ST = 8 SPL streams; 8 warps x (4 row groups x 8 stream groups) lanes, RPL x SPL outputs per lane;
+//         LSTM: row group = gate (i, f, g, o), a warp owns RPL hidden units, the four gate sums of a unit meet by shuffle.
+//   K in 8 chunks (160 or 80 wide): chunk partial sums are formed from zero and added in chunk order -- exactly the summation order
+//   of phase() (its 8 warps own the same 8 K slices and are summed in warp order), so both paths, any grid size, give the same bits.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+    const unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, m), hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m);
+    return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int RPL, int SPL, int MODE>
+__device__ void phase_pipe(const DecodeArgs& a, DecSmem& sm, int layer, int n, int round, int ne0) {
+    constexpr int K = MODE == MODE_LSTM ? 2 * HID : HID, NCH = 8, KW = K / NCH, WS = KW + 4, VPR = KW / 4;
+    constexpr int RT = 32 * RPL, ST = 8 * SPL, XM = MODE == MODE_JOINT ? 2 : 1;
+    constexpr int STAGE_F = (RT + XM * ST) * WS;
+    constexpr int NST_FIT = NW * STAGE_FLOATS / STAGE_F, NST = NST_FIT > 6 ? 6 : NST_FIT;
+    static_assert(NST >= 3, "at least three stages in the ring");
+    const int rows_total = MODE == MODE_LSTM ? 4 * HID : MODE == MODE_PRED ? JOINT : VOCAB;
+    const int n_rt = (rows_total + RT - 1) / RT, n_sb = (n + ST - 1) / ST, n_items = n_rt * n_sb;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, rg = lane >> 3, sg = lane & 7;
+    const int my_items = (int)blockIdx.x < n_items ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int total_steps = my_items * NCH;
+    float* ring = &sm.stage[0][0];
+
+    // global row of tile row rr (LSTM: rr = warp (4 RPL) + gate RPL + i  <->  row gate * 640 + unit)
+    auto w_row = [&](int rt, int rr) -> int {
+        if (MODE == MODE_LSTM) { const int w = rr / (4 * RPL), q = (rr / RPL) & 3, i = rr % RPL; return q * HID + rt * (8 * RPL) + w * RPL + i; }
+        return min(rt * RT + rr, rows_total - 1);
+    };
+    auto issue = [&](int q) {
+        if (q < total_steps) {
+            const int item = (int)blockIdx.x + (q / NCH) * (int)gridDim.x, c = q % NCH;
+            const int rt = item % n_rt, s0 = (item / n_rt) * ST, ns = min(ST, n - s0);
+            float* st = ring + (q % NST) * STAGE_F;
+            for (int p = tid; p < RT * VPR; p += NT) {
+                const int rr = p / VPR, v = (p % VPR) * 4, row = w_row(rt, rr);
+                const float* src;
+                if (MODE == MODE_LSTM) src = (c < NCH / 2 ? a.w.w_ih[layer] : a.w.w_hh[layer]) + (size_t)row * HID + (c % (NCH / 2)) * KW + v;   // k < 640: input, k >= 640: recurrent
+                else src = (MODE == MODE_PRED ? a.w.pred_w : a.w.out_w) + (size_t)row * HID + c * KW + v;
+                cp_async16(st + rr * WS + v, src);
+            }
+            for (int p = tid; p < ns * VPR; p += NT) {
+                const int g = p / VPR, v = (p % VPR) * 4;
+                const int b = sm.list[s0 + g], slot = sm.slot[b], par = sm.par[b];
+                const float* hb = a.s.hbuf + (size_t)slot * 2 * PAR_STRIDE;
+                const float* src;
+                if (MODE == MODE_LSTM) {
+                    const int kc = (c % (NCH / 2)) * KW;
+                    if (c < NCH / 2) src = (layer == 0 ? a.w.embed + (size_t)sm.prev[b] * HID : hb + (par ^ 1) * PAR_STRIDE) + kc;      // nemo-stream.cpp:825-828 | layer-0 h'
+                    else src = hb + par * PAR_STRIDE + layer * HID + kc;                                                               // committed h of this layer
+                } else if (MODE == MODE_PRED) {
+                    src = hb + (par ^ 1) * PAR_STRIDE + HID + c * KW;                                                                   // candidate decoder output
+                } else {
+                    src = a.enc_proj + ((size_t)b * a.T + sm.fi[b]) * JOINT + c * KW;
+                    cp_async16(st + (RT + ST + g) * WS + v, a.s.dec_proj + (size_t)slot * JOINT + c * KW + v);
+                }
+                cp_async16(st + (RT + g) * WS + v, src + v);
+            }
+        }
+        cp_async_commit();                                                         // an empty group keeps the wait arithmetic uniform
+    };
+
+    for (int q = 0; q < NST - 1; ++q) issue(q);
+    float tot[RPL][SPL];
+    for (int q = 0; q < total_steps; ++q) {
+        const int item = (int)blockIdx.x + (q / NCH) * (int)gridDim.x, c = q % NCH;
+        const int rt = item % n_rt, s0 = (item / n_rt) * ST, ns = min(ST, n - s0);
+        float* st = ring + (q % NST) * STAGE_F;
+        cp_async_wait<NST - 2>();                                                 // this thread's copies of step q have landed
+        if (MODE == MODE_JOINT) {                                                 // z = relu(enc_proj + pred_proj) once per element (nemo-ggml.cpp:1092-1094), by the thread that copied it
+            for (int p = tid; p < ns * VPR; p += NT) {
+                const int g = p / VPR, v = (p % VPR) * 4;
+                float4 e = *reinterpret_cast<const float4*>(st + (RT + g) * WS + v);
+                const float4 d = *reinterpret_cast<const float4*>(st + (RT + ST + g) * WS + v);
+                e.x = fmaxf(e.x + d.x, 0.f); e.y = fmaxf(e.y + d.y, 0.f); e.z = fmaxf(e.z + d.z, 0.f); e.w = fmaxf(e.w + d.w, 0.f);
+                *reinterpret_cast<float4*>(st + (RT + g) * WS + v) = e;
+            }
+        }
+        __syncthreads();                                                          // step q visible to everyone; everyone is done with step q - 1
+        issue(q + NST - 1);                                                       // refills the buffer step q - 1 used
+        const float* wsm = st + (warp * 4 * RPL + rg * RPL) * WS;
+        const float* xsm = st + (RT + sg) * WS;
+        float acc[RPL][SPL];
+#pragma unroll
+        for (int i = 0; i < RPL; ++i)
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < KW; k += 4) {
+            float4 w[RPL], x[SPL];
+#pragma unroll
+            for (int i = 0; i < RPL; ++i) w[i] = *reinterpret_cast<const float4*>(wsm + i * WS + k);
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) x[j] = *reinterpret_cast<const float4*>(xsm + 8 * j * WS + k);
+#pragma unroll
+            for (int i = 0; i < RPL; ++i)
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) {
+                    acc[i][j] = fmaf(w[i].x, x[j].x, acc[i][j]); acc[i][j] = fmaf(w[i].y, x[j].y, acc[i][j]);
+                    acc[i][j] = fmaf(w[i].z, x[j].z, acc[i][j]); acc[i][j] = fmaf(w[i].w, x[j].w, acc[i][j]);
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < RPL; ++i)
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) tot[i][j] = c == 0 ? acc[i][j] : tot[i][j] + acc[i][j];   // chunk order = phase()'s warp order
+        if (c != NCH - 1) continue;
+        // ---------------- the item is complete ----------------
+        if (MODE == MODE_LSTM) {                                                  // gate order i,f,g,o (nemo-ggml.cpp:518-541)
+#pragma unroll
+            for (int i = 0; i < RPL; ++i)
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) {
+                    float gsum[4];
+#pragma unroll
+                    for (int qg = 0; qg < 4; ++qg) gsum[qg] = __shfl_sync(0xffffffffu, tot[i][j], qg * 8 + sg);
+                    const int g = sg + 8 * j;
+                    if (rg == (i & 3) && g < ns) {                                // one lane of the four finalises this (unit, stream)
+                        const int b = sm.list[s0 + g], slot = sm.slot[b], par = sm.par[b];
+                        const int u = rt * (8 * RPL) + warp * RPL + i;
+                        float gate[4];
+#pragma unroll
+                        for (int qg = 0; qg < 4; ++qg) gate[qg] = (gsum[qg] + __ldg(a.w.b_ih[layer] + qg * HID + u)) + __ldg(a.w.b_hh[layer] + qg * HID + u);
+                        const float ig = sigmoid_exact(gate[0]), fg = sigmoid_exact(gate[1]), gg = tanhf(gate[2]), og = sigmoid_exact(gate[3]);
+                        const size_t o_old = (size_t)slot * 2 * PAR_STRIDE + par * PAR_STRIDE + layer * HID + u;
+                        const size_t o_new = (size_t)slot * 2 * PAR_STRIDE + (par ^ 1) * PAR_STRIDE + layer * HID + u;
+                        const float cn = fg * __ldcg(a.s.cbuf + o_old) + ig * gg;
+                        a.s.cbuf[o_new] = cn; a.s.hbuf[o_new] = og * tanhf(cn);
+                    }
+                }
+        } else if (MODE == MODE_PRED) {                                           // joint.pred (nemo-ggml.cpp:1086-1087)
+#pragma unroll
+            for (int i = 0; i < RPL; ++i)
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) {
+                    const int g = sg + 8 * j, row = rt * RT + warp * 4 * RPL + rg * RPL + i;
+                    if (g < ns && row < JOINT) a.s.dec_proj[(size_t)sm.slot[sm.list[s0 + g]] * JOINT + row] = tot[i][j] + __ldg(a.w.pred_b + row);
+                }
+        } else {                                                                  // logits of this tile -> per-stream argmax key
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) {
+                const int g = sg + 8 * j;
+                unsigned long long key = 0ull;
+#pragma unroll
+                for (int i = 0; i < RPL; ++i) {
+                    const int v = rt * RT + warp * 4 * RPL + rg * RPL + i;
+                    if (v < VOCAB && g < ns) {
+                        const float sv = tot[i][j] + __ldg(a.w.out_b + v);
+                        const unsigned long long kk = argmax_key(sv, v);             // largest logit, ties to the lowest index (:847-854)
+                        key = kk > key ? kk : key;
+                        if (a.logits_tap && sm.list[s0 + g] == 0 && ne0 < a.logits_tap_cap) a.logits_tap[(size_t)ne0 * VOCAB + v] = sv;
+                    }
+                }
+                unsigned long long o = shfl_xor_u64(key, 8); key = o > key ? o : key;
+                o = shfl_xor_u64(key, 16); key = o > key ? o : key;
+                if (rg == 0) sm.keys[warp][g] = key;
+            }
+            __syncthreads();
+            if (tid < ns) {
+                unsigned long long key = sm.keys[0][tid];
+#pragma unroll
+                for (int w8 = 1; w8 < NW; ++w8) { const unsigned long long o = sm.keys[w8][tid]; key = o > key ? o : key; }
+                atomicMax(a.best + (size_t)(round % 3) * a.B + sm.list[s0 + tid], key);
+            }
+            // sm.keys is rewritten at the end of the NEXT item at the earliest: at least one step barrier lies in between
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();                                                              // the ring is free for whatever runs next
+}
+
 template <int MODE>
 __device__ __forceinline__ void phase_dispatch(const DecodeArgs& a, DecSmem& sm, int layer, int n, int round, int ne0) {
+    // one or two items per CTA and phase (full-width grid, a handful of streams): the one-shot staging of phase(); a narrow grid (decode
+    // overlap) or many stream blocks: the pipelined tiles. Same arithmetic, same bits (see phase_pipe).
+    const bool pipe = gridDim.x <= 64 || n >= a.pipe_min_n;
     constexpr int RPL = MODE == MODE_LSTM ? 5 : 2;
-    if (n <= 8) phase<RPL, 1, MODE>(a, sm, layer, n, round, ne0);
-    else if constexpr (MODE == MODE_LSTM) phase<RPL, 2, MODE>(a, sm, layer, n, round, ne0);
-    else { if (n <= 16) phase<RPL, 2, MODE>(a, sm, layer, n, round, ne0); else phase<RPL, 4, MODE>(a, sm, layer, n, round, ne0); }
+    if (!pipe) {
+        if (n <= 8) phase<RPL, 1, MODE>(a, sm, layer, n, round, ne0);
+        else phase<RPL, 2, MODE>(a, sm, layer, n, round, ne0);
+        return;
+    }
+    if (n <= 8) phase_pipe<1, 1, MODE>(a, sm, layer, n, round, ne0);
+    else if (n <= 16) phase_pipe<1, 2, MODE>(a, sm, layer, n, round, ne0);
+    else if (n <= 64) phase_pipe<1, 4, MODE>(a, sm, layer, n, round, ne0);        // more (smaller) tiles while the stream blocks are few
+    else phase_pipe<2, 4, MODE>(a, sm, layer, n, round, ne0);
 }
 
 __global__ void __launch_bounds__(NT, 1) rnnt_decode_kernel(const DecodeArgs a) {
@@ -366,6 +557,9 @@ int launch_decode(const DecodeArgs& a_in, void* sync_buf, cudaStream_t st, int n
     const int full = decode_grid();
     if (a_in.B > MAXB) throw CudaError("decode: more than 1024 streams in one step");
     DecodeArgs a = a_in;
+    // full-width grid: pipelined tiles from this many streams per phase on (below, one or two one-shot items per CTA are as good or better)
+    static const int pipe_n = [] { const char* e = getenv("NSB_DECODE_PIPE_N"); return e ? atoi(e) : 65; }();
+    a.pipe_min_n = pipe_n;
     a.barrier = reinterpret_cast<unsigned*>(sync_buf);
     a.best = reinterpret_cast<unsigned long long*>((char*)sync_buf + 16);
     NSB_CUDA(cudaMemsetAsync(sync_buf, 0, decode_sync_bytes(a.B), st));           // barrier counter + argmax keys
