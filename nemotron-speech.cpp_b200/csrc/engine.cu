@@ -424,7 +424,7 @@ void Engine::alloc_state() {
     // conv / decoder state of its own whatever the streams are doing
     const size_t SS = (size_t)S + 1;
     kv_.alloc(SS * n_layers * 2 * Cap * D_MODEL * kv_elem_size(kv_dtype));               // zero-initialised (nemo-stream.cpp:292-297)
-    conv_cache_.alloc(SS * n_layers * (CONV_K - 1) * D_MODEL * 4);
+    conv_cache_.alloc(SS * 2 * n_layers * (CONV_K - 1) * D_MODEL * 4); cc_par_.alloc(SS * 4);
     mel_hist_.alloc(SS * PRE_CACHE * N_MELS * 4);                                         // 9 zero frames (:59-60)
     ring_pos_.alloc(SS * 4); valid_len_.alloc(SS * 4);
     dec_h_.alloc(SS * 4 * HID * 4); dec_c_.alloc(SS * 4 * HID * 4);                      // [S][2 parities][2 layers][640]
@@ -482,8 +482,9 @@ void Engine::zero_slot(int s) {
     const int Cap = ATT_L + T;
     const size_t kvb = (size_t)n_layers * 2 * Cap * D_MODEL * kv_elem_size(kv_dtype);
     NSB_CUDA(cudaMemsetAsync((char*)kv_.p + (size_t)s * kvb, 0, kvb, st_));
-    const size_t cb = (size_t)n_layers * (CONV_K - 1) * D_MODEL * 4;
+    const size_t cb = (size_t)2 * n_layers * (CONV_K - 1) * D_MODEL * 4;
     NSB_CUDA(cudaMemsetAsync((char*)conv_cache_.p + (size_t)s * cb, 0, cb, st_));
+    NSB_CUDA(cudaMemsetAsync((char*)cc_par_.p + (size_t)s * 4, 0, 4, st_));
     NSB_CUDA(cudaMemsetAsync((char*)mel_hist_.p + (size_t)s * PRE_CACHE * N_MELS * 4, 0, (size_t)PRE_CACHE * N_MELS * 4, st_));
     NSB_CUDA(cudaMemsetAsync((char*)dec_h_.p + (size_t)s * 4 * HID * 4, 0, (size_t)4 * HID * 4, st_));
     NSB_CUDA(cudaMemsetAsync((char*)dec_c_.p + (size_t)s * 4 * HID * 4, 0, (size_t)4 * HID * 4, st_));
@@ -607,12 +608,11 @@ void Engine::gemm_residual(const void* A, long long lda, const Weight& W, int M,
         const int nk = W.n_in / 64;
         while (splits < MAX_SPLITS && tiles * splits < 120 && nk % (splits * 2) == 0 && nk / (splits * 2) >= 2) splits *= 2;
     }
-    // Large batches, K = 4096 (FFN down-projections): with 14 x 8 tiles the N = 1024 GEMM cannot fill the machine with tiles wide
-    // enough to stay off the L2 -> SM ingest limit; four K slices on 256 x 256 pair tiles can (4 x 7 x 4 = 112 pairs). Measured at
-    // 256 streams x 560 ms: step 7.39 -> 7.23 ms with 4 slices (2 slices: 7.35 at BN = 208, 7.56 at BN = 256). NSB_FFDOWN_SPLIT=1: off.
-    static const int big_split = [] { const char* e = getenv("NSB_FFDOWN_SPLIT"); return e ? atoi(e) : 4; }();
-    // (not in Q8_0 mode: behind the per-launch dequantisation the split measured slower, 7.83 -> 7.96 ms)
-    if ((compute == NSB_COMPUTE_F16 || compute == NSB_COMPUTE_BF16) && M > 1024 && W.n_in >= 4096 && big_split > 1 && (size_t)big_split * M * D_MODEL * 4 <= part_.bytes) splits = big_split;
+    // Large batches, K = 4096 (FFN down-projections): with 7 x 8 tiles the N = 1024 GEMM cannot fill the machine. Two K slices on 256 x 112
+    // pair tiles = 7 x 10 x 2 = 140 tiles for the 148 co-resident pair slots; measured at 1792 rows (profiles/r02_gemm_sweep.txt):
+    // 15.2 us (987 TFLOP/s) against 17.4 us for four slices of 256 x 256 tiles and 21.6 us unsplit. NSB_FFDOWN_SPLIT=1: off.
+    static const int big_split = [] { const char* e = getenv("NSB_FFDOWN_SPLIT"); return e ? atoi(e) : 2; }();
+    if (!strict() && M > 1024 && W.n_in >= 4096 && big_split > 1 && (size_t)big_split * M * D_MODEL * 4 <= part_.bytes) splits = big_split;
     if (splits == 1) { gemm(A, lda, W, M, nullptr, x, D_MODEL, EPI_RESID, alpha, OUT_F32); return; }
     GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.w_scales = W.scales.p; a.M = M; a.N = W.n_out; a.K = W.n_in; a.C = part_.p; a.ldc = D_MODEL;
     a.epi = EPI_PARTIAL; a.out_type = OUT_F32; a.splits = splits;
@@ -857,7 +857,7 @@ void Engine::run_encoder_kernels(int B, const int16_t* d_pcm, int side) {
 
     // L: cache-aware conformer layers
     const long long kv_slot_stride = (long long)n_layers * 2 * (ATT_L + T) * D_MODEL;
-    const long long cc_slot_stride = (long long)n_layers * (CONV_K - 1) * D_MODEL;
+    const long long cc_par_stride = (long long)n_layers * (CONV_K - 1) * D_MODEL, cc_slot_stride = 2 * cc_par_stride;
     auto ln = [&](const float* g_, const float* b_) {
         if (skip & SK_LN) { pending_ = PartialSum{}; return; }
         ProfScope ps(this, PC_LAYERNORM); launch_layernorm(x, rows, g_, b_, a_.p, at, pending_, st_); count_launch(); pending_ = PartialSum{};
@@ -922,7 +922,8 @@ void Engine::run_encoder_kernels(int B, const int16_t* d_pcm, int side) {
         }
         if (!(skip & SK_CONV)) {
             ConvModArgs ca; ca.pw1 = pw1_.as<float>(); ca.planes = pw1_planes; ca.plane_stride = (long long)rows * 2 * D_MODEL; ca.conv_cache = conv_cache_.as<float>() + (size_t)l * (CONV_K - 1) * D_MODEL;
-            ca.slot_stride = cc_slot_stride; ca.dw_w = L.dw_w.as<float>(); ca.ln_g = L.cln_g.as<float>(); ca.ln_b = L.cln_b.as<float>();
+            ca.slot_stride = cc_slot_stride; ca.par_stride = cc_par_stride; ca.cc_par = cc_par_.as<int>();
+            ca.dw_w = L.dw_w.as<float>(); ca.ln_g = L.cln_g.as<float>(); ca.ln_b = L.cln_b.as<float>();
             ca.out = a_.p; ca.out_type = at; ca.slot_of_b = slot; ca.B = B; ca.T = T;
             ProfScope ps(this, PC_CONVMOD); launch_conv_module(ca, st_); count_launch();
         }
@@ -943,7 +944,7 @@ void Engine::run_encoder_kernels(int B, const int16_t* d_pcm, int side) {
                                              cudaMemcpyDeviceToDevice, st_));
     }
     cur_shadow_ = nullptr;
-    { ProfScope ps(this, PC_MISC); launch_advance_streams(slot, B, T, ring_pos_.as<int>(), valid_len_.as<int>(), st_); count_launch(); }
+    { ProfScope ps(this, PC_MISC); launch_advance_streams(slot, B, T, ring_pos_.as<int>(), valid_len_.as<int>(), cc_par_.as<int>(), st_); count_launch(); }
 
     // G: joint.enc for all frames (the decode kernel reads them from this side's buffer)
     if (skip & SK_DECODE) return;
@@ -1223,7 +1224,8 @@ long long Engine::debug_get_cache(int stream, int which, int layer, float* out, 
     NSB_CUDA(cudaStreamSynchronize(st_));
     if (which == 2) {
         const size_t n = (size_t)(CONV_K - 1) * D_MODEL; if (cap < n) return -(long long)n;
-        NSB_CUDA(cudaMemcpy(out, conv_cache_.as<float>() + ((size_t)stream * n_layers + layer) * n, n * 4, cudaMemcpyDeviceToHost));
+        int par = 0; NSB_CUDA(cudaMemcpy(&par, cc_par_.as<int>() + stream, 4, cudaMemcpyDeviceToHost));      // the parity the last step wrote = the current one
+        NSB_CUDA(cudaMemcpy(out, conv_cache_.as<float>() + (((size_t)stream * 2 + (par & 1)) * n_layers + layer) * n, n * 4, cudaMemcpyDeviceToHost));
         return (long long)n;
     }
     // K / V: return the 70 cache rows in logical order (oldest first), as the reference's rolled cache holds them
@@ -1369,7 +1371,7 @@ long long Engine::transcribe_full(const int16_t* pcm, int n_samples, int32_t* to
     }
 
     // L: the layers of build_conformer_layer (nemo-ggml.cpp:768-818) on the cached-layer kernels
-    const long long cc_slot_stride = (long long)n_layers * (CONV_K - 1) * D_MODEL;
+    const long long cc_par_stride = (long long)n_layers * (CONV_K - 1) * D_MODEL, cc_slot_stride = 2 * cc_par_stride;
     auto ln = [&](const float* g_, const float* b_) { launch_layernorm(x, rows, g_, b_, a_.p, at, pending_, st_); count_launch(); pending_ = PartialSum{}; };
     ln(layers_[0].ln[0].as<float>(), layers_[0].ln[1].as<float>());
     for (int l = 0; l < n_layers; ++l) {
@@ -1389,6 +1391,7 @@ long long Engine::transcribe_full(const int16_t* pcm, int n_samples, int32_t* to
         {
             ConvModArgs ca; ca.pw1 = pw1_.as<float>(); ca.planes = 1; ca.plane_stride = (long long)rows * 2 * D_MODEL;
             ca.conv_cache = conv_cache_.as<float>() + (size_t)l * (CONV_K - 1) * D_MODEL; ca.slot_stride = cc_slot_stride;
+            ca.par_stride = cc_par_stride; ca.cc_par = cc_par_.as<int>();
             ca.dw_w = L.dw_w.as<float>(); ca.ln_g = L.cln_g.as<float>(); ca.ln_b = L.cln_b.as<float>();
             ca.out = a_.p; ca.out_type = at; ca.slot_of_b = slot_dev; ca.B = 1; ca.T = rows;
             launch_conv_module(ca, st_); count_launch();

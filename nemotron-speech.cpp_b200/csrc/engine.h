@@ -184,7 +184,7 @@ private:
 
     // ---- per-slot state ----
     DevBuf kv_;                    // [S][layers][2][L+T][1024] kv dtype
-    DevBuf conv_cache_;            // [S][layers][8][1024] f32
+    DevBuf conv_cache_, cc_par_;   // conv state [S + 1][2 parities][layers][8][1024] f32, current parity [S + 1] (kernels.cuh: ConvModArgs)
     DevBuf mel_hist_;              // [S][9][128]
     DevBuf ring_pos_, valid_len_;  // [S] int
     DevBuf dec_h_, dec_c_, dec_par_, dec_proj_, prev_token_, cand_valid_;

@@ -1004,7 +1004,7 @@ void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
     if (a.splits > 1) {
         if (a.epi != EPI_PARTIAL || (a.K / BK) % a.splits != 0) throw CudaError("gemm_tc: bad split-K request");
         if (fmt != 2 && tiles_m >= 8 && pair256_enabled()) {            // large-batch split-K (FFN down): wide pair tiles
-            static const int bn = [] { const char* e = getenv("NSB_SPLIT_BN"); return e ? atoi(e) : 256; }();
+            static const int bn = [] { const char* e = getenv("NSB_SPLIT_BN"); return e ? atoi(e) : 112; }();
             launch_pair256(a, fmt, bn, st); return;
         }
         if (a.N % 128 == 0 && a.M > 128 && fmt == 2) { launch_cfg<128, 4>(a, fmt, st); return; }
@@ -1018,7 +1018,10 @@ void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
     // speed up and the next kernel loses its early residency, profiles/r01_notes.md)
     if (fmt != 2 && a.pair && !a.w_dynamic && pair_gemm_enabled() && tiles_m == 1 && a.N % 64 == 0) { launch_cfg_pair<64, 8>(a, fmt, st); return; }
     // >= 4 row tiles, 16-bit operands: 256-row CTA-pair tiles (the single-CTA tile is L2 -> SM ingest bound there)
-    if (fmt != 2 && tiles_m >= pair256_min_tiles() && pair256_enabled()) {
+    // (not for the small square matrices at > 1024 rows -- attention out-projection, pointwise-2: 128 x 128 single-CTA tiles, 4 stages,
+    //  measured 7.8 us against 9.0-9.3 us for the best pair tile at 1792 rows, profiles/r02_gemm_sweep.txt)
+    const bool small_square = a.N <= 1024 && a.K <= 1024 && tiles_m >= 8;
+    if (fmt != 2 && tiles_m >= pair256_min_tiles() && pair256_enabled() && !small_square) {
         const int bn = pick_pair256_bn(a.M, a.N);
         if (bn) { launch_pair256(a, fmt, bn, st); return; }
     }

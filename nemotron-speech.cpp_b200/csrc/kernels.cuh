@@ -99,8 +99,11 @@ bool pair_gemm_enabled();         // gemm_tc.cu: CTA-pair tiles on (default) / o
 struct ConvModArgs {
     const float* pw1;             // [planes][M][2048] f32  (a | gate); planes > 1 = split-K partials of the pointwise GEMM, summed on load
     int planes = 1; long long plane_stride = 0;
-    float* conv_cache;            // layer base; (slot, r, c) at slot*slot_stride + r*1024 + c, r in 0..7
+    float* conv_cache;            // layer base; (slot, parity, r, c) at slot*slot_stride + parity*par_stride + r*1024 + c, r in 0..7
     long long slot_stride;
+    // the state is double-buffered per slot: a step reads parity cc_par[slot] and writes the other one (every frame of the chunk is its
+    // own CTA: the writer must not overwrite what CTAs of earlier frames still read); launch_advance_streams flips the parity
+    const int* cc_par; long long par_stride;
     const float* dw_w;            // [9][1024] tap-major (GGUF layout)
     const float* ln_g; const float* ln_b;
     void* out; int out_type;      // [M][1024]
@@ -108,7 +111,7 @@ struct ConvModArgs {
 };
 void launch_conv_module(const ConvModArgs& a, cudaStream_t st);
 
-void launch_advance_streams(const int* slot_of_b, int B, int T, int* ring_pos, int* valid_len, cudaStream_t st);
+void launch_advance_streams(const int* slot_of_b, int B, int T, int* ring_pos, int* valid_len, int* cc_par, cudaStream_t st);
 
 // ---------------------------------------------------------------- RNN-T decode (kernels_decode.cu)
 struct DecodeWeights {

@@ -886,15 +886,21 @@ void launch_attention(const AttnArgs& a, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Conv module core: GLU -> cached causal depthwise conv (k = 9) -> LayerNorm -> SiLU, cache updated in place.
-// One CTA per batch row (stream), 256 threads x 4 channels, a 9-deep register window slides over time.
+// Conv module core: GLU -> cached causal depthwise conv (k = 9) -> LayerNorm -> SiLU, and the new conv state.
+// One CTA per (frame t, stream): 256 threads x 4 channels. Output frame t needs xp[t .. t + 8] of xp = [state (8 rows) || glu (T rows)]
+// (:323-328), i.e. up to 9 GLU rows recomputed from the pointwise-1 output (36 sigmoids per thread: nothing next to walking the T
+// frames of a chunk one after the other, as the first version did: 17 us per layer at T = 14, and T = 2048 in the batch path).
+// The CTA of the LAST frame holds xp[T - 1 .. T + 7] and therefore writes the new state xp[T .. T + 7] (:368-381) -- into the OTHER
+// parity of the double-buffered state, because the CTAs of earlier frames may still be reading the old one.
+// Same tap order, same LayerNorm as before: bit-identical results.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv_module_kernel(const ConvModArgs a) {
     NSB_KERNEL_BEGIN(TR_CONVMOD)                                                  // taps, conv state (written by this layer's kernel of earlier steps only), LN affine: pre-wait
     __shared__ float red[16];
-    const int b = blockIdx.x, c0 = threadIdx.x * 4, T = a.T;
-    const int slot = a.slot_of_b[b];
-    float* cache = a.conv_cache + (size_t)slot * a.slot_stride;
+    const int t = blockIdx.x, b = blockIdx.y, c0 = threadIdx.x * 4, T = a.T;
+    const int slot = a.slot_of_b[b], par = a.cc_par[slot] & 1;
+    const float* cache = a.conv_cache + (size_t)slot * a.slot_stride + (size_t)par * a.par_stride;
+    float* cache_new = a.conv_cache + (size_t)slot * a.slot_stride + (size_t)(par ^ 1) * a.par_stride;
     float win[4][CONV_K];
     float wk[4][CONV_K];
 #pragma unroll
@@ -903,71 +909,77 @@ __global__ void __launch_bounds__(256) conv_module_kernel(const ConvModArgs a) {
         wk[0][k] = w4.x; wk[1][k] = w4.y; wk[2][k] = w4.z; wk[3][k] = w4.w;
     }
 #pragma unroll
-    for (int k = 0; k < CONV_K - 1; ++k) {                                       // xp = [cache(8) || glu(T)] :323-328
-        const float4 v = *(const float4*)(cache + (size_t)k * D_MODEL + c0);
-        win[0][k] = v.x; win[1][k] = v.y; win[2][k] = v.z; win[3][k] = v.w;
+    for (int k = 0; k < CONV_K; ++k) {                                           // window rows that come from the state: xp[t + k], t + k < 8
+        if (t + k < CONV_K - 1) {
+            const float4 v = *(const float4*)(cache + (size_t)(t + k) * D_MODEL + c0);
+            win[0][k] = v.x; win[1][k] = v.y; win[2][k] = v.z; win[3][k] = v.w;
+        }
     }
     const float4 g4 = *(const float4*)(a.ln_g + c0), b4 = *(const float4*)(a.ln_b + c0);
     const float lg[4] = {g4.x, g4.y, g4.z, g4.w}, lb[4] = {b4.x, b4.y, b4.z, b4.w};
     NSB_KERNEL_WAIT()
     const float* row0 = a.pw1 + (size_t)b * T * 2 * D_MODEL;
-    float4 av = ld4_planes<PW1_MAX_PLANES>(row0 + c0, a.planes, a.plane_stride), gv = ld4_planes<PW1_MAX_PLANES>(row0 + D_MODEL + c0, a.planes, a.plane_stride);
-    for (int t = 0; t < T; ++t) {
-        float4 av_n = av, gv_n = gv;
-        if (t + 1 < T) {                                                         // next row's loads overlap this row's reductions
-            const float* rn = row0 + (size_t)(t + 1) * 2 * D_MODEL;
-            av_n = ld4_planes<PW1_MAX_PLANES>(rn + c0, a.planes, a.plane_stride); gv_n = ld4_planes<PW1_MAX_PLANES>(rn + D_MODEL + c0, a.planes, a.plane_stride);
+    float4 av[CONV_K], gv[CONV_K];
+#pragma unroll
+    for (int k = 0; k < CONV_K; ++k) {                                           // all loads of the window in flight before the first sigmoid
+        const int r = t + k - (CONV_K - 1);                                      // GLU row of window position k
+        if (r >= 0) {
+            const float* rp = row0 + (size_t)r * 2 * D_MODEL;
+            av[k] = ld4_planes<PW1_MAX_PLANES>(rp + c0, a.planes, a.plane_stride); gv[k] = ld4_planes<PW1_MAX_PLANES>(rp + D_MODEL + c0, a.planes, a.plane_stride);
         }
-        win[0][8] = av.x * sigmoid_exact(gv.x); win[1][8] = av.y * sigmoid_exact(gv.y);   // GLU :629-636
-        win[2][8] = av.z * sigmoid_exact(gv.z); win[3][8] = av.w * sigmoid_exact(gv.w);
-        float cv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {                                            // :341-360
-            float acc = win[u][0] * wk[u][0];
-#pragma unroll
-            for (int k = 1; k < CONV_K; ++k) acc = fmaf(win[u][k], wk[u][k], acc);
-            cv[u] = acc;
-        }
-        float mean, var, dd[4];                                                  // LN :643-645
-        if (a.out_type == OUT_F32) {
-            mean = block_sum_256(cv[0] + cv[1] + cv[2] + cv[3], red) * (1.0f / D_MODEL);
-            float sq = 0.f;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { const float e = cv[u] - mean; sq += e * e; }
-            var = block_sum_256(sq, red) * (1.0f / D_MODEL);
-        } else block_mean_var_256(cv[0], cv[1], cv[2], cv[3], red, mean, var);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) dd[u] = cv[u] - mean;
-        const float rs = 1.0f / sqrtf(var + 1e-5f);
-        const size_t o = ((size_t)b * T + t) * D_MODEL + c0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) store_out(a.out, o + u, silu_exact(dd[u] * rs * lg[u] + lb[u]), a.out_type);   // SiLU :646
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int k = 0; k < CONV_K - 1; ++k) win[u][k] = win[u][k + 1];
-        av = av_n; gv = gv_n;
     }
 #pragma unroll
-    for (int k = 0; k < CONV_K - 1; ++k)                                         // new cache = last 8 rows of xp :368-381
-        *(float4*)(cache + (size_t)k * D_MODEL + c0) = make_float4(win[0][k], win[1][k], win[2][k], win[3][k]);
+    for (int k = 0; k < CONV_K; ++k) {
+        if (t + k - (CONV_K - 1) >= 0) {                                         // GLU :629-636
+            win[0][k] = av[k].x * sigmoid_exact(gv[k].x); win[1][k] = av[k].y * sigmoid_exact(gv[k].y);
+            win[2][k] = av[k].z * sigmoid_exact(gv[k].z); win[3][k] = av[k].w * sigmoid_exact(gv[k].w);
+        }
+    }
+    float cv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {                                                // :341-360
+        float acc = win[u][0] * wk[u][0];
+#pragma unroll
+        for (int k = 1; k < CONV_K; ++k) acc = fmaf(win[u][k], wk[u][k], acc);
+        cv[u] = acc;
+    }
+    float mean, var, dd[4];                                                      // LN :643-645
+    if (a.out_type == OUT_F32) {
+        mean = block_sum_256(cv[0] + cv[1] + cv[2] + cv[3], red) * (1.0f / D_MODEL);
+        float sq = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const float e = cv[u] - mean; sq += e * e; }
+        var = block_sum_256(sq, red) * (1.0f / D_MODEL);
+    } else block_mean_var_256(cv[0], cv[1], cv[2], cv[3], red, mean, var);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) dd[u] = cv[u] - mean;
+    const float rs = 1.0f / sqrtf(var + 1e-5f);
+    const size_t o = ((size_t)b * T + t) * D_MODEL + c0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) store_out(a.out, o + u, silu_exact(dd[u] * rs * lg[u] + lb[u]), a.out_type);   // SiLU :646
+    if (t == T - 1) {                                                            // new state = last 8 rows of xp = window positions 1 .. 8 of the last frame :368-381
+#pragma unroll
+        for (int k = 0; k < CONV_K - 1; ++k)
+            *(float4*)(cache_new + (size_t)k * D_MODEL + c0) = make_float4(win[0][k + 1], win[1][k + 1], win[2][k + 1], win[3][k + 1]);
+    }
     NSB_KERNEL_EPILOGUE();
 }
 void launch_conv_module(const ConvModArgs& a, cudaStream_t st) {
-    if (a.B > 0) launch_k(conv_module_kernel, dim3(a.B), dim3(256), 0, st, a);
+    if (a.B > 0 && a.T > 0) launch_k(conv_module_kernel, dim3(a.T, a.B), dim3(256), 0, st, a);
 }
 
-__global__ void advance_streams_kernel(const int* __restrict__ slot_of_b, int B, int T, int* ring_pos, int* valid_len) {
+__global__ void advance_streams_kernel(const int* __restrict__ slot_of_b, int B, int T, int* ring_pos, int* valid_len, int* cc_par) {
     NSB_KERNEL_PROLOGUE(TR_ADVANCE)
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int s = slot_of_b[b];
     ring_pos[s] = (ring_pos[s] + T) % (ATT_L + T);
     valid_len[s] = min(valid_len[s] + T, ATT_L);                                 // :1018
+    cc_par[s] ^= 1;                                                              // every layer's conv module wrote the other parity of the conv state
     NSB_KERNEL_EPILOGUE();
 }
-void launch_advance_streams(const int* slot_of_b, int B, int T, int* ring_pos, int* valid_len, cudaStream_t st) {
-    if (B > 0) launch_k(advance_streams_kernel, dim3((B + 127) / 128), dim3(128), 0, st, slot_of_b, B, T, ring_pos, valid_len);
+void launch_advance_streams(const int* slot_of_b, int B, int T, int* ring_pos, int* valid_len, int* cc_par, cudaStream_t st) {
+    if (B > 0) launch_k(advance_streams_kernel, dim3((B + 127) / 128), dim3(128), 0, st, slot_of_b, B, T, ring_pos, valid_len, cc_par);
 }
 
 // ------------------------------------------------------------------------------------------
