@@ -1018,10 +1018,10 @@ void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
     // speed up and the next kernel loses its early residency, profiles/r01_notes.md)
     if (fmt != 2 && a.pair && !a.w_dynamic && pair_gemm_enabled() && tiles_m == 1 && a.N % 64 == 0) { launch_cfg_pair<64, 8>(a, fmt, st); return; }
     // >= 4 row tiles, 16-bit operands: 256-row CTA-pair tiles (the single-CTA tile is L2 -> SM ingest bound there)
-    // (not for the small square matrices at > 1024 rows -- attention out-projection, pointwise-2: 128 x 128 single-CTA tiles, 4 stages,
-    //  measured 7.8 us against 9.0-9.3 us for the best pair tile at 1792 rows, profiles/r02_gemm_sweep.txt)
-    const bool small_square = a.N <= 1024 && a.K <= 1024 && tiles_m >= 8;
-    if (fmt != 2 && tiles_m >= pair256_min_tiles() && pair256_enabled() && !small_square) {
+    // (the small square matrices -- attention out-projection, pointwise-2 -- measured 7.8 us on 128 x 128 single-CTA tiles against 9.0 us
+    //  on the best pair tile at 1792 rows with a plain store epilogue, profiles/r02_gemm_sweep.txt, but no faster with the residual
+    //  read-modify-write epilogue they run with in the step: left on the pair tiles)
+    if (fmt != 2 && tiles_m >= pair256_min_tiles() && pair256_enabled()) {
         const int bn = pick_pair256_bn(a.M, a.N);
         if (bn) { launch_pair256(a, fmt, bn, st); return; }
     }

@@ -104,7 +104,105 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* x, const float* _
     else { __nv_bfloat162* p = (__nv_bfloat162*)((__nv_bfloat16*)y + o); p[0] = __floats2bfloat162_rn(o0, o1); p[1] = __floats2bfloat162_rn(o2, o3); }
     NSB_KERNEL_EPILOGUE();
 }
+
+// ------------------------------------------------------------------------------------------
+// Large batches (> 512 rows, 16-bit modes): one WARP per row instead of one CTA per row. A lane owns 8 float4 of the row (all eight
+// loads -- and those of each split-K plane -- in flight at once), statistics by the same pairwise (mean, M2) merge through five
+// shuffles, no shared memory, no block barrier; 8 rows per CTA. At 1792 rows the one-CTA-per-row kernels spend most of their time in
+// two block-wide barriers per row with 1792 CTAs in flight; this form is bound by its L2 traffic. g2 != nullptr: the fused pair
+// norm_out -> norm_feed_forward1 of the next layer (layernorm2_kernel); y == nullptr with g2 == nullptr: norm_out of the last layer.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_mean_var_1024(const float4 (&v)[8], float& mean, float& var) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    float m = s * (1.0f / 32.0f), M2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float a = v[j].x - m, b = v[j].y - m, c = v[j].z - m, d = v[j].w - m; M2 += (a * a + b * b) + (c * c + d * d); }
+    float half_n = 16.0f;                                                         // n / 2 of each of the two groups being merged
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float mo = __shfl_xor_sync(0xffffffffu, m, o), M2o = __shfl_xor_sync(0xffffffffu, M2, o);
+        const float d = mo - m;
+        M2 = (M2 + M2o) + d * d * half_n; m = m + 0.5f * d; half_n *= 2.0f;
+    }
+    mean = m; var = M2 * (1.0f / D_MODEL);
+}
+__device__ __forceinline__ void store4_out(void* y, size_t o, float4 r, int out_type) {
+    if (out_type == OUT_F32) *(float4*)((float*)y + o) = r;
+    else if (out_type == OUT_F16) { __half2* p = (__half2*)((__half*)y + o); p[0] = __floats2half2_rn(r.x, r.y); p[1] = __floats2half2_rn(r.z, r.w); }
+    else { __nv_bfloat162* p = (__nv_bfloat162*)((__nv_bfloat16*)y + o); p[0] = __floats2bfloat162_rn(r.x, r.y); p[1] = __floats2bfloat162_rn(r.z, r.w); }
+}
+
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(float* x, int rows, const float* __restrict__ g1, const float* __restrict__ b1,
+                                                             const float* __restrict__ g2, const float* __restrict__ b2, void* y, int out_type,
+                                                             const PartialSum ps) {
+    NSB_KERNEL_BEGIN(g2 ? TR_LN2 : TR_LN)
+    const int lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    NSB_KERNEL_WAIT()
+    if (row >= rows) return;                                                      // warp-uniform
+    float* xr = x + (size_t)row * D_MODEL;
+    float4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = *(const float4*)(xr + 4 * (32 * j + lane));
+    if (ps.n > 0) {                                                               // fold the split-K partials of the previous GEMM: x += alpha * (p0 + p1 + ...), slice order
+        float4 acc[8];
+        for (int sl = 0; sl < ps.n; ++sl) {
+            const float* pr = ps.part + ((size_t)sl * rows + row) * D_MODEL;
+            float4 t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = __ldcg((const float4*)(pr + 4 * (32 * j + lane)));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (sl == 0) { acc[j] = make_float4(0.f + t[j].x, 0.f + t[j].y, 0.f + t[j].z, 0.f + t[j].w); }
+                else { acc[j].x += t[j].x; acc[j].y += t[j].y; acc[j].z += t[j].z; acc[j].w += t[j].w; }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[j].x += ps.alpha * acc[j].x; v[j].y += ps.alpha * acc[j].y; v[j].z += ps.alpha * acc[j].z; v[j].w += ps.alpha * acc[j].w; }
+        if (!g2 && y) {                                                           // plain LayerNorm: x keeps the reduced residual stream
+#pragma unroll
+            for (int j = 0; j < 8; ++j) *(float4*)(xr + 4 * (32 * j + lane)) = v[j];
+        }
+    }
+    float mean, var;
+    warp_mean_var_1024(v, mean, var);
+    float rs = 1.0f / sqrtf(var + 1e-5f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 gg = *(const float4*)(g1 + 4 * (32 * j + lane)), bb = *(const float4*)(b1 + 4 * (32 * j + lane));
+        v[j] = make_float4((v[j].x - mean) * rs * gg.x + bb.x, (v[j].y - mean) * rs * gg.y + bb.y, (v[j].z - mean) * rs * gg.z + bb.z, (v[j].w - mean) * rs * gg.w + bb.w);
+    }
+    if (!g2 && y) {                                                               // LN(x) -> y (operand of the next GEMM)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) store4_out(y, (size_t)row * D_MODEL + 4 * (32 * j + lane), v[j], out_type);
+        NSB_KERNEL_EPILOGUE();
+        return;
+    }
+    // norm_out: x <- LN1(x) (f32, in place) ...
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *(float4*)(xr + 4 * (32 * j + lane)) = v[j];
+    if (g2) {                                                                     // ... and y <- LN2(x) for the next layer's first GEMM
+        warp_mean_var_1024(v, mean, var);
+        rs = 1.0f / sqrtf(var + 1e-5f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 gg = *(const float4*)(g2 + 4 * (32 * j + lane)), bb = *(const float4*)(b2 + 4 * (32 * j + lane));
+            const float4 r = make_float4((v[j].x - mean) * rs * gg.x + bb.x, (v[j].y - mean) * rs * gg.y + bb.y, (v[j].z - mean) * rs * gg.z + bb.z, (v[j].w - mean) * rs * gg.w + bb.w);
+            store4_out(y, (size_t)row * D_MODEL + 4 * (32 * j + lane), r, out_type);
+        }
+    }
+    NSB_KERNEL_EPILOGUE();
+}
+static bool ln_rows_enabled(int rows, int out_type) {
+    static const int min_rows = [] { const char* e = getenv("NSB_LN_ROWS_MIN"); return e ? atoi(e) : 513; }();
+    return out_type != OUT_F32 && rows >= min_rows;                               // strict fp32 keeps the two-pass block kernels
+}
 void launch_layernorm(float* x, int rows, const float* g, const float* b, void* y, int out_type, const PartialSum& ps, cudaStream_t st) {
+    if (rows > 0 && ln_rows_enabled(rows, out_type)) {
+        launch_k(layernorm_rows_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, x, rows, g, b, (const float*)nullptr, (const float*)nullptr, y, out_type, ps);
+        return;
+    }
     if (rows > 0) launch_k(layernorm_kernel, dim3(rows), dim3(256), 0, st, x, g, b, y, out_type, ps);
 }
 
@@ -148,6 +246,10 @@ __global__ void __launch_bounds__(256) layernorm2_kernel(float* x, const float* 
 }
 void launch_layernorm2(float* x, int rows, const float* g1, const float* b1, const float* g2, const float* b2, void* y2, int out_type,
                        const PartialSum& ps, cudaStream_t st) {
+    if (rows > 0 && ln_rows_enabled(rows, out_type)) {
+        launch_k(layernorm_rows_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, x, rows, g1, b1, g2, b2, y2, out_type, ps);
+        return;
+    }
     if (rows > 0) launch_k(layernorm2_kernel, dim3(rows), dim3(256), 0, st, x, g1, b1, g2, b2, y2, out_type, ps);
 }
 
@@ -887,17 +989,21 @@ void launch_attention(const AttnArgs& a, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------
 // Conv module core: GLU -> cached causal depthwise conv (k = 9) -> LayerNorm -> SiLU, and the new conv state.
-// One CTA per (frame t, stream): 256 threads x 4 channels. Output frame t needs xp[t .. t + 8] of xp = [state (8 rows) || glu (T rows)]
-// (:323-328), i.e. up to 9 GLU rows recomputed from the pointwise-1 output (36 sigmoids per thread: nothing next to walking the T
-// frames of a chunk one after the other, as the first version did: 17 us per layer at T = 14, and T = 2048 in the batch path).
-// The CTA of the LAST frame holds xp[T - 1 .. T + 7] and therefore writes the new state xp[T .. T + 7] (:368-381) -- into the OTHER
-// parity of the double-buffered state, because the CTAs of earlier frames may still be reading the old one.
-// Same tap order, same LayerNorm as before: bit-identical results.
+// One CTA per (block of TB frames, stream): 256 threads x 4 channels, a 9-deep register window slides over the block's frames.
+// The window is primed with the 8 rows before the block: rows of the conv state where they precede the chunk, GLU rows of earlier
+// frames recomputed from the pointwise-1 output otherwise (8 x 4 sigmoids per thread, all loads in flight at once) -- a fixed cost
+// per block, so TB trades redundancy against the length of the serial chain: TB = T for chunks of <= 4 frames (one block, nothing
+// recomputed), 4 frames otherwise (T = 14: 4 blocks per stream, ~6 us instead of 17 us per layer; the batch path's T ~ 2000 frames
+// become 500 independent CTAs instead of one). The LAST block writes the new state xp[T .. T + 7] (:368-381) into the OTHER parity of
+// the double-buffered state: CTAs of earlier blocks may still be reading the old one.
+// Same tap order and LayerNorm per frame as a single sequential pass: bit-identical results.
+// (Tried and dropped: one CTA per frame -- 9x the GLU work and pointwise-1 reads; 33 us instead of 17 us per layer at 64 x 14 frames.)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) conv_module_kernel(const ConvModArgs a) {
+__global__ void __launch_bounds__(256) conv_module_kernel(const ConvModArgs a, int TB) {
     NSB_KERNEL_BEGIN(TR_CONVMOD)                                                  // taps, conv state (written by this layer's kernel of earlier steps only), LN affine: pre-wait
     __shared__ float red[16];
-    const int t = blockIdx.x, b = blockIdx.y, c0 = threadIdx.x * 4, T = a.T;
+    const int t0 = blockIdx.x * TB, b = blockIdx.y, c0 = threadIdx.x * 4, T = a.T;
+    const int t1 = min(T, t0 + TB);
     const int slot = a.slot_of_b[b], par = a.cc_par[slot] & 1;
     const float* cache = a.conv_cache + (size_t)slot * a.slot_stride + (size_t)par * a.par_stride;
     float* cache_new = a.conv_cache + (size_t)slot * a.slot_stride + (size_t)(par ^ 1) * a.par_stride;
@@ -909,9 +1015,9 @@ __global__ void __launch_bounds__(256) conv_module_kernel(const ConvModArgs a) {
         wk[0][k] = w4.x; wk[1][k] = w4.y; wk[2][k] = w4.z; wk[3][k] = w4.w;
     }
 #pragma unroll
-    for (int k = 0; k < CONV_K; ++k) {                                           // window rows that come from the state: xp[t + k], t + k < 8
-        if (t + k < CONV_K - 1) {
-            const float4 v = *(const float4*)(cache + (size_t)(t + k) * D_MODEL + c0);
+    for (int k = 0; k < CONV_K - 1; ++k) {                                       // window rows xp[t0 + k] that lie in the state: t0 + k < 8   (xp = [state(8) || glu(T)] :323-328)
+        if (t0 + k < CONV_K - 1) {
+            const float4 v = *(const float4*)(cache + (size_t)(t0 + k) * D_MODEL + c0);
             win[0][k] = v.x; win[1][k] = v.y; win[2][k] = v.z; win[3][k] = v.w;
         }
     }
@@ -919,53 +1025,73 @@ __global__ void __launch_bounds__(256) conv_module_kernel(const ConvModArgs a) {
     const float lg[4] = {g4.x, g4.y, g4.z, g4.w}, lb[4] = {b4.x, b4.y, b4.z, b4.w};
     NSB_KERNEL_WAIT()
     const float* row0 = a.pw1 + (size_t)b * T * 2 * D_MODEL;
-    float4 av[CONV_K], gv[CONV_K];
+    if (t0 > 0) {                                                                // the other window rows: GLU of frames t0 + k - 8 >= 0, recomputed (block-uniform branch)
+        float4 ha[CONV_K - 1], hg[CONV_K - 1];
 #pragma unroll
-    for (int k = 0; k < CONV_K; ++k) {                                           // all loads of the window in flight before the first sigmoid
-        const int r = t + k - (CONV_K - 1);                                      // GLU row of window position k
-        if (r >= 0) {
-            const float* rp = row0 + (size_t)r * 2 * D_MODEL;
-            av[k] = ld4_planes<PW1_MAX_PLANES>(rp + c0, a.planes, a.plane_stride); gv[k] = ld4_planes<PW1_MAX_PLANES>(rp + D_MODEL + c0, a.planes, a.plane_stride);
+        for (int k = 0; k < CONV_K - 1; ++k) {
+            const int r = t0 + k - (CONV_K - 1);
+            if (r >= 0) {
+                const float* rp = row0 + (size_t)r * 2 * D_MODEL;
+                ha[k] = ld4_planes<PW1_MAX_PLANES>(rp + c0, a.planes, a.plane_stride); hg[k] = ld4_planes<PW1_MAX_PLANES>(rp + D_MODEL + c0, a.planes, a.plane_stride);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CONV_K - 1; ++k) {
+            if (t0 + k - (CONV_K - 1) >= 0) {
+                win[0][k] = ha[k].x * sigmoid_exact(hg[k].x); win[1][k] = ha[k].y * sigmoid_exact(hg[k].y);
+                win[2][k] = ha[k].z * sigmoid_exact(hg[k].z); win[3][k] = ha[k].w * sigmoid_exact(hg[k].w);
+            }
         }
     }
-#pragma unroll
-    for (int k = 0; k < CONV_K; ++k) {
-        if (t + k - (CONV_K - 1) >= 0) {                                         // GLU :629-636
-            win[0][k] = av[k].x * sigmoid_exact(gv[k].x); win[1][k] = av[k].y * sigmoid_exact(gv[k].y);
-            win[2][k] = av[k].z * sigmoid_exact(gv[k].z); win[3][k] = av[k].w * sigmoid_exact(gv[k].w);
+    const float* rt0 = row0 + (size_t)t0 * 2 * D_MODEL;
+    float4 av = ld4_planes<PW1_MAX_PLANES>(rt0 + c0, a.planes, a.plane_stride), gv = ld4_planes<PW1_MAX_PLANES>(rt0 + D_MODEL + c0, a.planes, a.plane_stride);
+    for (int t = t0; t < t1; ++t) {
+        float4 av_n = av, gv_n = gv;
+        if (t + 1 < t1) {                                                        // next row's loads overlap this row's reductions
+            const float* rn = row0 + (size_t)(t + 1) * 2 * D_MODEL;
+            av_n = ld4_planes<PW1_MAX_PLANES>(rn + c0, a.planes, a.plane_stride); gv_n = ld4_planes<PW1_MAX_PLANES>(rn + D_MODEL + c0, a.planes, a.plane_stride);
         }
+        win[0][8] = av.x * sigmoid_exact(gv.x); win[1][8] = av.y * sigmoid_exact(gv.y);   // GLU :629-636
+        win[2][8] = av.z * sigmoid_exact(gv.z); win[3][8] = av.w * sigmoid_exact(gv.w);
+        float cv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                                            // :341-360
+            float acc = win[u][0] * wk[u][0];
+#pragma unroll
+            for (int k = 1; k < CONV_K; ++k) acc = fmaf(win[u][k], wk[u][k], acc);
+            cv[u] = acc;
+        }
+        float mean, var, dd[4];                                                  // LN :643-645
+        if (a.out_type == OUT_F32) {
+            mean = block_sum_256(cv[0] + cv[1] + cv[2] + cv[3], red) * (1.0f / D_MODEL);
+            float sq = 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const float e = cv[u] - mean; sq += e * e; }
+            var = block_sum_256(sq, red) * (1.0f / D_MODEL);
+        } else block_mean_var_256(cv[0], cv[1], cv[2], cv[3], red, mean, var);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dd[u] = cv[u] - mean;
+        const float rs = 1.0f / sqrtf(var + 1e-5f);
+        const size_t o = ((size_t)b * T + t) * D_MODEL + c0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) store_out(a.out, o + u, silu_exact(dd[u] * rs * lg[u] + lb[u]), a.out_type);   // SiLU :646
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < CONV_K - 1; ++k) win[u][k] = win[u][k + 1];
+        av = av_n; gv = gv_n;
     }
-    float cv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {                                                // :341-360
-        float acc = win[u][0] * wk[u][0];
-#pragma unroll
-        for (int k = 1; k < CONV_K; ++k) acc = fmaf(win[u][k], wk[u][k], acc);
-        cv[u] = acc;
-    }
-    float mean, var, dd[4];                                                      // LN :643-645
-    if (a.out_type == OUT_F32) {
-        mean = block_sum_256(cv[0] + cv[1] + cv[2] + cv[3], red) * (1.0f / D_MODEL);
-        float sq = 0.f;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { const float e = cv[u] - mean; sq += e * e; }
-        var = block_sum_256(sq, red) * (1.0f / D_MODEL);
-    } else block_mean_var_256(cv[0], cv[1], cv[2], cv[3], red, mean, var);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) dd[u] = cv[u] - mean;
-    const float rs = 1.0f / sqrtf(var + 1e-5f);
-    const size_t o = ((size_t)b * T + t) * D_MODEL + c0;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) store_out(a.out, o + u, silu_exact(dd[u] * rs * lg[u] + lb[u]), a.out_type);   // SiLU :646
-    if (t == T - 1) {                                                            // new state = last 8 rows of xp = window positions 1 .. 8 of the last frame :368-381
+    if (t1 == T) {                                                               // new state = last 8 rows of xp :368-381 (the window after the last frame)
 #pragma unroll
         for (int k = 0; k < CONV_K - 1; ++k)
-            *(float4*)(cache_new + (size_t)k * D_MODEL + c0) = make_float4(win[0][k + 1], win[1][k + 1], win[2][k + 1], win[3][k + 1]);
+            *(float4*)(cache_new + (size_t)k * D_MODEL + c0) = make_float4(win[0][k], win[1][k], win[2][k], win[3][k]);
     }
     NSB_KERNEL_EPILOGUE();
 }
 void launch_conv_module(const ConvModArgs& a, cudaStream_t st) {
-    if (a.B > 0 && a.T > 0) launch_k(conv_module_kernel, dim3(a.T, a.B), dim3(256), 0, st, a);
+    static const int tb_env = [] { const char* e = getenv("NSB_CONV_TB"); return e ? atoi(e) : 0; }();
+    const int TB = tb_env > 0 ? tb_env : (a.T <= 4 ? a.T : 4);
+    if (a.B > 0 && a.T > 0) launch_k(conv_module_kernel, dim3((a.T + TB - 1) / TB, a.B), dim3(256), 0, st, a, TB);
 }
 
 __global__ void advance_streams_kernel(const int* __restrict__ slot_of_b, int B, int T, int* ring_pos, int* valid_len, int* cc_par) {
