@@ -665,8 +665,8 @@ int Engine::step_begin() {
     NSB_CUDA(cudaMemcpyAsync(d_pcm_.p, hp, (size_t)B * rl_ * 2, cudaMemcpyHostToDevice, st_));
     NSB_CUDA(cudaMemcpyAsync(side_[side].slot.p, hsl, (size_t)B * 4, cudaMemcpyHostToDevice, st_));
     NSB_CUDA(cudaEventRecord(io.ev0, st_));
-    run_step(B, d_pcm_.as<int16_t>(), side);
-    cudaStream_t tail = tail_stream(B * T);                               // the decode's stream: its tokens go home behind it
+    // the decode's stream: its tokens go home behind it. A step begun while another one is in flight is part of a pipeline
+    cudaStream_t tail = run_step(B, d_pcm_.as<int16_t>(), side, n_inflight_ >= 1);
     NSB_CUDA(cudaEventRecord(io.ev1, tail));
     NSB_CUDA(cudaMemcpyAsync(io.h_cnt.p, side_[side].out_cnt.p, (size_t)B * 4, cudaMemcpyDeviceToHost, tail));
     NSB_CUDA(cudaMemcpyAsync(io.h_tok.p, side_[side].out_tok.p, (size_t)B * MAX_SYMBOLS * T * 4, cudaMemcpyDeviceToHost, tail));
@@ -744,14 +744,16 @@ static unsigned skip_mask() {
 }
 enum { SK_LN = 1, SK_ATTN = 2, SK_CONV = 4, SK_DECODE = 8, SK_FF = 16, SK_QKV = 32, SK_OUT = 64, SK_PW = 128, SK_SUB = 256, SK_MEL = 512 };
 
-// Decode overlap (nsb_engine_config::decode_overlap; NSB_DECODE_OVERLAP=0/1 overrides): meant for batches of <= 128 token rows, where
-// every encoder kernel launches <= 128 CTAs on the 148 SMs. Off while taps / per-launch profiling are on (they read decode-side
-// buffers behind a sync of st_ only). Automatic mode = decode_auto_overlap(): see there for when it pays.
-bool Engine::overlap_decode(int rows) const {
-    static const int env = [] { const char* e = getenv("NSB_DECODE_OVERLAP"); return e ? atoi(e) : -1; }();     // 0 / 1 override the config
+// Decode overlap (nsb_engine_config::decode_overlap: 0 automatic, 1 always, 2 never; NSB_DECODE_OVERLAP=0/1 overrides): for batches of
+// <= 128 token rows, where every encoder kernel launches <= 128 CTAs on the 148 SMs and the decode's per-symbol rounds are latency-
+// bound. Automatic = only for steps that are part of a pipeline (a step begun while another is in flight, back-to-back bench steps):
+// the narrow decode takes ~2x longer than the full-width one, which only pays when it hides under the next step's encoder. Off while
+// taps / per-launch profiling are on (they read decode-side buffers behind a sync of st_ only) and in the strict modes.
+bool Engine::overlap_decode(int rows, bool pipelined) const {
+    static const int env = [] { const char* e = getenv("NSB_DECODE_OVERLAP"); return e ? atoi(e) : -1; }();
     const int mode = env == 0 ? 2 : env == 1 ? 1 : cfg_.decode_overlap;
     if (debug_ || profiling_ || strict() || mode == 2) return false;
-    return mode == 1 || (rows <= 128 && decode_auto_overlap());
+    return mode == 1 || (rows <= 128 && pipelined);
 }
 
 void Engine::join_decode_stream() {
@@ -785,9 +787,9 @@ void Engine::run_graphed(std::map<Key, StepGraph>& cache, const Key& key, cudaSt
     stats.kernel_launches += g.launches;
 }
 
-void Engine::run_step(int B, const int16_t* d_pcm, int side) {
+cudaStream_t Engine::run_step(int B, const int16_t* d_pcm, int side, bool pipelined) {
     last_B_ = B;
-    const bool ov = overlap_decode(B * T);
+    const bool ov = overlap_decode(B * T, pipelined);
     Side& sd = side_[side];
     if (!ov) join_decode_stream();                                              // decode on st_: behind any decode still running on the other stream
     run_graphed(graphs_, std::make_tuple(B, (const void*)d_pcm, side), st_, [&] { run_encoder_kernels(B, d_pcm, side); });
@@ -800,6 +802,7 @@ void Engine::run_step(int B, const int16_t* d_pcm, int side) {
         run_graphed(dec_graphs_, std::make_tuple(B, side, ov ? 1 : 0), s, [&] { run_decode_kernels(B, side, s, ov); });
     if (ov) { NSB_CUDA(cudaEventRecord(sd.dec_done, st_dec_)); sd.dec_pending = true; }
     side_next_ = side ^ 1;
+    return s;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1030,8 +1033,8 @@ float Engine::bench_step() {
     collect_all();
     NSB_CUDA(cudaSetDevice(device_));
     NSB_CUDA(cudaEventRecord(ev0_, st_));
-    run_step(bench_B_, bench_next_pcm(), side_acquire());
-    NSB_CUDA(cudaEventRecord(ev1_, tail_stream(bench_B_ * T)));
+    cudaStream_t tail = run_step(bench_B_, bench_next_pcm(), side_acquire(), false);
+    NSB_CUDA(cudaEventRecord(ev1_, tail));
     NSB_CUDA(cudaEventSynchronize(ev1_));
     float ms = 0.f; NSB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
     stats.steps += 1; stats.chunks += bench_B_; stats.device_ms += ms; stats.last_step_ms = ms;
@@ -1048,7 +1051,7 @@ float Engine::bench_steps(int n, float* ms_each) {
     for (int i = 0; i <= n; ++i) ev[i] = prof_event();
     NSB_CUDA(cudaEventRecord(ev[0], st_));
     // with decode overlap the event after step i sits behind its DECODE (other stream): the encoder of step i + 1 is already running
-    for (int i = 0; i < n; ++i) { run_step(bench_B_, bench_next_pcm(), side_acquire()); NSB_CUDA(cudaEventRecord(ev[i + 1], tail_stream(bench_B_ * T))); }
+    for (int i = 0; i < n; ++i) { cudaStream_t tail = run_step(bench_B_, bench_next_pcm(), side_acquire(), n > 1); NSB_CUDA(cudaEventRecord(ev[i + 1], tail)); }
     NSB_CUDA(cudaEventSynchronize(ev[n]));
     float total = 0.f; NSB_CUDA(cudaEventElapsedTime(&total, ev[0], ev[n]));
     for (int i = 0; i < n; ++i) {

@@ -141,9 +141,11 @@ private:
     // <= 128 CTAs and leave those SMs idle anyway. Same kernel, same arithmetic, same tokens; the sides are what makes it safe.
     void join_decode_stream();                               // st_ waits for whatever the decode stream still runs
     int side_acquire();                                      // next side; orders st_ behind the decode that last read its buffers
-    void run_step(int B, const int16_t* d_pcm, int side);
-    bool overlap_decode(int rows) const;
-    cudaStream_t tail_stream(int rows) const { return overlap_decode(rows) ? st_dec_ : st_; }   // where a step's tokens become available
+    // pipelined = another step is (or is about to be) in flight behind this one: only then does the overlap buy anything -- a step
+    // run on its own gets the full-width decode, which is the faster of the two in isolation. Returns the stream the step's tokens
+    // become available on.
+    cudaStream_t run_step(int B, const int16_t* d_pcm, int side, bool pipelined);
+    bool overlap_decode(int rows, bool pipelined) const;
     struct StepGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; };
     std::map<std::tuple<int, const void*, int>, StepGraph> graphs_;      // encoder halves
     std::map<std::tuple<int, int, int>, StepGraph> dec_graphs_;           // decode halves: (batch, side, narrow)

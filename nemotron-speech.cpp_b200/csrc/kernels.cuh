@@ -139,8 +139,7 @@ struct DecodeArgs {
 // persistent kernel; sync_buf holds decode_sync_bytes(B) bytes. narrow_ctas = 0: one CTA per SM (cooperative launch); > 0: that many CTAs
 // as CTA pairs, sharing the GPU with other kernels (decode overlap). Returns the grid size used
 int launch_decode(const DecodeArgs& a, void* sync_buf, cudaStream_t st, int narrow_ctas = 0);
-int decode_narrow_ctas();          // NSB_DECODE_CTAS, default 16
-bool decode_auto_overlap();        // whether the narrow decode is fast enough for the overlap to pay at <= 128 token rows (kernels_decode.cu)
+int decode_narrow_ctas();          // NSB_DECODE_CTAS, default 20 (148 SMs - the 128 CTAs of the widest small-batch encoder kernel)
 size_t decode_sync_bytes(int B);
 
 }  // namespace nsb

@@ -428,17 +428,132 @@ __device__ void phase_pipe(const DecodeArgs& a, DecSmem& sm, int layer, int n, i
     __syncthreads();                                                              // the ring is free for whatever runs next
 }
 
+
+// ------------------------------------------------------------------------------------------
+// phase_gemv(): the LSTM phase for a handful of streams (<= 8 SPL) on a NARROW grid (decode overlap: ~20 CTAs next to the next
+// step's encoder). There a CTA owns 1/20 of the gate matrix and the phase is bound by how fast 256 threads can issue, so the tile is
+// built around instructions per FMA: 128 weight rows = 32 hidden units x 4 gates per CTA tile, a lane owns ONE unit (all four gates:
+// no shuffle, every thread finalises its own cell) x SPL streams = 4 + SPL shared-memory loads per 16 SPL FMAs (phase_pipe<1,1>: 2 per
+// 4). K streams through a 4-stage cp.async ring in steps of 80; the 160-wide chunk partials are formed and added exactly as in
+// phase() / phase_pipe(): same bits.
+// Stage layout: weight row (gate g, unit index i) at row g * 32 + i, so the four units a warp's row groups read sit in different
+// banks; stream vectors behind them.
+// ------------------------------------------------------------------------------------------
+template <int SPL>
+__device__ void phase_gemv(const DecodeArgs& a, DecSmem& sm, int layer, int n) {
+    constexpr int NSUB = 16, KS = 2 * HID / NSUB, WS = KS + 4, VPR = KS / 4;       // 16 pipeline steps of 80 floats = 8 chunks of 160
+    constexpr int UT = 32, RT = 4 * UT, ST = 8 * SPL;
+    constexpr int STAGE_F = (RT + ST) * WS;
+    constexpr int NST = NW * STAGE_FLOATS / STAGE_F > 5 ? 5 : NW * STAGE_FLOATS / STAGE_F;
+    static_assert(NST >= 3, "at least three stages in the ring");
+    const int n_rt = HID / UT, n_sb = (n + ST - 1) / ST, n_items = n_rt * n_sb;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, rgrp = lane >> 3, sg = lane & 7;
+    const int my_items = (int)blockIdx.x < n_items ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int total_steps = my_items * NSUB;
+    float* ring = &sm.stage[0][0];
+
+    auto issue = [&](int q) {
+        if (q < total_steps) {
+            const int item = (int)blockIdx.x + (q / NSUB) * (int)gridDim.x, sub = q % NSUB;
+            const int rt = item % n_rt, s0 = (item / n_rt) * ST, ns = min(ST, n - s0);
+            const bool rec = sub >= NSUB / 2;                                     // k >= 640: recurrent half
+            const int kc = (sub % (NSUB / 2)) * KS;
+            const float* wmat = rec ? a.w.w_hh[layer] : a.w.w_ih[layer];
+            float* st = ring + (q % NST) * STAGE_F;
+            for (int p = tid; p < RT * VPR; p += NT) {
+                const int rr = p / VPR, v = (p % VPR) * 4;
+                const int row = (rr / UT) * HID + rt * UT + (rr % UT);            // gate * 640 + unit
+                cp_async16(st + rr * WS + v, wmat + (size_t)row * HID + kc + v);
+            }
+            for (int p = tid; p < ns * VPR; p += NT) {
+                const int g = p / VPR, v = (p % VPR) * 4;
+                const int b = sm.list[s0 + g], slot = sm.slot[b], par = sm.par[b];
+                const float* hb = a.s.hbuf + (size_t)slot * 2 * PAR_STRIDE;
+                const float* src = rec ? hb + par * PAR_STRIDE + layer * HID                                   // committed h of this layer
+                                       : (layer == 0 ? a.w.embed + (size_t)sm.prev[b] * HID                    // nemo-stream.cpp:825-828
+                                                     : hb + (par ^ 1) * PAR_STRIDE);                           // layer-1 input = layer-0 h'
+                cp_async16(st + (RT + g) * WS + v, src + kc + v);
+            }
+        }
+        cp_async_commit();
+    };
+
+    for (int q = 0; q < NST - 1; ++q) issue(q);
+    float tot[4][SPL], acc[4][SPL];
+    for (int q = 0; q < total_steps; ++q) {
+        const int item = (int)blockIdx.x + (q / NSUB) * (int)gridDim.x, sub = q % NSUB;
+        const int rt = item % n_rt, s0 = (item / n_rt) * ST, ns = min(ST, n - s0);
+        const float* st = ring + (q % NST) * STAGE_F;
+        cp_async_wait<NST - 2>();
+        __syncthreads();
+        issue(q + NST - 1);
+        if ((sub & 1) == 0) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) acc[g][j] = 0.f;
+        }
+        const float* wsm = st + (warp * 4 + rgrp) * WS;
+        const float* xsm = st + (RT + sg) * WS;
+#pragma unroll 5
+        for (int k = 0; k < KS; k += 4) {
+            float4 w[4], x[SPL];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) w[g] = *reinterpret_cast<const float4*>(wsm + g * UT * WS + k);
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) x[j] = *reinterpret_cast<const float4*>(xsm + 8 * j * WS + k);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) {
+                    acc[g][j] = fmaf(w[g].x, x[j].x, acc[g][j]); acc[g][j] = fmaf(w[g].y, x[j].y, acc[g][j]);
+                    acc[g][j] = fmaf(w[g].z, x[j].z, acc[g][j]); acc[g][j] = fmaf(w[g].w, x[j].w, acc[g][j]);
+                }
+        }
+        if ((sub & 1) == 0) continue;                                             // second half of a 160-wide chunk: its partial is complete
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) tot[g][j] = sub == 1 ? acc[g][j] : tot[g][j] + acc[g][j];
+        if (sub != NSUB - 1) continue;
+        // ---------------- the unit's four gate sums are complete, in this lane: cell update (nemo-ggml.cpp:518-541) ----------------
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            const int g = sg + 8 * j;
+            if (g >= ns) continue;
+            const int b = sm.list[s0 + g], slot = sm.slot[b], par = sm.par[b];
+            const int u = rt * UT + warp * 4 + rgrp;
+            float gate[4];
+#pragma unroll
+            for (int qg = 0; qg < 4; ++qg) gate[qg] = (tot[qg][j] + __ldg(a.w.b_ih[layer] + qg * HID + u)) + __ldg(a.w.b_hh[layer] + qg * HID + u);
+            const float ig = sigmoid_exact(gate[0]), fg = sigmoid_exact(gate[1]), gg = tanhf(gate[2]), og = sigmoid_exact(gate[3]);
+            const size_t o_old = (size_t)slot * 2 * PAR_STRIDE + par * PAR_STRIDE + layer * HID + u;
+            const size_t o_new = (size_t)slot * 2 * PAR_STRIDE + (par ^ 1) * PAR_STRIDE + layer * HID + u;
+            const float cn = fg * __ldcg(a.s.cbuf + o_old) + ig * gg;
+            a.s.cbuf[o_new] = cn; a.s.hbuf[o_new] = og * tanhf(cn);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+}
+
 template <int MODE>
 __device__ __forceinline__ void phase_dispatch(const DecodeArgs& a, DecSmem& sm, int layer, int n, int round, int ne0) {
     // one or two items per CTA and phase (full-width grid, a handful of streams): the one-shot staging of phase(); a narrow grid (decode
     // overlap) or many stream blocks: the pipelined tiles. Same arithmetic, same bits (see phase_pipe).
-    const bool pipe = gridDim.x <= 64 || n >= a.pipe_min_n;
+    const bool narrow = gridDim.x <= 64;
+    const bool pipe = narrow || n >= a.pipe_min_n;
     constexpr int RPL = MODE == MODE_LSTM ? 5 : 2;
     if (!pipe) {
         if (n <= 8) phase<RPL, 1, MODE>(a, sm, layer, n, round, ne0);
         else phase<RPL, 2, MODE>(a, sm, layer, n, round, ne0);
         return;
     }
+    if (narrow && MODE == MODE_LSTM && n <= 16) {                                 // few emitting streams on a narrow grid: one unit per lane
+        if (n <= 8) phase_gemv<1>(a, sm, layer, n); else phase_gemv<2>(a, sm, layer, n);
+        return;
+    }
+    if (narrow && MODE == MODE_JOINT && n > 16) { phase_pipe<2, 4, MODE>(a, sm, layer, n, round, ne0); return; }   // fewer instructions per FMA than <1,4>
     if (n <= 8) phase_pipe<1, 1, MODE>(a, sm, layer, n, round, ne0);
     else if (n <= 16) phase_pipe<1, 2, MODE>(a, sm, layer, n, round, ne0);
     else if (n <= 64) phase_pipe<1, 4, MODE>(a, sm, layer, n, round, ne0);        // more (smaller) tiles while the stream blocks are few
@@ -539,13 +654,8 @@ static int decode_grid() {                 // per device ordinal: the attribute 
 }
 size_t decode_sync_bytes(int B) { return 16 + (size_t)3 * B * sizeof(unsigned long long); }
 
-// Measured (profiles/r02_trace_overlap.txt): this kernel on 16 CTAs takes ~7x longer per round than on 148 (its items are staged one
-// at a time: a narrow grid walks 8 items per phase, each exposing one L2 round trip), i.e. 2-3 ms per step against a 1.7 ms encoder:
-// the overlap would make the decode the bottleneck. Automatic mode therefore stays off.
-bool decode_auto_overlap() { return false; }
-
 int decode_narrow_ctas() {
-    static const int n = [] { const char* e = getenv("NSB_DECODE_CTAS"); const int v = e ? atoi(e) : 16; return std::max(2, v & ~1); }();
+    static const int n = [] { const char* e = getenv("NSB_DECODE_CTAS"); const int v = e ? atoi(e) : 20; return std::max(2, v & ~1); }();
     return n;
 }
 
