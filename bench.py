@@ -292,6 +292,7 @@ def run_config(no: int, args, ctx, headline: bool):
     # ---- device-resident timing: K steps, CUDA events inside the engine per step (engine stream) ----
     for _ in range(max(args.warmup, BENCH_CHUNKS)):       # >= W untimed steps; at least one pass over every staged chunk (one CUDA graph each)
         eng.bench_step()
+    eng.bench_steps(2 * BENCH_CHUNKS)                     # ... and over the graphs of the pipelined form (decode overlap: other decode graphs, both sides)
     st0 = eng.stats()
     sampler = ClockSampler(local); sampler.start()
     sync_all()
