@@ -75,6 +75,23 @@ __global__ void unpack_q8_planes_kernel(const uint16_t* __restrict__ raw, int8_t
         dst[0] = make_uint4(w[0], w[1], w[2], w[3]); dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
 }
+// Q4_0 blocks (fp16 d + 16 nibble bytes, 18 bytes) -> nibble plane (16 bytes per block, as stored) + fp16 scale plane; strict = 1: int8
+// plane of q - 8 instead (32 bytes per block: the strict Q8_0 x Q8_0 GEMM takes any int8 weight quants)
+__global__ void unpack_q4_planes_kernel(const uint16_t* __restrict__ raw, uint8_t* __restrict__ q, uint16_t* __restrict__ d, size_t nb, int strict) {
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (size_t)gridDim.x * blockDim.x) {
+        const uint16_t* p = raw + b * 9;
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = (uint32_t)p[1 + 2 * i] | ((uint32_t)p[2 + 2 * i] << 16);
+        d[b] = p[0];
+        if (!strict) { *reinterpret_cast<uint4*>(q + b * 16) = make_uint4(w[0], w[1], w[2], w[3]); continue; }
+        int8_t v[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const uint32_t by = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu; v[i] = (int8_t)((int)(by & 0xF) - 8); v[16 + i] = (int8_t)((int)(by >> 4) - 8); }
+        uint4* dst = reinterpret_cast<uint4*>(q + b * 32);
+        dst[0] = *reinterpret_cast<uint4*>(&v[0]); dst[1] = *reinterpret_cast<uint4*>(&v[16]);
+    }
+}
 // Q8_0 / Q4_0 blocks -> dense values d * q (exact in f32), rounded once to out_type: what ggml's dequantize_row_* returns
 __global__ void dequant_blocks_kernel(const uint16_t* __restrict__ raw, void* __restrict__ out, size_t nb, int q4, int out_type) {
     for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (size_t)gridDim.x * blockDim.x) {
@@ -182,8 +199,8 @@ Engine::Engine(const std::string& path, const nsb_engine_config& cfg) : cfg_(cfg
     compute = cfg.compute;
     if (compute == NSB_COMPUTE_AUTO) {
         const int t = g.require("encoder.layers.0.feed_forward1.linear1.weight").type;
-        // Q4_0 files: the matrices are expanded to fp16 at load (d * (q - 8) rounded once) and run on the fp16 tcgen05 path
-        compute = t == GGML_F32 ? NSB_COMPUTE_F32 : (t == GGML_F16 || t == GGML_Q4_0) ? NSB_COMPUTE_F16 : NSB_COMPUTE_Q8_0;
+        // Q8_0 and Q4_0 files stay quantised in HBM (fused-dequant GEMM; NSB_COMPUTE_F16 on such a file expands it to fp16 at load)
+        compute = t == GGML_F32 ? NSB_COMPUTE_F32 : t == GGML_F16 ? NSB_COMPUTE_F16 : NSB_COMPUTE_Q8_0;
     }
     load_weights(g);
     alloc_state();
@@ -288,17 +305,27 @@ void Engine::load_layer_matrix(Weight& w, const GgufFile& g, const std::string& 
     }
     if (d_raw_.bytes < part_elems * 4) { NSB_CUDA(cudaStreamSynchronize(st_)); d_raw_.alloc((size_t)D_FF * D_MODEL * 4, false); }
     if (q8_planes_mode()) {
-        w.data.alloc((size_t)n_out * n_in, false); w.scales.alloc((size_t)n_out * (n_in / 32) * 2, false);
+        // Q4_0 files keep their nibbles in HBM in the fast mode (0.5625 bytes per weight; the fused kernel's Q4 variant); the strict
+        // mode widens them to int8 quants q - 8 once (its integer block dots take any int8 weight)
+        bool all_q4 = true;
+        for (const std::string& pn : parts) all_q4 = all_q4 && g.require(pn).type == GGML_Q4_0;
+        const bool nib = all_q4 && compute == NSB_COMPUTE_Q8_0;
+        w.q4 = nib ? 1 : 0;
+        w.data.alloc(nib ? (size_t)n_out * n_in / 2 : (size_t)n_out * n_in, false); w.scales.alloc((size_t)n_out * (n_in / 32) * 2, false);
         for (size_t i = 0; i < parts.size(); ++i) {
             const GgufTensor& t = g.require(parts[i]);
-            int8_t* qd = w.data.as<int8_t>() + i * part_elems; uint16_t* dd = w.scales.as<uint16_t>() + i * (part_elems / 32);
+            uint16_t* dd = w.scales.as<uint16_t>() + i * (part_elems / 32);
             if (t.type == GGML_Q8_0) {                              // stays quantised: raw blocks up, split into planes on the device
                 stream_upload(d_raw_.p, g.data(t), t.nbytes);
-                unpack_q8_planes_kernel<<<grid_for(part_elems / 32), 256, 0, st_>>>(d_raw_.as<uint16_t>(), qd, dd, part_elems / 32);
+                unpack_q8_planes_kernel<<<grid_for(part_elems / 32), 256, 0, st_>>>(d_raw_.as<uint16_t>(), w.data.as<int8_t>() + i * part_elems, dd, part_elems / 32);
+            } else if (all_q4) {
+                stream_upload(d_raw_.p, g.data(t), t.nbytes);
+                unpack_q4_planes_kernel<<<grid_for(part_elems / 32), 256, 0, st_>>>(d_raw_.as<uint16_t>(), w.data.as<uint8_t>() + i * (nib ? part_elems / 2 : part_elems), dd,
+                                                                                   part_elems / 32, nib ? 0 : 1);
             } else {                                                // another stored type: quantised here with the converter's rule (host)
                 std::vector<int8_t> q; std::vector<uint16_t> d; q8_planes(g, parts[i], q, d);
                 NSB_CUDA(cudaStreamSynchronize(st_));
-                h2d_sync(qd, q.data(), q.size()); h2d_sync(dd, d.data(), d.size() * 2);
+                h2d_sync(w.data.as<int8_t>() + i * part_elems, q.data(), q.size()); h2d_sync(dd, d.data(), d.size() * 2);
             }
         }
         return;
@@ -526,9 +553,9 @@ void Engine::build_pos_tables(const GgufFile& g) {
 void Engine::gemm(const void* A, long long lda, const Weight& W, int M, const float* bias, void* C, long long ldc, int epi, float alpha,
                   int out_type) {
     GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.w_scales = W.scales.p; a.M = M; a.N = W.n_out; a.K = W.n_in; a.bias = bias; a.C = C; a.ldc = ldc;
-    a.epi = epi; a.alpha = alpha; a.out_type = out_type; a.pair = 1;
+    a.epi = epi; a.alpha = alpha; a.out_type = out_type; a.pair = 1; a.q4 = W.q4;
     ProfScope ps(this, PC_GEMM);
-    if (cur_shadow_ && W.shadow_slot >= 0) { a.W = cur_shadow_ + shadow_off_[W.shadow_slot]; a.w_scales = nullptr; }   // dequantised a layer ahead
+    if (cur_shadow_ && W.shadow_slot >= 0) { a.W = cur_shadow_ + shadow_off_[W.shadow_slot]; a.w_scales = nullptr; a.q4 = 0; }   // dequantised a layer ahead
     else q8_predequant(W, M, a);
     if (compute == NSB_COMPUTE_Q8_0_STRICT) { launch_gemm_q8_strict(a, q8s_scratch_.p, q8s_scratch_.bytes, st_); count_launch(); }
     else if (compute == NSB_COMPUTE_F32) launch_gemm_simt(a, st_);
@@ -566,9 +593,9 @@ void Engine::q8_predequant(const Weight& W, int M, GemmArgs& a) {
     if (compute != NSB_COMPUTE_Q8_0 || !W.scales.p || M < min_rows) return;
     const size_t bytes = (size_t)W.n_out * W.n_in * 2;
     if (wscratch_.bytes < bytes) throw std::runtime_error("q8_predequant: scratch not allocated");   // sized in alloc_state (no allocation inside a graph capture)
-    launch_dequant_q8(W.data.p, W.scales.p, wscratch_.p, W.n_out, W.n_in, st_);
+    launch_dequant_q8(W.data.p, W.scales.p, wscratch_.p, W.n_out, W.n_in, st_, W.q4);
     count_launch();
-    a.W = wscratch_.p; a.w_scales = nullptr; a.w_dynamic = 1; a.pair = 0;
+    a.W = wscratch_.p; a.w_scales = nullptr; a.w_dynamic = 1; a.pair = 0; a.q4 = 0;
 }
 
 bool Engine::shadow_mode(int rows) const {
@@ -581,7 +608,7 @@ void Engine::dequant_layer_async(int l, cudaStream_t s) {
     LayerW& L = layers_[l];
     char* base = shadow_[l & 1].as<char>();
     for (Weight* w : {&L.ff1a, &L.ff1b, &L.qkv, &L.out, &L.pw1, &L.pw2, &L.ff2a, &L.ff2b}) {
-        launch_dequant_q8(w->data.p, w->scales.p, base + shadow_off_[w->shadow_slot], w->n_out, w->n_in, s);
+        launch_dequant_q8(w->data.p, w->scales.p, base + shadow_off_[w->shadow_slot], w->n_out, w->n_in, s, w->q4);
         count_launch();
     }
 }

@@ -40,6 +40,7 @@ struct HostPinned {
 // one GEMM weight in the engine's compute arithmetic
 struct Weight {
     std::string name; int n_out = 0, n_in = 0;
+    int q4 = 0;             // Q8_0 mode, Q4_0 file: `data` is the nibble plane [n_out][n_in / 2] (fused-dequant GEMM variant)
     int shadow_slot = -1;   // Q8_0 mode: which of the layer's 8 matrices this is (offset into the fp16 shadow of the layer, see Engine::shadow_)
     DevBuf data;            // f32 / f16 / bf16 [n_out][n_in]; Q8_0 mode: int8 quants [n_out][n_in]
     DevBuf scales;          // Q8_0 mode only: fp16 block scales [n_out][n_in / 32]

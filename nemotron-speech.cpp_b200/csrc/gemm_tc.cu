@@ -654,7 +654,10 @@ struct SmemQ8 {
     int trace_slot;
 };
 
-template <int BN, int STAGES>
+// Q4 = 1: the same pipeline for Q4_0 weights (scripts/convert_to_gguf.py:132-179): the raw tile is [BN][32] bytes of nibbles per
+// k-block (two 32-value blocks; byte i of a block = value i in the low nibble, value i + 16 in the high one, stored value q in 0..15
+// meaning q - 8), the dequantiser expands fp16(d) * (q - 8) -- HBM traffic per weight 0.5625 bytes.
+template <int BN, int STAGES, int Q4>
 __global__ void __launch_bounds__(Q8_THREADS, 1)
 gemm_q8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmQ, const __half* __restrict__ scales,
                const TcParams p) {
@@ -668,7 +671,8 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int kb0 = (int)blockIdx.z * nk;
     const int rot = p.rot ? (int)(blockIdx.x % (unsigned)nk) : 0;
     constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-    constexpr uint32_t STAGE_BYTES = BM * ROW_BYTES + BN * 64;
+    constexpr int QROW = Q4 ? 32 : 64;                                          // raw bytes per weight row and k-block
+    constexpr uint32_t STAGE_BYTES = BM * ROW_BYTES + BN * QROW;
 
     if (threadIdx.x == 0) {
         s.trace_slot = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 ? trace_begin(TR_GEMM_Q8) : -1;
@@ -709,9 +713,9 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int pre = nk < STAGES ? nk : STAGES;
             for (int kb = 0; kb < pre; ++kb) {
                 mbar_expect_tx(&s.full[kb], STAGE_BYTES);
-                tma_load_2d(s.q[kb], &tmQ, &s.full[kb], (kb0 + (kb + rot) % nk) * BK, n0);
+                tma_load_2d(s.q[kb], &tmQ, &s.full[kb], (kb0 + (kb + rot) % nk) * QROW, n0);
             }
-            for (int kb = pre; kb < nk; ++kb) tma_prefetch_2d(&tmQ, (kb0 + (kb + rot) % nk) * BK, n0);
+            for (int kb = pre; kb < nk; ++kb) tma_prefetch_2d(&tmQ, (kb0 + (kb + rot) % nk) * QROW, n0);
             pdl_wait();
             for (int kb = 0; kb < pre; ++kb) tma_load_2d(s.a[kb], &tmA, &s.full[kb], (kb0 + (kb + rot) % nk) * BK, m0);
             for (int kb = pre; kb < nk; ++kb) {
@@ -720,7 +724,7 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_expect_tx(&s.full[st], STAGE_BYTES);
                 const int kc = (kb0 + (kb + rot) % nk) * BK;
                 tma_load_2d(s.a[st], &tmA, &s.full[st], kc, m0);
-                tma_load_2d(s.q[st], &tmQ, &s.full[st], kc, n0);
+                tma_load_2d(s.q[st], &tmQ, &s.full[st], kc / BK * QROW, n0);
             }
         }
     } else if (warp == 1) {
@@ -752,17 +756,22 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int pz = 0; pz < (BN + 63) / 64; ++pz) {
                 const int r = pz * 64 + (t >> 2);
                 if (BN % 64 != 0 && r >= BN) continue;                             // BN = 32: only the first 128 threads have a row
-                const uint4 raw = *reinterpret_cast<const uint4*>(&s.q[st][r * 64 + c * 16]);
+                // 16 weights per thread: Q8_0 = 16 bytes of the row; Q4_0 = the 16 low (c even) or high (c odd) nibbles of block c / 2
+                uint4 raw = *reinterpret_cast<const uint4*>(&s.q[st][r * QROW + (Q4 ? (c >> 1) * 16 : c * 16)]);
                 const __half2 d2 = __half2half2(s.sc[r * per_row + kk * 2 + (c >> 1)]);
                 // int8 -> fp16 without integer conversions: q + 128 as the low mantissa bits of 1024.0 (0x6400 | byte), minus 1152;
                 // then ONE fp16 multiply by the block scale = fp16(d) * q rounded once, exactly the value a load-time dequantisation
                 // to fp16 holds. 7 instructions per 4 weights (the conversion path was what bound this kernel).
+                if (Q4) {                                                             // nibble n -> byte n: then (0x6400 | n) - 1032 = n - 8
+                    const int sh = (c & 1) * 4;
+                    raw.x = (raw.x >> sh) & 0x0F0F0F0Fu; raw.y = (raw.y >> sh) & 0x0F0F0F0Fu; raw.z = (raw.z >> sh) & 0x0F0F0F0Fu; raw.w = (raw.w >> sh) & 0x0F0F0F0Fu;
+                }
                 const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
-                const __half2 off = __floats2half2_rn(1152.0f, 1152.0f);
+                const __half2 off = Q4 ? __floats2half2_rn(1032.0f, 1032.0f) : __floats2half2_rn(1152.0f, 1152.0f);
                 __half2 h[8];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const uint32_t x = w4[i] ^ 0x80808080u;
+                    const uint32_t x = Q4 ? w4[i] : (w4[i] ^ 0x80808080u);
                     const uint32_t lo = __byte_perm(x, 0x64646464u, 0x5140), hi = __byte_perm(x, 0x64646464u, 0x5342);
                     h[2 * i] = __hmul2(__hsub2(*reinterpret_cast<const __half2*>(&lo), off), d2);
                     h[2 * i + 1] = __hmul2(__hsub2(*reinterpret_cast<const __half2*>(&hi), off), d2);
@@ -812,11 +821,11 @@ CUtensorMap make_map(const void* ptr, int rows, int K, long long ld, int box_row
     return m;
 }
 
-CUtensorMap make_map_u8(const void* ptr, int rows, int K, int box_rows) {
+CUtensorMap make_map_u8(const void* ptr, int rows, int K, int box_rows, int box_cols = 64) {
     CUtensorMap m;
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)K};
-    const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -825,19 +834,21 @@ CUtensorMap make_map_u8(const void* ptr, int rows, int K, int box_rows) {
     return m;
 }
 
-template <int BN, int STAGES>
-void launch_cfg_q8(const GemmArgs& a, cudaStream_t st) {
+template <int BN, int STAGES, int Q4>
+void launch_cfg_q8x(const GemmArgs& a, cudaStream_t st) {
     static std::atomic<size_t> attr_set[MAX_DEVICES];
     const size_t smem = sizeof(SmemQ8<BN, STAGES>) + 1024;
-    ensure_dyn_smem(gemm_q8_kernel<BN, STAGES>, smem, attr_set);
+    ensure_dyn_smem(gemm_q8_kernel<BN, STAGES, Q4>, smem, attr_set);
     if (a.K / 64 / a.splits > 64) throw CudaError("gemm_q8: k range per CTA too long for the scale buffer");
     const CUtensorMap tmA = make_map(a.A, a.M, a.K, a.lda, BM, 0);
-    const CUtensorMap tmQ = make_map_u8(a.W, a.N, a.K, BN);
+    const CUtensorMap tmQ = Q4 ? make_map_u8(a.W, a.N, a.K / 2, BN, 32) : make_map_u8(a.W, a.N, a.K, BN);
     const int m_out = a.c_group > 0 ? (a.M / a.c_group) * (a.c_group - a.c_drop) : a.M;
     TcParams p{a.M, a.N, a.K, a.bias, a.C, a.ldc, a.epi, a.alpha, a.out_type, 0, a.rotate, a.c_group, a.c_drop, a.C0, m_out};
     dim3 grid(a.N / BN, (a.M + BM - 1) / BM, a.splits);
-    launch_k(gemm_q8_kernel<BN, STAGES>, grid, dim3(Q8_THREADS), smem, st, tmA, tmQ, (const __half*)a.w_scales, p);
+    launch_k(gemm_q8_kernel<BN, STAGES, Q4>, grid, dim3(Q8_THREADS), smem, st, tmA, tmQ, (const __half*)a.w_scales, p);
 }
+template <int BN, int STAGES>
+void launch_cfg_q8(const GemmArgs& a, cudaStream_t st) { if (a.q4) launch_cfg_q8x<BN, STAGES, 1>(a, st); else launch_cfg_q8x<BN, STAGES, 0>(a, st); }
 
 // Experimental, off by default: on B200 the multicast variant measured SLOWER than per-CTA A loads at M = 128
 // (ff1a 7.7 vs 6.9 us, profiles/r01_notes.md) -- L2 already serves the shared tile well and the cluster-wide stage release
@@ -955,8 +966,39 @@ __global__ void __launch_bounds__(256) dequant_q8_kernel(const uint4* __restrict
     NSB_KERNEL_EPILOGUE();
 }
 }  // namespace
-void launch_dequant_q8(const void* q, const void* scales, void* out_f16, int N, int K, cudaStream_t st) {
+namespace {
+// Q4_0 nibble plane [N][K / 2] + scales -> fp16 [N][K]: one thread per 32-value block (16 bytes in, 64 bytes out)
+__global__ void __launch_bounds__(256) dequant_q4_kernel(const uint4* __restrict__ q, const __half* __restrict__ sc, uint4* __restrict__ out, size_t nb) {
+    NSB_KERNEL_PROLOGUE(TR_OTHER)
+    const __half2 off = __floats2half2_rn(1032.0f, 1032.0f);
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (size_t)gridDim.x * blockDim.x) {
+        const uint4 raw = q[b];
+        const __half2 d2 = __half2half2(sc[b]);
+        const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {                                   // values 0..15 = low nibbles, 16..31 = high nibbles
+            __half2 h[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t x = (w4[j] >> (4 * half)) & 0x0F0F0F0Fu;
+                const uint32_t lo = __byte_perm(x, 0x64646464u, 0x5140), hi = __byte_perm(x, 0x64646464u, 0x5342);
+                h[2 * j] = __hmul2(__hsub2(*reinterpret_cast<const __half2*>(&lo), off), d2);
+                h[2 * j + 1] = __hmul2(__hsub2(*reinterpret_cast<const __half2*>(&hi), off), d2);
+            }
+            out[4 * b + 2 * half] = *reinterpret_cast<uint4*>(&h[0]);
+            out[4 * b + 2 * half + 1] = *reinterpret_cast<uint4*>(&h[4]);
+        }
+    }
+    NSB_KERNEL_EPILOGUE();
+}
+}  // namespace
+void launch_dequant_q8(const void* q, const void* scales, void* out_f16, int N, int K, cudaStream_t st, int q4) {
     if (K % 32 != 0) throw CudaError("dequant_q8: K must be a multiple of 32");
+    if (q4) {
+        const size_t nb = (size_t)N * K / 32;
+        launch_k(dequant_q4_kernel, dim3((unsigned)std::min<size_t>((nb + 255) / 256, 148 * 8)), dim3(256), 0, st, (const uint4*)q, (const __half*)scales, (uint4*)out_f16, nb);
+        return;
+    }
     const size_t n_vec = (size_t)N * K / 16;
     const int blocks = (int)std::min<size_t>((n_vec + 255) / 256, 148 * 8);
     launch_k(dequant_q8_kernel, dim3(blocks), dim3(256), 0, st, (const uint4*)q, (const __half*)scales, (uint4*)out_f16, n_vec, K);

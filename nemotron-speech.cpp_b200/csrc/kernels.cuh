@@ -43,7 +43,8 @@ struct GemmArgs {
     // optional row map: A row(m) = (m / group) * group_stride + (m % group + row_off) * lda   (group == 0 -> m * lda)
     int group = 0; long long group_stride = 0; int row_off = 0;
     const void* W = nullptr;      // [N, K] row-major (Q8_0: the int8 quant plane)
-    const void* w_scales = nullptr;   // Q8_0 only: fp16 block scales [N][K/32]; selects the fused-dequant tensor-core kernel
+    const void* w_scales = nullptr;   // Q8_0 / Q4_0 only: fp16 block scales [N][K/32]; selects the fused-dequant tensor-core kernel
+    int q4 = 0;                       // W is a Q4_0 nibble plane [N][K/2] (two values per byte as in the GGUF block) instead of an int8 plane
     int M = 0, N = 0, K = 0;
     const float* bias = nullptr;  // [N] or null
     void* C = nullptr; long long ldc = 0;
@@ -93,7 +94,7 @@ struct AttnFullArgs {
     const float* bias_u; const float* bias_v; void* ctx; int out_type; int T;
 };
 void launch_attention_full(const AttnFullArgs& a, cudaStream_t st);
-void launch_dequant_q8(const void* q, const void* scales, void* out_f16, int N, int K, cudaStream_t st);   // gemm_tc.cu
+void launch_dequant_q8(const void* q, const void* scales, void* out_f16, int N, int K, cudaStream_t st, int q4 = 0);   // gemm_tc.cu (q4: Q4_0 nibble plane)
 bool pair_gemm_enabled();         // gemm_tc.cu: CTA-pair tiles on (default) / off (NSB_PAIR_GEMM=0)
 
 struct ConvModArgs {

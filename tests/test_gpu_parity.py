@@ -133,7 +133,7 @@ def test_logmel_kernel_parity(built):
     eng.close()
 
 
-@pytest.mark.parametrize("wtype,compute,mm", [("f32", 2, O.MM_F16), ("f32", 3, O.MM_BF16), ("q8_0", 0, O.MM_Q8FAST)])
+@pytest.mark.parametrize("wtype,compute,mm", [("f32", 2, O.MM_F16), ("f32", 3, O.MM_BF16), ("q8_0", 0, O.MM_Q8FAST), ("q4_0", 0, O.MM_Q8FAST)])
 def test_tcgen05_gemm_parity(built, wtype, compute, mm):
     import nsb200
     path = synth.cached_model(wtype, 2, R=0)
@@ -153,7 +153,7 @@ def test_tcgen05_gemm_parity(built, wtype, compute, mm):
     eng.close()
 
 
-@pytest.mark.parametrize("wtype,compute,mm", [("f32", 2, O.MM_F16), ("f32", 3, O.MM_BF16), ("q8_0", 0, O.MM_Q8FAST)])
+@pytest.mark.parametrize("wtype,compute,mm", [("f32", 2, O.MM_F16), ("f32", 3, O.MM_BF16), ("q8_0", 0, O.MM_Q8FAST), ("q4_0", 0, O.MM_Q8FAST)])
 def test_tcgen05_gemm_large_batch_pair_tiles(built, wtype, compute, mm):
     """>= 4 row tiles: 256-row CTA-pair tiles (cta_group::2, M = 256) with BN in {256, 208, 160, 112} chosen per shape -- every
     BN, the overhang of the last tile along N (4096 = 19 x 208 + 144), a ragged last row tile (900 = 3 x 256 + 132), and in
@@ -212,7 +212,8 @@ def test_streaming_parity_f32_full_24_layer_model(built):
     ("f16", 0, 1, O.MM_REF, O.KV_F16, 3e-3, 2e-2, 1),       # F16 GGUF -> ggml F16 semantics (+ fp16 K/V ring)
     ("f32", 3, 2, O.MM_BF16, O.KV_BF16, 3e-2, 2e-1, 1),
     ("q8_0", 0, 0, O.MM_Q8FAST, O.KV_F32, 3e-3, 2e-2, 1),
-    ("q4_0", 0, 0, O.MM_Q8FAST, O.KV_F32, 3e-3, 2e-2, 1),    # Q4_0 GGUF: matrices expanded to fp16 at load, fp16 tcgen05 path
+    ("q4_0", 0, 0, O.MM_Q8FAST, O.KV_F32, 3e-3, 2e-2, 1),    # Q4_0 GGUF: nibbles resident in HBM, dequantisation fused into the GEMM operand path
+    ("q4_0", 2, 1, O.MM_Q8FAST, O.KV_F16, 3e-3, 2e-2, 1),    # the same file expanded to fp16 at load (NSB_COMPUTE_F16): same operand values
     ("f16", 0, 1, O.MM_REF, O.KV_F16, 3e-3, 2e-2, 0),       # 80 ms mode (T = 1): paired attention kernel, odd batches
     ("f16", 0, 1, O.MM_REF, O.KV_F16, 3e-3, 2e-2, 6),       # 560 ms mode (T = 7): tiled attention kernel with a 16-bit ring
 ])
