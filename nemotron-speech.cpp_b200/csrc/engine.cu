@@ -552,7 +552,7 @@ void Engine::build_pos_tables(const GgufFile& g) {
 
 void Engine::gemm(const void* A, long long lda, const Weight& W, int M, const float* bias, void* C, long long ldc, int epi, float alpha,
                   int out_type) {
-    GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.w_scales = W.scales.p; a.M = M; a.N = W.n_out; a.K = W.n_in; a.bias = bias; a.C = C; a.ldc = ldc;
+    GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.w_scales = W.scales.p; a.q4 = W.q4; a.M = M; a.N = W.n_out; a.K = W.n_in; a.bias = bias; a.C = C; a.ldc = ldc;
     a.epi = epi; a.alpha = alpha; a.out_type = out_type; a.pair = 1; a.q4 = W.q4;
     ProfScope ps(this, PC_GEMM);
     if (cur_shadow_ && W.shadow_slot >= 0) { a.W = cur_shadow_ + shadow_off_[W.shadow_slot]; a.w_scales = nullptr; a.q4 = 0; }   // dequantised a layer ahead
@@ -620,7 +620,7 @@ bool Engine::split_consumers(int rows) const {
 
 // split-K GEMM whose fp32 partial planes C[z][M][N] are left for the consumer kernel to sum (QKV -> attention, pointwise-1 -> conv module)
 void Engine::gemm_planes(const void* A, long long lda, const Weight& W, int M, void* C, int planes) {
-    GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.w_scales = W.scales.p; a.M = M; a.N = W.n_out; a.K = W.n_in; a.C = C; a.ldc = W.n_out;
+    GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.w_scales = W.scales.p; a.q4 = W.q4; a.M = M; a.N = W.n_out; a.K = W.n_in; a.C = C; a.ldc = W.n_out;
     a.epi = EPI_PARTIAL; a.out_type = OUT_F32; a.splits = planes; a.force_bn = 64; a.force_stages = 4;
     { ProfScope ps(this, PC_GEMM); launch_gemm_tc(a, act_type(), st_); }
     count_launch();
@@ -641,7 +641,7 @@ void Engine::gemm_residual(const void* A, long long lda, const Weight& W, int M,
     static const int big_split = [] { const char* e = getenv("NSB_FFDOWN_SPLIT"); return e ? atoi(e) : 2; }();
     if (!strict() && M > 1024 && W.n_in >= 4096 && big_split > 1 && (size_t)big_split * M * D_MODEL * 4 <= part_.bytes) splits = big_split;
     if (splits == 1) { gemm(A, lda, W, M, nullptr, x, D_MODEL, EPI_RESID, alpha, OUT_F32); return; }
-    GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.w_scales = W.scales.p; a.M = M; a.N = W.n_out; a.K = W.n_in; a.C = part_.p; a.ldc = D_MODEL;
+    GemmArgs a; a.A = A; a.lda = lda; a.W = W.data.p; a.w_scales = W.scales.p; a.q4 = W.q4; a.M = M; a.N = W.n_out; a.K = W.n_in; a.C = part_.p; a.ldc = D_MODEL;
     a.epi = EPI_PARTIAL; a.out_type = OUT_F32; a.splits = splits;
     { ProfScope ps(this, PC_GEMM);
       if (cur_shadow_ && W.shadow_slot >= 0) { a.W = cur_shadow_ + shadow_off_[W.shadow_slot]; a.w_scales = nullptr; } else q8_predequant(W, M, a);
@@ -1115,7 +1115,7 @@ float Engine::bench_gemm(int kind, int rows, int bn, int stages, int splits, int
                 pending_ = PartialSum{}; cur_shadow_ = nullptr;
                 continue;
             }
-            GemmArgs a; a.A = W.n_in == D_FF ? big_.p : a_.p; a.lda = W.n_in; a.W = W.data.p; a.w_scales = W.scales.p; a.M = rows; a.N = W.n_out; a.K = W.n_in;
+            GemmArgs a; a.A = W.n_in == D_FF ? big_.p : a_.p; a.lda = W.n_in; a.W = W.data.p; a.w_scales = W.scales.p; a.q4 = W.q4; a.M = rows; a.N = W.n_out; a.K = W.n_in;
             a.force_bn = bn; a.force_stages = stages; a.rotate = rotate; a.splits = splits; a.ldc = W.n_out; a.pair = splits == 1;
             if (splits > 1) { a.C = part_.p; a.epi = EPI_PARTIAL; a.out_type = OUT_F32; }
             else if (W.n_out == D_FF) { a.C = big_.p; a.epi = EPI_SILU; a.out_type = act_type(); }

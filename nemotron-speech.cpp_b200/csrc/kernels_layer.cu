@@ -992,9 +992,7 @@ void launch_attention(const AttnArgs& a, cudaStream_t st) {
 // One CTA per (block of TB frames, stream): 256 threads x 4 channels, a 9-deep register window slides over the block's frames.
 // The window is primed with the 8 rows before the block: rows of the conv state where they precede the chunk, GLU rows of earlier
 // frames recomputed from the pointwise-1 output otherwise (8 x 4 sigmoids per thread, all loads in flight at once) -- a fixed cost
-// per block, so TB trades redundancy against the length of the serial chain: TB = T for chunks of <= 4 frames (one block, nothing
-// recomputed), 4 frames otherwise (T = 14: 4 blocks per stream, ~6 us instead of 17 us per layer; the batch path's T ~ 2000 frames
-// become 500 independent CTAs instead of one). The LAST block writes the new state xp[T .. T + 7] (:368-381) into the OTHER parity of
+// per block, so TB trades redundancy against the length of the serial chain (launch_conv_module picks it). The LAST block writes the new state xp[T .. T + 7] (:368-381) into the OTHER parity of
 // the double-buffered state: CTAs of earlier blocks may still be reading the old one.
 // Same tap order and LayerNorm per frame as a single sequential pass: bit-identical results.
 // (Tried and dropped: one CTA per frame -- 9x the GLU work and pointwise-1 reads; 33 us instead of 17 us per layer at 64 x 14 frames.)
@@ -1090,7 +1088,9 @@ __global__ void __launch_bounds__(256) conv_module_kernel(const ConvModArgs a, i
 }
 void launch_conv_module(const ConvModArgs& a, cudaStream_t st) {
     static const int tb_env = [] { const char* e = getenv("NSB_CONV_TB"); return e ? atoi(e) : 0; }();
-    const int TB = tb_env > 0 ? tb_env : (a.T <= 4 ? a.T : 4);
+    // one block (nothing recomputed) up to 8 frames; two blocks at T = 14 (measured within 1 % of each other and of TB = 4 / 14 on the
+    // 64-stream step); 8-frame blocks beyond that (the batch path: hundreds of independent CTAs instead of one sequential walk)
+    const int TB = tb_env > 0 ? tb_env : (a.T <= 8 ? a.T : a.T <= 16 ? (a.T + 1) / 2 : 8);
     if (a.B > 0 && a.T > 0) launch_k(conv_module_kernel, dim3((a.T + TB - 1) / TB, a.B), dim3(256), 0, st, a, TB);
 }
 
