@@ -37,6 +37,13 @@ static bool pair256_enabled() {
     return on;
 }
 
+// persistent variant of the 256-row pair tiles (two TMEM accumulators, one ring across tiles): NSB_PAIR256_PERSIST=0/1, read per launch
+// (launches happen at graph capture, not at replay) so that a test can switch it between engines of one process
+static bool pair256_persist_enabled() {
+    const char* e = getenv("NSB_PAIR256_PERSIST");
+    return e ? e[0] == '1' : false;
+}
+
 static int pair256_min_tiles() {
     static const int v = [] { const char* e = getenv("NSB_PAIR256_MIN_TILES"); return e ? atoi(e) : 4; }();
     return v;
@@ -198,9 +205,11 @@ constexpr int EPI_STAGE_BYTES = 4 * 32 * EPI_RS * 4;             // 4 epilogue w
 
 // row0 = global output row of lane 0 of this warp (its TMEM lanes are (warp % 4) * 32 ..), n0 = global column of TMEM column 0,
 // BN = number of accumulator columns this warp reads, stage = this CTA's staging area (EPI_STAGE_BYTES, 16-byte aligned)
+// parity / zs: phase of the accumulator barrier and k-slice of the tile (persistent kernel: several tiles per CTA; otherwise 0 / blockIdx.z)
 template <int BN>
 __device__ __forceinline__ void tc_epilogue_at(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full, int warp, int row0, int n0, int trace_slot,
-                                               uint8_t* stage_base) {
+                                               uint8_t* stage_base, uint32_t parity = 0, int zs = -1) {
+        const int zslice = zs >= 0 ? zs : (int)blockIdx.z;
         const bool tracer = trace_slot >= 0 && threadIdx.x == 64;
         const int q = warp & 3, lane = threadIdx.x & 31;
         float* stage = reinterpret_cast<float*>(stage_base) + q * 32 * EPI_RS;
@@ -216,9 +225,9 @@ __device__ __forceinline__ void tc_epilogue_at(const TcParams& p, uint32_t tmem_
         }
         float* part_base = nullptr;
         if (p.epi == EPI_PARTIAL)
-            part_base = p.C0 ? (blockIdx.z == 0 ? (float*)p.C0 : (float*)p.C + (size_t)(blockIdx.z - 1) * p.m_out * p.ldc)
-                             : (float*)p.C + (size_t)blockIdx.z * p.m_out * p.ldc;
-        const bool add_bias = p.bias && (p.epi != EPI_PARTIAL || blockIdx.z == 0);
+            part_base = p.C0 ? (zslice == 0 ? (float*)p.C0 : (float*)p.C + (size_t)(zslice - 1) * p.m_out * p.ldc)
+                             : (float*)p.C + (size_t)zslice * p.m_out * p.ldc;
+        const bool add_bias = p.bias && (p.epi != EPI_PARTIAL || zslice == 0);
         const bool out16 = p.epi != EPI_PARTIAL && p.epi != EPI_RESID && p.out_type != OUT_F32;
         int orow_own = -1;                                      // output row of this thread's own TMEM lane (16-bit path)
         {
@@ -229,7 +238,7 @@ __device__ __forceinline__ void tc_epilogue_at(const TcParams& p, uint32_t tmem_
         }
         pdl_wait();                                             // C / bias may be produced (or still read) by the previous kernel
         if (tracer) trace_mark(trace_slot, 2);
-        mbar_wait(tmem_full, 0);
+        mbar_wait(tmem_full, parity);
         tc_fence_after();
         if (tracer) trace_mark(trace_slot, 3);
 #pragma unroll 1
@@ -633,6 +642,145 @@ gemm_tc_pair256_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------
+// The same 256 x BN pair tile as a PERSISTENT kernel: one CTA pair per SM pair walks the (k-slice, m, n) tiles of the problem
+// (n fastest: the pairs running side by side share the A rows in L2), with TWO accumulators in tensor memory (2 x up to 256 columns =
+// all of it: one CTA per SM). The TMA ring never drains between tiles, the MMA warp starts tile i + 1 into the other accumulator as
+// soon as its operands land, and the epilogue warps of both CTAs drain tile i meanwhile -- what the one-tile kernel above gets only
+// from a second co-resident CTA (at half the shared memory = half the stages each). The epilogue patch has its own shared memory.
+// Barriers: full / empty per stage as above; tmem_full[acc] (leader's commit, multicast to both CTAs) and tmem_empty[acc] in the
+// LEADER (8 arrivals: the four epilogue warps of each CTA, the peer's through mapa + a cluster-scope arrive).
+// ------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct SmemPairP {
+    alignas(1024) uint8_t a[STAGES][BM * ROW_BYTES];
+    alignas(1024) uint8_t b[STAGES][(BN / 2) * ROW_BYTES];
+    alignas(16) uint8_t epi[EPI_STAGE_BYTES];
+    alignas(8) uint64_t full[STAGES];
+    uint64_t empty[STAGES];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_slot;
+    int trace_slot;
+};
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {    // arrive on the barrier at this offset in CTA `cta` of the cluster
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_pair256_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p, int tiles_n, int tiles_m,
+                               int splits) {
+    static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "pair256 tile: UMMA N is a multiple of 16 up to 256");
+    extern __shared__ uint8_t smem_raw[];
+    using S = SmemPairP<BN, STAGES>;
+    S& s = *reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
+    constexpr int BK = ROW_BYTES / 2;
+    const int nk = p.K / BK / splits;
+    const int total = tiles_n * tiles_m * splits;
+    constexpr uint32_t ACC_COLS = tmem_cols_for(BN);
+    constexpr uint32_t HALF_BYTES = (BM + BN / 2) * ROW_BYTES;
+
+    if (threadIdx.x == 0) {
+        s.trace_slot = blockIdx.x == 0 ? trace_begin(TR_GEMM_TC) : -1;
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s.tmem_full[i], 1); mbar_init(&s.tmem_empty[i], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 2) tmem_alloc_pair(&s.tmem_slot, 2 * ACC_COLS);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = s.tmem_slot;
+    if (threadIdx.x == 0) { pdl_trigger(); trace_mark(s.trace_slot, 1); }
+    // tile w -> k-slice z, m tile, n tile (n fastest)
+    auto tile_of = [&](int w, int& z, int& m0, int& n0) {
+        const int nt = w % tiles_n, r = w / tiles_n;
+        z = r / tiles_m; m0 = (r % tiles_m) * (2 * BM); n0 = nt * BN;
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs, each its halves): one ring across all tiles =====================
+        if (elect_one()) {
+            int g = 0;                                                          // k-blocks issued so far
+            bool waited = false;
+            for (int w = pair; w < total; w += npairs) {
+                int z, m0, n0; tile_of(w, z, m0, n0);
+                const int a_row = m0 + (int)rank * BM, b_row = n0 + (int)rank * (BN / 2), kb0 = z * nk;
+                int kb = 0;
+                if (!waited) {
+                    // first tile: weights of the first stages BEFORE the dependency wait (they do not depend on the previous kernel)
+                    const int pre = nk < STAGES ? nk : STAGES;
+                    if (p.w_dyn) pdl_wait();
+                    for (int i = 0; i < pre; ++i) {
+                        if (rank == 0) mbar_expect_tx(&s.full[i], 2 * HALF_BYTES);
+                        tma_load_2d_pair(s.b[i], &tmB, &s.full[i], (kb0 + i) * BK, b_row);
+                    }
+                    if (!p.w_dyn) pdl_wait();
+                    for (int i = 0; i < pre; ++i) tma_load_2d_pair(s.a[i], &tmA, &s.full[i], (kb0 + i) * BK, a_row);
+                    kb = pre; g = pre; waited = true;
+                }
+                for (; kb < nk; ++kb, ++g) {
+                    const int st = g % STAGES; const uint32_t ph = (g / STAGES) & 1;
+                    if (g >= STAGES) mbar_wait(&s.empty[st], ph ^ 1);
+                    if (rank == 0) mbar_expect_tx(&s.full[st], 2 * HALF_BYTES);
+                    tma_load_2d_pair(s.a[st], &tmA, &s.full[st], (kb0 + kb) * BK, a_row);
+                    tma_load_2d_pair(s.b[st], &tmB, &s.full[st], (kb0 + kb) * BK, b_row);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (rank == 0 && elect_one()) {
+            const uint32_t idesc = make_idesc(p.fmt, BN, 2 * BM);
+            int g = 0, it = 0;
+            for (int w = pair; w < total; w += npairs, ++it) {
+                const uint32_t acc = it & 1;
+                mbar_wait(&s.tmem_empty[acc], (((uint32_t)it >> 1) & 1) ^ 1);   // both CTAs' epilogue warps have drained this accumulator (free at first use)
+                tc_fence_after();
+                const uint32_t tmem_c = tmem_base + acc * ACC_COLS;
+                for (int kb = 0; kb < nk; ++kb, ++g) {
+                    const int st = g % STAGES; const uint32_t ph = (g / STAGES) & 1;
+                    mbar_wait(&s.full[st], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(s.a[st]), b_addr = smem_u32(s.b[st]);
+#pragma unroll
+                    for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k)
+                        umma_f16_pair(tmem_c, make_desc(a_addr + k * UMMA_K_BYTES), make_desc(b_addr + k * UMMA_K_BYTES), idesc, (kb | k) ? 1u : 0u);
+                    umma_commit_pair(&s.empty[st]);
+                }
+                umma_commit_pair(&s.tmem_full[acc]);
+            }
+        }
+    } else {
+        // ===================== epilogue (both CTAs: 128 rows x BN columns of every tile) =====================
+        int it = 0;
+        for (int w = pair; w < total; w += npairs, ++it) {
+            int z, m0, n0; tile_of(w, z, m0, n0);
+            const uint32_t acc = it & 1;
+            tc_epilogue_at<BN>(p, tmem_base + acc * ACC_COLS, &s.tmem_full[acc], warp, m0 + (int)rank * BM + (warp & 3) * 32, n0, it == 0 ? s.trace_slot : -1,
+                               s.epi, ((uint32_t)it >> 1) & 1, z);
+            tc_fence_before();                                                  // this warp's tcgen05.ld of the accumulator are complete (wait::ld inside)
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&s.tmem_empty[acc], 0);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc_pair(tmem_base, 2 * ACC_COLS);
+}
+
+// ------------------------------------------------------------------------------------------
 // Q8_0 weights with the dequantisation fused into the operand path. The weight stays in HBM as the GGUF holds it, split
 // into two planes at load (int8 quants [N][K], fp16 block scales [N][K/32]; the 34-byte blocks are not TMA-friendly).
 // Per k-block: TMA brings the A tile (fp16, swizzled) and the RAW int8 W tile [BN][64]; warps 2-5 turn it into the fp16
@@ -895,6 +1043,31 @@ void launch_cfg_pair256(const GemmArgs& a, int fmt, cudaStream_t st) {
     dim3 grid(2 * ((a.N + BN - 1) / BN), (a.M + 2 * BM - 1) / (2 * BM), a.splits);
     launch_k_cluster(gemm_tc_pair256_kernel<BN, STAGES>, grid, dim3(TC_THREADS), smem, st, 2, tmA, tmB, p);
 }
+template <int BN, int STAGES>
+void launch_cfg_pair256_persist(const GemmArgs& a, int fmt, cudaStream_t st) {
+    static std::atomic<size_t> attr_set[MAX_DEVICES];
+    const size_t smem = sizeof(SmemPairP<BN, STAGES>) + 1024;
+    ensure_dyn_smem(gemm_tc_pair256_persist_kernel<BN, STAGES>, smem, attr_set);
+    const CUtensorMap tmA = make_map(a.A, a.M, a.K, a.lda, BM, fmt);
+    const CUtensorMap tmB = make_map(a.W, a.N, a.K, a.K, BN / 2, fmt);
+    const int m_out = a.c_group > 0 ? (a.M / a.c_group) * (a.c_group - a.c_drop) : a.M;
+    TcParams p{a.M, a.N, a.K, a.bias, a.C, a.ldc, a.epi, a.alpha, a.out_type, fmt, 0, a.c_group, a.c_drop, a.C0, m_out, a.w_dynamic};
+    const int tiles_n = (a.N + BN - 1) / BN, tiles_m = (a.M + 2 * BM - 1) / (2 * BM), splits = a.splits > 1 ? a.splits : 1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int npairs = std::min(tiles_n * tiles_m * splits, sms / 2);
+    launch_k_cluster(gemm_tc_pair256_persist_kernel<BN, STAGES>, dim3(2 * npairs), dim3(TC_THREADS), smem, st, 2, tmA, tmB, p, tiles_n, tiles_m, splits);
+}
+void launch_pair256_persist(const GemmArgs& a, int fmt, int bn, cudaStream_t st) {
+    switch (bn) {                                                   // stages: what fits next to the 18 KB epilogue patch in 227 KB
+        case 256: launch_cfg_pair256_persist<256, 6>(a, fmt, st); break;
+        case 208: launch_cfg_pair256_persist<208, 6>(a, fmt, st); break;
+        case 160: launch_cfg_pair256_persist<160, 7>(a, fmt, st); break;
+        case 128: launch_cfg_pair256_persist<128, 8>(a, fmt, st); break;
+        case 112: launch_cfg_pair256_persist<112, 8>(a, fmt, st); break;
+        default: throw CudaError("gemm_tc: persistent pair256 tile not instantiated");
+    }
+}
 // Pair tiles for large batches: BN per shape so that the pair tiles fill whole waves of the 74 SM pairs. Per-SM cost of a tile
 // ~ the bytes it stages per k-block, (128 + BN/2) rows (+ a fixed share for prologue / epilogue that does not overlap).
 int pick_pair256_bn(int M, int N) {
@@ -1027,6 +1200,7 @@ void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
     if (a.force_bn) {                                             // tuning hook
         if (a.splits > 1 && (a.epi != EPI_PARTIAL || (a.K / BK) % a.splits != 0)) throw CudaError("gemm_tc: bad split-K request");
         if (a.force_stages == 97) { if (fmt == 2) throw CudaError("gemm_tc: pair tiles are 16-bit only"); launch_pair256(a, fmt, a.force_bn, st); return; }
+        if (a.force_stages == 96) { if (fmt == 2) throw CudaError("gemm_tc: pair tiles are 16-bit only"); launch_pair256_persist(a, fmt, a.force_bn, st); return; }
         const int key = a.force_bn * 100 + a.force_stages;
         switch (key) {
             case 3204: launch_cfg<32, 4>(a, fmt, st); break;
@@ -1047,7 +1221,8 @@ void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
         if (a.epi != EPI_PARTIAL || (a.K / BK) % a.splits != 0) throw CudaError("gemm_tc: bad split-K request");
         if (fmt != 2 && tiles_m >= 8 && pair256_enabled()) {            // large-batch split-K (FFN down): wide pair tiles
             static const int bn = [] { const char* e = getenv("NSB_SPLIT_BN"); return e ? atoi(e) : 112; }();
-            launch_pair256(a, fmt, bn, st); return;
+            if (pair256_persist_enabled()) launch_pair256_persist(a, fmt, bn, st); else launch_pair256(a, fmt, bn, st);
+            return;
         }
         if (a.N % 128 == 0 && a.M > 128 && fmt == 2) { launch_cfg<128, 4>(a, fmt, st); return; }
         if (a.N % 64 == 0 && a.K >= 4096) launch_cfg<64, 4>(a, fmt, st); else launch_cfg<32, 5>(a, fmt, st);
@@ -1065,7 +1240,7 @@ void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
     //  read-modify-write epilogue they run with in the step: left on the pair tiles)
     if (fmt != 2 && tiles_m >= pair256_min_tiles() && pair256_enabled()) {
         const int bn = pick_pair256_bn(a.M, a.N);
-        if (bn) { launch_pair256(a, fmt, bn, st); return; }
+        if (bn) { if (pair256_persist_enabled()) launch_pair256_persist(a, fmt, bn, st); else launch_pair256(a, fmt, bn, st); return; }
     }
     const long long t256 = a.N % 256 == 0 ? (long long)tiles_m * (a.N / 256) : 0, t128 = a.N % 128 == 0 ? (long long)tiles_m * (a.N / 128) : 0;
     if (t256 >= 200) launch_cfg<256, 2>(a, fmt, st);

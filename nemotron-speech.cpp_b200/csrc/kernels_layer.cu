@@ -951,6 +951,264 @@ static void launch_attention_mma(const AttnArgs& a, cudaStream_t st) {
     ensure_dyn_smem(attention_mma_kernel<KV, NS>, lay.total, configured, true);
     launch_k(attention_mma_kernel<KV, NS>, dim3(N_HEADS, (a.B + NS - 1) / NS), dim3(128 * NS), lay.total, st, a);
 }
+
+// ------------------------------------------------------------------------------------------
+// The same arithmetic for LARGE batches (8 x B >> resident CTAs; 256 streams x 7 frames = 2048 (head, stream) items): the kernel above
+// hides its load -> score -> load -> softmax -> PV chain only through occupancy (4 CTAs per SM, 3.5 waves, 42 us per layer for the
+// 13 us of ring bytes). Here a CTA keeps ONE head, stages that head's positional rows once and walks its streams with the K / V tiles
+// of the next stream (cp.async into a three-tile ring: K_i, V_i, K_i+1; V_i+1 takes K_i's place after the scores) and the next
+// stream's q / k / v rows (registers) in flight under the current stream's MMAs. Two CTAs per SM. Same instructions per item in the
+// same order as attention_mma_kernel<KV, 1>: bit-identical output.
+// ------------------------------------------------------------------------------------------
+struct AttnStreamLayout {
+    int kpad, rpad, n_rel;
+    size_t ps, zero, tile0, tile_bytes, qu, qv, pat, ac, bd, total;          // three K / V tiles from tile0
+    __host__ __device__ AttnStreamLayout(int T) {
+        const int K = ATT_L + T;
+        n_rel = ATT_L + 2 * T - 1; kpad = (K + 15) & ~15; rpad = (n_rel + 7) & ~7;
+        const size_t row = ATT_RS * 2;
+        ps = 0; zero = ps + (size_t)rpad * row;
+        size_t o = zero + row;
+        tile0 = o; tile_bytes = (size_t)kpad * row; o += 3 * tile_bytes;
+        qu = o; o += (size_t)T * row; qv = o; o += (size_t)T * row;
+        pat = o; o += (size_t)T * (kpad + 8) * 2; o = (o + 15) & ~(size_t)15;
+        ac = o; o += (size_t)T * kpad * 4; bd = o; o += (size_t)T * rpad * 4;
+        total = (o + 15) & ~(size_t)15;
+    }
+};
+constexpr int ATT_STREAM_MAX_T = 8;                                               // one pass of the 4-rows-per-thread q / k / v staging
+
+// this chunk's q / k / v rows of one (stream, head): fp32 GEMM output, split-K planes folded in slice order; a thread owns two adjacent
+// head dims (t2) of every second row (rsel)
+__device__ __forceinline__ void att_load_rows(const AttnArgs& a, int bb, int h, int T, int rsel, int t2, float2 (&q)[4], float2 (&kn)[4], float2 (&vn)[4]) {
+    const float* qkv = a.qkv + (size_t)bb * T * 3 * D_MODEL + h * D_HEAD;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int i = rsel + 2 * u;
+        if (i < T) {
+            const float* row = qkv + (size_t)i * 3 * D_MODEL + t2;
+            q[u] = *reinterpret_cast<const float2*>(row); kn[u] = *reinterpret_cast<const float2*>(row + D_MODEL); vn[u] = *reinterpret_cast<const float2*>(row + 2 * D_MODEL);
+            for (int z = 1; z < a.planes; ++z) {
+                const float* rz = row + (size_t)z * a.plane_stride;
+                const float2 q2 = *reinterpret_cast<const float2*>(rz), k2 = *reinterpret_cast<const float2*>(rz + D_MODEL), v2 = *reinterpret_cast<const float2*>(rz + 2 * D_MODEL);
+                q[u].x += q2.x; q[u].y += q2.y; kn[u].x += k2.x; kn[u].y += k2.y; vn[u].x += v2.x; vn[u].y += v2.y;
+            }
+        }
+    }
+}
+
+template <int KV>
+__global__ void __launch_bounds__(128, 2) attention_mma_stream_kernel(const AttnArgs a, int G) {
+    using E = typename KvT<KV>::type;
+    static_assert(KV != 0, "16-bit ring only");
+    constexpr int EPV = 8, VPR = D_HEAD / EPV;
+    extern __shared__ __align__(16) uint8_t att_smem[];
+    const int T = a.T, K = ATT_L + T, Cap = K, B = a.B;
+    const AttnStreamLayout lay(T);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int h = blockIdx.x;
+    E* Ps = reinterpret_cast<E*>(att_smem + lay.ps);
+    E* Zero = reinterpret_cast<E*>(att_smem + lay.zero);
+    E* Qu = reinterpret_cast<E*>(att_smem + lay.qu);
+    E* Qv = reinterpret_cast<E*>(att_smem + lay.qv);
+    E* Pat = reinterpret_cast<E*>(att_smem + lay.pat);
+    float* Ac = reinterpret_cast<float*>(att_smem + lay.ac);
+    float* Bd = reinterpret_cast<float*>(att_smem + lay.bd);
+    const int kpad = lay.kpad, rpad = lay.rpad, n_rel = lay.n_rel, pat_rs = kpad + 8;
+    NSB_KERNEL_BEGIN(TR_ATTN)
+    const E* P = reinterpret_cast<const E*>(a.pos_proj) + h * D_HEAD;
+    for (int e = tid; e < rpad * VPR; e += 128) {
+        const int r = e / VPR, c = (e % VPR) * EPV;
+        if (r < n_rel) cp_async16(Ps + (size_t)r * ATT_RS + c, P + (size_t)r * D_MODEL + c);
+        else *reinterpret_cast<uint4*>(Ps + (size_t)r * ATT_RS + c) = make_uint4(0, 0, 0, 0);
+    }
+    for (int e = tid; e < VPR; e += 128) *reinterpret_cast<uint4*>(Zero + e * EPV) = make_uint4(0, 0, 0, 0);
+    struct St { int slot, rbase, first; };                                        // per-stream ring state
+    auto load_st = [&](int b) {
+        St s; s.slot = a.slot_of_b[b];
+        s.rbase = a.ring_pos[s.slot] + Cap - ATT_L;                               // ring row of key j: (rbase + j) mod Cap
+        s.first = ATT_L - a.valid_len[s.slot];                                    // keys j < first are not yet valid (:982-992)
+        return s;
+    };
+    auto ring_row = [&](const St& s, int j) { int r = s.rbase + j; r -= r >= Cap ? Cap : 0; r -= r >= Cap ? Cap : 0; return (size_t)r * D_MODEL; };
+    // cached rows of one tile: cp.async for the valid ones, zeros for the not-yet-valid and the padding rows (rows ATT_L .. K-1 = this
+    // chunk's rows are written by the staging step)
+    auto issue_tile = [&](E* dst, void* ring_base, const St& s) {
+        const E* ring = reinterpret_cast<const E*>(ring_base) + (size_t)s.slot * a.slot_stride + h * D_HEAD;
+        for (int e = tid; e < kpad * VPR; e += 128) {
+            const int j = e / VPR, c = (e % VPR) * EPV;
+            if (j >= s.first && j < ATT_L) cp_async16(dst + (size_t)j * ATT_RS + c, ring + ring_row(s, j) + c);
+            else if (j < s.first || j >= K) *reinterpret_cast<uint4*>(dst + (size_t)j * ATT_RS + c) = make_uint4(0, 0, 0, 0);
+        }
+    };
+    int b = blockIdx.y, kt = 0, vt = 1;
+    St cur = load_st(b), nxt = cur;
+    issue_tile(reinterpret_cast<E*>(att_smem + lay.tile0), a.k_ring, cur);
+    asm volatile("cp.async.commit_group;" ::: "memory");                        // group: P + K_0
+    issue_tile(reinterpret_cast<E*>(att_smem + lay.tile0 + lay.tile_bytes), a.v_ring, cur);
+    asm volatile("cp.async.commit_group;" ::: "memory");                        // group: V_0
+    if (b + G < B) nxt = load_st(b + G);
+    struct alignas(4) E2 { E a, b; };
+    const int t2 = (tid & 63) * 2, rsel = tid >> 6;
+    const float2 bu = *reinterpret_cast<const float2*>(a.bias_u + h * D_HEAD + t2), bv = *reinterpret_cast<const float2*>(a.bias_v + h * D_HEAD + t2);
+    float2 q[4], kn[4], vn[4];
+    NSB_KERNEL_WAIT()
+    att_load_rows(a, b, h, T, rsel, t2, q, kn, vn);
+    const int g = lane >> 2, tq = lane & 3;
+    const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_col = (lane >> 4) * 8;
+    const float scale = 0.08838834764831845f;                                   // 1/sqrt(128) :517
+    bool first_item = true;
+    for (; b < B; b += G) {
+        E* Ks = reinterpret_cast<E*>(att_smem + lay.tile0 + kt * lay.tile_bytes);
+        E* Vs = reinterpret_cast<E*>(att_smem + lay.tile0 + vt * lay.tile_bytes);
+        const bool has_next = b + G < B;
+        // ---- 1. stage this chunk's rows: (q + u), (q + v), new K / V rows (shared memory + ring append :465-484) ----
+        {
+            E* kring = reinterpret_cast<E*>(a.k_ring) + (size_t)cur.slot * a.slot_stride + h * D_HEAD;
+            E* vring = reinterpret_cast<E*>(a.v_ring) + (size_t)cur.slot * a.slot_stride + h * D_HEAD;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = rsel + 2 * u;
+                if (i < T) {
+                    *reinterpret_cast<E2*>(Qu + (size_t)i * ATT_RS + t2) = E2{from_f32<E>(q[u].x + bu.x), from_f32<E>(q[u].y + bu.y)};   // :503-507
+                    *reinterpret_cast<E2*>(Qv + (size_t)i * ATT_RS + t2) = E2{from_f32<E>(q[u].x + bv.x), from_f32<E>(q[u].y + bv.y)};
+                    const E2 ke{from_f32<E>(kn[u].x), from_f32<E>(kn[u].y)}, ve{from_f32<E>(vn[u].x), from_f32<E>(vn[u].y)};
+                    *reinterpret_cast<E2*>(Ks + (size_t)(ATT_L + i) * ATT_RS + t2) = ke;
+                    *reinterpret_cast<E2*>(Vs + (size_t)(ATT_L + i) * ATT_RS + t2) = ve;
+                    const size_t gr = ring_row(cur, ATT_L + i) + t2;
+                    *reinterpret_cast<E2*>(kring + gr) = ke; *reinterpret_cast<E2*>(vring + gr) = ve;
+                }
+            }
+        }
+        // ---- 2. next stream: K tile into the buffer V_{i-1} left, q / k / v rows into registers ----
+        if (has_next) { issue_tile(reinterpret_cast<E*>(att_smem + lay.tile0 + ((kt + 2) % 3) * lay.tile_bytes), a.k_ring, nxt); att_load_rows(a, b + G, h, T, rsel, t2, q, kn, vn); }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 2;" ::: "memory");                     // P and K_i have landed (V_i, K_i+1 may be in flight)
+        __syncthreads();
+        if (first_item && tr_slot >= 0) trace_mark(tr_slot, 3);
+        // ---- 3. AC = Qu K^T and BD_raw = Qv P^T ----
+        {
+            const int nt_ac = (K + 7) / 8, nt_bd = rpad / 8;
+            const E* qa_u = a_row < T ? Qu + (size_t)a_row * ATT_RS + a_col : Zero + a_col;
+            const E* qa_v = a_row < T ? Qv + (size_t)a_row * ATT_RS + a_col : Zero + a_col;
+            const int ntot = nt_ac + nt_bd;
+            for (int tile0 = warp; tile0 < ntot; tile0 += 8) {
+                float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                const E* bp[2]; const E* qa[2]; bool live[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int tile = tile0 + 4 * u;
+                    live[u] = tile < ntot;
+                    const bool is_ac = tile < nt_ac;
+                    const int n0 = live[u] ? (is_ac ? tile : tile - nt_ac) * 8 : 0;
+                    bp[u] = (is_ac ? Ks : Ps) + (size_t)(n0 + (lane & 7)) * ATT_RS + (lane >> 3) * 8;
+                    qa[u] = is_ac ? qa_u : qa_v;
+                }
+#pragma unroll
+                for (int ks = 0; ks < D_HEAD / 32; ++ks) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        uint32_t bf[4], a0[4], a1[4];
+                        ldsm_x4(bf, bp[u] + ks * 32);
+                        ldsm_x4(a0, qa[u] + ks * 32);
+                        ldsm_x4(a1, qa[u] + ks * 32 + 16);
+                        mma_16816<E>(c[u], a0, bf[0], bf[1]);
+                        mma_16816<E>(c[u], a1, bf[2], bf[3]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int tile = tile0 + 4 * u;
+                    if (!live[u]) continue;
+                    const bool is_ac = tile < nt_ac;
+                    const int n0 = (is_ac ? tile : tile - nt_ac) * 8;
+                    float* out = is_ac ? Ac : Bd;
+                    const int ld = is_ac ? kpad : rpad;
+                    if (g < T) { out[g * ld + n0 + 2 * tq] = c[u][0]; out[g * ld + n0 + 2 * tq + 1] = c[u][1]; }
+                    if (g + 8 < T) { out[(g + 8) * ld + n0 + 2 * tq] = c[u][2]; out[(g + 8) * ld + n0 + 2 * tq + 1] = c[u][3]; }
+                }
+            }
+        }
+        __syncthreads();                                                          // K_i is dead
+        // ---- 4. next stream's V tile into K_i's buffer ----
+        if (has_next) issue_tile(Ks, a.v_ring, nxt);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        // ---- 5. softmax over valid keys; rel-shift = index arithmetic: BD[i][j] = BD_raw[i][L + i - j + T-1] (:391-433) ----
+        const int first = cur.first;
+        for (int i = warp; i < T; i += 4) {
+            float mx = -INFINITY;
+            for (int j = first + lane; j < K; j += 32) {
+                const float sc = (Ac[i * kpad + j] + Bd[i * rpad + ATT_L + i - j + T - 1]) * scale;
+                Ac[i * kpad + j] = sc; mx = fmaxf(mx, sc);
+            }
+            mx = warp_max(mx);
+            float sum = 0.f;
+            for (int j = first + lane; j < K; j += 32) { const float e = expf(Ac[i * kpad + j] - mx); Ac[i * kpad + j] = e; sum += e; }
+            sum = warp_sum(sum);
+            const float inv = 1.0f / sum;
+            for (int j = lane; j < kpad; j += 32)
+                Pat[(size_t)i * pat_rs + j] = from_f32<E>(j >= first && j < K ? Ac[i * kpad + j] * inv : 0.f);
+        }
+        asm volatile("cp.async.wait_group 2;" ::: "memory");                     // V_i has landed (K_i+1, V_i+1 may be in flight)
+        __syncthreads();
+        if (first_item && tr_slot >= 0) trace_mark(tr_slot, 4);
+        // ---- 6. ctx = P V ----
+        {
+            const E* pa = a_row < T ? Pat + (size_t)a_row * pat_rs + a_col : Zero + a_col;
+            float c[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { c[u][0] = 0.f; c[u][1] = 0.f; c[u][2] = 0.f; c[u][3] = 0.f; }
+            for (int ks = 0; ks < kpad / 16; ++ks) {
+                uint32_t af[4];
+                ldsm_x4(af, pa + ks * 16);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint32_t bf[2];
+                    ldsm_x2_trans(bf, Vs + (size_t)(ks * 16 + (lane & 15)) * ATT_RS + (warp + 4 * u) * 8);
+                    mma_16816<E>(c[u], af, bf[0], bf[1]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int n0 = (warp + 4 * u) * 8;
+                if (g < T) {
+                    const size_t o = ((size_t)b * T + g) * D_MODEL + h * D_HEAD + n0 + 2 * tq;
+                    store_out(a.ctx, o, c[u][0], a.out_type); store_out(a.ctx, o + 1, c[u][1], a.out_type);
+                }
+                if (g + 8 < T) {
+                    const size_t o = ((size_t)b * T + g + 8) * D_MODEL + h * D_HEAD + n0 + 2 * tq;
+                    store_out(a.ctx, o, c[u][2], a.out_type); store_out(a.ctx, o + 1, c[u][3], a.out_type);
+                }
+            }
+        }
+        __syncthreads();                                                          // V_i, Qu / Qv / Pat / Ac / Bd are free for the next stream
+        cur = nxt;
+        if (b + 2 * G < B) nxt = load_st(b + 2 * G);
+        const int k_next = (kt + 2) % 3; vt = kt; kt = k_next;
+        first_item = false;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    NSB_KERNEL_EPILOGUE();
+}
+
+template <int KV>
+static void launch_attention_mma_stream(const AttnArgs& a, cudaStream_t st) {
+    const AttnStreamLayout lay(a.T);
+    static std::atomic<size_t> configured[MAX_DEVICES];
+    ensure_dyn_smem(attention_mma_stream_kernel<KV>, lay.total, configured, true);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int slots = std::max(1, 2 * sms / N_HEADS);                             // CTA columns that are resident at once (two CTAs per SM)
+    const int per = (a.B + slots - 1) / slots, G = (a.B + per - 1) / per;         // streams per CTA, evened out
+    launch_k(attention_mma_stream_kernel<KV>, dim3(N_HEADS, G), dim3(128), lay.total, st, a, G);
+}
+// NSB_ATT_STREAM=1: whenever T fits. EXPERIMENT, off by default: measured SLOWER than the one-item kernel at 256 streams x 7 frames
+// (62 vs 51 us per launch): the item is not bound by its load latency.
+static bool attention_stream_wanted(const AttnArgs& a) {
+    if (a.T < 3 || a.T > ATT_STREAM_MAX_T) return false;
+    const char* e = getenv("NSB_ATT_STREAM");
+    return e && e[0] == '1';
+}
 static bool attention_mma_enabled() {
     static const bool on = [] { const char* e = getenv("NSB_ATT_MMA"); return !(e && e[0] == '0'); }();
     return on;
@@ -970,7 +1228,9 @@ static void launch_attention_t(const AttnArgs& a, cudaStream_t st) {
     if constexpr (KV != 0) {                                                      // 16-bit ring: tensor-core kernel (T <= 16), else the paired / tiled scalar kernels
         if (a.T <= 16 && attention_mma_enabled()) {
             static const bool ns1 = [] { const char* e = getenv("NSB_ATT_NS1"); return e && e[0] == '1'; }();   // experiment: single-stream CTAs for T <= 2 too
-            if (a.T <= 2 && !ns1) launch_attention_mma<KV, 2>(a, st); else launch_attention_mma<KV, 1>(a, st);
+            if (a.T <= 2 && !ns1) launch_attention_mma<KV, 2>(a, st);
+            else if (attention_stream_wanted(a)) launch_attention_mma_stream<KV>(a, st);
+            else launch_attention_mma<KV, 1>(a, st);
             return;
         }
         if (a.T <= 2 && attention_pair_enabled()) { if (a.T == 1) launch_attention_pair<KV, 1>(a, st); else launch_attention_pair<KV, 2>(a, st); return; }
@@ -989,29 +1249,34 @@ void launch_attention(const AttnArgs& a, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------
 // Conv module core: GLU -> cached causal depthwise conv (k = 9) -> LayerNorm -> SiLU, and the new conv state.
-// One CTA per (block of TB frames, stream): 256 threads x 4 channels, a 9-deep register window slides over the block's frames.
+// One CTA per (block of TB <= 8 frames, stream): 256 threads x 4 channels, a 9-deep register window slides over the block's frames.
 // The window is primed with the 8 rows before the block: rows of the conv state where they precede the chunk, GLU rows of earlier
 // frames recomputed from the pointwise-1 output otherwise (8 x 4 sigmoids per thread, all loads in flight at once) -- a fixed cost
-// per block, so TB trades redundancy against the length of the serial chain (launch_conv_module picks it). The LAST block writes the new state xp[T .. T + 7] (:368-381) into the OTHER parity of
-// the double-buffered state: CTAs of earlier blocks may still be reading the old one.
-// Same tap order and LayerNorm per frame as a single sequential pass: bit-identical results.
-// (Tried and dropped: one CTA per frame -- 9x the GLU work and pointwise-1 reads; 33 us instead of 17 us per layer at 64 x 14 frames.)
+// per block, so TB trades redundancy against the length of the serial chain (launch_conv_module picks it).
+// The frame loop holds NO barrier: a frame's conv outputs are parked in shared memory (each thread reads back only its own), its
+// LayerNorm statistics are reduced inside the warp and left per warp; ONE block-wide exchange after the loop completes the statistics
+// of all frames (two in strict fp32: mean, then centred squares -- the reference's order), then the frames are normalised and stored.
+// (The per-frame block reductions were 2-4 barriers per frame on the critical path: 7 frames x 256 streams took 25 us for 34 MB.)
+// Per frame the arithmetic is the one of a sequential pass with block_sum_256 / block_mean_var_256: same tap order, same trees.
+// The LAST block writes the new state xp[T .. T + 7] (:368-381) into the OTHER parity of the double-buffered state: CTAs of earlier
+// blocks may still be reading the old one.
+// (Tried and dropped: one CTA per frame -- 9x the GLU work and pointwise-1 reads; 33 us instead of 17 us per layer at 64 x 14 frames.
+//  Fully unrolled rows x frames with register accumulators -- 10 k instructions of straight-line code, instruction-fetch bound: +8 us.)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) conv_module_kernel(const ConvModArgs a, int TB) {
+constexpr int CONV_TB = 8;                                                        // frames per CTA, at most
+__global__ void __launch_bounds__(256, 2) conv_module_kernel(const ConvModArgs a, int TB) {
     NSB_KERNEL_BEGIN(TR_CONVMOD)                                                  // taps, conv state (written by this layer's kernel of earlier steps only), LN affine: pre-wait
-    __shared__ float red[16];
+    __shared__ float4 cvs[CONV_TB][256];                                          // conv outputs of the block's frames, [frame][thread]
+    __shared__ float red[CONV_TB][16];
     const int t0 = blockIdx.x * TB, b = blockIdx.y, c0 = threadIdx.x * 4, T = a.T;
-    const int t1 = min(T, t0 + TB);
+    const int t1 = min(T, t0 + TB), nt = t1 - t0;
     const int slot = a.slot_of_b[b], par = a.cc_par[slot] & 1;
+    const int wrp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool f32 = a.out_type == OUT_F32;
     const float* cache = a.conv_cache + (size_t)slot * a.slot_stride + (size_t)par * a.par_stride;
     float* cache_new = a.conv_cache + (size_t)slot * a.slot_stride + (size_t)(par ^ 1) * a.par_stride;
     float win[4][CONV_K];
-    float wk[4][CONV_K];
-#pragma unroll
-    for (int k = 0; k < CONV_K; ++k) {
-        const float4 w4 = *(const float4*)(a.dw_w + (size_t)k * D_MODEL + c0);
-        wk[0][k] = w4.x; wk[1][k] = w4.y; wk[2][k] = w4.z; wk[3][k] = w4.w;
-    }
+    const float4* taps = reinterpret_cast<const float4*>(a.dw_w + c0);          // tap k of the thread's 4 channels: taps[k * 256]; re-read per frame (L1), not held in registers
 #pragma unroll
     for (int k = 0; k < CONV_K - 1; ++k) {                                       // window rows xp[t0 + k] that lie in the state: t0 + k < 8   (xp = [state(8) || glu(T)] :323-328)
         if (t0 + k < CONV_K - 1) {
@@ -1019,70 +1284,116 @@ __global__ void __launch_bounds__(256) conv_module_kernel(const ConvModArgs a, i
             win[0][k] = v.x; win[1][k] = v.y; win[2][k] = v.z; win[3][k] = v.w;
         }
     }
-    const float4 g4 = *(const float4*)(a.ln_g + c0), b4 = *(const float4*)(a.ln_b + c0);
-    const float lg[4] = {g4.x, g4.y, g4.z, g4.w}, lb[4] = {b4.x, b4.y, b4.z, b4.w};
     NSB_KERNEL_WAIT()
     const float* row0 = a.pw1 + (size_t)b * T * 2 * D_MODEL;
     if (t0 > 0) {                                                                // the other window rows: GLU of frames t0 + k - 8 >= 0, recomputed (block-uniform branch)
-        float4 ha[CONV_K - 1], hg[CONV_K - 1];
 #pragma unroll
-        for (int k = 0; k < CONV_K - 1; ++k) {
-            const int r = t0 + k - (CONV_K - 1);
-            if (r >= 0) {
-                const float* rp = row0 + (size_t)r * 2 * D_MODEL;
-                ha[k] = ld4_planes<PW1_MAX_PLANES>(rp + c0, a.planes, a.plane_stride); hg[k] = ld4_planes<PW1_MAX_PLANES>(rp + D_MODEL + c0, a.planes, a.plane_stride);
+        for (int k0 = 0; k0 < CONV_K - 1; k0 += 4) {                             // four rows' loads in flight at a time (registers)
+            float4 ha[4], hg[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = t0 + k0 + k - (CONV_K - 1);
+                if (r >= 0) {
+                    const float* rp = row0 + (size_t)r * 2 * D_MODEL;
+                    ha[k] = ld4_planes<PW1_MAX_PLANES>(rp + c0, a.planes, a.plane_stride); hg[k] = ld4_planes<PW1_MAX_PLANES>(rp + D_MODEL + c0, a.planes, a.plane_stride);
+                }
             }
-        }
 #pragma unroll
-        for (int k = 0; k < CONV_K - 1; ++k) {
-            if (t0 + k - (CONV_K - 1) >= 0) {
-                win[0][k] = ha[k].x * sigmoid_exact(hg[k].x); win[1][k] = ha[k].y * sigmoid_exact(hg[k].y);
-                win[2][k] = ha[k].z * sigmoid_exact(hg[k].z); win[3][k] = ha[k].w * sigmoid_exact(hg[k].w);
+            for (int k = 0; k < 4; ++k) {
+                if (t0 + k0 + k - (CONV_K - 1) >= 0) {
+                    win[0][k0 + k] = ha[k].x * sigmoid_exact(hg[k].x); win[1][k0 + k] = ha[k].y * sigmoid_exact(hg[k].y);
+                    win[2][k0 + k] = ha[k].z * sigmoid_exact(hg[k].z); win[3][k0 + k] = ha[k].w * sigmoid_exact(hg[k].w);
+                }
             }
         }
     }
-    const float* rt0 = row0 + (size_t)t0 * 2 * D_MODEL;
-    float4 av = ld4_planes<PW1_MAX_PLANES>(rt0 + c0, a.planes, a.plane_stride), gv = ld4_planes<PW1_MAX_PLANES>(rt0 + D_MODEL + c0, a.planes, a.plane_stride);
-    for (int t = t0; t < t1; ++t) {
-        float4 av_n = av, gv_n = gv;
-        if (t + 1 < t1) {                                                        // next row's loads overlap this row's reductions
-            const float* rn = row0 + (size_t)(t + 1) * 2 * D_MODEL;
-            av_n = ld4_planes<PW1_MAX_PLANES>(rn + c0, a.planes, a.plane_stride); gv_n = ld4_planes<PW1_MAX_PLANES>(rn + D_MODEL + c0, a.planes, a.plane_stride);
-        }
+    // rows t, t + 1, t + 2 of the block in flight: the loop holds no barrier, so the loads of a warp run ahead of its arithmetic
+    auto row_a = [&](int t) { return ld4_planes<PW1_MAX_PLANES>(row0 + (size_t)(t0 + t) * 2 * D_MODEL + c0, a.planes, a.plane_stride); };
+    auto row_g = [&](int t) { return ld4_planes<PW1_MAX_PLANES>(row0 + (size_t)(t0 + t) * 2 * D_MODEL + D_MODEL + c0, a.planes, a.plane_stride); };
+    float4 av = row_a(0), gv = row_g(0), av1 = av, gv1 = gv, av2 = av, gv2 = gv;
+    if (1 < nt) { av1 = row_a(1); gv1 = row_g(1); }
+    if (2 < nt) { av2 = row_a(2); gv2 = row_g(2); }
+    for (int t = 0; t < nt; ++t) {
+        float4 av3 = av2, gv3 = gv2;
+        if (t + 3 < nt) { av3 = row_a(t + 3); gv3 = row_g(t + 3); }
         win[0][8] = av.x * sigmoid_exact(gv.x); win[1][8] = av.y * sigmoid_exact(gv.y);   // GLU :629-636
         win[2][8] = av.z * sigmoid_exact(gv.z); win[3][8] = av.w * sigmoid_exact(gv.w);
         float cv[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {                                            // :341-360
-            float acc = win[u][0] * wk[u][0];
-#pragma unroll
-            for (int k = 1; k < CONV_K; ++k) acc = fmaf(win[u][k], wk[u][k], acc);
-            cv[u] = acc;
+        for (int k = 0; k < CONV_K; ++k) {                                       // :341-360, taps in ascending order
+            const float4 w4 = __ldg(taps + k * (D_MODEL / 4));
+            if (k == 0) { cv[0] = win[0][0] * w4.x; cv[1] = win[1][0] * w4.y; cv[2] = win[2][0] * w4.z; cv[3] = win[3][0] * w4.w; }
+            else { cv[0] = fmaf(win[0][k], w4.x, cv[0]); cv[1] = fmaf(win[1][k], w4.y, cv[1]); cv[2] = fmaf(win[2][k], w4.z, cv[2]); cv[3] = fmaf(win[3][k], w4.w, cv[3]); }
         }
-        float mean, var, dd[4];                                                  // LN :643-645
-        if (a.out_type == OUT_F32) {
-            mean = block_sum_256(cv[0] + cv[1] + cv[2] + cv[3], red) * (1.0f / D_MODEL);
-            float sq = 0.f;
+        cvs[t][threadIdx.x] = make_float4(cv[0], cv[1], cv[2], cv[3]);
+        if (f32) {                                                               // strict fp32, pass 1: the warp's part of the row sum (block_sum_256's tree)
+            const float s = warp_sum(cv[0] + cv[1] + cv[2] + cv[3]);
+            if (lane == 0) red[t][wrp] = s;
+        } else {                                                                 // 16-bit modes: the warp's (mean, M2) by Chan's pairwise merge (block_mean_var_256's tree)
+            float m = ((cv[0] + cv[1]) + (cv[2] + cv[3])) * 0.25f;
+            float M2 = (cv[0] - m) * (cv[0] - m) + (cv[1] - m) * (cv[1] - m) + (cv[2] - m) * (cv[2] - m) + (cv[3] - m) * (cv[3] - m);
+            float half_n = 2.0f;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { const float e = cv[u] - mean; sq += e * e; }
-            var = block_sum_256(sq, red) * (1.0f / D_MODEL);
-        } else block_mean_var_256(cv[0], cv[1], cv[2], cv[3], red, mean, var);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) dd[u] = cv[u] - mean;
-        const float rs = 1.0f / sqrtf(var + 1e-5f);
-        const size_t o = ((size_t)b * T + t) * D_MODEL + c0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) store_out(a.out, o + u, silu_exact(dd[u] * rs * lg[u] + lb[u]), a.out_type);   // SiLU :646
+            for (int o = 1; o < 32; o <<= 1) {
+                const float mo = __shfl_xor_sync(0xffffffffu, m, o), M2o = __shfl_xor_sync(0xffffffffu, M2, o);
+                const float d = mo - m;
+                M2 = (M2 + M2o) + d * d * half_n; m = m + 0.5f * d; half_n *= 2.0f;
+            }
+            if (lane == 0) { red[t][2 * wrp] = m; red[t][2 * wrp + 1] = M2; }
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
             for (int k = 0; k < CONV_K - 1; ++k) win[u][k] = win[u][k + 1];
-        av = av_n; gv = gv_n;
+        av = av1; gv = gv1; av1 = av2; gv1 = gv2; av2 = av3; gv2 = gv3;
     }
     if (t1 == T) {                                                               // new state = last 8 rows of xp :368-381 (the window after the last frame)
 #pragma unroll
         for (int k = 0; k < CONV_K - 1; ++k)
             *(float4*)(cache_new + (size_t)k * D_MODEL + c0) = make_float4(win[0][k], win[1][k], win[2][k], win[3][k]);
+    }
+    const float4 g4 = *(const float4*)(a.ln_g + c0), b4 = *(const float4*)(a.ln_b + c0);
+    __syncthreads();                                                             // every warp's partial statistics of every frame
+    if (f32) {                                                                   // pass 2: centred squares against the complete mean
+        for (int t = 0; t < nt; ++t) {
+            float tot = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tot += red[t][i];
+            const float mean = tot * (1.0f / D_MODEL);
+            const float4 c = cvs[t][threadIdx.x];
+            const float e0 = c.x - mean, e1 = c.y - mean, e2 = c.z - mean, e3 = c.w - mean;
+            const float s = warp_sum(e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3);
+            if (lane == 0) red[t][8 + wrp] = s;
+        }
+        __syncthreads();
+    }
+    for (int t = 0; t < nt; ++t) {                                               // LN :643-645, SiLU :646
+        float mean, var;
+        if (f32) {
+            float tot = 0.f, tq = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { tot += red[t][i]; tq += red[t][8 + i]; }
+            mean = tot * (1.0f / D_MODEL); var = tq * (1.0f / D_MODEL);
+        } else {
+            float mm[8], MM[8], hn = 64.0f;                                      // n / 2 of the groups being merged: 8 warps of 128 values -> 4 x 256 -> 2 x 512 -> 1024
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { mm[i] = red[t][2 * i]; MM[i] = red[t][2 * i + 1]; }
+#pragma unroll
+            for (int n = 8; n > 1; n >>= 1) {
+#pragma unroll
+                for (int i = 0; i < n / 2; ++i) {
+                    const float d = mm[2 * i + 1] - mm[2 * i];
+                    MM[i] = (MM[2 * i] + MM[2 * i + 1]) + d * d * hn; mm[i] = mm[2 * i] + 0.5f * d;
+                }
+                hn *= 2.0f;
+            }
+            mean = mm[0]; var = MM[0] * (1.0f / D_MODEL);
+        }
+        const float4 c = cvs[t][threadIdx.x];
+        const float rs = 1.0f / sqrtf(var + 1e-5f);
+        const float4 y = make_float4(silu_exact((c.x - mean) * rs * g4.x + b4.x), silu_exact((c.y - mean) * rs * g4.y + b4.y),
+                                     silu_exact((c.z - mean) * rs * g4.z + b4.z), silu_exact((c.w - mean) * rs * g4.w + b4.w));
+        store4_out(a.out, ((size_t)b * T + t0 + t) * D_MODEL + c0, y, a.out_type);
     }
     NSB_KERNEL_EPILOGUE();
 }
@@ -1090,7 +1401,7 @@ void launch_conv_module(const ConvModArgs& a, cudaStream_t st) {
     static const int tb_env = [] { const char* e = getenv("NSB_CONV_TB"); return e ? atoi(e) : 0; }();
     // one block (nothing recomputed) up to 8 frames; two blocks at T = 14 (measured within 1 % of each other and of TB = 4 / 14 on the
     // 64-stream step); 8-frame blocks beyond that (the batch path: hundreds of independent CTAs instead of one sequential walk)
-    const int TB = tb_env > 0 ? tb_env : (a.T <= 8 ? a.T : a.T <= 16 ? (a.T + 1) / 2 : 8);
+    const int TB = min(CONV_TB, tb_env > 0 ? tb_env : (a.T <= 8 ? a.T : a.T <= 16 ? (a.T + 1) / 2 : 8));
     if (a.B > 0 && a.T > 0) launch_k(conv_module_kernel, dim3((a.T + TB - 1) / TB, a.B), dim3(256), 0, st, a, TB);
 }
 

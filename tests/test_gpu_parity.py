@@ -153,12 +153,16 @@ def test_tcgen05_gemm_parity(built, wtype, compute, mm):
     eng.close()
 
 
+@pytest.mark.parametrize("persist", ["0", "1"])
 @pytest.mark.parametrize("wtype,compute,mm", [("f32", 2, O.MM_F16), ("f32", 3, O.MM_BF16), ("q8_0", 0, O.MM_Q8FAST), ("q4_0", 0, O.MM_Q8FAST)])
-def test_tcgen05_gemm_large_batch_pair_tiles(built, wtype, compute, mm):
+def test_tcgen05_gemm_large_batch_pair_tiles(built, wtype, compute, mm, persist, monkeypatch):
     """>= 4 row tiles: 256-row CTA-pair tiles (cta_group::2, M = 256) with BN in {256, 208, 160, 112} chosen per shape -- every
     BN, the overhang of the last tile along N (4096 = 19 x 208 + 144), a ragged last row tile (900 = 3 x 256 + 132), and in
-    Q8_0 mode the per-launch dequantisation into the fp16 scratch in front of it."""
+    Q8_0 mode the per-launch dequantisation into the fp16 scratch in front of it. persist = 1: the persistent variant of the same tiles
+    (one CTA pair per SM pair walks the tiles, two TMEM accumulators, one TMA ring across tiles; 900 rows x 1024 columns = 4 x 10 tiles
+    x 2 k-slices on 74 pairs: pairs with two tiles and pairs with one)."""
     import nsb200
+    monkeypatch.setenv("NSB_PAIR256_PERSIST", persist)
     path = synth.cached_model(wtype, 2, R=0)
     eng = nsb200.Engine(path, right_context=0, max_streams=1, compute=compute)
     om = O.Model(path, mm)

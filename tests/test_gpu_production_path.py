@@ -125,6 +125,53 @@ def test_config2_production_path_against_oracle(built, mode, wtype, compute, kv,
     eng.close()
 
 
+# The other BASELINE.json configs as benchmarked (24 layers, graph replay, two steps in flight, no taps), each past the roll of its
+# 70-row cache: 4 distinct streams against the checker, every other batch row a bit-identical copy of one of them.
+#   id, R, streams, chunks, GGUF, compute, K/V ring, oracle matmul, oracle K/V, encoder tol, near-tie band, max flips per decision
+OTHER_CONFIGS = [
+    ("config3_q8_0_256x560ms", 6, 256, 13, "q8_0", 0, 1, O.MM_Q8FAST, O.KV_F16, 1e-3, 2e-3, 1e-2),
+    ("config4_bf16_128x80ms", 0, 128, 75, "f16", 3, 2, O.MM_BF16, O.KV_BF16, 1e-2, 2e-2, 2e-2),
+    ("config5_bf16_64x1120ms", 13, 64, 7, "f16", 3, 2, O.MM_BF16, O.KV_BF16, 1e-2, 2e-2, 2e-2),
+]
+
+
+@pytest.mark.parametrize("cid,R,n,chunks,wtype,compute,kv,mm,okv,tol,band,max_flip_rate", OTHER_CONFIGS, ids=[c[0] for c in OTHER_CONFIGS])
+def test_other_baseline_configs_production_path_against_oracle(built, cid, R, n, chunks, wtype, compute, kv, mm, okv, tol, band, max_flip_rate):
+    """BASELINE.json configs 3 (256 streams x 560 ms, Q8_0 weights: 1792 token rows per step -- 256-row CTA-pair GEMM tiles, layer-ahead
+    dequantisation, warp-per-row LayerNorm, pipelined decode tiles), 4 (128 streams x 80 ms) and 5 (64 streams x 1.12 s) exactly as
+    bench.py runs them. Reference: src/nemo-stream.cpp:961-1057 (per-chunk driver), tests/test_compute.cpp:2808-2820 (token match)."""
+    import nsb200
+    T, n_orc = 1 + R, 4
+    path = synth.cached_model(wtype, 24, R=R)
+    eng = nsb200.Engine(path, right_context=R, max_streams=n, compute=compute, kv_dtype=kv, cuda_graph=True)
+    secs = (160 * (8 * T * chunks - 1) + 256) / 16000.0
+    base = [synth.synth_pcm(1200 + s, secs + 0.01) for s in range(n_orc)]
+    L = min(len(b) for b in base)
+    audio = np.stack([base[s % n_orc][:L] for s in range(n)])
+    ids, got, steps = run_two_in_flight(eng, audio)
+    assert steps == chunks, steps
+    x = eng.debug_get("x", n)
+    om = O.Model(path, mm, okv)
+    orc, worst = [], 0.0
+    for s in range(n_orc):
+        o = O.Stream(om, R, trace=True); o.push(audio[s]); orc.append(o)
+        assert o.chunks == chunks
+        worst = max(worst, rel(x[s * T:(s + 1) * T], o.trace_enc(chunks - 1)))
+    toks = [np.asarray(g, dtype=np.int32) for g in got]
+    det = {}
+    identical = assert_tokens_match_up_to_near_ties(toks[:n_orc], orc, band, det)
+    n_tok = sum(len(o.tokens()) for o in orc)
+    report(test="other_config_production_path", config=cid, streams=n, oracle_streams=n_orc, chunks=chunks, enc_rel_err_last_chunk=worst,
+           identical_streams=identical, tokens_in_oracle_streams=n_tok, tol=tol, band=band, **det)
+    assert n_tok > 20 * n_orc, n_tok
+    assert worst < tol, worst
+    assert det["flip_rate"] <= max_flip_rate, det
+    for s in range(n_orc, n):
+        assert np.array_equal(toks[s], toks[s % n_orc]), s
+        assert np.array_equal(x[s * T:(s + 1) * T], x[(s % n_orc) * T:(s % n_orc + 1) * T]), s
+    eng.close()
+
+
 def test_strict_q8_0_gemm_is_bit_identical_to_the_reference_arithmetic(built):
     """NSB_COMPUTE_Q8_0_STRICT, one GEMM: activation rows quantised like quantize_row_q8_0, integer block dots, f32 scale-accumulate
     in block order == the checker's restatement of ggml_mul_mat on a Q8_0 weight, bit for bit (every M / K / N shape of a layer)."""
@@ -280,3 +327,58 @@ def test_encoder_error_at_24_layers_per_chunk(built, mode, wtype, compute, kv, m
            first=float(errs[0]), last=float(errs[-1]))
     assert np.max(errs) < (1e-2 if mode == "bf16" else 1e-3), float(np.max(errs))       # measured: 3.5e-3 / 4.8e-4 (f16 ring) / 3.2e-4 (f32 ring)
     eng.close()
+
+
+def test_large_batch_attention_walks_streams_bit_identical_and_vs_oracle(built):
+    """160 streams x 560 ms chunks (T = 7) = 1280 (head, stream) items: the attention kernel that keeps one head per CTA and walks its
+    streams behind a three-tile cp.async ring (attention_mma_stream_kernel) against the one-item-per-CTA kernel -- bit for bit, every
+    chunk's encoder output and all tokens -- and against the checker. Half of the streams start two chunks late, so CTAs see ragged
+    cache fill levels (`first` differs between consecutive items of a walk) and steps with 80 and 160 rows.
+    Also covers the conv module's block-wide LayerNorm over all frames of a chunk at once (T = 7, one block per stream).
+    Reference: src/nemo-stream.cpp:435-545 (cached rel-pos attention), :565-662."""
+    import nsb200
+    R, n, layers = 6, 160, 2
+    T = 1 + R
+    path = synth.cached_model("f32", layers, R=R)
+    base = [synth.synth_pcm(900 + s, 7.5) for s in range(8)]
+    audio = np.stack([base[s % 8] for s in range(n)])
+    late = np.arange(n) % 2 == 1
+    shift = 160 * 8 * T
+    head = 2 * shift
+
+    def run(mode):
+        os.environ["NSB_ATT_STREAM"] = mode
+        try:
+            eng = nsb200.Engine(path, right_context=R, max_streams=n, compute=nsb200.COMPUTE_BF16, kv_dtype=nsb200.KV_BF16)
+            ids = np.array([eng.open_stream() for _ in range(n)], dtype=np.int32)
+            encs = []
+            eng.push_batch(ids[~late], audio[~late][:, :head + shift])       # the early half runs ahead
+            while eng.step() > 0:
+                encs.append(eng.debug_get("x", int((~late).sum())).copy())
+            eng.push_batch(ids[~late], audio[~late][:, head + shift:])
+            eng.push_batch(ids[late], audio[late][:, :audio.shape[1] - head - shift])
+            while True:
+                k = eng.step()
+                if k <= 0:
+                    break
+                encs.append(eng.debug_get("x", k).copy())
+            toks = [eng.pop_tokens(int(i)) for i in ids]
+            eng.close()
+            return encs, toks
+        finally:
+            os.environ.pop("NSB_ATT_STREAM", None)
+
+    enc_s, tok_s = run("1")
+    enc_o, tok_o = run("0")
+    assert len(enc_s) == len(enc_o) >= 4
+    for c, (x, y) in enumerate(zip(enc_s, enc_o)):
+        assert x.shape == y.shape and np.array_equal(x, y), c
+    for s in range(n):
+        assert np.array_equal(tok_s[s], tok_o[s]), s
+    # against the checker: one early and one late stream
+    om = O.Model(path, O.MM_BF16, O.KV_BF16)
+    for s, pcm in ((0, audio[0]), (1, audio[1][:audio.shape[1] - head - shift])):
+        o = O.Stream(om, R, trace=True)
+        o.push(pcm)
+        assert_tokens_match_up_to_near_ties([tok_s[s]], [o], 2e-1)
+    report(test="stream_attention", chunks=len(enc_s), streams=n, identical=True)
