@@ -591,6 +591,7 @@ void Engine::gemm_f32w(GemmArgs& g, const Weight& W, bool a_presplit) {
 void Engine::q8_predequant(const Weight& W, int M, GemmArgs& a) {
     static const int min_rows = [] { const char* e = getenv("NSB_Q8_PREDEQUANT_ROWS"); return e ? atoi(e) : 512; }();
     if (compute != NSB_COMPUTE_Q8_0 || !W.scales.p || M < min_rows) return;
+    if (q8_pair256_enabled()) return;                              // large batches: the dequantisation is fused into the CTA-pair tiles (gemm_q8_pair256_kernel)
     const size_t bytes = (size_t)W.n_out * W.n_in * 2;
     if (wscratch_.bytes < bytes) throw std::runtime_error("q8_predequant: scratch not allocated");   // sized in alloc_state (no allocation inside a graph capture)
     launch_dequant_q8(W.data.p, W.scales.p, wscratch_.p, W.n_out, W.n_in, st_, W.q4);
@@ -601,7 +602,7 @@ void Engine::q8_predequant(const Weight& W, int M, GemmArgs& a) {
 bool Engine::shadow_mode(int rows) const {
     static const bool off = [] { const char* e = getenv("NSB_Q8_SHADOW"); return e && e[0] == '0'; }();
     static const int min_rows = [] { const char* e = getenv("NSB_Q8_PREDEQUANT_ROWS"); return e ? atoi(e) : 512; }();
-    return !off && compute == NSB_COMPUTE_Q8_0 && shadow_bytes_ && rows >= min_rows && !profiling_;
+    return !off && !q8_pair256_enabled() && compute == NSB_COMPUTE_Q8_0 && shadow_bytes_ && rows >= min_rows && !profiling_;
 }
 // all 8 matrices of layer l -> fp16 in shadow_[l % 2], on stream s (same fp16(d) * q values as the fused operand path)
 void Engine::dequant_layer_async(int l, cudaStream_t s) {

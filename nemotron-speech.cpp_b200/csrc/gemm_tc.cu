@@ -32,6 +32,15 @@ bool pair_gemm_enabled() {
     return on;
 }
 
+// NSB_Q8_PAIR=1: Q8_0 / Q4_0 dequantisation fused into the 256-row CTA-pair tiles at large batches (gemm_q8_pair256_kernel). Off by
+// default: measured 7.55 ms per 256-stream x 560 ms step against 6.79 ms for the layer-ahead fp16 shadows (which run at exactly the bf16
+// engine's speed: 6.78 ms) -- the dequantise -> relay -> MMA chain lengthens every stage's turnaround and three stages are all that fit
+// next to a second CTA. Read per launch, so a test can switch it between engines of one process.
+bool q8_pair256_enabled() {
+    const char* e = getenv("NSB_Q8_PAIR");
+    return e && e[0] == '1';
+}
+
 static bool pair256_enabled() {
     static const bool on = [] { const char* e = getenv("NSB_PAIR256"); return !(e && e[0] == '0'); }();
     return on;
@@ -53,7 +62,8 @@ namespace {
 
 constexpr int BM = 128, ROW_BYTES = 128, UMMA_K_BYTES = 32;      // one k-block = one 128-byte swizzle row per tile row; 4 MMAs per k-block
 constexpr int TC_THREADS = 192;
-constexpr int Q8_THREADS = 320, Q8_DEQ = 256;                    // Q8_0 kernel: warps 2-9 dequantise (warps 2-5 also run the epilogue)
+constexpr int Q8_THREADS = 320, Q8_DEQ = 256;
+constexpr int QP_THREADS = 192, QP_DEQ = 128;                   // Q8_0 pair-tile kernel: warps 2-5 dequantise, then run the epilogue (two CTAs per SM)                    // Q8_0 kernel: warps 2-9 dequantise (warps 2-5 also run the epilogue)
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -938,6 +948,180 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------
+// Q8_0 / Q4_0 weights on the 256-row CTA-pair tiles (large batches): the fused-dequantisation pipeline of gemm_q8_kernel inside the
+// cta_group::2 structure of gemm_tc_pair256_kernel. Each CTA of the pair stages its 128 rows of A (fp16, TMA, counted on the leader's
+// `full` barrier) and the RAW quants of its BN/2 weight rows (TMA into its own shared memory, its own `qfull` barrier); its four
+// dequantiser warps expand them into the fp16 SWIZZLE_128B half-tile the pair's MMA reads and arrive on the CTA's own `bready` barrier;
+// the peer CTA's (otherwise idle) MMA warp relays its barrier to the leader's `peer_ready` through mapa + a cluster-scope arrive. The same
+// four warps run the epilogue afterwards. A weight is dequantised once per 256 output rows (the single-CTA
+// kernel: once per 128) and crosses L2 -> SM as 1.06 (0.56) bytes instead of 2: on tiles whose main loop is bound by what an SM can
+// ingest, the quantised operand is the FASTER one. Block scales are read straight from global memory one k-block ahead (4 bytes per
+// row and k-block: no shared-memory table). Values = fp16(d) * q rounded once: identical to the other Q8_0 paths.
+// ------------------------------------------------------------------------------------------
+template <int BN, int STAGES, int Q4>
+struct SmemQ8Pair {
+    static constexpr int QROW = Q4 ? 32 : 64;
+    alignas(1024) uint8_t a[STAGES][BM * ROW_BYTES];
+    alignas(1024) uint8_t b[STAGES][(BN / 2) * ROW_BYTES];      // dequantised half tile
+    alignas(128) uint8_t q[STAGES][(BN / 2) * QROW];            // raw quants of this CTA's weight rows
+    alignas(8) uint64_t full[STAGES];                            // leader: both CTAs' A halves landed
+    uint64_t qfull[STAGES];                                      // own: raw quants landed
+    uint64_t bready[STAGES];                                     // own: this CTA's half tile dequantised (4 warp arrivals)
+    uint64_t peer_ready[STAGES];                                 // leader: the peer's half tile dequantised (relayed by the peer's idle MMA warp)
+    uint64_t empty[STAGES];
+    uint64_t tmem_full;
+    uint32_t tmem_slot;
+    int trace_slot;
+};
+
+template <int BN, int STAGES, int Q4>
+__global__ void __launch_bounds__(QP_THREADS, 2)
+gemm_q8_pair256_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmQ, const __half* __restrict__ scales,
+                       const TcParams p) {
+    static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "pair256 tile: UMMA N is a multiple of 16 up to 256");
+    extern __shared__ uint8_t smem_raw[];
+    using S = SmemQ8Pair<BN, STAGES, Q4>;
+    S& s = *reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int n0 = (int)(blockIdx.x >> 1) * BN, m0 = blockIdx.y * (2 * BM);
+    constexpr int BK = 64, QROW = S::QROW, HB = BN / 2;
+    const int nk = p.K / BK / (int)gridDim.z;
+    const int kb0 = (int)blockIdx.z * nk;
+    constexpr uint32_t TMEM_COLS = tmem_cols_for(BN);
+    const int b_row = n0 + (int)rank * HB;                                       // this CTA's weight rows
+
+    if (threadIdx.x == 0) {
+        s.trace_slot = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 ? trace_begin(TR_GEMM_Q8) : -1;
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.qfull[i], 1); mbar_init(&s.bready[i], QP_DEQ / 32); mbar_init(&s.peer_ready[i], 1); mbar_init(&s.empty[i], 1); }
+        mbar_init(&s.tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+    }
+    if (warp == 2) tmem_alloc_pair(&s.tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = s.tmem_slot;
+    if (threadIdx.x == 0) { pdl_trigger(); trace_mark(s.trace_slot, 1); }
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (elect_one()) {
+            const int a_row = m0 + (int)rank * BM;
+            const int pre = nk < STAGES ? nk : STAGES;
+            for (int kb = 0; kb < pre; ++kb) {                                  // weights first: they do not depend on the previous kernel
+                mbar_expect_tx(&s.qfull[kb], HB * QROW);
+                tma_load_2d(s.q[kb], &tmQ, &s.qfull[kb], (kb0 + kb) * QROW, b_row);
+                if (rank == 0) mbar_expect_tx(&s.full[kb], 2 * BM * ROW_BYTES);
+            }
+            pdl_wait();
+            for (int kb = 0; kb < pre; ++kb) tma_load_2d_pair(s.a[kb], &tmA, &s.full[kb], (kb0 + kb) * BK, a_row);
+            for (int kb = pre; kb < nk; ++kb) {
+                const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&s.empty[st], ph ^ 1);                                // the pair's MMAs on this stage have retired (multicast commit)
+                mbar_expect_tx(&s.qfull[st], HB * QROW);
+                tma_load_2d(s.q[st], &tmQ, &s.qfull[st], (kb0 + kb) * QROW, b_row);
+                if (rank == 0) mbar_expect_tx(&s.full[st], 2 * BM * ROW_BYTES);
+                tma_load_2d_pair(s.a[st], &tmA, &s.full[st], (kb0 + kb) * BK, a_row);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA); in the peer CTA this warp relays "half tile dequantised" to the leader =====================
+        if (rank != 0) {
+            // one thread, nothing of its own in flight: the cluster-scope release of the remote arrive (a MEMBAR.GPU) costs it nothing, whereas
+            // issued by the dequantiser warps themselves it was 20 % of the kernel's stall samples (and waited for their scale loads)
+            if (elect_one()) {
+                for (int kb = 0; kb < nk; ++kb) {
+                    const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+                    mbar_wait(&s.bready[st], ph);                               // acquire: the dequantisers' (proxy-fenced) shared-memory writes are performed
+                    // relaxed: nothing of THIS thread needs publishing, and the release form costs a MEMBAR.GPU round trip per k-block on the
+                    // critical path of every stage (7.7 % of the kernel's stall samples, all of them here)
+                    uint32_t remote;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(&s.peer_ready[st])), "r"(0));
+                    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+                }
+            }
+        } else if (elect_one()) {
+            const uint32_t idesc = make_idesc(0, BN, 2 * BM);
+            for (int kb = 0; kb < nk; ++kb) {
+                const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&s.full[st], ph);                                     // both A halves landed
+                mbar_wait(&s.bready[st], ph);                                   // this CTA's W half tile dequantised
+                mbar_wait(&s.peer_ready[st], ph);                               // the peer's
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(s.a[st]), b_addr = smem_u32(s.b[st]);
+#pragma unroll
+                for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k)
+                    umma_f16_pair(tmem_base, make_desc(a_addr + k * UMMA_K_BYTES), make_desc(b_addr + k * UMMA_K_BYTES), idesc, (kb | k) ? 1u : 0u);
+                umma_commit_pair(&s.empty[st]);
+            }
+            umma_commit_pair(&s.tmem_full);
+        }
+    } else {
+        // ===================== dequantiser (then epilogue) =====================
+        const int t = threadIdx.x - 64;                                          // 0..127: 32 rows x 4 sixteen-value chunks per pass
+        const int c = t & 3;
+        constexpr int RPP = QP_DEQ / 4, PASSES = (HB + RPP - 1) / RPP;
+        const int kblocks = p.K / 32;                                            // block scales per weight row
+        // block scale of (row of pass pz, k-block kb): one half per thread, fetched one k-block ahead
+        auto load_scale = [&](int pz, int kb) {
+            const int r = pz * RPP + (t >> 2), n = b_row + r;
+            return (r < HB && n < p.N) ? scales[(size_t)n * kblocks + (size_t)(kb0 + kb) * 2 + (c >> 1)] : __float2half(0.f);
+        };
+        __half d_cur[PASSES];                                                     // scales of the k-block about to be expanded: loaded right AFTER the previous
+#pragma unroll                                                                   // k-block's arrive, so that no load is in flight at its fence, and consumed after the next barrier wait
+        for (int pz = 0; pz < PASSES; ++pz) d_cur[pz] = load_scale(pz, 0);
+        for (int kb = 0; kb < nk; ++kb) {
+            const int st = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(&s.qfull[st], ph);
+#pragma unroll
+            for (int pz = 0; pz < PASSES; ++pz) {
+                const int r = pz * RPP + (t >> 2);
+                if (HB % RPP != 0 && r >= HB) continue;
+                uint4 raw = *reinterpret_cast<const uint4*>(&s.q[st][r * QROW + (Q4 ? (c >> 1) * 16 : c * 16)]);
+                const __half2 d2 = __half2half2(d_cur[pz]);
+                if (Q4) {
+                    const int sh = (c & 1) * 4;
+                    raw.x = (raw.x >> sh) & 0x0F0F0F0Fu; raw.y = (raw.y >> sh) & 0x0F0F0F0Fu; raw.z = (raw.z >> sh) & 0x0F0F0F0Fu; raw.w = (raw.w >> sh) & 0x0F0F0F0Fu;
+                }
+                const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+                const __half2 off = Q4 ? __floats2half2_rn(1032.0f, 1032.0f) : __floats2half2_rn(1152.0f, 1152.0f);
+                __half2 h[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {                                    // (0x6400 | byte) - offset = q exactly; one fp16 multiply by the block scale
+                    const uint32_t x = Q4 ? w4[i] : (w4[i] ^ 0x80808080u);
+                    const uint32_t lo = __byte_perm(x, 0x64646464u, 0x5140), hi = __byte_perm(x, 0x64646464u, 0x5342);
+                    h[2 * i] = __hmul2(__hsub2(*reinterpret_cast<const __half2*>(&lo), off), d2);
+                    h[2 * i + 1] = __hmul2(__hsub2(*reinterpret_cast<const __half2*>(&hi), off), d2);
+                }
+                uint8_t* row = &s.b[st][r * ROW_BYTES];
+                *reinterpret_cast<uint4*>(row + (((2 * c) ^ (r & 7)) << 4)) = *reinterpret_cast<uint4*>(&h[0]);      // SWIZZLE_128B: chunk ^= row % 8
+                *reinterpret_cast<uint4*>(row + (((2 * c + 1) ^ (r & 7)) << 4)) = *reinterpret_cast<uint4*>(&h[4]);
+            }
+            // generic-proxy writes -> visible to the tensor cores of the pair. The shared::cta form only: the unqualified fence also waits
+            // for the scale load in flight for the next k-block (an L2 round trip per k-block: measured 2x the whole kernel)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s.bready[st])) : "memory");
+            if (kb + 1 < nk) {
+#pragma unroll
+                for (int pz = 0; pz < PASSES; ++pz) d_cur[pz] = load_scale(pz, kb + 1);
+            }
+        }
+        tc_epilogue_at<BN>(p, tmem_base, &s.tmem_full, warp, m0 + (int)rank * BM + (warp & 3) * 32, n0, s.trace_slot, s.a[0]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -998,6 +1182,27 @@ void launch_cfg_q8x(const GemmArgs& a, cudaStream_t st) {
 template <int BN, int STAGES>
 void launch_cfg_q8(const GemmArgs& a, cudaStream_t st) { if (a.q4) launch_cfg_q8x<BN, STAGES, 1>(a, st); else launch_cfg_q8x<BN, STAGES, 0>(a, st); }
 
+template <int BN, int STAGES, int Q4>
+void launch_cfg_q8_pair256x(const GemmArgs& a, cudaStream_t st) {
+    static std::atomic<size_t> attr_set[MAX_DEVICES];
+    const size_t smem = sizeof(SmemQ8Pair<BN, STAGES, Q4>) + 1024;
+    ensure_dyn_smem(gemm_q8_pair256_kernel<BN, STAGES, Q4>, smem, attr_set);
+    const CUtensorMap tmA = make_map(a.A, a.M, a.K, a.lda, BM, 0);
+    const CUtensorMap tmQ = Q4 ? make_map_u8(a.W, a.N, a.K / 2, BN / 2, 32) : make_map_u8(a.W, a.N, a.K, BN / 2, 64);
+    const int m_out = a.c_group > 0 ? (a.M / a.c_group) * (a.c_group - a.c_drop) : a.M;
+    TcParams p{a.M, a.N, a.K, a.bias, a.C, a.ldc, a.epi, a.alpha, a.out_type, 0, 0, a.c_group, a.c_drop, a.C0, m_out};
+    dim3 grid(2 * ((a.N + BN - 1) / BN), (a.M + 2 * BM - 1) / (2 * BM), a.splits > 1 ? a.splits : 1);
+    launch_k_cluster(gemm_q8_pair256_kernel<BN, STAGES, Q4>, grid, dim3(QP_THREADS), smem, st, 2, tmA, tmQ, (const __half*)a.w_scales, p);
+}
+void launch_q8_pair256(const GemmArgs& a, int bn, cudaStream_t st) {
+    // stage counts: <= ~111 KB per CTA so that two CTAs of different pairs share an SM (16 KB A + BN/2 x (128 + 64) bytes per stage)
+    switch (bn) {
+        case 208: if (a.q4) launch_cfg_q8_pair256x<208, 3, 1>(a, st); else launch_cfg_q8_pair256x<208, 3, 0>(a, st); break;
+        case 160: if (a.q4) launch_cfg_q8_pair256x<160, 3, 1>(a, st); else launch_cfg_q8_pair256x<160, 3, 0>(a, st); break;
+        case 112: if (a.q4) launch_cfg_q8_pair256x<112, 4, 1>(a, st); else launch_cfg_q8_pair256x<112, 4, 0>(a, st); break;
+        default: throw CudaError("gemm_q8: pair256 tile not instantiated");
+    }
+}
 // Experimental, off by default: on B200 the multicast variant measured SLOWER than per-CTA A loads at M = 128
 // (ff1a 7.7 vs 6.9 us, profiles/r01_notes.md) -- L2 already serves the shared tile well and the cluster-wide stage release
 // couples the CTAs -- and it is not covered by the parity suite.
@@ -1081,6 +1286,19 @@ int pick_pair256_bn(int M, int N) {
     for (int bn : {112, 160, 208, 256}) if (tiles(bn) <= 148) return bn;
     int best = 256; long long best_cost = 0;
     for (int bn : {256, 208, 160, 112}) {
+        const long long cost = ((tiles(bn) + 147) / 148) * (BM + bn / 2);
+        if (!best_cost || cost < best_cost) { best = bn; best_cost = cost; }
+    }
+    return best;
+}
+// the same choice for the fused Q8_0 / Q4_0 pair tiles (BN <= 208: raw + dequantised half tiles and two CTAs per SM)
+int pick_q8_pair256_bn(int M, int N) {
+    const int tiles_m = (M + 2 * BM - 1) / (2 * BM);
+    auto tiles = [&](int bn) { return (long long)tiles_m * ((N + bn - 1) / bn); };
+    if (tiles(112) < 100) return 0;
+    for (int bn : {112, 160, 208}) if (tiles(bn) <= 148) return bn;
+    int best = 208; long long best_cost = 0;
+    for (int bn : {208, 160, 112}) {
         const long long cost = ((tiles(bn) + 147) / 148) * (BM + bn / 2);
         if (!best_cost || cost < best_cost) { best = bn; best_cost = cost; }
     }
@@ -1191,6 +1409,12 @@ void launch_gemm_tc(const GemmArgs& a, int in_type, cudaStream_t st) {
     if (a.w_scales) {                                             // Q8_0 planes: fused-dequant kernel (A is fp16)
         if (fmt != 0) throw CudaError("gemm_q8: activations must be fp16");
         if (a.splits > 1 && (a.epi != EPI_PARTIAL || (a.K / BK) % a.splits != 0)) throw CudaError("gemm_tc: bad split-K request");
+        if (a.force_bn && a.force_stages == 95) { launch_q8_pair256(a, a.force_bn, st); return; }      // tuning hook
+        if (tiles_m >= pair256_min_tiles() && q8_pair256_enabled()) {   // large batches: fused dequantisation on the 256-row CTA-pair tiles
+            static const int split_bn = [] { const char* e = getenv("NSB_SPLIT_BN"); return e ? atoi(e) : 112; }();
+            const int bn = a.splits > 1 ? (split_bn == 256 ? 208 : split_bn) : pick_q8_pair256_bn(a.M, a.N);
+            if (bn) { launch_q8_pair256(a, bn, st); return; }
+        }
         if (a.splits > 1) { if (a.N % 64 == 0 && a.K >= 4096) launch_cfg_q8<64, 4>(a, st); else launch_cfg_q8<32, 5>(a, st); return; }
         if (a.N % 128 == 0 && (long long)tiles_m * (a.N / 128) >= 120) launch_cfg_q8<128, 4>(a, st);
         else if (a.N % 64 == 0 && (long long)tiles_m * (a.N / 64) >= 120) launch_cfg_q8<64, 4>(a, st);

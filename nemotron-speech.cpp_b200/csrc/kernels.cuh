@@ -96,6 +96,7 @@ struct AttnFullArgs {
 void launch_attention_full(const AttnFullArgs& a, cudaStream_t st);
 void launch_dequant_q8(const void* q, const void* scales, void* out_f16, int N, int K, cudaStream_t st, int q4 = 0);   // gemm_tc.cu (q4: Q4_0 nibble plane)
 bool pair_gemm_enabled();         // gemm_tc.cu: CTA-pair tiles on (default) / off (NSB_PAIR_GEMM=0)
+bool q8_pair256_enabled();        // gemm_tc.cu: Q8_0 / Q4_0 dequantisation fused into the 256-row CTA-pair tiles at large batches: NSB_Q8_PAIR=1 (default off: the layer-ahead fp16 shadows are faster)
 
 struct ConvModArgs {
     const float* pw1;             // [planes][M][2048] f32  (a | gate); planes > 1 = split-K partials of the pointwise GEMM, summed on load

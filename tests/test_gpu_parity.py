@@ -163,6 +163,10 @@ def test_tcgen05_gemm_large_batch_pair_tiles(built, wtype, compute, mm, persist,
     x 2 k-slices on 74 pairs: pairs with two tiles and pairs with one)."""
     import nsb200
     monkeypatch.setenv("NSB_PAIR256_PERSIST", persist)
+    if wtype in ("q8_0", "q4_0"):
+        # quantised weights: 0 = dequantisation fused into the CTA-pair tiles (gemm_q8_pair256_kernel, the default), 1 = the earlier path
+        # (dequantise into an fp16 scratch per launch, then the fp16 pair tiles)
+        monkeypatch.setenv("NSB_Q8_PAIR", "1" if persist == "0" else "0")
     path = synth.cached_model(wtype, 2, R=0)
     eng = nsb200.Engine(path, right_context=0, max_streams=1, compute=compute)
     om = O.Model(path, mm)

@@ -7,11 +7,13 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
 import nsb200, synth
 ROWS = int(os.environ.get("ROWS", 1792)); R = int(os.environ.get('R', 6)); T = R + 1
 CFGS = [tuple((list(map(int, c.split(":"))) + [1])[:3]) for c in os.environ.get("CFGS", "0:0,256:2,256:3,128:3,128:4,128:6,64:4").split(",")]   # bn:stages[:splits]; stages 97 = 256-row CTA-pair tile, 96 = its persistent variant; 0:0:-1 = the step's own launch
-eng = nsb200.Engine(synth.cached_model("f16", 24, R=R), right_context=R, max_streams=(ROWS + T - 1) // T, compute=nsb200.COMPUTE_BF16, kv_dtype=nsb200.KV_BF16)
+Q8 = os.environ.get("COMPUTE", "bf16") == "q8_0"          # Q8_0 weights: stages 95 = fused dequantisation on the 256-row pair tiles; 0:0 = the engine's own path
+eng = (nsb200.Engine(synth.cached_model("q8_0", 24, R=R), right_context=R, max_streams=(ROWS + T - 1) // T, compute=0, kv_dtype=nsb200.KV_F16) if Q8 else
+       nsb200.Engine(synth.cached_model("f16", 24, R=R), right_context=R, max_streams=(ROWS + T - 1) // T, compute=nsb200.COMPUTE_BF16, kv_dtype=nsb200.KV_BF16))
 KIND = {0: ("ff_up", 4096, 1024), 1: ("ff_down", 1024, 4096), 2: ("qkv", 3072, 1024), 3: ("out", 1024, 1024), 4: ("pw1", 2048, 1024)}
 for kind, (nm, N, K) in KIND.items():
     for bn, st, sp in CFGS:
-        if bn and st not in (96, 97) and N % bn: continue
+        if bn and st not in (95, 96, 97) and N % bn: continue
         if sp > 1 and N != 1024: continue
         try:
             us = eng.bench_gemm(kind, ROWS, bn, st, sp, 1, 10)
