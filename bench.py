@@ -488,7 +488,9 @@ def main():
                 "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": c["scaling"], "vs_baseline": None,
                 "dtype": c["compute"], "data": "synthetic",
                 "config": {"workload": f"nemotron-speech-streaming-en-0.6b architecture ({N_LAYERS} conformer layers, random-init synthetic weights), "
-                                       f"{c['compute']} tcgen05 GEMMs, {c['kv']} K/V ring, {head['streams_per_gpu']} concurrent streams per GPU, {head['chunk_ms']} ms chunks "
+                                       f"{c['compute']} tcgen05 GEMMs" + (" (Q8_0 weights resident in HBM as int8 + block scales; dequantised to fp16 inside the step: fused into "
+                                       "the GEMM operand path below 512 token rows, one layer ahead on a side stream into two L2-sized fp16 shadows from there)" if q8 else "")
+                                       + f", {c['kv']} K/V ring, {head['streams_per_gpu']} concurrent streams per GPU, {head['chunk_ms']} ms chunks "
                                        f"(att_right_context={c['R']}), steady state (70-frame attention cache full); joint blank bias calibrated to a "
                                        f"{'speech-like' if PROFILE == 'speech' else 'dense (parity-test)'} token rate ({head['e2e']['tokens_per_audio_s']:.1f} tokens per audio second measured in the e2e leg)",
                            "baseline_config": args.config, "streams_per_gpu": head["streams_per_gpu"], "chunk_ms": head["chunk_ms"],

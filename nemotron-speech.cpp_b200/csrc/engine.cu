@@ -797,6 +797,15 @@ int Engine::side_acquire() {
 template <class Key, class Fn>
 void Engine::run_graphed(std::map<Key, StepGraph>& cache, const Key& key, cudaStream_t s, Fn&& body) {
     if (!cfg_.use_cuda_graph || debug_ || profiling_) { body(); return; }
+    // bounded cache: a step graph exists per (batch size, staging buffer, side); serving with ever-changing batch sizes would otherwise
+    // accumulate up to 4 x max_streams executables. Past the bound everything is dropped and re-captured on demand (both streams drained
+    // first: an executable must not be destroyed under a launch that is still running).
+    constexpr size_t MAX_GRAPHS = 96;
+    if (cache.size() >= MAX_GRAPHS && cache.find(key) == cache.end()) {
+        NSB_CUDA(cudaStreamSynchronize(st_)); NSB_CUDA(cudaStreamSynchronize(st_dec_));
+        for (auto& e : cache) if (e.second.exec) cudaGraphExecDestroy(e.second.exec);
+        cache.clear();
+    }
     StepGraph& g = cache[key];
     if (!g.exec) {
         const long long before = stats.kernel_launches;

@@ -201,6 +201,34 @@ def test_streaming_parity_f32_all_latency_modes(built, R):
     eng.close()
 
 
+def test_long_form_stream_two_minutes_strict_fp32(built):
+    """BASELINE.json config 5's long-form aspect at test size: two streams of 2 minutes at 1.12 s chunks (106 chunks each: the 70-row
+    ring wraps 21 times, 1.9 M samples through the host-side staging with its lazy compaction), one fed in one-hour-style bulk (a single
+    push, then drained), one in chunk-sized reads; strict fp32 with the CUDA graph on and no taps: tokens identical to the checker (reference: src/nemo-stream.cpp:961-1057, 1079-1127)."""
+    import nsb200
+    R, T = 13, 14
+    path = synth.cached_model("f32", 2, R=R)
+    eng = nsb200.Engine(path, right_context=R, max_streams=2, compute=nsb200.COMPUTE_F32, cuda_graph=True)
+    om = O.Model(path)
+    audio = [synth.synth_pcm(40 + s, 120.0) for s in range(2)]
+    ids = [eng.open_stream() for _ in range(2)]
+    eng.push(ids[0], audio[0])                                                   # bulk: everything at once
+    pos, read = 0, eng.chunk_samples
+    while pos < len(audio[1]) or eng.ready(ids[0]) or eng.ready(ids[1]):
+        if pos < len(audio[1]):
+            eng.push(ids[1], audio[1][pos:pos + read]); pos += read
+        if eng.step() == 0 and pos >= len(audio[1]):
+            break
+    toks = [eng.pop_tokens(i) for i in ids]
+    for s in range(2):
+        o = O.Stream(om, R)
+        o.push(audio[s])
+        assert eng.chunks(ids[s]) == o.chunks >= 106, (eng.chunks(ids[s]), o.chunks)
+        assert np.array_equal(toks[s], o.tokens()), s
+        assert len(toks[s]) > 1000
+    eng.close()
+
+
 def test_streaming_parity_f32_full_24_layer_model(built):
     import nsb200
     path = synth.cached_model("f32", 24, R=1)
