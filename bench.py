@@ -18,7 +18,7 @@ torch.distributed is used only for the barrier, the max-over-ranks of the timed 
 Per config:
   value   : device-resident throughput -- PCM of the step already in HBM, K steps enqueued back to back on the engine's stream,
             CUDA events around them
-  e2e     : the same K steps through the public C ABI with HOST buffers, two steps in flight: nsb_push_pcm_batch,
+  e2e     : the same K steps through the public C ABI with HOST buffers, up to three steps in flight: nsb_push_pcm_batch,
             nsb_engine_step_begin (pinned staging + H2D + step + D2H of the token ids enqueued), the next chunk pushed meanwhile,
             nsb_engine_step_end, nsb_pop_tokens_batch; wall clock. The tokens of this leg are check-summed and compared with a
             re-run of the same audio WITHOUT the CUDA graph, one step at a time (`token_check`)
@@ -49,6 +49,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 N_LAYERS = int(os.environ.get("NSB_BENCH_LAYERS", 24))
 PROFILE = os.environ.get("NSB_BENCH_PROFILE", "speech")   # synthetic-model calibration: "speech" = ~4.5 tokens per audio second, "parity" = the tests' dense emission
+IN_FLIGHT = max(1, min(3, int(os.environ.get("NSB_BENCH_IN_FLIGHT", 3))))   # steps between step_begin and step_end in the e2e leg
 BENCH_CHUNKS = 8                                          # distinct chunks staged in HBM for the device-resident leg, cycled
 
 # BASELINE.json configs by number (configs[0] is the CPU case = --impl reference).
@@ -367,13 +368,16 @@ def run_config(no: int, args, ctx, headline: bool):
     sync_all()
     t0 = time.perf_counter()
     ntok = 0
-    # two steps in flight: while the device runs step i the host hands over the next chunk of every stream and stages + enqueues
-    # step i+1 (pinned staging, H2D, all kernels, D2H of the token ids), then waits for step i and pops its tokens
-    assert eng.step_begin() == S
+    # steps in flight (IN_FLIGHT, default 3 = the C ABI's limit): while the device runs step i the host hands over the next chunks of
+    # every stream and stages + enqueues steps i+1 (and i+2) (pinned staging, H2D, all kernels, D2H of the token ids), then waits for
+    # step i and pops its tokens. The third slot keeps the engine stream busy while a long greedy decode is still running on its own.
+    begun = 0
     for i in range(steps):
-        if i + 1 < steps:
-            feed(shift)
+        while begun < steps and begun - i < IN_FLIGHT:
+            if begun:
+                feed(shift)
             assert eng.step_begin() == S
+            begun += 1
         assert eng.step_end() == S                        # wait for the OLDEST step in flight, queue its tokens
         ntok += pop()
     sync_all()
@@ -419,7 +423,7 @@ def run_config(no: int, args, ctx, headline: bool):
                "latency_ms": {"p50": p50, "p99": p99, "n": n_lat, "definition": "host to host: chunk handed to nsb_push_pcm_batch -> its token ids popped "
                               "(one chunk at a time, graph-capture step excluded); max over ranks",
                               "device_p50": dev_lat[len(dev_lat) // 2], "device_p99": dev_lat[min(len(dev_lat) - 1, int(0.99 * len(dev_lat)))]},
-               "token_check": {"crc32_graph_two_in_flight": ck, "crc32_no_graph_single_steps": ck_ng, "identical": ck == ck_ng,
+               "token_check": {"crc32_graph_steps_in_flight": ck, "crc32_no_graph_single_steps": ck_ng, "identical": ck == ck_ng,
                                "tokens": sum(len(v) for v in all_g.values()), "chunks_per_stream": n_done},
                "roofline": roofline, "step_roofline": step_roof, "breakdown": breakdown, "gpu_launches": launches, "clocks": clocks,
                "wall_ms_per_step": 1e3 * wall_s / steps, "engine_load_s": round(t_load, 2)}

@@ -116,8 +116,9 @@ int nsb_stream_ready(const nsb_engine* e, int stream); /* 1 if a full chunk is b
 int nsb_engine_step(nsb_engine* e);                    /* returns #streams advanced (0 = nothing ready), <0 error */
 /* step() split in two so that the host can feed the NEXT chunk while the device works on this one: begin stages the ready
  * streams, enqueues the H2D copy, the step and the D2H copy of the token ids and returns; end waits for them and queues the
- * tokens of the OLDEST step in flight. Up to two steps may be in flight (begin, begin, end, begin, end, ...: the device goes from
- * one step straight into the next; a third begin is an error); push_pcm / pop_tokens are allowed in between, stream open / close /
+ * tokens of the OLDEST step in flight. Up to three steps may be in flight (begin, begin, [begin,] end, begin, end, ...: the device
+ * goes from one step straight into the next; with a third step queued the engine stream also stays busy while the greedy decode of a
+ * step with many symbols is still running on its own stream; a fourth begin is an error); push_pcm / pop_tokens are allowed in between, stream open / close /
  * reset and nsb_engine_step collect first. nsb_stream_ready() counts launched chunks (it asks for the chunk after the ones in
  * flight); nsb_stream_chunks() counts collected ones. */
 int nsb_engine_step_begin(nsb_engine* e);              /* returns #streams in the launched step (0 = nothing ready), <0 error */

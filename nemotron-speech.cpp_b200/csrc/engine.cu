@@ -493,7 +493,7 @@ void Engine::alloc_state() {
     part_.alloc((size_t)MAX_SPLITS * std::min<size_t>(Mrows, 1024) * D_MODEL * 4);       // split-K workspace (only used when rows <= 1024)
     out_tok_.alloc((size_t)S * MAX_SYMBOLS * T * 4); out_cnt_.alloc((size_t)S * 4);
     dec_sync_.alloc(decode_sync_bytes(S));
-    for (Side& sd : side_) {                                                             // hand-over buffers of a step, double-buffered (decode overlap)
+    for (Side& sd : side_) {                                                             // hand-over buffers of a step, one set per step in flight (decode overlap)
         sd.slot.alloc((size_t)S * 4); sd.encp.alloc(Mrows * JOINT * 4); sd.out_tok.alloc((size_t)S * MAX_SYMBOLS * T * 4);
         sd.out_cnt.alloc((size_t)S * 4); sd.sync.alloc(decode_sync_bytes(S));
     }
@@ -672,11 +672,13 @@ void Engine::push_pcm(int s, const int16_t* pcm, int n) {
 // chunk gate and PCM row of a stream: host_stream.h (pure host code, driven on CPU by tests/test_host_api.py)
 bool Engine::ready(int s) const { return hs_ready(hs_[s], T); }
 
-// Up to two steps in flight: step i+1 is staged and enqueued while step i runs, so the device never waits for the host between
-// steps. Host buffers (pinned PCM rows, slots, token ids) are double-buffered; the device-side step workspace is shared --
-// everything is ordered on the engine stream.
+// Up to MAX_INFLIGHT (three) steps in flight: step i+1 is staged and enqueued while step i runs, so the device never waits for the
+// host between steps; the third slot lets the encoder of step i+2 be queued before the decode of step i has finished (decode overlap:
+// a step with many symbol rounds decodes longer than one encoder pass; with two slots the engine stream then idled until the host
+// came back from step_end). Host buffers (pinned PCM rows, slots, token ids) and the device-side hand-over buffers are rings of that
+// depth; the device-side step workspace is shared -- everything is ordered on the engine stream.
 int Engine::step_begin() {
-    if (n_inflight_ == 2) throw std::runtime_error("step_begin: two steps are already in flight (call step_end)");
+    if (n_inflight_ == MAX_INFLIGHT) throw std::runtime_error("step_begin: three steps are already in flight (call step_end)");
     NSB_CUDA(cudaSetDevice(device_));
     std::vector<int> batch;
     for (int s = 0; s < max_streams; ++s) if (ready(s)) batch.push_back(s);
@@ -701,14 +703,14 @@ int Engine::step_begin() {
     NSB_CUDA(cudaEventRecord(io.done, tail));
     if (tail != st_) { NSB_CUDA(cudaEventRecord(side_[side].dec_done, tail)); }   // the side is free again once its tokens have left
     io.batch = std::move(batch);
-    io_next_ ^= 1; n_inflight_ += 1;
+    io_next_ = (io_next_ + 1) % MAX_INFLIGHT; n_inflight_ += 1;
     return B;
 }
 
 int Engine::step_end() {
     if (n_inflight_ == 0) return 0;
     NSB_CUDA(cudaSetDevice(device_));
-    StepIO& io = io_[n_inflight_ == 2 ? io_next_ : io_next_ ^ 1];         // the OLDEST step in flight
+    StepIO& io = io_[(io_next_ + MAX_INFLIGHT - n_inflight_) % MAX_INFLIGHT];   // the OLDEST step in flight
     n_inflight_ -= 1;
     const int B = (int)io.batch.size();
     NSB_CUDA(cudaEventSynchronize(io.done));
@@ -838,7 +840,7 @@ cudaStream_t Engine::run_step(int B, const int16_t* d_pcm, int side, bool pipeli
     if (!(skip_mask() & 8u /* SK_DECODE */))
         run_graphed(dec_graphs_, std::make_tuple(B, side, ov ? 1 : 0), s, [&] { run_decode_kernels(B, side, s, ov); });
     if (ov) { NSB_CUDA(cudaEventRecord(sd.dec_done, st_dec_)); sd.dec_pending = true; }
-    side_next_ = side ^ 1;
+    side_next_ = (side + 1) % MAX_INFLIGHT;
     return s;
 }
 
@@ -1198,7 +1200,7 @@ float Engine::bench_profile(float* ms_per_class, int* launches_per_class) {
     join_decode_stream();
     prof_.clear(); ev_used_ = 0; profiling_ = true;
     NSB_CUDA(cudaEventRecord(ev0_, st_));
-    { const int side = side_acquire(); run_encoder_kernels(bench_B_, bench_pcm_.as<int16_t>(), side); run_decode_kernels(bench_B_, side, st_, false); side_next_ = side ^ 1; }
+    { const int side = side_acquire(); run_encoder_kernels(bench_B_, bench_pcm_.as<int16_t>(), side); run_decode_kernels(bench_B_, side, st_, false); side_next_ = (side + 1) % MAX_INFLIGHT; }
     NSB_CUDA(cudaEventRecord(ev1_, st_));
     profiling_ = false;
     NSB_CUDA(cudaEventSynchronize(ev1_));

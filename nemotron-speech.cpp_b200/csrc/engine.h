@@ -152,14 +152,15 @@ private:
     std::map<std::tuple<int, int, int>, StepGraph> dec_graphs_;           // decode halves: (batch, side, narrow)
     template <class Key, class Fn> void run_graphed(std::map<Key, StepGraph>& cache, const Key& key, cudaStream_t s, Fn&& body);
     struct Side { DevBuf slot, encp, out_tok, out_cnt, sync; cudaEvent_t enc_done = nullptr, dec_done = nullptr; bool dec_pending = false; };
-    Side side_[2]; int side_next_ = 0;
+    static constexpr int MAX_INFLIGHT = 3;   // steps between step_begin and step_end: host-side step state and the device-side hand-over buffers are rings of this depth
+    Side side_[MAX_INFLIGHT]; int side_next_ = 0;
     cudaStream_t st_dec_ = nullptr;
     struct StepIO {                   // host side of one step in flight
         HostPinned h_pcm, h_slot, h_tok, h_cnt;
         cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
         std::vector<int> batch;       // batch row -> stream slot
     };
-    StepIO io_[2]; int io_next_ = 0, n_inflight_ = 0;
+    StepIO io_[MAX_INFLIGHT]; int io_next_ = 0, n_inflight_ = 0;
     void collect_tokens(StepIO& io);
     void collect_all();               // step_end() until nothing is in flight
     // strict modes keep every activation in f32 and run no tcgen05 kernel: NSB_COMPUTE_F32 (f32 weights, SIMT) and

@@ -220,20 +220,21 @@ void run_worker(const Options& opt, int device, const std::vector<Input>& inputs
                 std::this_thread::sleep_until(t0 + std::chrono::duration_cast<Clock::duration>(std::chrono::duration<double>(tick * shift / 16000.0)));
             }
         } else {
-            // throughput: two steps in flight -- while the device runs step i the host hands over the next shift of every stream
-            // and stages + enqueues step i+1 (nsb200.h: begin, begin, end, begin, end, ...)
+            // throughput: up to three steps in flight -- while the device runs step i the host hands over the next shifts of every
+            // stream and stages + enqueues steps i+1, i+2 (nsb200.h: begin, begin, begin, end, begin, end, ...)
+            constexpr int DEPTH = 3;
             int inflight = 0;
             if (feed_all(chunk) < 0) break;
             for (;;) {
                 int launched = 0;
-                if (inflight < 2) {
+                if (inflight < DEPTH) {
                     launched = nsb_engine_step_begin(e);
                     if (launched < 0) { fail("nsb_engine_step_begin"); break; }
                     if (launched > 0) ++inflight;
                 }
                 const long long pushed = feed_all(shift);
                 if (pushed < 0) break;
-                if (inflight == 2 || (inflight > 0 && launched == 0)) {
+                if (inflight == DEPTH || (inflight > 0 && launched == 0)) {
                     if (nsb_engine_step_end(e) < 0) { fail("nsb_engine_step_end"); break; }
                     --inflight;
                     if (!pop_all()) break;

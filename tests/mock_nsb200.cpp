@@ -53,7 +53,7 @@ int nsb_stream_push_pcm(nsb_engine* e, int s, const int16_t* pcm, int n) {
     return NSB_OK;
 }
 int nsb_engine_step_begin(nsb_engine* e) {
-    if (e->inflight.size() == 2) return fail(NSB_ERR_STATE, "step_begin: two steps are already in flight");
+    if (e->inflight.size() == 3) return fail(NSB_ERR_STATE, "step_begin: three steps are already in flight");
     std::vector<std::pair<int, int>> batch;
     std::vector<int16_t> row((size_t)nsb::hs_row_len(e->T));
     for (int s = 0; s < e->max_streams; ++s)

@@ -454,6 +454,35 @@ def test_many_streams_batch_invariance(built):
     eng.close(); solo.close()
 
 
+def test_maximum_batch_1024_streams_in_one_engine(built):
+    """The largest batch one engine takes (the decode kernel's stream table holds 1024): 1024 streams x 80 ms chunks per step, bf16,
+    graph on -- BASELINE.json config 4's whole population on one GPU. The streams carry 8 distinct recordings: rows with the same
+    recording must produce the same tokens bit for bit (batch invariance up to the largest grid sizes), the first 8 rows must match the
+    checker up to its near-ties, and a 1025th stream is refused."""
+    import nsb200
+    R, n = 0, 1024
+    path = synth.cached_model("f16", 2, R=R)
+    base = [synth.synth_pcm(300 + s, 1.0) for s in range(8)]
+    L = min(len(b) for b in base)
+    eng = nsb200.Engine(path, right_context=R, max_streams=n, compute=nsb200.COMPUTE_BF16, kv_dtype=nsb200.KV_BF16, cuda_graph=True)
+    ids = np.array([eng.open_stream() for _ in range(n)], dtype=np.int32)
+    with pytest.raises(nsb200.NsbError):
+        eng.open_stream()
+    eng.push_batch(ids, np.stack([base[s % 8][:L] for s in range(n)]))
+    assert eng.drain() > 0
+    toks = [eng.pop_tokens(int(i)) for i in ids]
+    assert sum(len(t) for t in toks[:8]) > 20
+    for s in range(8, n):
+        assert np.array_equal(toks[s], toks[s % 8]), s
+    om = O.Model(path, O.MM_BF16, O.KV_BF16)
+    orc = []
+    for s in range(8):
+        o = O.Stream(om, R, trace=True); o.push(base[s][:L]); orc.append(o)
+        assert eng.chunks(int(ids[s])) == o.chunks
+    assert_tokens_match_up_to_near_ties(toks[:8], orc, 2e-1)
+    eng.close()
+
+
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "nemotron-asr-dropin")), reason="drop-in CLI not prebuilt")
 def test_reference_cli_dropin_end_to_end(built, tmp_path):
     """The reference's own src/transcribe_stream.cpp (byte-identical, compiled against include/) driving the engine:
@@ -540,10 +569,12 @@ def test_split_step_overlapping_the_next_push_equals_plain_step(built):
 
 
 @pytest.mark.gpu
-def test_two_steps_in_flight_equal_plain_steps(built):
-    """begin, begin, end, begin, end, ...: step i+1 is staged and enqueued while step i runs (double-buffered host side);
-    tokens, their order and the chunk counts equal the one-step-at-a-time run; a third begin is an error; ready() counts
-    launched chunks, chunks() collected ones; reset while two steps are in flight collects them first."""
+@pytest.mark.parametrize("depth", [2, 3])
+def test_steps_in_flight_equal_plain_steps(built, depth):
+    """begin, begin, [begin,] end, begin, end, ...: steps i+1 (and i+2) are staged and enqueued while step i runs (the host side of a
+    step and the device-side hand-over buffers are rings of three); tokens, their order and the chunk counts equal the
+    one-step-at-a-time run; a fourth begin is an error; ready() counts launched chunks, chunks() collected ones; reset while steps
+    are in flight collects them first."""
     import nsb200
     R = 1
     path = synth.cached_model("f32", 2, R=R)
@@ -562,26 +593,34 @@ def test_two_steps_in_flight_equal_plain_steps(built):
         toks, cnt = b.pop_tokens_batch(ids2, 64)
         for s in range(4):
             got[s] += toks[s, :cnt[s]].tolist()
-    assert b.step_begin() == 4
-    assert b.chunks(ids2[0]) == 0                                        # launched, not collected
-    n_launched = 1
+    n_launched = inflight = 0
+    exhausted = False
     while True:
-        n = b.step_begin()                                               # second step in flight
-        if n:
-            n_launched += 1
+        while not exhausted and inflight < depth:
+            n = b.step_begin()
+            if n == 0:
+                exhausted = True
+                break
+            assert n == 4
+            n_launched += 1; inflight += 1
+            if n_launched == 1:
+                assert b.chunks(ids2[0]) == 0                            # launched, not collected
+        if inflight == 3 and not exhausted:
             with pytest.raises(nsb200.NsbError):
-                b.step_begin()                                           # at most two
-        assert b.step_end() == 4                                         # the OLDEST one
-        collect()
-        if n == 0:
+                b.step_begin()                                           # at most three
+        if inflight == 0:
             break
+        assert b.step_end() == 4                                         # the OLDEST one
+        inflight -= 1
+        collect()
     assert b.step_end() == 0
     for s in range(4):
         assert got[s] == ref[s].tolist(), s
         assert b.chunks(ids2[s]) == a.chunks(ids[s]) == n_launched
     # reset with steps in flight: collected first, then the slot starts over
     b.reset_stream(ids2[0]); b.push(ids2[0], audio[0])
-    assert b.step_begin() == 1 and b.step_begin() == 1
+    for _ in range(depth):
+        assert b.step_begin() == 1
     b.reset_stream(ids2[0])
     assert b.chunks(ids2[0]) == 0 and b.step_end() == 0
     b.push(ids2[0], audio[0]); b.drain()

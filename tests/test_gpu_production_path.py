@@ -38,9 +38,9 @@ def report(**kw):
         pass
 
 
-def run_two_in_flight(eng, audio):
-    """bench.py's e2e loop: feed one chunk shift per stream per tick, begin step i+1 while step i runs, collect the OLDEST step.
-    Returns per-stream token lists; the engine is left with the last step's encoder output in its workspace ("x" tap)."""
+def run_two_in_flight(eng, audio, depth=2):
+    """bench.py's e2e loop: feed one chunk shift per stream per tick, begin steps i+1 (.. i+depth-1) while step i runs, collect the
+    OLDEST step. Returns per-stream token lists; the engine is left with the last step's encoder output in its workspace ("x" tap)."""
     n = audio.shape[0]
     ids = np.array([eng.open_stream() for _ in range(n)], dtype=np.int32)
     T = eng.T
@@ -59,17 +59,23 @@ def run_two_in_flight(eng, audio):
             got[s] += toks[s, :cnt[s]].tolist()
 
     feed(first)
-    steps = 0
-    assert eng.step_begin() == n
+    steps = inflight = 0
+    exhausted = False
     while True:
-        feed(shift)
-        nb = eng.step_begin()                                  # second step in flight (0 once the audio is exhausted)
-        assert nb in (0, n)
+        while not exhausted and inflight < depth:
+            nb = eng.step_begin()                              # 0 once the audio is exhausted
+            assert nb in (0, n)
+            if nb == 0:
+                exhausted = True
+                break
+            inflight += 1
+            feed(shift)                                        # the next chunk arrives while the device works
+        if inflight == 0:
+            break
         assert eng.step_end() == n                             # the OLDEST one
+        inflight -= 1
         steps += 1
         collect()
-        if nb == 0:
-            break
     assert eng.step_end() == 0
     return ids, got, steps
 
@@ -269,8 +275,8 @@ def test_graph_replay_equals_direct_launches_equals_tapped_run(built):
 
 def test_decode_overlap_gives_the_same_tokens_as_inline_decode(built):
     """Decode overlap (the decode of step i on its own stream and 16 CTAs, under the encoder of step i + 1; automatic at <= 128 token
-    rows = the bench's config 2 / 4) against the inline full-width decode: identical tokens and identical encoder output, with two
-    steps in flight and with single steps, bf16, 24 layers, 64 streams."""
+    rows = the bench's config 2 / 4) against the inline full-width decode: identical tokens and identical encoder output, with two /
+    three steps in flight and with single steps, bf16, 24 layers, 64 streams."""
     import nsb200
     R, T, n, chunks = 1, 2, 64, 12
     path = synth.cached_model("f16", 24, R=R)
@@ -279,9 +285,9 @@ def test_decode_overlap_gives_the_same_tokens_as_inline_decode(built):
     L = min(len(b) for b in base)
     audio = np.stack([np.roll(base[s % 8][:L], 173 * (s // 8)) for s in range(n)])
     res = []
-    for ov in (2, 1):
+    for ov, depth in ((2, 2), (1, 3)):                       # inline decode with two steps in flight; overlapped decode with three
         eng = nsb200.Engine(path, right_context=R, max_streams=n, compute=nsb200.COMPUTE_BF16, kv_dtype=nsb200.KV_BF16, decode_overlap=ov)
-        _, got, steps = run_two_in_flight(eng, audio)
+        _, got, steps = run_two_in_flight(eng, audio, depth)
         x = eng.debug_get("x", n)
         for s in range(n):
             eng.reset_stream(s)
