@@ -411,6 +411,97 @@ def test_api_edge_cases(built):
     eng.close()
 
 
+@pytest.mark.parametrize("seed,R", [(11, 1), (12, 0), (13, 6)])
+def test_randomised_serving_schedule_matches_per_session_oracle(built, seed, R):
+    """A randomised serving schedule over 5 stream slots: pushes of random size (1 sample .. 2.5 chunks, now and then nothing), plain
+    steps and split steps with up to three in flight, streams that end (close -> the slot is reused by a new session), streams reset
+    in mid-utterance, slots that stay idle for a while -- so the batch composition, the batch size and every slot's cache fill level
+    change from step to step. Strict fp32: every SESSION's tokens must equal the checker's run over exactly the audio that session
+    pushed since its open / reset, and the chunk counts must agree (reference: the per-stream driver, src/nemo-stream.cpp:1079-1127,
+    one nemo_stream_context per session)."""
+    import nsb200
+    rng = np.random.default_rng(seed)
+    T = 1 + R
+    path = synth.cached_model("f32", 2, R=R)
+    eng = nsb200.Engine(path, right_context=R, max_streams=5, compute=nsb200.COMPUTE_F32, cuda_graph=True)
+    om = O.Model(path)
+    shift = eng.shift_samples
+    pool = [synth.synth_pcm(400 + 10 * seed + k, 4.0 + 0.7 * k) for k in range(6)]
+    sessions = {}                                            # slot -> dict(audio=recording, pos, pushed=list of arrays, toks=list)
+    finished = []                                            # (pushed audio, tokens, chunks)
+    inflight = 0
+
+    def open_session():
+        nonlocal inflight
+        slot = eng.open_stream()                             # collects the steps in flight first (nsb200.h)
+        inflight = 0
+        sessions[slot] = dict(audio=pool[int(rng.integers(len(pool)))], pos=0, pushed=[], toks=[])
+
+    def harvest(slot):
+        sessions[slot]["toks"] += eng.pop_tokens(slot).tolist()
+
+    def finish(slot, close):
+        nonlocal inflight
+        ses = sessions[slot]
+        # close / reset collect the steps in flight first (nsb200.h); ready chunks that were never launched are dropped with the session,
+        # so run them now: the checker sees everything that was pushed
+        while inflight:
+            eng.step_end(); inflight -= 1
+        while eng.ready(slot):
+            eng.step()
+        harvest(slot)
+        finished.append((np.concatenate(ses["pushed"]) if ses["pushed"] else np.zeros(0, np.int16), ses["toks"], eng.chunks(slot)))
+        if close:
+            eng.close_stream(slot); del sessions[slot]
+        else:
+            eng.reset_stream(slot); sessions[slot] = dict(audio=pool[int(rng.integers(len(pool)))], pos=0, pushed=[], toks=[])
+
+    for _ in range(3):
+        open_session()
+    for tick in range(140):
+        for slot in list(sessions):
+            ses = sessions[slot]
+            u = rng.random()
+            if ses["pos"] >= len(ses["audio"]):
+                finish(slot, close=True)
+                continue
+            if u < 0.03:
+                finish(slot, close=False)                    # reset in mid-utterance
+                continue
+            if u < 0.15:
+                continue                                     # this stream is idle for a tick
+            n = int(rng.choice([1, 17, shift // 3, shift, int(2.5 * shift)]))
+            piece = ses["audio"][ses["pos"]:ses["pos"] + n]
+            eng.push(slot, piece); ses["pushed"].append(piece); ses["pos"] += len(piece)
+        if len(sessions) < 5 and rng.random() < 0.2:
+            open_session()
+        mode = rng.random()
+        if mode < 0.4:
+            while inflight:
+                assert eng.step_end() > 0; inflight -= 1
+            eng.step()
+        else:
+            while inflight < 3 and eng.step_begin() > 0:
+                inflight += 1
+            if inflight and rng.random() < 0.7:
+                assert eng.step_end() > 0; inflight -= 1
+        for slot in sessions:
+            harvest(slot)
+    for slot in list(sessions):
+        finish(slot, close=True)
+    assert len(finished) >= 6
+    n_tok = 0
+    for pushed, toks, chunks in finished:
+        o = O.Stream(om, R)
+        if len(pushed):
+            o.push(pushed)
+        assert chunks == o.chunks, (chunks, o.chunks)
+        assert toks == o.tokens().tolist()
+        n_tok += len(toks)
+    assert n_tok > 50
+    eng.close()
+
+
 def test_loader_rejects_mis_shaped_and_mis_typed_matrices_by_name(built, tmp_path):
     """Tensor-type / shape validation of the per-layer matrices (the reference's loader checks presence only, nemo-ggml.cpp:362-384):
     a [4096, 1024] matrix stored as [1024, 4096], and a matrix of an unsupported ggml type, are refused with the tensor's name."""
