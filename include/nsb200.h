@@ -32,7 +32,7 @@ extern "C" {
 /* arithmetic the per-layer weight GEMMs run in (what ggml picks from the tensor type,
  * src/nemo-ggml.cpp:187-191 "quantized tensors stay quantized, ggml_mul_mat handles dequant") */
 enum nsb_compute {
-    NSB_COMPUTE_AUTO = 0, /* from the GGUF tensor type: F32 -> F32, F16 -> F16, Q8_0 -> Q8_0 fused dequant */
+    NSB_COMPUTE_AUTO = 0, /* from the GGUF tensor type: F32 -> F32, F16 -> F16, Q8_0 / Q4_0 -> quantised in HBM, fp16 tensor-core GEMMs */
     NSB_COMPUTE_F32 = 1,  /* SIMT fp32 GEMM (strict parity with the f32 reference path)                   */
     NSB_COMPUTE_F16 = 2,  /* tcgen05 kind::f16, fp16 operands, fp32 TMEM accumulate                       */
     NSB_COMPUTE_BF16 = 3, /* tcgen05 kind::f16, bf16 operands, fp32 TMEM accumulate                       */

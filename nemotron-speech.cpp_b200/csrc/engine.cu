@@ -443,6 +443,7 @@ void Engine::load_weights(const GgufFile& g) {
     }
 }
 
+int q8_dense_min_rows();
 void Engine::alloc_state() {
     const int S = max_streams, Cap = ATT_L + T, M = PRE_CACHE + 8 * T;
     const int t1 = M / 2 + 1, t2 = t1 / 2 + 1, t3 = t2 / 2 + 1;
@@ -476,7 +477,7 @@ void Engine::alloc_state() {
     const size_t planes = Mrows <= SPLIT_CONSUMER_MAX_ROWS ? 4 : 1;
     consumer_planes_ = (int)planes;
     if (compute == NSB_COMPUTE_Q8_0) wscratch_.alloc((size_t)D_FF * D_MODEL * 2, false);   // largest layer matrix as fp16 (q8_predequant: op_gemm / bench_gemm)
-    if (compute == NSB_COMPUTE_Q8_0 && Mrows >= 512) {                                     // layer-ahead fp16 shadows (see engine.h)
+    if (compute == NSB_COMPUTE_Q8_0 && (int)Mrows >= q8_dense_min_rows()) {                // layer-ahead fp16 shadows (see engine.h)
         const size_t sz[8] = {(size_t)D_FF * D_MODEL, (size_t)D_MODEL * D_FF, (size_t)3 * D_MODEL * D_MODEL, (size_t)D_MODEL * D_MODEL,
                               (size_t)2 * D_MODEL * D_MODEL, (size_t)D_MODEL * D_MODEL, (size_t)D_FF * D_MODEL, (size_t)D_MODEL * D_FF};
         size_t off = 0; for (int k = 0; k < 8; ++k) { shadow_off_[k] = off; off += sz[k] * 2; }
@@ -588,8 +589,17 @@ void Engine::gemm_f32w(GemmArgs& g, const Weight& W, bool a_presplit) {
 
 // Q8_0 mode, batches of >= 4 row tiles: dequantise the matrix once into an fp16 scratch (L2-resident hand-over to the GEMM that
 // follows) instead of once per m-tile inside the fused kernel. Small batches keep the fused operand path (weight streaming).
+// token rows per step from which Q8_0 / Q4_0 matrices are expanded to fp16 before the GEMMs (layer-ahead shadows in the step, a scratch
+// per launch for single operator calls) instead of inside every m-tile CTA of the fused kernel. Default 1 = always: measured per step,
+// shadows vs fused, 1 stream x 160 ms 2.05 vs 2.30 ms, 64 streams 2.38 vs 2.49, 128 streams 3.18 vs 3.55, 24 streams x 1.12 s 3.3 vs 4.7,
+// 64 streams x 560 ms 3.74 vs 4.35 (profiles/r02_notes.md): the expansion runs on its own stream under the previous layer and the GEMMs
+// then are the fp16 ones. NSB_Q8_PREDEQUANT_ROWS=<rows> brings the fused operand path back below that many rows (no shadows: 122 MB less).
+int q8_dense_min_rows() {
+    const char* e = getenv("NSB_Q8_PREDEQUANT_ROWS");          // read per call (engine creation, graph capture): a test can switch it between engines
+    return e ? atoi(e) : 1;
+}
 void Engine::q8_predequant(const Weight& W, int M, GemmArgs& a) {
-    static const int min_rows = [] { const char* e = getenv("NSB_Q8_PREDEQUANT_ROWS"); return e ? atoi(e) : 512; }();
+    const int min_rows = q8_dense_min_rows();
     if (compute != NSB_COMPUTE_Q8_0 || !W.scales.p || M < min_rows) return;
     if (q8_pair256_enabled()) return;                              // large batches: the dequantisation is fused into the CTA-pair tiles (gemm_q8_pair256_kernel)
     const size_t bytes = (size_t)W.n_out * W.n_in * 2;
@@ -601,7 +611,7 @@ void Engine::q8_predequant(const Weight& W, int M, GemmArgs& a) {
 
 bool Engine::shadow_mode(int rows) const {
     static const bool off = [] { const char* e = getenv("NSB_Q8_SHADOW"); return e && e[0] == '0'; }();
-    static const int min_rows = [] { const char* e = getenv("NSB_Q8_PREDEQUANT_ROWS"); return e ? atoi(e) : 512; }();
+    const int min_rows = q8_dense_min_rows();
     return !off && !q8_pair256_enabled() && compute == NSB_COMPUTE_Q8_0 && shadow_bytes_ && rows >= min_rows && !profiling_;
 }
 // all 8 matrices of layer l -> fp16 in shadow_[l % 2], on stream s (same fp16(d) * q values as the fused operand path)

@@ -133,9 +133,12 @@ def test_logmel_kernel_parity(built):
     eng.close()
 
 
-@pytest.mark.parametrize("wtype,compute,mm", [("f32", 2, O.MM_F16), ("f32", 3, O.MM_BF16), ("q8_0", 0, O.MM_Q8FAST), ("q4_0", 0, O.MM_Q8FAST)])
-def test_tcgen05_gemm_parity(built, wtype, compute, mm):
+@pytest.mark.parametrize("wtype,compute,mm,fused", [("f32", 2, O.MM_F16, 0), ("f32", 3, O.MM_BF16, 0), ("q8_0", 0, O.MM_Q8FAST, 0), ("q4_0", 0, O.MM_Q8FAST, 0),
+                                                     ("q8_0", 0, O.MM_Q8FAST, 1), ("q4_0", 0, O.MM_Q8FAST, 1)])
+def test_tcgen05_gemm_parity(built, wtype, compute, mm, fused, monkeypatch):
     import nsb200
+    if fused:                                      # the fused-dequantisation kernels (gemm_q8_kernel), otherwise behind the fp16 expansion
+        monkeypatch.setenv("NSB_Q8_PREDEQUANT_ROWS", "100000")
     path = synth.cached_model(wtype, 2, R=0)
     eng = nsb200.Engine(path, right_context=0, max_streams=1, compute=compute)
     om = O.Model(path, mm)
@@ -264,6 +267,25 @@ def test_streaming_parity_16bit_and_q8(built, wtype, compute, kv, mm, okv, tol, 
     assert worst < tol, worst
     identical = assert_tokens_match_up_to_near_ties(toks, orc, band)
     assert identical >= 2, identical
+    eng.close()
+
+
+@pytest.mark.parametrize("wtype", ["q8_0", "q4_0"])
+def test_streaming_parity_quantised_fused_operand_path(built, wtype, monkeypatch):
+    """The fused-dequantisation GEMM kernels inside the step (gemm_q8_kernel: raw quants by TMA, dequantiser warps, tcgen05) -- since the
+    layer-ahead fp16 shadows became the default at every batch size they run only on request (NSB_Q8_PREDEQUANT_ROWS above the batch's
+    rows): same operand values, so the same tolerances as the default path."""
+    import nsb200
+    monkeypatch.setenv("NSB_Q8_PREDEQUANT_ROWS", "100000")
+    R = 1
+    path = synth.cached_model(wtype, 2, R=R)
+    eng = nsb200.Engine(path, right_context=R, max_streams=4, compute=0, kv_dtype=0)
+    eng.debug_enable(True)
+    om = O.Model(path, O.MM_Q8FAST, O.KV_F32)
+    audio = [synth.synth_pcm(20 + s, 2.0 + 0.3 * s) for s in range(4)]
+    toks, orc, worst, _ = run_engine_vs_oracle(eng, om, R, audio)
+    assert worst < 3e-3, worst
+    assert assert_tokens_match_up_to_near_ties(toks, orc, 2e-2) >= 2
     eng.close()
 
 
