@@ -53,7 +53,7 @@ typedef struct nsb_engine_config {
     int32_t max_streams;       /* stream slots resident on this GPU                                    */
     int32_t use_cuda_graph;    /* capture the per-step launch sequence per batch size                  */
     int32_t decode_overlap;    /* RNN-T decode of step i on its own stream, on a few SMs, under the encoder of step i+1:
-                                  0 = automatic (steps of <= 128 token rows that are begun while another step is in flight),
+                                  0 = automatic (steps of <= 512 token rows that are begun while another step is in flight),
                                   1 = always, 2 = never. Same tokens either way */
     int32_t reserved[5];
 } nsb_engine_config;

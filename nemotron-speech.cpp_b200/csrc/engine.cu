@@ -785,15 +785,18 @@ static unsigned skip_mask() {
 enum { SK_LN = 1, SK_ATTN = 2, SK_CONV = 4, SK_DECODE = 8, SK_FF = 16, SK_QKV = 32, SK_OUT = 64, SK_PW = 128, SK_SUB = 256, SK_MEL = 512 };
 
 // Decode overlap (nsb_engine_config::decode_overlap: 0 automatic, 1 always, 2 never; NSB_DECODE_OVERLAP=0/1 overrides): for batches of
-// <= 128 token rows, where every encoder kernel launches <= 128 CTAs on the 148 SMs and the decode's per-symbol rounds are latency-
-// bound. Automatic = only for steps that are part of a pipeline (a step begun while another is in flight, back-to-back bench steps):
+// <= 512 token rows (NSB_DECODE_OVERLAP_ROWS). Up to 128 rows every encoder kernel launches <= 128 CTAs on the 148 SMs, so the 20 CTAs of
+// the narrow decode cost the encoder nothing; up to ~512 rows the encoder loses less to them than the decode's latency-bound rounds
+// take inline (measured per step: 224 rows 2.95 -> 2.57 ms, 448 rows 3.73 -> 3.28; at 896 rows 5.08 -> 5.84 and at 1792 rows 6.80 -> 8.78:
+// off there). Automatic = only for steps that are part of a pipeline (a step begun while another is in flight, back-to-back bench steps):
 // the narrow decode takes ~2x longer than the full-width one, which only pays when it hides under the next step's encoder. Off while
 // taps / per-launch profiling are on (they read decode-side buffers behind a sync of st_ only) and in the strict modes.
 bool Engine::overlap_decode(int rows, bool pipelined) const {
     static const int env = [] { const char* e = getenv("NSB_DECODE_OVERLAP"); return e ? atoi(e) : -1; }();
     const int mode = env == 0 ? 2 : env == 1 ? 1 : cfg_.decode_overlap;
     if (debug_ || profiling_ || strict() || mode == 2) return false;
-    return mode == 1 || (rows <= 128 && pipelined);
+    static const int max_rows = [] { const char* e = getenv("NSB_DECODE_OVERLAP_ROWS"); return e ? atoi(e) : 512; }();
+    return mode == 1 || (rows <= max_rows && pipelined);
 }
 
 void Engine::join_decode_stream() {

@@ -138,6 +138,8 @@ OTHER_CONFIGS = [
     ("config3_q8_0_256x560ms", 6, 256, 13, "q8_0", 0, 1, O.MM_Q8FAST, O.KV_F16, 1e-3, 2e-3, 1e-2),
     ("config4_bf16_128x80ms", 0, 128, 75, "f16", 3, 2, O.MM_BF16, O.KV_BF16, 1e-2, 2e-2, 2e-2),
     ("config5_bf16_64x1120ms", 13, 64, 7, "f16", 3, 2, O.MM_BF16, O.KV_BF16, 1e-2, 2e-2, 2e-2),
+    # one rank's share of config 3 strong-scaled over 4 GPUs: 448 token rows -- 16-bit GEMMs on single-CTA tiles, decode overlapped (narrow grid, T = 7)
+    ("config3_share_of_4_q8_0_64x560ms", 6, 64, 13, "q8_0", 0, 1, O.MM_Q8FAST, O.KV_F16, 1e-3, 2e-3, 1e-2),
     # Q4_0 weights (scripts/convert_to_gguf.py:132-179) through the same fused-dequantisation kernels, at config 2's shape and at config 3's
     ("config2_q4_0_64x160ms", 1, 64, 46, "q4_0", 0, 1, O.MM_Q8FAST, O.KV_F16, 1e-3, 2e-3, 1e-2),
     ("config3_q4_0_256x560ms", 6, 256, 13, "q4_0", 0, 1, O.MM_Q8FAST, O.KV_F16, 1e-3, 2e-3, 1e-2),
