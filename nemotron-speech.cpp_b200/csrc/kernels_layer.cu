@@ -1399,9 +1399,14 @@ __global__ void __launch_bounds__(256, 2) conv_module_kernel(const ConvModArgs a
 }
 void launch_conv_module(const ConvModArgs& a, cudaStream_t st) {
     static const int tb_env = [] { const char* e = getenv("NSB_CONV_TB"); return e ? atoi(e) : 0; }();
-    // one block (nothing recomputed) up to 8 frames; two blocks at T = 14 (measured within 1 % of each other and of TB = 4 / 14 on the
-    // 64-stream step); 8-frame blocks beyond that (the batch path: hundreds of independent CTAs instead of one sequential walk)
-    const int TB = min(CONV_TB, tb_env > 0 ? tb_env : (a.T <= 8 ? a.T : a.T <= 16 ? (a.T + 1) / 2 : 8));
+    // Frames per block: a block primes its window with 8 recomputed rows, so few blocks are cheapest in work, but the kernel is bound by
+    // its load -> GLU -> conv -> reduce chain, not by work: aim for ~256 CTAs, never less than 2 frames per block. Measured per step:
+    // 32 streams x 7 frames 2.57 (one block) -> 2.46 ms (blocks of 2), 64 x 7 3.29 -> 3.21 (blocks of 3), 64 x 14 5.09 (blocks of 7) ->
+    // 5.01 (blocks of 4); 256 x 7 stays one block per stream (6.98 vs 7.14 ms with two), the batch path (one stream x ~2000 frames) 8-frame blocks.
+    int blocks = std::max(1, std::min((256 + a.B - 1) / std::max(a.B, 1), (a.T + 1) / 2));
+    int TB = (a.T + blocks - 1) / blocks;
+    if (tb_env > 0) TB = tb_env;
+    TB = std::max(1, std::min(TB, CONV_TB));
     if (a.B > 0 && a.T > 0) launch_k(conv_module_kernel, dim3((a.T + TB - 1) / TB, a.B), dim3(256), 0, st, a, TB);
 }
 
