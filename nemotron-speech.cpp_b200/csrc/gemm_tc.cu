@@ -1282,7 +1282,8 @@ int pick_pair256_bn(int M, int N) {
     // short of tiles (returns 0: the single-CTA tiles win there).
     const int tiles_m = (M + 2 * BM - 1) / (2 * BM);
     auto tiles = [&](int bn) { return (long long)tiles_m * ((N + bn - 1) / bn); };
-    if (tiles(112) < 100) return 0;
+    static const int min_pairs = [] { const char* e = getenv("NSB_PAIR256_MIN_PAIRS"); return e ? atoi(e) : 100; }();
+    if (tiles(112) < min_pairs) return 0;
     for (int bn : {112, 160, 208, 256}) if (tiles(bn) <= 148) return bn;
     int best = 256; long long best_cost = 0;
     for (int bn : {256, 208, 160, 112}) {
