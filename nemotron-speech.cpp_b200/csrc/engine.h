@@ -155,9 +155,11 @@ private:
     static constexpr int MAX_INFLIGHT = 3;   // steps between step_begin and step_end: host-side step state and the device-side hand-over buffers are rings of this depth
     Side side_[MAX_INFLIGHT]; int side_next_ = 0;
     cudaStream_t st_dec_ = nullptr;
+    cudaStream_t st_copy_ = nullptr;   // host -> device upload of a step's PCM rows: not on the engine stream, where it would sit between two steps' kernels
     struct StepIO {                   // host side of one step in flight
         HostPinned h_pcm, h_slot, h_tok, h_cnt;
-        cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
+        DevBuf d_pcm;                 // this step's PCM rows in HBM (uploaded on the copy stream while earlier steps compute)
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr, h2d = nullptr;
         std::vector<int> batch;       // batch row -> stream slot
     };
     StepIO io_[MAX_INFLIGHT]; int io_next_ = 0, n_inflight_ = 0;
@@ -196,7 +198,7 @@ private:
 
     // ---- step workspace (batch-compact) ----
     int rl_ = 0;                   // PCM row length per stream-step
-    DevBuf d_pcm_, d_slot_, mel_new_, dw_, pw_, a3_, x_, a_, big_, qkv_, pw1_, encp_, part_;
+    DevBuf d_slot_, mel_new_, dw_, pw_, a3_, x_, a_, big_, qkv_, pw1_, encp_, part_;
     DevBuf out_tok_, out_cnt_, dec_sync_;
     // workspace of the non-streaming batch path (swapped in for the duration of transcribe_full)
     struct BatchWork { DevBuf dw, pw, a3, x, a, big, qkv, pw1, encp, part, out_tok, out_frm; int rows = 0; } bw_;
