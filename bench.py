@@ -64,6 +64,12 @@ if "NSB_BENCH_R" in os.environ:
     CONFIGS[2]["R"] = int(os.environ["NSB_BENCH_R"])
 
 
+def stream_recording(g: int) -> int:
+    """Which of the 8 synthetic recordings global stream g carries (shifted by 977 (g // 8) samples). Must not be a function of g mod G
+    alone for any G the streams are sharded over (sharding.py: stream -> rank g mod G), or a rank's whole batch is one recording."""
+    return (g + g // 8) % 8
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -282,7 +288,7 @@ def run_config(no: int, args, ctx, headline: bool):
     # distinct streams from 8 seeds, keyed by GLOBAL stream id g: recording (g + g // 8) % 8 rolled by 977 (g // 8) samples. (g % 8 alone
     # would hand every stream of a rank the SAME recording under s mod G sharding with G = 8: the whole batch then bursts together and
     # the max over ranks reports the burstiest recording instead of the workload -- seen as 2.07 vs 1.77 ms per step at 8 vs 1 GPU.)
-    pcm = np.stack([np.roll(base[(g + g // 8) % 8], 977 * (g // 8)) for g in mine])
+    pcm = np.stack([np.roll(base[stream_recording(g)], 977 * (g // 8)) for g in mine])
     eng.bench_prepare(pcm, warm_chunks)
 
     def sync_all():

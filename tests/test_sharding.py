@@ -71,3 +71,26 @@ def test_two_rank_gloo_gather_equals_single_process(built):
     single = _decode(list(range(5)))
     assert merged == single
     assert sum(len(v) for v in single.values()) > 0
+
+
+def test_bench_workload_mixes_recordings_on_every_rank():
+    """bench.py builds its streams from 8 synthetic recordings keyed by the GLOBAL stream id; under `stream s -> rank s mod G` every rank of
+    a 1 / 2 / 4 / 8-GPU run must still see all 8 recordings in equal shares (an 8-GPU run once gave every stream of a rank the same
+    recording: whole batches burst together and the max over ranks measured the burstiest recording, not the workload)."""
+    import collections
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from nemotron_speech_cpp_b200 import sharding
+    for world in (1, 2, 4, 8):
+        for per_gpu in (64, 128):
+            total = per_gpu * world
+            for rank in range(world):
+                mine = sharding.local_streams(range(total), rank, world)
+                assert len(mine) == per_gpu
+                cnt = collections.Counter(bench.stream_recording(g) for g in mine)
+                assert len(cnt) == 8 and max(cnt.values()) == min(cnt.values()), (world, rank, cnt)
+                pairs = {(bench.stream_recording(g), g // 8) for g in mine}
+                assert len(pairs) == per_gpu                      # no two streams of a rank are the same (recording, shift)
