@@ -1333,10 +1333,11 @@ long long Engine::op_logmel(const int16_t* pcm, int n_streams, int n_samples, fl
 }
 
 // ------------------------------------------------------------------------------------------
-// Non-streaming batch path. EXPERIMENTAL: written after this round's GPU budget was spent -- compiled, checked against
-// nothing on hardware yet (the checker exists: orc_transcribe_full + tests/golden/batch_ref_L2.npz). Everything except the full-
-// context attention kernel and the un-chunked stem variant is the streaming step's own kernels: a non-cached conformer layer is the
-// cached one with an empty cache (zeroed conv state = the causal pad of nemo-ggml.cpp:706-707).
+// Non-streaming batch path, validated on hardware against the checker (orc_transcribe_full) and the fixture made by the
+// reference's own compiled modules (tests/golden/batch_ref_L2.npz; tests/test_zz_batch_path.py: 2 layers and 24 layers x 30 s). Everything
+// except the full-context attention kernel and the un-chunked stem variant is the streaming step's own kernels: a non-cached conformer
+// layer is the cached one with an empty cache (zeroed conv state = the causal pad of nemo-ggml.cpp:706-707). Private workspace and a
+// private state slot: open streams are not disturbed.
 // ------------------------------------------------------------------------------------------
 void Engine::ensure_full_pos(int frames) {
     if (frames <= full_pos_cap_) return;

@@ -1426,8 +1426,8 @@ void launch_advance_streams(const int* slot_of_b, int B, int T, int* ring_pos, i
 
 // ------------------------------------------------------------------------------------------
 // Full-context rel-pos attention of the non-streaming batch path (build_rel_pos_mha + build_rel_shift, nemo-ggml.cpp:548-680).
-// EXPERIMENTAL: written after this round's GPU budget was spent, not yet validated on hardware; correctness-
-// first SIMT. One warp = one (head, query row i), lane l owns head dims 4l .. 4l+3.
+// Correctness-first SIMT (validated on hardware, tests/test_zz_batch_path.py; the path is bound by the single-stream greedy decode, not by
+// this kernel: DESIGN.md section 1). One warp = one (head, query row i), lane l owns head dims 4l .. 4l+3.
 //   pass 1: S[j] = ((q_i + u).k_j + (q_i + v).P[i - j]) / sqrt(128) for all T keys into shared memory -- the pad / reshape / drop
 //           rel-shift is index arithmetic: BD[i, j] = BD_raw[i, j + T - 1 - i] <-> relative position i - j;
 //   pass 2: softmax over the row (max-subtract, expf, sum), as ggml_soft_max;
